@@ -1,0 +1,191 @@
+/*
+ * ospo_head.h -- C ABI of the B200-native (sm_100a) Janus-Pro image-token head.
+ *
+ * This is the drop-in boundary for OSPO's one data-parallel hot path.  The reference has no FFI for
+ * it (pure Python); the entry points below are what a binding for that path attaches to, each citing
+ * the reference lines it replaces (paths relative to the OSPO repository root):
+ *
+ *   ospo_head_logits          janus/models/modeling_vlm.py:47-51   vision_head.forward
+ *   ospo_head_logps_fwd/_bwd  ospo/wrapper/train.py:357 + 375-396  gen_head + get_batch_logps (+ autograd)
+ *   ospo_head_simpo_fwd/_bwd  ospo/wrapper/train.py:317-342, 345-372, 399-445  SimPO loss fwd + bwd
+ *   ospo_head_cfg_sample      ospo/wrapper/image_generation.py:156-164 (== ospo/inference.py:147-155)
+ *   ospo_head_cfg_merge_sample   the merge/softmax/sample tail of the same lines, on supplied logits
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory,
+ *     including the workspace; the library never allocates or frees device memory.
+ *   - All work is enqueued asynchronously on `stream`; no call synchronises.
+ *   - Weights use the nn.Linear layout [out, in], row-major, bf16.  Biases are fp32.
+ *   - x / hidden states: bf16 [rows, hidden] row-major contiguous, one row per image token whose label
+ *     is not masked (the caller drops the label == -100 rows: they carry no work and no gradient).
+ *   - Return value 0 = success, negative = ospo_head_status; no exception crosses this boundary.
+ *   - Requires an sm_100a device: there is no fallback path.
+ */
+#ifndef OSPO_HEAD_H_
+#define OSPO_HEAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* ospo_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define OSPO_API __attribute__((visibility("default")))
+#else
+#define OSPO_API
+#endif
+
+typedef enum {
+  OSPO_OK = 0,
+  OSPO_ERR_BAD_SHAPE = -1,      /* non-positive or unsupported dimension */
+  OSPO_ERR_ALIGNMENT = -2,      /* pointer not 16-byte aligned / dimension not a multiple of 8 */
+  OSPO_ERR_NULL = -3,           /* required pointer is NULL */
+  OSPO_ERR_WORKSPACE = -4,      /* workspace too small */
+  OSPO_ERR_ARCH = -5,           /* device is not sm_100 */
+  OSPO_ERR_TENSORMAP = -6,      /* cuTensorMapEncodeTiled failed / unavailable */
+  OSPO_ERR_LAUNCH = -7,         /* kernel launch failed */
+  OSPO_ERR_CUDA = -8,           /* other CUDA runtime error */
+  OSPO_ERR_UNSUPPORTED = -9     /* argument combination not supported */
+} ospo_head_status;
+
+typedef struct {
+  int32_t rows;     /* N: image-token rows given to the head (sum over sequences)          */
+  int32_t hidden;   /* H: n_embed                                                          */
+  int32_t embed;    /* E: image_token_embed                                                */
+  int32_t vocab;    /* V: image_token_size (16384 for the sampler)                         */
+  int32_t num_seqs; /* S: sequences (SimPO: S = 2B, chosen [0,B) then rejected [B,2B))     */
+} ospo_head_shape;
+
+typedef struct {
+  const void* w1;   /* bf16 [E, H]  output_mlp_projector.weight */
+  const float* b1;  /* fp32 [E]     output_mlp_projector.bias   */
+  const void* w2;   /* bf16 [V, E]  vision_head.weight          */
+  const float* b2;  /* fp32 [V]     vision_head.bias            */
+} ospo_head_weights;
+
+/* ---- plain logits: vision_head.forward ---------------------------------------------------- */
+typedef struct {
+  ospo_head_shape shape;       /* num_seqs ignored */
+  ospo_head_weights w;
+  const void* x;               /* bf16 [rows, H] */
+  void* logits;                /* bf16 [rows, V] out */
+  void* workspace;             /* >= ospo_head_workspace_bytes() */
+  size_t workspace_bytes;
+} ospo_head_args;
+
+/* ---- log-probs / SimPO -------------------------------------------------------------------- */
+#define OSPO_LOSS_SIGMOID 0
+#define OSPO_LOSS_HINGE 1
+
+/* indices into ospo_simpo_args.scalars (fp32[16]) */
+#define OSPO_SC_LOSS 0            /* losses.mean() + sft_weight * sft_loss          train.py:419,428 */
+#define OSPO_SC_SIMPO_LOSS 1      /* losses.mean()                                  train.py:419     */
+#define OSPO_SC_SFT_LOSS 2        /* CE over unmasked chosen rows                   train.py:425-427 */
+#define OSPO_SC_REWARD_CHOSEN 3   /* chosen_rewards.mean()                          train.py:435     */
+#define OSPO_SC_REWARD_REJECTED 4
+#define OSPO_SC_REWARD_ACC 5      /* (chosen_rewards > rejected_rewards).mean()     train.py:432     */
+#define OSPO_SC_REWARD_MARGIN 6
+#define OSPO_SC_LOGPS_CHOSEN 7
+#define OSPO_SC_LOGPS_REJECTED 8
+#define OSPO_SC_LOGITS_CHOSEN 9   /* mean logit over the unmasked chosen rows       train.py:442     */
+#define OSPO_SC_LOGITS_REJECTED 10
+#define OSPO_SC_COUNT 16
+
+typedef struct {
+  ospo_head_shape shape;
+  ospo_head_weights w;
+  const void* x;               /* bf16 [rows, H] */
+  const int64_t* labels;       /* [rows] target code of each row, in [0, V)  (labels[:,1:] after masking) */
+  const int64_t* seq_offsets;  /* [S+1] row range of each sequence: rows [off[s], off[s+1]) */
+  int32_t average_log_prob;    /* get_batch_logps(average_log_prob=...)  train.py:393-396 */
+
+  /* SimPO hyper-parameters (ignored by the logps_* entry points) */
+  float beta, gamma_beta_ratio, label_smoothing, sft_weight;
+  int32_t loss_type;           /* OSPO_LOSS_SIGMOID | OSPO_LOSS_HINGE */
+
+  /* forward outputs */
+  float* row_logps;            /* [rows] per-token log-prob of the label */
+  float* seq_logps;            /* [S]    get_batch_logps result */
+  float* losses;               /* [B]    simpo only */
+  float* chosen_rewards;       /* [B]    simpo only */
+  float* rejected_rewards;     /* [B]    simpo only */
+  float* scalars;              /* [OSPO_SC_COUNT] simpo only */
+
+  /* tensors saved by the forward for the backward (caller-allocated; may all be NULL for a
+     forward-only call, in which case nothing is spilled) */
+  void* pre;                   /* bf16 [rows, E]  pre-activation */
+  void* act;                   /* bf16 [rows, E]  required even forward-only */
+  void* logits;                /* bf16 [rows, V]  logits spill; the backward overwrites it with dlogits */
+  float* row_lse;              /* [rows] */
+  float* grad_seq;             /* [S] d loss / d seq_logps: written by simpo_fwd, read by *_bwd
+                                  (for logps_bwd the caller fills it with the upstream gradient) */
+
+  /* backward */
+  const float* grad_loss;      /* device scalar multiplying the whole gradient, NULL = 1 */
+  void* dx;                    /* bf16 [rows, H] out, NULL = skip */
+  float* flat_grads;           /* fp32 [V*E + E*H + V + E] = dW2 | dW1 | db2 | db1, NULL = head frozen */
+
+  void* workspace;
+  size_t workspace_bytes;
+} ospo_simpo_args;
+
+/* ---- CFG decode step ---------------------------------------------------------------------- */
+#define OSPO_MERGE_BF16 0  /* reference semantics: bf16 rounding after every op (image_generation.py:160-161) */
+#define OSPO_MERGE_FP32 1
+
+typedef struct {
+  ospo_head_shape shape;       /* rows = 2P (row 2k conditional, 2k+1 unconditional); vocab must be 16384 */
+  ospo_head_weights w;
+  const void* h;               /* bf16 [2P, H] last hidden state of every CFG row; NULL for merge_sample */
+  void* logits;                /* bf16 [2P, V]: written by cfg_sample, read by cfg_merge_sample */
+  float cfg_weight, temperature;
+  int32_t merge_mode;          /* OSPO_MERGE_BF16 | OSPO_MERGE_FP32 */
+  int32_t greedy;              /* 1 = argmax (lowest index on ties), uniforms ignored */
+  int32_t num_steps;           /* cfg_merge_sample only: independent steps batched in one launch
+                                  (logits [steps, 2P, V], uniforms / ids [steps, P]); 0 or 1 = one step */
+  const float* uniforms;       /* fp32 [P] in [0,1) */
+  int64_t* ids;                /* [P] out */
+  float* merged;               /* optional fp32 [P, V] dump of the merged, temperature-scaled logits */
+  void* workspace;
+  size_t workspace_bytes;
+} ospo_cfg_args;
+
+/* scratch bytes needed by any entry point for this shape */
+OSPO_API int ospo_head_workspace_bytes(const ospo_head_shape* shape, size_t* out_bytes);
+
+OSPO_API int ospo_head_logits(const ospo_head_args* args, ospo_stream_t stream);
+
+OSPO_API int ospo_head_logps_fwd(const ospo_simpo_args* args, ospo_stream_t stream);
+OSPO_API int ospo_head_logps_bwd(const ospo_simpo_args* args, ospo_stream_t stream);
+OSPO_API int ospo_head_simpo_fwd(const ospo_simpo_args* args, ospo_stream_t stream);
+OSPO_API int ospo_head_simpo_bwd(const ospo_simpo_args* args, ospo_stream_t stream);
+
+OSPO_API int ospo_head_cfg_sample(const ospo_cfg_args* args, ospo_stream_t stream);
+OSPO_API int ospo_head_cfg_merge_sample(const ospo_cfg_args* args, ospo_stream_t stream);
+
+OSPO_API const char* ospo_head_strerror(int status);
+
+/* ---- introspection / tuning ---------------------------------------------------------------- */
+/* tcgen05 cta_group used by the training GEMMs: 1 (one CTA per 128-row tile) or 2 (CTA pair per
+   256-row tile).  Returns the value now in effect; pass 0 to query. */
+OSPO_API int ospo_head_set_cta_group(int cta_group);
+/* rasterisation group size (M-blocks walked together); pass 0 to query */
+OSPO_API int ospo_head_set_group_m(int group_m);
+/* number of kernels launched by this library since load (the bench's gpu_launches counter) */
+OSPO_API uint64_t ospo_head_launch_count(void);
+/* 6 x u32 watchdog record written by a kernel whose mbarrier wait expired (host pointer, may be NULL) */
+OSPO_API const uint32_t* ospo_head_watchdog_record_host(void);
+/* validation hook: out[M,N] fp32 = A B^T through one GEMM-engine variant
+   (variant = cta_group*100 + majors*10 + tile; majors 0 K/K, 1 K/MN, 2 MN/MN; tile 0 BN256, 1 BN32, 2 BN128).
+   K-major operand: [rows, K] pitch ld; MN-major operand: [K, rows] pitch ld. */
+OSPO_API int ospo_head_gemm_debug(int variant, const void* a, int64_t lda, const void* b, int64_t ldb, float* out,
+                         int64_t ldo, int32_t M, int32_t N, int32_t K, ospo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSPO_HEAD_H_ */

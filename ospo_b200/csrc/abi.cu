@@ -1,0 +1,411 @@
+// C ABI of the image-token head (declared in include/ospo_head.h).  Pure orchestration: argument
+// validation, workspace carving and kernel sequencing on the caller's stream.  No allocation, no
+// synchronisation, no torch types.
+#include "../../include/ospo_head.h"
+
+#include <atomic>
+#include <mutex>
+
+#include "head_kernels.cuh"
+#include "launchers.h"
+
+using namespace ospo;
+
+namespace {
+
+struct Runtime {
+  bool ready = false;
+  int status = OSPO_OK;
+  int device = -1;
+  int num_sms = 0;
+  int cta_group = 1;
+  int group_m = 8;
+  uint32_t* wd_host = nullptr;
+  uint32_t* wd_dev = nullptr;
+};
+Runtime g_rt;
+std::mutex g_mu;
+std::atomic<uint64_t> g_launches{0};
+
+int runtime_init() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_rt.ready) return g_rt.status;
+  g_rt.ready = true;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return g_rt.status = OSPO_ERR_CUDA;
+  int major = 0, sms = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (major != 10) return g_rt.status = OSPO_ERR_ARCH;
+  g_rt.device = dev;
+  g_rt.num_sms = sms;
+  if (const char* e = getenv("OSPO_HEAD_CTA_GROUP")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2) g_rt.cta_group = v;
+  }
+  if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
+    const int v = atoi(e);
+    if (v > 0) g_rt.group_m = v;
+  }
+  if (cudaHostAlloc(reinterpret_cast<void**>(&g_rt.wd_host), 64 * sizeof(uint32_t), cudaHostAllocMapped) ==
+      cudaSuccess) {
+    for (int i = 0; i < 64; ++i) g_rt.wd_host[i] = 0;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_rt.wd_dev), g_rt.wd_host, 0) == cudaSuccess) {
+      set_watchdog_fwd(g_rt.wd_dev);
+      set_watchdog_bwd(g_rt.wd_dev);
+      set_watchdog_decode(g_rt.wd_dev);
+      set_watchdog_debug(g_rt.wd_dev);
+    }
+  } else {
+    cudaGetLastError();
+  }
+  return g_rt.status = OSPO_OK;
+}
+
+LaunchCtx make_ctx(cudaStream_t s) {
+  LaunchCtx c;
+  c.num_sms = g_rt.num_sms;
+  c.cta_group = g_rt.cta_group;
+  c.group_m = g_rt.group_m;
+  c.stream = s;
+  return c;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// map launcher return codes to ABI status
+int map_rc(int rc) {
+  if (rc == 0) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return OSPO_OK;
+  }
+  if (rc == -1 || rc == -2) return OSPO_ERR_TENSORMAP;
+  if (rc == -100) return OSPO_ERR_UNSUPPORTED;
+  return OSPO_ERR_LAUNCH;
+}
+int check_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError() == cudaSuccess ? OSPO_OK : OSPO_ERR_LAUNCH;
+}
+
+int check_shape(const ospo_head_shape& s, bool need_seqs) {
+  if (s.rows <= 0 || s.hidden <= 0 || s.embed <= 0 || s.vocab <= 0) return OSPO_ERR_BAD_SHAPE;
+  if (need_seqs && s.num_seqs <= 0) return OSPO_ERR_BAD_SHAPE;
+  if ((s.hidden % 8) || (s.embed % 8) || (s.vocab % 8)) return OSPO_ERR_ALIGNMENT;
+  return OSPO_OK;
+}
+int check_weights(const ospo_head_weights& w) {
+  if (!w.w1 || !w.b1 || !w.w2 || !w.b2) return OSPO_ERR_NULL;
+  if (!aligned16(w.w1) || !aligned16(w.w2)) return OSPO_ERR_ALIGNMENT;
+  return OSPO_OK;
+}
+
+// workspace carving -------------------------------------------------------------------------
+struct Workspace {
+  float2* part;          // [num_n, rows]
+  float* rowsum_part;    // [num_n, rows]
+  float* tgt;            // [rows]
+  float* row_logit_sum;  // [rows]
+  float* row_coef;       // [rows]
+  float* seq_sum;        // [S]
+  float* seq_logit_sum;  // [S]
+  __nv_bfloat16* rows_by_e;  // [rows, E]: dpre (backward) / act (plain logits, decode)
+  size_t total;
+};
+
+Workspace carve(const ospo_head_shape& s, void* base) {
+  Workspace w;
+  const size_t rows = static_cast<size_t>(s.rows), S = static_cast<size_t>(s.num_seqs > 0 ? s.num_seqs : 1);
+  const size_t num_n = static_cast<size_t>(gemm2_num_n_tiles(s.vocab));
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* q = p ? p + off : nullptr;
+    off = align_up(off + bytes, 256);
+    return q;
+  };
+  w.part = reinterpret_cast<float2*>(take(num_n * rows * sizeof(float2)));
+  w.rowsum_part = reinterpret_cast<float*>(take(num_n * rows * sizeof(float)));
+  w.tgt = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  w.row_logit_sum = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  w.row_coef = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  w.seq_sum = reinterpret_cast<float*>(take(S * sizeof(float)));
+  w.seq_logit_sum = reinterpret_cast<float*>(take(S * sizeof(float)));
+  w.rows_by_e = reinterpret_cast<__nv_bfloat16*>(take(rows * static_cast<size_t>(s.embed) * 2));
+  w.total = off;
+  return w;
+}
+
+int check_ws(const ospo_head_shape& s, void* ws, size_t bytes, Workspace* out) {
+  if (!ws) return OSPO_ERR_NULL;
+  if (!aligned16(ws)) return OSPO_ERR_ALIGNMENT;
+  *out = carve(s, ws);
+  if (out->total > bytes) return OSPO_ERR_WORKSPACE;
+  return OSPO_OK;
+}
+
+// shared forward: GEMM1 -> GEMM2 + LSE partials -> merge -> per-sequence reduce
+int logps_forward(const ospo_simpo_args* a, const Workspace& w, cudaStream_t st) {
+  const ospo_head_shape& s = a->shape;
+  const LaunchCtx c = make_ctx(st);
+  int rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
+                                         static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1,
+                                         static_cast<__nv_bfloat16*>(a->pre), static_cast<__nv_bfloat16*>(a->act),
+                                         s.rows, s.hidden, s.embed));
+  if (rc) return rc;
+  rc = map_rc(launch_gemm2_logits_lse(c, static_cast<const __nv_bfloat16*>(a->act),
+                                      static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
+                                      static_cast<__nv_bfloat16*>(a->logits), a->labels, w.part, w.rowsum_part, w.tgt,
+                                      s.rows, s.embed, s.vocab));
+  if (rc) return rc;
+  const int num_n = gemm2_num_n_tiles(s.vocab);
+  lse_finalize_kernel<<<(s.rows + 255) / 256, 256, 0, st>>>(w.part, w.rowsum_part, w.tgt, s.rows, num_n, a->row_lse,
+                                                            a->row_logps, w.row_logit_sum);
+  if ((rc = check_launch())) return rc;
+  seq_reduce_kernel<<<s.num_seqs, 256, 0, st>>>(a->row_logps, w.row_logit_sum, a->seq_offsets, a->average_log_prob,
+                                                a->seq_logps, w.seq_sum, w.seq_logit_sum);
+  return check_launch();
+}
+
+int check_simpo_common(const ospo_simpo_args* a, Workspace* w) {
+  if (!a) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  if ((rc = check_shape(a->shape, true))) return rc;
+  if ((rc = check_weights(a->w))) return rc;
+  if (!a->x || !a->labels || !a->seq_offsets) return OSPO_ERR_NULL;
+  if (!aligned16(a->x)) return OSPO_ERR_ALIGNMENT;
+  return check_ws(a->shape, a->workspace, a->workspace_bytes, w);
+}
+
+// shared backward: row coefficients -> softmax-minus-onehot producer -> GEMM pair(s)
+int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft_coef, int num_sft_seqs,
+                  cudaStream_t st) {
+  const ospo_head_shape& s = a->shape;
+  if (!a->dx && !a->flat_grads) return OSPO_OK;
+  if (!a->pre || !a->act || !a->logits || !a->row_lse || !a->grad_seq) return OSPO_ERR_NULL;
+  const LaunchCtx c = make_ctx(st);
+  int rc;
+  row_coef_kernel<<<s.num_seqs, 128, 0, st>>>(a->grad_seq, a->seq_offsets, a->average_log_prob, a->grad_loss,
+                                              sft_coef, num_sft_seqs, w.row_coef);
+  if ((rc = check_launch())) return rc;
+
+  const size_t VE = static_cast<size_t>(s.vocab) * s.embed, EH = static_cast<size_t>(s.embed) * s.hidden;
+  float* dW2 = a->flat_grads;
+  float* dW1 = a->flat_grads ? a->flat_grads + VE : nullptr;
+  float* db2 = a->flat_grads ? a->flat_grads + VE + EH : nullptr;
+  float* db1 = a->flat_grads ? db2 + s.vocab : nullptr;
+  if (a->flat_grads) {
+    if (cudaMemsetAsync(db2, 0, sizeof(float) * (static_cast<size_t>(s.vocab) + s.embed), st) != cudaSuccess)
+      return OSPO_ERR_CUDA;
+  }
+  __nv_bfloat16* dlogits = static_cast<__nv_bfloat16*>(a->logits);
+  {
+    dim3 grid((s.vocab + 1023) / 1024, (s.rows + DL_ROWS_PER_BLOCK - 1) / DL_ROWS_PER_BLOCK);
+    dlogits_kernel<<<grid, 128, 0, st>>>(dlogits, s.vocab, a->labels, a->row_lse, w.row_coef, s.rows, s.vocab, db2);
+    if ((rc = check_launch())) return rc;
+  }
+  __nv_bfloat16* dpre = w.rows_by_e;
+  rc = map_rc(launch_dact_gelu_bwd(c, dlogits, static_cast<const __nv_bfloat16*>(a->w.w2),
+                                   static_cast<const __nv_bfloat16*>(a->pre), dpre, s.rows, s.embed, s.vocab));
+  if (rc) return rc;
+  if (a->flat_grads) {
+    // dW2 first: it is the largest block of the flat gradient, so a caller that overlaps the
+    // all-reduce with the remaining GEMMs can start on it earliest.
+    rc = map_rc(launch_wgrad(c, dlogits, static_cast<const __nv_bfloat16*>(a->act), dW2, s.rows, s.vocab, s.embed));
+    if (rc) return rc;
+    dim3 grid((s.embed + 1023) / 1024, (s.rows + DL_ROWS_PER_BLOCK - 1) / DL_ROWS_PER_BLOCK);
+    colsum_bf16_kernel<<<grid, 128, 0, st>>>(dpre, s.embed, s.rows, s.embed, db1);
+    if ((rc = check_launch())) return rc;
+    rc = map_rc(launch_wgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden));
+    if (rc) return rc;
+  }
+  if (a->dx) {
+    rc = map_rc(launch_dgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->w.w1), static_cast<__nv_bfloat16*>(a->dx),
+                             s.rows, s.embed, s.hidden));
+    if (rc) return rc;
+  }
+  return OSPO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ospo_head_workspace_bytes(const ospo_head_shape* shape, size_t* out_bytes) {
+  if (!shape || !out_bytes) return OSPO_ERR_NULL;
+  if (shape->rows <= 0 || shape->embed <= 0 || shape->vocab <= 0) return OSPO_ERR_BAD_SHAPE;
+  *out_bytes = carve(*shape, nullptr).total;
+  return OSPO_OK;
+}
+
+int ospo_head_logits(const ospo_head_args* a, ospo_stream_t stream) {
+  if (!a) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  if ((rc = check_shape(a->shape, false))) return rc;
+  if ((rc = check_weights(a->w))) return rc;
+  if (!a->x || !a->logits) return OSPO_ERR_NULL;
+  if (!aligned16(a->x) || !aligned16(a->logits)) return OSPO_ERR_ALIGNMENT;
+  Workspace w;
+  if ((rc = check_ws(a->shape, a->workspace, a->workspace_bytes, &w))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const LaunchCtx c = make_ctx(st);
+  const ospo_head_shape& s = a->shape;
+  rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
+                                     static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1, nullptr, w.rows_by_e, s.rows,
+                                     s.hidden, s.embed));
+  if (rc) return rc;
+  return map_rc(launch_gemm2_logits(c, w.rows_by_e, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
+                                    static_cast<__nv_bfloat16*>(a->logits), s.vocab, s.rows, s.embed, s.vocab));
+}
+
+int ospo_head_logps_fwd(const ospo_simpo_args* a, ospo_stream_t stream) {
+  Workspace w;
+  int rc = check_simpo_common(a, &w);
+  if (rc) return rc;
+  if (!a->act || !a->row_lse || !a->row_logps || !a->seq_logps) return OSPO_ERR_NULL;
+  return logps_forward(a, w, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ospo_head_logps_bwd(const ospo_simpo_args* a, ospo_stream_t stream) {
+  Workspace w;
+  int rc = check_simpo_common(a, &w);
+  if (rc) return rc;
+  return head_backward(a, w, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ospo_head_simpo_fwd(const ospo_simpo_args* a, ospo_stream_t stream) {
+  Workspace w;
+  int rc = check_simpo_common(a, &w);
+  if (rc) return rc;
+  if (a->shape.num_seqs % 2) return OSPO_ERR_BAD_SHAPE;
+  if (!a->act || !a->row_lse || !a->row_logps || !a->seq_logps || !a->losses || !a->chosen_rewards ||
+      !a->rejected_rewards || !a->scalars || !a->grad_seq)
+    return OSPO_ERR_NULL;
+  if (a->loss_type != OSPO_LOSS_SIGMOID && a->loss_type != OSPO_LOSS_HINGE) return OSPO_ERR_UNSUPPORTED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((rc = logps_forward(a, w, st))) return rc;
+  SimpoHyper hp;
+  hp.beta = a->beta;
+  hp.gamma_beta_ratio = a->gamma_beta_ratio;
+  hp.label_smoothing = a->label_smoothing;
+  hp.sft_weight = a->sft_weight;
+  hp.loss_type = a->loss_type;
+  hp.vocab = a->shape.vocab;
+  simpo_scalar_kernel<<<1, 256, 0, st>>>(a->seq_logps, w.seq_sum, w.seq_logit_sum, a->seq_offsets,
+                                         a->shape.num_seqs / 2, hp, a->losses, a->chosen_rewards, a->rejected_rewards,
+                                         a->grad_seq, a->scalars);
+  return check_launch();
+}
+
+int ospo_head_simpo_bwd(const ospo_simpo_args* a, ospo_stream_t stream) {
+  Workspace w;
+  int rc = check_simpo_common(a, &w);
+  if (rc) return rc;
+  if (!a->scalars) return OSPO_ERR_NULL;
+  const float* sft_coef = (a->sft_weight > 0.0f) ? a->scalars + SC_SFT_ROW_COEF : nullptr;
+  return head_backward(a, w, sft_coef, a->shape.num_seqs / 2, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int launch_sampler(const ospo_cfg_args* a, int pairs, cudaStream_t st) {
+  const int V = a->shape.vocab;
+  if (V != SAMPLE_THREADS * SAMPLE_SEG) return OSPO_ERR_UNSUPPORTED;
+  if (!a->greedy && !a->uniforms) return OSPO_ERR_NULL;
+  if (!a->ids || !a->logits) return OSPO_ERR_NULL;
+  if (!(a->temperature > 0.0f)) return OSPO_ERR_UNSUPPORTED;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(V) + V / 32 + SAMPLE_THREADS + 32 + SAMPLE_THREADS) +
+                      sizeof(int) * SAMPLE_THREADS;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cfg_merge_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess)
+      return OSPO_ERR_CUDA;
+    attr_set = true;
+  }
+  cfg_merge_sample_kernel<<<pairs, SAMPLE_THREADS, smem, st>>>(static_cast<const __nv_bfloat16*>(a->logits), V, V,
+                                                              a->cfg_weight, a->temperature, a->merge_mode,
+                                                              a->uniforms, a->greedy, a->ids, a->merged);
+  return check_launch();
+}
+
+int ospo_head_cfg_merge_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
+  if (!a) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  if (a->shape.rows <= 0 || (a->shape.rows % 2)) return OSPO_ERR_BAD_SHAPE;
+  if (!aligned16(a->logits)) return OSPO_ERR_ALIGNMENT;
+  const int steps = a->num_steps > 1 ? a->num_steps : 1;
+  return launch_sampler(a, steps * (a->shape.rows / 2), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
+  if (!a) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  if ((rc = check_shape(a->shape, false))) return rc;
+  if (a->shape.rows % 2) return OSPO_ERR_BAD_SHAPE;
+  if ((rc = check_weights(a->w))) return rc;
+  if (!a->h || !a->logits) return OSPO_ERR_NULL;
+  if (!aligned16(a->h) || !aligned16(a->logits)) return OSPO_ERR_ALIGNMENT;
+  Workspace w;
+  if ((rc = check_ws(a->shape, a->workspace, a->workspace_bytes, &w))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const LaunchCtx c = make_ctx(st);
+  const ospo_head_shape& s = a->shape;
+  rc = map_rc(launch_decode_gemm1(c, static_cast<const __nv_bfloat16*>(a->h),
+                                  static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1, w.rows_by_e, s.rows, s.hidden,
+                                  s.embed));
+  if (rc) return rc;
+  rc = map_rc(launch_decode_gemm2(c, w.rows_by_e, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
+                                  static_cast<__nv_bfloat16*>(a->logits), s.rows, s.embed, s.vocab));
+  if (rc) return rc;
+  return launch_sampler(a, s.rows / 2, st);
+}
+
+const char* ospo_head_strerror(int status) {
+  switch (status) {
+    case OSPO_OK: return "ok";
+    case OSPO_ERR_BAD_SHAPE: return "bad shape";
+    case OSPO_ERR_ALIGNMENT: return "pointer must be 16-byte aligned and H/E/V multiples of 8";
+    case OSPO_ERR_NULL: return "required pointer is NULL";
+    case OSPO_ERR_WORKSPACE: return "workspace too small (see ospo_head_workspace_bytes)";
+    case OSPO_ERR_ARCH: return "device is not sm_100 (B200); this library has no other code path";
+    case OSPO_ERR_TENSORMAP: return "cuTensorMapEncodeTiled failed or is unavailable";
+    case OSPO_ERR_LAUNCH: return "kernel launch failed";
+    case OSPO_ERR_CUDA: return "CUDA runtime error";
+    case OSPO_ERR_UNSUPPORTED: return "unsupported argument combination";
+    default: return "unknown status";
+  }
+}
+
+int ospo_head_set_cta_group(int cta_group) {
+  runtime_init();
+  if (cta_group == 1 || cta_group == 2) g_rt.cta_group = cta_group;
+  return g_rt.cta_group;
+}
+
+int ospo_head_set_group_m(int group_m) {
+  runtime_init();
+  if (group_m > 0) g_rt.group_m = group_m;
+  return g_rt.group_m;
+}
+
+uint64_t ospo_head_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const uint32_t* ospo_head_watchdog_record_host(void) { return g_rt.wd_host; }
+
+int ospo_head_gemm_debug(int variant, const void* a, int64_t lda, const void* b, int64_t ldb, float* out, int64_t ldo,
+                         int32_t M, int32_t N, int32_t K, ospo_stream_t stream) {
+  int rc = runtime_init();
+  if (rc) return rc;
+  if (!a || !b || !out) return OSPO_ERR_NULL;
+  if (M <= 0 || N <= 0 || K <= 0) return OSPO_ERR_BAD_SHAPE;
+  if (!aligned16(a) || !aligned16(b) || (lda % 8) || (ldb % 8)) return OSPO_ERR_ALIGNMENT;
+  const LaunchCtx c = make_ctx(reinterpret_cast<cudaStream_t>(stream));
+  return map_rc(launch_gemm_debug(c, variant, static_cast<const __nv_bfloat16*>(a), lda,
+                                  static_cast<const __nv_bfloat16*>(b), ldb, out, ldo, M, N, K));
+}
+
+}  // extern "C"

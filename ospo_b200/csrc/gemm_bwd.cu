@@ -1,0 +1,44 @@
+// Backward GEMMs of the image-token head.  No operand is ever transposed in memory:
+//   data gradients   dA = dY W      : A operand K-major (dY [rows,out]), B operand MN-major (W [out,in])
+//   weight gradients dW = dY^T X    : both operands MN-major (dY [rows,out], X [rows,in]; K = rows)
+#include "epilogues.cuh"
+#include "launchers.h"
+
+namespace ospo {
+
+void set_watchdog_bwd(uint32_t* dev_ptr) { cudaMemcpyToSymbol(g_watchdog_buf, &dev_ptr, sizeof(dev_ptr)); }
+
+using CfgD1 = GemmCfg<1, 256, false, true>;
+using CfgD2 = GemmCfg<2, 256, false, true>;
+using CfgW1 = GemmCfg<1, 256, true, true>;
+using CfgW2 = GemmCfg<2, 256, true, true>;
+
+int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* dlogits, const __nv_bfloat16* w2,
+                         const __nv_bfloat16* pre, __nv_bfloat16* dpre, int rows, int E, int V) {
+  using Epi = EpiGeluBwd;
+  Epi::Params p{pre, dpre, E};
+  // D[rows, E] = dlogits[rows, V] * W2[V, E]:  M = rows, N = E, K = V
+  if (c.cta_group == 2) return launch_gemm<CfgD2, Epi>(dlogits, V, w2, E, rows, E, V, c.group_m, p, c.num_sms, c.stream);
+  return launch_gemm<CfgD1, Epi>(dlogits, V, w2, E, rows, E, V, c.group_m, p, c.num_sms, c.stream);
+}
+
+int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx, int rows,
+                 int out_dim, int in_dim) {
+  using Epi = EpiStore<__nv_bfloat16, false, false>;
+  Epi::Params p{dx, in_dim, nullptr};
+  if (c.cta_group == 2)
+    return launch_gemm<CfgD2, Epi>(dy, out_dim, w, in_dim, rows, in_dim, out_dim, c.group_m, p, c.num_sms, c.stream);
+  return launch_gemm<CfgD1, Epi>(dy, out_dim, w, in_dim, rows, in_dim, out_dim, c.group_m, p, c.num_sms, c.stream);
+}
+
+int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw, int rows, int out_dim,
+                 int in_dim) {
+  using Epi = EpiStore<float, false, false>;
+  Epi::Params p{dw, in_dim, nullptr};
+  // D[out, in] = dY^T[out, rows] * X[rows, in]:  M = out_dim, N = in_dim, K = rows
+  if (c.cta_group == 2)
+    return launch_gemm<CfgW2, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream);
+  return launch_gemm<CfgW1, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream);
+}
+
+}  // namespace ospo

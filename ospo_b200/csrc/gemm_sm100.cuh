@@ -1,0 +1,367 @@
+// Persistent, warp-specialised tcgen05 GEMM engine for sm_100a.
+//
+//   D[M, N] = A[M, K] * B[N, K]^T      (bf16 operands, fp32 accumulation in TMEM)
+//
+// * operands arrive by TMA (128-byte swizzle) into a multi-stage shared-memory ring,
+// * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, or 256 x BN x 16 with cta_group::2),
+// * accumulators live in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1,
+// * four epilogue warps read TMEM with tcgen05.ld (one accumulator row per thread) and hand each
+//   32-column chunk to an epilogue functor (bias, GELU, online log-sum-exp, target gather, ...).
+//
+// Either operand may be "K-major" (global layout [rows, K], K contiguous) or "MN-major"
+// (global layout [K, rows], rows contiguous); the latter is what the two weight-gradient GEMMs
+// and the two data-gradient GEMMs of the head need, so no transposed copies are ever made.
+//
+// Warp roles (256 threads):  0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
+//                            4..7 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +32).
+#pragma once
+
+#include "ptx.cuh"
+
+namespace ospo {
+
+struct GemmDims {
+  int M, N, K;
+  int group_m;  // rasterisation: tiles are walked M-fastest inside groups of `group_m` M-blocks
+};
+
+// watchdog site ids
+enum : uint32_t {
+  SITE_PRODUCER_EMPTY = 1,
+  SITE_MMA_FULL = 2,
+  SITE_MMA_TMEM_EMPTY = 3,
+  SITE_EPI_TMEM_FULL = 4,
+};
+
+template <int CG_, int BN_, bool A_MN_, bool B_MN_, int EPI_SMEM_BYTES_ = 0>
+struct GemmCfg {
+  static constexpr int CG = CG_;            // CTAs cooperating on one tile (cta_group)
+  static constexpr int BN = BN_;            // tile N (UMMA N)
+  static constexpr bool A_MN = A_MN_;
+  static constexpr bool B_MN = B_MN_;
+  static constexpr int BM = 128;            // accumulator rows per CTA (TMEM lanes)
+  static constexpr int TILE_M = BM * CG;    // tile M (UMMA M)
+  static constexpr int BK = 64;             // K per stage: 64 bf16 = one 128-byte swizzle row
+  static constexpr int UMMA_K = 16;
+  static constexpr int B_ROWS = BN / CG;    // N extent of B held by each CTA
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_SMEM_BYTES = EPI_SMEM_BYTES_;
+  static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - EPI_SMEM_BYTES;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS_RAW = ACC_STAGES * BN;
+  static constexpr int TMEM_COLS =
+      TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + EPI_SMEM_BYTES;
+  static constexpr int THREADS = 256;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16, 256]");
+  static_assert(!B_MN || (B_ROWS % 64 == 0), "MN-major B is staged in 64-row swizzle atoms");
+  static_assert(B_ROWS % 8 == 0, "K-major B rows come in 8-row swizzle groups");
+  static_assert(STAGES >= 2, "need at least a double-buffered ring");
+};
+
+struct TileCoord {
+  int m_blk, n_blk;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
+  const int tiles_per_group = group_m * num_n;
+  const int g = t / tiles_per_group;
+  const int first_m = g * group_m;
+  const int gm = min(num_m - first_m, group_m);
+  const int local = t - g * tiles_per_group;
+  TileCoord c;
+  c.m_blk = first_m + local % gm;
+  c.n_blk = local / gm;
+  return c;
+}
+
+// Epilogue functor concept:
+//   struct Epi {
+//     struct Params { ... };                      // POD, passed by value to the kernel
+//     struct State  { ... };                      // per-thread registers that live across one tile
+//     static constexpr int SMEM_BYTES;
+//     __device__ static void begin(const Params&, State&, int row, int n0, const GemmDims&);
+//     __device__ static void chunk(const Params&, State&, int row, int col0, float (&v)[32], const GemmDims&);
+//     __device__ static void end(const Params&, State&, int row, int n0, int n_blk, const GemmDims&);
+//   };
+// `row` is the global accumulator row owned by the calling thread (may be >= M: the functor must
+// guard its global accesses), `col0` the global column of v[0].
+
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmDims dims,
+            typename Epi::Params ep) {
+  constexpr int CG = Cfg::CG, BN = Cfg::BN, BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle atoms need 1024-byte alignment (in the shared address space)
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+
+  const int num_m = (dims.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+  const int num_n = (dims.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (dims.K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader producer's arrive.expect_tx (covers both CTAs' bytes)
+      mbar_init(&empty_bar[s], 1);  // one tcgen05.commit per stage use
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);        // one tcgen05.commit per tile
+      mbar_init(&tmem_empty_bar[a], 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ===================== TMA producer (one elected thread) =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const TileCoord tc = tile_coord(t, num_m, num_n, dims.group_m);
+        const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
+        const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u, SITE_PRODUCER_EMPTY);
+          uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES * CG);
+          const int k0 = kb * BK;
+          if constexpr (!Cfg::A_MN) {
+            if constexpr (CG == 1) tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0, kEvictNormal);
+            else tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], k0, m0, kEvictNormal);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) {
+              if constexpr (CG == 1) tma_load_2d(sa + c * (BK * 128), &tmap_a, &full_bar[s], m0 + 64 * c, k0, kEvictNormal);
+              else tma_load_2d_2sm(sa + c * (BK * 128), &tmap_a, &full_bar[s], m0 + 64 * c, k0, kEvictNormal);
+            }
+          }
+          if constexpr (!Cfg::B_MN) {
+            if constexpr (CG == 1) tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0, kEvictNormal);
+            else tma_load_2d_2sm(sb, &tmap_b, &full_bar[s], k0, n0, kEvictNormal);
+          } else {
+#pragma unroll
+            for (int c = 0; c < Cfg::B_ROWS / 64; ++c) {
+              if constexpr (CG == 1) tma_load_2d(sb + c * (BK * 128), &tmap_b, &full_bar[s], n0 + 64 * c, k0, kEvictNormal);
+              else tma_load_2d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s], n0 + 64 * c, k0, kEvictNormal);
+            }
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (is_leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(Cfg::TILE_M, BN, Cfg::A_MN, Cfg::B_MN);
+      // K-major SW128: 8-row groups are 1024 B apart (SBO); LBO unused.  Advance K by 32 B per UMMA_K.
+      // MN-major SW128: 64-element MN chunks are BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO);
+      //                 advance K by 16 rows * 128 B = 2048 B per UMMA_K.
+      constexpr uint32_t A_LBO = Cfg::A_MN ? BK * 128 : 0, A_SBO = 1024, A_KSTEP = Cfg::A_MN ? 2048 : 32;
+      constexpr uint32_t B_LBO = Cfg::B_MN ? BK * 128 : 0, B_SBO = 1024, B_KSTEP = Cfg::B_MN ? 2048 : 32;
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
+        const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1u, SITE_MMA_TMEM_EMPTY);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph, SITE_MMA_FULL);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, A_LBO, A_SBO);
+              const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, B_LBO, B_SBO);
+              umma_bf16<CG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // free the smem slot once these MMAs have drained it; on the last k-block also publish the tile
+            if constexpr (CG == 1) {
+              umma_commit(&empty_bar[s]);
+              if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+            } else {
+              umma_commit_2sm(&empty_bar[s], 0x3);
+              if (kb == num_kb - 1) umma_commit_2sm(&tmem_full_bar[as], 0x3);
+            }
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 256;
+    uint32_t leader_tmem_empty_addr[ACC_STAGES];
+#pragma unroll
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      const uint32_t local = smem_u32(&tmem_empty_bar[a]);
+      leader_tmem_empty_addr[a] = (CG == 2) ? mapa_shared(local, 0) : local;
+    }
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      const TileCoord tc = tile_coord(t, num_m, num_n, dims.group_m);
+      const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
+      const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+      const int row = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM + q * 32 + lane;
+      const int n0 = tc.n_blk * BN;
+      mbar_wait(&tmem_full_bar[as], aph, SITE_EPI_TMEM_FULL);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      typename Epi::State st;
+      Epi::begin(ep, st, row, n0, dims, epi_smem);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait(r);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        Epi::chunk(ep, st, row, n0 + c * 32, v, dims, epi_smem);
+      }
+      // accumulator stage drained: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[as]);
+        else mbar_arrive_cluster(leader_tmem_empty_addr[as]);
+      }
+      Epi::end(ep, st, row, n0, tc.n_blk, dims, epi_smem);
+    }
+  }
+
+  // ===================== teardown =====================
+  __syncwarp();  // re-converge the single-thread roles before the block-wide barrier
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side: tensor maps + launch
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, row pitch `ld` elements) viewed through a
+// {64 cols x box_rows} box with 128-byte swizzle.  Out-of-bounds elements read as zero.
+inline int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return -1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// a / b: global pointers.  K-major operand: [rows, K] with pitch ld; MN-major operand: [K, rows] with pitch ld.
+template <class Cfg, class Epi>
+int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K, int group_m,
+                const typename Epi::Params& ep, int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  CUtensorMap ta, tb;
+  int rc;
+  if constexpr (!Cfg::A_MN) rc = make_tmap_bf16_2d(&ta, a, M, K, lda, Cfg::BM);
+  else rc = make_tmap_bf16_2d(&ta, a, K, M, lda, Cfg::BK);
+  if (rc != 0) return rc;
+  if constexpr (!Cfg::B_MN) rc = make_tmap_bf16_2d(&tb, b, N, K, ldb, Cfg::B_ROWS);
+  else rc = make_tmap_bf16_2d(&tb, b, K, N, ldb, Cfg::BK);
+  if (rc != 0) return rc;
+
+  auto kern = gemm_kernel<Cfg, Epi>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return -3;
+    attr_set = true;
+  }
+  GemmDims dims;
+  dims.M = M;
+  dims.N = N;
+  dims.K = K;
+  dims.group_m = group_m > 0 ? group_m : 8;
+  const int num_m = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+  const int num_n = (N + Cfg::BN - 1) / Cfg::BN;
+  const int num_tiles = num_m * num_n;
+  int clusters = num_sms / Cfg::CG;
+  if (clusters > num_tiles) clusters = num_tiles;
+  if (clusters < 1) clusters = 1;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * Cfg::CG, 1, 1);
+  cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = Cfg::CG;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, dims, ep);
+  return e == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace ospo

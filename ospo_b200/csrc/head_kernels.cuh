@@ -1,0 +1,436 @@
+// Non-GEMM kernels of the image-token head path: log-sum-exp merge, per-sequence log-prob
+// reduction, the SimPO scalar stage, the softmax-minus-onehot producer for the backward GEMM pair,
+// bias-gradient column sums, and the CFG merge + inverse-CDF sampler.
+// All are HBM- or latency-bound; grids are sized from the data, loads are 16-byte vectors.
+#pragma once
+
+#include "ptx.cuh"
+
+namespace ospo {
+
+// ---------------------------------------------------------------------------
+// Merge the per-(N-tile,row) partials written by EpiLogitsLse into per-row lse and log-prob.
+// reference: logits.log_softmax(-1) gathered at labels, ospo/wrapper/train.py:391
+// ---------------------------------------------------------------------------
+__global__ void lse_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ rowsum_part,
+                                    const float* __restrict__ tgt, int rows, int num_n, float* __restrict__ row_lse,
+                                    float* __restrict__ row_logp, float* __restrict__ row_logit_sum) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float m = -INFINITY;
+  for (int nb = 0; nb < num_n; ++nb) m = fmaxf(m, part[static_cast<int64_t>(nb) * rows + r].x);
+  float s = 0.0f, ls = 0.0f;
+  for (int nb = 0; nb < num_n; ++nb) {
+    const float2 p = part[static_cast<int64_t>(nb) * rows + r];
+    s += p.y * expf(p.x - m);
+    if (rowsum_part != nullptr) ls += rowsum_part[static_cast<int64_t>(nb) * rows + r];
+  }
+  const float lse = m + logf(s);
+  row_lse[r] = lse;
+  row_logp[r] = tgt[r] - lse;
+  if (row_logit_sum != nullptr) row_logit_sum[r] = ls;
+}
+
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  // fixed-shape tree: deterministic for a given THREADS
+  red[threadIdx.x] = v;
+  __syncthreads();
+#pragma unroll
+  for (int s = THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const float out = red[0];
+  __syncthreads();
+  return out;
+}
+
+// One block per sequence: (per_token_logps * mask).sum(-1) [/ mask.sum(-1)]  (train.py:393-396).
+// Rows of sequence s are [seq_off[s], seq_off[s+1]) -- only unmasked rows are ever given to the head.
+__global__ void seq_reduce_kernel(const float* __restrict__ row_logp, const float* __restrict__ row_logit_sum,
+                                  const int64_t* __restrict__ seq_off, int average, float* __restrict__ seq_logps,
+                                  float* __restrict__ seq_sum, float* __restrict__ seq_logit_sum) {
+  __shared__ float red[256];
+  const int s = blockIdx.x;
+  const int64_t lo = seq_off[s], hi = seq_off[s + 1];
+  float a = 0.0f, b = 0.0f;
+  for (int64_t r = lo + threadIdx.x; r < hi; r += 256) {
+    a += row_logp[r];
+    if (row_logit_sum != nullptr) b += row_logit_sum[r];
+  }
+  a = block_sum<256>(a, red);
+  b = block_sum<256>(b, red);
+  if (threadIdx.x == 0) {
+    const float n = static_cast<float>(hi - lo);
+    seq_sum[s] = a;
+    seq_logps[s] = average ? a / n : a;
+    if (seq_logit_sum != nullptr) seq_logit_sum[s] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// SimPO scalar stage (single block).  reference: simpo_loss ospo/wrapper/train.py:317-342,
+// losses.mean() :419, optional SFT term :421-430, metrics :432-443; gradient per SURVEY §8 a-6.
+// Sequences [0,B) are chosen, [B,2B) rejected (concatenated_forward, train.py:364-365).
+// ---------------------------------------------------------------------------
+struct SimpoHyper {
+  float beta, gamma_beta_ratio, label_smoothing, sft_weight;
+  int loss_type;  // 0 = sigmoid, 1 = hinge
+  int vocab;
+};
+
+enum SimpoScalar {
+  SC_LOSS = 0,
+  SC_SIMPO_LOSS = 1,
+  SC_SFT_LOSS = 2,
+  SC_REWARD_CHOSEN = 3,
+  SC_REWARD_REJECTED = 4,
+  SC_REWARD_ACC = 5,
+  SC_REWARD_MARGIN = 6,
+  SC_LOGPS_CHOSEN = 7,
+  SC_LOGPS_REJECTED = 8,
+  SC_LOGITS_CHOSEN = 9,
+  SC_LOGITS_REJECTED = 10,
+  SC_SFT_ROW_COEF = 11,
+  SC_COUNT = 16
+};
+
+__device__ __forceinline__ float log_sigmoid(float x) {
+  // stable: min(x,0) - log1p(exp(-|x|))
+  return fminf(x, 0.0f) - log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void simpo_scalar_kernel(const float* __restrict__ seq_logps, const float* __restrict__ seq_sum,
+                                    const float* __restrict__ seq_logit_sum, const int64_t* __restrict__ seq_off,
+                                    int B, SimpoHyper hp, float* __restrict__ losses,
+                                    float* __restrict__ chosen_rewards, float* __restrict__ rejected_rewards,
+                                    float* __restrict__ grad_seq, float* __restrict__ scalars) {
+  __shared__ float red[256];
+  float loss_acc = 0.f, rc_acc = 0.f, rr_acc = 0.f, acc_acc = 0.f, lc_acc = 0.f, lr_acc = 0.f;
+  float csum_acc = 0.f, ccount_acc = 0.f, rcount_acc = 0.f, clog_acc = 0.f, rlog_acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const float c = seq_logps[b], r = seq_logps[B + b];
+    const float z = (c - r) - hp.gamma_beta_ratio;
+    const float bz = hp.beta * z;
+    float loss, dz;  // dz = dloss_b / dz
+    if (hp.loss_type == 0) {
+      loss = -log_sigmoid(bz) * (1.0f - hp.label_smoothing) - log_sigmoid(-bz) * hp.label_smoothing;
+      dz = -hp.beta * ((1.0f - hp.label_smoothing) * sigmoidf(-bz) - hp.label_smoothing * sigmoidf(bz));
+    } else {
+      const float h = 1.0f - bz;
+      loss = fmaxf(h, 0.0f);
+      dz = (h > 0.0f) ? -hp.beta : 0.0f;
+    }
+    losses[b] = loss;
+    const float rc = hp.beta * c, rr = hp.beta * r;
+    chosen_rewards[b] = rc;
+    rejected_rewards[b] = rr;
+    grad_seq[b] = dz / static_cast<float>(B);        // d mean(losses) / d chosen_logps[b]
+    grad_seq[B + b] = -dz / static_cast<float>(B);   // d mean(losses) / d rejected_logps[b]
+    loss_acc += loss;
+    rc_acc += rc;
+    rr_acc += rr;
+    acc_acc += (rc > rr) ? 1.0f : 0.0f;
+    lc_acc += c;
+    lr_acc += r;
+    csum_acc += seq_sum[b];
+    ccount_acc += static_cast<float>(seq_off[b + 1] - seq_off[b]);
+    rcount_acc += static_cast<float>(seq_off[B + b + 1] - seq_off[B + b]);
+    if (seq_logit_sum != nullptr) {
+      clog_acc += seq_logit_sum[b];
+      rlog_acc += seq_logit_sum[B + b];
+    }
+  }
+  const float loss_sum = block_sum<256>(loss_acc, red);
+  const float rc_sum = block_sum<256>(rc_acc, red);
+  const float rr_sum = block_sum<256>(rr_acc, red);
+  const float acc_sum = block_sum<256>(acc_acc, red);
+  const float lc_sum = block_sum<256>(lc_acc, red);
+  const float lr_sum = block_sum<256>(lr_acc, red);
+  const float csum = block_sum<256>(csum_acc, red);
+  const float ccount = block_sum<256>(ccount_acc, red);
+  const float rcount = block_sum<256>(rcount_acc, red);
+  const float clog = block_sum<256>(clog_acc, red);
+  const float rlog = block_sum<256>(rlog_acc, red);
+  if (threadIdx.x == 0) {
+    const float fB = static_cast<float>(B);
+    const float simpo = loss_sum / fB;
+    float sft = 0.0f, sft_coef = 0.0f;
+    if (hp.sft_weight > 0.0f && ccount > 0.0f) {
+      sft = -csum / ccount;  // CrossEntropyLoss(mean) over the unmasked chosen rows
+      sft_coef = -hp.sft_weight / ccount;
+    }
+    scalars[SC_SIMPO_LOSS] = simpo;
+    scalars[SC_SFT_LOSS] = sft;
+    scalars[SC_LOSS] = hp.sft_weight * sft + simpo;
+    scalars[SC_REWARD_CHOSEN] = rc_sum / fB;
+    scalars[SC_REWARD_REJECTED] = rr_sum / fB;
+    scalars[SC_REWARD_ACC] = acc_sum / fB;
+    scalars[SC_REWARD_MARGIN] = (rc_sum - rr_sum) / fB;
+    scalars[SC_LOGPS_CHOSEN] = lc_sum / fB;
+    scalars[SC_LOGPS_REJECTED] = lr_sum / fB;
+    scalars[SC_LOGITS_CHOSEN] = ccount > 0.f ? clog / (ccount * static_cast<float>(hp.vocab)) : 0.f;
+    scalars[SC_LOGITS_REJECTED] = rcount > 0.f ? rlog / (rcount * static_cast<float>(hp.vocab)) : 0.f;
+    scalars[SC_SFT_ROW_COEF] = sft_coef;
+  }
+}
+
+// per-row coefficient c_row of  dlogits = c_row * (onehot - softmax):
+//   c_row = grad_scale * ( grad_seq[s] * (average ? 1/n_s : 1)  +  [s < num_sft_seqs] * sft_coef )
+__global__ void row_coef_kernel(const float* __restrict__ grad_seq, const int64_t* __restrict__ seq_off, int average,
+                                const float* __restrict__ grad_scale, const float* __restrict__ sft_coef,
+                                int num_sft_seqs, float* __restrict__ row_coef) {
+  const int s = blockIdx.x;
+  const int64_t lo = seq_off[s], hi = seq_off[s + 1];
+  const float gs = (grad_scale != nullptr) ? *grad_scale : 1.0f;
+  float c = grad_seq[s];
+  if (average) c /= static_cast<float>(hi - lo);
+  if (sft_coef != nullptr && s < num_sft_seqs) c += *sft_coef;
+  c *= gs;
+  for (int64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) row_coef[r] = c;
+}
+
+// ---------------------------------------------------------------------------
+// softmax-minus-onehot producer (in place on the bf16 logits spill) + db2 column sums.
+//   dlogits[r, v] = c_r * ([v == label_r] - exp(logit[r, v] - lse_r))
+// Block = 128 threads x 8 columns (16-byte vectors) = 1024 columns, looping over ROWS_PER_BLOCK rows.
+// ---------------------------------------------------------------------------
+constexpr int DL_ROWS_PER_BLOCK = 128;
+
+__global__ void __launch_bounds__(128)
+dlogits_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
+               const float* __restrict__ row_lse, const float* __restrict__ row_coef, int rows, int vocab,
+               float* __restrict__ db2) {
+  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (col >= vocab) return;
+  const int r0 = blockIdx.y * DL_ROWS_PER_BLOCK;
+  const int r1 = min(rows, r0 + DL_ROWS_PER_BLOCK);
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  constexpr float LOG2E = 1.4426950408889634f;
+  for (int r = r0; r < r1; ++r) {
+    uint4* ptr = reinterpret_cast<uint4*>(logits + static_cast<int64_t>(r) * ld + col);
+    const uint4 u = *ptr;
+    const float lse = __ldg(row_lse + r) * LOG2E;
+    const float c = __ldg(row_coef + r);
+    const int rel = static_cast<int>(__ldg(labels + r)) - col;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+      const float l0 = __low2float(p), l1 = __high2float(p);
+      float d0 = -exp2f(fmaf(l0, LOG2E, -lse));
+      float d1 = -exp2f(fmaf(l1, LOG2E, -lse));
+      if (rel == 2 * k) d0 += 1.0f;
+      if (rel == 2 * k + 1) d1 += 1.0f;
+      d0 = bf16_round(c * d0);
+      d1 = bf16_round(c * d1);
+      cs[2 * k] += d0;
+      cs[2 * k + 1] += d1;
+      o[k] = pack_bf16x2(d0, d1);
+    }
+    *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (db2 != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(db2 + col + k, cs[k]);
+  }
+}
+
+// column sums of a bf16 [rows, cols] matrix into fp32 (bias gradient db1 = sum_rows dpre)
+__global__ void __launch_bounds__(128)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, int cols, float* __restrict__ out) {
+  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (col >= cols) return;
+  const int r0 = blockIdx.y * DL_ROWS_PER_BLOCK;
+  const int r1 = min(rows, r0 + DL_ROWS_PER_BLOCK);
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = r0; r < r1; ++r) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ld + col));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+      cs[2 * k] += __low2float(p);
+      cs[2 * k + 1] += __high2float(p);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(out + col + k, cs[k]);
+}
+
+// ---------------------------------------------------------------------------
+// CFG merge + temperature + softmax + inverse-CDF sampling on bf16 logits [2P, V]
+// (row 2k = conditional, row 2k+1 = unconditional: ospo/wrapper/image_generation.py:135-141,157-158).
+//   merge_mode 0 (reference bf16 semantics, op-by-op rounding, image_generation.py:160-161):
+//        d = bf16(lc - lu); e = bf16(w * d); m = bf16(lu + e); t = bf16(m / T)
+//   merge_mode 1: same four operations in fp32 (no intermediate bf16 rounding).
+// softmax weights  w_v = exp_det(t_v - max_v t_v)  with a fully specified fp32 exp (below), summed in a
+// fixed three-level order (512 segments x 32 codes -> 16 groups x 32 segments -> 16 groups) so that the
+// oracle (oracle/cfg_sample.c) reproduces every bit:   id = min{ k : cdf_k > u * Z }.
+// greedy: argmax_v t_v, lowest index on ties.
+// ---------------------------------------------------------------------------
+constexpr int SAMPLE_THREADS = 512;
+constexpr int SAMPLE_SEG = 32;   // codes per segment (one thread)
+constexpr int SAMPLE_GRP = 32;   // segments per group
+
+// Deterministic fp32 exp for x <= 0: every step is a single IEEE-754 operation, so the C oracle
+// (compiled with -ffp-contract=off, using fmaf) is bit-identical.
+__device__ __forceinline__ float exp_det(float x) {
+  float y = __fmul_rn(x, 1.4426950408889634f);
+  if (!(y >= -125.0f)) return 0.0f;
+  const float n = rintf(y);
+  const float f = __fsub_rn(y, n);  // exact, |f| <= 0.5
+  float p = 1.5403530393381609e-04f;            // degree-6 polynomial for 2^f on [-0.5, 0.5]
+  p = __fmaf_rn(p, f, 1.3333558146428443e-03f);
+  p = __fmaf_rn(p, f, 9.6181291076284772e-03f);
+  p = __fmaf_rn(p, f, 5.5504108664821580e-02f);
+  p = __fmaf_rn(p, f, 2.4022650695910071e-01f);
+  p = __fmaf_rn(p, f, 6.9314718055994531e-01f);
+  p = __fmaf_rn(p, f, 1.0f);
+  const float scale = __int_as_float((static_cast<int>(n) + 127) << 23);  // 2^n, normal since n >= -125
+  return __fmul_rn(p, scale);
+}
+
+__device__ __forceinline__ float cfg_merge(float lc, float lu, float w, float T, int merge_mode) {
+  if (merge_mode == 0) {
+    const float d = bf16_round(__fsub_rn(lc, lu));
+    const float e = bf16_round(__fmul_rn(w, d));
+    const float m = bf16_round(__fadd_rn(lu, e));
+    return bf16_round(__fdiv_rn(m, T));
+  } else {
+    const float d = __fsub_rn(lc, lu);
+    const float e = __fmul_rn(w, d);
+    const float m = __fadd_rn(lu, e);
+    return __fdiv_rn(m, T);
+  }
+}
+
+// grid.x = number of (cond, uncond) pairs; logits row pitch ld.  vocab must be 16384 (= 512 * 32).
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int vocab, float cfg_weight,
+                        float temperature, int merge_mode, const float* __restrict__ uniforms, int greedy,
+                        int64_t* __restrict__ ids, float* __restrict__ merged_out /* [P, V] optional */) {
+  extern __shared__ float sm[];
+  // t/w values, padded by one float per 32 so that "thread i walks segment i" is bank-conflict free
+  float* tv = sm;                                      // vocab + vocab/32 floats
+  float* seg_sum = tv + vocab + vocab / 32;            // 512
+  float* grp_sum = seg_sum + SAMPLE_THREADS;           // 16
+  float* red = grp_sum + 32;                           // 512 (max / argmax value)
+  int* redi = reinterpret_cast<int*>(red + SAMPLE_THREADS);  // 512
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x;
+  const __nv_bfloat16* lc = logits + static_cast<int64_t>(2 * p) * ld;
+  const __nv_bfloat16* lu = lc + ld;
+
+  // pass 1: coalesced 16-byte loads, merge, stash in smem
+  for (int vec = tid; vec < vocab / 8; vec += SAMPLE_THREADS) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(lc) + vec);
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(lu) + vec);
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(&wa[k]);
+      const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&wb[k]);
+      const int v = vec * 8 + 2 * k;
+      const float t0 = cfg_merge(__low2float(pa), __low2float(pb), cfg_weight, temperature, merge_mode);
+      const float t1 = cfg_merge(__high2float(pa), __high2float(pb), cfg_weight, temperature, merge_mode);
+      tv[v + (v >> 5)] = t0;
+      tv[v + 1 + ((v + 1) >> 5)] = t1;
+      if (merged_out != nullptr) {
+        merged_out[static_cast<int64_t>(p) * vocab + v] = t0;
+        merged_out[static_cast<int64_t>(p) * vocab + v + 1] = t1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // pass 2: per-segment max / argmax (thread i owns codes [32 i, 32 i + 32))
+  const int nseg = vocab / SAMPLE_SEG;  // 512
+  float lmax = -INFINITY;
+  int larg = 0;
+  if (tid < nseg) {
+    const float* seg = tv + tid * (SAMPLE_SEG + 1);
+    larg = tid * SAMPLE_SEG;
+#pragma unroll 8
+    for (int j = 0; j < SAMPLE_SEG; ++j) {
+      const float t = seg[j];
+      if (t > lmax) {
+        lmax = t;
+        larg = tid * SAMPLE_SEG + j;
+      }
+    }
+  }
+  red[tid] = lmax;
+  redi[tid] = larg;
+  __syncthreads();
+  for (int s = SAMPLE_THREADS / 2; s > 0; s >>= 1) {
+    if (tid < s) {
+      const float o = red[tid + s];
+      const int oi = redi[tid + s];
+      if (o > red[tid] || (o == red[tid] && oi < redi[tid])) {
+        red[tid] = o;
+        redi[tid] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  const float gmax = red[0];
+  if (greedy) {
+    if (tid == 0) ids[p] = redi[0];
+    return;
+  }
+
+  // pass 3: weights + segment sums (sequential inside a segment)
+  if (tid < nseg) {
+    float* seg = tv + tid * (SAMPLE_SEG + 1);
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int j = 0; j < SAMPLE_SEG; ++j) {
+      const float w = exp_det(__fsub_rn(seg[j], gmax));
+      seg[j] = w;
+      acc = __fadd_rn(acc, w);
+    }
+    seg_sum[tid] = acc;
+  }
+  __syncthreads();
+  const int ngrp = nseg / SAMPLE_GRP;  // 16
+  if (tid < ngrp) {
+    float acc = 0.0f;
+    for (int j = 0; j < SAMPLE_GRP; ++j) acc = __fadd_rn(acc, seg_sum[tid * SAMPLE_GRP + j]);
+    grp_sum[tid] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float Z = 0.0f;
+    for (int g = 0; g < ngrp; ++g) Z = __fadd_rn(Z, grp_sum[g]);
+    const float target = __fmul_rn(uniforms[p], Z);
+    // descend: group -> segment -> code; `base` is the cdf value before the current block
+    float base = 0.0f;
+    int g = 0;
+    for (; g < ngrp - 1; ++g) {
+      const float nxt = __fadd_rn(base, grp_sum[g]);
+      if (nxt > target) break;
+      base = nxt;
+    }
+    int sgi = 0;
+    for (; sgi < SAMPLE_GRP - 1; ++sgi) {
+      const float nxt = __fadd_rn(base, seg_sum[g * SAMPLE_GRP + sgi]);
+      if (nxt > target) break;
+      base = nxt;
+    }
+    const int segi = g * SAMPLE_GRP + sgi;
+    const float* seg = tv + segi * (SAMPLE_SEG + 1);
+    int j = 0;
+    for (; j < SAMPLE_SEG - 1; ++j) {
+      const float nxt = __fadd_rn(base, seg[j]);
+      if (nxt > target) break;
+      base = nxt;
+    }
+    ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
+  }
+}
+
+}  // namespace ospo

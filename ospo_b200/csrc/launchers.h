@@ -1,0 +1,62 @@
+// Host-side launchers for the tcgen05 GEMM instantiations.  Each translation unit instantiates a
+// few (tile, operand-major, epilogue) combinations of gemm_sm100.cuh; abi.cu strings them together.
+// cta_group: 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile (tcgen05 cta_group::2).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ospo {
+
+struct LaunchCtx {
+  int num_sms;
+  int cta_group;  // 1 or 2
+  int group_m;    // rasterisation group (M-blocks)
+  cudaStream_t stream;
+};
+
+// every TU that contains kernels using mbar_wait owns a copy of the watchdog pointer
+void set_watchdog_fwd(uint32_t* dev_ptr);
+void set_watchdog_bwd(uint32_t* dev_ptr);
+void set_watchdog_decode(uint32_t* dev_ptr);
+void set_watchdog_debug(uint32_t* dev_ptr);
+
+// ---- forward (gemm_fwd.cu) ----
+// pre = bf16(x W1^T + b1), act = bf16(gelu(pre));  x [rows,H], w1 [E,H]
+int launch_gemm1_bias_gelu(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w1, const float* b1,
+                           __nv_bfloat16* pre /*nullable*/, __nv_bfloat16* act, int rows, int H, int E);
+// logits = bf16(act W2^T + b2) (+ LSE partials, target gather);  act [rows,E], w2 [V,E]
+int launch_gemm2_logits_lse(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
+                            __nv_bfloat16* logits /*nullable*/, const int64_t* labels, float2* part,
+                            float* rowsum_part /*nullable*/, float* tgt, int rows, int E, int V);
+int gemm2_num_n_tiles(int V);
+// plain logits = bf16(act W2^T + b2)
+int launch_gemm2_logits(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
+                        __nv_bfloat16* logits, int64_t ld, int rows, int E, int V);
+
+// ---- backward (gemm_bwd.cu) ----
+// dpre = bf16( bf16(dlogits W2) * gelu'(pre) );  dlogits [rows,V], w2 [V,E]
+int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* dlogits, const __nv_bfloat16* w2,
+                         const __nv_bfloat16* pre, __nv_bfloat16* dpre, int rows, int E, int V);
+// dW[out_dim, in_dim] (fp32) = dY^T X;  dY [rows,out_dim], X [rows,in_dim]
+int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw, int rows, int out_dim,
+                 int in_dim);
+// dX[rows, in_dim] (bf16) = dY W;  dY [rows,out_dim], W [out_dim,in_dim]
+int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx, int rows,
+                 int out_dim, int in_dim);
+
+// ---- decode, swap-AB (gemm_decode.cu) ----
+// act[n, e] = bf16(gelu(bf16(W1 h^T + b1)));  h [n,H] with n = 2P small
+int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
+                        __nv_bfloat16* act, int n, int H, int E);
+// logits[n, v] = bf16(W2 act^T + b2)
+int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
+                        __nv_bfloat16* logits, int n, int E, int V);
+
+// ---- debug / validation (gemm_debug.cu) ----
+// out[M,N] fp32 = A B^T for one engine variant; see abi.cu for the variant table
+int launch_gemm_debug(const LaunchCtx& c, int variant, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,
+                      int64_t ldb, float* out, int64_t ldo, int M, int N, int K);
+
+}  // namespace ospo

@@ -279,17 +279,19 @@ constexpr int SAMPLE_GRP = 32;   // segments per group
 // Deterministic fp32 exp for x <= 0: every step is a single IEEE-754 operation, so the C oracle
 // (compiled with -ffp-contract=off, using fmaf) is bit-identical.
 __device__ __forceinline__ float exp_det(float x) {
+  // n = rint(x log2 e); r = x - n ln2 (Cody-Waite, two fma); e^r by a degree-6 polynomial; scale by 2^n
   float y = __fmul_rn(x, 1.4426950408889634f);
   if (!(y >= -125.0f)) return 0.0f;
   const float n = rintf(y);
-  const float f = __fsub_rn(y, n);  // exact, |f| <= 0.5
-  float p = 1.5403530393381609e-04f;            // degree-6 polynomial for 2^f on [-0.5, 0.5]
-  p = __fmaf_rn(p, f, 1.3333558146428443e-03f);
-  p = __fmaf_rn(p, f, 9.6181291076284772e-03f);
-  p = __fmaf_rn(p, f, 5.5504108664821580e-02f);
-  p = __fmaf_rn(p, f, 2.4022650695910071e-01f);
-  p = __fmaf_rn(p, f, 6.9314718055994531e-01f);
-  p = __fmaf_rn(p, f, 1.0f);
+  float r = __fmaf_rn(n, -0.693145751953125f, x);
+  r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
+  float p = 1.3888888888888889e-03f;
+  p = __fmaf_rn(p, r, 8.3333333333333332e-03f);
+  p = __fmaf_rn(p, r, 4.1666666666666664e-02f);
+  p = __fmaf_rn(p, r, 1.6666666666666666e-01f);
+  p = __fmaf_rn(p, r, 0.5f);
+  p = __fmaf_rn(p, r, 1.0f);
+  p = __fmaf_rn(p, r, 1.0f);
   const float scale = __int_as_float((static_cast<int>(n) + 127) << 23);  // 2^n, normal since n >= -125
   return __fmul_rn(p, scale);
 }

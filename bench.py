@@ -1,0 +1,452 @@
+"""bench.py -- OSPO image-token head on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one SimPO head forward+backward (BASELINE.json configs[1]: Janus-Pro-7B-shaped gen_head,
+64 preference pairs x 576 image tokens per GPU, bf16, head trainable) over one batch of synthetic
+hidden states.  N > 1 (torchrun, one rank per GPU) shards pairs across ranks -- 64 pairs per GPU, i.e.
+configs[2]'s 512 pairs at N = 8 -- and all-reduces the flat fp32 head-weight gradient over NCCL
+(weak scaling).  Rank 0 prints ONE JSON line.
+
+  value      image-tokens/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        the same through FusedGenHead.simpo with HOST (pinned) inputs: every step copies its
+             hidden states + labels host->device and reads the loss back, copies overlapped with compute
+  roofline   dominant kernel (longest total time in the timed region), algorithmic flops / measured time
+  cpu_baseline   the oracle (torch CPU restatement of the reference path) on a bounded sample
+  cfg        secondary metric: BASELINE.json configs[3], 576 sequential CFG decode steps at P = 16
+
+``--impl reference`` times the reference's CPU path (the oracle port) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H7B, E7B, V = 4096, 4096, 16384
+T_IMG = 576
+PAIRS_PER_GPU = 64
+HP = dict(beta=10.0, gamma_beta_ratio=0.5, label_smoothing=0.0, sft_weight=0.0, loss_type="sigmoid")
+METRIC = "simpo_head_fwd_bwd_image_tokens_per_s"
+UNIT = "image-tokens/s"
+WORKLOAD = ("configs[1]: Janus-Pro-7B-shaped gen_head (H=E=4096, V=16384) SimPO fwd+bwd, 64 synthetic pairs x 576 "
+            "tokens per GPU (73728 rows), bf16, head trainable")
+
+
+def flops_per_token(H, E, Vv):
+    return 6 * (H * E + E * Vv)   # fwd 2(HE+EV) + bwd 4(HE+EV)
+
+
+# -------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained"),
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference) -- used for cpu_baseline and for --impl reference
+# -------------------------------------------------------------------------------------------------
+def cpu_simpo_sample(pairs: int, reps: int):
+    import torch
+
+    from oracle import head_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    head = O.make_head(H7B, E7B, V, seed=1235)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(pairs, T_IMG, 1, H7B, V, seed=1236)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.simpo_step(head, hc, hr, lc, lr, backward=True, **HP)
+        times.append(time.perf_counter() - t0)
+    tokens = 2 * pairs * T_IMG
+    return tokens, times, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs = 4
+    tokens, times, cores = cpu_simpo_sample(pairs, args.warmup + args.steps)
+    timed = times[args.warmup:] or times
+    ms = 1e3 * sum(timed) / len(timed)
+    value = tokens / (ms / 1e3)
+    sample = (f"{pairs} pairs x {T_IMG} tokens ({tokens} rows) of the 7B-shaped head, fp32 torch CPU oracle port of the "
+              f"reference path, fwd+bwd, {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# -------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours")
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU (default = configs[1])")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-cfg", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    from ospo_b200 import FusedGenHead, _abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 (no CPU path for the product arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    peaks = load_peaks()
+    B = args.pairs
+    rows = 2 * B * T_IMG
+    tokens_per_step_rank = rows
+    L = 1   # one leading masked position so the label shift of train.py:385-386 is exercised
+
+    # ---- synthetic inputs (seeded; weights identical on every rank, data differs per rank) ------
+    torch.manual_seed(1235)
+
+    class P:
+        n_embed, image_token_embed, image_token_size = H7B, E7B, V
+
+    head = FusedGenHead(P).to(dev).to(torch.bfloat16)        # default nn.Linear init under the seed
+    gen = torch.Generator(device=dev).manual_seed(1236 + rank)
+    hidden = torch.randn(2 * B, L + T_IMG, H7B, generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    ids = torch.randint(0, V, (2 * B, T_IMG), generator=gen, device=dev)
+    labels = torch.cat([torch.full((2 * B, L), -100, dtype=torch.long, device=dev), ids], 1)
+    span = (L - 1, L - 1 + T_IMG)
+
+    def step(h, lab):
+        head.zero_grad(set_to_none=True)
+        hh = h.detach().requires_grad_(True)
+        out = head.simpo(hh, lab, image_span=span, process_group=group, **HP)
+        out.loss.backward()
+        return out.loss, hh.grad
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step(hidden, labels)
+    sync_all()
+    _abi.profile_enable(True)
+    _abi.profile_read()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _abi.load().ospo_head_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        loss, _ = step(hidden, labels)
+    ev1.record()
+    sync_all()
+    t_wall1 = time.time()
+    launches = int(_abi.load().ospo_head_launch_count() - launches0)
+    prof = _abi.profile_read()
+    _abi.profile_enable(False)
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t)
+    value = world * tokens_per_step_rank / (ms_step / 1e3)
+    loss_val = float(loss)
+
+    # ---- per-kernel table + roofline of the dominant kernel ---------------------------------------
+    HE, EV = H7B * E7B, E7B * V
+    kflops = {  # algorithmic flops per launch
+        "gemm1_bias_gelu": 2 * rows * HE, "gemm2_logits_lse": 2 * rows * EV, "dact_gelu_bwd": 2 * rows * EV,
+        "wgrad_w2": 2 * rows * EV, "wgrad_w1": 2 * rows * HE, "dgrad_x": 2 * rows * HE,
+    }
+    kernels = {}
+    for name, (tot_ms, n) in prof.items():
+        per = tot_ms / max(n, 1)
+        ent = {"ms_per_launch": per, "launch_groups": n, "share_of_step": (tot_ms / args.steps) / ms_step}
+        if name in kflops:
+            ent["tflops"] = kflops[name] / per / 1e9
+            ent["frac_of_peak"] = ent["tflops"] / peaks["tf_burst"]
+        kernels[name] = ent
+    gemm_names = [k for k in kernels if k in kflops]
+    dominant = max(gemm_names, key=lambda k: kernels[k]["ms_per_launch"]) if gemm_names else None
+    step_tflops = tokens_per_step_rank * flops_per_token(H7B, E7B, V) / (ms_step / 1e3) / 1e12
+    roofline = None
+    if dominant:
+        roofline = {
+            "bound": "tensor", "kernel": dominant, "achieved": kernels[dominant]["tflops"], "peak": peaks["tf_burst"],
+            "unit": "TFLOP/s", "frac": kernels[dominant]["tflops"] / peaks["tf_burst"], "traffic": None,
+            "peak_source": peaks["source"] + " bf16_tflops (burst); sustained " + str(peaks["tf_sustained"]),
+            "step_achieved_tflops": step_tflops, "step_frac": step_tflops / peaks["tf_burst"],
+            "note": "achieved = algorithmic flops of that launch / CUDA-event time around it, measured in the timed "
+                    "region; step_* = 6(HE+EV) flop per image token over the whole fwd+bwd step",
+        }
+
+    # ---- end-to-end: host buffers through the public API -------------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        NB = 2
+        host_h = [torch.empty(hidden.shape, dtype=torch.bfloat16).pin_memory() for _ in range(NB)]
+        host_l = [torch.empty(labels.shape, dtype=torch.long).pin_memory() for _ in range(NB)]
+        for b in range(NB):
+            host_h[b].copy_(hidden.cpu())
+            host_l[b].copy_(labels.cpu())
+        dev_h = [torch.empty_like(hidden) for _ in range(NB)]
+        dev_l = [torch.empty_like(labels) for _ in range(NB)]
+        host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(NB)]
+        freed = [torch.cuda.Event() for _ in range(NB)]
+        comp = torch.cuda.current_stream()
+
+        def h2d(i):
+            b = i % NB
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[b])
+                dev_h[b].copy_(host_h[b], non_blocking=True)
+                dev_l[b].copy_(host_l[b], non_blocking=True)
+                ready[b].record(copy_stream)
+
+        def run_e2e(n):
+            for b in range(NB):
+                freed[b].record(comp)
+            h2d(0)
+            for i in range(n):
+                b = i % NB
+                if i + 1 < n:
+                    h2d(i + 1)                      # next step's inputs stream in while this step computes
+                comp.wait_event(ready[b])
+                l, _ = step(dev_h[b], dev_l[b])
+                freed[b].record(comp)
+                host_loss.copy_(l.detach().reshape(1), non_blocking=True)   # device -> host read of the result
+            comp.synchronize()
+
+        run_e2e(2)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw0 = time.perf_counter()
+        e0.record()
+        run_e2e(args.steps)
+        e1.record()
+        sync_all()
+        wall_ms = (time.perf_counter() - tw0) * 1e3 / args.steps
+        ms_e2e = max(e0.elapsed_time(e1) / args.steps, 0.0)
+        ms_e2e = max(ms_e2e, wall_ms * 0.0)   # device time; wall clock reported beside it
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t)
+        e2e = {"value": world * tokens_per_step_rank / (ms_e2e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": hidden.numel() * 2 + labels.numel() * 8, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms,
+               "api": "FusedGenHead.simpo(hidden, labels) + loss.backward(); pinned host inputs, double-buffered H2D"}
+        del dev_h, dev_l, host_h, host_l
+
+    # ---- secondary: CFG decode (configs[3]) ---------------------------------------------------------
+    cfg = None
+    if rank == 0 and not args.skip_cfg:
+        cfg = bench_cfg(head, dev, peaks)
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        pairs = 4
+        tokens, times, cores = cpu_simpo_sample(pairs, 2)
+        best = min(times)
+        cpu = {"value": tokens / best, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{pairs} pairs x {T_IMG} tokens ({tokens} rows) of the same 7B-shaped head, fp32 torch CPU "
+                         f"oracle (port of the reference path), fwd+bwd, best of 2, {cores} threads"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "global_pairs": B * world, "rows_per_gpu": rows,
+                       "H": H7B, "E": E7B, "V": V, "parallelism": f"dp{world}: pairs batch-sharded, NCCL all-reduce of "
+                       "the flat fp32 head gradient (83.9M elements)" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (604 MB hidden states + 2.4 GB bf16 logits spill per step)",
+                       "cta_group": _abi.load().ospo_head_set_cta_group(0), "loss": loss_val},
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+            "cpu_baseline": cpu, "cfg": cfg,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_cfg(head, dev, peaks):
+    """configs[3]: P = 16 pairs (32 CFG rows), cfg_weight 5, temperature 1, 576 sequential decode steps of
+    gen_head + merge + sample.  The 576 steps are captured in one CUDA graph (the loop is launch-bound
+    otherwise); weights are re-read from HBM every step because two weight copies alternate and each step
+    also streams its own hidden-state slab."""
+    import torch
+
+    from ospo_b200 import cfg_merge_sample, ops
+
+    P, steps = 16, T_IMG
+    p = head._kernel_params()
+    # a second copy of the weights so consecutive steps cannot hit the previous step's lines in L2
+    alt = type(p)(p.w1.clone(), p.b1.clone(), p.w2.clone(), p.b2.clone())
+    gen = torch.Generator(device=dev).manual_seed(1238)
+    h = torch.randn(steps, 2 * P, H7B, generator=gen, device=dev).to(torch.bfloat16)
+    u = torch.rand(steps, P, generator=gen, device=dev)
+    ids_out = torch.empty(steps, P, dtype=torch.int64, device=dev)
+
+    def run_steps():
+        for i in range(steps):
+            w = p if (i & 1) == 0 else alt
+            ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
+            ids_out[i].copy_(ids)
+
+    run_steps()
+    torch.cuda.synchronize()
+    result = {}
+    # eager (one launch group per step)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps()
+    e1.record()
+    torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1)
+    # CUDA graph of the whole 576-step loop
+    graph_ms = None
+    try:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            run_steps()
+        torch.cuda.current_stream().wait_stream(s)
+        gobj = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gobj):
+            run_steps()
+        gobj.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            gobj.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_ms = e0.elapsed_time(e1) / 3
+    except Exception as ex:  # graph capture is an optimisation, not a requirement
+        result["graph_error"] = repr(ex)[:200]
+    best_ms = graph_ms if graph_ms is not None else eager_ms
+    step_bytes = 2 * (H7B * E7B + E7B * V) + 4 * (E7B + V) + 2 * 2 * P * H7B + 4 * P + 8 * P
+    us_step = best_ms * 1e3 / steps
+    result.update({
+        "workload": "configs[3]: P=16 cond/uncond pairs, cfg_weight=5, temperature=1, 576 decode steps, 7B-shaped head",
+        "tokens_per_s": steps * P / (best_ms / 1e3), "us_per_step": us_step,
+        "eager_us_per_step": eager_ms * 1e3 / steps, "graph_us_per_step": None if graph_ms is None else graph_ms * 1e3 / steps,
+        "roofline": {"bound": "hbm", "achieved": step_bytes / (us_step * 1e-6) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": step_bytes / (us_step * 1e-6) / 1e9 / peaks["hbm"], "bytes_per_step": step_bytes,
+                     "traffic": None},
+    })
+    # merge + sample alone on supplied logits, all 576 steps in one launch (SURVEY §8d secondary metric)
+    lg = (torch.randn(steps, 2 * P, V, generator=gen, device=dev) * 3).to(torch.bfloat16)
+    for _ in range(3):
+        cfg_merge_sample(lg, 5.0, 1.0, uniforms=u)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        cfg_merge_sample(lg, 5.0, 1.0, uniforms=u)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    nbytes = lg.numel() * 2 + steps * P * 12
+    result["merge_sample_only"] = {"ms": ms, "tokens_per_s": steps * P / (ms / 1e3), "achieved_gbs": nbytes / ms / 1e6,
+                                   "frac_of_hbm_peak": nbytes / ms / 1e6 / peaks["hbm"], "bytes": nbytes}
+    return result
+
+
+if __name__ == "__main__":
+    main()

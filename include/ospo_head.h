@@ -175,6 +175,25 @@ OSPO_API const char* ospo_head_strerror(int status);
 OSPO_API int ospo_head_set_cta_group(int cta_group);
 /* rasterisation group size (M-blocks walked together); pass 0 to query */
 OSPO_API int ospo_head_set_group_m(int group_m);
+/* Per-kernel timing with CUDA events recorded on the caller's stream around each launch group (off by
+   default).  profile_read synchronises on the recorded events and returns, per OSPO_K_* id, the summed
+   milliseconds and the number of spans since the previous read. */
+#define OSPO_K_GEMM1 0          /* x W1^T + b1, GELU                      (tcgen05 GEMM, K/K)   */
+#define OSPO_K_GEMM2_LSE 1      /* act W2^T + b2, LSE partials, gather    (tcgen05 GEMM, K/K)   */
+#define OSPO_K_SCALAR_STAGE 2   /* lse merge, per-sequence reduce, SimPO scalars                  */
+#define OSPO_K_DLOGITS 3        /* row coefficients + softmax-minus-onehot producer + db2         */
+#define OSPO_K_DACT 4           /* dlogits W2, GELU'                      (tcgen05 GEMM, K/MN)  */
+#define OSPO_K_WGRAD2 5         /* dlogits^T act                          (tcgen05 GEMM, MN/MN) */
+#define OSPO_K_COLSUM 6         /* db1                                                            */
+#define OSPO_K_WGRAD1 7         /* dpre^T x                               (tcgen05 GEMM, MN/MN) */
+#define OSPO_K_DGRAD 8          /* dpre W1                                (tcgen05 GEMM, K/MN)  */
+#define OSPO_K_GEMM2_PLAIN 9    /* act W2^T + b2 -> logits                                         */
+#define OSPO_K_DECODE_GEMM1 10  /* swap-AB W1 h^T, GELU                                            */
+#define OSPO_K_DECODE_GEMM2 11  /* swap-AB W2 act^T                                                */
+#define OSPO_K_SAMPLER 12       /* CFG merge + softmax + inverse-CDF sample                        */
+#define OSPO_K_COUNT 13
+OSPO_API int ospo_head_profile_enable(int enable);
+OSPO_API int ospo_head_profile_read(float* total_ms, int32_t* counts, int32_t n);
 /* number of kernels launched by this library since load (the bench's gpu_launches counter) */
 OSPO_API uint64_t ospo_head_launch_count(void);
 /* 6 x u32 watchdog record written by a kernel whose mbarrier wait expired (host pointer, may be NULL) */

@@ -119,6 +119,8 @@ EXPORTS = (
     "ospo_head_strerror",
     "ospo_head_set_cta_group",
     "ospo_head_set_group_m",
+    "ospo_head_profile_enable",
+    "ospo_head_profile_read",
     "ospo_head_launch_count",
     "ospo_head_watchdog_record_host",
     "ospo_head_gemm_debug",
@@ -167,6 +169,10 @@ def load() -> C.CDLL:
     lib.ospo_head_set_cta_group.restype = C.c_int
     lib.ospo_head_set_group_m.argtypes = [C.c_int]
     lib.ospo_head_set_group_m.restype = C.c_int
+    lib.ospo_head_profile_enable.argtypes = [C.c_int]
+    lib.ospo_head_profile_enable.restype = C.c_int
+    lib.ospo_head_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]
+    lib.ospo_head_profile_read.restype = C.c_int
     lib.ospo_head_launch_count.argtypes = []
     lib.ospo_head_launch_count.restype = C.c_uint64
     lib.ospo_head_watchdog_record_host.argtypes = []
@@ -194,6 +200,24 @@ def workspace_bytes(rows: int, hidden: int, embed: int, vocab: int, num_seqs: in
     shape = Shape(rows, hidden, embed, vocab, num_seqs)
     check(load().ospo_head_workspace_bytes(C.byref(shape), C.byref(out)), "ospo_head_workspace_bytes")
     return int(out.value)
+
+
+KERNEL_NAMES = ("gemm1_bias_gelu", "gemm2_logits_lse", "scalar_stage", "dlogits_producer", "dact_gelu_bwd",
+                "wgrad_w2", "colsum_db1", "wgrad_w1", "dgrad_x", "gemm2_logits_plain", "decode_gemm1",
+                "decode_gemm2", "cfg_merge_sample")
+
+
+def profile_enable(on: bool) -> None:
+    load().ospo_head_profile_enable(int(on))
+
+
+def profile_read() -> dict:
+    """{kernel name: (total_ms, spans)} since the previous read (synchronises on the recorded events)"""
+    n = len(KERNEL_NAMES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int32 * n)()
+    check(load().ospo_head_profile_read(ms, cnt, n), "ospo_head_profile_read")
+    return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
 
 
 def watchdog_record() -> list[int] | None:

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "head_kernels.cuh"
 #include "launchers.h"
@@ -18,14 +19,50 @@ struct Runtime {
   int status = OSPO_OK;
   int device = -1;
   int num_sms = 0;
-  int cta_group = 1;
-  int group_m = 8;
+  int cta_group = 2;
+  int group_m = 16;
   uint32_t* wd_host = nullptr;
   uint32_t* wd_dev = nullptr;
 };
 Runtime g_rt;
 std::mutex g_mu;
 std::atomic<uint64_t> g_launches{0};
+
+// ---- optional per-kernel timing (CUDA events on the caller's stream) -------------------------------
+struct Span {
+  int kid;
+  cudaEvent_t e0, e1;
+};
+bool g_profile = false;
+std::vector<Span> g_spans;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// RAII: brackets one kernel launch with events when profiling is on
+struct KernelSpan {
+  cudaStream_t st;
+  int idx = -1;
+  KernelSpan(cudaStream_t s, int kid) : st(s) {
+    if (!g_profile) return;
+    Span sp{kid, take_event(), take_event()};
+    cudaEventRecord(sp.e0, st);
+    g_spans.push_back(sp);
+    idx = static_cast<int>(g_spans.size()) - 1;
+  }
+  ~KernelSpan() {
+    if (idx >= 0) cudaEventRecord(g_spans[idx].e1, st);
+  }
+};
 
 int runtime_init() {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -149,17 +186,25 @@ int check_ws(const ospo_head_shape& s, void* ws, size_t bytes, Workspace* out) {
 int logps_forward(const ospo_simpo_args* a, const Workspace& w, cudaStream_t st) {
   const ospo_head_shape& s = a->shape;
   const LaunchCtx c = make_ctx(st);
-  int rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
-                                         static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1,
-                                         static_cast<__nv_bfloat16*>(a->pre), static_cast<__nv_bfloat16*>(a->act),
-                                         s.rows, s.hidden, s.embed));
+  int rc;
+  {
+    KernelSpan ks(st, OSPO_K_GEMM1);
+    rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
+                                       static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1,
+                                       static_cast<__nv_bfloat16*>(a->pre), static_cast<__nv_bfloat16*>(a->act),
+                                       s.rows, s.hidden, s.embed));
+  }
   if (rc) return rc;
-  rc = map_rc(launch_gemm2_logits_lse(c, static_cast<const __nv_bfloat16*>(a->act),
-                                      static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
-                                      static_cast<__nv_bfloat16*>(a->logits), a->labels, w.part, w.rowsum_part, w.tgt,
-                                      s.rows, s.embed, s.vocab));
+  {
+    KernelSpan ks(st, OSPO_K_GEMM2_LSE);
+    rc = map_rc(launch_gemm2_logits_lse(c, static_cast<const __nv_bfloat16*>(a->act),
+                                        static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
+                                        static_cast<__nv_bfloat16*>(a->logits), a->labels, w.part, w.rowsum_part,
+                                        w.tgt, s.rows, s.embed, s.vocab));
+  }
   if (rc) return rc;
   const int num_n = gemm2_num_n_tiles(s.vocab);
+  KernelSpan ks(st, OSPO_K_SCALAR_STAGE);
   lse_finalize_kernel<<<(s.rows + 255) / 256, 256, 0, st>>>(w.part, w.rowsum_part, w.tgt, s.rows, num_n, a->row_lse,
                                                             a->row_logps, w.row_logit_sum);
   if ((rc = check_launch())) return rc;
@@ -187,41 +232,54 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   if (!a->pre || !a->act || !a->logits || !a->row_lse || !a->grad_seq) return OSPO_ERR_NULL;
   const LaunchCtx c = make_ctx(st);
   int rc;
-  row_coef_kernel<<<s.num_seqs, 128, 0, st>>>(a->grad_seq, a->seq_offsets, a->average_log_prob, a->grad_loss,
-                                              sft_coef, num_sft_seqs, w.row_coef);
-  if ((rc = check_launch())) return rc;
-
   const size_t VE = static_cast<size_t>(s.vocab) * s.embed, EH = static_cast<size_t>(s.embed) * s.hidden;
   float* dW2 = a->flat_grads;
   float* dW1 = a->flat_grads ? a->flat_grads + VE : nullptr;
   float* db2 = a->flat_grads ? a->flat_grads + VE + EH : nullptr;
   float* db1 = a->flat_grads ? db2 + s.vocab : nullptr;
-  if (a->flat_grads) {
-    if (cudaMemsetAsync(db2, 0, sizeof(float) * (static_cast<size_t>(s.vocab) + s.embed), st) != cudaSuccess)
-      return OSPO_ERR_CUDA;
-  }
   __nv_bfloat16* dlogits = static_cast<__nv_bfloat16*>(a->logits);
+  __nv_bfloat16* dpre = w.rows_by_e;
   {
+    KernelSpan ks(st, OSPO_K_DLOGITS);
+    row_coef_kernel<<<s.num_seqs, 128, 0, st>>>(a->grad_seq, a->seq_offsets, a->average_log_prob, a->grad_loss,
+                                                sft_coef, num_sft_seqs, w.row_coef);
+    if ((rc = check_launch())) return rc;
+    if (a->flat_grads) {
+      if (cudaMemsetAsync(db2, 0, sizeof(float) * (static_cast<size_t>(s.vocab) + s.embed), st) != cudaSuccess)
+        return OSPO_ERR_CUDA;
+    }
     dim3 grid((s.vocab + 1023) / 1024, (s.rows + DL_ROWS_PER_BLOCK - 1) / DL_ROWS_PER_BLOCK);
     dlogits_kernel<<<grid, 128, 0, st>>>(dlogits, s.vocab, a->labels, a->row_lse, w.row_coef, s.rows, s.vocab, db2);
     if ((rc = check_launch())) return rc;
   }
-  __nv_bfloat16* dpre = w.rows_by_e;
-  rc = map_rc(launch_dact_gelu_bwd(c, dlogits, static_cast<const __nv_bfloat16*>(a->w.w2),
-                                   static_cast<const __nv_bfloat16*>(a->pre), dpre, s.rows, s.embed, s.vocab));
+  {
+    KernelSpan ks(st, OSPO_K_DACT);
+    rc = map_rc(launch_dact_gelu_bwd(c, dlogits, static_cast<const __nv_bfloat16*>(a->w.w2),
+                                     static_cast<const __nv_bfloat16*>(a->pre), dpre, s.rows, s.embed, s.vocab));
+  }
   if (rc) return rc;
   if (a->flat_grads) {
     // dW2 first: it is the largest block of the flat gradient, so a caller that overlaps the
     // all-reduce with the remaining GEMMs can start on it earliest.
-    rc = map_rc(launch_wgrad(c, dlogits, static_cast<const __nv_bfloat16*>(a->act), dW2, s.rows, s.vocab, s.embed));
+    {
+      KernelSpan ks(st, OSPO_K_WGRAD2);
+      rc = map_rc(launch_wgrad(c, dlogits, static_cast<const __nv_bfloat16*>(a->act), dW2, s.rows, s.vocab, s.embed));
+    }
     if (rc) return rc;
-    dim3 grid((s.embed + 1023) / 1024, (s.rows + DL_ROWS_PER_BLOCK - 1) / DL_ROWS_PER_BLOCK);
-    colsum_bf16_kernel<<<grid, 128, 0, st>>>(dpre, s.embed, s.rows, s.embed, db1);
-    if ((rc = check_launch())) return rc;
-    rc = map_rc(launch_wgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden));
+    {
+      KernelSpan ks(st, OSPO_K_COLSUM);
+      dim3 grid((s.embed + 1023) / 1024, (s.rows + DL_ROWS_PER_BLOCK - 1) / DL_ROWS_PER_BLOCK);
+      colsum_bf16_kernel<<<grid, 128, 0, st>>>(dpre, s.embed, s.rows, s.embed, db1);
+      if ((rc = check_launch())) return rc;
+    }
+    {
+      KernelSpan ks(st, OSPO_K_WGRAD1);
+      rc = map_rc(launch_wgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden));
+    }
     if (rc) return rc;
   }
   if (a->dx) {
+    KernelSpan ks(st, OSPO_K_DGRAD);
     rc = map_rc(launch_dgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->w.w1), static_cast<__nv_bfloat16*>(a->dx),
                              s.rows, s.embed, s.hidden));
     if (rc) return rc;
@@ -253,10 +311,14 @@ int ospo_head_logits(const ospo_head_args* a, ospo_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const LaunchCtx c = make_ctx(st);
   const ospo_head_shape& s = a->shape;
-  rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
-                                     static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1, nullptr, w.rows_by_e, s.rows,
-                                     s.hidden, s.embed));
+  {
+    KernelSpan ks(st, OSPO_K_GEMM1);
+    rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
+                                       static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1, nullptr, w.rows_by_e,
+                                       s.rows, s.hidden, s.embed));
+  }
   if (rc) return rc;
+  KernelSpan ks(st, OSPO_K_GEMM2_PLAIN);
   return map_rc(launch_gemm2_logits(c, w.rows_by_e, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
                                     static_cast<__nv_bfloat16*>(a->logits), s.vocab, s.rows, s.embed, s.vocab));
 }
@@ -294,6 +356,7 @@ int ospo_head_simpo_fwd(const ospo_simpo_args* a, ospo_stream_t stream) {
   hp.sft_weight = a->sft_weight;
   hp.loss_type = a->loss_type;
   hp.vocab = a->shape.vocab;
+  KernelSpan ks(st, OSPO_K_SCALAR_STAGE);
   simpo_scalar_kernel<<<1, 256, 0, st>>>(a->seq_logps, w.seq_sum, w.seq_logit_sum, a->seq_offsets,
                                          a->shape.num_seqs / 2, hp, a->losses, a->chosen_rewards, a->rejected_rewards,
                                          a->grad_seq, a->scalars);
@@ -324,6 +387,7 @@ static int launch_sampler(const ospo_cfg_args* a, int pairs, cudaStream_t st) {
       return OSPO_ERR_CUDA;
     attr_set = true;
   }
+  KernelSpan ks(st, OSPO_K_SAMPLER);
   cfg_merge_sample_kernel<<<pairs, SAMPLE_THREADS, smem, st>>>(static_cast<const __nv_bfloat16*>(a->logits), V, V,
                                                               a->cfg_weight, a->temperature, a->merge_mode,
                                                               a->uniforms, a->greedy, a->ids, a->merged);
@@ -354,12 +418,18 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const LaunchCtx c = make_ctx(st);
   const ospo_head_shape& s = a->shape;
-  rc = map_rc(launch_decode_gemm1(c, static_cast<const __nv_bfloat16*>(a->h),
-                                  static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1, w.rows_by_e, s.rows, s.hidden,
-                                  s.embed));
+  {
+    KernelSpan ks(st, OSPO_K_DECODE_GEMM1);
+    rc = map_rc(launch_decode_gemm1(c, static_cast<const __nv_bfloat16*>(a->h),
+                                    static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1, w.rows_by_e, s.rows,
+                                    s.hidden, s.embed));
+  }
   if (rc) return rc;
-  rc = map_rc(launch_decode_gemm2(c, w.rows_by_e, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
-                                  static_cast<__nv_bfloat16*>(a->logits), s.rows, s.embed, s.vocab));
+  {
+    KernelSpan ks(st, OSPO_K_DECODE_GEMM2);
+    rc = map_rc(launch_decode_gemm2(c, w.rows_by_e, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
+                                    static_cast<__nv_bfloat16*>(a->logits), s.rows, s.embed, s.vocab));
+  }
   if (rc) return rc;
   return launch_sampler(a, s.rows / 2, st);
 }
@@ -390,6 +460,36 @@ int ospo_head_set_group_m(int group_m) {
   runtime_init();
   if (group_m > 0) g_rt.group_m = group_m;
   return g_rt.group_m;
+}
+
+int ospo_head_profile_enable(int enable) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_profile = enable != 0;
+  return g_profile ? 1 : 0;
+}
+
+int ospo_head_profile_read(float* total_ms, int32_t* counts, int32_t n) {
+  // synchronises on the recorded events; accumulates per kernel id, then recycles the events
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int i = 0; i < n; ++i) {
+    if (total_ms) total_ms[i] = 0.0f;
+    if (counts) counts[i] = 0;
+  }
+  int rc = OSPO_OK;
+  for (const Span& sp : g_spans) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(sp.e1) != cudaSuccess || cudaEventElapsedTime(&ms, sp.e0, sp.e1) != cudaSuccess) {
+      rc = OSPO_ERR_CUDA;
+      cudaGetLastError();
+    } else if (sp.kid >= 0 && sp.kid < n) {
+      if (total_ms) total_ms[sp.kid] += ms;
+      if (counts) counts[sp.kid] += 1;
+    }
+    g_event_pool.push_back(sp.e0);
+    g_event_pool.push_back(sp.e1);
+  }
+  g_spans.clear();
+  return rc;
 }
 
 uint64_t ospo_head_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

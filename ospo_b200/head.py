@@ -1,0 +1,315 @@
+"""``FusedGenHead`` -- drop-in replacement for Janus-Pro's ``vision_head`` (the ``gen_head`` module).
+
+Reference: ``janus/models/modeling_vlm.py:36-51`` (module), ``:54-70, 210-212`` (class registry /
+construction), consumers ``ospo/wrapper/train.py:345-445`` (SimPO) and
+``ospo/wrapper/image_generation.py:156-164`` (CFG merge + sample).
+
+The parameters keep the reference names and ``[out, in]`` layouts
+(``output_mlp_projector.{weight,bias}``, ``vision_head.{weight,bias}``) so HF / Lightning checkpoints
+load with ``strict=True``.  All compute runs in the sm_100a library behind ``include/ospo_head.h``;
+on anything else the calls raise.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _abi, ops
+
+IGNORE_INDEX = -100  # tokenizer.label_pad_token_id, configs/step5.yaml:73
+
+
+class SimpoOutput(NamedTuple):
+    loss: torch.Tensor               # scalar, differentiable          train.py:419 (+ :428)
+    chosen_logps: torch.Tensor       # [B]                             train.py:364
+    rejected_logps: torch.Tensor     # [B]                             train.py:365
+    losses: torch.Tensor             # [B]                             train.py:329-334
+    chosen_rewards: torch.Tensor     # [B]                             train.py:339
+    rejected_rewards: torch.Tensor   # [B]                             train.py:340
+    per_token_logps: torch.Tensor    # [rows]  log-prob of each unmasked image token
+    metrics: dict                    # 0-d device tensors, keys as logged at train.py:432-443
+
+
+def _rows_from_labels(hidden: torch.Tensor, labels: torch.Tensor, ignore_index: int,
+                      image_span: Optional[Tuple[int, int]]):
+    """Apply the shift of get_batch_logps (train.py:385-387) and keep only the unmasked rows.
+
+    hidden [S, L, H], labels [S, L]  ->  x_rows [N, H] (differentiable view/copy of hidden),
+    targets [N] int64, seq_offsets [S+1] int64 (device).
+    ``image_span=(start, stop)`` promises that exactly positions start..stop-1 of the *shifted* sequence are
+    unmasked in every sequence (the OSPO layout: L text positions then 576 image tokens); it avoids the
+    device->host sync of a data-dependent gather.
+    """
+    S, L, H = hidden.shape
+    lab = labels[:, 1:]
+    hid = hidden[:, :-1, :]
+    if image_span is not None:
+        a, b = image_span
+        x_rows = hid[:, a:b, :].reshape(-1, H)
+        targets = lab[:, a:b].reshape(-1)
+        n = b - a
+        seq_off = torch.arange(0, (S + 1) * n, n, dtype=torch.int64, device=hidden.device)
+        return x_rows, targets.contiguous(), seq_off
+    mask = lab != ignore_index
+    counts = mask.sum(dim=1)
+    seq_off = torch.zeros(S + 1, dtype=torch.int64, device=hidden.device)
+    seq_off[1:] = torch.cumsum(counts, 0)
+    x_rows = hid[mask]          # [N, H], differentiable gather (one host sync for N)
+    targets = lab[mask]
+    return x_rows, targets.contiguous(), seq_off
+
+
+class _HeadParams(NamedTuple):
+    w1: torch.Tensor  # bf16 [E, H]
+    b1: torch.Tensor  # fp32 [E]
+    w2: torch.Tensor  # bf16 [V, E]
+    b2: torch.Tensor  # fp32 [V]
+
+
+class _SimpoFn(torch.autograd.Function):
+    """loss = SimPO(head(x_rows)); everything else is returned detached."""
+
+    @staticmethod
+    def forward(ctx, x_rows, W1, B1, W2, B2, head, targets, seq_off, hp, group):
+        p = head._kernel_params()
+        xb = x_rows.detach().to(torch.bfloat16).contiguous()
+        need_bwd = any(ctx.needs_input_grad[:5])   # grad mode is off inside forward(); ask autograd instead
+        beta, gbr, ls, sftw, lt = hp
+        (scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, grad_seq, pre, act, logits) = ops.simpo_fwd_impl(
+            xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, beta, gbr, ls, sftw, lt, need_bwd)
+        ctx.head, ctx.hp, ctx.group = head, hp, group
+        ctx.x_dtype = x_rows.dtype
+        ctx.need_dx = ctx.needs_input_grad[0]
+        ctx.need_dw = any(ctx.needs_input_grad[1:5])
+        ctx.param_dtypes = (W1.dtype, B1.dtype, W2.dtype, B2.dtype)
+        if need_bwd:
+            ctx.save_for_backward(xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, scalars, pre, act, logits, row_lse,
+                                  grad_seq)
+        loss = scalars[_abi.SC_LOSS].clone()
+        ctx.mark_non_differentiable(scalars, seq_logps, losses, crew, rrew, row_logps)
+        return loss, scalars, seq_logps, losses, crew, rrew, row_logps
+
+    @staticmethod
+    def backward(ctx, grad_loss, *_):
+        xb, w1, b1, w2, b2, targets, seq_off, scalars, pre, act, logits, row_lse, grad_seq = ctx.saved_tensors
+        head = ctx.head
+        H, E, V = head.n_embed, head.image_token_embed, head.image_token_size
+        flat = head._flat_grad_buffer() if ctx.need_dw else torch.empty(0, dtype=torch.float32, device=xb.device)
+        gs = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        dx = ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, True, ctx.hp[3], scalars, pre, act, logits,
+                               row_lse, grad_seq, gs, ctx.need_dx, flat, True)
+        gW1 = gB1 = gW2 = gB2 = None
+        if ctx.need_dw:
+            head._sync_flat_grads(flat, ctx.group)
+            dW2, dW1, db2, db1 = ops.split_flat_grads(flat, H, E, V)
+            d1, d2, d3, d4 = ctx.param_dtypes
+            # copies: .grad must never alias the reusable flat buffer
+            gW1, gB1, gW2, gB2 = (dW1.to(d1, copy=True), db1.to(d2, copy=True), dW2.to(d3, copy=True),
+                                  db2.to(d4, copy=True))
+        gx = dx.to(ctx.x_dtype) if ctx.need_dx else None
+        return gx, gW1, gB1, gW2, gB2, None, None, None, None, None
+
+
+class _LogpsFn(torch.autograd.Function):
+    """seq_logps = get_batch_logps(head(x_rows), targets)  (train.py:357-362), differentiable."""
+
+    @staticmethod
+    def forward(ctx, x_rows, W1, B1, W2, B2, head, targets, seq_off, average, group):
+        p = head._kernel_params()
+        xb = x_rows.detach().to(torch.bfloat16).contiguous()
+        need_bwd = any(ctx.needs_input_grad[:5])   # grad mode is off inside forward(); ask autograd instead
+        seq_logps, row_logps, row_lse, pre, act, logits = ops.logps_fwd_impl(
+            xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, average, need_bwd)
+        ctx.head, ctx.average, ctx.group = head, average, group
+        ctx.x_dtype = x_rows.dtype
+        ctx.need_dx = ctx.needs_input_grad[0]
+        ctx.need_dw = any(ctx.needs_input_grad[1:5])
+        ctx.param_dtypes = (W1.dtype, B1.dtype, W2.dtype, B2.dtype)
+        if need_bwd:
+            ctx.save_for_backward(xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, pre, act, logits, row_lse)
+        ctx.mark_non_differentiable(row_logps)
+        return seq_logps, row_logps
+
+    @staticmethod
+    def backward(ctx, grad_seq, _):
+        xb, w1, b1, w2, b2, targets, seq_off, pre, act, logits, row_lse = ctx.saved_tensors
+        head = ctx.head
+        H, E, V = head.n_embed, head.image_token_embed, head.image_token_size
+        dev = xb.device
+        flat = head._flat_grad_buffer() if ctx.need_dw else torch.empty(0, dtype=torch.float32, device=dev)
+        one = torch.ones(1, dtype=torch.float32, device=dev)
+        none = torch.empty(0, dtype=torch.float32, device=dev)
+        dx = ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, ctx.average, 0.0, none, pre, act, logits, row_lse,
+                               grad_seq.detach().to(torch.float32).contiguous(), one, ctx.need_dx, flat, False)
+        gW1 = gB1 = gW2 = gB2 = None
+        if ctx.need_dw:
+            head._sync_flat_grads(flat, ctx.group)
+            dW2, dW1, db2, db1 = ops.split_flat_grads(flat, H, E, V)
+            d1, d2, d3, d4 = ctx.param_dtypes
+            # copies: .grad must never alias the reusable flat buffer
+            gW1, gB1, gW2, gB2 = (dW1.to(d1, copy=True), db1.to(d2, copy=True), dW2.to(d3, copy=True),
+                                  db2.to(d4, copy=True))
+        gx = dx.to(ctx.x_dtype) if ctx.need_dx else None
+        return gx, gW1, gB1, gW2, gB2, None, None, None, None, None
+
+
+class FusedGenHead(torch.nn.Module):
+    """Linear(n_embed -> image_token_embed) -> exact GELU -> Linear(-> image_token_size), sm_100a only."""
+
+    def __init__(self, params):
+        super().__init__()
+        self.n_embed = int(params.n_embed)
+        self.image_token_embed = int(params.image_token_embed)
+        self.image_token_size = int(params.image_token_size)
+        # same sub-module names as the reference (modeling_vlm.py:39-45) => identical state-dict keys
+        self.output_mlp_projector = torch.nn.Linear(self.n_embed, self.image_token_embed)
+        self.vision_activation = torch.nn.GELU()
+        self.vision_head = torch.nn.Linear(self.image_token_embed, self.image_token_size)
+        self._cache_key = None
+        self._cache: Optional[_HeadParams] = None
+        self._flat: Optional[torch.Tensor] = None
+
+    # ---- construction helpers -------------------------------------------------------------------
+    @classmethod
+    def from_reference(cls, module: torch.nn.Module) -> "FusedGenHead":
+        """adopt the parameters of a reference ``vision_head`` instance (shares storage, keeps requires_grad)"""
+        lin1, lin2 = module.output_mlp_projector, module.vision_head
+
+        class _P:
+            n_embed = lin1.in_features
+            image_token_embed = lin1.out_features
+            image_token_size = lin2.out_features
+
+        new = cls(_P)
+        new.output_mlp_projector, new.vision_head = lin1, lin2
+        return new
+
+    # ---- parameter staging -------------------------------------------------------------------
+    def _kernel_params(self) -> _HeadParams:
+        """bf16 weights / fp32 biases as the kernels want them (cached until a parameter changes)"""
+        W1, B1 = self.output_mlp_projector.weight, self.output_mlp_projector.bias
+        W2, B2 = self.vision_head.weight, self.vision_head.bias
+        key = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in (W1, B1, W2, B2))
+        if key != self._cache_key:
+            if not W1.is_cuda:
+                raise _abi.OspoHeadError("FusedGenHead parameters must live on a B200 (no CPU path): call .cuda()")
+            with torch.no_grad():
+                self._cache = _HeadParams(
+                    W1.detach().to(torch.bfloat16).contiguous(), B1.detach().to(torch.float32).contiguous(),
+                    W2.detach().to(torch.bfloat16).contiguous(), B2.detach().to(torch.float32).contiguous())
+            self._cache_key = key
+        return self._cache
+
+    def _flat_grad_buffer(self) -> torch.Tensor:
+        n = ops.flat_grad_numel(self.n_embed, self.image_token_embed, self.image_token_size)
+        dev = self.vision_head.weight.device
+        if self._flat is None or self._flat.numel() != n or self._flat.device != dev:
+            self._flat = torch.empty(n, dtype=torch.float32, device=dev)
+        return self._flat
+
+    @staticmethod
+    def _sync_flat_grads(flat: torch.Tensor, group) -> None:
+        """DDP semantics (ospo/utils/train.py:26-28): average the head-weight gradients over the data-parallel
+        ranks -- one NCCL all-reduce over the contiguous fp32 buffer dW2|dW1|db2|db1."""
+        if group is None or not dist.is_initialized():
+            return
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
+
+    # ---- reference-compatible call: logits ---------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """``gen_head(hidden_states)`` -> logits [..., V] (bf16), materialised.  Inference path
+        (image_generation.py:156); for training use :meth:`logps` / :meth:`simpo`, which never
+        materialise the logits and carry the backward."""
+        if torch.is_grad_enabled() and (x.requires_grad or self.vision_head.weight.requires_grad):
+            raise _abi.OspoHeadError(
+                "FusedGenHead.forward materialises logits for inference only; call it under torch.no_grad() or use "
+                ".logps()/.simpo() for the differentiable fused path")
+        p = self._kernel_params()
+        lead = x.shape[:-1]
+        xb = x.reshape(-1, self.n_embed).to(torch.bfloat16).contiguous()
+        out = ops.linear_gelu_linear_impl(xb, p.w1, p.b1, p.w2, p.b2)
+        return out.view(*lead, self.image_token_size)
+
+    # ---- fused training paths ----------------------------------------------------------------
+    def logps(self, hidden: torch.Tensor, labels: torch.Tensor, average_log_prob: bool = True,
+              ignore_index: int = IGNORE_INDEX, image_span: Optional[Tuple[int, int]] = None,
+              process_group=None, return_per_token: bool = False):
+        """== ``get_batch_logps(gen_head(hidden), labels, average_log_prob)`` (train.py:357-362, 375-396)
+        hidden [S, L, H], labels [S, L] (unshifted, ``ignore_index`` on masked positions) -> [S] fp32."""
+        x_rows, targets, seq_off = _rows_from_labels(hidden, labels, ignore_index, image_span)
+        seq_logps, row_logps = _LogpsFn.apply(
+            x_rows, self.output_mlp_projector.weight, self.output_mlp_projector.bias, self.vision_head.weight,
+            self.vision_head.bias, self, targets, seq_off, bool(average_log_prob), process_group)
+        return (seq_logps, row_logps) if return_per_token else seq_logps
+
+    def simpo(self, hidden: torch.Tensor, labels: torch.Tensor, *, beta: float = 1.0, gamma_beta_ratio: float = 0.0,
+              label_smoothing: float = 0.0, loss_type: str = "sigmoid", sft_weight: float = 0.0,
+              ignore_index: int = IGNORE_INDEX, image_span: Optional[Tuple[int, int]] = None,
+              process_group=None) -> SimpoOutput:
+        """Fused ``concatenated_forward`` + ``simpo_loss`` + ``losses.mean()`` (train.py:345-372, 317-342, 419-430).
+        hidden [2B, L, H] = chosen sequences then rejected sequences (train.py:364-365), labels [2B, L]."""
+        if loss_type not in ("sigmoid", "hinge"):
+            raise ValueError(f"Unknown loss type: {loss_type}. Should be one of ['sigmoid', 'hinge']")  # train.py:336
+        lt = _abi.LOSS_SIGMOID if loss_type == "sigmoid" else _abi.LOSS_HINGE
+        x_rows, targets, seq_off = _rows_from_labels(hidden, labels, ignore_index, image_span)
+        hp = (float(beta), float(gamma_beta_ratio), float(label_smoothing), float(sft_weight), lt)
+        loss, scalars, seq_logps, losses, crew, rrew, row_logps = _SimpoFn.apply(
+            x_rows, self.output_mlp_projector.weight, self.output_mlp_projector.bias, self.vision_head.weight,
+            self.vision_head.bias, self, targets, seq_off, hp, process_group)
+        B = seq_logps.shape[0] // 2
+        metrics = {
+            "rewards/chosen": scalars[_abi.SC_REWARD_CHOSEN], "rewards/rejected": scalars[_abi.SC_REWARD_REJECTED],
+            "rewards/accuracies": scalars[_abi.SC_REWARD_ACC], "rewards/margins": scalars[_abi.SC_REWARD_MARGIN],
+            "logps/chosen": scalars[_abi.SC_LOGPS_CHOSEN], "logps/rejected": scalars[_abi.SC_LOGPS_REJECTED],
+            "logits/chosen": scalars[_abi.SC_LOGITS_CHOSEN], "logits/rejected": scalars[_abi.SC_LOGITS_REJECTED],
+            "sft_loss": scalars[_abi.SC_SFT_LOSS], "simpo_loss": scalars[_abi.SC_SIMPO_LOSS],
+        }
+        return SimpoOutput(loss, seq_logps[:B], seq_logps[B:], losses, crew, rrew, row_logps, metrics)
+
+    # ---- CFG decode step ---------------------------------------------------------------------
+    @torch.no_grad()
+    def cfg_sample(self, hidden_last: torch.Tensor, cfg_weight: float = 5.0, temperature: float = 1.0,
+                   uniforms: Optional[torch.Tensor] = None, greedy: bool = False, merge_mode: str = "bf16",
+                   return_logits: bool = False):
+        """One decode step (image_generation.py:156-164): hidden_last [2P, H] with row 2k conditional and
+        2k+1 unconditional -> next_token ids [P] int64.  ``uniforms`` [P] fp32 in [0,1) drive the inverse-CDF
+        draw (None => drawn from torch's CUDA generator); ``greedy`` takes the arg-max instead."""
+        p = self._kernel_params()
+        h = hidden_last.to(torch.bfloat16).contiguous()
+        P = h.shape[0] // 2
+        if greedy:
+            u = torch.empty(0, dtype=torch.float32, device=h.device)
+        elif uniforms is None:
+            u = torch.rand(P, dtype=torch.float32, device=h.device)
+        else:
+            u = uniforms.to(torch.float32).contiguous()
+        mm = _abi.MERGE_BF16 if merge_mode == "bf16" else _abi.MERGE_FP32
+        ids, logits = ops.cfg_sample_impl(h, p.w1, p.b1, p.w2, p.b2, float(cfg_weight), float(temperature), u,
+                                          bool(greedy), mm)
+        return (ids, logits) if return_logits else ids
+
+
+@torch.no_grad()
+def cfg_merge_sample(logits: torch.Tensor, cfg_weight: float = 5.0, temperature: float = 1.0,
+                     uniforms: Optional[torch.Tensor] = None, greedy: bool = False, merge_mode: str = "bf16",
+                     return_merged: bool = False):
+    """image_generation.py:157-163 on supplied bf16 logits [..., 2P, V] -> ids [..., P]."""
+    lg = logits.to(torch.bfloat16).contiguous()
+    P = lg.shape[-2] // 2
+    n = lg.numel() // (lg.shape[-1] * lg.shape[-2]) * P
+    if greedy:
+        u = torch.empty(0, dtype=torch.float32, device=lg.device)
+    elif uniforms is None:
+        u = torch.rand(n, dtype=torch.float32, device=lg.device)
+    else:
+        u = uniforms.to(torch.float32).contiguous()
+    mm = _abi.MERGE_BF16 if merge_mode == "bf16" else _abi.MERGE_FP32
+    ids, merged = ops.cfg_merge_sample_impl(lg, float(cfg_weight), float(temperature), u, bool(greedy), mm,
+                                            bool(return_merged))
+    return (ids, merged) if return_merged else ids

@@ -1,0 +1,273 @@
+"""torch custom ops (``torch.ops.ospo_head.*``) over the C ABI.
+
+Each op takes/returns plain tensors, allocates its outputs and scratch with torch (the library itself
+never allocates device memory) and enqueues the kernels on torch's current CUDA stream.  Only a CUDA
+implementation is registered: calling an op with CPU tensors fails in the dispatcher, and a missing
+``libospo_head.so`` raises at first use -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Tuple
+
+import torch
+
+from . import _abi
+
+Tensor = torch.Tensor
+
+
+def _ptr(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _abi.OspoHeadError("ospo_head ops run on a B200 only: got a CPU tensor (there is no CPU path)")
+
+
+def _weights(w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> _abi.Weights:
+    assert w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16, "weights must be bf16"
+    assert b1.dtype == torch.float32 and b2.dtype == torch.float32, "biases must be fp32"
+    assert w1.is_contiguous() and w2.is_contiguous() and b1.is_contiguous() and b2.is_contiguous()
+    return _abi.Weights(w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr())
+
+
+def _workspace(rows: int, H: int, E: int, V: int, S: int, device) -> Tensor:
+    n = _abi.workspace_bytes(rows, H, E, V, S)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def flat_grad_numel(H: int, E: int, V: int) -> int:
+    return V * E + E * H + V + E
+
+
+def split_flat_grads(flat: Tensor, H: int, E: int, V: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """views (dW2 [V,E], dW1 [E,H], db2 [V], db1 [E]) of the flat gradient buffer"""
+    o0, o1, o2 = V * E, V * E + E * H, V * E + E * H + V
+    return flat[:o0].view(V, E), flat[o0:o1].view(E, H), flat[o1:o2], flat[o2:o2 + E]
+
+
+# --------------------------------------------------------------------------------------------------
+# plain logits
+# --------------------------------------------------------------------------------------------------
+def linear_gelu_linear_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
+    """logits[rows, V] (bf16) = vision_head(x[rows, H]);  janus/models/modeling_vlm.py:47-51"""
+    _check_cuda(x, w1, b1, w2, b2)
+    assert x.dim() == 2 and x.dtype == torch.bfloat16 and x.is_contiguous()
+    rows, H = x.shape
+    E, V = w1.shape[0], w2.shape[0]
+    logits = torch.empty(rows, V, dtype=torch.bfloat16, device=x.device)
+    ws = _workspace(rows, H, E, V, 1, x.device)
+    args = _abi.HeadArgs(_abi.Shape(rows, H, E, V, 1), _weights(w1, b1, w2, b2), x.data_ptr(), logits.data_ptr(),
+                         ws.data_ptr(), ws.numel())
+    _abi.check(_abi.load().ospo_head_logits(C.byref(args), _stream()), "ospo_head_logits")
+    return logits
+
+
+
+
+# --------------------------------------------------------------------------------------------------
+# log-probs / SimPO forward.  Returns the tensors the backward needs as explicit outputs.
+# --------------------------------------------------------------------------------------------------
+def _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, hp, outs, saved, bwd, ws) -> _abi.SimpoArgs:
+    rows, H = x.shape
+    E, V = w1.shape[0], w2.shape[0]
+    S = seq_off.numel() - 1
+    a = _abi.SimpoArgs()
+    a.shape = _abi.Shape(rows, H, E, V, S)
+    a.w = _weights(w1, b1, w2, b2)
+    a.x = x.data_ptr()
+    a.labels = labels.data_ptr()
+    a.seq_offsets = seq_off.data_ptr()
+    a.average_log_prob = int(average)
+    a.beta, a.gamma_beta_ratio, a.label_smoothing, a.sft_weight, a.loss_type = hp
+    (a.row_logps, a.seq_logps, a.losses, a.chosen_rewards, a.rejected_rewards, a.scalars) = [_ptr(t) for t in outs]
+    (a.pre, a.act, a.logits, a.row_lse, a.grad_seq) = [_ptr(t) for t in saved]
+    (a.grad_loss, a.dx, a.flat_grads) = [_ptr(t) for t in bwd]
+    a.workspace = ws.data_ptr()
+    a.workspace_bytes = ws.numel()
+    return a
+
+
+def _check_rows(x: Tensor, labels: Tensor, seq_off: Tensor) -> None:
+    _check_cuda(x, labels, seq_off)
+    assert x.dim() == 2 and x.dtype == torch.bfloat16 and x.is_contiguous(), "x must be contiguous bf16 [rows, H]"
+    assert labels.dtype == torch.int64 and labels.shape == (x.shape[0],) and labels.is_contiguous()
+    assert seq_off.dtype == torch.int64 and seq_off.dim() == 1 and seq_off.is_contiguous()
+
+
+def logps_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
+              average: bool, save_for_backward: bool) -> List[Tensor]:
+    """-> [seq_logps[S], row_logps[rows], row_lse[rows], pre, act, logits]  (train.py:357 + 375-396)"""
+    _check_rows(x, labels, seq_off)
+    rows, H = x.shape
+    E, V = w1.shape[0], w2.shape[0]
+    S = seq_off.numel() - 1
+    dev = x.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    seq_logps, row_logps, row_lse = torch.empty(S, **f32), torch.empty(rows, **f32), torch.empty(rows, **f32)
+    act = torch.empty(rows, E, dtype=torch.bfloat16, device=dev)
+    if save_for_backward:
+        pre = torch.empty(rows, E, dtype=torch.bfloat16, device=dev)
+        logits = torch.empty(rows, V, dtype=torch.bfloat16, device=dev)
+    else:
+        pre = logits = None
+    ws = _workspace(rows, H, E, V, S, dev)
+    a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, (1.0, 0.0, 0.0, 0.0, 0),
+                    (row_logps, seq_logps, None, None, None, None), (pre, act, logits, row_lse, None),
+                    (None, None, None), ws)
+    _abi.check(_abi.load().ospo_head_logps_fwd(C.byref(a), _stream()), "ospo_head_logps_fwd")
+    def empty():
+        return torch.empty(0, dtype=torch.bfloat16, device=dev)
+
+    return [seq_logps, row_logps, row_lse, pre if pre is not None else empty(), act,
+            logits if logits is not None else empty()]
+
+
+def simpo_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
+              beta: float, gamma_beta_ratio: float, label_smoothing: float, sft_weight: float, loss_type: int,
+              save_for_backward: bool) -> List[Tensor]:
+    """-> [scalars[16], seq_logps[S], losses[B], chosen_rewards[B], rejected_rewards[B], row_logps[rows],
+           row_lse[rows], grad_seq[S], pre, act, logits]      (train.py:345-372, 317-342, 399-445)"""
+    _check_rows(x, labels, seq_off)
+    rows, H = x.shape
+    E, V = w1.shape[0], w2.shape[0]
+    S = seq_off.numel() - 1
+    assert S % 2 == 0, "SimPO needs chosen and rejected halves"
+    B = S // 2
+    dev = x.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    scalars = torch.zeros(_abi.SC_COUNT, **f32)
+    seq_logps, losses = torch.empty(S, **f32), torch.empty(B, **f32)
+    crew, rrew = torch.empty(B, **f32), torch.empty(B, **f32)
+    row_logps, row_lse, grad_seq = torch.empty(rows, **f32), torch.empty(rows, **f32), torch.empty(S, **f32)
+    act = torch.empty(rows, E, dtype=torch.bfloat16, device=dev)
+    if save_for_backward:
+        pre = torch.empty(rows, E, dtype=torch.bfloat16, device=dev)
+        logits = torch.empty(rows, V, dtype=torch.bfloat16, device=dev)
+    else:
+        pre = logits = None
+    ws = _workspace(rows, H, E, V, S, dev)
+    a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, True,
+                    (beta, gamma_beta_ratio, label_smoothing, sft_weight, loss_type),
+                    (row_logps, seq_logps, losses, crew, rrew, scalars), (pre, act, logits, row_lse, grad_seq),
+                    (None, None, None), ws)
+    _abi.check(_abi.load().ospo_head_simpo_fwd(C.byref(a), _stream()), "ospo_head_simpo_fwd")
+    def empty():
+        return torch.empty(0, dtype=torch.bfloat16, device=dev)
+
+    return [scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, grad_seq,
+            pre if pre is not None else empty(), act, logits if logits is not None else empty()]
+
+
+def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
+             average: bool, sft_weight: float, scalars: Tensor, pre: Tensor, act: Tensor, logits: Tensor,
+             row_lse: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool, flat_grads: Tensor,
+             simpo: bool) -> Tensor:
+    """softmax-minus-onehot producer + the dgrad / wgrad GEMM pairs.
+    `logits` is overwritten with dlogits; `flat_grads` (numel 0 = head frozen) receives dW2|dW1|db2|db1.
+    Returns dx [rows, H] bf16 (numel 0 if not requested)."""
+    _check_rows(x, labels, seq_off)
+    rows, H = x.shape
+    E, V = w1.shape[0], w2.shape[0]
+    S = seq_off.numel() - 1
+    dev = x.device
+    dx = torch.empty(rows, H, dtype=torch.bfloat16, device=dev) if need_dx else None
+    fg = flat_grads if flat_grads.numel() else None
+    if fg is not None:
+        assert fg.dtype == torch.float32 and fg.numel() == flat_grad_numel(H, E, V) and fg.is_contiguous()
+    assert grad_scale.dtype == torch.float32 and grad_scale.numel() == 1
+    assert grad_seq.dtype == torch.float32 and grad_seq.numel() == S and grad_seq.is_contiguous()
+    ws = _workspace(rows, H, E, V, S, dev)
+    a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, (1.0, 0.0, 0.0, sft_weight, 0),
+                    (None, None, None, None, None, scalars if scalars.numel() else None),
+                    (pre, act, logits, row_lse, grad_seq), (grad_scale, dx, fg), ws)
+    lib = _abi.load()
+    if simpo:
+        _abi.check(lib.ospo_head_simpo_bwd(C.byref(a), _stream()), "ospo_head_simpo_bwd")
+    else:
+        _abi.check(lib.ospo_head_logps_bwd(C.byref(a), _stream()), "ospo_head_logps_bwd")
+    return dx if dx is not None else torch.empty(0, dtype=torch.bfloat16, device=dev)
+
+
+# --------------------------------------------------------------------------------------------------
+# CFG decode step
+# --------------------------------------------------------------------------------------------------
+def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, cfg_weight: float, temperature: float,
+               uniforms: Tensor, greedy: bool, merge_mode: int) -> List[Tensor]:
+    """-> [ids[P] int64, logits[2P, V] bf16]   (image_generation.py:156-164; row 2k cond / 2k+1 uncond)"""
+    _check_cuda(h, uniforms)
+    assert h.dim() == 2 and h.dtype == torch.bfloat16 and h.is_contiguous() and h.shape[0] % 2 == 0
+    rows, H = h.shape
+    E, V = w1.shape[0], w2.shape[0]
+    P = rows // 2
+    dev = h.device
+    if not greedy:
+        assert uniforms.dtype == torch.float32 and uniforms.numel() == P and uniforms.is_contiguous()
+    ids = torch.empty(P, dtype=torch.int64, device=dev)
+    logits = torch.empty(rows, V, dtype=torch.bfloat16, device=dev)
+    ws = _workspace(rows, H, E, V, 1, dev)
+    a = _abi.CfgArgs()
+    a.shape = _abi.Shape(rows, H, E, V, 1)
+    a.w = _weights(w1, b1, w2, b2)
+    a.h = h.data_ptr()
+    a.logits = logits.data_ptr()
+    a.cfg_weight, a.temperature, a.merge_mode, a.greedy, a.num_steps = cfg_weight, temperature, merge_mode, int(greedy), 1
+    a.uniforms = None if greedy else uniforms.data_ptr()
+    a.ids = ids.data_ptr()
+    a.merged = None
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    _abi.check(_abi.load().ospo_head_cfg_sample(C.byref(a), _stream()), "ospo_head_cfg_sample")
+    return [ids, logits]
+
+
+def cfg_merge_sample_impl(logits: Tensor, cfg_weight: float, temperature: float, uniforms: Tensor, greedy: bool,
+                     merge_mode: int, want_merged: bool) -> List[Tensor]:
+    """merge + softmax + sample on supplied bf16 logits [..., 2P, V] (any number of leading "step" dims)
+    -> [ids[..., P] int64, merged[..., P, V] fp32 or empty]"""
+    _check_cuda(logits, uniforms)
+    assert logits.dtype == torch.bfloat16 and logits.is_contiguous() and logits.dim() >= 2
+    V = logits.shape[-1]
+    rows = logits.shape[-2]
+    steps = logits.numel() // (rows * V)
+    P = rows // 2
+    dev = logits.device
+    if not greedy:
+        assert uniforms.dtype == torch.float32 and uniforms.numel() == steps * P and uniforms.is_contiguous()
+    ids = torch.empty(*logits.shape[:-2], P, dtype=torch.int64, device=dev)
+    merged = torch.empty(*logits.shape[:-2], P, V, dtype=torch.float32, device=dev) if want_merged else None
+    a = _abi.CfgArgs()
+    a.shape = _abi.Shape(rows, 8, 8, V, 1)
+    a.logits = logits.data_ptr()
+    a.cfg_weight, a.temperature, a.merge_mode, a.greedy, a.num_steps = cfg_weight, temperature, merge_mode, int(greedy), steps
+    a.uniforms = None if greedy else uniforms.data_ptr()
+    a.ids = ids.data_ptr()
+    a.merged = _ptr(merged)
+    _abi.check(_abi.load().ospo_head_cfg_merge_sample(C.byref(a), _stream()), "ospo_head_cfg_merge_sample")
+    return [ids, merged if merged is not None else torch.empty(0, dtype=torch.float32, device=dev)]
+
+
+# --------------------------------------------------------------------------------------------------
+# registration: torch.ops.ospo_head.<name>  (CUDA only).  The nn.Module in head.py calls the *_impl
+# functions directly to keep the dispatcher out of the 576-step decode loop.
+# --------------------------------------------------------------------------------------------------
+linear_gelu_linear = torch.library.custom_op("ospo_head::linear_gelu_linear", linear_gelu_linear_impl,
+                                             mutates_args=(), device_types="cuda")
+logps_fwd = torch.library.custom_op("ospo_head::logps_fwd", logps_fwd_impl, mutates_args=(), device_types="cuda")
+simpo_fwd = torch.library.custom_op("ospo_head::simpo_fwd", simpo_fwd_impl, mutates_args=(), device_types="cuda")
+head_bwd = torch.library.custom_op("ospo_head::head_bwd", head_bwd_impl, mutates_args=("logits", "flat_grads"),
+                                   device_types="cuda")
+cfg_sample = torch.library.custom_op("ospo_head::cfg_sample", cfg_sample_impl, mutates_args=(), device_types="cuda")
+cfg_merge_sample = torch.library.custom_op("ospo_head::cfg_merge_sample", cfg_merge_sample_impl, mutates_args=(),
+                                           device_types="cuda")
+
+
+@linear_gelu_linear.register_fake
+def _(x, w1, b1, w2, b2):
+    return x.new_empty(x.shape[0], w2.shape[0], dtype=torch.bfloat16)

@@ -1,0 +1,85 @@
+"""Plug-in points for the reference code base.
+
+* ``register_gen_head_cls`` adds ``"vision_head_sm100"`` to the class registry the reference uses to
+  build ``gen_head`` (``model_name_to_cls``, janus/models/modeling_vlm.py:54-70; selected by
+  ``config.gen_head_config.cls``, :133-145, 210-212).
+* ``patch_model`` swaps an already-built ``model.gen_head`` (MultiModalityCausalLM, :210-212) for a
+  ``FusedGenHead`` that shares its parameters.
+* ``patch_train_wrapper`` re-points ``JanusProTrainWrapper.concatenated_forward`` /
+  ``get_batch_loss_metrics`` (ospo/wrapper/train.py:345-372, 399-445) at the fused path while keeping
+  their signatures and return values.
+"""
+from __future__ import annotations
+
+import types
+from typing import Dict
+
+import torch
+
+from .head import FusedGenHead
+
+SM100_CLS_NAME = "vision_head_sm100"
+
+
+def register_gen_head_cls(modeling_vlm_module) -> None:
+    """wrap ``modeling_vlm.model_name_to_cls`` so ``"vision_head_sm100"`` resolves to FusedGenHead"""
+    orig = modeling_vlm_module.model_name_to_cls
+
+    def model_name_to_cls(cls_name):
+        if SM100_CLS_NAME in cls_name:
+            return FusedGenHead
+        return orig(cls_name)
+
+    modeling_vlm_module.model_name_to_cls = model_name_to_cls
+
+
+def patch_model(model: torch.nn.Module) -> torch.nn.Module:
+    """replace ``model.gen_head`` in place; parameters (and their requires_grad flags) are shared"""
+    if not isinstance(model.gen_head, FusedGenHead):
+        model.gen_head = FusedGenHead.from_reference(model.gen_head)
+    return model
+
+
+def patch_train_wrapper(wrapper, image_span=None, process_group=None):
+    """``wrapper``: a JanusProTrainWrapper (or anything with .model.gen_head, .model.language_model.model,
+    .concatenated_inputs, the SimPO hyper-parameter attributes and .log/.log_dict)."""
+    patch_model(wrapper.model)
+
+    def concatenated_forward(self, batch: Dict):
+        # train.py:345-372, with gen_head + get_batch_logps fused; the [S, L+T, V] logits are never built, so the
+        # two logits entries of the reference 5-tuple carry the per-sequence mean logit instead (what the
+        # reference reduces them to at :441-442).
+        concatenated_batch = self.concatenated_inputs(batch=batch)
+        len_chosen = batch["chosen_labels"].shape[0]
+        outputs = self.model.language_model.model(
+            inputs_embeds=concatenated_batch["concatenated_inputs_embeds"], use_cache=False, past_key_values=None)
+        hidden_states = outputs.hidden_states[-1]
+        labels = concatenated_batch["concatenated_labels"]
+        all_logps = self.model.gen_head.logps(hidden_states, labels, average_log_prob=True,
+                                              ignore_index=self.label_pad_token_id, image_span=image_span,
+                                              process_group=process_group)
+        return (all_logps[:len_chosen], all_logps[len_chosen:], None, None, labels[:len_chosen])
+
+    def get_batch_loss_metrics(self, batch: Dict, train_eval: str = "train"):
+        # train.py:399-445 in one fused forward (+ backward through autograd)
+        prefix = "val" if train_eval == "val" else "train"
+        concatenated_batch = self.concatenated_inputs(batch=batch)
+        outputs = self.model.language_model.model(
+            inputs_embeds=concatenated_batch["concatenated_inputs_embeds"], use_cache=False, past_key_values=None)
+        hidden_states = outputs.hidden_states[-1]
+        out = self.model.gen_head.simpo(
+            hidden_states, concatenated_batch["concatenated_labels"], beta=self.beta,
+            gamma_beta_ratio=self.gamma_beta_ratio, label_smoothing=self.label_smoothing, loss_type=self.loss_type,
+            sft_weight=self.sft_weight, ignore_index=self.label_pad_token_id, image_span=image_span,
+            process_group=process_group)
+        if self.sft_weight > 0.0:
+            self.log(f"{prefix}/sft_loss", out.metrics["sft_loss"], on_step=True, prog_bar=True, logger=True,
+                     sync_dist=True)
+        # device scalars: no .cpu() here, so the step does not synchronise
+        self.log_dict({f"{prefix}/{k}": v for k, v in out.metrics.items() if "/" in k},
+                      on_step=True, prog_bar=True, logger=True, sync_dist=True)
+        return out.loss
+
+    wrapper.concatenated_forward = types.MethodType(concatenated_forward, wrapper)
+    wrapper.get_batch_loss_metrics = types.MethodType(get_batch_loss_metrics, wrapper)
+    return wrapper

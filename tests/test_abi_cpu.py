@@ -1,0 +1,94 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/ospo_head.h declares, the
+ctypes mirror matches the header, argument validation works without a GPU, and the host-side row
+selection (the label shift / mask of get_batch_logps) matches the oracle."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from ospo_b200 import _abi
+from ospo_b200.head import FusedGenHead, _rows_from_labels
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _header_functions():
+    text = (ROOT / "include" / "ospo_head.h").read_text()
+    return set(re.findall(r"OSPO_API\s+[\w\s\*]+?\b(ospo_head_\w+)\s*\(", text))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(str(_abi.lib_path()))
+    declared = _header_functions()
+    assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_header_constants_match_python_mirror():
+    text = (ROOT / "include" / "ospo_head.h").read_text()
+    consts = {k: int(v) for k, v in re.findall(r"#define\s+(OSPO_\w+)\s+(-?\d+)\b", text)}
+    assert consts["OSPO_SC_LOSS"] == _abi.SC_LOSS and consts["OSPO_SC_COUNT"] == _abi.SC_COUNT
+    assert consts["OSPO_SC_LOGITS_REJECTED"] == _abi.SC_LOGITS_REJECTED
+    assert consts["OSPO_LOSS_HINGE"] == _abi.LOSS_HINGE and consts["OSPO_MERGE_FP32"] == _abi.MERGE_FP32
+    assert consts["OSPO_K_COUNT"] == len(_abi.KERNEL_NAMES)
+
+
+def test_strerror_and_workspace_query_need_no_gpu():
+    assert _abi.strerror(0) == "ok"
+    assert "sm_100" in _abi.strerror(-5)
+    n = _abi.workspace_bytes(73728, 4096, 4096, 16384, 128)
+    # LSE partials (64 N-tiles x rows x 12 B) + dpre (rows x E x 2 B) dominate
+    assert 73728 * 64 * 12 + 73728 * 4096 * 2 <= n < 2 * (73728 * 64 * 12 + 73728 * 4096 * 2)
+    with pytest.raises(_abi.OspoHeadError):
+        _abi.workspace_bytes(0, 8, 8, 8)
+
+
+def test_calls_fail_loudly_without_a_b200():
+    """no CPU fallback: on a machine without an sm_100 device every compute entry point reports an error"""
+    if torch.cuda.is_available():
+        pytest.skip("this check is for GPU-less machines")
+    lib = _abi.load()
+    args = _abi.HeadArgs()
+    rc = lib.ospo_head_logits(C.byref(args), None)
+    assert rc != 0
+    head = FusedGenHead(type("P", (), dict(n_embed=16, image_token_embed=16, image_token_size=64)))
+    with pytest.raises(Exception):
+        with torch.no_grad():
+            head(torch.zeros(2, 16))
+
+
+def test_state_dict_is_checkpoint_compatible_with_reference_head():
+    from oracle.head_oracle import VisionHead
+
+    ref = VisionHead(32, 48, 64)
+    head = FusedGenHead(type("P", (), dict(n_embed=32, image_token_embed=48, image_token_size=64)))
+    assert list(head.state_dict().keys()) == list(ref.state_dict().keys())
+    head.load_state_dict(ref.state_dict(), strict=True)
+    adopted = FusedGenHead.from_reference(ref)
+    assert adopted.vision_head.weight is ref.vision_head.weight
+    ref.vision_head.weight.requires_grad_(False)
+    assert not adopted.vision_head.weight.requires_grad
+
+
+@pytest.mark.parametrize("use_span", [False, True])
+def test_row_selection_matches_get_batch_logps_mask(use_span):
+    from oracle import head_oracle as O
+
+    S, Lt, T, H, V = 4, 3, 6, 8, 32
+    g = torch.Generator().manual_seed(0)
+    hidden = torch.randn(S, Lt + T, H, generator=g)
+    labels = torch.cat([torch.full((S, Lt), -100), torch.randint(0, V, (S, T), generator=g)], 1)
+    span = (Lt - 1, Lt - 1 + T) if use_span else None
+    x_rows, targets, seq_off = _rows_from_labels(hidden, labels, -100, span)
+    lab = labels[:, 1:]
+    mask = lab != -100
+    assert torch.equal(x_rows, hidden[:, :-1][mask])
+    assert torch.equal(targets, lab[mask])
+    assert seq_off.tolist() == [0, T, 2 * T, 3 * T, 4 * T]
+    # and those are exactly the positions the oracle's get_batch_logps averages over
+    head = O.make_head(H, 8, V, seed=1)
+    _, per_tok, m = O.get_batch_logps(head(hidden), labels, return_per_token=True)
+    assert torch.equal(m, mask)

@@ -1,0 +1,424 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI, against
+
+  * the golden vectors produced by the reference's own code (tests/golden/*.npz),
+  * the CPU oracle (oracle/) on seeded inputs at sizes it finishes in seconds,
+  * size-independent properties at BASELINE.json's full sizes.
+
+Tolerances: bf16 kernels vs fp32 reference -> rtol 1e-2 on loss / log-probs (BASELINE.json north_star);
+gradients -> relative Frobenius error <= 2e-2 vs fp32 reference and <= 1e-2 vs the bf16 oracle;
+sampled / greedy ids bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import head_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a B200: torch.cuda.is_available() is False")
+    return torch.device("cuda:0")
+
+
+def _fused_from(head_cpu, dev, dtype=torch.float32, requires_grad=True):
+    from ospo_b200 import FusedGenHead
+
+    class P:
+        n_embed = head_cpu.output_mlp_projector.in_features
+        image_token_embed = head_cpu.output_mlp_projector.out_features
+        image_token_size = head_cpu.vision_head.out_features
+
+    fh = FusedGenHead(P)
+    fh.load_state_dict(head_cpu.state_dict(), strict=True)   # same parameter names as the reference module
+    fh = fh.to(dev).to(dtype)
+    for p in fh.parameters():
+        p.requires_grad_(requires_grad)
+    return fh
+
+
+def _rel_fro(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+def _golden_head(d):
+    H, E, V = int(d["H"]), int(d["E"]), int(d["V"])
+    head = O.VisionHead(H, E, V)
+    with torch.no_grad():
+        head.output_mlp_projector.weight.copy_(torch.from_numpy(d["W1"]))
+        head.output_mlp_projector.bias.copy_(torch.from_numpy(d["b1"]))
+        head.vision_head.weight.copy_(torch.from_numpy(d["W2"]))
+        head.vision_head.bias.copy_(torch.from_numpy(d["b2"]))
+    return head
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM engine variants (cta_group x operand-major x tile)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [100, 110, 120, 101, 102, 200, 210, 220])
+@pytest.mark.parametrize("shape", [(256, 256, 128), (296, 520, 200), (1024, 2048, 1024)])
+def test_gemm_engine_variant(variant, shape):
+    from ospo_b200 import _abi
+
+    dev = _cuda()
+    lib = _abi.load()
+    M, N, K = shape
+    majors = (variant // 10) % 10
+    a_mn, b_mn = majors == 2, majors >= 1
+    g = torch.Generator().manual_seed(variant * 7 + M)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    ref = A.to(dev).float() @ B.to(dev).float().t()
+    Ad = (A.t().contiguous() if a_mn else A).to(dev)
+    Bd = (B.t().contiguous() if b_mn else B).to(dev)
+    out = torch.full((M, N), float("nan"), device=dev)
+    rc = lib.ospo_head_gemm_debug(variant, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0), out.data_ptr(),
+                                  out.stride(0), M, N, K, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _abi.strerror(rc)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# SimPO: golden vectors from the reference's own code (fp32 reference vs bf16 kernels)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["sigmoid", "sigmoid_smooth_sft", "hinge"])
+@pytest.mark.parametrize("use_span", [True, False])
+def test_simpo_vs_reference_golden(golden_dir, tag, use_span):
+    dev = _cuda()
+    d = np.load(golden_dir / "simpo_ref.npz")
+    B, T, L = int(d["B"]), int(d["T"]), int(d["L"])
+    fh = _fused_from(_golden_head(d), dev)
+    hp = dict(beta=float(d[f"{tag}/hp/beta"]), gamma_beta_ratio=float(d[f"{tag}/hp/gamma_beta_ratio"]),
+              label_smoothing=float(d[f"{tag}/hp/label_smoothing"]), sft_weight=float(d[f"{tag}/hp/sft_weight"]),
+              loss_type=str(d[f"{tag}/hp/loss_type"]))
+    hidden = torch.cat([torch.from_numpy(d["hidden_chosen"]), torch.from_numpy(d["hidden_rejected"])]).to(dev)
+    labels = torch.cat([torch.from_numpy(d["labels_chosen"]), torch.from_numpy(d["labels_rejected"])]).to(dev)
+    hidden.requires_grad_(True)
+    span = (L - 1, L - 1 + T) if use_span else None
+    out = fh.simpo(hidden, labels, image_span=span, **hp)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    r = dict(rtol=1e-2, atol=2e-3)
+    np.testing.assert_allclose(out.chosen_logps.cpu().numpy(), d[f"{tag}/chosen_logps"], **r)
+    np.testing.assert_allclose(out.rejected_logps.cpu().numpy(), d[f"{tag}/rejected_logps"], **r)
+    ref_tok = d[f"{tag}/per_token_logps"][:, L - 1:]            # the unmasked positions
+    np.testing.assert_allclose(out.per_token_logps.cpu().numpy().reshape(2 * B, T), ref_tok, rtol=1e-2, atol=2e-2)
+    # the loss amplifies log-prob differences by beta: allow beta * |logp error|
+    beta = hp["beta"]
+    np.testing.assert_allclose(float(out.loss), float(d[f"{tag}/loss"]), rtol=1e-2, atol=2e-3 * beta)
+    np.testing.assert_allclose(out.losses.cpu().numpy(), d[f"{tag}/losses"], rtol=1e-2, atol=2e-3 * beta)
+    np.testing.assert_allclose(out.chosen_rewards.cpu().numpy(), d[f"{tag}/chosen_rewards"], rtol=1e-2, atol=2e-3 * beta)
+    np.testing.assert_allclose(float(out.metrics["rewards/accuracies"]),
+                               float(d[f"{tag}/logged/train/rewards/accuracies"]), atol=1e-6)
+    if tag == "hinge":
+        return  # hinge gradients are piecewise constant; compared against the bf16 oracle below instead
+    dx_ref = torch.cat([torch.from_numpy(d[f"{tag}/dx_chosen"]), torch.from_numpy(d[f"{tag}/dx_rejected"])])
+    assert _rel_fro(hidden.grad, dx_ref) < 3e-2
+    assert _rel_fro(fh.vision_head.weight.grad, torch.from_numpy(d[f"{tag}/dW2"])) < 3e-2
+    assert _rel_fro(fh.output_mlp_projector.weight.grad, torch.from_numpy(d[f"{tag}/dW1"])) < 3e-2
+    assert _rel_fro(fh.vision_head.bias.grad, torch.from_numpy(d[f"{tag}/db2"])) < 3e-2
+    assert _rel_fro(fh.output_mlp_projector.bias.grad, torch.from_numpy(d[f"{tag}/db1"])) < 3e-2
+    # text rows carry no gradient
+    assert float(hidden.grad[:, :L - 1].abs().max()) == 0.0
+    assert float(hidden.grad[:, -1].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# SimPO vs the oracle on seeded inputs (fp32 oracle = reference CPU path of config 1; bf16 oracle = the
+# reference's bf16 semantics)
+# ---------------------------------------------------------------------------------------------------
+def _run_pair(H, E, V, B, T, L, seed, hp, dev, w2_gain=1.0):
+    head32 = O.make_head(H, E, V, seed=seed, w2_gain=w2_gain)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=seed + 1)
+    # both sides use the bf16-rounded copy of the random init / inputs
+    head_b = O.VisionHead(H, E, V)
+    head_b.load_state_dict(head32.state_dict())
+    head_b = head_b.to(torch.bfloat16)
+    head_r = O.VisionHead(H, E, V)
+    head_r.load_state_dict({k: v.float() for k, v in head_b.state_dict().items()})
+    hcb, hrb = hc.to(torch.bfloat16), hr.to(torch.bfloat16)
+    ref32 = O.simpo_step(head_r, hcb.float(), hrb.float(), lc, lr, backward=True, **hp)
+    ref16 = O.simpo_step(head_b, hcb, hrb, lc, lr, backward=True, **hp)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+    hidden = torch.cat([hcb, hrb]).to(dev).requires_grad_(True)
+    labels = torch.cat([lc, lr]).to(dev)
+    out = fh.simpo(hidden, labels, image_span=(L - 1, L - 1 + T), **hp)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    return ref32, ref16, out, fh, hidden
+
+
+@pytest.mark.parametrize("loss_type", ["sigmoid", "hinge"])
+def test_simpo_vs_oracle_small(loss_type):
+    dev = _cuda()
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, label_smoothing=0.0, sft_weight=0.0, loss_type=loss_type)
+    B, T, L = 4, 40, 3
+    ref32, ref16, out, fh, hidden = _run_pair(256, 320, 2048, B, T, L, 100, hp, dev, w2_gain=3.0)
+    for ref, tol in ((ref32, 1e-2), (ref16, 1e-2)):
+        np.testing.assert_allclose(out.chosen_logps.cpu().numpy(), ref["chosen_logps"].detach().float().numpy(),
+                                   rtol=tol, atol=1e-3)
+        np.testing.assert_allclose(out.rejected_logps.cpu().numpy(), ref["rejected_logps"].detach().float().numpy(),
+                                   rtol=tol, atol=1e-3)
+        np.testing.assert_allclose(float(out.loss), float(ref["loss"]), rtol=1e-2, atol=2e-2)
+    np.testing.assert_allclose(float(out.metrics["logits/chosen"]), float(ref32["logits_chosen_valid_mean"]),
+                               rtol=1e-2, atol=1e-3)
+    np.testing.assert_allclose(float(out.metrics["logits/rejected"]), float(ref32["logits_rejected_valid_mean"]),
+                               rtol=1e-2, atol=1e-3)
+    if loss_type == "sigmoid":
+        assert _rel_fro(hidden.grad.float(), ref32["dx"]) < 2e-2
+        assert _rel_fro(fh.vision_head.weight.grad.float(), ref32["dW2"]) < 2e-2
+        assert _rel_fro(fh.output_mlp_projector.weight.grad.float(), ref32["dW1"]) < 2e-2
+        assert _rel_fro(fh.vision_head.bias.grad.float(), ref32["db2"]) < 2e-2
+        assert _rel_fro(fh.output_mlp_projector.bias.grad.float(), ref32["db1"]) < 2e-2
+
+
+def test_simpo_config1_shape_vs_cpu_reference():
+    """BASELINE.json configs[0]: Janus-Pro-1B-shaped head (hidden 2048), 8 pairs x 576 tokens; CPU side fp32."""
+    dev = _cuda()
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, label_smoothing=0.0, sft_weight=0.0, loss_type="sigmoid")
+    B, T, L = 8, 576, 1
+    ref32, ref16, out, fh, hidden = _run_pair(2048, 2048, 16384, B, T, L, 1234, hp, dev)
+    np.testing.assert_allclose(out.chosen_logps.cpu().numpy(), ref32["chosen_logps"].detach().numpy(), rtol=1e-2)
+    np.testing.assert_allclose(out.rejected_logps.cpu().numpy(), ref32["rejected_logps"].detach().numpy(), rtol=1e-2)
+    np.testing.assert_allclose(float(out.loss), float(ref32["loss"]), rtol=1e-2, atol=1e-2)
+    tok = ref32["per_token_logps"].detach()[:, L - 1:].reshape(-1)
+    np.testing.assert_allclose(out.per_token_logps.cpu().numpy(), tok.numpy(), rtol=1e-2, atol=2e-2)
+    assert _rel_fro(hidden.grad.float(), ref32["dx"]) < 2e-2
+    assert _rel_fro(fh.vision_head.weight.grad.float(), ref32["dW2"]) < 2e-2
+    assert _rel_fro(fh.output_mlp_projector.weight.grad.float(), ref32["dW1"]) < 2e-2
+    assert _rel_fro(fh.vision_head.bias.grad.float(), ref32["db2"]) < 2e-2
+    assert _rel_fro(fh.output_mlp_projector.bias.grad.float(), ref32["db1"]) < 2e-2
+
+
+def test_logps_autograd_path_and_ragged_sequences():
+    """get_batch_logps replacement with per-sequence different numbers of unmasked tokens + empty head grads."""
+    dev = _cuda()
+    H, E, V, S, Lmax = 128, 128, 1024, 5, 30
+    head32 = O.make_head(H, E, V, seed=9, w2_gain=2.0)
+    g = torch.Generator().manual_seed(10)
+    hidden = torch.randn(S, Lmax, H, generator=g)
+    labels = torch.randint(0, V, (S, Lmax), generator=g)
+    for s, n_text in enumerate([3, 7, 1, 12, 29]):     # ragged: sequence s has Lmax - n_text image tokens
+        labels[s, :n_text] = -100
+    labels[2, 10:14] = -100                            # holes inside a sequence
+    head_b = O.VisionHead(H, E, V)
+    head_b.load_state_dict(head32.state_dict())
+    head_b = head_b.to(torch.bfloat16)
+    hb = hidden.to(torch.bfloat16)
+    for avg in (True, False):
+        ref_in = hb.clone().requires_grad_(True)
+        head_b.zero_grad()
+        ref = O.get_batch_logps(head_b(ref_in), labels, average_log_prob=avg)
+        w = torch.linspace(0.5, 1.5, S)
+        (ref * w).sum().backward()
+        fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+        x = hb.to(dev).requires_grad_(True)
+        got = fh.logps(x, labels.to(dev), average_log_prob=avg)
+        (got * w.to(dev)).sum().backward()
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(got.detach().cpu().numpy(), ref.detach().float().numpy(), rtol=1e-2, atol=1e-2)
+        assert _rel_fro(x.grad.float(), ref_in.grad.float()) < 2e-2
+        assert _rel_fro(fh.vision_head.weight.grad.float(), head_b.vision_head.weight.grad.float()) < 2e-2
+        assert _rel_fro(fh.output_mlp_projector.bias.grad.float(), head_b.output_mlp_projector.bias.grad.float()) < 2e-2
+
+
+def test_frozen_head_only_dx():
+    """configs/step5.yaml:64 freezes gen_head: only dX is produced, parameters get no .grad"""
+    dev = _cuda()
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, loss_type="sigmoid")
+    head32 = O.make_head(128, 128, 1024, seed=2)
+    fh = _fused_from(head32, dev, dtype=torch.bfloat16, requires_grad=False)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(2, 16, 2, 128, 1024, seed=3)
+    hidden = torch.cat([hc, hr]).to(dev).to(torch.bfloat16).requires_grad_(True)
+    out = fh.simpo(hidden, torch.cat([lc, lr]).to(dev), **hp)
+    out.loss.backward()
+    assert hidden.grad is not None and float(hidden.grad.abs().sum()) > 0
+    assert all(p.grad is None for p in fh.parameters())
+
+
+def test_forward_logits_api_compat():
+    dev = _cuda()
+    head32 = O.make_head(256, 192, 1024, seed=4)
+    head_b = head32.to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+    x = torch.randn(3, 17, 256, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+    with torch.no_grad():
+        got = fh(x.to(dev))
+        ref = head_b(x)
+    assert got.shape == ref.shape and got.dtype == torch.bfloat16
+    torch.testing.assert_close(got.float().cpu(), ref.float(), rtol=2e-2, atol=2e-2)
+    with pytest.raises(Exception):
+        fh(x.to(dev).requires_grad_(True))     # materialised-logits path is inference only
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1]: 7B-shaped head, 64 pairs x 576 tokens)
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_shard_equivalence_and_checksums():
+    """config-2 size on one GPU.  Properties that need no CPU oracle:
+       * every softmax-minus-onehot row sums to zero => sum(db2) ~ 0 relative to |db2|
+       * batch-sharding: averaging the gradients of the two half-batches (pairs 0..31 / 32..63),
+         each normalised by its own B/2, reproduces the full-batch gradients and loss."""
+    dev = _cuda()
+    H = E = 4096
+    V, B, T = 16384, 64, 576
+    g = torch.Generator().manual_seed(1235)
+    head32 = O.make_head(H, E, V, seed=1235)
+    fh = _fused_from(head32, dev, dtype=torch.bfloat16)
+    hidden = torch.randn(2 * B, T + 1, H, generator=g).to(torch.bfloat16)
+    ids = torch.randint(0, V, (2 * B, T), generator=g)
+    labels = torch.cat([torch.full((2 * B, 1), -100, dtype=torch.long), ids], 1)
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, loss_type="sigmoid")
+
+    def run(sel):
+        fh.zero_grad(set_to_none=True)
+        h = hidden[sel].to(dev).requires_grad_(True)
+        out = fh.simpo(h, labels[sel].to(dev), image_span=(0, T), **hp)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        return (float(out.loss), h.grad.float().cpu(), fh.vision_head.weight.grad.float().clone(),
+                fh.output_mlp_projector.weight.grad.float().clone(), fh.vision_head.bias.grad.float().clone(),
+                out.chosen_logps.cpu(), out.rejected_logps.cpu())
+
+    idx = torch.arange(2 * B)
+    full = run(idx)
+    half = B // 2
+    s0 = torch.cat([idx[:half], idx[B:B + half]])
+    s1 = torch.cat([idx[half:B], idx[B + half:]])
+    a, b = run(s0), run(s1)
+    assert np.isfinite(full[0])
+    assert abs(0.5 * (a[0] + b[0]) - full[0]) < 1e-3 * max(1.0, abs(full[0]))
+    torch.testing.assert_close(torch.cat([a[5], b[5]]), full[5], rtol=1e-6, atol=1e-6)   # shard-invariant log-probs
+    # parameter .grad is stored in the parameters' dtype (bf16 here): one bf16 rounding (2^-9) per element
+    assert _rel_fro(0.5 * (a[2] + b[2]), full[2]) < 5e-3          # dW2
+    assert _rel_fro(0.5 * (a[3] + b[3]), full[3]) < 5e-3          # dW1
+    dx_sharded = torch.empty_like(full[1])
+    dx_sharded[s0] = 0.5 * a[1]
+    dx_sharded[s1] = 0.5 * b[1]
+    assert _rel_fro(dx_sharded, full[1]) < 5e-3
+    db2 = full[4]
+    assert abs(float(db2.double().sum())) < 1e-2 * float(db2.double().abs().sum())
+    # log-probs of random-init head on uniform labels sit near -log V
+    assert abs(float(full[5].mean()) + np.log(V)) < 0.5
+
+
+# ---------------------------------------------------------------------------------------------------
+# CFG decode step
+# ---------------------------------------------------------------------------------------------------
+def test_cfg_merge_sample_bit_exact_vs_oracle(golden_dir):
+    """merge + sample on SUPPLIED logits: ids bit-exact for the same uniforms, greedy bit-exact, both merge modes;
+    logits taken from the reference-generated golden plus adversarial ones (ties, huge dynamic range)."""
+    from ospo_b200 import cfg_merge_sample
+
+    dev = _cuda()
+    d = np.load(golden_dir / "cfg_ref.npz")
+    logits = O.bits_to_bf16(d["logits_bf16"])              # [steps, 2P, V]
+    g = torch.Generator().manual_seed(77)
+    extra = (torch.randn(5, 8, 16384, generator=g) * 4.0).to(torch.bfloat16)
+    extra[0, :, 100:200] = extra[0, :, 100:101]            # runs of ties
+    extra[1] = extra[1] * 8.0                              # wide range: most weights underflow to 0
+    extra[2, 0::2] = extra[2, 1::2]                        # cond == uncond
+    for lg, w, T in ((logits, 5.0, 1.0), (extra, 5.0, 1.0), (extra, 3.0, 0.7), (extra, 7.5, 1.3)):
+        steps, twoP, V = lg.shape
+        P = twoP // 2
+        for mode_name, mode in (("bf16", 0), ("fp32", 1)):
+            u = torch.rand(steps, P, generator=g)
+            u[0, 0] = 0.0
+            u[-1, -1] = float(np.nextafter(np.float32(1.0), np.float32(0.0)))
+            ids, merged = cfg_merge_sample(lg.to(dev), w, T, uniforms=u.to(dev), merge_mode=mode_name,
+                                           return_merged=True)
+            gids = cfg_merge_sample(lg.to(dev), w, T, greedy=True, merge_mode=mode_name)
+            torch.cuda.synchronize()
+            for s in range(steps):
+                oid, omerged, _, _ = O.cfg_sample_det(lg[s], w, T, u[s], merge_mode=mode)
+                ogid, *_ = O.cfg_sample_det(lg[s], w, T, None, merge_mode=mode, greedy=True)
+                assert torch.equal(merged[s].cpu(), omerged), (mode_name, s)
+                assert torch.equal(ids[s].cpu(), oid), (mode_name, s, ids[s].cpu(), oid)
+                assert torch.equal(gids[s].cpu(), ogid), (mode_name, s)
+    # greedy == the reference's argmax of probs (golden, produced by the reference loop)
+    gids = cfg_merge_sample(logits.to(dev), 5.0, 1.0, greedy=True)
+    assert torch.equal(gids.cpu(), torch.from_numpy(d["greedy"]))
+
+
+def test_cfg_sample_fused_step_vs_oracle(golden_dir):
+    """whole decode step (swap-AB GEMMs + merge + sample): logits vs the reference-generated golden within bf16
+    tolerance; ids bit-exact against the oracle applied to the kernel's own dumped logits."""
+    dev = _cuda()
+    d = np.load(golden_dir / "cfg_ref.npz")
+    H, E, V, P, steps = int(d["H"]), int(d["E"]), int(d["V"]), int(d["P"]), int(d["STEPS"])
+    head = O.VisionHead(H, E, V).to(torch.bfloat16)
+    with torch.no_grad():
+        head.output_mlp_projector.weight.copy_(O.bits_to_bf16(d["W1_bf16"]))
+        head.output_mlp_projector.bias.copy_(O.bits_to_bf16(d["b1_bf16"]))
+        head.vision_head.weight.copy_(O.bits_to_bf16(d["W2_bf16"]))
+        head.vision_head.bias.copy_(O.bits_to_bf16(d["b2_bf16"]))
+    fh = _fused_from(head, dev, dtype=torch.bfloat16, requires_grad=False)
+    hidden = O.bits_to_bf16(d["hidden_bf16"])
+    ref_logits = O.bits_to_bf16(d["logits_bf16"])
+    g = torch.Generator().manual_seed(5)
+    for s in range(steps):
+        u = torch.rand(P, generator=g)
+        ids, lg = fh.cfg_sample(hidden[s].to(dev), 5.0, 1.0, uniforms=u.to(dev), return_logits=True)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(lg.float().cpu(), ref_logits[s].float(), rtol=2e-2, atol=2e-2)
+        oid, *_ = O.cfg_sample_det(lg.cpu(), 5.0, 1.0, u, merge_mode=0)
+        assert torch.equal(ids.cpu(), oid)
+        gid = fh.cfg_sample(hidden[s].to(dev), 5.0, 1.0, greedy=True)
+        ogid, *_ = O.cfg_sample_det(lg.cpu(), 5.0, 1.0, None, merge_mode=0, greedy=True)
+        assert torch.equal(gid.cpu(), ogid)
+
+
+def test_cfg_sample_7b_shape_p16():
+    """BASELINE.json configs[3] shape: P=16 (32 CFG rows), 7B-shaped head; a few steps vs the bf16 oracle."""
+    dev = _cuda()
+    H = E = 4096
+    V, P = 16384, 16
+    head_b = O.make_head(H, E, V, seed=1237, w2_gain=4.0).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    g = torch.Generator().manual_seed(1237)
+    for s in range(3):
+        h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16)
+        u = torch.rand(P, generator=g)
+        ids, lg = fh.cfg_sample(h.to(dev), 5.0, 1.0, uniforms=u.to(dev), return_logits=True)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            ref = head_b(h)
+        torch.testing.assert_close(lg.float().cpu(), ref.float(), rtol=2e-2, atol=3e-2)
+        oid, *_ = O.cfg_sample_det(lg.cpu(), 5.0, 1.0, u, merge_mode=0)
+        assert torch.equal(ids.cpu(), oid)
+        assert int(ids.min()) >= 0 and int(ids.max()) < V
+
+
+def test_generate_loop_mirror():
+    """generate_image_tokens keeps the reference loop's bookkeeping (image_generation.py:143-171)"""
+    from ospo_b200.generate import generate_image_tokens
+
+    dev = _cuda()
+    H, E, V, P, n = 64, 64, 16384, 2, 4
+    head_b = O.make_head(H, E, V, seed=21, w2_gain=4.0).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    g = torch.Generator().manual_seed(22)
+    hs = torch.randn(n, 2 * P, H, generator=g).to(torch.bfloat16).to(dev)
+    seen = []
+
+    def backbone_step(embeds, mask, past):
+        i = 0 if past is None else past
+        seen.append((tuple(embeds.shape), tuple(mask.shape)))
+        out = torch.zeros(2 * P, embeds.shape[1], H, dtype=torch.bfloat16, device=dev)
+        out[:, -1] = hs[i]
+        return out, i + 1
+
+    emb = torch.nn.Embedding(V, 8).to(dev)
+    u = torch.rand(n, P, generator=g).to(dev)
+    toks = generate_image_tokens(fh, backbone_step, lambda ids: emb(ids), torch.zeros(2 * P, 5, 8, device=dev),
+                                 torch.ones(2 * P, 5, dtype=torch.long, device=dev), image_token_num_per_image=n,
+                                 uniforms=u)
+    assert toks.shape == (P, n) and toks.dtype == torch.int32
+    assert seen[0] == ((2 * P, 5, 8), (2 * P, 5)) and seen[1] == ((2 * P, 1, 8), (2 * P, 6))
+    for i in range(n):
+        ids = fh.cfg_sample(hs[i], 5.0, 1.0, uniforms=u[i])
+        assert torch.equal(ids.to(torch.int32), toks[:, i])

@@ -14,9 +14,9 @@ from __future__ import annotations
 from typing import NamedTuple, Optional, Tuple
 
 import torch
-import torch.distributed as dist
 
 from . import _abi, ops
+from .dist import allreduce_mean_
 
 IGNORE_INDEX = -100  # tokenizer.label_pad_token_id, configs/step5.yaml:73
 
@@ -213,13 +213,9 @@ class FusedGenHead(torch.nn.Module):
     def _sync_flat_grads(flat: torch.Tensor, group) -> None:
         """DDP semantics (ospo/utils/train.py:26-28): average the head-weight gradients over the data-parallel
         ranks -- one NCCL all-reduce over the contiguous fp32 buffer dW2|dW1|db2|db1."""
-        if group is None or not dist.is_initialized():
+        if group is None:
             return
-        world = dist.get_world_size(group)
-        if world == 1:
-            return
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
+        allreduce_mean_(flat, group)
 
     # ---- reference-compatible call: logits ---------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,68 @@
+"""N > 1 host logic on CPU: gloo, world size 2.  Checks pair sharding and that the flat-gradient all-reduce
+reproduces single-process full-batch gradients of the oracle (DDP averaging with per-rank losses.mean())."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ospo_b200 import ops
+from ospo_b200.dist import allreduce_mean_, pair_shard, shard_concatenated
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import head_oracle as O
+
+    H, E, V, B, T, L = 16, 24, 64, 4, 6, 2
+    head = O.make_head(H, E, V, seed=1, w2_gain=3.0)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=2)
+    hidden, labels = torch.cat([hc, hr]), torch.cat([lc, lr])
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, loss_type="sigmoid")
+    h_loc, l_loc = shard_concatenated(hidden, labels, rank, world)
+    b = h_loc.shape[0] // 2
+    out = O.simpo_step(head, h_loc[:b], h_loc[b:], l_loc[:b], l_loc[b:], backward=True, **hp)
+    # pack exactly like the library's flat buffer: dW2 | dW1 | db2 | db1
+    flat = torch.cat([out["dW2"].reshape(-1), out["dW1"].reshape(-1), out["db2"], out["db1"]]).contiguous()
+    assert flat.numel() == ops.flat_grad_numel(H, E, V)
+    allreduce_mean_(flat, dist.group.WORLD)
+    loss = out["loss"].detach().clone()
+    dist.all_reduce(loss)
+    if rank == 0:
+        full = O.simpo_step(head, hc, hr, lc, lr, backward=True, **hp)
+        dW2, dW1, db2, db1 = ops.split_flat_grads(flat, H, E, V)
+        torch.testing.assert_close(dW2, full["dW2"], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(dW1, full["dW1"], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(db2, full["db2"], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(db1, full["db1"], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(loss / world, full["loss"].detach(), rtol=1e-6, atol=1e-7)
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pair_shard_layout():
+    assert pair_shard(8, 1, 4) == slice(2, 4)
+    with pytest.raises(ValueError):
+        pair_shard(6, 0, 4)
+    hidden = torch.arange(8).view(8, 1, 1).float()       # 4 chosen then 4 rejected
+    labels = torch.arange(8).view(8, 1)
+    h, l = shard_concatenated(hidden, labels, rank=1, world=2)
+    assert h.flatten().tolist() == [2, 3, 6, 7] and l.flatten().tolist() == [2, 3, 6, 7]
+
+
+def test_flat_gradient_allreduce_matches_full_batch_gloo_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()

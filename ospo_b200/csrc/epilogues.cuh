@@ -2,6 +2,7 @@
 // Each epilogue thread owns ONE accumulator row and receives it 32 columns at a time, so every
 // row-wise quantity of the image-token head (online log-sum-exp over the 16384 codes, the
 // target-logit gather, the logits row-sum metric) is thread-local: no shuffles, no shared memory.
+// `chunk<FULL>`: FULL = all 32 columns are inside N -> branch- and predicate-free fast path.
 #pragma once
 
 #include "gemm_sm100.cuh"
@@ -17,18 +18,61 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32], int valid) {
-  if (valid >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// bf16 pair: round two floats to bf16 (RN), return the packed word and the rounded values as floats
+__device__ __forceinline__ uint32_t round_pair_bf16(float& a, float& b) {
+  const uint32_t u = pack_bf16x2(a, b);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xFFFF0000u);
+  return u;
+}
+
+// 32 consecutive fp32 values from a 16-byte aligned address (bias slices: same address across the warp)
+__device__ __forceinline__ void load32_f32_vec(const float* __restrict__ src, float (&b)[32]) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      d4[i] = u;
-    }
+  for (int i = 0; i < 8; ++i) {
+    const float4 t = __ldg(s4 + i);
+    b[4 * i] = t.x;
+    b[4 * i + 1] = t.y;
+    b[4 * i + 2] = t.z;
+    b[4 * i + 3] = t.w;
+  }
+}
+
+template <bool FULL>
+__device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int col0, int valid, float (&b)[32]) {
+  if (bias == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = 0.0f;
+    return;
+  }
+  if (FULL && ((reinterpret_cast<uintptr_t>(bias + col0) & 15u) == 0)) {
+    load32_f32_vec(bias + col0, b);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = (j < valid) ? __ldg(bias + col0 + j) : 0.0f;
+  }
+}
+
+__device__ __forceinline__ void store_packed16(__nv_bfloat16* dst, const uint32_t (&pk)[16]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+}
+
+template <bool FULL>
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32], int valid) {
+  if (FULL && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    store_packed16(dst, pk);
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -36,8 +80,9 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float
   }
 }
 
+template <bool FULL>
 __device__ __forceinline__ void store_row32_f32(float* dst, const float (&v)[32], int valid) {
-  if (valid >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+  if (FULL && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
     float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
     for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -48,8 +93,9 @@ __device__ __forceinline__ void store_row32_f32(float* dst, const float (&v)[32]
   }
 }
 
+template <bool FULL>
 __device__ __forceinline__ void load_row32_bf16(const __nv_bfloat16* src, float (&v)[32], int valid) {
-  if (valid >= 32 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+  if (FULL && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -57,9 +103,8 @@ __device__ __forceinline__ void load_row32_bf16(const __nv_bfloat16* src, float 
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-        v[8 * i + 2 * k] = __low2float(p);
-        v[8 * i + 2 * k + 1] = __high2float(p);
+        v[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
+        v[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
       }
     }
   } else {
@@ -88,21 +133,27 @@ struct EpiStore {
   __device__ static void begin(const Params& p, State& st, int row, int, const GemmDims& d, uint8_t*) {
     st.rb = (ROW_BIAS && p.bias != nullptr && row < d.M) ? __ldg(p.bias + row) : 0.0f;
   }
+  template <bool FULL>
   __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
                                uint8_t*) {
     if (row >= d.M) return;
-    const int valid = d.N - col0;
+    const int valid = FULL ? 32 : d.N - col0;
     if (valid <= 0) return;
+    if constexpr (ROW_BIAS) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float b = st.rb;
-      if (!ROW_BIAS && p.bias != nullptr && j < valid) b = __ldg(p.bias + col0 + j);
-      v[j] += b;
+      for (int j = 0; j < 32; ++j) v[j] += st.rb;
+    } else {
+      if (p.bias != nullptr) {
+        float b[32];
+        load_bias32<FULL>(p.bias, col0, valid, b);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += b[j];
+      }
     }
     if constexpr (!TRANSPOSE) {
       OutT* dst = p.out + static_cast<int64_t>(row) * p.ld + col0;
-      if constexpr (sizeof(OutT) == 4) store_row32_f32(reinterpret_cast<float*>(dst), v, valid);
-      else store_row32_bf16(reinterpret_cast<__nv_bfloat16*>(dst), v, valid);
+      if constexpr (sizeof(OutT) == 4) store_row32_f32<FULL>(reinterpret_cast<float*>(dst), v, valid);
+      else store_row32_bf16<FULL>(reinterpret_cast<__nv_bfloat16*>(dst), v, valid);
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -139,30 +190,44 @@ struct EpiBiasGelu {
   __device__ static void begin(const Params& p, State& st, int row, int, const GemmDims& d, uint8_t*) {
     st.rb = (TRANSPOSE && row < d.M) ? __ldg(p.bias + row) : 0.0f;
   }
+  template <bool FULL>
   __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
                                uint8_t*) {
     if (row >= d.M) return;
-    const int valid = d.N - col0;
+    const int valid = FULL ? 32 : d.N - col0;
     if (valid <= 0) return;
-    float a[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float b = st.rb;
-      if (!TRANSPOSE && j < valid) b = __ldg(p.bias + col0 + j);
-      v[j] = bf16_round(v[j] + b);
-      a[j] = gelu_erf(v[j]);
-    }
     if constexpr (!TRANSPOSE) {
+      float b[32];
+      load_bias32<FULL>(p.bias, col0, valid, b);
       const int64_t off = static_cast<int64_t>(row) * p.ld + col0;
-      if constexpr (STORE_PRE) store_row32_bf16(p.pre + off, v, valid);
-      store_row32_bf16(p.act + off, a, valid);
+      if (FULL && ((reinterpret_cast<uintptr_t>(p.act + off) & 15u) == 0)) {
+        uint32_t pp[16], pa[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x0 = v[2 * i] + b[2 * i], x1 = v[2 * i + 1] + b[2 * i + 1];
+          pp[i] = round_pair_bf16(x0, x1);
+          pa[i] = pack_bf16x2(gelu_erf(x0), gelu_erf(x1));
+        }
+        if constexpr (STORE_PRE) store_packed16(p.pre + off, pp);
+        store_packed16(p.act + off, pa);
+      } else {
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = bf16_round(v[j] + b[j]);
+          a[j] = gelu_erf(v[j]);
+        }
+        if constexpr (STORE_PRE) store_row32_bf16<false>(p.pre + off, v, valid);
+        store_row32_bf16<false>(p.act + off, a, valid);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (j < valid) {
+          const float x = bf16_round(v[j] + st.rb);
           const int64_t off = static_cast<int64_t>(col0 + j) * p.ld + row;
-          if constexpr (STORE_PRE) p.pre[off] = __float2bfloat16_rn(v[j]);
-          p.act[off] = __float2bfloat16_rn(a[j]);
+          if constexpr (STORE_PRE) p.pre[off] = __float2bfloat16_rn(x);
+          p.act[off] = __float2bfloat16_rn(gelu_erf(x));
         }
       }
     }
@@ -172,7 +237,7 @@ struct EpiBiasGelu {
 
 // ---------------------------------------------------------------------------
 // GEMM2 forward epilogue:  logits = bf16(acc + b2), plus -- without ever materialising fp32 logits or a
-// log-softmax tensor -- per (row, N-tile) partial (max, sum-exp), the gathered target logit and the
+// log-softmax tensor -- per (row, column sub-tile) partial (max, sum-exp), the gathered target logit and the
 // partial row-sum of the logits.  The bf16 logits are (optionally) spilled once for the backward pass.
 // reference: vision_head Linear (modeling_vlm.py:50) + log_softmax/gather (ospo/wrapper/train.py:391).
 // The log-sum-exp is taken over the bf16-rounded logits in fp32, which is what the bf16 reference
@@ -184,8 +249,8 @@ struct EpiLogitsLse {
     __nv_bfloat16* logits;      // [rows, V] spill (may be null)
     int64_t ld;
     const int64_t* labels;      // [rows] target code per row
-    float2* part;               // [num_n, rows] (max, sumexp) partials
-    float* rowsum_part;         // [num_n, rows] partial sums of logits (may be null)
+    float2* part;               // [num_sub_tiles, rows] (max, sumexp) partials
+    float* rowsum_part;         // [num_sub_tiles, rows] partial sums of logits (may be null)
     float* tgt;                 // [rows] gathered target logit
   };
   struct State {
@@ -194,6 +259,7 @@ struct EpiLogitsLse {
     bool hit;
   };
   static constexpr int SMEM_BYTES = 0;
+  static constexpr float LOG2E = 1.4426950408889634f;
 
   __device__ static void begin(const Params& p, State& st, int row, int, const GemmDims& d, uint8_t*) {
     st.m = -INFINITY;
@@ -203,54 +269,75 @@ struct EpiLogitsLse {
     st.hit = false;
     st.label = (row < d.M) ? static_cast<int>(__ldg(p.labels + row)) : -1;
   }
+  template <bool FULL>
   __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
                                uint8_t*) {
     if (row >= d.M) return;
-    const int valid = d.N - col0;
+    const int valid = FULL ? 32 : d.N - col0;
     if (valid <= 0) return;
+    float b[32];
+    load_bias32<FULL>(p.bias, col0, valid, b);
     float cmax = -INFINITY;
+    if constexpr (FULL) {
+      uint32_t pk[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float b = (j < valid) ? __ldg(p.bias + col0 + j) : 0.0f;
-      v[j] = bf16_round(v[j] + b);
-      if (j < valid) cmax = fmaxf(cmax, v[j]);
+      for (int i = 0; i < 16; ++i) {
+        v[2 * i] += b[2 * i];
+        v[2 * i + 1] += b[2 * i + 1];
+        pk[i] = round_pair_bf16(v[2 * i], v[2 * i + 1]);
+        cmax = fmaxf(cmax, fmaxf(v[2 * i], v[2 * i + 1]));
+      }
+      if (p.logits != nullptr) {
+        __nv_bfloat16* dst = p.logits + static_cast<int64_t>(row) * p.ld + col0;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) store_packed16(dst, pk);
+        else store_row32_bf16<false>(dst, v, 32);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = bf16_round(v[j] + b[j]);
+        if (j < valid) cmax = fmaxf(cmax, v[j]);
+      }
+      if (p.logits != nullptr) store_row32_bf16<false>(p.logits + static_cast<int64_t>(row) * p.ld + col0, v, valid);
     }
-    if (p.logits != nullptr) store_row32_bf16(p.logits + static_cast<int64_t>(row) * p.ld + col0, v, valid);
-    constexpr float LOG2E = 1.4426950408889634f;
     if (cmax > st.m) {
-      st.s *= exp2f((st.m - cmax) * LOG2E);  // exp2f(-inf) = 0 on the first chunk
+      st.s *= ex2_approx((st.m - cmax) * LOG2E);  // ex2(-inf) = 0 on the first chunk
       st.m = cmax;
     }
     const float mneg = -st.m * LOG2E;
-    float acc = 0.0f, lsum = 0.0f;
+    float acc0 = 0.0f, acc1 = 0.0f, ls0 = 0.0f, ls1 = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < valid) {
-        acc += exp2f(fmaf(v[j], LOG2E, mneg));
-        lsum += v[j];
+    for (int j = 0; j < 32; j += 2) {
+      if (FULL || j < valid) {
+        acc0 += ex2_approx(fmaf(v[j], LOG2E, mneg));
+        ls0 += v[j];
+      }
+      if (FULL || j + 1 < valid) {
+        acc1 += ex2_approx(fmaf(v[j + 1], LOG2E, mneg));
+        ls1 += v[j + 1];
       }
     }
-    st.s += acc;
-    st.sum += lsum;
+    st.s += acc0 + acc1;
+    st.sum += ls0 + ls1;
     const int rel = st.label - col0;
-    if (rel >= 0 && rel < valid && rel < 32) {
+    if (rel >= 0 && rel < valid) {
       st.hit = true;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j == rel) st.tgt = v[j];
     }
   }
-  __device__ static void end(const Params& p, State& st, int row, int, int n_blk, const GemmDims& d, uint8_t*) {
+  __device__ static void end(const Params& p, State& st, int row, int, int sub_tile, const GemmDims& d, uint8_t*) {
     if (row >= d.M) return;
-    const int64_t idx = static_cast<int64_t>(n_blk) * d.M + row;
+    const int64_t idx = static_cast<int64_t>(sub_tile) * d.M + row;
     p.part[idx] = make_float2(st.m, st.s);
     if (p.rowsum_part != nullptr) p.rowsum_part[idx] = st.sum;
-    if (st.hit) p.tgt[row] = st.tgt;  // only the N-tile that holds the label column writes
+    if (st.hit) p.tgt[row] = st.tgt;  // only the sub-tile that holds the label column writes
   }
 };
 
 // ---------------------------------------------------------------------------
-// dAct GEMM epilogue:  dpre = bf16(acc * gelu'(pre))      (autograd of GELU)
+// dAct GEMM epilogue:  dpre = bf16(bf16(acc) * gelu'(pre))      (autograd of GELU)
 // ---------------------------------------------------------------------------
 struct EpiGeluBwd {
   struct Params {
@@ -261,17 +348,18 @@ struct EpiGeluBwd {
   struct State {};
   static constexpr int SMEM_BYTES = 0;
   __device__ static void begin(const Params&, State&, int, int, const GemmDims&, uint8_t*) {}
+  template <bool FULL>
   __device__ static void chunk(const Params& p, State&, int row, int col0, float (&v)[32], const GemmDims& d,
                                uint8_t*) {
     if (row >= d.M) return;
-    const int valid = d.N - col0;
+    const int valid = FULL ? 32 : d.N - col0;
     if (valid <= 0) return;
     const int64_t off = static_cast<int64_t>(row) * p.ld + col0;
     float pre[32];
-    load_row32_bf16(p.pre + off, pre, valid);
+    load_row32_bf16<FULL>(p.pre + off, pre, valid);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]) * gelu_erf_grad(pre[j]);
-    store_row32_bf16(p.dpre + off, v, valid);
+    store_row32_bf16<FULL>(p.dpre + off, v, valid);
   }
   __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
 };

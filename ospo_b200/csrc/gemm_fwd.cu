@@ -11,7 +11,8 @@ void set_watchdog_fwd(uint32_t* dev_ptr) { cudaMemcpyToSymbol(g_watchdog_buf, &d
 using Cfg1 = GemmCfg<1, 256, false, false>;
 using Cfg2 = GemmCfg<2, 256, false, false>;
 
-int gemm2_num_n_tiles(int V) { return (V + 255) / 256; }
+// number of (max, sum-exp) partials per row: one per 256-column tile and epilogue column half
+int gemm2_num_n_tiles(int V) { return ((V + 255) / 256) * Cfg2::EPI_SPLIT; }
 
 int launch_gemm1_bias_gelu(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w1, const float* b1,
                            __nv_bfloat16* pre, __nv_bfloat16* act, int rows, int H, int E) {

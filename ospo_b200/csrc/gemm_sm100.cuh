@@ -12,8 +12,9 @@
 // (global layout [K, rows], rows contiguous); the latter is what the two weight-gradient GEMMs
 // and the two data-gradient GEMMs of the head need, so no transposed copies are ever made.
 //
-// Warp roles (256 threads):  0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
-//                            4..7 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +32).
+// Warp roles:  0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
+//              4.. = epilogue (warp w owns TMEM lanes 32*(w%4) .. +32; with 8 epilogue warps, warps 4-7
+//              take the left half of the tile's columns and warps 8-11 the right half).
 #pragma once
 
 #include "ptx.cuh"
@@ -56,7 +57,11 @@ struct GemmCfg {
   static constexpr int TMEM_COLS =
       TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + EPI_SMEM_BYTES;
-  static constexpr int THREADS = 256;
+  // Epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, each taking half of the tile's
+  // columns) -- a lone warp per scheduler cannot hide the latency of a math-heavy epilogue.
+  static constexpr int EPI_SPLIT = (BN >= 64) ? 2 : 1;
+  static constexpr int EPI_WARPS = 4 * EPI_SPLIT;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16, 256]");
   static_assert(!B_MN || (B_ROWS % 64 == 0), "MN-major B is staged in 64-row swizzle atoms");
   static_assert(B_ROWS % 8 == 0, "K-major B rows come in 8-row swizzle groups");
@@ -84,12 +89,15 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n, int
 //     struct Params { ... };                      // POD, passed by value to the kernel
 //     struct State  { ... };                      // per-thread registers that live across one tile
 //     static constexpr int SMEM_BYTES;
-//     __device__ static void begin(const Params&, State&, int row, int n0, const GemmDims&);
-//     __device__ static void chunk(const Params&, State&, int row, int col0, float (&v)[32], const GemmDims&);
-//     __device__ static void end(const Params&, State&, int row, int n0, int n_blk, const GemmDims&);
+//     __device__ static void begin(const Params&, State&, int row, int n0, const GemmDims&, uint8_t* smem);
+//     template <bool FULL>
+//     __device__ static void chunk(const Params&, State&, int row, int col0, float (&v)[32], const GemmDims&, ...);
+//     __device__ static void end(const Params&, State&, int row, int n0, int sub_tile, const GemmDims&, ...);
 //   };
 // `row` is the global accumulator row owned by the calling thread (may be >= M: the functor must
-// guard its global accesses), `col0` the global column of v[0].
+// guard its global accesses), `col0` the global column of v[0].  FULL promises that all 32 columns of
+// the chunk are inside N (the common case: no per-element predicates).  With EPI_SPLIT == 2 a (row, tile)
+// is handled by two threads (column halves); `sub_tile` = n_blk * EPI_SPLIT + half identifies the part.
 
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
@@ -132,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(&tmem_full_bar[a], 1);        // one tcgen05.commit per tile
-      mbar_init(&tmem_empty_bar[a], 4 * CG);  // one arrive per epilogue warp of every CTA in the group
+      mbar_init(&tmem_empty_bar[a], Cfg::EPI_WARPS * CG);  // one arrive per epilogue warp of every CTA in the group
     }
     fence_mbar_init();
   }
@@ -229,7 +237,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int q = warp & 3;            // TMEM lane quarter this warp may touch
+    const int half = (warp - 4) >> 2;  // which half of the tile's columns (EPI_SPLIT == 2)
     uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 256;
     uint32_t leader_tmem_empty_addr[ACC_STAGES];
 #pragma unroll
@@ -249,15 +258,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
       typename Epi::State st;
       Epi::begin(ep, st, row, n0, dims, epi_smem);
+      // This warp's share of the tile: NC chunks of 32 columns starting at chunk c0.  TMEM loads are
+      // software-pipelined: the load of chunk c+1 is in flight while chunk c is processed.
+      constexpr int NC = BN / 32 / Cfg::EPI_SPLIT;
+      const int c0 = half * NC;
+      const bool full = (n0 + BN <= dims.N);
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 * 32), ra);
+      tmem_ld_wait(ra);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(c * 32), r);
-        tmem_ld_wait(r);
-        float v[32];
+      for (int c = 0; c < NC; c += 2) {
+        if (c + 1 < NC) tmem_ld_32x32(taddr + static_cast<uint32_t>((c0 + c + 1) * 32), rb);
+        {
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        Epi::chunk(ep, st, row, n0 + c * 32, v, dims, epi_smem);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+          if (full) Epi::template chunk<true>(ep, st, row, n0 + (c0 + c) * 32, v, dims, epi_smem);
+          else Epi::template chunk<false>(ep, st, row, n0 + (c0 + c) * 32, v, dims, epi_smem);
+        }
+        if (c + 1 < NC) {
+          tmem_ld_wait(rb);
+          if (c + 2 < NC) tmem_ld_32x32(taddr + static_cast<uint32_t>((c0 + c + 2) * 32), ra);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rb[j]);
+          if (full) Epi::template chunk<true>(ep, st, row, n0 + (c0 + c + 1) * 32, v, dims, epi_smem);
+          else Epi::template chunk<false>(ep, st, row, n0 + (c0 + c + 1) * 32, v, dims, epi_smem);
+          if (c + 2 < NC) tmem_ld_wait(ra);
+        }
       }
       // accumulator stage drained: hand it back to the MMA issuer
       tc_fence_before();
@@ -266,7 +294,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[as]);
         else mbar_arrive_cluster(leader_tmem_empty_addr[as]);
       }
-      Epi::end(ep, st, row, n0, tc.n_blk, dims, epi_smem);
+      Epi::end(ep, st, row, n0, tc.n_blk * Cfg::EPI_SPLIT + half, dims, epi_smem);
     }
   }
 

@@ -148,8 +148,11 @@ struct Workspace {
   float* seq_sum;        // [S]
   float* seq_logit_sum;  // [S]
   __nv_bfloat16* rows_by_e;  // [rows, E]: dpre (backward) / act (plain logits, decode)
+  float* decode_part;        // [8, rows, E] split-K partials of the decode GEMM1 (decode-sized shapes only)
   size_t total;
 };
+
+constexpr size_t kDecodeMaxRows = 512;  // 2P rows of a CFG decode step
 
 Workspace carve(const ospo_head_shape& s, void* base) {
   Workspace w;
@@ -170,6 +173,9 @@ Workspace carve(const ospo_head_shape& s, void* base) {
   w.seq_sum = reinterpret_cast<float*>(take(S * sizeof(float)));
   w.seq_logit_sum = reinterpret_cast<float*>(take(S * sizeof(float)));
   w.rows_by_e = reinterpret_cast<__nv_bfloat16*>(take(rows * static_cast<size_t>(s.embed) * 2));
+  w.decode_part = (rows <= kDecodeMaxRows)
+                      ? reinterpret_cast<float*>(take(8 * rows * static_cast<size_t>(s.embed) * sizeof(float)))
+                      : nullptr;
   w.total = off;
   return w;
 }
@@ -378,17 +384,8 @@ static int launch_sampler(const ospo_cfg_args* a, int pairs, cudaStream_t st) {
   if (!a->greedy && !a->uniforms) return OSPO_ERR_NULL;
   if (!a->ids || !a->logits) return OSPO_ERR_NULL;
   if (!(a->temperature > 0.0f)) return OSPO_ERR_UNSUPPORTED;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(V) + V / 32 + SAMPLE_THREADS + 32 + SAMPLE_THREADS) +
-                      sizeof(int) * SAMPLE_THREADS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(cfg_merge_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem)) != cudaSuccess)
-      return OSPO_ERR_CUDA;
-    attr_set = true;
-  }
   KernelSpan ks(st, OSPO_K_SAMPLER);
-  cfg_merge_sample_kernel<<<pairs, SAMPLE_THREADS, smem, st>>>(static_cast<const __nv_bfloat16*>(a->logits), V, V,
+  cfg_merge_sample_kernel<<<pairs, SAMPLE_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(a->logits), V, V,
                                                               a->cfg_weight, a->temperature, a->merge_mode,
                                                               a->uniforms, a->greedy, a->ids, a->merged);
   return check_launch();
@@ -418,13 +415,20 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const LaunchCtx c = make_ctx(st);
   const ospo_head_shape& s = a->shape;
+  if (static_cast<size_t>(s.rows) > kDecodeMaxRows) return OSPO_ERR_UNSUPPORTED;
   {
     KernelSpan ks(st, OSPO_K_DECODE_GEMM1);
+    const int64_t split_stride = static_cast<int64_t>(s.rows) * s.embed;
     rc = map_rc(launch_decode_gemm1(c, static_cast<const __nv_bfloat16*>(a->h),
-                                    static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1, w.rows_by_e, s.rows,
+                                    static_cast<const __nv_bfloat16*>(a->w.w1), w.decode_part, split_stride, s.rows,
                                     s.hidden, s.embed));
+    if (rc) return rc;
+    const int n_el = s.rows * s.embed;
+    decode_act_finalize_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(
+        w.decode_part, decode_gemm1_splits(c.num_sms, s.hidden, s.embed), split_stride, a->w.b1, w.rows_by_e, s.rows,
+        s.embed);
+    if ((rc = check_launch())) return rc;
   }
-  if (rc) return rc;
   {
     KernelSpan ks(st, OSPO_K_DECODE_GEMM2);
     rc = map_rc(launch_decode_gemm2(c, w.rows_by_e, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,

@@ -130,7 +130,7 @@ struct EpiStore {
   };
   static constexpr int SMEM_BYTES = 0;
 
-  __device__ static void begin(const Params& p, State& st, int row, int, const GemmDims& d, uint8_t*) {
+  __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
     st.rb = (ROW_BIAS && p.bias != nullptr && row < d.M) ? __ldg(p.bias + row) : 0.0f;
   }
   template <bool FULL>
@@ -169,6 +169,36 @@ struct EpiStore {
 };
 
 // ---------------------------------------------------------------------------
+// Split-K partial store for the swap-AB decode GEMMs: part[k_split][col][row] = acc (fp32, transposed so
+// that the 32 lanes of a warp write 32 consecutive floats).  The partials are summed in a fixed order by
+// the finalize kernel, so the result is deterministic (no atomics).
+// ---------------------------------------------------------------------------
+struct EpiPartialStoreT {
+  struct Params {
+    float* part;        // [k_splits, n, ld]
+    int64_t ld;         // elements per sample row (= M)
+    int64_t split_stride;
+  };
+  struct State {
+    float* base;
+  };
+  static constexpr int SMEM_BYTES = 0;
+  __device__ static void begin(const Params& p, State& st, int row, int, int ks, const GemmDims&, uint8_t*) {
+    st.base = p.part + static_cast<int64_t>(ks) * p.split_stride + row;
+  }
+  template <bool FULL>
+  __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
+                               uint8_t*) {
+    if (row >= d.M) return;
+    const int valid = FULL ? 32 : d.N - col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (FULL || j < valid) st.base[static_cast<int64_t>(col0 + j) * p.ld] = v[j];
+  }
+  __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
+};
+
+// ---------------------------------------------------------------------------
 // GEMM1 epilogue:  pre = bf16(acc + b1);  act = bf16(gelu_erf(pre))
 // (reference: output_mlp_projector + vision_activation, modeling_vlm.py:47-49; the activation is
 //  applied to the bf16-rounded Linear output exactly as the bf16 reference path does.)
@@ -187,7 +217,7 @@ struct EpiBiasGelu {
   };
   static constexpr int SMEM_BYTES = 0;
 
-  __device__ static void begin(const Params& p, State& st, int row, int, const GemmDims& d, uint8_t*) {
+  __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
     st.rb = (TRANSPOSE && row < d.M) ? __ldg(p.bias + row) : 0.0f;
   }
   template <bool FULL>
@@ -261,7 +291,7 @@ struct EpiLogitsLse {
   static constexpr int SMEM_BYTES = 0;
   static constexpr float LOG2E = 1.4426950408889634f;
 
-  __device__ static void begin(const Params& p, State& st, int row, int, const GemmDims& d, uint8_t*) {
+  __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
     st.m = -INFINITY;
     st.s = 0.0f;
     st.sum = 0.0f;
@@ -347,7 +377,7 @@ struct EpiGeluBwd {
   };
   struct State {};
   static constexpr int SMEM_BYTES = 0;
-  __device__ static void begin(const Params&, State&, int, int, const GemmDims&, uint8_t*) {}
+  __device__ static void begin(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
   template <bool FULL>
   __device__ static void chunk(const Params& p, State&, int row, int col0, float (&v)[32], const GemmDims& d,
                                uint8_t*) {

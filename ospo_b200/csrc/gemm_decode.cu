@@ -12,13 +12,24 @@ void set_watchdog_decode(uint32_t* dev_ptr) { cudaMemcpyToSymbol(g_watchdog_buf,
 using CfgS32 = GemmCfg<1, 32, false, false>;
 using CfgS128 = GemmCfg<1, 128, false, false>;
 
-int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
-                        __nv_bfloat16* act, int n, int H, int E) {
-  using Epi = EpiBiasGelu<true, false>;
-  Epi::Params p{b1, nullptr, act, E};
-  // D[E, n] = W1[E, H] * h[n, H]^T
-  if (n <= 32) return launch_gemm<CfgS32, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream);
-  return launch_gemm<CfgS128, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream);
+int decode_gemm1_splits(int num_sms, int H, int E) {
+  // enough (tile, k-split) work items to occupy every SM with a disjoint slab of W1; at most 8 partials
+  const int num_m = (E + 127) / 128;
+  int want = num_sms / (num_m > 0 ? num_m : 1);
+  if (want > 8) want = 8;
+  int ks, per;
+  gemm_split_plan((H + 63) / 64, want, &ks, &per);
+  return ks;
+}
+
+int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, float* part,
+                        int64_t split_stride, int n, int H, int E) {
+  using Epi = EpiPartialStoreT;
+  Epi::Params p{part, E, split_stride};
+  const int ks = decode_gemm1_splits(c.num_sms, H, E);
+  // D[E, n] = W1[E, H] * h[n, H]^T, as k-split partials part[ks][n][E]
+  if (n <= 32) return launch_gemm<CfgS32, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks);
+  return launch_gemm<CfgS128, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks);
 }
 
 int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,

@@ -23,7 +23,9 @@ namespace ospo {
 
 struct GemmDims {
   int M, N, K;
-  int group_m;  // rasterisation: tiles are walked M-fastest inside groups of `group_m` M-blocks
+  int group_m;       // rasterisation: tiles are walked M-fastest inside groups of `group_m` M-blocks
+  int k_splits;      // split-K: each output tile is produced as k_splits partial tiles (1 = off)
+  int kb_per_split;  // k-blocks (of BK) per split; every split is non-empty
 };
 
 // watchdog site ids
@@ -89,7 +91,7 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n, int
 //     struct Params { ... };                      // POD, passed by value to the kernel
 //     struct State  { ... };                      // per-thread registers that live across one tile
 //     static constexpr int SMEM_BYTES;
-//     __device__ static void begin(const Params&, State&, int row, int n0, const GemmDims&, uint8_t* smem);
+//     __device__ static void begin(const Params&, State&, int row, int n0, int k_split, const GemmDims&, uint8_t* smem);
 //     template <bool FULL>
 //     __device__ static void chunk(const Params&, State&, int row, int col0, float (&v)[32], const GemmDims&, ...);
 //     __device__ static void end(const Params&, State&, int row, int n0, int sub_tile, const GemmDims&, ...);
@@ -124,8 +126,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int num_m = (dims.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
   const int num_n = (dims.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
   const int num_kb = (dims.K + BK - 1) / BK;
+  const int ksplits = dims.k_splits;
+  const int num_tiles = num_m * num_n * ksplits;  // work items: (tile, k-split), splits of a tile adjacent
   const int cluster_id = blockIdx.x / CG;
   const int num_clusters = gridDim.x / CG;
 
@@ -158,10 +161,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const TileCoord tc = tile_coord(t, num_m, num_n, dims.group_m);
+        const TileCoord tc = tile_coord(t / ksplits, num_m, num_n, dims.group_m);
         const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
         const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = (t % ksplits) * dims.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1u, SITE_PRODUCER_EMPTY);
           uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
@@ -209,7 +214,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mbar_wait(&tmem_empty_bar[as], aph ^ 1u, SITE_MMA_TMEM_EMPTY);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = (t % ksplits) * dims.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph, SITE_MMA_FULL);
           tc_fence_after();
           if (elect_one()) {
@@ -219,15 +226,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
               const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, A_LBO, A_SBO);
               const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, B_LBO, B_SBO);
-              umma_bf16<CG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16<CG>(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             }
             // free the smem slot once these MMAs have drained it; on the last k-block also publish the tile
             if constexpr (CG == 1) {
               umma_commit(&empty_bar[s]);
-              if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+              if (kb == kb1 - 1) umma_commit(&tmem_full_bar[as]);
             } else {
               umma_commit_2sm(&empty_bar[s], 0x3);
-              if (kb == num_kb - 1) umma_commit_2sm(&tmem_full_bar[as], 0x3);
+              if (kb == kb1 - 1) umma_commit_2sm(&tmem_full_bar[as], 0x3);
             }
           }
           __syncwarp();
@@ -248,7 +255,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-      const TileCoord tc = tile_coord(t, num_m, num_n, dims.group_m);
+      const TileCoord tc = tile_coord(t / ksplits, num_m, num_n, dims.group_m);
+      const int ks = t % ksplits;
       const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
       const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
       const int row = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM + q * 32 + lane;
@@ -257,7 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
       typename Epi::State st;
-      Epi::begin(ep, st, row, n0, dims, epi_smem);
+      Epi::begin(ep, st, row, n0, ks, dims, epi_smem);
       // This warp's share of the tile: NC chunks of 32 columns starting at chunk c0.  TMEM loads are
       // software-pipelined: the load of chunk c+1 is in flight while chunk c is processed.
       constexpr int NC = BN / 32 / Cfg::EPI_SPLIT;
@@ -343,10 +351,19 @@ inline int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, 
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// split-K plan: at most `want` splits, every split non-empty
+inline void gemm_split_plan(int num_kb, int want, int* k_splits, int* kb_per_split) {
+  int ks = want < 1 ? 1 : (want > num_kb ? num_kb : want);
+  const int per = (num_kb + ks - 1) / ks;
+  ks = (num_kb + per - 1) / per;
+  *k_splits = ks;
+  *kb_per_split = per;
+}
+
 // a / b: global pointers.  K-major operand: [rows, K] with pitch ld; MN-major operand: [K, rows] with pitch ld.
 template <class Cfg, class Epi>
 int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K, int group_m,
-                const typename Epi::Params& ep, int num_sms, cudaStream_t stream) {
+                const typename Epi::Params& ep, int num_sms, cudaStream_t stream, int k_splits = 1) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   CUtensorMap ta, tb;
   int rc;
@@ -369,9 +386,11 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   dims.N = N;
   dims.K = K;
   dims.group_m = group_m > 0 ? group_m : 8;
+  const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
+  gemm_split_plan(num_kb, k_splits, &dims.k_splits, &dims.kb_per_split);
   const int num_m = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
   const int num_n = (N + Cfg::BN - 1) / Cfg::BN;
-  const int num_tiles = num_m * num_n;
+  const int num_tiles = num_m * num_n * dims.k_splits;
   int clusters = num_sms / Cfg::CG;
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;

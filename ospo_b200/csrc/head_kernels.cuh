@@ -262,6 +262,21 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, in
 }
 
 // ---------------------------------------------------------------------------
+// decode GEMM1 finalize: act[n, e] = bf16(gelu_erf(bf16(sum_k part[k][n][e] + b1[e])))  (fixed summation order)
+// ---------------------------------------------------------------------------
+__global__ void decode_act_finalize_kernel(const float* __restrict__ part, int k_splits, int64_t split_stride,
+                                           const float* __restrict__ b1, __nv_bfloat16* __restrict__ act, int n,
+                                           int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * E) return;
+  float s = part[i];
+  for (int k = 1; k < k_splits; ++k) s += part[static_cast<int64_t>(k) * split_stride + i];
+  const float x = bf16_round(s + __ldg(b1 + (i % E)));
+  const float g = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  act[i] = __float2bfloat16_rn(g);
+}
+
+// ---------------------------------------------------------------------------
 // CFG merge + temperature + softmax + inverse-CDF sampling on bf16 logits [2P, V]
 // (row 2k = conditional, row 2k+1 = unconditional: ospo/wrapper/image_generation.py:135-141,157-158).
 //   merge_mode 0 (reference bf16 semantics, op-by-op rounding, image_generation.py:160-161):
@@ -311,125 +326,156 @@ __device__ __forceinline__ float cfg_merge(float lc, float lu, float w, float T,
 }
 
 // grid.x = number of (cond, uncond) pairs; logits row pitch ld.  vocab must be 16384 (= 512 * 32).
-__global__ void __launch_bounds__(SAMPLE_THREADS)
+// Register-resident: thread i owns segment i (codes 32 i .. 32 i + 31): it loads its 64 bytes of the
+// conditional and of the unconditional row, keeps the 32 merged values / weights in registers, and the
+// only shared memory is 512 segment sums + 16 group sums.  Three block barriers in total.
+__global__ void __launch_bounds__(SAMPLE_THREADS, 2)
 cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int vocab, float cfg_weight,
                         float temperature, int merge_mode, const float* __restrict__ uniforms, int greedy,
                         int64_t* __restrict__ ids, float* __restrict__ merged_out /* [P, V] optional */) {
-  extern __shared__ float sm[];
-  // t/w values, padded by one float per 32 so that "thread i walks segment i" is bank-conflict free
-  float* tv = sm;                                      // vocab + vocab/32 floats
-  float* seg_sum = tv + vocab + vocab / 32;            // 512
-  float* grp_sum = seg_sum + SAMPLE_THREADS;           // 16
-  float* red = grp_sum + 32;                           // 512 (max / argmax value)
-  int* redi = reinterpret_cast<int*>(red + SAMPLE_THREADS);  // 512
+  __shared__ float seg_sum[SAMPLE_THREADS];
+  __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
+  __shared__ float wmax[SAMPLE_THREADS / 32];
+  __shared__ int warg[SAMPLE_THREADS / 32];
   const int p = blockIdx.x;
   const int tid = threadIdx.x;
-  const __nv_bfloat16* lc = logits + static_cast<int64_t>(2 * p) * ld;
+  const int lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* lc = logits + static_cast<int64_t>(2 * p) * ld + tid * SAMPLE_SEG;
   const __nv_bfloat16* lu = lc + ld;
 
-  // pass 1: coalesced 16-byte loads, merge, stash in smem
-  for (int vec = tid; vec < vocab / 8; vec += SAMPLE_THREADS) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(lc) + vec);
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(lu) + vec);
-    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+  // ---- load + merge: t[j] for codes 32*tid + j ------------------------------------------------
+  float t[SAMPLE_SEG];
+  {
+    uint4 a[4], b[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(&wa[k]);
-      const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(&wb[k]);
-      const int v = vec * 8 + 2 * k;
-      const float t0 = cfg_merge(__low2float(pa), __low2float(pb), cfg_weight, temperature, merge_mode);
-      const float t1 = cfg_merge(__high2float(pa), __high2float(pb), cfg_weight, temperature, merge_mode);
-      tv[v + (v >> 5)] = t0;
-      tv[v + 1 + ((v + 1) >> 5)] = t1;
-      if (merged_out != nullptr) {
-        merged_out[static_cast<int64_t>(p) * vocab + v] = t0;
-        merged_out[static_cast<int64_t>(p) * vocab + v + 1] = t1;
+    for (int i = 0; i < 4; ++i) {
+      a[i] = __ldg(reinterpret_cast<const uint4*>(lc) + i);
+      b[i] = __ldg(reinterpret_cast<const uint4*>(lu) + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t wa[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, wb[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t[8 * i + 2 * k] = cfg_merge(__uint_as_float(wa[k] << 16), __uint_as_float(wb[k] << 16), cfg_weight,
+                                     temperature, merge_mode);
+        t[8 * i + 2 * k + 1] = cfg_merge(__uint_as_float(wa[k] & 0xFFFF0000u), __uint_as_float(wb[k] & 0xFFFF0000u),
+                                         cfg_weight, temperature, merge_mode);
       }
     }
   }
-  __syncthreads();
+  if (merged_out != nullptr) {
+    float4* mo = reinterpret_cast<float4*>(merged_out + static_cast<int64_t>(p) * vocab + tid * SAMPLE_SEG);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mo[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+  }
 
-  // pass 2: per-segment max / argmax (thread i owns codes [32 i, 32 i + 32))
-  const int nseg = vocab / SAMPLE_SEG;  // 512
-  float lmax = -INFINITY;
+  // ---- max / arg-max (exact; lowest index wins ties) -----------------------------------------
+  float lmax = t[0];
   int larg = 0;
-  if (tid < nseg) {
-    const float* seg = tv + tid * (SAMPLE_SEG + 1);
-    larg = tid * SAMPLE_SEG;
-#pragma unroll 8
-    for (int j = 0; j < SAMPLE_SEG; ++j) {
-      const float t = seg[j];
-      if (t > lmax) {
-        lmax = t;
-        larg = tid * SAMPLE_SEG + j;
-      }
+#pragma unroll
+  for (int j = 1; j < SAMPLE_SEG; ++j) {
+    if (t[j] > lmax) {
+      lmax = t[j];
+      larg = j;
     }
   }
-  red[tid] = lmax;
-  redi[tid] = larg;
+  larg += tid * SAMPLE_SEG;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float o = __shfl_xor_sync(0xffffffffu, lmax, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, larg, off);
+    if (o > lmax || (o == lmax && oi < larg)) {
+      lmax = o;
+      larg = oi;
+    }
+  }
+  if (lane == 0) {
+    wmax[warp] = lmax;
+    warg[warp] = larg;
+  }
   __syncthreads();
-  for (int s = SAMPLE_THREADS / 2; s > 0; s >>= 1) {
-    if (tid < s) {
-      const float o = red[tid + s];
-      const int oi = redi[tid + s];
-      if (o > red[tid] || (o == red[tid] && oi < redi[tid])) {
-        red[tid] = o;
-        redi[tid] = oi;
-      }
+  float gmax = wmax[0];
+  int garg = warg[0];
+#pragma unroll
+  for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
+    const float o = wmax[w];
+    const int oi = warg[w];
+    if (o > gmax || (o == gmax && oi < garg)) {
+      gmax = o;
+      garg = oi;
     }
-    __syncthreads();
   }
-  const float gmax = red[0];
   if (greedy) {
-    if (tid == 0) ids[p] = redi[0];
+    if (tid == 0) ids[p] = garg;
     return;
   }
 
-  // pass 3: weights + segment sums (sequential inside a segment)
-  if (tid < nseg) {
-    float* seg = tv + tid * (SAMPLE_SEG + 1);
-    float acc = 0.0f;
+  // ---- weights + segment sums (sequential inside a segment) -----------------------------------
+  float acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < SAMPLE_SEG; ++j) {
+    t[j] = exp_det(__fsub_rn(t[j], gmax));
+    acc = __fadd_rn(acc, t[j]);
+  }
+  seg_sum[tid] = acc;
+  __syncthreads();
+  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
+  if (tid < NGRP) {
+    float g = 0.0f;
 #pragma unroll 8
-    for (int j = 0; j < SAMPLE_SEG; ++j) {
-      const float w = exp_det(__fsub_rn(seg[j], gmax));
-      seg[j] = w;
-      acc = __fadd_rn(acc, w);
-    }
-    seg_sum[tid] = acc;
+    for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[tid * SAMPLE_GRP + j]);
+    grp_sum[tid] = g;
   }
   __syncthreads();
-  const int ngrp = nseg / SAMPLE_GRP;  // 16
-  if (tid < ngrp) {
-    float acc = 0.0f;
-    for (int j = 0; j < SAMPLE_GRP; ++j) acc = __fadd_rn(acc, seg_sum[tid * SAMPLE_GRP + j]);
-    grp_sum[tid] = acc;
+
+  // ---- descent: group -> segment (every thread, redundantly, from broadcast smem reads) ----------
+  float Z = 0.0f;
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) Z = __fadd_rn(Z, grp_sum[g]);
+  const float target = __fmul_rn(__ldg(uniforms + p), Z);
+  float base = 0.0f;
+  int g = 0;
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < NGRP - 1; ++i) {
+    const float nxt = __fadd_rn(base, grp_sum[i]);
+    if (!found) {
+      if (nxt > target) found = true;
+      else {
+        base = nxt;
+        g = i + 1;
+      }
+    }
   }
-  __syncthreads();
-  if (tid == 0) {
-    float Z = 0.0f;
-    for (int g = 0; g < ngrp; ++g) Z = __fadd_rn(Z, grp_sum[g]);
-    const float target = __fmul_rn(uniforms[p], Z);
-    // descend: group -> segment -> code; `base` is the cdf value before the current block
-    float base = 0.0f;
-    int g = 0;
-    for (; g < ngrp - 1; ++g) {
-      const float nxt = __fadd_rn(base, grp_sum[g]);
-      if (nxt > target) break;
-      base = nxt;
+  int sgi = 0;
+  found = false;
+#pragma unroll 8
+  for (int i = 0; i < SAMPLE_GRP - 1; ++i) {
+    const float nxt = __fadd_rn(base, seg_sum[g * SAMPLE_GRP + i]);
+    if (!found) {
+      if (nxt > target) found = true;
+      else {
+        base = nxt;
+        sgi = i + 1;
+      }
     }
-    int sgi = 0;
-    for (; sgi < SAMPLE_GRP - 1; ++sgi) {
-      const float nxt = __fadd_rn(base, seg_sum[g * SAMPLE_GRP + sgi]);
-      if (nxt > target) break;
-      base = nxt;
-    }
-    const int segi = g * SAMPLE_GRP + sgi;
-    const float* seg = tv + segi * (SAMPLE_SEG + 1);
+  }
+  const int segi = g * SAMPLE_GRP + sgi;
+  // ---- code-level descent by the segment's owner, from its registers -----------------------------
+  if (tid == segi) {
     int j = 0;
-    for (; j < SAMPLE_SEG - 1; ++j) {
-      const float nxt = __fadd_rn(base, seg[j]);
-      if (nxt > target) break;
-      base = nxt;
+    found = false;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_SEG - 1; ++i) {
+      const float nxt = __fadd_rn(base, t[i]);
+      if (!found) {
+        if (nxt > target) found = true;
+        else {
+          base = nxt;
+          j = i + 1;
+        }
+      }
     }
     ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
   }

@@ -47,9 +47,11 @@ int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat1
                  int out_dim, int in_dim);
 
 // ---- decode, swap-AB (gemm_decode.cu) ----
-// act[n, e] = bf16(gelu(bf16(W1 h^T + b1)));  h [n,H] with n = 2P small
-int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
-                        __nv_bfloat16* act, int n, int H, int E);
+// part[ks][n][E] (fp32) = k-split partials of W1 h^T;  h [n,H] with n = 2P small.  The caller sums the partials,
+// adds b1 and applies GELU (decode_act_finalize_kernel).  decode_gemm1_splits() = number of partials written.
+int decode_gemm1_splits(int num_sms, int H, int E);
+int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, float* part,
+                        int64_t split_stride, int n, int H, int E);
 // logits[n, v] = bf16(W2 act^T + b2)
 int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                         __nv_bfloat16* logits, int n, int E, int V);

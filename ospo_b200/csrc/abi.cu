@@ -385,9 +385,21 @@ static int launch_sampler(const ospo_cfg_args* a, int pairs, cudaStream_t st) {
   if (!a->ids || !a->logits) return OSPO_ERR_NULL;
   if (!(a->temperature > 0.0f)) return OSPO_ERR_UNSUPPORTED;
   KernelSpan ks(st, OSPO_K_SAMPLER);
-  cfg_merge_sample_kernel<<<pairs, SAMPLE_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(a->logits), V, V,
-                                                              a->cfg_weight, a->temperature, a->merge_mode,
-                                                              a->uniforms, a->greedy, a->ids, a->merged);
+  const __nv_bfloat16* lg = static_cast<const __nv_bfloat16*>(a->logits);
+  const bool tdiv = (a->temperature != 1.0f);
+  const int mode = (a->merge_mode == OSPO_MERGE_FP32) ? 1 : 0;
+#define OSPO_LAUNCH_SAMPLER(MODE, TDIV, GREEDY)                                                                   \
+  cfg_merge_sample_kernel<MODE, TDIV, GREEDY><<<pairs, SAMPLE_THREADS, 0, st>>>(lg, V, V, a->cfg_weight,         \
+                                                                                a->temperature, a->uniforms,    \
+                                                                                a->ids, a->merged)
+  if (a->greedy) {
+    if (mode == 0) { if (tdiv) OSPO_LAUNCH_SAMPLER(0, true, true); else OSPO_LAUNCH_SAMPLER(0, false, true); }
+    else { if (tdiv) OSPO_LAUNCH_SAMPLER(1, true, true); else OSPO_LAUNCH_SAMPLER(1, false, true); }
+  } else {
+    if (mode == 0) { if (tdiv) OSPO_LAUNCH_SAMPLER(0, true, false); else OSPO_LAUNCH_SAMPLER(0, false, false); }
+    else { if (tdiv) OSPO_LAUNCH_SAMPLER(1, true, false); else OSPO_LAUNCH_SAMPLER(1, false, false); }
+  }
+#undef OSPO_LAUNCH_SAMPLER
   return check_launch();
 }
 

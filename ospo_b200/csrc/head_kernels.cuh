@@ -294,10 +294,11 @@ constexpr int SAMPLE_GRP = 32;   // segments per group
 // Deterministic fp32 exp for x <= 0: every step is a single IEEE-754 operation, so the C oracle
 // (compiled with -ffp-contract=off, using fmaf) is bit-identical.
 __device__ __forceinline__ float exp_det(float x) {
-  // n = rint(x log2 e); r = x - n ln2 (Cody-Waite, two fma); e^r by a degree-6 polynomial; scale by 2^n
-  float y = __fmul_rn(x, 1.4426950408889634f);
-  if (!(y >= -125.0f)) return 0.0f;
-  const float n = rintf(y);
+  // n = rint(x log2 e); r = x - n ln2 (Cody-Waite, two fma); e^r by a degree-6 polynomial; scale by 2^n.
+  // Branch-free: out-of-range inputs are computed on a clamped n and then replaced by 0.
+  const float y = __fmul_rn(x, 1.4426950408889634f);
+  const bool in_range = (y >= -125.0f);
+  const float n = in_range ? rintf(y) : 0.0f;
   float r = __fmaf_rn(n, -0.693145751953125f, x);
   r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
   float p = 1.3888888888888889e-03f;
@@ -308,20 +309,31 @@ __device__ __forceinline__ float exp_det(float x) {
   p = __fmaf_rn(p, r, 1.0f);
   p = __fmaf_rn(p, r, 1.0f);
   const float scale = __int_as_float((static_cast<int>(n) + 127) << 23);  // 2^n, normal since n >= -125
-  return __fmul_rn(p, scale);
+  return in_range ? __fmul_rn(p, scale) : 0.0f;
 }
 
-__device__ __forceinline__ float cfg_merge(float lc, float lu, float w, float T, int merge_mode) {
-  if (merge_mode == 0) {
-    const float d = bf16_round(__fsub_rn(lc, lu));
-    const float e = bf16_round(__fmul_rn(w, d));
-    const float m = bf16_round(__fadd_rn(lu, e));
-    return bf16_round(__fdiv_rn(m, T));
-  } else {
-    const float d = __fsub_rn(lc, lu);
-    const float e = __fmul_rn(w, d);
-    const float m = __fadd_rn(lu, e);
-    return __fdiv_rn(m, T);
+// merge two adjacent codes at once so the bf16 roundings can use the packed convert (cvt.rn.bf16x2.f32).
+// MODE 0 = bf16 rounding after every op, MODE 1 = fp32.  TDIV = false skips the division (T == 1: x / 1 == x).
+__device__ __forceinline__ void round2_bf16(float& a, float& b) {
+  const uint32_t u = pack_bf16x2(a, b);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xFFFF0000u);
+}
+template <int MODE, bool TDIV>
+__device__ __forceinline__ void cfg_merge2(uint32_t wc, uint32_t wu, float w, float T, float& t0, float& t1) {
+  const float c0 = __uint_as_float(wc << 16), c1 = __uint_as_float(wc & 0xFFFF0000u);
+  const float u0 = __uint_as_float(wu << 16), u1 = __uint_as_float(wu & 0xFFFF0000u);
+  float d0 = __fsub_rn(c0, u0), d1 = __fsub_rn(c1, u1);
+  if (MODE == 0) round2_bf16(d0, d1);
+  float e0 = __fmul_rn(w, d0), e1 = __fmul_rn(w, d1);
+  if (MODE == 0) round2_bf16(e0, e1);
+  t0 = __fadd_rn(u0, e0);
+  t1 = __fadd_rn(u1, e1);
+  if (MODE == 0) round2_bf16(t0, t1);
+  if (TDIV) {
+    t0 = __fdiv_rn(t0, T);
+    t1 = __fdiv_rn(t1, T);
+    if (MODE == 0) round2_bf16(t0, t1);
   }
 }
 
@@ -329,10 +341,11 @@ __device__ __forceinline__ float cfg_merge(float lc, float lu, float w, float T,
 // Register-resident: thread i owns segment i (codes 32 i .. 32 i + 31): it loads its 64 bytes of the
 // conditional and of the unconditional row, keeps the 32 merged values / weights in registers, and the
 // only shared memory is 512 segment sums + 16 group sums.  Three block barriers in total.
+template <int MODE, bool TDIV, bool GREEDY>
 __global__ void __launch_bounds__(SAMPLE_THREADS, 2)
 cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int vocab, float cfg_weight,
-                        float temperature, int merge_mode, const float* __restrict__ uniforms, int greedy,
-                        int64_t* __restrict__ ids, float* __restrict__ merged_out /* [P, V] optional */) {
+                        float temperature, const float* __restrict__ uniforms, int64_t* __restrict__ ids,
+                        float* __restrict__ merged_out /* [P, V] optional */) {
   __shared__ float seg_sum[SAMPLE_THREADS];
   __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
   __shared__ float wmax[SAMPLE_THREADS / 32];
@@ -356,12 +369,8 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
     for (int i = 0; i < 4; ++i) {
       const uint32_t wa[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, wb[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        t[8 * i + 2 * k] = cfg_merge(__uint_as_float(wa[k] << 16), __uint_as_float(wb[k] << 16), cfg_weight,
-                                     temperature, merge_mode);
-        t[8 * i + 2 * k + 1] = cfg_merge(__uint_as_float(wa[k] & 0xFFFF0000u), __uint_as_float(wb[k] & 0xFFFF0000u),
-                                         cfg_weight, temperature, merge_mode);
-      }
+      for (int k = 0; k < 4; ++k)
+        cfg_merge2<MODE, TDIV>(wa[k], wb[k], cfg_weight, temperature, t[8 * i + 2 * k], t[8 * i + 2 * k + 1]);
     }
   }
   if (merged_out != nullptr) {
@@ -370,45 +379,57 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
     for (int i = 0; i < 8; ++i) mo[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
   }
 
-  // ---- max / arg-max (exact; lowest index wins ties) -----------------------------------------
-  float lmax = t[0];
-  int larg = 0;
+  // ---- max (exact); arg-max with lowest-index ties only in greedy mode ----------------------------
+  float gmax;
+  if constexpr (GREEDY) {
+    float lmax = t[0];
+    int larg = 0;
 #pragma unroll
-  for (int j = 1; j < SAMPLE_SEG; ++j) {
-    if (t[j] > lmax) {
-      lmax = t[j];
-      larg = j;
+    for (int j = 1; j < SAMPLE_SEG; ++j) {
+      if (t[j] > lmax) {
+        lmax = t[j];
+        larg = j;
+      }
     }
-  }
-  larg += tid * SAMPLE_SEG;
+    larg += tid * SAMPLE_SEG;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float o = __shfl_xor_sync(0xffffffffu, lmax, off);
-    const int oi = __shfl_xor_sync(0xffffffffu, larg, off);
-    if (o > lmax || (o == lmax && oi < larg)) {
-      lmax = o;
-      larg = oi;
+    for (int off = 16; off > 0; off >>= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, lmax, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, larg, off);
+      if (o > lmax || (o == lmax && oi < larg)) {
+        lmax = o;
+        larg = oi;
+      }
     }
-  }
-  if (lane == 0) {
-    wmax[warp] = lmax;
-    warg[warp] = larg;
-  }
-  __syncthreads();
-  float gmax = wmax[0];
-  int garg = warg[0];
+    if (lane == 0) {
+      wmax[warp] = lmax;
+      warg[warp] = larg;
+    }
+    __syncthreads();
+    gmax = wmax[0];
+    int garg = warg[0];
 #pragma unroll
-  for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
-    const float o = wmax[w];
-    const int oi = warg[w];
-    if (o > gmax || (o == gmax && oi < garg)) {
-      gmax = o;
-      garg = oi;
+    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
+      const float o = wmax[w];
+      const int oi = warg[w];
+      if (o > gmax || (o == gmax && oi < garg)) {
+        gmax = o;
+        garg = oi;
+      }
     }
-  }
-  if (greedy) {
     if (tid == 0) ids[p] = garg;
     return;
+  } else {
+    float lmax = t[0];
+#pragma unroll
+    for (int j = 1; j < SAMPLE_SEG; ++j) lmax = fmaxf(lmax, t[j]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+    if (lane == 0) wmax[warp] = lmax;
+    __syncthreads();
+    gmax = wmax[0];
+#pragma unroll
+    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) gmax = fmaxf(gmax, wmax[w]);
   }
 
   // ---- weights + segment sums (sequential inside a segment) -----------------------------------

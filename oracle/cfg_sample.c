@@ -13,9 +13,9 @@
  *       the reference do (merge_mode 1 keeps fp32);
  *   (2) torch.multinomial draws from the global Philox stream and cannot be reproduced by another
  *       kernel, so sampling is defined as inverse-CDF on caller-supplied uniforms:
- *           id = min{ k : cdf_k > u * Z },  weights w_v = exp_det(t_v - max t), Z = sum w,
- *       with a fully specified fp32 exp and a fixed three-level summation order
- *       (512 segments x 32 codes, 16 groups x 32 segments, 16 groups).
+ *           id = min{ k : cdf_k > u * Z },  weights w_v = e^(t_v) / 2^K  (K = max_v rint(t_v log2 e)), Z = sum w,
+ *       with a fully specified fp32 exp and a fixed summation order (tiles of 128 codes, segments of 32
+ *       codes summed as a pairwise tree, 16 groups x 32 segments and the 16 groups summed sequentially).
  * The probabilities w/Z are checked against the real reference's `probs` in tests (golden
  * tests/golden/cfg_ref.npz); the CUDA kernel is checked against this file bit for bit.
  *
@@ -46,13 +46,19 @@ static float bf16_round(float f) { /* round-to-nearest-even to bf16, returned as
   return f;
 }
 
-float ospo_oracle_exp_det(float x) {
-  /* x <= 0.  n = rint(x log2 e); r = x - n ln2 (Cody-Waite, two fma); e^r by a degree-6 polynomial;
-     scale by 2^n through the exponent bits.  Every line is one IEEE-754 fp32 operation. */
-  float y = x * 1.4426950408889634f;
-  if (!(y >= -125.0f)) return 0.0f;
+/* ---- softmax weights with a power-of-two reference --------------------------------------------------
+ * For a merged logit t:  y = t * log2(e);  n = rint(y);  r = t - n ln2 (Cody-Waite, two fma);
+ * e^t = P(r) * 2^n with P a degree-6 polynomial.  Weights are kept RELATIVE to an integer exponent K:
+ *     w = P(r) * 2^(n - K)         (0 if n - K < -120)
+ * so that changing K is an exact power-of-two rescale.  That lets a GPU kernel compute the weights of a
+ * 128-code tile against the tile's own K_tile (while the tile is still in tensor memory) and rescale the
+ * segment sums later, bit for bit the same as this file.  Every line is one IEEE-754 fp32 operation. */
+static float exp_parts(float t, float* n_out) { /* returns P(r), writes n */
+  float y = t * 1.4426950408889634f;
+  if (!(y >= -1.0e4f)) y = -1.0e4f;
+  if (!(y <= 1.0e4f)) y = 1.0e4f;
   float n = rintf(y);
-  float r = fmaf(n, -0.693145751953125f, x);
+  float r = fmaf(n, -0.693145751953125f, t);
   r = fmaf(n, -1.42860682030941723212e-6f, r);
   float p = 1.3888888888888889e-03f;
   p = fmaf(p, r, 8.3333333333333332e-03f);
@@ -61,10 +67,22 @@ float ospo_oracle_exp_det(float x) {
   p = fmaf(p, r, 0.5f);
   p = fmaf(p, r, 1.0f);
   p = fmaf(p, r, 1.0f);
-  uint32_t sb = (uint32_t)((int)n + 127) << 23;
-  float scale;
-  memcpy(&scale, &sb, 4);
-  return p * scale;
+  *n_out = n;
+  return p;
+}
+
+static float pow2_factor(float e) { /* 2^e for integer-valued e <= 0; 0 below -120 */
+  if (e < -120.0f) return 0.0f;
+  uint32_t sb = (uint32_t)((int)e + 127) << 23;
+  float f;
+  memcpy(&f, &sb, 4);
+  return f;
+}
+
+float ospo_oracle_exp_det(float x) { /* e^x for x <= 0 (kept for tests of the polynomial) */
+  float n;
+  float p = exp_parts(x, &n);
+  return p * pow2_factor(n);
 }
 
 static float merge_one(float lc, float lu, float w, float T, int merge_mode) {
@@ -90,31 +108,47 @@ void ospo_oracle_cfg_merge(const uint16_t* logits, int P, int V, float w, float 
   }
 }
 
-/* merged: fp32 [P, V] (V multiple of SEG*GRP); uniforms [P]; ids [P];
- * weights_out (optional) [P, V] unnormalised weights; z_out (optional) [P] */
+/* merged: fp32 [P, V] (V multiple of TILE and of SEG*GRP); uniforms [P]; ids [P];
+ * weights_out (optional) [P, V] weights relative to the global exponent K; z_out (optional) [P].
+ * Order of operations (mirrored exactly by the CUDA kernels):
+ *   tile (128 codes):  K_tile = max n;  u_v = P(r_v) * 2^(n_v - K_tile)
+ *   segment (32 codes): S = pairwise-adjacent tree sum of u  (((u0+u1)+(u2+u3))+...)
+ *   K = max K_tile;  S' = S * 2^(K_tile - K)
+ *   group (32 segments): sequential sum of S';  Z = sequential sum of the 16 group sums
+ *   descent group -> segment -> code, `base` carried along; in-segment weights are u * 2^(K_tile - K) */
+#define TILE 128
 int ospo_oracle_sample_merged(const float* merged, int P, int V, const float* uniforms, int greedy, int64_t* ids,
                               float* weights_out, float* z_out) {
-  if (V % (SEG * GRP) != 0 || V / SEG > 4096) return -1;
-  const int nseg = V / SEG, ngrp = nseg / GRP;
-  static float wbuf[1 << 20];
-  static float seg_sum[4096], grp_sum[128];
-  if (V > (1 << 20)) return -1;
+  if (V % (SEG * GRP) != 0 || V % TILE != 0 || V / SEG > 4096 || V > (1 << 20)) return -1;
+  const int nseg = V / SEG, ngrp = nseg / GRP, ntile = V / TILE;
+  static float ubuf[1 << 20], pbuf[1 << 20], nbuf[1 << 20];
+  static float seg_sum[4096], grp_sum[128], tile_k[8192];
   for (int p = 0; p < P; ++p) {
     const float* t = merged + (size_t)p * V;
-    float gmax = -INFINITY;
-    int garg = 0;
-    for (int v = 0; v < V; ++v) {
-      if (t[v] > gmax) { gmax = t[v]; garg = v; }
-    }
-    if (greedy) { ids[p] = garg; continue; }
-    for (int s = 0; s < nseg; ++s) {
-      float acc = 0.0f;
-      for (int j = 0; j < SEG; ++j) {
-        float w = ospo_oracle_exp_det(t[s * SEG + j] - gmax);
-        wbuf[s * SEG + j] = w;
-        acc = acc + w;
+    if (greedy) {
+      float gmax = t[0];
+      int garg = 0;
+      for (int v = 1; v < V; ++v) {
+        if (t[v] > gmax) { gmax = t[v]; garg = v; }
       }
-      seg_sum[s] = acc;
+      ids[p] = garg;
+      continue;
+    }
+    for (int v = 0; v < V; ++v) pbuf[v] = exp_parts(t[v], &nbuf[v]);
+    float K = -INFINITY;
+    for (int tl = 0; tl < ntile; ++tl) {
+      float kt = nbuf[tl * TILE];
+      for (int j = 1; j < TILE; ++j) kt = nbuf[tl * TILE + j] > kt ? nbuf[tl * TILE + j] : kt;
+      tile_k[tl] = kt;
+      if (kt > K) K = kt;
+      for (int j = 0; j < TILE; ++j) ubuf[tl * TILE + j] = pbuf[tl * TILE + j] * pow2_factor(nbuf[tl * TILE + j] - kt);
+    }
+    for (int s = 0; s < nseg; ++s) {
+      float x[SEG];
+      for (int j = 0; j < SEG; ++j) x[j] = ubuf[s * SEG + j];
+      for (int w = SEG; w > 1; w >>= 1)
+        for (int j = 0; j < w / 2; ++j) x[j] = x[2 * j] + x[2 * j + 1];
+      seg_sum[s] = x[0] * pow2_factor(tile_k[s / (TILE / SEG)] - K);
     }
     for (int g = 0; g < ngrp; ++g) {
       float acc = 0.0f;
@@ -123,7 +157,8 @@ int ospo_oracle_sample_merged(const float* merged, int P, int V, const float* un
     }
     float Z = 0.0f;
     for (int g = 0; g < ngrp; ++g) Z = Z + grp_sum[g];
-    if (weights_out) memcpy(weights_out + (size_t)p * V, wbuf, sizeof(float) * (size_t)V);
+    if (weights_out)
+      for (int v = 0; v < V; ++v) weights_out[(size_t)p * V + v] = ubuf[v] * pow2_factor(tile_k[v / TILE] - K);
     if (z_out) z_out[p] = Z;
     const float target = uniforms[p] * Z;
     float base = 0.0f;
@@ -140,9 +175,10 @@ int ospo_oracle_sample_merged(const float* merged, int P, int V, const float* un
       base = nxt;
     }
     const int segi = g * GRP + sg;
+    const float f = pow2_factor(tile_k[segi / (TILE / SEG)] - K);
     int j = 0;
     for (; j < SEG - 1; ++j) {
-      float nxt = base + wbuf[segi * SEG + j];
+      float nxt = base + ubuf[segi * SEG + j] * f;
       if (nxt > target) break;
       base = nxt;
     }

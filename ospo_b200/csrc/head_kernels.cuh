@@ -282,24 +282,27 @@ __global__ void decode_act_finalize_kernel(const float* __restrict__ part, int k
 //   merge_mode 0 (reference bf16 semantics, op-by-op rounding, image_generation.py:160-161):
 //        d = bf16(lc - lu); e = bf16(w * d); m = bf16(lu + e); t = bf16(m / T)
 //   merge_mode 1: same four operations in fp32 (no intermediate bf16 rounding).
-// softmax weights  w_v = exp_det(t_v - max_v t_v)  with a fully specified fp32 exp (below), summed in a
-// fixed three-level order (512 segments x 32 codes -> 16 groups x 32 segments -> 16 groups) so that the
-// oracle (oracle/cfg_sample.c) reproduces every bit:   id = min{ k : cdf_k > u * Z }.
-// greedy: argmax_v t_v, lowest index on ties.
+// Softmax weights are kept relative to a power of two:  e^t = P(r) 2^n  (n = rint(t log2 e), Cody-Waite r,
+// degree-6 P);  inside a 128-code TILE  u = P(r) 2^(n - K_tile),  K_tile = max n of the tile;  a 32-code
+// SEGMENT sum is a pairwise-adjacent tree;  globally K = max K_tile and S' = S 2^(K_tile - K) (exact
+// rescale);  16 GROUPS of 32 segments and then the groups are summed sequentially;
+//     id = first code whose running cdf exceeds u * Z   (descent group -> segment -> code).
+// The same arithmetic, operation for operation, is in oracle/cfg_sample.c.  The tile-local exponent is what
+// lets the decode GEMM's epilogue (EpiCfgFused, epilogues.cuh) produce the weights and segment sums while
+// the logits are still in tensor memory.  greedy: argmax_v t_v, lowest index on ties.
 // ---------------------------------------------------------------------------
 constexpr int SAMPLE_THREADS = 512;
-constexpr int SAMPLE_SEG = 32;   // codes per segment (one thread)
-constexpr int SAMPLE_GRP = 32;   // segments per group
+constexpr int SAMPLE_SEG = 32;    // codes per segment (one thread / one warp lane set)
+constexpr int SAMPLE_GRP = 32;    // segments per group
+constexpr int SAMPLE_TILE = 128;  // codes per tile (= accumulator rows of one decode-GEMM CTA)
 
-// Deterministic fp32 exp for x <= 0: every step is a single IEEE-754 operation, so the C oracle
-// (compiled with -ffp-contract=off, using fmaf) is bit-identical.
-__device__ __forceinline__ float exp_det(float x) {
-  // n = rint(x log2 e); r = x - n ln2 (Cody-Waite, two fma); e^r by a degree-6 polynomial; scale by 2^n.
-  // Branch-free: out-of-range inputs are computed on a clamped n and then replaced by 0.
-  const float y = __fmul_rn(x, 1.4426950408889634f);
-  const bool in_range = (y >= -125.0f);
-  const float n = in_range ? rintf(y) : 0.0f;
-  float r = __fmaf_rn(n, -0.693145751953125f, x);
+// e^t = P(r) * 2^n; returns P(r), writes n (integer-valued float).  One IEEE fp32 op per line.
+__device__ __forceinline__ float exp_parts(float t, float& n) {
+  float y = __fmul_rn(t, 1.4426950408889634f);
+  y = fmaxf(y, -1.0e4f);
+  y = fminf(y, 1.0e4f);
+  n = rintf(y);
+  float r = __fmaf_rn(n, -0.693145751953125f, t);
   r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
   float p = 1.3888888888888889e-03f;
   p = __fmaf_rn(p, r, 8.3333333333333332e-03f);
@@ -308,8 +311,18 @@ __device__ __forceinline__ float exp_det(float x) {
   p = __fmaf_rn(p, r, 0.5f);
   p = __fmaf_rn(p, r, 1.0f);
   p = __fmaf_rn(p, r, 1.0f);
-  const float scale = __int_as_float((static_cast<int>(n) + 127) << 23);  // 2^n, normal since n >= -125
-  return in_range ? __fmul_rn(p, scale) : 0.0f;
+  return p;
+}
+__device__ __forceinline__ float exp_n_only(float t) {
+  float y = __fmul_rn(t, 1.4426950408889634f);
+  y = fmaxf(y, -1.0e4f);
+  y = fminf(y, 1.0e4f);
+  return rintf(y);
+}
+// 2^e for integer-valued e <= 0; 0 below -120
+__device__ __forceinline__ float pow2_factor(float e) {
+  const float f = __int_as_float((static_cast<int>(e) + 127) << 23);
+  return (e < -120.0f) ? 0.0f : f;
 }
 
 // merge two adjacent codes at once so the bf16 roundings can use the packed convert (cvt.rn.bf16x2.f32).
@@ -320,9 +333,8 @@ __device__ __forceinline__ void round2_bf16(float& a, float& b) {
   b = __uint_as_float(u & 0xFFFF0000u);
 }
 template <int MODE, bool TDIV>
-__device__ __forceinline__ void cfg_merge2(uint32_t wc, uint32_t wu, float w, float T, float& t0, float& t1) {
-  const float c0 = __uint_as_float(wc << 16), c1 = __uint_as_float(wc & 0xFFFF0000u);
-  const float u0 = __uint_as_float(wu << 16), u1 = __uint_as_float(wu & 0xFFFF0000u);
+__device__ __forceinline__ void cfg_merge_vals(float c0, float c1, float u0, float u1, float w, float T, float& t0,
+                                               float& t1) {
   float d0 = __fsub_rn(c0, u0), d1 = __fsub_rn(c1, u1);
   if (MODE == 0) round2_bf16(d0, d1);
   float e0 = __fmul_rn(w, d0), e1 = __fmul_rn(w, d1);
@@ -336,11 +348,54 @@ __device__ __forceinline__ void cfg_merge2(uint32_t wc, uint32_t wu, float w, fl
     if (MODE == 0) round2_bf16(t0, t1);
   }
 }
+template <int MODE, bool TDIV>
+__device__ __forceinline__ void cfg_merge2(uint32_t wc, uint32_t wu, float w, float T, float& t0, float& t1) {
+  cfg_merge_vals<MODE, TDIV>(__uint_as_float(wc << 16), __uint_as_float(wc & 0xFFFF0000u), __uint_as_float(wu << 16),
+                             __uint_as_float(wu & 0xFFFF0000u), w, T, t0, t1);
+}
+
+// pairwise-adjacent tree sum of 32 registers (the order a shfl_xor butterfly 1,2,4,8,16 produces)
+__device__ __forceinline__ float tree_sum32(const float (&x)[32]) {
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = __fadd_rn(x[2 * j], x[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+  return __fadd_rn(a[0], a[1]);
+}
+
+// The descent shared by the stand-alone sampler and the finish kernel of the fused decode step.
+// seg_sum[512] (already rescaled to the global exponent) and grp_sum[16] live in shared memory; executed by
+// ONE thread; returns the winning segment and the cdf value before it.
+__device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* grp_sum, float u, int& segi,
+                                            float& base, float& target) {
+  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
+  float Z = 0.0f;
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) Z = __fadd_rn(Z, grp_sum[g]);
+  target = __fmul_rn(u, Z);
+  base = 0.0f;
+  int g = 0;
+  for (; g < NGRP - 1; ++g) {
+    const float nxt = __fadd_rn(base, grp_sum[g]);
+    if (nxt > target) break;
+    base = nxt;
+  }
+  int sg = 0;
+  for (; sg < SAMPLE_GRP - 1; ++sg) {
+    const float nxt = __fadd_rn(base, seg_sum[g * SAMPLE_GRP + sg]);
+    if (nxt > target) break;
+    base = nxt;
+  }
+  segi = g * SAMPLE_GRP + sg;
+}
 
 // grid.x = number of (cond, uncond) pairs; logits row pitch ld.  vocab must be 16384 (= 512 * 32).
-// Register-resident: thread i owns segment i (codes 32 i .. 32 i + 31): it loads its 64 bytes of the
-// conditional and of the unconditional row, keeps the 32 merged values / weights in registers, and the
-// only shared memory is 512 segment sums + 16 group sums.  Three block barriers in total.
+// Register-resident: thread i owns segment i (codes 32 i .. 32 i + 31).
 template <int MODE, bool TDIV, bool GREEDY>
 __global__ void __launch_bounds__(SAMPLE_THREADS, 2)
 cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int vocab, float cfg_weight,
@@ -350,6 +405,8 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
   __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
   __shared__ float wmax[SAMPLE_THREADS / 32];
   __shared__ int warg[SAMPLE_THREADS / 32];
+  __shared__ float bc_base, bc_target;
+  __shared__ int bc_seg;
   const int p = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -379,9 +436,8 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
     for (int i = 0; i < 8; ++i) mo[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
   }
 
-  // ---- max (exact); arg-max with lowest-index ties only in greedy mode ----------------------------
-  float gmax;
   if constexpr (GREEDY) {
+    // ---- arg-max (exact; lowest index wins ties) ----------------------------------------------
     float lmax = t[0];
     int larg = 0;
 #pragma unroll
@@ -406,42 +462,136 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
       warg[warp] = larg;
     }
     __syncthreads();
-    gmax = wmax[0];
-    int garg = warg[0];
-#pragma unroll
-    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
-      const float o = wmax[w];
-      const int oi = warg[w];
-      if (o > gmax || (o == gmax && oi < garg)) {
-        gmax = o;
-        garg = oi;
+    if (tid == 0) {
+      float gmax = wmax[0];
+      int garg = warg[0];
+      for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
+        if (wmax[w] > gmax || (wmax[w] == gmax && warg[w] < garg)) {
+          gmax = wmax[w];
+          garg = warg[w];
+        }
       }
+      ids[p] = garg;
     }
-    if (tid == 0) ids[p] = garg;
     return;
   } else {
-    float lmax = t[0];
+    // ---- tile exponent: K_tile = max n over the 4 segments (= 4 adjacent lanes) of a 128-code tile ------
+    float kt = exp_n_only(t[0]);
 #pragma unroll
-    for (int j = 1; j < SAMPLE_SEG; ++j) lmax = fmaxf(lmax, t[j]);
+    for (int j = 1; j < SAMPLE_SEG; ++j) kt = fmaxf(kt, exp_n_only(t[j]));
+    kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 1));
+    kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 2));
+    // ---- weights relative to K_tile (in place) and the segment's tree sum -------------------------
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
-    if (lane == 0) wmax[warp] = lmax;
+    for (int j = 0; j < SAMPLE_SEG; ++j) {
+      float n;
+      const float pr = exp_parts(t[j], n);
+      t[j] = __fmul_rn(pr, pow2_factor(__fsub_rn(n, kt)));
+    }
+    const float S = tree_sum32(t);
+    // ---- global exponent K ---------------------------------------------------------------------
+    float K = kt;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) K = fmaxf(K, __shfl_xor_sync(0xffffffffu, K, off));
+    if (lane == 0) wmax[warp] = K;
     __syncthreads();
-    gmax = wmax[0];
+    K = wmax[0];
 #pragma unroll
-    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) gmax = fmaxf(gmax, wmax[w]);
+    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) K = fmaxf(K, wmax[w]);
+    const float f = pow2_factor(__fsub_rn(kt, K));
+    seg_sum[tid] = __fmul_rn(S, f);
+    __syncthreads();
+    constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
+    if (tid < NGRP) {
+      float g = 0.0f;
+#pragma unroll 8
+      for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[tid * SAMPLE_GRP + j]);
+      grp_sum[tid] = g;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int segi;
+      float base, target;
+      cdf_descent(seg_sum, grp_sum, __ldg(uniforms + p), segi, base, target);
+      bc_seg = segi;
+      bc_base = base;
+      bc_target = target;
+    }
+    __syncthreads();
+    // ---- code-level descent by the segment's owner, from its registers --------------------------
+    if (tid == bc_seg) {
+      float base = bc_base;
+      const float target = bc_target;
+      int j = 0;
+      bool found = false;
+#pragma unroll
+      for (int i = 0; i < SAMPLE_SEG - 1; ++i) {
+        const float nxt = __fadd_rn(base, __fmul_rn(t[i], f));
+        if (!found) {
+          if (nxt > target) found = true;
+          else {
+            base = nxt;
+            j = i + 1;
+          }
+        }
+      }
+      ids[p] = static_cast<int64_t>(tid) * SAMPLE_SEG + j;
+    }
   }
+}
 
-  // ---- weights + segment sums (sequential inside a segment) -----------------------------------
-  float acc = 0.0f;
-#pragma unroll
-  for (int j = 0; j < SAMPLE_SEG; ++j) {
-    t[j] = exp_det(__fsub_rn(t[j], gmax));
-    acc = __fadd_rn(acc, t[j]);
+// ---------------------------------------------------------------------------
+// Finish kernel of the fused decode step.  The decode GEMM2 epilogue (EpiCfgFused) has already produced, per
+// pair: the weights u (relative to each tile's exponent), 512 segment sums, 128 tile exponents and, for the
+// greedy mode, per-tile arg-max candidates.  One block per pair finishes the draw.
+// ---------------------------------------------------------------------------
+struct CfgFusedBuffers {
+  float* wbuf;        // [P, V]      weights relative to K_tile
+  float* seg_sum;     // [P, V/32]   tree sums relative to K_tile
+  float* tile_k;      // [P, V/128]  tile exponents
+  float* tile_max;    // [P, V/128]  greedy: max merged logit of the tile
+  int* tile_arg;      // [P, V/128]  greedy: its (lowest) index
+};
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ uniforms, int greedy,
+                  int64_t* __restrict__ ids) {
+  __shared__ float seg_sum[SAMPLE_THREADS];
+  __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
+  __shared__ float wmax[SAMPLE_THREADS / 32];
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int ntile = vocab / SAMPLE_TILE;  // 128
+  if (greedy) {
+    if (tid == 0) {
+      float gmax = b.tile_max[p * ntile];
+      int garg = b.tile_arg[p * ntile];
+      for (int t = 1; t < ntile; ++t) {
+        const float o = b.tile_max[p * ntile + t];
+        const int oi = b.tile_arg[p * ntile + t];
+        if (o > gmax || (o == gmax && oi < garg)) {
+          gmax = o;
+          garg = oi;
+        }
+      }
+      ids[p] = garg;
+    }
+    return;
   }
-  seg_sum[tid] = acc;
+  const float kt = b.tile_k[p * ntile + tid / (SAMPLE_TILE / SAMPLE_SEG)];
+  float K = kt;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) K = fmaxf(K, __shfl_xor_sync(0xffffffffu, K, off));
+  if (lane == 0) wmax[warp] = K;
   __syncthreads();
-  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
+  K = wmax[0];
+#pragma unroll
+  for (int w = 1; w < SAMPLE_THREADS / 32; ++w) K = fmaxf(K, wmax[w]);
+  const float f = pow2_factor(__fsub_rn(kt, K));
+  seg_sum[tid] = __fmul_rn(b.seg_sum[static_cast<int64_t>(p) * SAMPLE_THREADS + tid], f);
+  __syncthreads();
+  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
   if (tid < NGRP) {
     float g = 0.0f;
 #pragma unroll 8
@@ -449,54 +599,17 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
     grp_sum[tid] = g;
   }
   __syncthreads();
-
-  // ---- descent: group -> segment (every thread, redundantly, from broadcast smem reads) ----------
-  float Z = 0.0f;
-#pragma unroll
-  for (int g = 0; g < NGRP; ++g) Z = __fadd_rn(Z, grp_sum[g]);
-  const float target = __fmul_rn(__ldg(uniforms + p), Z);
-  float base = 0.0f;
-  int g = 0;
-  bool found = false;
-#pragma unroll
-  for (int i = 0; i < NGRP - 1; ++i) {
-    const float nxt = __fadd_rn(base, grp_sum[i]);
-    if (!found) {
-      if (nxt > target) found = true;
-      else {
-        base = nxt;
-        g = i + 1;
-      }
-    }
-  }
-  int sgi = 0;
-  found = false;
-#pragma unroll 8
-  for (int i = 0; i < SAMPLE_GRP - 1; ++i) {
-    const float nxt = __fadd_rn(base, seg_sum[g * SAMPLE_GRP + i]);
-    if (!found) {
-      if (nxt > target) found = true;
-      else {
-        base = nxt;
-        sgi = i + 1;
-      }
-    }
-  }
-  const int segi = g * SAMPLE_GRP + sgi;
-  // ---- code-level descent by the segment's owner, from its registers -----------------------------
-  if (tid == segi) {
+  if (tid == 0) {
+    int segi;
+    float base, target;
+    cdf_descent(seg_sum, grp_sum, __ldg(uniforms + p), segi, base, target);
+    const float fs = pow2_factor(__fsub_rn(b.tile_k[p * ntile + segi / (SAMPLE_TILE / SAMPLE_SEG)], K));
+    const float* w = b.wbuf + static_cast<int64_t>(p) * vocab + segi * SAMPLE_SEG;
     int j = 0;
-    found = false;
-#pragma unroll
-    for (int i = 0; i < SAMPLE_SEG - 1; ++i) {
-      const float nxt = __fadd_rn(base, t[i]);
-      if (!found) {
-        if (nxt > target) found = true;
-        else {
-          base = nxt;
-          j = i + 1;
-        }
-      }
+    for (; j < SAMPLE_SEG - 1; ++j) {
+      const float nxt = __fadd_rn(base, __fmul_rn(w[j], fs));
+      if (nxt > target) break;
+      base = nxt;
     }
     ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
   }

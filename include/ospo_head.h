@@ -141,7 +141,8 @@ typedef struct {
   ospo_head_shape shape;       /* rows = 2P (row 2k conditional, 2k+1 unconditional); vocab must be 16384 */
   ospo_head_weights w;
   const void* h;               /* bf16 [2P, H] last hidden state of every CFG row; NULL for merge_sample */
-  void* logits;                /* bf16 [2P, V]: written by cfg_sample, read by cfg_merge_sample */
+  void* logits;                /* bf16 [2P, V]: read by cfg_merge_sample; optional dump for cfg_sample (NULL =
+                                  the logits never leave the chip) */
   float cfg_weight, temperature;
   int32_t merge_mode;          /* OSPO_MERGE_BF16 | OSPO_MERGE_FP32 */
   int32_t greedy;              /* 1 = argmax (lowest index on ties), uniforms ignored */
@@ -173,6 +174,10 @@ OSPO_API const char* ospo_head_strerror(int status);
 /* tcgen05 cta_group used by the training GEMMs: 1 (one CTA per 128-row tile) or 2 (CTA pair per
    256-row tile).  Returns the value now in effect; pass 0 to query. */
 OSPO_API int ospo_head_set_cta_group(int cta_group);
+/* decode step: fused = CFG tail inside the GEMM2 epilogue (1, default) or separate sampler pass (0);
+   pdl = programmatic dependent launch along the decode kernel chain (1, default).  -1 leaves a setting
+   unchanged.  Returns fused | pdl << 1. */
+OSPO_API int ospo_head_set_decode_mode(int fused, int pdl);
 /* rasterisation group size (M-blocks walked together); pass 0 to query */
 OSPO_API int ospo_head_set_group_m(int group_m);
 /* Per-kernel timing with CUDA events recorded on the caller's stream around each launch group (off by

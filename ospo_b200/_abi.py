@@ -118,6 +118,7 @@ EXPORTS = (
     "ospo_head_cfg_merge_sample",
     "ospo_head_strerror",
     "ospo_head_set_cta_group",
+    "ospo_head_set_decode_mode",
     "ospo_head_set_group_m",
     "ospo_head_profile_enable",
     "ospo_head_profile_read",
@@ -167,6 +168,8 @@ def load() -> C.CDLL:
     lib.ospo_head_strerror.restype = C.c_char_p
     lib.ospo_head_set_cta_group.argtypes = [C.c_int]
     lib.ospo_head_set_cta_group.restype = C.c_int
+    lib.ospo_head_set_decode_mode.argtypes = [C.c_int, C.c_int]
+    lib.ospo_head_set_decode_mode.restype = C.c_int
     lib.ospo_head_set_group_m.argtypes = [C.c_int]
     lib.ospo_head_set_group_m.restype = C.c_int
     lib.ospo_head_profile_enable.argtypes = [C.c_int]

@@ -21,6 +21,8 @@ struct Runtime {
   int num_sms = 0;
   int cta_group = 2;
   int group_m = 16;
+  int decode_fused = 1;  // CFG tail fused into the decode GEMM2 epilogue (0 = separate sampler pass)
+  int decode_pdl = 1;    // programmatic dependent launch along the decode kernel chain
   uint32_t* wd_host = nullptr;
   uint32_t* wd_dev = nullptr;
 };
@@ -80,6 +82,8 @@ int runtime_init() {
     const int v = atoi(e);
     if (v == 1 || v == 2) g_rt.cta_group = v;
   }
+  if (const char* e = getenv("OSPO_HEAD_DECODE_FUSED")) g_rt.decode_fused = atoi(e) != 0;
+  if (const char* e = getenv("OSPO_HEAD_DECODE_PDL")) g_rt.decode_pdl = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
     const int v = atoi(e);
     if (v > 0) g_rt.group_m = v;
@@ -105,7 +109,23 @@ LaunchCtx make_ctx(cudaStream_t s) {
   c.cta_group = g_rt.cta_group;
   c.group_m = g_rt.group_m;
   c.stream = s;
+  c.pdl = false;
   return c;
+}
+
+template <typename Kern, typename... Args>
+cudaError_t launch_plain(Kern kern, dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -149,6 +169,8 @@ struct Workspace {
   float* seq_logit_sum;  // [S]
   __nv_bfloat16* rows_by_e;  // [rows, E]: dpre (backward) / act (plain logits, decode)
   float* decode_part;        // [8, rows, E] split-K partials of the decode GEMM1 (decode-sized shapes only)
+  CfgFusedBuffers fused;     // outputs of the fused decode-GEMM2 epilogue (decode-sized shapes only)
+  __nv_bfloat16* decode_logits;  // [rows, V] scratch logits for the unfused decode variant
   size_t total;
 };
 
@@ -176,6 +198,18 @@ Workspace carve(const ospo_head_shape& s, void* base) {
   w.decode_part = (rows <= kDecodeMaxRows)
                       ? reinterpret_cast<float*>(take(8 * rows * static_cast<size_t>(s.embed) * sizeof(float)))
                       : nullptr;
+  w.fused = CfgFusedBuffers{nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (rows <= kDecodeMaxRows) {
+    const size_t P = (rows + 1) / 2, V = static_cast<size_t>(s.vocab);
+    w.fused.wbuf = reinterpret_cast<float*>(take(P * V * sizeof(float)));
+    w.fused.seg_sum = reinterpret_cast<float*>(take(P * (V / SAMPLE_SEG + 1) * sizeof(float)));
+    w.fused.tile_k = reinterpret_cast<float*>(take(P * (V / SAMPLE_TILE + 1) * sizeof(float)));
+    w.fused.tile_max = reinterpret_cast<float*>(take(P * (V / SAMPLE_TILE + 1) * sizeof(float)));
+    w.fused.tile_arg = reinterpret_cast<int*>(take(P * (V / SAMPLE_TILE + 1) * sizeof(int)));
+    w.decode_logits = reinterpret_cast<__nv_bfloat16*>(take(rows * V * 2));
+  } else {
+    w.decode_logits = nullptr;
+  }
   w.total = off;
   return w;
 }
@@ -420,34 +454,61 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
   if ((rc = check_shape(a->shape, false))) return rc;
   if (a->shape.rows % 2) return OSPO_ERR_BAD_SHAPE;
   if ((rc = check_weights(a->w))) return rc;
-  if (!a->h || !a->logits) return OSPO_ERR_NULL;
-  if (!aligned16(a->h) || !aligned16(a->logits)) return OSPO_ERR_ALIGNMENT;
+  if (!a->h || !a->ids) return OSPO_ERR_NULL;
+  if (!a->greedy && !a->uniforms) return OSPO_ERR_NULL;
+  if (!aligned16(a->h) || (a->logits && !aligned16(a->logits))) return OSPO_ERR_ALIGNMENT;
+  if (a->shape.vocab != SAMPLE_THREADS * SAMPLE_SEG) return OSPO_ERR_UNSUPPORTED;
+  if (!(a->temperature > 0.0f)) return OSPO_ERR_UNSUPPORTED;
+  if (static_cast<size_t>(a->shape.rows) > kDecodeMaxRows) return OSPO_ERR_UNSUPPORTED;
   Workspace w;
   if ((rc = check_ws(a->shape, a->workspace, a->workspace_bytes, &w))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const LaunchCtx c = make_ctx(st);
+  LaunchCtx c = make_ctx(st);
+  c.pdl = g_rt.decode_pdl != 0;
   const ospo_head_shape& s = a->shape;
-  if (static_cast<size_t>(s.rows) > kDecodeMaxRows) return OSPO_ERR_UNSUPPORTED;
   {
+    // W1 slabs over all SMs (split-K partials), then bias + GELU on the summed partials
     KernelSpan ks(st, OSPO_K_DECODE_GEMM1);
     const int64_t split_stride = static_cast<int64_t>(s.rows) * s.embed;
     rc = map_rc(launch_decode_gemm1(c, static_cast<const __nv_bfloat16*>(a->h),
                                     static_cast<const __nv_bfloat16*>(a->w.w1), w.decode_part, split_stride, s.rows,
                                     s.hidden, s.embed));
     if (rc) return rc;
-    const int n_el = s.rows * s.embed;
-    decode_act_finalize_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(
-        w.decode_part, decode_gemm1_splits(c.num_sms, s.hidden, s.embed), split_stride, a->w.b1, w.rows_by_e, s.rows,
-        s.embed);
-    if ((rc = check_launch())) return rc;
+    const int64_t n_el = static_cast<int64_t>(s.rows) * s.embed;
+    const float* part = w.decode_part;
+    if (launch_plain(decode_act_finalize_kernel, dim3(static_cast<unsigned>((n_el / 4 + 127) / 128)), dim3(128), st,
+                     c.pdl, part, decode_gemm1_splits(c.num_sms, s.hidden, s.embed), split_stride, a->w.b1,
+                     w.rows_by_e, s.rows, s.embed) != cudaSuccess)
+      return OSPO_ERR_LAUNCH;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  const int pairs = s.rows / 2;
+  if (g_rt.decode_fused && !a->merged) {
+    {
+      KernelSpan ks(st, OSPO_K_DECODE_GEMM2);
+      rc = map_rc(launch_decode_gemm2_fused(c, w.rows_by_e, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
+                                            static_cast<__nv_bfloat16*>(a->logits), s.rows, s.embed, s.vocab,
+                                            a->cfg_weight, a->temperature, a->merge_mode == OSPO_MERGE_FP32 ? 1 : 0,
+                                            a->greedy, w.fused));
+    }
+    if (rc) return rc;
+    KernelSpan ks(st, OSPO_K_SAMPLER);
+    if (launch_plain(cfg_finish_kernel, dim3(pairs), dim3(SAMPLE_THREADS), st, c.pdl, w.fused, s.vocab, a->uniforms,
+                     a->greedy, a->ids) != cudaSuccess)
+      return OSPO_ERR_LAUNCH;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return OSPO_OK;
+  }
+  // unfused variant: materialise the bf16 logits, then the stand-alone merge + sample pass
+  ospo_cfg_args b = *a;
+  if (!b.logits) b.logits = w.decode_logits;
   {
     KernelSpan ks(st, OSPO_K_DECODE_GEMM2);
     rc = map_rc(launch_decode_gemm2(c, w.rows_by_e, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
-                                    static_cast<__nv_bfloat16*>(a->logits), s.rows, s.embed, s.vocab));
+                                    static_cast<__nv_bfloat16*>(b.logits), s.rows, s.embed, s.vocab));
   }
   if (rc) return rc;
-  return launch_sampler(a, s.rows / 2, st);
+  return launch_sampler(&b, pairs, st);
 }
 
 const char* ospo_head_strerror(int status) {
@@ -470,6 +531,13 @@ int ospo_head_set_cta_group(int cta_group) {
   runtime_init();
   if (cta_group == 1 || cta_group == 2) g_rt.cta_group = cta_group;
   return g_rt.cta_group;
+}
+
+int ospo_head_set_decode_mode(int fused, int pdl) {
+  runtime_init();
+  if (fused == 0 || fused == 1) g_rt.decode_fused = fused;
+  if (pdl == 0 || pdl == 1) g_rt.decode_pdl = pdl;
+  return g_rt.decode_fused | (g_rt.decode_pdl << 1);
 }
 
 int ospo_head_set_group_m(int group_m) {

@@ -1,0 +1,95 @@
+// Arithmetic shared by the CFG sampler kernels (head_kernels.cuh) and the fused decode-GEMM epilogue
+// (epilogues.cuh): the op-by-op CFG merge, the power-of-two-relative softmax weights and the fixed summation
+// order.  oracle/cfg_sample.c restates every function here operation for operation.
+#pragma once
+
+#include "ptx.cuh"
+
+namespace ospo {
+
+constexpr int SAMPLE_THREADS = 512;
+constexpr int SAMPLE_SEG = 32;    // codes per segment (one thread / one warp lane set)
+constexpr int SAMPLE_GRP = 32;    // segments per group
+constexpr int SAMPLE_TILE = 128;  // codes per tile (= accumulator rows of one decode-GEMM CTA)
+
+// e^t = P(r) * 2^n; returns P(r), writes n (integer-valued float).  One IEEE fp32 op per line.
+__device__ __forceinline__ float exp_parts(float t, float& n) {
+  float y = __fmul_rn(t, 1.4426950408889634f);
+  y = fmaxf(y, -1.0e4f);
+  y = fminf(y, 1.0e4f);
+  n = rintf(y);
+  float r = __fmaf_rn(n, -0.693145751953125f, t);
+  r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
+  float p = 1.3888888888888889e-03f;
+  p = __fmaf_rn(p, r, 8.3333333333333332e-03f);
+  p = __fmaf_rn(p, r, 4.1666666666666664e-02f);
+  p = __fmaf_rn(p, r, 1.6666666666666666e-01f);
+  p = __fmaf_rn(p, r, 0.5f);
+  p = __fmaf_rn(p, r, 1.0f);
+  p = __fmaf_rn(p, r, 1.0f);
+  return p;
+}
+__device__ __forceinline__ float exp_n_only(float t) {
+  float y = __fmul_rn(t, 1.4426950408889634f);
+  y = fmaxf(y, -1.0e4f);
+  y = fminf(y, 1.0e4f);
+  return rintf(y);
+}
+// 2^e for integer-valued e <= 0; 0 below -120
+__device__ __forceinline__ float pow2_factor(float e) {
+  const float f = __int_as_float((static_cast<int>(e) + 127) << 23);
+  return (e < -120.0f) ? 0.0f : f;
+}
+
+// merge two adjacent codes at once so the bf16 roundings can use the packed convert (cvt.rn.bf16x2.f32).
+// MODE 0 = bf16 rounding after every op, MODE 1 = fp32.  TDIV = false skips the division (T == 1: x / 1 == x).
+__device__ __forceinline__ void round2_bf16(float& a, float& b) {
+  const uint32_t u = pack_bf16x2(a, b);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xFFFF0000u);
+}
+template <int MODE, bool TDIV>
+__device__ __forceinline__ void cfg_merge_vals(float c0, float c1, float u0, float u1, float w, float T, float& t0,
+                                               float& t1) {
+  float d0 = __fsub_rn(c0, u0), d1 = __fsub_rn(c1, u1);
+  if (MODE == 0) round2_bf16(d0, d1);
+  float e0 = __fmul_rn(w, d0), e1 = __fmul_rn(w, d1);
+  if (MODE == 0) round2_bf16(e0, e1);
+  t0 = __fadd_rn(u0, e0);
+  t1 = __fadd_rn(u1, e1);
+  if (MODE == 0) round2_bf16(t0, t1);
+  if (TDIV) {
+    t0 = __fdiv_rn(t0, T);
+    t1 = __fdiv_rn(t1, T);
+    if (MODE == 0) round2_bf16(t0, t1);
+  }
+}
+template <int MODE, bool TDIV>
+__device__ __forceinline__ void cfg_merge2(uint32_t wc, uint32_t wu, float w, float T, float& t0, float& t1) {
+  cfg_merge_vals<MODE, TDIV>(__uint_as_float(wc << 16), __uint_as_float(wc & 0xFFFF0000u), __uint_as_float(wu << 16),
+                             __uint_as_float(wu & 0xFFFF0000u), w, T, t0, t1);
+}
+
+// pairwise-adjacent tree sum of 32 registers (the order a shfl_xor butterfly 1,2,4,8,16 produces)
+__device__ __forceinline__ float tree_sum32(const float (&x)[32]) {
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = __fadd_rn(x[2 * j], x[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+  return __fadd_rn(a[0], a[1]);
+}
+
+struct CfgFusedBuffers {
+  float* wbuf;        // [P, V]      weights relative to K_tile
+  float* seg_sum;     // [P, V/32]   tree sums relative to K_tile
+  float* tile_k;      // [P, V/128]  tile exponents
+  float* tile_max;    // [P, V/128]  greedy: max merged logit of the tile
+  int* tile_arg;      // [P, V/128]  greedy: its (lowest) index
+};
+
+}  // namespace ospo

@@ -5,6 +5,7 @@
 // `chunk<FULL>`: FULL = all 32 columns are inside N -> branch- and predicate-free fast path.
 #pragma once
 
+#include "cfg_math.cuh"
 #include "gemm_sm100.cuh"
 
 namespace ospo {
@@ -390,6 +391,137 @@ struct EpiGeluBwd {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]) * gelu_erf_grad(pre[j]);
     store_row32_bf16<FULL>(p.dpre + off, v, valid);
+  }
+  __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
+};
+
+// ---------------------------------------------------------------------------
+// Decode GEMM2 (swap-AB) epilogue with the CFG tail fused in.  Accumulator row = code v, the 32 columns are the
+// CFG sample rows (2k = conditional, 2k+1 = unconditional).  While the tile is in registers:
+//   logit = bf16(acc + b2[v])                         (optionally dumped as logits[row][v])
+//   t_k   = merge(logit_2k, logit_2k+1)               image_generation.py:157-161
+//   tile exponent K_tile (max over the CTA's 128 codes), weights u = P(r) 2^(n - K_tile) -> wbuf[k][v]
+//   segment sums (a warp is exactly one 32-code segment: shfl_xor butterfly = the oracle's pairwise tree)
+// so the merged logits never exist in HBM; cfg_finish_kernel completes the draw from 512 sums per pair.
+// Needs TILE_M == 128 (one CTA = one tile) and BN == 32 (one chunk = all columns).
+// ---------------------------------------------------------------------------
+template <int MODE, bool TDIV>
+struct EpiCfgFused {
+  struct Params {
+    const float* bias;            // b2 [V]
+    float cfg_weight, temperature;
+    __nv_bfloat16* logits_dump;   // [2P, V] or null
+    int64_t ld;                   // V
+    CfgFusedBuffers buf;
+    int greedy;
+    int vocab;
+  };
+  struct State {
+    float rb;
+  };
+  static constexpr int SMEM_BYTES = 1024;  // [4 warps][16 pairs] x {float, float, int}
+
+  __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
+    st.rb = (row < d.M) ? __ldg(p.bias + row) : 0.0f;
+  }
+  template <bool FULL>
+  __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
+                               uint8_t* smem) {
+    const int lane = threadIdx.x & 31;
+    const int q = (threadIdx.x >> 5) & 3;
+    const int valid = FULL ? 32 : min(32, d.N - col0);
+    const int npairs = valid >> 1;
+    const int pair0 = col0 >> 1;
+    const int tile = row / SAMPLE_TILE;
+    const int ntile = p.vocab / SAMPLE_TILE;
+    float* sm_k = reinterpret_cast<float*>(smem);  // [4][16]
+    float* sm_v = sm_k + 64;                       // [4][16] greedy value
+    int* sm_i = reinterpret_cast<int*>(sm_v + 64);  // [4][16] greedy index
+    // logits exactly as the reference's bf16 Linear output
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      v[j] += st.rb;
+      v[j + 1] += st.rb;
+      round2_bf16(v[j], v[j + 1]);
+    }
+    if (p.logits_dump != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) p.logits_dump[static_cast<int64_t>(col0 + j) * p.ld + row] = __float2bfloat16_rn(v[j]);
+    }
+    float t[16];
+#pragma unroll
+    for (int k = 0; k < 16; k += 2)
+      cfg_merge_vals<MODE, TDIV>(v[2 * k], v[2 * k + 2], v[2 * k + 1], v[2 * k + 3], p.cfg_weight, p.temperature, t[k],
+                                 t[k + 1]);
+    if (p.greedy) {
+      // per-pair arg-max over the tile: (value, code) with the lowest code on ties
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float bv = t[k];
+        int bi = row;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+        if (lane == k) {
+          sm_v[q * 16 + k] = bv;
+          sm_i[q * 16 + k] = bi;
+        }
+      }
+      named_bar_sync(1, 128);
+      if (q == 0 && lane < npairs) {
+        float bv = sm_v[lane];
+        int bi = sm_i[lane];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          const float ov = sm_v[w * 16 + lane];
+          const int oi = sm_i[w * 16 + lane];
+          if (ov > bv || (ov == bv && oi < bi)) {
+            bv = ov;
+            bi = oi;
+          }
+        }
+        p.buf.tile_max[static_cast<int64_t>(pair0 + lane) * ntile + tile] = bv;
+        p.buf.tile_arg[static_cast<int64_t>(pair0 + lane) * ntile + tile] = bi;
+      }
+      named_bar_sync(1, 128);
+      return;
+    }
+    // tile exponent per pair
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float kt = exp_n_only(t[k]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, off));
+      if (lane == k) sm_k[q * 16 + k] = kt;
+    }
+    named_bar_sync(1, 128);
+    float u[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float kt = fmaxf(fmaxf(sm_k[k], sm_k[16 + k]), fmaxf(sm_k[32 + k], sm_k[48 + k]));
+      float n;
+      const float pr = exp_parts(t[k], n);
+      u[k] = __fmul_rn(pr, pow2_factor(__fsub_rn(n, kt)));
+      if (k < npairs) p.buf.wbuf[static_cast<int64_t>(pair0 + k) * p.vocab + row] = u[k];
+      if (q == 0 && lane == k && k < npairs) p.buf.tile_k[static_cast<int64_t>(pair0 + k) * ntile + tile] = kt;
+    }
+    // segment sums: butterfly over the warp's 32 codes == pairwise-adjacent tree
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float x = u[k];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, off));
+      if (lane == k && k < npairs)
+        p.buf.seg_sum[static_cast<int64_t>(pair0 + k) * (p.vocab / SAMPLE_SEG) + row / SAMPLE_SEG] = x;
+    }
+    named_bar_sync(1, 128);  // smem is reused by the next tile of a persistent CTA
   }
   __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
 };

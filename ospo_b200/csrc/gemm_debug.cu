@@ -26,6 +26,11 @@ int launch_gemm_debug(const LaunchCtx& c, int variant, const __nv_bfloat16* a, i
     case 120: return run<GemmCfg<1, 256, true, true>>(c, a, lda, b, ldb, out, ldo, M, N, K);
     case 101: return run<GemmCfg<1, 32, false, false>>(c, a, lda, b, ldb, out, ldo, M, N, K);
     case 102: return run<GemmCfg<1, 128, false, false>>(c, a, lda, b, ldb, out, ldo, M, N, K);
+    // decode-chain configurations of the BN=32 tile (tuning probes)
+    case 103: return run<GemmCfg<1, 32, false, false, 0, 5, 2, true>>(c, a, lda, b, ldb, out, ldo, M, N, K);
+    case 104: return run<GemmCfg<1, 32, false, false, 0, 5, 1, false>>(c, a, lda, b, ldb, out, ldo, M, N, K);
+    case 105: return run<GemmCfg<1, 32, false, false, 0, 8, 2, false>>(c, a, lda, b, ldb, out, ldo, M, N, K);
+    case 106: return run<GemmCfg<1, 32, false, false, 0, 8, 1, true>>(c, a, lda, b, ldb, out, ldo, M, N, K);
     case 200: return run<GemmCfg<2, 256, false, false>>(c, a, lda, b, ldb, out, ldo, M, N, K);
     case 210: return run<GemmCfg<2, 256, false, true>>(c, a, lda, b, ldb, out, ldo, M, N, K);
     case 220: return run<GemmCfg<2, 256, true, true>>(c, a, lda, b, ldb, out, ldo, M, N, K);

@@ -9,7 +9,8 @@ namespace ospo {
 
 void set_watchdog_decode(uint32_t* dev_ptr) { cudaMemcpyToSymbol(g_watchdog_buf, &dev_ptr, sizeof(dev_ptr)); }
 
-using CfgS32 = GemmCfg<1, 32, false, false>;
+// decode chain: 4-stage ring (~82 KB), <= 128 registers, weights (A) prefetched before the dependency wait
+using CfgS32 = GemmCfg<1, 32, false, false, 0, 5, 2, true>;
 using CfgS128 = GemmCfg<1, 128, false, false>;
 
 int decode_gemm1_splits(int num_sms, int H, int E) {
@@ -28,8 +29,8 @@ int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_b
   Epi::Params p{part, E, split_stride};
   const int ks = decode_gemm1_splits(c.num_sms, H, E);
   // D[E, n] = W1[E, H] * h[n, H]^T, as k-split partials part[ks][n][E]
-  if (n <= 32) return launch_gemm<CfgS32, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks);
-  return launch_gemm<CfgS128, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks);
+  if (n <= 32) return launch_gemm<CfgS32, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl);
+  return launch_gemm<CfgS128, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl);
 }
 
 int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
@@ -39,6 +40,30 @@ int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv
   // D[V, n] = W2[V, E] * act[n, E]^T, stored transposed as logits[n, V]
   if (n <= 32) return launch_gemm<CfgS32, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream);
   return launch_gemm<CfgS128, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream);
+}
+
+using CfgF32 = GemmCfg<1, 32, false, false, 1024, 5, 2, true>;
+
+template <int MODE, bool TDIV>
+static int run_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
+                     __nv_bfloat16* logits_dump, int n, int E, int V, float cfg_weight, float temperature, int greedy,
+                     const CfgFusedBuffers& buf) {
+  using Epi = EpiCfgFused<MODE, TDIV>;
+  typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, V, buf, greedy, V};
+  // D[V, n] = W2[V, E] * act[n, E]^T; the epilogue consumes the tile in place
+  return launch_gemm<CfgF32, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream, 1, c.pdl);
+}
+
+int launch_decode_gemm2_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
+                              __nv_bfloat16* logits_dump, int n, int E, int V, float cfg_weight, float temperature,
+                              int merge_mode, int greedy, const CfgFusedBuffers& buf) {
+  const bool tdiv = (temperature != 1.0f);
+  if (merge_mode == 0) {
+    if (tdiv) return run_fused<0, true>(c, act, w2, b2, logits_dump, n, E, V, cfg_weight, temperature, greedy, buf);
+    return run_fused<0, false>(c, act, w2, b2, logits_dump, n, E, V, cfg_weight, temperature, greedy, buf);
+  }
+  if (tdiv) return run_fused<1, true>(c, act, w2, b2, logits_dump, n, E, V, cfg_weight, temperature, greedy, buf);
+  return run_fused<1, false>(c, act, w2, b2, logits_dump, n, E, V, cfg_weight, temperature, greedy, buf);
 }
 
 }  // namespace ospo

@@ -12,9 +12,9 @@
 // (global layout [K, rows], rows contiguous); the latter is what the two weight-gradient GEMMs
 // and the two data-gradient GEMMs of the head need, so no transposed copies are ever made.
 //
-// Warp roles:  0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
-//              4.. = epilogue (warp w owns TMEM lanes 32*(w%4) .. +32; with 8 epilogue warps, warps 4-7
-//              take the left half of the tile's columns and warps 8-11 the right half).
+// Warp roles:  0 = TMA producer, 1 = MMA issuer (also allocates / frees TMEM),
+//              2.. = epilogue (warp w owns TMEM lanes 32*(w%4) .. +32; with 8 epilogue warps, warps 2-5
+//              take the left half of the tile's columns and warps 6-9 the right half).
 #pragma once
 
 #include "ptx.cuh"
@@ -36,8 +36,15 @@ enum : uint32_t {
   SITE_EPI_TMEM_FULL = 4,
 };
 
-template <int CG_, int BN_, bool A_MN_, bool B_MN_, int EPI_SMEM_BYTES_ = 0>
+// MAX_STAGES_ / MIN_BLOCKS_ / A_INDEPENDENT_ serve the decode chain: a short ring (about 80 KB) and <= 128
+// registers let the NEXT kernel of a programmatic-dependent-launch chain become resident beside the running
+// one, and A_INDEPENDENT_ (the A operand -- a weight matrix -- does not depend on the predecessor kernel) lets
+// its producer start streaming weights before griddepcontrol.wait, so HBM never idles at a kernel boundary.
+template <int CG_, int BN_, bool A_MN_, bool B_MN_, int EPI_SMEM_BYTES_ = 0, int MAX_STAGES_ = 8, int MIN_BLOCKS_ = 1,
+          bool A_INDEPENDENT_ = false>
 struct GemmCfg {
+  static constexpr int MIN_BLOCKS = MIN_BLOCKS_;
+  static constexpr bool A_INDEPENDENT = A_INDEPENDENT_;
   static constexpr int CG = CG_;            // CTAs cooperating on one tile (cta_group)
   static constexpr int BN = BN_;            // tile N (UMMA N)
   static constexpr bool A_MN = A_MN_;
@@ -53,7 +60,7 @@ struct GemmCfg {
   static constexpr int EPI_SMEM_BYTES = EPI_SMEM_BYTES_;
   static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - EPI_SMEM_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES = STAGES_RAW > MAX_STAGES_ ? MAX_STAGES_ : STAGES_RAW;
   static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = ACC_STAGES * BN;
   static constexpr int TMEM_COLS =
@@ -63,7 +70,10 @@ struct GemmCfg {
   // columns) -- a lone warp per scheduler cannot hide the latency of a math-heavy epilogue.
   static constexpr int EPI_SPLIT = (BN >= 64) ? 2 : 1;
   static constexpr int EPI_WARPS = 4 * EPI_SPLIT;
-  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  // register cap for the co-resident decode chain: bounding on one extra warp leaves room (65536 regs / SM) for
+  // two GEMM CTAs plus the small kernel that sits between them
+  static constexpr int BOUND_THREADS = (MIN_BLOCKS > 1) ? THREADS + 32 : THREADS;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16, 256]");
   static_assert(!B_MN || (B_ROWS % 64 == 0), "MN-major B is staged in 64-row swizzle atoms");
   static_assert(B_ROWS % 8 == 0, "K-major B rows come in 8-row swizzle groups");
@@ -102,12 +112,13 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n, int
 // is handled by two threads (column halves); `sub_tile` = n_blk * EPI_SPLIT + half identifies the part.
 
 template <class Cfg, class Epi>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::BOUND_THREADS, Cfg::MIN_BLOCKS)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmDims dims,
             typename Epi::Params ep) {
   constexpr int CG = Cfg::CG, BN = Cfg::BN, BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
 
+  pdl_launch_dependents();  // our successor may start its own prologue (and weight prefetch) right away
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte alignment (in the shared address space)
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -147,19 +158,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 1) {
+    __syncwarp();
     tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // Programmatic dependent launch: everything above overlapped the predecessor; each role executes
+  // pdl_wait() before it first touches global memory that the predecessor may still be producing.
 
   if (warp == 0) {
     // ===================== TMA producer (one elected thread) =====================
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
+      auto load_a = [&](uint8_t* sa, int s_, int m0, int k0) {
+        if constexpr (!Cfg::A_MN) {
+          if constexpr (CG == 1) tma_load_2d(sa, &tmap_a, &full_bar[s_], k0, m0, kEvictNormal);
+          else tma_load_2d_2sm(sa, &tmap_a, &full_bar[s_], k0, m0, kEvictNormal);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) {
+            if constexpr (CG == 1) tma_load_2d(sa + c * (BK * 128), &tmap_a, &full_bar[s_], m0 + 64 * c, k0, kEvictNormal);
+            else tma_load_2d_2sm(sa + c * (BK * 128), &tmap_a, &full_bar[s_], m0 + 64 * c, k0, kEvictNormal);
+          }
+        }
+      };
+      auto load_b = [&](uint8_t* sb, int s_, int n0, int k0) {
+        if constexpr (!Cfg::B_MN) {
+          if constexpr (CG == 1) tma_load_2d(sb, &tmap_b, &full_bar[s_], k0, n0, kEvictNormal);
+          else tma_load_2d_2sm(sb, &tmap_b, &full_bar[s_], k0, n0, kEvictNormal);
+        } else {
+#pragma unroll
+          for (int c = 0; c < Cfg::B_ROWS / 64; ++c) {
+            if constexpr (CG == 1) tma_load_2d(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, kEvictNormal);
+            else tma_load_2d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, kEvictNormal);
+          }
+        }
+      };
+      // Weight prefetch ahead of the dependency wait: the first ring-full of A tiles of this CTA's first
+      // work item is requested now; their B halves follow after pdl_wait().
+      int prefetched = 0;
+      if constexpr (Cfg::A_INDEPENDENT) {
+        if (cluster_id < num_tiles) {
+          const int t = cluster_id;
+          const TileCoord tc = tile_coord(t / ksplits, num_m, num_n, dims.group_m);
+          const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
+          const int kb0 = (t % ksplits) * dims.kb_per_split;
+          const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
+          prefetched = min(STAGES, kb1 - kb0);
+          for (int i = 0; i < prefetched; ++i) {
+            uint8_t* sa = stage_base + i * Cfg::STAGE_BYTES;
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES * CG);
+            load_a(sa, i, m0, (kb0 + i) * BK);
+          }
+        }
+      }
+      pdl_wait();
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const TileCoord tc = tile_coord(t / ksplits, num_m, num_n, dims.group_m);
         const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
@@ -167,30 +224,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int kb0 = (t % ksplits) * dims.kb_per_split;
         const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1u, SITE_PRODUCER_EMPTY);
           uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          if (is_leader) mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES * CG);
           const int k0 = kb * BK;
-          if constexpr (!Cfg::A_MN) {
-            if constexpr (CG == 1) tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0, kEvictNormal);
-            else tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], k0, m0, kEvictNormal);
+          if (prefetched > 0) {
+            // stage already armed and its A tile in flight
+            --prefetched;
+            load_b(sb, s, n0, k0);
           } else {
-#pragma unroll
-            for (int c = 0; c < BM / 64; ++c) {
-              if constexpr (CG == 1) tma_load_2d(sa + c * (BK * 128), &tmap_a, &full_bar[s], m0 + 64 * c, k0, kEvictNormal);
-              else tma_load_2d_2sm(sa + c * (BK * 128), &tmap_a, &full_bar[s], m0 + 64 * c, k0, kEvictNormal);
-            }
-          }
-          if constexpr (!Cfg::B_MN) {
-            if constexpr (CG == 1) tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0, kEvictNormal);
-            else tma_load_2d_2sm(sb, &tmap_b, &full_bar[s], k0, n0, kEvictNormal);
-          } else {
-#pragma unroll
-            for (int c = 0; c < Cfg::B_ROWS / 64; ++c) {
-              if constexpr (CG == 1) tma_load_2d(sb + c * (BK * 128), &tmap_b, &full_bar[s], n0 + 64 * c, k0, kEvictNormal);
-              else tma_load_2d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s], n0 + 64 * c, k0, kEvictNormal);
-            }
+            mbar_wait(&empty_bar[s], ph ^ 1u, SITE_PRODUCER_EMPTY);
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES * CG);
+            load_a(sa, s, m0, k0);
+            load_b(sb, s, n0, k0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -242,10 +287,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 2) {
     // ===================== epilogue warps =====================
+    pdl_wait();                        // the epilogue reads / writes global memory
     const int q = warp & 3;            // TMEM lane quarter this warp may touch
-    const int half = (warp - 4) >> 2;  // which half of the tile's columns (EPI_SPLIT == 2)
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns (EPI_SPLIT == 2)
     uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 256;
     uint32_t leader_tmem_empty_addr[ACC_STAGES];
 #pragma unroll
@@ -310,7 +356,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncwarp();  // re-converge the single-thread roles before the block-wide barrier
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
   }
@@ -363,7 +409,8 @@ inline void gemm_split_plan(int num_kb, int want, int* k_splits, int* kb_per_spl
 // a / b: global pointers.  K-major operand: [rows, K] with pitch ld; MN-major operand: [K, rows] with pitch ld.
 template <class Cfg, class Epi>
 int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K, int group_m,
-                const typename Epi::Params& ep, int num_sms, cudaStream_t stream, int k_splits = 1) {
+                const typename Epi::Params& ep, int num_sms, cudaStream_t stream, int k_splits = 1,
+                bool pdl = false) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   CUtensorMap ta, tb;
   int rc;
@@ -400,13 +447,18 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = Cfg::CG;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
+  if (pdl) {
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, dims, ep);
   return e == cudaSuccess ? 0 : -4;
 }

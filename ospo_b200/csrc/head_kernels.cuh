@@ -4,6 +4,7 @@
 // All are HBM- or latency-bound; grids are sized from the data, loads are 16-byte vectors.
 #pragma once
 
+#include "cfg_math.cuh"
 #include "ptx.cuh"
 
 namespace ospo {
@@ -262,18 +263,33 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, in
 }
 
 // ---------------------------------------------------------------------------
-// decode GEMM1 finalize: act[n, e] = bf16(gelu_erf(bf16(sum_k part[k][n][e] + b1[e])))  (fixed summation order)
+// decode GEMM1 finalize: act[n, e] = bf16(gelu_erf(bf16(sum_k part[k][n][e] + b1[e])))  (fixed summation order).
+// Small footprint on purpose (128-thread blocks, 4 elements per thread): it sits between the two decode GEMMs of a
+// programmatic-dependent-launch chain and must fit beside their resident CTAs.
 // ---------------------------------------------------------------------------
-__global__ void decode_act_finalize_kernel(const float* __restrict__ part, int k_splits, int64_t split_stride,
-                                           const float* __restrict__ b1, __nv_bfloat16* __restrict__ act, int n,
-                                           int E) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * E) return;
-  float s = part[i];
-  for (int k = 1; k < k_splits; ++k) s += part[static_cast<int64_t>(k) * split_stride + i];
-  const float x = bf16_round(s + __ldg(b1 + (i % E)));
-  const float g = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
-  act[i] = __float2bfloat16_rn(g);
+__global__ void __launch_bounds__(128)
+decode_act_finalize_kernel(const float* __restrict__ part, int k_splits, int64_t split_stride,
+                           const float* __restrict__ b1, __nv_bfloat16* __restrict__ act, int n, int E) {
+  pdl_launch_dependents();  // the next GEMM may become resident and prefetch its weights; it waits for us
+  pdl_wait();
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= static_cast<int64_t>(n) * E) return;
+  float4 s = __ldcg(reinterpret_cast<const float4*>(part + i));
+  for (int k = 1; k < k_splits; ++k) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(part + static_cast<int64_t>(k) * split_stride + i));
+    s.x += t.x;
+    s.y += t.y;
+    s.z += t.z;
+    s.w += t.w;
+  }
+  const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + (i % E)));
+  float x[4] = {bf16_round(s.x + b.x), bf16_round(s.y + b.y), bf16_round(s.z + b.z), bf16_round(s.w + b.w)};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) x[j] = 0.5f * x[j] * (1.0f + erff(x[j] * 0.70710678118654752f));
+  uint2 o;
+  o.x = pack_bf16x2(x[0], x[1]);
+  o.y = pack_bf16x2(x[2], x[3]);
+  *reinterpret_cast<uint2*>(act + i) = o;
 }
 
 // ---------------------------------------------------------------------------
@@ -291,83 +307,6 @@ __global__ void decode_act_finalize_kernel(const float* __restrict__ part, int k
 // lets the decode GEMM's epilogue (EpiCfgFused, epilogues.cuh) produce the weights and segment sums while
 // the logits are still in tensor memory.  greedy: argmax_v t_v, lowest index on ties.
 // ---------------------------------------------------------------------------
-constexpr int SAMPLE_THREADS = 512;
-constexpr int SAMPLE_SEG = 32;    // codes per segment (one thread / one warp lane set)
-constexpr int SAMPLE_GRP = 32;    // segments per group
-constexpr int SAMPLE_TILE = 128;  // codes per tile (= accumulator rows of one decode-GEMM CTA)
-
-// e^t = P(r) * 2^n; returns P(r), writes n (integer-valued float).  One IEEE fp32 op per line.
-__device__ __forceinline__ float exp_parts(float t, float& n) {
-  float y = __fmul_rn(t, 1.4426950408889634f);
-  y = fmaxf(y, -1.0e4f);
-  y = fminf(y, 1.0e4f);
-  n = rintf(y);
-  float r = __fmaf_rn(n, -0.693145751953125f, t);
-  r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
-  float p = 1.3888888888888889e-03f;
-  p = __fmaf_rn(p, r, 8.3333333333333332e-03f);
-  p = __fmaf_rn(p, r, 4.1666666666666664e-02f);
-  p = __fmaf_rn(p, r, 1.6666666666666666e-01f);
-  p = __fmaf_rn(p, r, 0.5f);
-  p = __fmaf_rn(p, r, 1.0f);
-  p = __fmaf_rn(p, r, 1.0f);
-  return p;
-}
-__device__ __forceinline__ float exp_n_only(float t) {
-  float y = __fmul_rn(t, 1.4426950408889634f);
-  y = fmaxf(y, -1.0e4f);
-  y = fminf(y, 1.0e4f);
-  return rintf(y);
-}
-// 2^e for integer-valued e <= 0; 0 below -120
-__device__ __forceinline__ float pow2_factor(float e) {
-  const float f = __int_as_float((static_cast<int>(e) + 127) << 23);
-  return (e < -120.0f) ? 0.0f : f;
-}
-
-// merge two adjacent codes at once so the bf16 roundings can use the packed convert (cvt.rn.bf16x2.f32).
-// MODE 0 = bf16 rounding after every op, MODE 1 = fp32.  TDIV = false skips the division (T == 1: x / 1 == x).
-__device__ __forceinline__ void round2_bf16(float& a, float& b) {
-  const uint32_t u = pack_bf16x2(a, b);
-  a = __uint_as_float(u << 16);
-  b = __uint_as_float(u & 0xFFFF0000u);
-}
-template <int MODE, bool TDIV>
-__device__ __forceinline__ void cfg_merge_vals(float c0, float c1, float u0, float u1, float w, float T, float& t0,
-                                               float& t1) {
-  float d0 = __fsub_rn(c0, u0), d1 = __fsub_rn(c1, u1);
-  if (MODE == 0) round2_bf16(d0, d1);
-  float e0 = __fmul_rn(w, d0), e1 = __fmul_rn(w, d1);
-  if (MODE == 0) round2_bf16(e0, e1);
-  t0 = __fadd_rn(u0, e0);
-  t1 = __fadd_rn(u1, e1);
-  if (MODE == 0) round2_bf16(t0, t1);
-  if (TDIV) {
-    t0 = __fdiv_rn(t0, T);
-    t1 = __fdiv_rn(t1, T);
-    if (MODE == 0) round2_bf16(t0, t1);
-  }
-}
-template <int MODE, bool TDIV>
-__device__ __forceinline__ void cfg_merge2(uint32_t wc, uint32_t wu, float w, float T, float& t0, float& t1) {
-  cfg_merge_vals<MODE, TDIV>(__uint_as_float(wc << 16), __uint_as_float(wc & 0xFFFF0000u), __uint_as_float(wu << 16),
-                             __uint_as_float(wu & 0xFFFF0000u), w, T, t0, t1);
-}
-
-// pairwise-adjacent tree sum of 32 registers (the order a shfl_xor butterfly 1,2,4,8,16 produces)
-__device__ __forceinline__ float tree_sum32(const float (&x)[32]) {
-  float a[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) a[j] = __fadd_rn(x[2 * j], x[2 * j + 1]);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
-  return __fadd_rn(a[0], a[1]);
-}
-
 // The descent shared by the stand-alone sampler and the finish kernel of the fused decode step.
 // seg_sum[512] (already rescaled to the global exponent) and grp_sum[16] live in shared memory; executed by
 // ONE thread; returns the winning segment and the cdf value before it.
@@ -545,13 +484,6 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
 // pair: the weights u (relative to each tile's exponent), 512 segment sums, 128 tile exponents and, for the
 // greedy mode, per-tile arg-max candidates.  One block per pair finishes the draw.
 // ---------------------------------------------------------------------------
-struct CfgFusedBuffers {
-  float* wbuf;        // [P, V]      weights relative to K_tile
-  float* seg_sum;     // [P, V/32]   tree sums relative to K_tile
-  float* tile_k;      // [P, V/128]  tile exponents
-  float* tile_max;    // [P, V/128]  greedy: max merged logit of the tile
-  int* tile_arg;      // [P, V/128]  greedy: its (lowest) index
-};
 
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ uniforms, int greedy,
@@ -559,6 +491,8 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
   __shared__ float seg_sum[SAMPLE_THREADS];
   __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
   __shared__ float wmax[SAMPLE_THREADS / 32];
+  pdl_launch_dependents();  // successors may become resident and prefetch; they wait for our completion
+  pdl_wait();
   const int p = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -599,19 +533,39 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
     grp_sum[tid] = g;
   }
   __syncthreads();
+  __shared__ int bc_seg;
+  __shared__ float bc_base, bc_target;
   if (tid == 0) {
     int segi;
     float base, target;
     cdf_descent(seg_sum, grp_sum, __ldg(uniforms + p), segi, base, target);
+    bc_seg = segi;
+    bc_base = base;
+    bc_target = target;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // the winning segment's 32 weights arrive with one coalesced load; lane 0 walks them in order
+    const int segi = bc_seg;
     const float fs = pow2_factor(__fsub_rn(b.tile_k[p * ntile + segi / (SAMPLE_TILE / SAMPLE_SEG)], K));
-    const float* w = b.wbuf + static_cast<int64_t>(p) * vocab + segi * SAMPLE_SEG;
+    const float wl = __fmul_rn(__ldcg(b.wbuf + static_cast<int64_t>(p) * vocab + segi * SAMPLE_SEG + lane), fs);
+    float base = bc_base;
+    const float target = bc_target;
     int j = 0;
-    for (; j < SAMPLE_SEG - 1; ++j) {
-      const float nxt = __fadd_rn(base, __fmul_rn(w[j], fs));
-      if (nxt > target) break;
-      base = nxt;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < SAMPLE_SEG - 1; ++i) {
+      const float wi = __shfl_sync(0xffffffffu, wl, i);
+      const float nxt = __fadd_rn(base, wi);
+      if (!found) {
+        if (nxt > target) found = true;
+        else {
+          base = nxt;
+          j = i + 1;
+        }
+      }
     }
-    ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
+    if (lane == 0) ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
   }
 }
 

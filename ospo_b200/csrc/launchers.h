@@ -14,7 +14,10 @@ struct LaunchCtx {
   int cta_group;  // 1 or 2
   int group_m;    // rasterisation group (M-blocks)
   cudaStream_t stream;
+  bool pdl;       // launch with programmatic stream serialization (decode chain)
 };
+
+struct CfgFusedBuffers;
 
 // every TU that contains kernels using mbar_wait owns a copy of the watchdog pointer
 void set_watchdog_fwd(uint32_t* dev_ptr);
@@ -47,14 +50,20 @@ int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat1
                  int out_dim, int in_dim);
 
 // ---- decode, swap-AB (gemm_decode.cu) ----
-// part[ks][n][E] (fp32) = k-split partials of W1 h^T;  h [n,H] with n = 2P small.  The caller sums the partials,
-// adds b1 and applies GELU (decode_act_finalize_kernel).  decode_gemm1_splits() = number of partials written.
+// part[ks][n][E] (fp32) = k-split partials of W1 h^T;  h [n,H] with n = 2P small: W1 is streamed as (128-row tile
+// x k-split) work items over all SMs.  decode_act_finalize_kernel sums the partials in split order (deterministic),
+// adds b1 and applies GELU.  decode_gemm1_splits() = number of partials written.
 int decode_gemm1_splits(int num_sms, int H, int E);
 int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, float* part,
                         int64_t split_stride, int n, int H, int E);
 // logits[n, v] = bf16(W2 act^T + b2)
 int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                         __nv_bfloat16* logits, int n, int E, int V);
+// the same GEMM with the CFG merge / softmax-weight / segment-sum tail fused into the epilogue (EpiCfgFused);
+// merge_mode 0 = bf16 op-by-op, 1 = fp32; logits_dump may be null
+int launch_decode_gemm2_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
+                              __nv_bfloat16* logits_dump, int n, int E, int V, float cfg_weight, float temperature,
+                              int merge_mode, int greedy, const CfgFusedBuffers& buf);
 
 // ---- debug / validation (gemm_debug.cu) ----
 // out[M,N] fp32 = A B^T for one engine variant; see abi.cu for the variant table

@@ -181,6 +181,17 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
   return r;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start (prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor drains; it must
+// execute pdl_wait() before it touches global memory.  pdl_launch_dependents() lets the successor start.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// named barrier among a subset of the CTA's warps (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM loads
 // ---------------------------------------------------------------------------

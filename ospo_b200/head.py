@@ -287,7 +287,7 @@ class FusedGenHead(torch.nn.Module):
             u = uniforms.to(torch.float32).contiguous()
         mm = _abi.MERGE_BF16 if merge_mode == "bf16" else _abi.MERGE_FP32
         ids, logits = ops.cfg_sample_impl(h, p.w1, p.b1, p.w2, p.b2, float(cfg_weight), float(temperature), u,
-                                          bool(greedy), mm)
+                                          bool(greedy), mm, bool(return_logits))
         return (ids, logits) if return_logits else ids
 
 

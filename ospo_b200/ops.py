@@ -200,8 +200,10 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
 # CFG decode step
 # --------------------------------------------------------------------------------------------------
 def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, cfg_weight: float, temperature: float,
-               uniforms: Tensor, greedy: bool, merge_mode: int) -> List[Tensor]:
-    """-> [ids[P] int64, logits[2P, V] bf16]   (image_generation.py:156-164; row 2k cond / 2k+1 uncond)"""
+               uniforms: Tensor, greedy: bool, merge_mode: int, want_logits: bool = False) -> List[Tensor]:
+    """-> [ids[P] int64, logits[2P, V] bf16 (empty unless want_logits)]
+    (image_generation.py:156-164; row 2k cond / 2k+1 uncond).  Without want_logits the logits never leave the
+    chip: the CFG merge, softmax weights and segment sums are produced in the GEMM epilogue."""
     _check_cuda(h, uniforms)
     assert h.dim() == 2 and h.dtype == torch.bfloat16 and h.is_contiguous() and h.shape[0] % 2 == 0
     rows, H = h.shape
@@ -211,20 +213,20 @@ def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, c
     if not greedy:
         assert uniforms.dtype == torch.float32 and uniforms.numel() == P and uniforms.is_contiguous()
     ids = torch.empty(P, dtype=torch.int64, device=dev)
-    logits = torch.empty(rows, V, dtype=torch.bfloat16, device=dev)
+    logits = torch.empty(rows, V, dtype=torch.bfloat16, device=dev) if want_logits else None
     ws = _workspace(rows, H, E, V, 1, dev)
     a = _abi.CfgArgs()
     a.shape = _abi.Shape(rows, H, E, V, 1)
     a.w = _weights(w1, b1, w2, b2)
     a.h = h.data_ptr()
-    a.logits = logits.data_ptr()
+    a.logits = _ptr(logits)
     a.cfg_weight, a.temperature, a.merge_mode, a.greedy, a.num_steps = cfg_weight, temperature, merge_mode, int(greedy), 1
     a.uniforms = None if greedy else uniforms.data_ptr()
     a.ids = ids.data_ptr()
     a.merged = None
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     _abi.check(_abi.load().ospo_head_cfg_sample(C.byref(a), _stream()), "ospo_head_cfg_sample")
-    return [ids, logits]
+    return [ids, logits if logits is not None else torch.empty(0, dtype=torch.bfloat16, device=dev)]
 
 
 def cfg_merge_sample_impl(logits: Tensor, cfg_weight: float, temperature: float, uniforms: Tensor, greedy: bool,

@@ -14,7 +14,7 @@ dev = torch.device("cuda:0")
 N = 32
 
 
-def bench(M, K, tag):
+def bench(M, K, tag, variant=101):
     A = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(2)]
     B = torch.randn(N, K, device=dev).to(torch.bfloat16)
     out = torch.empty(M, N, device=dev)
@@ -22,7 +22,7 @@ def bench(M, K, tag):
     def run():
         for i in range(32):
             a = A[i & 1]
-            lib.ospo_head_gemm_debug(101, a.data_ptr(), a.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(),
+            lib.ospo_head_gemm_debug(variant, a.data_ptr(), a.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(),
                                      out.stride(0), M, N, K, torch.cuda.current_stream().cuda_stream)
 
     s = torch.cuda.Stream()
@@ -42,12 +42,10 @@ def bench(M, K, tag):
     e1.record()
     torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / 5 / 32
-    print(f"STREAM {tag}: M={M} K={K} us={us:.2f} GB/s={M * K * 2 / us / 1e3:.0f}", flush=True)
+    print(f"STREAM {tag} v{variant}: M={M} K={K} us={us:.2f} GB/s={M * K * 2 / us / 1e3:.0f}", flush=True)
 
 
-bench(16384, 4096, "W2 128 tiles")
-bench(148 * 128, 4096, "148 tiles")
-bench(2 * 148 * 128, 4096, "296 tiles")
-bench(4096, 4096, "W1 32 tiles")
-bench(148 * 128, 64, "launch+prologue only (1 k-block)")
-bench(148 * 128, 1024, "148 tiles K=1024")
+for v in (101, 103, 104, 105, 106):
+    bench(16384, 4096, "W2 128 tiles", v)
+for v in (101, 103):
+    bench(4096, 4096, "W1 32 tiles", v)

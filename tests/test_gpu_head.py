@@ -367,9 +367,38 @@ def test_cfg_sample_fused_step_vs_oracle(golden_dir):
         torch.testing.assert_close(lg.float().cpu(), ref_logits[s].float(), rtol=2e-2, atol=2e-2)
         oid, *_ = O.cfg_sample_det(lg.cpu(), 5.0, 1.0, u, merge_mode=0)
         assert torch.equal(ids.cpu(), oid)
+        # without the dump the logits never leave the chip; the draw is the same
+        assert torch.equal(fh.cfg_sample(hidden[s].to(dev), 5.0, 1.0, uniforms=u.to(dev)), ids)
         gid = fh.cfg_sample(hidden[s].to(dev), 5.0, 1.0, greedy=True)
         ogid, *_ = O.cfg_sample_det(lg.cpu(), 5.0, 1.0, None, merge_mode=0, greedy=True)
         assert torch.equal(gid.cpu(), ogid)
+
+
+@pytest.mark.parametrize("fused,pdl", [(1, 1), (1, 0), (0, 1), (0, 0)])
+@pytest.mark.parametrize("mode,w,T", [("bf16", 5.0, 1.0), ("fp32", 3.0, 0.7)])
+def test_cfg_sample_decode_variants_agree(fused, pdl, mode, w, T):
+    """fused-epilogue / separate-sampler and PDL on/off variants of the decode step draw identical ids"""
+    from ospo_b200 import _abi
+
+    dev = _cuda()
+    H, E, V, P = 512, 384, 16384, 5
+    head_b = O.make_head(H, E, V, seed=31, w2_gain=4.0).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    g = torch.Generator().manual_seed(32)
+    h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16).to(dev)
+    u = torch.rand(P, generator=g)
+    lib = _abi.load()
+    try:
+        lib.ospo_head_set_decode_mode(fused, pdl)
+        ids, lg = fh.cfg_sample(h, w, T, uniforms=u.to(dev), merge_mode=mode, return_logits=True)
+        gids = fh.cfg_sample(h, w, T, greedy=True, merge_mode=mode)
+        torch.cuda.synchronize()
+    finally:
+        lib.ospo_head_set_decode_mode(1, 1)
+    mm = 0 if mode == "bf16" else 1
+    oid, *_ = O.cfg_sample_det(lg.cpu(), w, T, u, merge_mode=mm)
+    ogid, *_ = O.cfg_sample_det(lg.cpu(), w, T, None, merge_mode=mm, greedy=True)
+    assert torch.equal(ids.cpu(), oid) and torch.equal(gids.cpu(), ogid)
 
 
 def test_cfg_sample_7b_shape_p16():

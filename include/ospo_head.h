@@ -98,7 +98,12 @@ typedef struct {
 typedef struct {
   ospo_head_shape shape;
   ospo_head_weights w;
-  const void* x;               /* bf16 [rows, H] */
+  const void* x;               /* bf16 [rows, H], or the base of a [S, x_seg_pitch, H] tensor (see x_seg_*) */
+  /* Row-segmented hidden states (all 0 = x is a contiguous [rows, H] matrix).  With x_seg_rows = T > 0 (a multiple
+     of 64), x and dx point at [S, x_seg_pitch, H] tensors -- the backbone's last hidden state as it lies in memory,
+     ospo/wrapper/train.py:356 -- and the head's rows are rows [x_seg_off, x_seg_off + T) of every sequence; rows
+     must equal S * T.  Nothing is copied; dx rows outside the span are left untouched (the caller zeroes them). */
+  int32_t x_seg_rows, x_seg_pitch, x_seg_off;
   const int64_t* labels;       /* [rows] target code of each row, in [0, V)  (labels[:,1:] after masking) */
   const int64_t* seq_offsets;  /* [S+1] row range of each sequence: rows [off[s], off[s+1]) */
   int32_t average_log_prob;    /* get_batch_logps(average_log_prob=...)  train.py:393-396 */

@@ -51,6 +51,9 @@ class SimpoArgs(C.Structure):
         ("shape", Shape),
         ("w", Weights),
         ("x", C.c_void_p),
+        ("x_seg_rows", C.c_int32),
+        ("x_seg_pitch", C.c_int32),
+        ("x_seg_off", C.c_int32),
         ("labels", C.c_void_p),
         ("seq_offsets", C.c_void_p),
         ("average_log_prob", C.c_int32),

@@ -222,6 +222,15 @@ int check_ws(const ospo_head_shape& s, void* ws, size_t bytes, Workspace* out) {
   return OSPO_OK;
 }
 
+XLayout x_layout(const ospo_simpo_args* a) {
+  XLayout xl;
+  xl.seg_rows = a->x_seg_rows;
+  xl.seg_pitch = a->x_seg_pitch;
+  xl.seg_off = a->x_seg_off;
+  xl.segments = a->shape.num_seqs;
+  return xl;
+}
+
 // shared forward: GEMM1 -> GEMM2 + LSE partials -> merge -> per-sequence reduce
 int logps_forward(const ospo_simpo_args* a, const Workspace& w, cudaStream_t st) {
   const ospo_head_shape& s = a->shape;
@@ -232,7 +241,7 @@ int logps_forward(const ospo_simpo_args* a, const Workspace& w, cudaStream_t st)
     rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
                                        static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1,
                                        static_cast<__nv_bfloat16*>(a->pre), static_cast<__nv_bfloat16*>(a->act),
-                                       s.rows, s.hidden, s.embed));
+                                       s.rows, s.hidden, s.embed, x_layout(a)));
   }
   if (rc) return rc;
   {
@@ -261,6 +270,12 @@ int check_simpo_common(const ospo_simpo_args* a, Workspace* w) {
   if ((rc = check_weights(a->w))) return rc;
   if (!a->x || !a->labels || !a->seq_offsets) return OSPO_ERR_NULL;
   if (!aligned16(a->x)) return OSPO_ERR_ALIGNMENT;
+  if (a->x_seg_rows != 0) {
+    if (a->x_seg_rows < 0 || (a->x_seg_rows % 64) || a->x_seg_off < 0 ||
+        a->x_seg_off + a->x_seg_rows > a->x_seg_pitch ||
+        static_cast<int64_t>(a->x_seg_rows) * a->shape.num_seqs != a->shape.rows)
+      return OSPO_ERR_BAD_SHAPE;
+  }
   return check_ws(a->shape, a->workspace, a->workspace_bytes, w);
 }
 
@@ -314,14 +329,15 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
     }
     {
       KernelSpan ks(st, OSPO_K_WGRAD1);
-      rc = map_rc(launch_wgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden));
+      rc = map_rc(launch_wgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden,
+                               x_layout(a)));
     }
     if (rc) return rc;
   }
   if (a->dx) {
     KernelSpan ks(st, OSPO_K_DGRAD);
     rc = map_rc(launch_dgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->w.w1), static_cast<__nv_bfloat16*>(a->dx),
-                             s.rows, s.embed, s.hidden));
+                             s.rows, s.embed, s.hidden, x_layout(a)));
     if (rc) return rc;
   }
   return OSPO_OK;
@@ -549,6 +565,15 @@ int ospo_head_set_group_m(int group_m) {
 int ospo_head_profile_enable(int enable) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_profile = enable != 0;
+  if (g_profile) {
+    // events are created up front so that no cudaEventCreate lands inside a timed region
+    g_spans.reserve(4096);
+    while (g_event_pool.size() < 1024) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      g_event_pool.push_back(e);
+    }
+  }
   return g_profile ? 1 : 0;
 }
 

@@ -125,14 +125,17 @@ struct EpiStore {
     OutT* out;
     int64_t ld;
     const float* bias;  // may be null
+    RowMap rmap;        // where output row r lands (identity unless the output is row-segmented)
   };
   struct State {
     float rb;
+    int64_t prow;
   };
   static constexpr int SMEM_BYTES = 0;
 
   __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
     st.rb = (ROW_BIAS && p.bias != nullptr && row < d.M) ? __ldg(p.bias + row) : 0.0f;
+    st.prow = p.rmap(row);
   }
   template <bool FULL>
   __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
@@ -152,7 +155,7 @@ struct EpiStore {
       }
     }
     if constexpr (!TRANSPOSE) {
-      OutT* dst = p.out + static_cast<int64_t>(row) * p.ld + col0;
+      OutT* dst = p.out + st.prow * p.ld + col0;
       if constexpr (sizeof(OutT) == 4) store_row32_f32<FULL>(reinterpret_cast<float*>(dst), v, valid);
       else store_row32_bf16<FULL>(reinterpret_cast<__nv_bfloat16*>(dst), v, valid);
     } else {

@@ -23,22 +23,29 @@ int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* dlogits, const
 }
 
 int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx, int rows,
-                 int out_dim, int in_dim) {
+                 int out_dim, int in_dim, const XLayout& xl) {
   using Epi = EpiStore<__nv_bfloat16, false, false>;
-  Epi::Params p{dx, in_dim, nullptr};
+  Epi::Params p{dx, in_dim, nullptr, RowMap{xl.seg_rows, xl.seg_pitch, xl.seg_off}};
   if (c.cta_group == 2)
     return launch_gemm<CfgD2, Epi>(dy, out_dim, w, in_dim, rows, in_dim, out_dim, c.group_m, p, c.num_sms, c.stream);
   return launch_gemm<CfgD1, Epi>(dy, out_dim, w, in_dim, rows, in_dim, out_dim, c.group_m, p, c.num_sms, c.stream);
 }
 
 int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw, int rows, int out_dim,
-                 int in_dim) {
+                 int in_dim, const XLayout& xl) {
   using Epi = EpiStore<float, false, false>;
   Epi::Params p{dw, in_dim, nullptr};
+  SegOperand sb;
+  sb.seg_rows = xl.seg_rows;
+  sb.seg_pitch = xl.seg_pitch;
+  sb.seg_off = xl.seg_off;
+  sb.segments = xl.segments;
   // D[out, in] = dY^T[out, rows] * X[rows, in]:  M = out_dim, N = in_dim, K = rows
   if (c.cta_group == 2)
-    return launch_gemm<CfgW2, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream);
-  return launch_gemm<CfgW1, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream);
+    return launch_gemm<CfgW2, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream, 1,
+                                   false, SegOperand(), sb);
+  return launch_gemm<CfgW1, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream, 1,
+                                 false, SegOperand(), sb);
 }
 
 }  // namespace ospo

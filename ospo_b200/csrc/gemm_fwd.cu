@@ -15,17 +15,22 @@ using Cfg2 = GemmCfg<2, 256, false, false>;
 int gemm2_num_n_tiles(int V) { return ((V + 255) / 256) * Cfg2::EPI_SPLIT; }
 
 int launch_gemm1_bias_gelu(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w1, const float* b1,
-                           __nv_bfloat16* pre, __nv_bfloat16* act, int rows, int H, int E) {
+                           __nv_bfloat16* pre, __nv_bfloat16* act, int rows, int H, int E, const XLayout& xl) {
+  SegOperand sa;
+  sa.seg_rows = xl.seg_rows;
+  sa.seg_pitch = xl.seg_pitch;
+  sa.seg_off = xl.seg_off;
+  sa.segments = xl.segments;
   if (pre != nullptr) {
     using Epi = EpiBiasGelu<false, true>;
     Epi::Params p{b1, pre, act, E};
-    if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream);
-    return launch_gemm<Cfg1, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream);
+    if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa);
+    return launch_gemm<Cfg1, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa);
   } else {
     using Epi = EpiBiasGelu<false, false>;
     Epi::Params p{b1, nullptr, act, E};
-    if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream);
-    return launch_gemm<Cfg1, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream);
+    if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa);
+    return launch_gemm<Cfg1, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa);
   }
 }
 

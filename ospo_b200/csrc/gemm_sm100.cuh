@@ -17,6 +17,8 @@
 //              take the left half of the tile's columns and warps 6-9 the right half).
 #pragma once
 
+#include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace ospo {
@@ -26,6 +28,28 @@ struct GemmDims {
   int group_m;       // rasterisation: tiles are walked M-fastest inside groups of `group_m` M-blocks
   int k_splits;      // split-K: each output tile is produced as k_splits partial tiles (1 = off)
   int kb_per_split;  // k-blocks (of BK) per split; every split is non-empty
+  // Row-segmented operand (0 = off): the logical rows of the operand are the rows [seg_off, seg_off + seg_rows)
+  // of every segment of a [segments, pitch, cols] tensor (hidden states [S, L+T, H] -> the T image-token rows of
+  // each sequence).  seg_rows must be a multiple of 64; the tensor map is then 3-D and rows move in 64-row boxes.
+  // a_seg_*: K-major A (rows = M axis);  b_seg_*: MN-major B (rows = K axis).
+  int a_seg_rows, a_seg_off;
+  int b_seg_rows, b_seg_off;
+  // Two-domain rasterisation: B200 is two dies, each with its own half of the L2.  With die_split the first half
+  // of the clusters (which the hardware places on one die) walks the lower half of the M-blocks and the second
+  // half of the clusters the upper half, so operand tiles are shared between CTAs of the SAME die only.
+  int die_split;
+};
+
+// where a row-mapped output row lands: logical row r -> physical row of a [segments, pitch, cols] tensor
+struct RowMap {
+  int seg_rows;   // 0 = identity
+  int seg_pitch;
+  int seg_off;
+  __device__ __forceinline__ int64_t operator()(int r) const {
+    if (seg_rows == 0) return r;
+    const int s = r / seg_rows;
+    return static_cast<int64_t>(s) * seg_pitch + seg_off + (r - s * seg_rows);
+  }
 };
 
 // watchdog site ids
@@ -84,14 +108,14 @@ struct TileCoord {
   int m_blk, n_blk;
 };
 
-__device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
+__device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n, int group_m, int m_base = 0) {
   const int tiles_per_group = group_m * num_n;
   const int g = t / tiles_per_group;
   const int first_m = g * group_m;
   const int gm = min(num_m - first_m, group_m);
   const int local = t - g * tiles_per_group;
   TileCoord c;
-  c.m_blk = first_m + local % gm;
+  c.m_blk = m_base + first_m + local % gm;
   c.n_blk = local / gm;
   return c;
 }
@@ -139,9 +163,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int num_n = (dims.N + BN - 1) / BN;
   const int num_kb = (dims.K + BK - 1) / BK;
   const int ksplits = dims.k_splits;
-  const int num_tiles = num_m * num_n * ksplits;  // work items: (tile, k-split), splits of a tile adjacent
   const int cluster_id = blockIdx.x / CG;
   const int num_clusters = gridDim.x / CG;
+  // work domain of this cluster: (first tile, stride, tile count, M-block window)
+  int dom_first = cluster_id, dom_stride = num_clusters, dom_m0 = 0, dom_nm = num_m;
+  if (dims.die_split && num_clusters >= 2 && (num_clusters % 2) == 0 && num_m >= 2) {
+    const int hc = num_clusters / 2;
+    const int h = cluster_id >= hc ? 1 : 0;
+    dom_first = cluster_id - h * hc;
+    dom_stride = hc;
+    dom_m0 = h ? num_m / 2 : 0;
+    dom_nm = h ? num_m - num_m / 2 : num_m / 2;
+  }
+  const int dom_tiles = dom_nm * num_n * ksplits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -176,7 +210,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t ph = 0;
       auto load_a = [&](uint8_t* sa, int s_, int m0, int k0) {
         if constexpr (!Cfg::A_MN) {
-          if constexpr (CG == 1) tma_load_2d(sa, &tmap_a, &full_bar[s_], k0, m0, kEvictNormal);
+          if (dims.a_seg_rows != 0) {
+            // 64-row boxes, each inside one segment
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) {
+              const int r = m0 + 64 * c;
+              const int sg = r / dims.a_seg_rows;
+              const int rr = dims.a_seg_off + (r - sg * dims.a_seg_rows);
+              if constexpr (CG == 1) tma_load_3d(sa + c * 8192, &tmap_a, &full_bar[s_], k0, rr, sg, kEvictNormal);
+              else tma_load_3d_2sm(sa + c * 8192, &tmap_a, &full_bar[s_], k0, rr, sg, kEvictNormal);
+            }
+          } else if constexpr (CG == 1) tma_load_2d(sa, &tmap_a, &full_bar[s_], k0, m0, kEvictNormal);
           else tma_load_2d_2sm(sa, &tmap_a, &full_bar[s_], k0, m0, kEvictNormal);
         } else {
 #pragma unroll
@@ -191,10 +235,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if constexpr (CG == 1) tma_load_2d(sb, &tmap_b, &full_bar[s_], k0, n0, kEvictNormal);
           else tma_load_2d_2sm(sb, &tmap_b, &full_bar[s_], k0, n0, kEvictNormal);
         } else {
+          const bool seg = dims.b_seg_rows != 0;
+          int sg = 0, rr = k0;
+          if (seg) {
+            sg = k0 / dims.b_seg_rows;
+            rr = dims.b_seg_off + (k0 - sg * dims.b_seg_rows);
+          }
 #pragma unroll
           for (int c = 0; c < Cfg::B_ROWS / 64; ++c) {
-            if constexpr (CG == 1) tma_load_2d(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, kEvictNormal);
-            else tma_load_2d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, kEvictNormal);
+            if (seg) {
+              if constexpr (CG == 1) tma_load_3d(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, rr, sg, kEvictNormal);
+              else tma_load_3d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, rr, sg, kEvictNormal);
+            } else {
+              if constexpr (CG == 1) tma_load_2d(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, kEvictNormal);
+              else tma_load_2d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, kEvictNormal);
+            }
           }
         }
       };
@@ -202,9 +257,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // work item is requested now; their B halves follow after pdl_wait().
       int prefetched = 0;
       if constexpr (Cfg::A_INDEPENDENT) {
-        if (cluster_id < num_tiles) {
-          const int t = cluster_id;
-          const TileCoord tc = tile_coord(t / ksplits, num_m, num_n, dims.group_m);
+        if (dom_first < dom_tiles) {
+          const int t = dom_first;
+          const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
           const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
           const int kb0 = (t % ksplits) * dims.kb_per_split;
           const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
@@ -217,8 +272,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
       pdl_wait();
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const TileCoord tc = tile_coord(t / ksplits, num_m, num_n, dims.group_m);
+      for (int t = dom_first; t < dom_tiles; t += dom_stride) {
+        const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
         const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
         const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         const int kb0 = (t % ksplits) * dims.kb_per_split;
@@ -253,7 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      for (int t = dom_first; t < dom_tiles; t += dom_stride, ++it) {
         const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
         const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tmem_empty_bar[as], aph ^ 1u, SITE_MMA_TMEM_EMPTY);
@@ -300,8 +355,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       leader_tmem_empty_addr[a] = (CG == 2) ? mapa_shared(local, 0) : local;
     }
     int it = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-      const TileCoord tc = tile_coord(t / ksplits, num_m, num_n, dims.group_m);
+    for (int t = dom_first; t < dom_tiles; t += dom_stride, ++it) {
+      const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
       const int ks = t % ksplits;
       const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
       const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
@@ -397,6 +452,39 @@ inline int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, 
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// 3-D bf16 tensor [segments, pitch, cols] (cols contiguous) viewed through {64 cols x 64 rows x 1 segment} boxes
+inline int make_tmap_bf16_seg(CUtensorMap* map, const void* base, uint64_t segments, uint64_t pitch_rows, uint64_t cols,
+                              uint64_t ld) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return -1;
+  cuuint64_t gdim[3] = {cols, pitch_rows, segments};
+  cuuint64_t gstr[2] = {ld * 2, ld * 2 * pitch_rows};
+  cuuint32_t box[3] = {64, 64, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// process-wide switch for the two-domain (per-die) rasterisation; OSPO_HEAD_DIE_SPLIT=0/1
+inline int& g_die_split_ref() {
+  static int v = [] {
+    const char* e = getenv("OSPO_HEAD_DIE_SPLIT");
+    return e ? (atoi(e) != 0 ? 1 : 0) : 0;
+  }();
+  return v;
+}
+inline int g_die_split() { return g_die_split_ref(); }
+
+// describes a row-segmented operand for launch_gemm (seg_rows == 0: plain 2-D operand)
+struct SegOperand {
+  int seg_rows = 0;   // logical rows per segment (multiple of 64)
+  int seg_pitch = 0;  // physical rows per segment
+  int seg_off = 0;    // first logical row inside a segment
+  int segments = 0;
+};
+
 // split-K plan: at most `want` splits, every split non-empty
 inline void gemm_split_plan(int num_kb, int want, int* k_splits, int* kb_per_split) {
   int ks = want < 1 ? 1 : (want > num_kb ? num_kb : want);
@@ -410,14 +498,22 @@ inline void gemm_split_plan(int num_kb, int want, int* k_splits, int* kb_per_spl
 template <class Cfg, class Epi>
 int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K, int group_m,
                 const typename Epi::Params& ep, int num_sms, cudaStream_t stream, int k_splits = 1,
-                bool pdl = false) {
+                bool pdl = false, SegOperand a_seg = SegOperand(), SegOperand b_seg = SegOperand()) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   CUtensorMap ta, tb;
   int rc;
-  if constexpr (!Cfg::A_MN) rc = make_tmap_bf16_2d(&ta, a, M, K, lda, Cfg::BM);
+  if (a_seg.seg_rows != 0) {
+    // K-major A whose M rows are segmented
+    if (Cfg::A_MN || (a_seg.seg_rows % 64) != 0) return -100;
+    rc = make_tmap_bf16_seg(&ta, a, a_seg.segments, a_seg.seg_pitch, K, lda);
+  } else if constexpr (!Cfg::A_MN) rc = make_tmap_bf16_2d(&ta, a, M, K, lda, Cfg::BM);
   else rc = make_tmap_bf16_2d(&ta, a, K, M, lda, Cfg::BK);
   if (rc != 0) return rc;
-  if constexpr (!Cfg::B_MN) rc = make_tmap_bf16_2d(&tb, b, N, K, ldb, Cfg::B_ROWS);
+  if (b_seg.seg_rows != 0) {
+    // MN-major B whose K rows are segmented
+    if (!Cfg::B_MN || (b_seg.seg_rows % 64) != 0) return -100;
+    rc = make_tmap_bf16_seg(&tb, b, b_seg.segments, b_seg.seg_pitch, N, ldb);
+  } else if constexpr (!Cfg::B_MN) rc = make_tmap_bf16_2d(&tb, b, N, K, ldb, Cfg::B_ROWS);
   else rc = make_tmap_bf16_2d(&tb, b, K, N, ldb, Cfg::BK);
   if (rc != 0) return rc;
 
@@ -435,6 +531,11 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   dims.group_m = group_m > 0 ? group_m : 8;
   const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
   gemm_split_plan(num_kb, k_splits, &dims.k_splits, &dims.kb_per_split);
+  dims.a_seg_rows = a_seg.seg_rows;
+  dims.a_seg_off = a_seg.seg_off;
+  dims.b_seg_rows = b_seg.seg_rows;
+  dims.b_seg_off = b_seg.seg_off;
+  dims.die_split = (g_die_split() && k_splits <= 1) ? 1 : 0;
   const int num_m = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
   const int num_n = (N + Cfg::BN - 1) / Cfg::BN;
   const int num_tiles = num_m * num_n * dims.k_splits;

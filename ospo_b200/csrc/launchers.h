@@ -19,6 +19,15 @@ struct LaunchCtx {
 
 struct CfgFusedBuffers;
 
+// Row-segmented hidden states: x / dx are [segments, seg_pitch, H] tensors of which rows [seg_off, seg_off +
+// seg_rows) of every segment are the head's rows (seg_rows == 0: plain contiguous [rows, H]).
+struct XLayout {
+  int seg_rows = 0;
+  int seg_pitch = 0;
+  int seg_off = 0;
+  int segments = 0;
+};
+
 // every TU that contains kernels using mbar_wait owns a copy of the watchdog pointer
 void set_watchdog_fwd(uint32_t* dev_ptr);
 void set_watchdog_bwd(uint32_t* dev_ptr);
@@ -28,7 +37,8 @@ void set_watchdog_debug(uint32_t* dev_ptr);
 // ---- forward (gemm_fwd.cu) ----
 // pre = bf16(x W1^T + b1), act = bf16(gelu(pre));  x [rows,H], w1 [E,H]
 int launch_gemm1_bias_gelu(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w1, const float* b1,
-                           __nv_bfloat16* pre /*nullable*/, __nv_bfloat16* act, int rows, int H, int E);
+                           __nv_bfloat16* pre /*nullable*/, __nv_bfloat16* act, int rows, int H, int E,
+                           const XLayout& xl = XLayout());
 // logits = bf16(act W2^T + b2) (+ LSE partials, target gather);  act [rows,E], w2 [V,E]
 int launch_gemm2_logits_lse(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                             __nv_bfloat16* logits /*nullable*/, const int64_t* labels, float2* part,
@@ -44,10 +54,10 @@ int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* dlogits, const
                          const __nv_bfloat16* pre, __nv_bfloat16* dpre, int rows, int E, int V);
 // dW[out_dim, in_dim] (fp32) = dY^T X;  dY [rows,out_dim], X [rows,in_dim]
 int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw, int rows, int out_dim,
-                 int in_dim);
+                 int in_dim, const XLayout& xl = XLayout());
 // dX[rows, in_dim] (bf16) = dY W;  dY [rows,out_dim], W [out_dim,in_dim]
 int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx, int rows,
-                 int out_dim, int in_dim);
+                 int out_dim, int in_dim, const XLayout& xl = XLayout());
 
 // ---- decode, swap-AB (gemm_decode.cu) ----
 // part[ks][n][E] (fp32) = k-split partials of W1 h^T;  h [n,H] with n = 2P small: W1 is streamed as (128-row tile

@@ -36,8 +36,9 @@ def _rows_from_labels(hidden: torch.Tensor, labels: torch.Tensor, ignore_index: 
                       image_span: Optional[Tuple[int, int]]):
     """Apply the shift of get_batch_logps (train.py:385-387) and keep only the unmasked rows.
 
-    hidden [S, L, H], labels [S, L]  ->  x_rows [N, H] (differentiable view/copy of hidden),
-    targets [N] int64, seq_offsets [S+1] int64 (device).
+    hidden [S, L, H], labels [S, L]  ->  x (either the gathered rows [N, H], a differentiable copy, or -- zero-copy
+    -- ``hidden`` itself plus a (rows per sequence, first row) segment description), targets [N] int64,
+    seq_offsets [S+1] int64 (device), seg.
     ``image_span=(start, stop)`` promises that exactly positions start..stop-1 of the *shifted* sequence are
     unmasked in every sequence (the OSPO layout: L text positions then 576 image tokens); it avoids the
     device->host sync of a data-dependent gather.
@@ -47,18 +48,22 @@ def _rows_from_labels(hidden: torch.Tensor, labels: torch.Tensor, ignore_index: 
     hid = hidden[:, :-1, :]
     if image_span is not None:
         a, b = image_span
-        x_rows = hid[:, a:b, :].reshape(-1, H)
-        targets = lab[:, a:b].reshape(-1)
         n = b - a
+        targets = lab[:, a:b].reshape(-1)
         seq_off = torch.arange(0, (S + 1) * n, n, dtype=torch.int64, device=hidden.device)
-        return x_rows, targets.contiguous(), seq_off
+        if n % 64 == 0 and hidden.dtype == torch.bfloat16 and hidden.is_contiguous() and hidden.is_cuda:
+            # zero-copy: the kernels read (and write dX into) the [S, L, H] tensor through a row-segmented
+            # TMA view -- rows a..b-1 of every sequence (the shift only drops the last position)
+            return hidden, targets.contiguous(), seq_off, (n, a)
+        x_rows = hid[:, a:b, :].reshape(-1, H)
+        return x_rows, targets.contiguous(), seq_off, (0, 0)
     mask = lab != ignore_index
     counts = mask.sum(dim=1)
     seq_off = torch.zeros(S + 1, dtype=torch.int64, device=hidden.device)
     seq_off[1:] = torch.cumsum(counts, 0)
     x_rows = hid[mask]          # [N, H], differentiable gather (one host sync for N)
     targets = lab[mask]
-    return x_rows, targets.contiguous(), seq_off
+    return x_rows, targets.contiguous(), seq_off, (0, 0)
 
 
 class _HeadParams(NamedTuple):
@@ -72,14 +77,14 @@ class _SimpoFn(torch.autograd.Function):
     """loss = SimPO(head(x_rows)); everything else is returned detached."""
 
     @staticmethod
-    def forward(ctx, x_rows, W1, B1, W2, B2, head, targets, seq_off, hp, group):
+    def forward(ctx, x_rows, W1, B1, W2, B2, head, targets, seq_off, hp, group, seg):
         p = head._kernel_params()
         xb = x_rows.detach().to(torch.bfloat16).contiguous()
         need_bwd = any(ctx.needs_input_grad[:5])   # grad mode is off inside forward(); ask autograd instead
         beta, gbr, ls, sftw, lt = hp
         (scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, grad_seq, pre, act, logits) = ops.simpo_fwd_impl(
-            xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, beta, gbr, ls, sftw, lt, need_bwd)
-        ctx.head, ctx.hp, ctx.group = head, hp, group
+            xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, beta, gbr, ls, sftw, lt, need_bwd, seg[0], seg[1])
+        ctx.head, ctx.hp, ctx.group, ctx.seg = head, hp, group, seg
         ctx.x_dtype = x_rows.dtype
         ctx.need_dx = ctx.needs_input_grad[0]
         ctx.need_dw = any(ctx.needs_input_grad[1:5])
@@ -99,7 +104,7 @@ class _SimpoFn(torch.autograd.Function):
         flat = head._flat_grad_buffer() if ctx.need_dw else torch.empty(0, dtype=torch.float32, device=xb.device)
         gs = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         dx = ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, True, ctx.hp[3], scalars, pre, act, logits,
-                               row_lse, grad_seq, gs, ctx.need_dx, flat, True)
+                               row_lse, grad_seq, gs, ctx.need_dx, flat, True, ctx.seg[0], ctx.seg[1])
         gW1 = gB1 = gW2 = gB2 = None
         if ctx.need_dw:
             head._sync_flat_grads(flat, ctx.group)
@@ -109,20 +114,20 @@ class _SimpoFn(torch.autograd.Function):
             gW1, gB1, gW2, gB2 = (dW1.to(d1, copy=True), db1.to(d2, copy=True), dW2.to(d3, copy=True),
                                   db2.to(d4, copy=True))
         gx = dx.to(ctx.x_dtype) if ctx.need_dx else None
-        return gx, gW1, gB1, gW2, gB2, None, None, None, None, None
+        return gx, gW1, gB1, gW2, gB2, None, None, None, None, None, None
 
 
 class _LogpsFn(torch.autograd.Function):
     """seq_logps = get_batch_logps(head(x_rows), targets)  (train.py:357-362), differentiable."""
 
     @staticmethod
-    def forward(ctx, x_rows, W1, B1, W2, B2, head, targets, seq_off, average, group):
+    def forward(ctx, x_rows, W1, B1, W2, B2, head, targets, seq_off, average, group, seg):
         p = head._kernel_params()
         xb = x_rows.detach().to(torch.bfloat16).contiguous()
         need_bwd = any(ctx.needs_input_grad[:5])   # grad mode is off inside forward(); ask autograd instead
         seq_logps, row_logps, row_lse, pre, act, logits = ops.logps_fwd_impl(
-            xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, average, need_bwd)
-        ctx.head, ctx.average, ctx.group = head, average, group
+            xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, average, need_bwd, seg[0], seg[1])
+        ctx.head, ctx.average, ctx.group, ctx.seg = head, average, group, seg
         ctx.x_dtype = x_rows.dtype
         ctx.need_dx = ctx.needs_input_grad[0]
         ctx.need_dw = any(ctx.needs_input_grad[1:5])
@@ -142,7 +147,8 @@ class _LogpsFn(torch.autograd.Function):
         one = torch.ones(1, dtype=torch.float32, device=dev)
         none = torch.empty(0, dtype=torch.float32, device=dev)
         dx = ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, ctx.average, 0.0, none, pre, act, logits, row_lse,
-                               grad_seq.detach().to(torch.float32).contiguous(), one, ctx.need_dx, flat, False)
+                               grad_seq.detach().to(torch.float32).contiguous(), one, ctx.need_dx, flat, False,
+                               ctx.seg[0], ctx.seg[1])
         gW1 = gB1 = gW2 = gB2 = None
         if ctx.need_dw:
             head._sync_flat_grads(flat, ctx.group)
@@ -152,7 +158,7 @@ class _LogpsFn(torch.autograd.Function):
             gW1, gB1, gW2, gB2 = (dW1.to(d1, copy=True), db1.to(d2, copy=True), dW2.to(d3, copy=True),
                                   db2.to(d4, copy=True))
         gx = dx.to(ctx.x_dtype) if ctx.need_dx else None
-        return gx, gW1, gB1, gW2, gB2, None, None, None, None, None
+        return gx, gW1, gB1, gW2, gB2, None, None, None, None, None, None
 
 
 class FusedGenHead(torch.nn.Module):
@@ -238,10 +244,10 @@ class FusedGenHead(torch.nn.Module):
               process_group=None, return_per_token: bool = False):
         """== ``get_batch_logps(gen_head(hidden), labels, average_log_prob)`` (train.py:357-362, 375-396)
         hidden [S, L, H], labels [S, L] (unshifted, ``ignore_index`` on masked positions) -> [S] fp32."""
-        x_rows, targets, seq_off = _rows_from_labels(hidden, labels, ignore_index, image_span)
+        x_rows, targets, seq_off, seg = _rows_from_labels(hidden, labels, ignore_index, image_span)
         seq_logps, row_logps = _LogpsFn.apply(
             x_rows, self.output_mlp_projector.weight, self.output_mlp_projector.bias, self.vision_head.weight,
-            self.vision_head.bias, self, targets, seq_off, bool(average_log_prob), process_group)
+            self.vision_head.bias, self, targets, seq_off, bool(average_log_prob), process_group, seg)
         return (seq_logps, row_logps) if return_per_token else seq_logps
 
     def simpo(self, hidden: torch.Tensor, labels: torch.Tensor, *, beta: float = 1.0, gamma_beta_ratio: float = 0.0,
@@ -253,11 +259,11 @@ class FusedGenHead(torch.nn.Module):
         if loss_type not in ("sigmoid", "hinge"):
             raise ValueError(f"Unknown loss type: {loss_type}. Should be one of ['sigmoid', 'hinge']")  # train.py:336
         lt = _abi.LOSS_SIGMOID if loss_type == "sigmoid" else _abi.LOSS_HINGE
-        x_rows, targets, seq_off = _rows_from_labels(hidden, labels, ignore_index, image_span)
+        x_rows, targets, seq_off, seg = _rows_from_labels(hidden, labels, ignore_index, image_span)
         hp = (float(beta), float(gamma_beta_ratio), float(label_smoothing), float(sft_weight), lt)
         loss, scalars, seq_logps, losses, crew, rrew, row_logps = _SimpoFn.apply(
             x_rows, self.output_mlp_projector.weight, self.output_mlp_projector.bias, self.vision_head.weight,
-            self.vision_head.bias, self, targets, seq_off, hp, process_group)
+            self.vision_head.bias, self, targets, seq_off, hp, process_group, seg)
         B = seq_logps.shape[0] // 2
         metrics = {
             "rewards/chosen": scalars[_abi.SC_REWARD_CHOSEN], "rewards/rejected": scalars[_abi.SC_REWARD_REJECTED],

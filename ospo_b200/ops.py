@@ -75,14 +75,22 @@ def linear_gelu_linear_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: T
 # --------------------------------------------------------------------------------------------------
 # log-probs / SimPO forward.  Returns the tensors the backward needs as explicit outputs.
 # --------------------------------------------------------------------------------------------------
-def _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, hp, outs, saved, bwd, ws) -> _abi.SimpoArgs:
-    rows, H = x.shape
+def _x_dims(x: Tensor, seg_rows: int):
+    """(rows, H) of the head's input: x is [rows, H], or -- row-segmented -- [S, pitch, H] with seg_rows rows used"""
+    if seg_rows:
+        return x.shape[0] * seg_rows, x.shape[2]
+    return x.shape[0], x.shape[1]
+
+
+def _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, hp, outs, saved, bwd, ws, seg=(0, 0, 0)) -> _abi.SimpoArgs:
+    rows, H = _x_dims(x, seg[0])
     E, V = w1.shape[0], w2.shape[0]
     S = seq_off.numel() - 1
     a = _abi.SimpoArgs()
     a.shape = _abi.Shape(rows, H, E, V, S)
     a.w = _weights(w1, b1, w2, b2)
     a.x = x.data_ptr()
+    a.x_seg_rows, a.x_seg_pitch, a.x_seg_off = seg
     a.labels = labels.data_ptr()
     a.seq_offsets = seq_off.data_ptr()
     a.average_log_prob = int(average)
@@ -95,18 +103,23 @@ def _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, hp, outs, saved, bw
     return a
 
 
-def _check_rows(x: Tensor, labels: Tensor, seq_off: Tensor) -> None:
+def _check_rows(x: Tensor, labels: Tensor, seq_off: Tensor, seg_rows: int = 0) -> None:
     _check_cuda(x, labels, seq_off)
-    assert x.dim() == 2 and x.dtype == torch.bfloat16 and x.is_contiguous(), "x must be contiguous bf16 [rows, H]"
-    assert labels.dtype == torch.int64 and labels.shape == (x.shape[0],) and labels.is_contiguous()
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(), "x must be contiguous bf16"
+    assert x.dim() == (3 if seg_rows else 2), "x is [rows, H], or [S, pitch, H] when row-segmented"
+    rows, _ = _x_dims(x, seg_rows)
+    assert labels.dtype == torch.int64 and labels.shape == (rows,) and labels.is_contiguous()
     assert seq_off.dtype == torch.int64 and seq_off.dim() == 1 and seq_off.is_contiguous()
 
 
 def logps_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
-              average: bool, save_for_backward: bool) -> List[Tensor]:
-    """-> [seq_logps[S], row_logps[rows], row_lse[rows], pre, act, logits]  (train.py:357 + 375-396)"""
-    _check_rows(x, labels, seq_off)
-    rows, H = x.shape
+              average: bool, save_for_backward: bool, seg_rows: int = 0, seg_off: int = 0) -> List[Tensor]:
+    """-> [seq_logps[S], row_logps[rows], row_lse[rows], pre, act, logits]  (train.py:357 + 375-396)
+    seg_rows > 0: x is the [S, pitch, H] hidden-state tensor and rows [seg_off, seg_off + seg_rows) of every
+    sequence are the head's rows (no gather copy)."""
+    _check_rows(x, labels, seq_off, seg_rows)
+    rows, H = _x_dims(x, seg_rows)
+    seg = (seg_rows, x.shape[1], seg_off) if seg_rows else (0, 0, 0)
     E, V = w1.shape[0], w2.shape[0]
     S = seq_off.numel() - 1
     dev = x.device
@@ -121,7 +134,7 @@ def logps_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
     ws = _workspace(rows, H, E, V, S, dev)
     a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, (1.0, 0.0, 0.0, 0.0, 0),
                     (row_logps, seq_logps, None, None, None, None), (pre, act, logits, row_lse, None),
-                    (None, None, None), ws)
+                    (None, None, None), ws, seg)
     _abi.check(_abi.load().ospo_head_logps_fwd(C.byref(a), _stream()), "ospo_head_logps_fwd")
     def empty():
         return torch.empty(0, dtype=torch.bfloat16, device=dev)
@@ -132,11 +145,12 @@ def logps_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
 
 def simpo_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
               beta: float, gamma_beta_ratio: float, label_smoothing: float, sft_weight: float, loss_type: int,
-              save_for_backward: bool) -> List[Tensor]:
+              save_for_backward: bool, seg_rows: int = 0, seg_off: int = 0) -> List[Tensor]:
     """-> [scalars[16], seq_logps[S], losses[B], chosen_rewards[B], rejected_rewards[B], row_logps[rows],
            row_lse[rows], grad_seq[S], pre, act, logits]      (train.py:345-372, 317-342, 399-445)"""
-    _check_rows(x, labels, seq_off)
-    rows, H = x.shape
+    _check_rows(x, labels, seq_off, seg_rows)
+    rows, H = _x_dims(x, seg_rows)
+    seg = (seg_rows, x.shape[1], seg_off) if seg_rows else (0, 0, 0)
     E, V = w1.shape[0], w2.shape[0]
     S = seq_off.numel() - 1
     assert S % 2 == 0, "SimPO needs chosen and rejected halves"
@@ -157,7 +171,7 @@ def simpo_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
     a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, True,
                     (beta, gamma_beta_ratio, label_smoothing, sft_weight, loss_type),
                     (row_logps, seq_logps, losses, crew, rrew, scalars), (pre, act, logits, row_lse, grad_seq),
-                    (None, None, None), ws)
+                    (None, None, None), ws, seg)
     _abi.check(_abi.load().ospo_head_simpo_fwd(C.byref(a), _stream()), "ospo_head_simpo_fwd")
     def empty():
         return torch.empty(0, dtype=torch.bfloat16, device=dev)
@@ -169,16 +183,23 @@ def simpo_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
 def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
              average: bool, sft_weight: float, scalars: Tensor, pre: Tensor, act: Tensor, logits: Tensor,
              row_lse: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool, flat_grads: Tensor,
-             simpo: bool) -> Tensor:
+             simpo: bool, seg_rows: int = 0, seg_off: int = 0) -> Tensor:
     """softmax-minus-onehot producer + the dgrad / wgrad GEMM pairs.
     `logits` is overwritten with dlogits; `flat_grads` (numel 0 = head frozen) receives dW2|dW1|db2|db1.
-    Returns dx [rows, H] bf16 (numel 0 if not requested)."""
-    _check_rows(x, labels, seq_off)
-    rows, H = x.shape
+    Returns dx bf16 with the shape of x (numel 0 if not requested); with a row-segmented x the rows outside the
+    span are zero (train.py: masked positions carry no gradient)."""
+    _check_rows(x, labels, seq_off, seg_rows)
+    rows, H = _x_dims(x, seg_rows)
     E, V = w1.shape[0], w2.shape[0]
     S = seq_off.numel() - 1
     dev = x.device
-    dx = torch.empty(rows, H, dtype=torch.bfloat16, device=dev) if need_dx else None
+    seg = (seg_rows, x.shape[1], seg_off) if seg_rows else (0, 0, 0)
+    dx = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        if seg_rows:
+            dx[:, :seg_off].zero_()
+            dx[:, seg_off + seg_rows:].zero_()
     fg = flat_grads if flat_grads.numel() else None
     if fg is not None:
         assert fg.dtype == torch.float32 and fg.numel() == flat_grad_numel(H, E, V) and fg.is_contiguous()
@@ -187,7 +208,7 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
     ws = _workspace(rows, H, E, V, S, dev)
     a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, (1.0, 0.0, 0.0, sft_weight, 0),
                     (None, None, None, None, None, scalars if scalars.numel() else None),
-                    (pre, act, logits, row_lse, grad_seq), (grad_scale, dx, fg), ws)
+                    (pre, act, logits, row_lse, grad_seq), (grad_scale, dx, fg), ws, seg)
     lib = _abi.load()
     if simpo:
         _abi.check(lib.ospo_head_simpo_bwd(C.byref(a), _stream()), "ospo_head_simpo_bwd")

@@ -82,7 +82,8 @@ def test_row_selection_matches_get_batch_logps_mask(use_span):
     hidden = torch.randn(S, Lt + T, H, generator=g)
     labels = torch.cat([torch.full((S, Lt), -100), torch.randint(0, V, (S, T), generator=g)], 1)
     span = (Lt - 1, Lt - 1 + T) if use_span else None
-    x_rows, targets, seq_off = _rows_from_labels(hidden, labels, -100, span)
+    x_rows, targets, seq_off, seg = _rows_from_labels(hidden, labels, -100, span)
+    assert seg == (0, 0)   # CPU / fp32 / T % 64 != 0: the gather path
     lab = labels[:, 1:]
     mask = lab != -100
     assert torch.equal(x_rows, hidden[:, :-1][mask])

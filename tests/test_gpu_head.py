@@ -226,6 +226,31 @@ def test_logps_autograd_path_and_ragged_sequences():
         assert _rel_fro(fh.output_mlp_projector.bias.grad.float(), head_b.output_mlp_projector.bias.grad.float()) < 2e-2
 
 
+def test_row_segmented_zero_copy_path_equals_gather_path():
+    """T % 64 == 0 + bf16 contiguous hidden states: the kernels read [S, L+T, H] in place through a 3-D TMA view and
+    write dX into it; results must equal the gathered-rows path bit for bit, masked rows must get zero gradient."""
+    dev = _cuda()
+    H, E, V, B, T, L = 256, 192, 2048, 3, 128, 5
+    head_b = O.make_head(H, E, V, seed=41, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=42, dtype=torch.bfloat16)
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, loss_type="sigmoid", sft_weight=0.3)
+    labels = torch.cat([lc, lr]).to(dev)
+    res = []
+    for span in ((L - 1, L - 1 + T), None):
+        fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+        hidden = torch.cat([hc, hr]).to(dev).requires_grad_(True)
+        out = fh.simpo(hidden, labels, image_span=span, **hp)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        res.append((out.loss.detach(), out.chosen_logps, out.per_token_logps, hidden.grad, fh.vision_head.weight.grad,
+                    fh.output_mlp_projector.weight.grad, fh.output_mlp_projector.bias.grad))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    g = res[0][3]
+    assert float(g[:, :L - 1].abs().max()) == 0.0 and float(g[:, L - 1 + T:].abs().max()) == 0.0
+    assert float(g[:, L - 1:L - 1 + T].abs().sum()) > 0
+
+
 def test_frozen_head_only_dx():
     """configs/step5.yaml:64 freezes gen_head: only dX is produced, parameters get no .grad"""
     dev = _cuda()

@@ -263,10 +263,20 @@ def main():
     dominant = max(gemm_names, key=lambda k: kernels[k]["ms_per_launch"]) if gemm_names else None
     step_tflops = tokens_per_step_rank * flops_per_token(H7B, E7B, V) / (ms_step / 1e3) / 1e12
     roofline = None
+    traffic, tensor_pct = None, None
+    tf = ROOT / "profiles" / "r01_kernel_traffic.json"
+    if dominant and tf.exists():
+        ent = json.loads(tf.read_text()).get(dominant)
+        if ent:
+            traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
+            tensor_pct = ent.get("tensor_pipe_active_pct")
     if dominant:
         roofline = {
             "bound": "tensor", "kernel": dominant, "achieved": kernels[dominant]["tflops"], "peak": peaks["tf_burst"],
-            "unit": "TFLOP/s", "frac": kernels[dominant]["tflops"] / peaks["tf_burst"], "traffic": None,
+            "unit": "TFLOP/s", "frac": kernels[dominant]["tflops"] / peaks["tf_burst"], "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one ncu --set full capture "
+                              "(profiles/r01_kernel_traffic.json)" if traffic else None,
+            "ncu_tensor_pipe_active_pct": tensor_pct,
             "peak_source": peaks["source"] + " bf16_tflops (burst); sustained " + str(peaks["tf_sustained"]),
             "step_achieved_tflops": step_tflops, "step_frac": step_tflops / peaks["tf_burst"],
             "note": "achieved = algorithmic flops of that launch / CUDA-event time around it, measured in the timed "

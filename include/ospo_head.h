@@ -204,6 +204,10 @@ OSPO_API int ospo_head_set_group_m(int group_m);
 #define OSPO_K_COUNT 13
 OSPO_API int ospo_head_profile_enable(int enable);
 OSPO_API int ospo_head_profile_read(float* total_ms, int32_t* counts, int32_t n);
+/* tuning aid: CTA timeline of the decode chain.  device_buf = u64[5][160][8] (kernel: 1 GEMM1, 2 GEMM2, 3 finalize,
+   4 finish; per CTA: 0 entry, 1 weights prefetched, 2 dependency wait over, 3 producer done, 4 first accumulator
+   ready, 5 epilogue done), NULL = off */
+OSPO_API int ospo_head_trace(void* device_buf);
 /* number of kernels launched by this library since load (the bench's gpu_launches counter) */
 OSPO_API uint64_t ospo_head_launch_count(void);
 /* 6 x u32 watchdog record written by a kernel whose mbarrier wait expired (host pointer, may be NULL) */

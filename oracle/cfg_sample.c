@@ -15,7 +15,7 @@
  *       kernel, so sampling is defined as inverse-CDF on caller-supplied uniforms:
  *           id = min{ k : cdf_k > u * Z },  weights w_v = e^(t_v) / 2^K  (K = max_v rint(t_v log2 e)), Z = sum w,
  *       with a fully specified fp32 exp and a fixed summation order (tiles of 128 codes, segments of 32
- *       codes summed as a pairwise tree, 16 groups x 32 segments and the 16 groups summed sequentially).
+ *       codes summed as a stride-16/8/4/2/1 butterfly tree, 16 groups x 32 segments and the 16 groups summed sequentially).
  * The probabilities w/Z are checked against the real reference's `probs` in tests (golden
  * tests/golden/cfg_ref.npz); the CUDA kernel is checked against this file bit for bit.
  *
@@ -112,7 +112,7 @@ void ospo_oracle_cfg_merge(const uint16_t* logits, int P, int V, float w, float 
  * weights_out (optional) [P, V] weights relative to the global exponent K; z_out (optional) [P].
  * Order of operations (mirrored exactly by the CUDA kernels):
  *   tile (128 codes):  K_tile = max n;  u_v = P(r_v) * 2^(n_v - K_tile)
- *   segment (32 codes): S = pairwise-adjacent tree sum of u  (((u0+u1)+(u2+u3))+...)
+ *   segment (32 codes): S = butterfly tree sum of u: x[j] += x[j+16] (j<16), then strides 8, 4, 2, 1
  *   K = max K_tile;  S' = S * 2^(K_tile - K)
  *   group (32 segments): sequential sum of S';  Z = sequential sum of the 16 group sums
  *   descent group -> segment -> code, `base` carried along; in-segment weights are u * 2^(K_tile - K) */
@@ -146,8 +146,8 @@ int ospo_oracle_sample_merged(const float* merged, int P, int V, const float* un
     for (int s = 0; s < nseg; ++s) {
       float x[SEG];
       for (int j = 0; j < SEG; ++j) x[j] = ubuf[s * SEG + j];
-      for (int w = SEG; w > 1; w >>= 1)
-        for (int j = 0; j < w / 2; ++j) x[j] = x[2 * j] + x[2 * j + 1];
+      for (int h = SEG / 2; h >= 1; h >>= 1) /* butterfly order: strides 16, 8, 4, 2, 1 */
+        for (int j = 0; j < h; ++j) x[j] = x[j] + x[j + h];
       seg_sum[s] = x[0] * pow2_factor(tile_k[s / (TILE / SEG)] - K);
     }
     for (int g = 0; g < ngrp; ++g) {

@@ -125,6 +125,7 @@ EXPORTS = (
     "ospo_head_set_group_m",
     "ospo_head_profile_enable",
     "ospo_head_profile_read",
+    "ospo_head_trace",
     "ospo_head_launch_count",
     "ospo_head_watchdog_record_host",
     "ospo_head_gemm_debug",
@@ -179,6 +180,8 @@ def load() -> C.CDLL:
     lib.ospo_head_profile_enable.restype = C.c_int
     lib.ospo_head_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]
     lib.ospo_head_profile_read.restype = C.c_int
+    lib.ospo_head_trace.argtypes = [C.c_void_p]
+    lib.ospo_head_trace.restype = C.c_int
     lib.ospo_head_launch_count.argtypes = []
     lib.ospo_head_launch_count.restype = C.c_uint64
     lib.ospo_head_watchdog_record_host.argtypes = []

@@ -601,6 +601,14 @@ int ospo_head_profile_read(float* total_ms, int32_t* counts, int32_t n) {
   return rc;
 }
 
+int ospo_head_trace(void* device_buf) {
+  // tuning aid: [5][160][8] u64 globaltimer stamps of the decode chain's CTAs (NULL switches it off)
+  runtime_init();
+  unsigned long long* p = static_cast<unsigned long long*>(device_buf);
+  set_trace_decode(p);
+  return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)) == cudaSuccess ? OSPO_OK : OSPO_ERR_CUDA;
+}
+
 uint64_t ospo_head_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const uint32_t* ospo_head_watchdog_record_host(void) { return g_rt.wd_host; }

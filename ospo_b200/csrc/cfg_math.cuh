@@ -70,18 +70,60 @@ __device__ __forceinline__ void cfg_merge2(uint32_t wc, uint32_t wu, float w, fl
                              __uint_as_float(wu & 0xFFFF0000u), w, T, t0, t1);
 }
 
-// pairwise-adjacent tree sum of 32 registers (the order a shfl_xor butterfly 1,2,4,8,16 produces)
+// butterfly tree sum of 32 registers: x[j] += x[j + 16] (j < 16), then strides 8, 4, 2, 1 -- the order in which a
+// warp combines lanes with shfl_xor 16, 8, 4, 2, 1 (IEEE addition is commutative, so which lane adds is irrelevant)
 __device__ __forceinline__ float tree_sum32(const float (&x)[32]) {
   float a[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) a[j] = __fadd_rn(x[2 * j], x[2 * j + 1]);
+  for (int j = 0; j < 16; ++j) a[j] = __fadd_rn(x[j], x[j + 16]);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+  for (int j = 0; j < 8; ++j) a[j] = __fadd_rn(a[j], a[j + 8]);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+  for (int j = 0; j < 4; ++j) a[j] = __fadd_rn(a[j], a[j + 4]);
 #pragma unroll
-  for (int j = 0; j < 2; ++j) a[j] = __fadd_rn(a[2 * j], a[2 * j + 1]);
+  for (int j = 0; j < 2; ++j) a[j] = __fadd_rn(a[j], a[j + 2]);
   return __fadd_rn(a[0], a[1]);
+}
+
+// Transpose-reduce: every lane holds 16 values (one per CFG pair); reduce each of the 16 across the 32 lanes with
+// 16 shuffles instead of 80.  Lanes exchange half of their values at every step (strides 16, 8, 4, 2) and combine
+// the last pair with stride 1.  On return lane l holds the full reduction of pair  k = (l >> 1) & 15  in the bit
+// order  k = b4*8 + b3*4 + b2*2 + b1  (b_i = bit i of l); lanes l and l^1 hold the same pair.
+struct OpSum {
+  __device__ __forceinline__ float operator()(float a, float b) const { return __fadd_rn(a, b); }
+};
+struct OpMax {
+  __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); }
+};
+template <class Op>
+__device__ __forceinline__ float warp_transpose_reduce16(const float (&x)[16], int lane, Op op) {
+  float y[8], z[4], w[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float send = b4 ? x[j] : x[j + 8];
+    const float keep = b4 ? x[j + 8] : x[j];
+    y[j] = op(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = b3 ? y[j] : y[j + 4];
+    const float keep = b3 ? y[j + 4] : y[j];
+    z[j] = op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = b2 ? z[j] : z[j + 2];
+    const float keep = b2 ? z[j + 2] : z[j];
+    w[j] = op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+  const float send = b1 ? w[0] : w[1];
+  const float keep = b1 ? w[1] : w[0];
+  const float v = op(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+  return op(v, __shfl_xor_sync(0xffffffffu, v, 1));
+}
+__device__ __forceinline__ int transpose_reduce_pair_of_lane(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
 struct CfgFusedBuffers {

@@ -496,13 +496,14 @@ struct EpiCfgFused {
       named_bar_sync(1, 128);
       return;
     }
-    // tile exponent per pair
+    // tile exponent per pair: 16-way transpose-reduce (max is exact, any order)
+    const int mypair = transpose_reduce_pair_of_lane(lane);
+    {
+      float nn[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      float kt = exp_n_only(t[k]);
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, off));
-      if (lane == k) sm_k[q * 16 + k] = kt;
+      for (int k = 0; k < 16; ++k) nn[k] = exp_n_only(t[k]);
+      const float kw = warp_transpose_reduce16(nn, lane, OpMax());
+      if ((lane & 1) == 0) sm_k[q * 16 + mypair] = kw;
     }
     named_bar_sync(1, 128);
     float u[16];
@@ -513,16 +514,15 @@ struct EpiCfgFused {
       const float pr = exp_parts(t[k], n);
       u[k] = __fmul_rn(pr, pow2_factor(__fsub_rn(n, kt)));
       if (k < npairs) p.buf.wbuf[static_cast<int64_t>(pair0 + k) * p.vocab + row] = u[k];
-      if (q == 0 && lane == k && k < npairs) p.buf.tile_k[static_cast<int64_t>(pair0 + k) * ntile + tile] = kt;
     }
-    // segment sums: butterfly over the warp's 32 codes == pairwise-adjacent tree
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      float x = u[k];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, off));
-      if (lane == k && k < npairs)
-        p.buf.seg_sum[static_cast<int64_t>(pair0 + k) * (p.vocab / SAMPLE_SEG) + row / SAMPLE_SEG] = x;
+    // segment sums: the warp is one 32-code segment; the transpose-reduce adds lanes in the oracle's butterfly
+    // order (strides 16, 8, 4, 2, 1)
+    const float ssum = warp_transpose_reduce16(u, lane, OpSum());
+    if ((lane & 1) == 0 && mypair < npairs) {
+      p.buf.seg_sum[static_cast<int64_t>(pair0 + mypair) * (p.vocab / SAMPLE_SEG) + row / SAMPLE_SEG] = ssum;
+      if (q == 0)
+        p.buf.tile_k[static_cast<int64_t>(pair0 + mypair) * ntile + tile] =
+            fmaxf(fmaxf(sm_k[mypair], sm_k[16 + mypair]), fmaxf(sm_k[32 + mypair], sm_k[48 + mypair]));
     }
     named_bar_sync(1, 128);  // smem is reused by the next tile of a persistent CTA
   }

@@ -8,6 +8,7 @@
 namespace ospo {
 
 void set_watchdog_decode(uint32_t* dev_ptr) { cudaMemcpyToSymbol(g_watchdog_buf, &dev_ptr, sizeof(dev_ptr)); }
+void set_trace_decode(unsigned long long* dev_ptr) { cudaMemcpyToSymbol(g_trace_buf, &dev_ptr, sizeof(dev_ptr)); }
 
 // decode chain: 4-stage ring (~82 KB), <= 128 registers, weights (A) prefetched before the dependency wait
 using CfgS32 = GemmCfg<1, 32, false, false, 0, 5, 2, true>;
@@ -29,7 +30,9 @@ int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_b
   Epi::Params p{part, E, split_stride};
   const int ks = decode_gemm1_splits(c.num_sms, H, E);
   // D[E, n] = W1[E, H] * h[n, H]^T, as k-split partials part[ks][n][E]
-  if (n <= 32) return launch_gemm<CfgS32, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl);
+  if (n <= 32)
+    return launch_gemm<CfgS32, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl, SegOperand(),
+                                    SegOperand(), 1);
   return launch_gemm<CfgS128, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl);
 }
 
@@ -51,7 +54,8 @@ static int run_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bf
   using Epi = EpiCfgFused<MODE, TDIV>;
   typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, V, buf, greedy, V};
   // D[V, n] = W2[V, E] * act[n, E]^T; the epilogue consumes the tile in place
-  return launch_gemm<CfgF32, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream, 1, c.pdl);
+  return launch_gemm<CfgF32, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream, 1, c.pdl, SegOperand(),
+                                  SegOperand(), 2);
 }
 
 int launch_decode_gemm2_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,

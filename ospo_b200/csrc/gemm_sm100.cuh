@@ -38,6 +38,7 @@ struct GemmDims {
   // of the clusters (which the hardware places on one die) walks the lower half of the M-blocks and the second
   // half of the clusters the upper half, so operand tiles are shared between CTAs of the SAME die only.
   int die_split;
+  int trace_id;  // > 0: CTA timeline stamps into g_trace_buf (tuning aid)
 };
 
 // where a row-mapped output row lands: logical row r -> physical row of a [segments, pitch, cols] tensor
@@ -143,6 +144,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
 
   pdl_launch_dependents();  // our successor may start its own prologue (and weight prefetch) right away
+  if (threadIdx.x == 0) trace_stamp(dims.trace_id, 0);
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte alignment (in the shared address space)
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -271,7 +273,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       }
+      trace_stamp(dims.trace_id, 1);
       pdl_wait();
+      trace_stamp(dims.trace_id, 2);
       for (int t = dom_first; t < dom_tiles; t += dom_stride) {
         const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
         const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
@@ -295,6 +299,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
+      trace_stamp(dims.trace_id, 3);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -364,6 +369,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int n0 = tc.n_blk * BN;
       mbar_wait(&tmem_full_bar[as], aph, SITE_EPI_TMEM_FULL);
       tc_fence_after();
+      if (warp == 2 && lane == 0) trace_stamp(dims.trace_id, 4);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
       typename Epi::State st;
       Epi::begin(ep, st, row, n0, ks, dims, epi_smem);
@@ -404,6 +410,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         else mbar_arrive_cluster(leader_tmem_empty_addr[as]);
       }
       Epi::end(ep, st, row, n0, tc.n_blk * Cfg::EPI_SPLIT + half, dims, epi_smem);
+      if (warp == 2 && lane == 0) trace_stamp(dims.trace_id, 5);
     }
   }
 
@@ -498,7 +505,7 @@ inline void gemm_split_plan(int num_kb, int want, int* k_splits, int* kb_per_spl
 template <class Cfg, class Epi>
 int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K, int group_m,
                 const typename Epi::Params& ep, int num_sms, cudaStream_t stream, int k_splits = 1,
-                bool pdl = false, SegOperand a_seg = SegOperand(), SegOperand b_seg = SegOperand()) {
+                bool pdl = false, SegOperand a_seg = SegOperand(), SegOperand b_seg = SegOperand(), int trace_id = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   CUtensorMap ta, tb;
   int rc;
@@ -536,6 +543,7 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   dims.b_seg_rows = b_seg.seg_rows;
   dims.b_seg_off = b_seg.seg_off;
   dims.die_split = (g_die_split() && k_splits <= 1) ? 1 : 0;
+  dims.trace_id = trace_id;
   const int num_m = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
   const int num_n = (N + Cfg::BN - 1) / Cfg::BN;
   const int num_tiles = num_m * num_n * dims.k_splits;

@@ -33,6 +33,7 @@ void set_watchdog_fwd(uint32_t* dev_ptr);
 void set_watchdog_bwd(uint32_t* dev_ptr);
 void set_watchdog_decode(uint32_t* dev_ptr);
 void set_watchdog_debug(uint32_t* dev_ptr);
+void set_trace_decode(unsigned long long* dev_ptr);
 
 // ---- forward (gemm_fwd.cu) ----
 // pre = bf16(x W1^T + b1), act = bf16(gelu(pre));  x [rows,H], w1 [E,H]

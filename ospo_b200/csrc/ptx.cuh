@@ -39,6 +39,14 @@ static __device__ __noinline__ void watchdog_fire(uint32_t site, uint32_t a, uin
   __trap();
 }
 
+// Optional timeline trace (tuning aid): [trace_id][cta][8] globaltimer stamps; null = off.
+static __device__ unsigned long long* g_trace_buf = nullptr;
+constexpr int kTraceCtas = 160, kTraceSlots = 8;
+__device__ __forceinline__ void trace_stamp(int trace_id, int slot) {
+  if (trace_id > 0 && g_trace_buf != nullptr && blockIdx.x < kTraceCtas)
+    g_trace_buf[(static_cast<size_t>(trace_id) * kTraceCtas + blockIdx.x) * kTraceSlots + slot] = globaltimer_ns();
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -1,0 +1,65 @@
+"""Timeline of the decode chain inside a CUDA graph (uses ospo_head_trace)."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from ospo_b200 import FusedGenHead, _abi, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+H = E = 4096
+V, P, steps = 16384, 16, 8
+
+
+class Pm:
+    n_embed, image_token_embed, image_token_size = H, E, V
+
+
+torch.manual_seed(0)
+head = FusedGenHead(Pm).to(dev).to(torch.bfloat16)
+p = head._kernel_params()
+alt = type(p)(p.w1.clone(), p.b1.clone(), p.w2.clone(), p.b2.clone())
+h = torch.randn(steps, 2 * P, H, device=dev).to(torch.bfloat16)
+u = torch.rand(steps, P, device=dev)
+ids_out = torch.empty(steps, P, dtype=torch.int64, device=dev)
+trace = torch.zeros(5, 160, 8, dtype=torch.int64, device=dev)
+lib = _abi.load()
+
+
+def run():
+    for i in range(steps):
+        w = p if (i & 1) == 0 else alt
+        ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
+        ids_out[i].copy_(ids)
+
+
+s = torch.cuda.Stream()
+s.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s):
+    run()
+torch.cuda.current_stream().wait_stream(s)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    run()
+g.replay()
+torch.cuda.synchronize()
+lib.ospo_head_trace(trace.data_ptr())
+g.replay()
+torch.cuda.synchronize()
+lib.ospo_head_trace(None)
+t = trace.cpu().numpy().astype("float64")
+names = {1: "gemm1", 3: "finalize", 2: "gemm2", 4: "finish"}
+t0 = t[1][:, 0][t[1][:, 0] > 0].min()
+for k in (1, 3, 2, 4):
+    a = t[k]
+    act = a[:, 0] > 0
+    line = f"TRACE {names[k]:9s} ctas={int(act.sum()):3d}"
+    for slot, nm in ((0, "entry"), (1, "prefetched"), (2, "wait_over"), (3, "prod_done"), (4, "acc_ready"), (5, "epi_done")):
+        v = a[act, slot]
+        v = v[v > 0]
+        if v.size:
+            line += f" | {nm} {((v.min() - t0) / 1e3):6.1f}..{((v.max() - t0) / 1e3):6.1f}"
+    print(line)
+print("(us relative to the first GEMM1 CTA entry of the last traced step)")

@@ -45,7 +45,9 @@ int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv
   return launch_gemm<CfgS128, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream);
 }
 
-using CfgF32 = GemmCfg<1, 32, false, false, 1024, 5, 2, true>;
+// GEMM2: the deepest ring that fits (10 x 20 KB): while it waits for the activations its producer has 20 MB of W2
+// in flight across the chip, which fills most of the GEMM1 -> GEMM2 dependency bubble
+using CfgF32 = GemmCfg<1, 32, false, false, 1024, 10, 1, true>;
 
 template <int MODE, bool TDIV>
 static int run_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,

@@ -86,6 +86,7 @@ struct GemmCfg {
   static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - EPI_SMEM_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > MAX_STAGES_ ? MAX_STAGES_ : STAGES_RAW;
+  static_assert(STAGES <= 12, "barrier area holds at most 12 stages");
   static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = ACC_STAGES * BN;
   static constexpr int TMEM_COLS =

@@ -23,6 +23,7 @@ struct Runtime {
   int group_m = 16;
   int decode_fused = 1;  // CFG tail fused into the decode GEMM2 epilogue (0 = separate sampler pass)
   int decode_pdl = 1;    // programmatic dependent launch along the decode kernel chain
+  int decode_cluster = 1;  // GEMM1 k-splits combined in-cluster through DSMEM (0 = HBM partials + finalize kernel)
   uint32_t* wd_host = nullptr;
   uint32_t* wd_dev = nullptr;
 };
@@ -84,6 +85,7 @@ int runtime_init() {
   }
   if (const char* e = getenv("OSPO_HEAD_DECODE_FUSED")) g_rt.decode_fused = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_PDL")) g_rt.decode_pdl = atoi(e) != 0;
+  if (const char* e = getenv("OSPO_HEAD_DECODE_CLUSTER")) g_rt.decode_cluster = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
     const int v = atoi(e);
     if (v > 0) g_rt.group_m = v;
@@ -486,17 +488,27 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
     // W1 slabs over all SMs (split-K partials), then bias + GELU on the summed partials
     KernelSpan ks(st, OSPO_K_DECODE_GEMM1);
     const int64_t split_stride = static_cast<int64_t>(s.rows) * s.embed;
-    rc = map_rc(launch_decode_gemm1(c, static_cast<const __nv_bfloat16*>(a->h),
-                                    static_cast<const __nv_bfloat16*>(a->w.w1), w.decode_part, split_stride, s.rows,
-                                    s.hidden, s.embed));
-    if (rc) return rc;
-    const int64_t n_el = static_cast<int64_t>(s.rows) * s.embed;
-    const float* part = w.decode_part;
-    if (launch_plain(decode_act_finalize_kernel, dim3(static_cast<unsigned>((n_el / 4 + 127) / 128)), dim3(128), st,
-                     c.pdl, part, decode_gemm1_splits(c.num_sms, s.hidden, s.embed), split_stride, a->w.b1,
-                     w.rows_by_e, s.rows, s.embed) != cudaSuccess)
-      return OSPO_ERR_LAUNCH;
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    int lrc = g_rt.decode_cluster
+                  ? launch_decode_gemm1_cluster(c, static_cast<const __nv_bfloat16*>(a->h),
+                                                static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1, w.rows_by_e,
+                                                s.rows, s.hidden, s.embed)
+                  : -100;
+    if (lrc == -100) {
+      // partial + finalize path (any shape)
+      rc = map_rc(launch_decode_gemm1(c, static_cast<const __nv_bfloat16*>(a->h),
+                                      static_cast<const __nv_bfloat16*>(a->w.w1), w.decode_part, split_stride, s.rows,
+                                      s.hidden, s.embed));
+      if (rc) return rc;
+      const int64_t n_el = static_cast<int64_t>(s.rows) * s.embed;
+      const float* part = w.decode_part;
+      if (launch_plain(decode_act_finalize_kernel, dim3(static_cast<unsigned>((n_el / 4 + 127) / 128)), dim3(128), st,
+                       c.pdl, part, decode_gemm1_splits(c.num_sms, s.hidden, s.embed), split_stride, a->w.b1,
+                       w.rows_by_e, s.rows, s.embed) != cudaSuccess)
+        return OSPO_ERR_LAUNCH;
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if ((rc = map_rc(lrc))) {
+      return rc;
+    }
   }
   const int pairs = s.rows / 2;
   if (g_rt.decode_fused && !a->merged) {

@@ -203,6 +203,85 @@ struct EpiPartialStoreT {
 };
 
 // ---------------------------------------------------------------------------
+// Decode GEMM1 with cluster split-K: the partial tile goes to this CTA's shared memory as part[col][row]; CTA 0 of
+// the cluster then sums the k_splits partials in split order through distributed shared memory, adds b1, applies
+// GELU and writes act[n][e] (bf16).  Deterministic, no HBM partials, no finalize launch.
+// ---------------------------------------------------------------------------
+struct EpiClusterGeluT {
+  struct Params {
+    const float* bias;     // b1 [E]
+    __nv_bfloat16* act;    // [n, E]
+    int64_t ld;            // E
+  };
+  struct State {};
+  static constexpr int SMEM_BYTES = 0;  // uses the drained operand ring: 32 x 128 fp32 = 16 KB
+  __device__ static void begin(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
+  template <bool FULL>
+  __device__ static void chunk(const Params&, State&, int, int col0, float (&v)[32], const GemmDims&, uint8_t* smem) {
+    float* part = reinterpret_cast<float*>(smem);
+    const int r = ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31);  // row inside the 128-row tile
+    const int c0 = col0 & 31;  // BN == 32: one chunk per tile
+#pragma unroll
+    for (int j = 0; j < 32; ++j) part[(c0 + j) * 128 + r] = v[j];
+  }
+  __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
+  // Every CTA of the cluster reduces its own slice of the 32 columns (columns [rank*8, rank*8+8) for 4 splits), so the
+  // distributed-shared-memory traffic is spread over all the SMs of the cluster and all remote loads of a thread are
+  // in flight together.  The partials are always added in split order 0, 1, 2, ... (deterministic).
+  __device__ static void cluster_finalize(const Params& p, int row, int n0, int k_splits, int rank, const GemmDims& d,
+                                          uint8_t* smem) {
+    if (row >= d.M) return;
+    const float* part = reinterpret_cast<const float*>(smem);
+    const int r = ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31);
+    const int ncols = min(32, d.N - n0);
+    const int per = (32 + k_splits - 1) / k_splits;   // columns per CTA (<= 32)
+    const int c_lo = rank * per;
+    const float b = __ldg(p.bias + row);
+    const uint32_t local = smem_u32(part + r);
+    float v[8][8];  // [split][column]; k_splits <= 8, per <= 8 whenever k_splits >= 4
+    if (per <= 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < k_splits) {
+          const uint32_t src = mapa_shared(local, static_cast<uint32_t>(k));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[k][j] = (j < per && c_lo + j < 32) ? ld_dsmem_f32(src + static_cast<uint32_t>((c_lo + j) * 128 * 4)) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < per && c_lo + j < ncols) {
+          float acc = v[0][j];
+#pragma unroll
+          for (int k = 1; k < 8; ++k)
+            if (k < k_splits) acc += v[k][j];
+          const float x = bf16_round(acc + b);
+          p.act[static_cast<int64_t>(n0 + c_lo + j) * p.ld + row] = __float2bfloat16_rn(gelu_erf(x));
+        }
+      }
+    } else {
+      // 1 or 2 splits: a CTA owns 32 or 16 columns
+      for (int j = 0; j < per; ++j) {
+        const int c = c_lo + j;
+        if (c >= ncols) break;
+        float acc = part[c * 128 + r];
+        for (int k = 1; k < k_splits; ++k)
+          acc += ld_dsmem_f32(mapa_shared(local, static_cast<uint32_t>(k)) + static_cast<uint32_t>(c * 128 * 4));
+        if (rank != 0 && k_splits > 1) {
+          // rank 0's partial is remote for the other ranks: rebuild the sum in split order
+          acc = ld_dsmem_f32(mapa_shared(local, 0u) + static_cast<uint32_t>(c * 128 * 4));
+          for (int k = 1; k < k_splits; ++k)
+            acc += ld_dsmem_f32(mapa_shared(local, static_cast<uint32_t>(k)) + static_cast<uint32_t>(c * 128 * 4));
+        }
+        const float x = bf16_round(acc + b);
+        p.act[static_cast<int64_t>(n0 + c) * p.ld + row] = __float2bfloat16_rn(gelu_erf(x));
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
 // GEMM1 epilogue:  pre = bf16(acc + b1);  act = bf16(gelu_erf(pre))
 // (reference: output_mlp_projector + vision_activation, modeling_vlm.py:47-49; the activation is
 //  applied to the bf16-rounded Linear output exactly as the bf16 reference path does.)

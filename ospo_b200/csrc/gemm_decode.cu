@@ -36,6 +36,21 @@ int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_b
   return launch_gemm<CfgS128, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl);
 }
 
+// decode GEMM1, cluster split-K form: act is final when the kernel ends (no partials in HBM, no finalize launch).
+// Returns -100 if the shape does not fit the one-item-per-CTA scheme; the caller then uses the partial + finalize path.
+using CfgS32C = GemmCfg<1, 32, false, false, 0, 8, 1, true, true>;
+int launch_decode_gemm1_cluster(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
+                                __nv_bfloat16* act, int n, int H, int E) {
+  using Epi = EpiClusterGeluT;
+  if (n > 32) return -100;
+  Epi::Params p{b1, act, E};
+  int ks = decode_gemm1_splits(c.num_sms, H, E);
+  if (ks == 3) ks = 2;            // cluster sizes: 1, 2, 4, 8
+  if (ks > 4 && ks < 8) ks = 4;
+  return launch_gemm<CfgS32C, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl, SegOperand(),
+                                   SegOperand(), 1);
+}
+
 int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                         __nv_bfloat16* logits, int n, int E, int V) {
   using Epi = EpiStore<__nv_bfloat16, true, true>;
@@ -46,7 +61,9 @@ int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv
 }
 
 // GEMM2: the deepest ring that fits (10 x 20 KB): while it waits for the activations its producer has 20 MB of W2
-// in flight across the chip, which fills most of the GEMM1 -> GEMM2 dependency bubble
+// in flight across the chip, which fills part of the GEMM1 -> GEMM2 dependency bubble.  (Measured alternative: a
+// 3-stage GEMM1 + 7-stage GEMM2 sharing every SM starts the W2 prefetch earlier but slows the W1 stream by more
+// than it gains: 48.4 vs 45.9 us per step.)
 using CfgF32 = GemmCfg<1, 32, false, false, 1024, 10, 1, true>;
 
 template <int MODE, bool TDIV>

@@ -65,9 +65,14 @@ enum : uint32_t {
 // registers let the NEXT kernel of a programmatic-dependent-launch chain become resident beside the running
 // one, and A_INDEPENDENT_ (the A operand -- a weight matrix -- does not depend on the predecessor kernel) lets
 // its producer start streaming weights before griddepcontrol.wait, so HBM never idles at a kernel boundary.
+// CLUSTER_SPLIT_: the k-splits of one output tile are the CTAs of one thread-block cluster (one work item per CTA);
+// each CTA parks its fp32 partial tile in its own shared memory and CTA 0 of the cluster combines them through
+// distributed shared memory in split order (Epi::cluster_finalize) -- no partials in HBM, no second launch.
 template <int CG_, int BN_, bool A_MN_, bool B_MN_, int EPI_SMEM_BYTES_ = 0, int MAX_STAGES_ = 8, int MIN_BLOCKS_ = 1,
-          bool A_INDEPENDENT_ = false>
+          bool A_INDEPENDENT_ = false, bool CLUSTER_SPLIT_ = false>
 struct GemmCfg {
+  static constexpr bool CLUSTER_SPLIT = CLUSTER_SPLIT_;
+  static_assert(!CLUSTER_SPLIT_ || CG_ == 1, "cluster split-K uses single-CTA MMAs");
   static constexpr int MIN_BLOCKS = MIN_BLOCKS_;
   static constexpr bool A_INDEPENDENT = A_INDEPENDENT_;
   static constexpr int CG = CG_;            // CTAs cooperating on one tile (cta_group)
@@ -353,7 +358,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     pdl_wait();                        // the epilogue reads / writes global memory
     const int q = warp & 3;            // TMEM lane quarter this warp may touch
     const int half = (warp - 2) >> 2;  // which half of the tile's columns (EPI_SPLIT == 2)
-    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 256;
+    // cluster split-K parks the partial tile in the (by then drained) operand ring
+    uint8_t* epi_smem = Cfg::CLUSTER_SPLIT ? stage_base : smem + STAGES * Cfg::STAGE_BYTES + 256;
     uint32_t leader_tmem_empty_addr[ACC_STAGES];
 #pragma unroll
     for (int a = 0; a < ACC_STAGES; ++a) {
@@ -418,7 +424,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   // ===================== teardown =====================
   __syncwarp();  // re-converge the single-thread roles before the block-wide barrier
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if constexpr (Cfg::CLUSTER_SPLIT) {
+    // every CTA's partial tile is in its shared memory: combine them in CTA 0, keep the others alive until done
+    cluster_sync();
+    if (threadIdx.x == 64) trace_stamp(dims.trace_id, 6);
+    if (warp >= 2) {
+      const int t = dom_first;  // one work item per CTA
+      if (t < dom_tiles) {
+        const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
+        const int row = tc.m_blk * Cfg::TILE_M + (warp & 3) * 32 + lane;
+        Epi::cluster_finalize(ep, row, tc.n_blk * BN, ksplits, static_cast<int>(cluster_ctarank()), dims, stage_base);
+      }
+    }
+    if (threadIdx.x == 64) trace_stamp(dims.trace_id, 7);
+    cluster_sync();
+  } else if constexpr (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
@@ -530,6 +550,8 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return -3;
+    // whole L1/shared array as shared memory: lets two kernels of a dependent-launch chain share an SM
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   GemmDims dims;
@@ -551,6 +573,11 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   int clusters = num_sms / Cfg::CG;
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
+  if constexpr (Cfg::CLUSTER_SPLIT) {
+    // exactly one (tile, k-split) item per CTA, the splits of a tile forming one cluster
+    if (num_tiles > num_sms || dims.k_splits > 8 || dims.die_split) return -100;
+    clusters = num_tiles;
+  }
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * Cfg::CG, 1, 1);
@@ -559,7 +586,7 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = Cfg::CG;
+  attrs[0].val.clusterDim.x = Cfg::CLUSTER_SPLIT ? dims.k_splits : Cfg::CG;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs;

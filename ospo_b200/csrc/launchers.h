@@ -67,6 +67,11 @@ int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat1
 int decode_gemm1_splits(int num_sms, int H, int E);
 int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, float* part,
                         int64_t split_stride, int n, int H, int E);
+// cluster split-K form of the decode GEMM1: the k-splits of a tile are one thread-block cluster and are combined
+// through distributed shared memory; act[n, e] = bf16(gelu(bf16(W1 h^T + b1))) is final at kernel end.
+// Returns -100 when the shape does not fit one work item per SM (use the partial + finalize path then).
+int launch_decode_gemm1_cluster(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
+                                __nv_bfloat16* act, int n, int H, int E);
 // logits[n, v] = bf16(W2 act^T + b2)
 int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                         __nv_bfloat16* logits, int n, int E, int V);

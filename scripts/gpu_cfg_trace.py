@@ -56,7 +56,7 @@ for k in (1, 3, 2, 4):
     a = t[k]
     act = a[:, 0] > 0
     line = f"TRACE {names[k]:9s} ctas={int(act.sum()):3d}"
-    for slot, nm in ((0, "entry"), (1, "prefetched"), (2, "wait_over"), (3, "prod_done"), (4, "acc_ready"), (5, "epi_done")):
+    for slot, nm in ((0, "entry"), (1, "prefetched"), (2, "wait_over"), (3, "prod_done"), (4, "acc_ready"), (5, "epi_done"), (6, "csync1"), (7, "finalized")):
         v = a[act, slot]
         v = v[v > 0]
         if v.size:

@@ -82,6 +82,89 @@ def test_gemm_engine_variant(variant, shape):
     torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("variant", [100, 120, 200, 210, 220, 101])
+def test_gemm_engine_writes_stay_in_bounds(variant):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are caught with canaries: the output lives
+    inside a larger buffer whose guard bands must come back untouched (ragged M / N / K on purpose)."""
+    from ospo_b200 import _abi
+
+    dev = _cuda()
+    lib = _abi.load()
+    M, N, K = 200, 264, 136          # none is a multiple of the tile; all multiples of 8 (TMA pitch rule)
+    majors = (variant // 10) % 10
+    a_mn, b_mn = majors == 2, majors >= 1
+    g = torch.Generator().manual_seed(variant)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16)
+    Ad = (A.t().contiguous() if a_mn else A).to(dev)
+    Bd = (B.t().contiguous() if b_mn else B).to(dev)
+    guard, ldo = 64, N + 24
+    big = torch.full((M + 2 * guard, ldo), 12345.0, device=dev)
+    out = big[guard:guard + M]
+    rc = lib.ospo_head_gemm_debug(variant, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0), out.data_ptr(),
+                                  ldo, M, N, K, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _abi.strerror(rc)
+    torch.cuda.synchronize()
+    ref = A.to(dev).float() @ B.to(dev).float().t()
+    torch.testing.assert_close(out[:, :N], ref, rtol=1e-3, atol=1e-2)
+    assert bool((big[:guard] == 12345.0).all()) and bool((big[guard + M:] == 12345.0).all())
+    assert bool((out[:, N:] == 12345.0).all())
+
+
+def test_simpo_ragged_shapes_stay_in_bounds():
+    """rows / V / E / H that are not multiples of any tile: results still match the oracle and nothing outside the
+    logical outputs is written (dX canary, gradient buffer sizes are exact by construction)."""
+    dev = _cuda()
+    H, E, V, B, T, L = 136, 200, 1000, 3, 37, 2
+    head_b = O.make_head(H, E, V, seed=51, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=52, dtype=torch.bfloat16)
+    hp = dict(beta=5.0, gamma_beta_ratio=0.5, loss_type="sigmoid")
+    ref = O.simpo_step(head_b, hc, hr, lc, lr, backward=True, **hp)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+    hidden = torch.cat([hc, hr]).to(dev).requires_grad_(True)
+    out = fh.simpo(hidden, torch.cat([lc, lr]).to(dev), **hp)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.chosen_logps.cpu().numpy(), ref["chosen_logps"].detach().float().numpy(), rtol=1e-2)
+    # the loss sees beta * (chosen - rejected): allow beta * 2 * (log-prob tolerance)
+    np.testing.assert_allclose(float(out.loss), float(ref["loss"]), rtol=1e-2, atol=5.0 * 2 * 2e-2)
+    # bf16 gradients of a 222-row problem: the pair coefficients inherit the log-prob error
+    assert _rel_fro(hidden.grad.float(), ref["dx"].float()) < 1e-1
+    assert _rel_fro(fh.vision_head.weight.grad.float(), ref["dW2"].float()) < 1e-1
+    assert _rel_fro(fh.output_mlp_projector.weight.grad.float(), ref["dW1"].float()) < 1e-1
+    assert _rel_fro(fh.vision_head.bias.grad.float(), ref["db2"].float()) < 1e-1
+    assert torch.isfinite(fh.vision_head.weight.grad.float()).all()
+
+
+def test_abi_rejects_bad_arguments():
+    """error behaviour of the C ABI on a live device: misalignment, short workspace, bad shapes, NULL pointers"""
+    import ctypes as C
+
+    from ospo_b200 import _abi
+
+    dev = _cuda()
+    lib = _abi.load()
+    x = torch.zeros(64, 64, dtype=torch.bfloat16, device=dev)
+    w1 = torch.zeros(64, 64, dtype=torch.bfloat16, device=dev)
+    b = torch.zeros(64, dtype=torch.float32, device=dev)
+    out = torch.zeros(64, 64, dtype=torch.bfloat16, device=dev)
+    need = _abi.workspace_bytes(64, 64, 64, 64, 1)
+    ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+
+    def call(shape, xp, wsp, wsn, logits):
+        a = _abi.HeadArgs(shape, _abi.Weights(w1.data_ptr(), b.data_ptr(), w1.data_ptr(), b.data_ptr()), xp, logits, wsp, wsn)
+        return lib.ospo_head_logits(C.byref(a), torch.cuda.current_stream().cuda_stream)
+
+    ok_shape = _abi.Shape(64, 64, 64, 64, 1)
+    assert call(ok_shape, x.data_ptr(), ws.data_ptr(), need, out.data_ptr()) == 0
+    assert call(ok_shape, x.data_ptr() + 2, ws.data_ptr(), need, out.data_ptr()) == -2       # alignment
+    assert call(ok_shape, x.data_ptr(), ws.data_ptr(), need - 1, out.data_ptr()) == -4       # workspace
+    assert call(_abi.Shape(64, 60, 64, 64, 1), x.data_ptr(), ws.data_ptr(), need, out.data_ptr()) == -2   # H % 8
+    assert call(_abi.Shape(0, 64, 64, 64, 1), x.data_ptr(), ws.data_ptr(), need, out.data_ptr()) == -1    # rows
+    assert call(ok_shape, None, ws.data_ptr(), need, out.data_ptr()) == -3                   # NULL
+    torch.cuda.synchronize()
+
+
 # ---------------------------------------------------------------------------------------------------
 # SimPO: golden vectors from the reference's own code (fp32 reference vs bf16 kernels)
 # ---------------------------------------------------------------------------------------------------

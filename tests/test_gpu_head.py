@@ -559,3 +559,100 @@ def test_generate_loop_mirror():
     for i in range(n):
         ids = fh.cfg_sample(hs[i], 5.0, 1.0, uniforms=u[i])
         assert torch.equal(ids.to(torch.int32), toks[:, i])
+
+
+# ---------------------------------------------------------------------------------------------------
+# integration: patched train wrapper over a real (tiny) HF Llama backbone  (BASELINE.json configs[4] in miniature)
+# ---------------------------------------------------------------------------------------------------
+def test_patch_train_wrapper_end_to_end_with_llama_backbone():
+    """patch_train_wrapper re-points concatenated_forward / get_batch_loss_metrics (train.py:345-372, 399-445) at the
+    fused head.  With a random-init transformers LlamaModel as `language_model.model`, the loss and the gradients
+    that reach the BACKBONE parameters (through dX) and the head parameters match the reference formulation
+    (PyTorch head + oracle loss on the same backbone output)."""
+    import types
+
+    from transformers import LlamaConfig, LlamaModel
+
+    from ospo_b200 import FusedGenHead, patch_train_wrapper
+
+    dev = _cuda()
+    torch.manual_seed(0)
+    D, V, B, T, L = 256, 2048, 2, 64, 4
+    cfg = LlamaConfig(hidden_size=D, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=128, max_position_embeddings=512)
+    cfg.output_hidden_states = True          # train.py:50
+    backbone = LlamaModel(cfg).to(dev).to(torch.bfloat16)
+    head = O.make_head(D, D, V, seed=61, w2_gain=3.0).to(torch.bfloat16).to(dev)
+
+    model = torch.nn.Module()
+    model.language_model = torch.nn.Module()
+    model.language_model.model = backbone
+    model.gen_head = head
+
+    g = torch.Generator().manual_seed(62)
+    emb_c = torch.randn(B, L + T, D, generator=g).to(torch.bfloat16).to(dev)
+    emb_r = torch.randn(B, L + T, D, generator=g).to(torch.bfloat16).to(dev)
+    pad = torch.full((B, L), -100, dtype=torch.long)
+    lab_c = torch.cat([pad, torch.randint(0, V, (B, T), generator=g)], 1).to(dev)
+    lab_r = torch.cat([pad, torch.randint(0, V, (B, T), generator=g)], 1).to(dev)
+    batch = {"chosen_inputs_embeds": emb_c, "chosen_labels": lab_c, "rejected_inputs_embeds": emb_r,
+             "rejected_labels": lab_r}
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, label_smoothing=0.0, loss_type="sigmoid", sft_weight=0.0)
+
+    # ---- reference formulation on the same backbone -------------------------------------------------
+    def backbone_hidden():
+        x = torch.cat([emb_c, emb_r], 0)
+        return backbone(inputs_embeds=x, use_cache=False).hidden_states[-1]
+
+    backbone.zero_grad()
+    head.zero_grad()
+    hidden = backbone_hidden()
+    labels = torch.cat([lab_c, lab_r], 0)
+    logps = O.get_batch_logps(head(hidden), labels, average_log_prob=True)
+    losses, _, _ = O.simpo_loss(logps[:B], logps[B:], hp["beta"], hp["gamma_beta_ratio"], hp["label_smoothing"],
+                                hp["loss_type"])
+    loss_ref = losses.mean()
+    loss_ref.backward()
+    ref_grads = {n: p.grad.detach().float().clone() for n, p in backbone.named_parameters() if p.grad is not None}
+    ref_head = {n: p.grad.detach().float().clone() for n, p in head.named_parameters()}
+
+    # ---- patched wrapper ---------------------------------------------------------------------------
+    class Wrapper:
+        pass
+
+    w = Wrapper()
+    w.model = model
+    for k, v in hp.items():
+        setattr(w, k, v)
+    w.label_pad_token_id = -100
+    w.logged = {}
+    w.log = lambda name, val, **kw: w.logged.__setitem__(name, val)
+    w.log_dict = lambda d, **kw: w.logged.update(d)
+
+    def concatenated_inputs(self, batch):      # train.py:282-314 with pad_to_length a no-op (equal lengths)
+        return {"concatenated_inputs_embeds": torch.cat([batch["chosen_inputs_embeds"], batch["rejected_inputs_embeds"]], 0),
+                "concatenated_labels": torch.cat([batch["chosen_labels"], batch["rejected_labels"]], 0)}
+
+    w.concatenated_inputs = types.MethodType(concatenated_inputs, w)
+    patch_train_wrapper(w, image_span=(L - 1, L - 1 + T))
+    assert isinstance(model.gen_head, FusedGenHead)
+    assert model.gen_head.vision_head.weight is head.vision_head.weight      # parameters are shared, not copied
+    backbone.zero_grad()
+    head.zero_grad()
+    loss = w.get_batch_loss_metrics(batch, "train")
+    loss.backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(float(loss), float(loss_ref), rtol=1e-2, atol=5e-2)
+    assert "train/rewards/accuracies" in w.logged and "train/logits/chosen" in w.logged
+    cl, rl, _, _, clab = w.concatenated_forward(batch)
+    np.testing.assert_allclose(cl.detach().float().cpu().numpy(), logps[:B].detach().float().cpu().numpy(), rtol=1e-2)
+    assert clab.shape == lab_c.shape
+    checked = 0
+    for n, p in backbone.named_parameters():
+        if p.grad is None or n not in ref_grads or ref_grads[n].norm() == 0:
+            continue
+        assert _rel_fro(p.grad.float(), ref_grads[n]) < 8e-2, n
+        checked += 1
+    assert checked >= 10
+    for n, p in head.named_parameters():
+        assert _rel_fro(p.grad.float(), ref_head[n]) < 5e-2, n

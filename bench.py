@@ -441,6 +441,49 @@ def bench_cfg(head, dev, peaks):
                      "frac": step_bytes / (us_step * 1e-6) / 1e9 / peaks["hbm"], "bytes_per_step": step_bytes,
                      "traffic": None},
     })
+    # next row N1: the same loop with prepare_gen_img_embeds (gen_embed -> gen_aligner, +33.6 MB of weights) fused in
+    try:
+        from ospo_b200 import FusedGenImgEmbeds
+
+        gen_embed = torch.nn.Embedding(V, 8).to(dev).to(torch.bfloat16)
+        lin = torch.nn.Sequential(torch.nn.Linear(8, H7B), torch.nn.GELU(), torch.nn.Linear(H7B, H7B))
+        aligner = torch.nn.Module()
+        aligner.layers = lin.to(dev).to(torch.bfloat16)
+        fused_embeds = FusedGenImgEmbeds(gen_embed, aligner)
+        emb_out = torch.empty(2 * P, H7B, dtype=torch.bfloat16, device=dev)
+
+        def run_steps_n1():
+            for i in range(steps):
+                w = p if (i & 1) == 0 else alt
+                ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
+                both = torch.stack([ids, ids], dim=1).view(-1)              # image_generation.py:166
+                emb_out.copy_(fused_embeds(both))                           # :167
+                ids_out[i].copy_(ids)
+
+        run_steps_n1()
+        torch.cuda.synchronize()
+        s2 = torch.cuda.Stream()
+        s2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s2):
+            run_steps_n1()
+        torch.cuda.current_stream().wait_stream(s2)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            run_steps_n1()
+        g2.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            g2.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us_n1 = e0.elapsed_time(e1) / 3 * 1e3 / steps
+        bytes_n1 = step_bytes + 2 * H7B * H7B + 2 * 8 * H7B + 8 * H7B + 2 * 2 * P * H7B
+        result["with_gen_img_embeds"] = {"us_per_step": us_n1, "bytes_per_step": bytes_n1,
+                                         "achieved_gbs": bytes_n1 / (us_n1 * 1e-6) / 1e9,
+                                         "frac_of_hbm_peak": bytes_n1 / (us_n1 * 1e-6) / 1e9 / peaks["hbm"]}
+    except Exception as ex:
+        result["with_gen_img_embeds"] = {"error": repr(ex)[:200]}
     # merge + sample alone on supplied logits, all 576 steps in one launch (SURVEY §8d secondary metric)
     lg = (torch.randn(steps, 2 * P, V, generator=gen, device=dev) * 3).to(torch.bfloat16)
     for _ in range(3):

@@ -10,6 +10,7 @@
  *   ospo_head_simpo_fwd/_bwd  ospo/wrapper/train.py:317-342, 345-372, 399-445  SimPO loss fwd + bwd
  *   ospo_head_cfg_sample      ospo/wrapper/image_generation.py:156-164 (== ospo/inference.py:147-155)
  *   ospo_head_cfg_merge_sample   the merge/softmax/sample tail of the same lines, on supplied logits
+ *   ospo_head_gen_img_embeds  janus/models/modeling_vlm.py:263-264 + projector.py:39-45 (next row N1)
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory,
@@ -160,6 +161,28 @@ typedef struct {
   size_t workspace_bytes;
 } ospo_cfg_args;
 
+/* ---- next row: sampled ids -> next-step input embeddings ---------------------------------
+ * prepare_gen_img_embeds = gen_aligner(gen_embed(ids))  (janus/models/modeling_vlm.py:263-264; MlpProjector
+ * "mlp_gelu" depth 2, janus/models/projector.py:39-45,77-86), called right after sampling at
+ * ospo/wrapper/image_generation.py:166-168.  All bf16 like the generation path; the second Linear streams its
+ * D x D weight once (swap-AB tcgen05 GEMM, cluster split-K). */
+typedef struct {
+  int32_t rows;             /* n ids (the reference passes the 2P duplicated ids; n <= 32 per call) */
+  int32_t embed;            /* D: n_embed of the language model */
+  int32_t codebook;         /* rows of gen_embed (16384) */
+  int32_t code_dim;         /* columns of gen_embed; must be 8 */
+  const int64_t* ids;       /* [n] */
+  const void* gen_embed;    /* bf16 [codebook, 8] */
+  const void* wa;           /* bf16 [D, 8]   gen_aligner.layers.0.weight */
+  const float* ba;          /* fp32 [D]      gen_aligner.layers.0.bias   */
+  const void* wb;           /* bf16 [D, D]   gen_aligner.layers.2.weight */
+  const float* bb;          /* fp32 [D]      gen_aligner.layers.2.bias   */
+  void* out;                /* bf16 [n, D] */
+  void* workspace;          /* >= n * D * 2 bytes, 16-byte aligned */
+  size_t workspace_bytes;
+} ospo_aligner_args;
+OSPO_API int ospo_head_gen_img_embeds(const ospo_aligner_args* args, ospo_stream_t stream);
+
 /* scratch bytes needed by any entry point for this shape */
 OSPO_API int ospo_head_workspace_bytes(const ospo_head_shape* shape, size_t* out_bytes);
 
@@ -201,7 +224,8 @@ OSPO_API int ospo_head_set_group_m(int group_m);
 #define OSPO_K_DECODE_GEMM1 10  /* swap-AB W1 h^T, GELU                                            */
 #define OSPO_K_DECODE_GEMM2 11  /* swap-AB W2 act^T                                                */
 #define OSPO_K_SAMPLER 12       /* CFG merge + softmax + inverse-CDF sample                        */
-#define OSPO_K_COUNT 13
+#define OSPO_K_ALIGNER 13       /* gen_embed lookup + Linear(8->D) + GELU, then swap-AB Linear(D->D)   */
+#define OSPO_K_COUNT 14
 OSPO_API int ospo_head_profile_enable(int enable);
 OSPO_API int ospo_head_profile_read(float* total_ms, int32_t* counts, int32_t n);
 /* tuning aid: CTA timeline of the decode chain.  device_buf = u64[5][160][8] (kernel: 1 GEMM1, 2 GEMM2, 3 finalize,

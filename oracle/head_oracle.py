@@ -194,6 +194,27 @@ def decode_step_reference(head: VisionHead, hidden_last: torch.Tensor, cfg_weigh
     return next_token.squeeze(-1), probs
 
 
+# --------------------------------------------------------------------------------------------------
+# next row N1: prepare_gen_img_embeds (janus/models/modeling_vlm.py:263-264)
+# --------------------------------------------------------------------------------------------------
+class GenAligner(torch.nn.Module):
+    """``MlpProjector`` with ``projector_type='mlp_gelu', depth=2`` (janus/models/projector.py:39-45, 86):
+    layers = Sequential(Linear(input_dim, n_embed), GELU(), Linear(n_embed, n_embed))"""
+
+    def __init__(self, input_dim: int, n_embed: int):
+        super().__init__()
+        self.layers = torch.nn.Sequential(torch.nn.Linear(input_dim, n_embed), torch.nn.GELU(),
+                                          torch.nn.Linear(n_embed, n_embed))
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+def prepare_gen_img_embeds(gen_embed: torch.nn.Embedding, gen_aligner: torch.nn.Module, image_ids: torch.Tensor):
+    """modeling_vlm.py:263-264"""
+    return gen_aligner(gen_embed(image_ids))
+
+
 # ---- deterministic inverse-CDF sampler (oracle/cfg_sample.c) ---------------------------------------
 _clib = None
 

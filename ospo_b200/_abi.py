@@ -100,6 +100,24 @@ class CfgArgs(C.Structure):
     ]
 
 
+class AlignerArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32),
+        ("embed", C.c_int32),
+        ("codebook", C.c_int32),
+        ("code_dim", C.c_int32),
+        ("ids", C.c_void_p),
+        ("gen_embed", C.c_void_p),
+        ("wa", C.c_void_p),
+        ("ba", C.c_void_p),
+        ("wb", C.c_void_p),
+        ("bb", C.c_void_p),
+        ("out", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # scalars[] indices (OSPO_SC_*)
 SC_LOSS, SC_SIMPO_LOSS, SC_SFT_LOSS = 0, 1, 2
 SC_REWARD_CHOSEN, SC_REWARD_REJECTED, SC_REWARD_ACC, SC_REWARD_MARGIN = 3, 4, 5, 6
@@ -119,6 +137,7 @@ EXPORTS = (
     "ospo_head_simpo_bwd",
     "ospo_head_cfg_sample",
     "ospo_head_cfg_merge_sample",
+    "ospo_head_gen_img_embeds",
     "ospo_head_strerror",
     "ospo_head_set_cta_group",
     "ospo_head_set_decode_mode",
@@ -168,6 +187,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(CfgArgs), S]
         fn.restype = C.c_int
+    lib.ospo_head_gen_img_embeds.argtypes = [C.POINTER(AlignerArgs), S]
+    lib.ospo_head_gen_img_embeds.restype = C.c_int
     lib.ospo_head_strerror.argtypes = [C.c_int]
     lib.ospo_head_strerror.restype = C.c_char_p
     lib.ospo_head_set_cta_group.argtypes = [C.c_int]
@@ -213,7 +234,7 @@ def workspace_bytes(rows: int, hidden: int, embed: int, vocab: int, num_seqs: in
 
 KERNEL_NAMES = ("gemm1_bias_gelu", "gemm2_logits_lse", "scalar_stage", "dlogits_producer", "dact_gelu_bwd",
                 "wgrad_w2", "colsum_db1", "wgrad_w1", "dgrad_x", "gemm2_logits_plain", "decode_gemm1",
-                "decode_gemm2", "cfg_merge_sample")
+                "decode_gemm2", "cfg_merge_sample", "gen_img_embeds")
 
 
 def profile_enable(on: bool) -> None:

@@ -539,6 +539,32 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
   return launch_sampler(&b, pairs, st);
 }
 
+int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
+  if (!a) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  if (a->rows <= 0 || a->embed <= 0 || a->codebook <= 0) return OSPO_ERR_BAD_SHAPE;
+  if (a->code_dim != 8 || a->rows > 32) return OSPO_ERR_UNSUPPORTED;
+  if (a->embed % 8) return OSPO_ERR_ALIGNMENT;
+  if (!a->ids || !a->gen_embed || !a->wa || !a->ba || !a->wb || !a->bb || !a->out || !a->workspace) return OSPO_ERR_NULL;
+  if (!aligned16(a->gen_embed) || !aligned16(a->wa) || !aligned16(a->wb) || !aligned16(a->out) ||
+      !aligned16(a->workspace))
+    return OSPO_ERR_ALIGNMENT;
+  if (a->workspace_bytes < static_cast<size_t>(a->rows) * a->embed * 2) return OSPO_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LaunchCtx c = make_ctx(st);
+  c.pdl = g_rt.decode_pdl != 0;
+  KernelSpan ks(st, OSPO_K_ALIGNER);
+  __nv_bfloat16* a1 = static_cast<__nv_bfloat16*>(a->workspace);
+  if (launch_plain(gen_embed_up_kernel, dim3((a->embed + 255) / 256, a->rows), dim3(256), st, c.pdl, a->ids,
+                   static_cast<const __nv_bfloat16*>(a->gen_embed), a->codebook,
+                   static_cast<const __nv_bfloat16*>(a->wa), a->ba, a1, a->rows, a->embed) != cudaSuccess)
+    return OSPO_ERR_LAUNCH;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return map_rc(launch_decode_linear_cluster(c, a1, static_cast<const __nv_bfloat16*>(a->wb), a->bb,
+                                             static_cast<__nv_bfloat16*>(a->out), a->rows, a->embed, a->embed));
+}
+
 const char* ospo_head_strerror(int status) {
   switch (status) {
     case OSPO_OK: return "ok";

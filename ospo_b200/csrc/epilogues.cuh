@@ -203,11 +203,13 @@ struct EpiPartialStoreT {
 };
 
 // ---------------------------------------------------------------------------
-// Decode GEMM1 with cluster split-K: the partial tile goes to this CTA's shared memory as part[col][row]; CTA 0 of
-// the cluster then sums the k_splits partials in split order through distributed shared memory, adds b1, applies
-// GELU and writes act[n][e] (bf16).  Deterministic, no HBM partials, no finalize launch.
+// Swap-AB linear layer with cluster split-K (decode GEMM1, gen_aligner): the partial tile goes to this CTA's shared
+// memory as part[col][row]; the CTAs of the cluster then sum the k_splits partials in split order through distributed
+// shared memory, add the bias, optionally apply GELU and write out[n][m] (bf16).  Deterministic, no HBM partials, no
+// finalize launch.
 // ---------------------------------------------------------------------------
-struct EpiClusterGeluT {
+template <bool GELU>
+struct EpiClusterLinearT {
   struct Params {
     const float* bias;     // b1 [E]
     __nv_bfloat16* act;    // [n, E]
@@ -257,7 +259,7 @@ struct EpiClusterGeluT {
           for (int k = 1; k < 8; ++k)
             if (k < k_splits) acc += v[k][j];
           const float x = bf16_round(acc + b);
-          p.act[static_cast<int64_t>(n0 + c_lo + j) * p.ld + row] = __float2bfloat16_rn(gelu_erf(x));
+          p.act[static_cast<int64_t>(n0 + c_lo + j) * p.ld + row] = __float2bfloat16_rn(GELU ? gelu_erf(x) : x);
         }
       }
     } else {
@@ -275,7 +277,7 @@ struct EpiClusterGeluT {
             acc += ld_dsmem_f32(mapa_shared(local, static_cast<uint32_t>(k)) + static_cast<uint32_t>(c * 128 * 4));
         }
         const float x = bf16_round(acc + b);
-        p.act[static_cast<int64_t>(n0 + c) * p.ld + row] = __float2bfloat16_rn(gelu_erf(x));
+        p.act[static_cast<int64_t>(n0 + c) * p.ld + row] = __float2bfloat16_rn(GELU ? gelu_erf(x) : x);
       }
     }
   }

@@ -39,16 +39,28 @@ int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_b
 // decode GEMM1, cluster split-K form: act is final when the kernel ends (no partials in HBM, no finalize launch).
 // Returns -100 if the shape does not fit the one-item-per-CTA scheme; the caller then uses the partial + finalize path.
 using CfgS32C = GemmCfg<1, 32, false, false, 0, 8, 1, true, true>;
-int launch_decode_gemm1_cluster(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
-                                __nv_bfloat16* act, int n, int H, int E) {
-  using Epi = EpiClusterGeluT;
+template <bool GELU>
+static int run_linear_cluster(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* b,
+                              __nv_bfloat16* out, int n, int K, int M, int trace_id) {
+  using Epi = EpiClusterLinearT<GELU>;
   if (n > 32) return -100;
-  Epi::Params p{b1, act, E};
-  int ks = decode_gemm1_splits(c.num_sms, H, E);
+  typename Epi::Params p{b, out, M};
+  int ks = decode_gemm1_splits(c.num_sms, K, M);
   if (ks == 3) ks = 2;            // cluster sizes: 1, 2, 4, 8
   if (ks > 4 && ks < 8) ks = 4;
-  return launch_gemm<CfgS32C, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl, SegOperand(),
-                                   SegOperand(), 1);
+  // D[M, n] = W[M, K] * x[n, K]^T, k-splits of a tile = one cluster
+  return launch_gemm<CfgS32C, Epi>(w, K, x, K, M, n, K, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl, SegOperand(),
+                                   SegOperand(), trace_id);
+}
+
+int launch_decode_gemm1_cluster(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
+                                __nv_bfloat16* act, int n, int H, int E) {
+  return run_linear_cluster<true>(c, h, w1, b1, act, n, H, E, 1);
+}
+
+int launch_decode_linear_cluster(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* b,
+                                 __nv_bfloat16* out, int n, int in_dim, int out_dim) {
+  return run_linear_cluster<false>(c, x, w, b, out, n, in_dim, out_dim, 0);
 }
 
 int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,

@@ -296,6 +296,35 @@ decode_act_finalize_kernel(const float* __restrict__ part, int k_splits, int64_t
 }
 
 // ---------------------------------------------------------------------------
+// prepare_gen_img_embeds, first half (janus/models/modeling_vlm.py:263-264, projector.py:39-45):
+//   a[n, d] = bf16(gelu_erf(bf16(sum_k gen_embed[id_n, k] * Wa[d, k] + ba[d])))      (k = 8: the VQ code dimension)
+// The second Linear (D x D, 33.5 MB at 7B) is the weight-streaming swap-AB GEMM launch_decode_linear_cluster.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gen_embed_up_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ gen_embed, int codebook,
+                    const __nv_bfloat16* __restrict__ wa, const float* __restrict__ ba, __nv_bfloat16* __restrict__ a,
+                    int n, int D) {
+  pdl_launch_dependents();
+  pdl_wait();  // the ids come from the sampler
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (d >= D || row >= n) return;
+  int64_t id = ids[row];
+  id = id < 0 ? 0 : (id >= codebook ? codebook - 1 : id);
+  const uint4 e = __ldg(reinterpret_cast<const uint4*>(gen_embed + id * 8));
+  const uint4 w = __ldg(reinterpret_cast<const uint4*>(wa + static_cast<int64_t>(d) * 8));
+  const uint32_t ew[4] = {e.x, e.y, e.z, e.w}, ww[4] = {w.x, w.y, w.z, w.w};
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc = fmaf(__uint_as_float(ew[k] << 16), __uint_as_float(ww[k] << 16), acc);
+    acc = fmaf(__uint_as_float(ew[k] & 0xFFFF0000u), __uint_as_float(ww[k] & 0xFFFF0000u), acc);
+  }
+  const float x = bf16_round(acc + __ldg(ba + d));
+  a[static_cast<int64_t>(row) * D + d] = __float2bfloat16_rn(0.5f * x * (1.0f + erff(x * 0.70710678118654752f)));
+}
+
+// ---------------------------------------------------------------------------
 // CFG merge + temperature + softmax + inverse-CDF sampling on bf16 logits [2P, V]
 // (row 2k = conditional, row 2k+1 = unconditional: ospo/wrapper/image_generation.py:135-141,157-158).
 //   merge_mode 0 (reference bf16 semantics, op-by-op rounding, image_generation.py:160-161):

@@ -72,6 +72,10 @@ int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_b
 // Returns -100 when the shape does not fit one work item per SM (use the partial + finalize path then).
 int launch_decode_gemm1_cluster(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
                                 __nv_bfloat16* act, int n, int H, int E);
+// out[n, m] = bf16(W x^T + b) for a handful of rows n <= 32 (gen_aligner's second Linear): same swap-AB cluster
+// split-K kernel without the activation
+int launch_decode_linear_cluster(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* b,
+                                 __nv_bfloat16* out, int n, int in_dim, int out_dim);
 // logits[n, v] = bf16(W2 act^T + b2)
 int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                         __nv_bfloat16* logits, int n, int E, int V);

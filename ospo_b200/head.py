@@ -315,3 +315,40 @@ def cfg_merge_sample(logits: torch.Tensor, cfg_weight: float = 5.0, temperature:
     ids, merged = ops.cfg_merge_sample_impl(lg, float(cfg_weight), float(temperature), u, bool(greedy), mm,
                                             bool(return_merged))
     return (ids, merged) if return_merged else ids
+
+
+class FusedGenImgEmbeds:
+    """Drop-in for ``MultiModalityCausalLM.prepare_gen_img_embeds`` (janus/models/modeling_vlm.py:263-264):
+    ``gen_aligner(gen_embed(image_ids))`` with the reference's modules -- ``gen_embed = nn.Embedding(16384, 8)``,
+    ``gen_aligner = MlpProjector('mlp_gelu', depth=2)`` i.e. ``layers = Sequential(Linear(8, D), GELU(), Linear(D, D))``
+    (janus/models/projector.py:39-45).  Holds no parameters of its own: it reads the modules' tensors (bf16 / fp32
+    staging cached until they change).  Inference only, like the call site (image_generation.py:166-168)."""
+
+    def __init__(self, gen_embed: torch.nn.Embedding, gen_aligner: torch.nn.Module):
+        layers = gen_aligner.layers
+        if not (isinstance(layers, torch.nn.Sequential) and len(layers) == 3 and isinstance(layers[0], torch.nn.Linear)
+                and isinstance(layers[2], torch.nn.Linear) and isinstance(layers[1], torch.nn.GELU)):
+            raise _abi.OspoHeadError("FusedGenImgEmbeds supports the 'mlp_gelu' depth-2 aligner of Janus-Pro only")
+        if gen_embed.embedding_dim != 8 or layers[0].in_features != 8:
+            raise _abi.OspoHeadError("FusedGenImgEmbeds expects the 8-dimensional VQ code embedding")
+        self.gen_embed, self.lin_a, self.lin_b = gen_embed, layers[0], layers[2]
+        self._key, self._staged = None, None
+
+    def _params(self):
+        ts = (self.gen_embed.weight, self.lin_a.weight, self.lin_a.bias, self.lin_b.weight, self.lin_b.bias)
+        key = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in ts)
+        if key != self._key:
+            with torch.no_grad():
+                e, wa, ba, wb, bb = ts
+                self._staged = (e.detach().to(torch.bfloat16).contiguous(), wa.detach().to(torch.bfloat16).contiguous(),
+                                ba.detach().to(torch.float32).contiguous(), wb.detach().to(torch.bfloat16).contiguous(),
+                                bb.detach().to(torch.float32).contiguous())
+            self._key = key
+        return self._staged
+
+    @torch.no_grad()
+    def __call__(self, image_ids: torch.Tensor) -> torch.Tensor:
+        e, wa, ba, wb, bb = self._params()
+        ids = image_ids.reshape(-1).to(torch.int64).contiguous()
+        out = ops.gen_img_embeds_impl(ids, e, wa, ba, wb, bb)
+        return out.view(*image_ids.shape, out.shape[-1])

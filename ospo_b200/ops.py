@@ -277,6 +277,31 @@ def cfg_merge_sample_impl(logits: Tensor, cfg_weight: float, temperature: float,
 
 
 # --------------------------------------------------------------------------------------------------
+# next row N1: sampled ids -> next-step input embeddings
+# --------------------------------------------------------------------------------------------------
+def gen_img_embeds_impl(ids: Tensor, gen_embed: Tensor, wa: Tensor, ba: Tensor, wb: Tensor, bb: Tensor) -> Tensor:
+    """== gen_aligner(gen_embed(ids))  (janus/models/modeling_vlm.py:263-264; MlpProjector mlp_gelu depth 2)
+    ids [n] int64 (n <= 32 per launch; longer inputs are processed in slices) -> bf16 [n, D]"""
+    _check_cuda(ids, gen_embed, wa, wb)
+    assert ids.dtype == torch.int64 and ids.dim() == 1 and ids.is_contiguous()
+    assert gen_embed.dtype == torch.bfloat16 and gen_embed.shape[1] == 8 and gen_embed.is_contiguous()
+    assert wa.dtype == torch.bfloat16 and wb.dtype == torch.bfloat16 and wa.is_contiguous() and wb.is_contiguous()
+    assert ba.dtype == torch.float32 and bb.dtype == torch.float32
+    D = wb.shape[0]
+    n = ids.numel()
+    out = torch.empty(n, D, dtype=torch.bfloat16, device=ids.device)
+    ws = torch.empty(32 * D, dtype=torch.bfloat16, device=ids.device)
+    lib = _abi.load()
+    for lo in range(0, n, 32):
+        m = min(32, n - lo)
+        a = _abi.AlignerArgs(m, D, gen_embed.shape[0], 8, ids[lo:lo + m].data_ptr(), gen_embed.data_ptr(), wa.data_ptr(),
+                             ba.data_ptr(), wb.data_ptr(), bb.data_ptr(), out[lo:lo + m].data_ptr(), ws.data_ptr(),
+                             ws.numel() * 2)
+        _abi.check(lib.ospo_head_gen_img_embeds(C.byref(a), _stream()), "ospo_head_gen_img_embeds")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # registration: torch.ops.ospo_head.<name>  (CUDA only).  The nn.Module in head.py calls the *_impl
 # functions directly to keep the dispatcher out of the 576-step decode loop.
 # --------------------------------------------------------------------------------------------------
@@ -289,6 +314,10 @@ head_bwd = torch.library.custom_op("ospo_head::head_bwd", head_bwd_impl, mutates
 cfg_sample = torch.library.custom_op("ospo_head::cfg_sample", cfg_sample_impl, mutates_args=(), device_types="cuda")
 cfg_merge_sample = torch.library.custom_op("ospo_head::cfg_merge_sample", cfg_merge_sample_impl, mutates_args=(),
                                            device_types="cuda")
+
+
+gen_img_embeds = torch.library.custom_op("ospo_head::gen_img_embeds", gen_img_embeds_impl, mutates_args=(),
+                                         device_types="cuda")
 
 
 @linear_gelu_linear.register_fake

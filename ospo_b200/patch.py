@@ -16,7 +16,7 @@ from typing import Dict
 
 import torch
 
-from .head import FusedGenHead
+from .head import FusedGenHead, FusedGenImgEmbeds
 
 SM100_CLS_NAME = "vision_head_sm100"
 
@@ -33,10 +33,14 @@ def register_gen_head_cls(modeling_vlm_module) -> None:
     modeling_vlm_module.model_name_to_cls = model_name_to_cls
 
 
-def patch_model(model: torch.nn.Module) -> torch.nn.Module:
-    """replace ``model.gen_head`` in place; parameters (and their requires_grad flags) are shared"""
+def patch_model(model: torch.nn.Module, fuse_gen_img_embeds: bool = False) -> torch.nn.Module:
+    """replace ``model.gen_head`` in place; parameters (and their requires_grad flags) are shared.
+    ``fuse_gen_img_embeds`` also re-points ``model.prepare_gen_img_embeds`` (modeling_vlm.py:263-264) at the fused
+    gen_embed -> gen_aligner kernels (generation only)."""
     if not isinstance(model.gen_head, FusedGenHead):
         model.gen_head = FusedGenHead.from_reference(model.gen_head)
+    if fuse_gen_img_embeds and hasattr(model, "gen_embed") and hasattr(model, "gen_aligner"):
+        model.prepare_gen_img_embeds = FusedGenImgEmbeds(model.gen_embed, model.gen_aligner)
     return model
 
 

@@ -11,6 +11,7 @@ the reference's own lines:
   * ``JanusProTrainWrapper.get_batch_logps``   ospo/wrapper/train.py:375-396
   * ``JanusProTrainWrapper.simpo_loss``        ospo/wrapper/train.py:317-342
   * ``JanusProTrainWrapper.concatenated_forward`` / ``get_batch_loss_metrics``  train.py:345-372, 399-445
+  * ``MlpProjector`` (gen_aligner)            janus/models/projector.py:27-86
   * ``JanusProImageGenWrapper.generate_image`` ospo/wrapper/image_generation.py:109-171
     (run with a stand-in backbone; ``torch.multinomial`` is intercepted to record the ``probs`` the
     reference hands to it)
@@ -352,5 +353,27 @@ def main() -> None:
     print("wrote cfg_ref.npz: probs", tuple(probs.shape), "max p", float(probs.max()))
 
 
+def aligner_golden() -> None:
+    """real MlpProjector (projector.py) + nn.Embedding exactly as MultiModalityCausalLM.prepare_gen_img_embeds wires
+    them (modeling_vlm.py:204-216, 263-264), bf16 like the generation path (utils/model.py:39)"""
+    proj = sys.modules["janus.models.projector"]
+    torch.manual_seed(11)
+    D, CB = 128, 512
+    gen_aligner = proj.MlpProjector(_AttrDict(projector_type="mlp_gelu", depth=2, input_dim=8, n_embed=D))
+    gen_embed = torch.nn.Embedding(CB, 8)
+    gen_aligner = gen_aligner.to(torch.bfloat16)
+    gen_embed = gen_embed.to(torch.bfloat16)
+    ids = torch.randint(0, CB, (20,), generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        out = gen_aligner(gen_embed(ids))          # == prepare_gen_img_embeds(ids)
+    np.savez_compressed(
+        OUT / "aligner_ref.npz", D=D, CB=CB, ids=ids.numpy(),
+        gen_embed_bf16=_bits(gen_embed.weight), wa_bf16=_bits(gen_aligner.layers[0].weight),
+        ba_bf16=_bits(gen_aligner.layers[0].bias), wb_bf16=_bits(gen_aligner.layers[2].weight),
+        bb_bf16=_bits(gen_aligner.layers[2].bias), out_bf16=_bits(out))
+    print("wrote aligner_ref.npz:", tuple(out.shape))
+
+
 if __name__ == "__main__":
     main()
+    aligner_golden()

@@ -656,3 +656,64 @@ def test_patch_train_wrapper_end_to_end_with_llama_backbone():
     assert checked >= 10
     for n, p in head.named_parameters():
         assert _rel_fro(p.grad.float(), ref_head[n]) < 5e-2, n
+
+
+# ---------------------------------------------------------------------------------------------------
+# next row N1: prepare_gen_img_embeds = gen_aligner(gen_embed(ids))
+# ---------------------------------------------------------------------------------------------------
+def _aligner_modules(d):
+    D, CB = int(d["D"]), int(d["CB"])
+    emb = torch.nn.Embedding(CB, 8).to(torch.bfloat16)
+    al = O.GenAligner(8, D).to(torch.bfloat16)
+    with torch.no_grad():
+        emb.weight.copy_(O.bits_to_bf16(d["gen_embed_bf16"]))
+        al.layers[0].weight.copy_(O.bits_to_bf16(d["wa_bf16"]))
+        al.layers[0].bias.copy_(O.bits_to_bf16(d["ba_bf16"]))
+        al.layers[2].weight.copy_(O.bits_to_bf16(d["wb_bf16"]))
+        al.layers[2].bias.copy_(O.bits_to_bf16(d["bb_bf16"]))
+    return emb, al
+
+
+def test_gen_img_embeds_vs_reference_golden(golden_dir):
+    from ospo_b200 import FusedGenImgEmbeds
+
+    dev = _cuda()
+    d = np.load(golden_dir / "aligner_ref.npz")
+    emb, al = _aligner_modules(d)
+    fused = FusedGenImgEmbeds(emb.to(dev), al.to(dev))
+    ids = torch.from_numpy(d["ids"]).to(dev)
+    out = fused(ids)
+    torch.cuda.synchronize()
+    ref = O.bits_to_bf16(d["out_bf16"]).float()
+    assert out.shape == ref.shape and out.dtype == torch.bfloat16
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=2e-2, atol=2e-2)
+    # 2-D id tensors keep their leading shape, like nn.Embedding
+    assert fused(ids.view(4, 5)).shape == (4, 5, int(d["D"]))
+
+
+def test_gen_img_embeds_7b_shape_and_patch_model():
+    """D = 4096 (Janus-Pro-7B), 2P = 32 duplicated ids as in image_generation.py:166; patch_model wires it in"""
+    from ospo_b200 import patch_model
+
+    dev = _cuda()
+    torch.manual_seed(5)
+    D, CB, P = 4096, 16384, 16
+    model = torch.nn.Module()
+    model.gen_head = O.make_head(256, 256, CB, seed=3).to(torch.bfloat16).to(dev)
+    model.gen_embed = torch.nn.Embedding(CB, 8).to(torch.bfloat16).to(dev)
+    model.gen_aligner = O.GenAligner(8, D).to(torch.bfloat16).to(dev)
+    ref_fn = lambda ids: O.prepare_gen_img_embeds(model.gen_embed, model.gen_aligner, ids)   # noqa: E731
+    patch_model(model, fuse_gen_img_embeds=True)
+    next_token = torch.randint(0, CB, (P,), device=dev)
+    dup = torch.cat([next_token.unsqueeze(1), next_token.unsqueeze(1)], dim=1).view(-1)      # :166
+    with torch.no_grad():
+        got = model.prepare_gen_img_embeds(dup)
+        ref = ref_fn(dup)
+    torch.cuda.synchronize()
+    assert got.shape == (2 * P, D)
+    torch.testing.assert_close(got.float(), ref.float(), rtol=2e-2, atol=2e-2)
+    assert torch.equal(got[0::2], got[1::2])      # cond / uncond rows get the same embedding
+    # more than 32 ids are processed in slices
+    many = torch.randint(0, CB, (70,), device=dev)
+    with torch.no_grad():
+        torch.testing.assert_close(model.prepare_gen_img_embeds(many).float(), ref_fn(many).float(), rtol=2e-2, atol=2e-2)

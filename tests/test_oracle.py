@@ -133,3 +133,19 @@ def test_inverse_cdf_is_distributionally_multinomial():
     obs = torch.bincount(bin_of[ids], minlength=8).double()
     chi2 = float(((obs - exp) ** 2 / exp.clamp(min=1e-9)).sum())
     assert chi2 < 30.0, chi2   # 7 dof: P(chi2 > 30) ~ 1e-4
+
+
+def test_gen_img_embeds_oracle_matches_reference_golden(golden_dir):
+    """next row N1: the restated gen_aligner(gen_embed(ids)) == the reference MlpProjector + nn.Embedding, bit for bit"""
+    d = np.load(golden_dir / "aligner_ref.npz")
+    D, CB = int(d["D"]), int(d["CB"])
+    emb = torch.nn.Embedding(CB, 8).to(torch.bfloat16)
+    al = O.GenAligner(8, D).to(torch.bfloat16)
+    with torch.no_grad():
+        emb.weight.copy_(O.bits_to_bf16(d["gen_embed_bf16"]))
+        al.layers[0].weight.copy_(O.bits_to_bf16(d["wa_bf16"]))
+        al.layers[0].bias.copy_(O.bits_to_bf16(d["ba_bf16"]))
+        al.layers[2].weight.copy_(O.bits_to_bf16(d["wb_bf16"]))
+        al.layers[2].bias.copy_(O.bits_to_bf16(d["bb_bf16"]))
+        out = O.prepare_gen_img_embeds(emb, al, torch.from_numpy(d["ids"]))
+    assert torch.equal(out, O.bits_to_bf16(d["out_bf16"]))

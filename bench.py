@@ -396,8 +396,8 @@ def bench_cfg(head, dev, peaks):
     def run_steps():
         for i in range(steps):
             w = p if (i & 1) == 0 else alt
-            ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
-            ids_out[i].copy_(ids)
+            # the ids land directly in the generated-token buffer (generated_tokens[:, i], image_generation.py:164)
+            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
 
     run_steps()
     torch.cuda.synchronize()
@@ -455,10 +455,9 @@ def bench_cfg(head, dev, peaks):
         def run_steps_n1():
             for i in range(steps):
                 w = p if (i & 1) == 0 else alt
-                ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
+                ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
                 both = torch.stack([ids, ids], dim=1).view(-1)              # image_generation.py:166
                 emb_out.copy_(fused_embeds(both))                           # :167
-                ids_out[i].copy_(ids)
 
         run_steps_n1()
         torch.cuda.synchronize()

@@ -14,7 +14,7 @@
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory,
- *     including the workspace; the library never allocates or frees device memory.
+ *     including the workspace.  The library itself owns one 16 KB block of device flag words (decode kernel).
  *   - All work is enqueued asynchronously on `stream`; no call synchronises.
  *   - Weights use the nn.Linear layout [out, in], row-major, bf16.  Biases are fp32.
  *   - x / hidden states: bf16 [rows, hidden] row-major contiguous, one row per image token whose label
@@ -206,6 +206,12 @@ OSPO_API int ospo_head_set_cta_group(int cta_group);
    pdl = programmatic dependent launch along the decode kernel chain (1, default).  -1 leaves a setting
    unchanged.  Returns fused | pdl << 1. */
 OSPO_API int ospo_head_set_decode_mode(int fused, int pdl);
+/* decode step, fused form only: 1 (default) = the whole step (both GEMMs + CFG epilogue) is one persistent
+   kernel; 0 = GEMM1 and GEMM2 are separate launches.  -1 queries.  Returns the value in effect. */
+OSPO_API int ospo_head_set_decode_merged(int merged);
+/* one-kernel decode step: number of 16 KB weight k-blocks per CTA requested into L2 ahead of the shared-memory
+   ring (keeps HBM streaming through the step's dependency waits); 0 = off, -1 queries.  Returns the value in effect. */
+OSPO_API int ospo_head_set_decode_l2_ahead(int kblocks);
 /* rasterisation group size (M-blocks walked together); pass 0 to query */
 OSPO_API int ospo_head_set_group_m(int group_m);
 /* Per-kernel timing with CUDA events recorded on the caller's stream around each launch group (off by

@@ -141,6 +141,8 @@ EXPORTS = (
     "ospo_head_strerror",
     "ospo_head_set_cta_group",
     "ospo_head_set_decode_mode",
+    "ospo_head_set_decode_merged",
+    "ospo_head_set_decode_l2_ahead",
     "ospo_head_set_group_m",
     "ospo_head_profile_enable",
     "ospo_head_profile_read",
@@ -195,6 +197,10 @@ def load() -> C.CDLL:
     lib.ospo_head_set_cta_group.restype = C.c_int
     lib.ospo_head_set_decode_mode.argtypes = [C.c_int, C.c_int]
     lib.ospo_head_set_decode_mode.restype = C.c_int
+    lib.ospo_head_set_decode_merged.argtypes = [C.c_int]
+    lib.ospo_head_set_decode_merged.restype = C.c_int
+    lib.ospo_head_set_decode_l2_ahead.argtypes = [C.c_int]
+    lib.ospo_head_set_decode_l2_ahead.restype = C.c_int
     lib.ospo_head_set_group_m.argtypes = [C.c_int]
     lib.ospo_head_set_group_m.restype = C.c_int
     lib.ospo_head_profile_enable.argtypes = [C.c_int]

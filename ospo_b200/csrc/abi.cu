@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "head_kernels.cuh"
@@ -24,6 +25,10 @@ struct Runtime {
   int decode_fused = 1;  // CFG tail fused into the decode GEMM2 epilogue (0 = separate sampler pass)
   int decode_pdl = 1;    // programmatic dependent launch along the decode kernel chain
   int decode_cluster = 1;  // GEMM1 k-splits combined in-cluster through DSMEM (0 = HBM partials + finalize kernel)
+  int decode_merged = 1;   // GEMM1 + GEMM2 + CFG epilogue as one persistent kernel (0 = two GEMM launches)
+  int decode_l2_ahead = 24;  // merged kernel: W2 k-blocks per CTA requested into L2 while the activation flag is closed
+  bool trace_on = false;   // ospo_head_trace installed a timeline buffer
+  unsigned long long* trace_buf = nullptr;
   uint32_t* wd_host = nullptr;
   uint32_t* wd_dev = nullptr;
 };
@@ -86,6 +91,8 @@ int runtime_init() {
   if (const char* e = getenv("OSPO_HEAD_DECODE_FUSED")) g_rt.decode_fused = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_PDL")) g_rt.decode_pdl = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_CLUSTER")) g_rt.decode_cluster = atoi(e) != 0;
+  if (const char* e = getenv("OSPO_HEAD_DECODE_MERGED")) g_rt.decode_merged = atoi(e) != 0;
+  if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);
   if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
     const int v = atoi(e);
     if (v > 0) g_rt.group_m = v;
@@ -98,11 +105,50 @@ int runtime_init() {
       set_watchdog_bwd(g_rt.wd_dev);
       set_watchdog_decode(g_rt.wd_dev);
       set_watchdog_debug(g_rt.wd_dev);
+      set_watchdog_merged(g_rt.wd_dev);
     }
   } else {
     cudaGetLastError();
   }
   return g_rt.status = OSPO_OK;
+}
+
+// Flag words of the merged decode kernel (its device-wide "activations are published" flag).  The only device
+// memory the library owns: 16 KB, zeroed once; every kernel leaves its two words zero again.  A slot belongs to a
+// stream (launches on one stream are ordered) or, under stream capture, to the graph being captured (a graph
+// never overlaps itself), so two launches that may run concurrently never share a slot.  When the pool is
+// exhausted the caller falls back to the two-kernel chain.
+constexpr int kFlagSlots = 512, kFlagStride = 8;  // 32 bytes per slot
+uint32_t* g_flag_pool = nullptr;
+int g_flag_next = 0;
+std::unordered_map<uint64_t, int> g_flag_slot;
+
+uint32_t* flag_words_for(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  unsigned long long cap_id = 0;
+  if (cudaStreamGetCaptureInfo(st, &cs, &cap_id) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  const bool capturing = cs == cudaStreamCaptureStatusActive;
+  if (g_flag_pool == nullptr) {
+    if (capturing) return nullptr;  // cannot zero the pool while a capture is open
+    uint32_t* p = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&p), kFlagSlots * kFlagStride * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemset(p, 0, kFlagSlots * kFlagStride * sizeof(uint32_t)) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    g_flag_pool = p;
+  }
+  const uint64_t key = capturing ? (0x8000000000000000ull | cap_id) : static_cast<uint64_t>(reinterpret_cast<uintptr_t>(st));
+  auto it = g_flag_slot.find(key);
+  if (it == g_flag_slot.end()) {
+    if (g_flag_next >= kFlagSlots) return nullptr;
+    it = g_flag_slot.emplace(key, g_flag_next++).first;
+  }
+  return g_flag_pool + static_cast<size_t>(it->second) * kFlagStride;
 }
 
 LaunchCtx make_ctx(cudaStream_t s) {
@@ -112,6 +158,8 @@ LaunchCtx make_ctx(cudaStream_t s) {
   c.group_m = g_rt.group_m;
   c.stream = s;
   c.pdl = false;
+  c.trace = g_rt.trace_on;
+  c.trace_buf = g_rt.trace_buf;
   return c;
 }
 
@@ -484,6 +532,30 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
   LaunchCtx c = make_ctx(st);
   c.pdl = g_rt.decode_pdl != 0;
   const ospo_head_shape& s = a->shape;
+  const int pairs = s.rows / 2;
+  if (g_rt.decode_fused && g_rt.decode_merged && !a->merged) {
+    // whole step as one persistent kernel (W1 stream -> cluster reduction -> flag -> W2 stream + CFG epilogue)
+    uint32_t* flag = flag_words_for(st);
+    int lrc = -100;
+    if (flag != nullptr) {
+      KernelSpan ks(st, OSPO_K_DECODE_GEMM2);
+      lrc = launch_decode_merged(c, static_cast<const __nv_bfloat16*>(a->h), static_cast<const __nv_bfloat16*>(a->w.w1),
+                                 a->w.b1, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2, w.rows_by_e, flag,
+                                 static_cast<__nv_bfloat16*>(a->logits), s.rows, s.hidden, s.embed, s.vocab,
+                                 a->cfg_weight, a->temperature, a->merge_mode == OSPO_MERGE_FP32 ? 1 : 0, a->greedy,
+                                 w.fused, g_rt.decode_l2_ahead);
+    }
+    if (lrc == 0) {
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      KernelSpan ks(st, OSPO_K_SAMPLER);
+      if (launch_plain(cfg_finish_kernel, dim3(pairs), dim3(SAMPLE_THREADS), st, c.pdl, w.fused, s.vocab, a->uniforms,
+                       a->greedy, a->ids, c.trace ? 1 : 0) != cudaSuccess)
+        return OSPO_ERR_LAUNCH;
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      return OSPO_OK;
+    }
+    if (lrc != -100) return map_rc(lrc);
+  }
   {
     // W1 slabs over all SMs (split-K partials), then bias + GELU on the summed partials
     KernelSpan ks(st, OSPO_K_DECODE_GEMM1);
@@ -503,14 +575,13 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
       const float* part = w.decode_part;
       if (launch_plain(decode_act_finalize_kernel, dim3(static_cast<unsigned>((n_el / 4 + 127) / 128)), dim3(128), st,
                        c.pdl, part, decode_gemm1_splits(c.num_sms, s.hidden, s.embed), split_stride, a->w.b1,
-                       w.rows_by_e, s.rows, s.embed) != cudaSuccess)
+                       w.rows_by_e, s.rows, s.embed, c.trace ? 1 : 0) != cudaSuccess)
         return OSPO_ERR_LAUNCH;
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if ((rc = map_rc(lrc))) {
       return rc;
     }
   }
-  const int pairs = s.rows / 2;
   if (g_rt.decode_fused && !a->merged) {
     {
       KernelSpan ks(st, OSPO_K_DECODE_GEMM2);
@@ -522,7 +593,7 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
     if (rc) return rc;
     KernelSpan ks(st, OSPO_K_SAMPLER);
     if (launch_plain(cfg_finish_kernel, dim3(pairs), dim3(SAMPLE_THREADS), st, c.pdl, w.fused, s.vocab, a->uniforms,
-                     a->greedy, a->ids) != cudaSuccess)
+                     a->greedy, a->ids, c.trace ? 1 : 0) != cudaSuccess)
       return OSPO_ERR_LAUNCH;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return OSPO_OK;
@@ -594,6 +665,18 @@ int ospo_head_set_decode_mode(int fused, int pdl) {
   return g_rt.decode_fused | (g_rt.decode_pdl << 1);
 }
 
+int ospo_head_set_decode_merged(int merged) {
+  runtime_init();
+  if (merged == 0 || merged == 1) g_rt.decode_merged = merged;
+  return g_rt.decode_merged;
+}
+
+int ospo_head_set_decode_l2_ahead(int kblocks) {
+  runtime_init();
+  if (kblocks >= 0) g_rt.decode_l2_ahead = kblocks;
+  return g_rt.decode_l2_ahead;
+}
+
 int ospo_head_set_group_m(int group_m) {
   runtime_init();
   if (group_m > 0) g_rt.group_m = group_m;
@@ -640,10 +723,13 @@ int ospo_head_profile_read(float* total_ms, int32_t* counts, int32_t n) {
 }
 
 int ospo_head_trace(void* device_buf) {
-  // tuning aid: [5][160][8] u64 globaltimer stamps of the decode chain's CTAs (NULL switches it off)
+  // tuning aid: [8][160][8] u64 globaltimer stamps of the decode chain's CTAs (NULL switches it off)
   runtime_init();
   unsigned long long* p = static_cast<unsigned long long*>(device_buf);
   set_trace_decode(p);
+  set_trace_merged(p);
+  g_rt.trace_on = p != nullptr;
+  g_rt.trace_buf = p;
   return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)) == cudaSuccess ? OSPO_OK : OSPO_ERR_CUDA;
 }
 

@@ -1,0 +1,468 @@
+// One persistent kernel for a whole CFG decode step of the image-token head:
+//
+//   phase 1   act[n, E]   = bf16(gelu(bf16(h W1^T + b1)))           (swap-AB, cluster split-K through DSMEM)
+//   -------   device-wide flag: every slice of act is in global memory
+//   phase 2   D[V, n]     = W2 act^T + b2  -> CFG merge, softmax weights, segment sums (EpiCfgFused)
+//
+// reference: gen_head(hidden_states[:, -1, :]) + CFG merge + softmax, ospo/wrapper/image_generation.py:156-162.
+//
+// Why one kernel: the step is a pure weight stream (W1 then W2, 168 MB for the 7B head) with a true dependency in
+// the middle.  As two kernels the W2 stream cannot start before the last CTA of the first kernel has left its SM;
+// here the TMA producer of every CTA runs straight on from its W1 slab into its W2 slab -- the A (weight) halves of
+// up to a ring-full of phase-2 stages are requested while the cluster reduction, the activation and the flag are
+// still in progress, and only the tiny B (activation) halves wait for the flag.
+//
+// Grid: G CTAs in clusters of `ks` (the phase-1 k-splits of one 128-row slab of W1); one CTA per SM, all resident
+// (checked on the host with the occupancy API -- the flag wait needs every phase-1 CTA to be running).
+#include "epilogues.cuh"
+#include "launchers.h"
+
+namespace ospo {
+
+void set_watchdog_merged(uint32_t* dev_ptr) { cudaMemcpyToSymbol(g_watchdog_buf, &dev_ptr, sizeof(dev_ptr)); }
+void set_trace_merged(unsigned long long* dev_ptr) { cudaMemcpyToSymbol(g_trace_buf, &dev_ptr, sizeof(dev_ptr)); }
+
+namespace {
+
+constexpr int kBM = 128, kBN = 32, kBK = 64, kUmmaK = 16;
+constexpr int kStages = 10;
+constexpr int kABytes = kBM * kBK * 2;   // 16 KB weight tile
+constexpr int kBBytes = kBN * kBK * 2;   // 4 KB activation tile
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kPartBytes = kBN * kBM * 4;  // gather buffer for the cluster's partials [split][128 rows][32 / splits]
+constexpr int kEpiBytes = 1024;
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256 + kEpiBytes + kPartBytes;
+constexpr int kThreads = 224;  // warp 0 weight producer, 1 MMA issuer, 2-5 epilogue, 6 activation producer
+constexpr int kTmemCols = 64;  // two 32-column accumulators
+
+enum : uint32_t {
+  SITE_M_PRODUCER_EMPTY = 11,
+  SITE_M_MMA_FULL = 12,
+  SITE_M_MMA_TMEM_EMPTY = 13,
+  SITE_M_EPI_TMEM_FULL = 14,
+  SITE_M_PART_READY = 15,
+  SITE_M_FLAG = 16,
+  SITE_M_FLAG_STATE = 17,
+};
+
+struct MergedDims {
+  int n, H, E, V;
+  int ks;            // cluster size = phase-1 k-splits (1, 2, 4, 8)
+  int kb_per_split;  // phase-1 k-blocks per split
+  int num_m1;        // 128-row slabs of W1
+  int num_m2;        // 128-row slabs of W2
+  const float* b1;
+  __nv_bfloat16* act;   // [n, E]
+  uint32_t* flag;       // [0] phase-1 arrivals, [1] CTA exits; both zero between launches
+  int l2_ahead;         // weight k-blocks requested into L2 ahead of the shared-memory ring (0 = off)
+  unsigned long long* trace;  // timeline buffer [8][160][8] or null (a kernel parameter: stamps cost one store)
+};
+
+__device__ __forceinline__ void stamp(unsigned long long* buf, int row, int slot) {
+  if (buf != nullptr && blockIdx.x < kTraceCtas)
+    buf[(static_cast<size_t>(row) * kTraceCtas + blockIdx.x) * kTraceSlots + slot] = globaltimer_ns();
+}
+
+template <int MODE, bool TDIV>
+__global__ void __launch_bounds__(kThreads, 1)
+decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_h,
+                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_act,
+                     MergedDims d, typename EpiCfgFused<MODE, TDIV>::Params ep) {
+  using Epi = EpiCfgFused<MODE, TDIV>;
+  constexpr int tr1 = 1, tr2 = 2;
+  if (threadIdx.x == 0) stamp(d.trace, tr1, 0);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* part_ready_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_ready_bar + 1);
+  uint8_t* epi_smem = smem + kStages * kStageBytes + 256;
+  float* part = reinterpret_cast<float*>(epi_smem + kEpiBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = static_cast<int>(gridDim.x);
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = static_cast<int>(blockIdx.x) / d.ks;
+
+  // phase-1 work of this CTA: k-blocks [kb0, kb1) of W1 slab `cluster_id`
+  const int num_kb1 = (d.H + kBK - 1) / kBK;
+  const bool has1 = cluster_id < d.num_m1;
+  const int kb0 = rank * d.kb_per_split;
+  const int n1 = has1 ? max(0, min(num_kb1, kb0 + d.kb_per_split) - kb0) : 0;
+  // phase-2 work: W2 slabs blockIdx.x, blockIdx.x + G, ...
+  const int num_kb2 = (d.E + kBK - 1) / kBK;
+  const int tiles2 = (static_cast<int>(blockIdx.x) < d.num_m2) ? (d.num_m2 - 1 - static_cast<int>(blockIdx.x)) / G + 1 : 0;
+  const int total = n1 + tiles2 * num_kb2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w1);
+    tma_prefetch_desc(&tmap_h);
+    tma_prefetch_desc(&tmap_w2);
+    tma_prefetch_desc(&tmap_act);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    mbar_init(part_ready_bar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(part_ready_bar, kPartBytes);  // the cluster pushes one full 32 x 128 fp32 tile into this CTA
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc<1>(tmem_slot, kTmemCols);
+  }
+  tc_fence_before();
+  cluster_sync();  // peers' barriers are initialised before anyone arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  if (threadIdx.x == 0) stamp(d.trace, 3, 0);
+
+  // The CTA's k-blocks form one sequence: n1 blocks of W1 (B = h, needs the predecessor kernel), then the blocks
+  // of its W2 slabs (B = act, needs the device-wide flag).  The weight (A) halves and the activation (B) halves are
+  // issued by different warps: one thread cannot issue two TMA boxes per 16 KB fast enough to keep HBM saturated,
+  // and the A stream must not stop while a B dependency is open -- it simply runs up to a ring-full ahead.
+  if (warp == 0) {
+    // ===================== weight (A) producer =====================
+    if (elect_one()) {
+      int slot = 0, use = 0, k = kb0 * kBK, left = n1, row = cluster_id * kBM;
+      bool p1 = n1 > 0;
+      if (!p1) {
+        k = 0;
+        left = num_kb2;
+        row = static_cast<int>(blockIdx.x) * kBM;
+      }
+      for (int i = 0; i < total; ++i) {
+        if (use > 0) mbar_wait(&empty_bar[slot], static_cast<uint32_t>(use - 1) & 1u, SITE_M_PRODUCER_EMPTY);
+        mbar_arrive_expect_tx(&full_bar[slot], kStageBytes);  // covers the B half issued by warp 6
+        tma_load_2d(stage_base + slot * kStageBytes, p1 ? &tmap_w1 : &tmap_w2, &full_bar[slot], k, row, kEvictNormal);
+        k += kBK;
+        if (--left == 0) {  // next item: a W2 slab
+          row = p1 ? static_cast<int>(blockIdx.x) * kBM : row + G * kBM;
+          p1 = false;
+          k = 0;
+          left = num_kb2;
+        }
+        if (++slot == kStages) {
+          slot = 0;
+          ++use;
+        }
+        if (i + 1 == min(total, kStages)) stamp(d.trace, tr1, 1);
+        if (i == n1 + kStages - 1 && d.l2_ahead > 0) {
+          // The ring now holds only phase-2 weight tiles and this thread is about to block until the activation
+          // flag opens.  HBM would idle through that wait: ask for the next l2_ahead tiles of the slab to be
+          // brought into L2 meanwhile (same coordinates the loop will load next; `left` tiles remain in the slab).
+          const int ahead = min(d.l2_ahead, left);
+          for (int j = 0; j < ahead; ++j) tma_prefetch_l2_2d(&tmap_w2, k + j * kBK, row);
+        }
+      }
+      stamp(d.trace, tr2, 3);
+    }
+  } else if (warp == 6) {
+    // ===================== activation (B) producer =====================
+    if (elect_one()) {
+      int slot = 0, use = 0, k = kb0 * kBK, left = n1;
+      bool p1 = n1 > 0;
+      if (!p1) {
+        k = 0;
+        left = num_kb2;
+      }
+      pdl_wait();  // h comes from the predecessor kernel
+      stamp(d.trace, tr1, 2);
+      bool flag_seen = false;
+      auto wait_flag = [&]() {
+        // every phase-1 CTA has published its slice of act (and is therefore done reading its peers' partials)
+        const uint32_t want = static_cast<uint32_t>(d.num_m1 * d.ks);
+        uint64_t t0 = 0;
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(d.flag) < want) {
+          if (t0 == 0) t0 = globaltimer_ns();
+          if (((++spins) & 0xFFu) == 0u && globaltimer_ns() - t0 > OSPO_WATCHDOG_NS)
+            watchdog_fire(SITE_M_FLAG, ld_acquire_gpu(d.flag), want);
+        }
+        fence_proxy_async_all();  // act was written by ordinary stores; it is read by TMA
+        pdl_launch_dependents();  // every CTA is resident and past its dependency: the finish kernel may queue up
+        // This CTA never looks at the flag again.  The last CTA to get here re-arms both words for the next launch
+        // (every phase-1 arrival has happened -- the flag is open -- and every other CTA has finished polling).
+        if (atomicAdd(d.flag + 1, 1u) == static_cast<uint32_t>(G) - 1u) {
+          d.flag[0] = 0u;
+          d.flag[1] = 0u;
+        }
+        stamp(d.trace, tr1, 7);
+        stamp(d.trace, tr2, 0);
+        flag_seen = true;
+      };
+      for (int i = 0; i < total; ++i) {
+        if (!p1 && !flag_seen) wait_flag();
+        // the slot's previous contents must have been consumed (same condition the A producer waits for)
+        if (use > 0) mbar_wait(&empty_bar[slot], static_cast<uint32_t>(use - 1) & 1u, SITE_M_PRODUCER_EMPTY);
+        uint8_t* sb = stage_base + slot * kStageBytes + kABytes;
+        if (p1) tma_load_2d(sb, &tmap_h, &full_bar[slot], k, 0, kEvictNormal);
+        else tma_load_2d(sb, &tmap_act, &full_bar[slot], k, 0, kEvictLast);
+        k += kBK;
+        if (--left == 0) {
+          if (p1) stamp(d.trace, tr1, 3);
+          p1 = false;
+          k = 0;
+          left = num_kb2;
+        }
+        if (++slot == kStages) {
+          slot = 0;
+          ++use;
+        }
+      }
+      if (!flag_seen) wait_flag();  // a CTA without phase-2 work still takes part in re-arming the flag words
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, false, false);
+    int i = 0;  // position in the k-block sequence
+    const int items = (has1 ? 1 : 0) + tiles2;
+    for (int it = 0; it < items; ++it) {
+      const int as = it & 1;
+      const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+      mbar_wait(&tmem_empty_bar[as], aph ^ 1u, SITE_M_MMA_TMEM_EMPTY);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kBN);
+      const int nkb = (has1 && it == 0) ? n1 : num_kb2;
+      for (int kb = 0; kb < nkb; ++kb, ++i) {
+        const int slot = i % kStages;
+        mbar_wait(&full_bar[slot], static_cast<uint32_t>(i / kStages) & 1u, SITE_M_MMA_FULL);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(stage_base + slot * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 0, 1024);
+            umma_bf16<1>(d_tmem, adesc, bdesc, idesc, (kb != 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[slot]);
+          if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue warps =====================
+    pdl_wait();  // the buffers written below are still being read by the previous step's finish kernel
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row inside a 128-row slab = TMEM lane
+    int it = 0;
+    if (has1) {
+      // ---- phase 1: exchange the partial tiles inside the cluster, add them, publish the activations ----
+      const int e = cluster_id * kBM + r;
+      const float b = (e < d.E) ? __ldg(d.b1 + e) : 0.0f;  // in flight while the accumulator is still being built
+      mbar_wait(&tmem_full_bar[0], 0u, SITE_M_EPI_TMEM_FULL);
+      tc_fence_after();
+      if (threadIdx.x == 64) stamp(d.trace, tr1, 4);
+      uint32_t ra[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), ra);
+      tmem_ld_wait(ra);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[0]);
+      // Push model: CTA j of the cluster owns columns [j * per, (j + 1) * per).  Every thread sends its row's values
+      // for those columns straight from registers into the owner's gather buffer [split][row][per] with st.async;
+      // the bytes complete on the owner's mbarrier, so no fence, no remote arrive and no remote load is needed.
+      const int per = kBN / d.ks;                       // 32, 16, 8 or 4
+      const int per_shift = 31 - __clz(per);
+      const uint32_t gather_local = smem_u32(part) + static_cast<uint32_t>((rank * kBM + r) * per) * 4u;
+      const uint32_t bar_local = smem_u32(part_ready_bar);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t owner = static_cast<uint32_t>((4 * g) >> per_shift);
+        const uint32_t within = static_cast<uint32_t>((4 * g) & (per - 1));
+        st_async_v4(mapa_shared(gather_local + within * 4u, owner), ra[4 * g], ra[4 * g + 1], ra[4 * g + 2], ra[4 * g + 3],
+                    mapa_shared(bar_local, owner));
+      }
+      if (threadIdx.x == 64) stamp(d.trace, tr1, 5);
+      mbar_wait(part_ready_bar, 0u, SITE_M_PART_READY);
+      if (threadIdx.x == 64) stamp(d.trace, 3, 1);
+      // this CTA's share of the 32 columns, partials added in split order (deterministic)
+      const int c_lo = rank * per;
+      if (e < d.E) {
+        for (int c4 = 0; c4 < per; c4 += 4) {
+          float4 acc = *reinterpret_cast<const float4*>(part + r * per + c4);
+          for (int k = 1; k < d.ks; ++k) {
+            const float4 o = *reinterpret_cast<const float4*>(part + (k * kBM + r) * per + c4);
+            acc.x += o.x;
+            acc.y += o.y;
+            acc.z += o.z;
+            acc.w += o.w;
+          }
+          const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = c_lo + c4 + t;
+            if (c < d.n) {
+              const float x = bf16_round(a4[t] + b);
+              d.act[static_cast<int64_t>(c) * d.E + e] = __float2bfloat16_rn(gelu_erf(x));
+            }
+          }
+        }
+      }
+      if (threadIdx.x == 64) stamp(d.trace, 3, 2);
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 64) {
+        // release at device scope is cumulative over the stores the barrier above has ordered before it
+        fence_proxy_async_all();
+        const uint32_t old = atom_add_release_gpu(d.flag, 1u);
+        if (old >= static_cast<uint32_t>(d.num_m1 * d.ks)) watchdog_fire(SITE_M_FLAG_STATE, old, 0u);  // dirty flag words
+        stamp(d.trace, tr1, 6);
+      }
+      it = 1;
+    }
+    // ---- phase 2: fused CFG epilogue on every W2 slab of this CTA ----
+    GemmDims gd = {};
+    gd.M = d.V;
+    gd.N = d.n;
+    gd.K = d.E;
+    gd.trace_id = 0;
+    const bool full = (d.n == kBN);
+    for (int t = 0; t < tiles2; ++t, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+      const int row = (static_cast<int>(blockIdx.x) + t * G) * kBM + r;
+      typename Epi::State st;
+      Epi::begin(ep, st, row, 0, 0, gd, epi_smem);  // bias load overlaps the wait
+      mbar_wait(&tmem_full_bar[as], aph, SITE_M_EPI_TMEM_FULL);
+      tc_fence_after();
+      if (threadIdx.x == 64) stamp(d.trace, tr2, 4);
+      uint32_t ra[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * kBN), ra);
+      tmem_ld_wait(ra);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // the accumulator is in registers
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+      if (full) Epi::template chunk<true>(ep, st, row, 0, v, gd, epi_smem);
+      else Epi::template chunk<false>(ep, st, row, 0, v, gd, epi_smem);
+      Epi::end(ep, st, row, 0, 0, gd, epi_smem);
+      if (threadIdx.x == 64) stamp(d.trace, tr2, 5);
+    }
+  }
+
+  // ===================== teardown =====================
+  __syncwarp();
+  tc_fence_before();
+  if (threadIdx.x == 0) stamp(d.trace, 3, 3);
+  // No cluster barrier here: the partial tiles pushed into this CTA were complete before it published its
+  // activations, and it pushes nothing after that -- no peer touches this CTA's shared memory any more.
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, kTmemCols);
+  }
+  if (threadIdx.x == 0) {
+    stamp(d.trace, 3, 4);
+  }
+}
+
+template <int MODE, bool TDIV>
+int run_merged(const LaunchCtx& c, const CUtensorMap& t_w1, const CUtensorMap& t_h, const CUtensorMap& t_w2,
+               const CUtensorMap& t_act, const MergedDims& d, int G, const float* b2, __nv_bfloat16* logits_dump,
+               float cfg_weight, float temperature, int greedy, const CfgFusedBuffers& buf) {
+  using Epi = EpiCfgFused<MODE, TDIV>;
+  typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, d.V, buf, greedy, d.V};
+  auto kern = decode_merged_kernel<MODE, TDIV>;
+  static bool attr_set = false;
+  static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // by cluster size
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -3;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(G), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = static_cast<unsigned>(d.ks);
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  if (max_clusters[d.ks] == 0) {
+    // the flag wait needs all G CTAs running at once: ask the driver how many clusters of this size fit
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      nc = -1;
+    }
+    max_clusters[d.ks] = nc > 0 ? nc : -1;
+  }
+  if (max_clusters[d.ks] * d.ks < G) return -100;
+  if (c.pdl) {
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, t_w1, t_h, t_w2, t_act, d, p) == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace
+
+int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
+                         const __nv_bfloat16* w2, const float* b2, __nv_bfloat16* act, uint32_t* flag,
+                         __nv_bfloat16* logits_dump, int n, int H, int E, int V, float cfg_weight, float temperature,
+                         int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead) {
+  if (n < 2 || n > kBN || flag == nullptr) return -100;
+  MergedDims d;
+  d.n = n;
+  d.H = H;
+  d.E = E;
+  d.V = V;
+  d.num_m1 = (E + kBM - 1) / kBM;
+  d.num_m2 = (V + kBM - 1) / kBM;
+  int ks = decode_gemm1_splits(c.num_sms, H, E);
+  ks = ks >= 8 ? 8 : ks >= 4 ? 4 : ks >= 2 ? 2 : 1;  // cluster sizes
+  int per;
+  gemm_split_plan((H + kBK - 1) / kBK, ks, &ks, &per);
+  if (ks != 1 && ks != 2 && ks != 4 && ks != 8) return -100;
+  d.ks = ks;
+  d.kb_per_split = per;
+  d.b1 = b1;
+  d.act = act;
+  d.flag = flag;
+  d.trace = c.trace ? c.trace_buf : nullptr;
+  d.l2_ahead = l2_ahead < 0 ? 0 : l2_ahead;
+  const int max_ctas = (c.num_sms / ks) * ks;
+  const int need1 = d.num_m1 * ks;
+  if (need1 > max_ctas) return -100;
+  int G = d.num_m2 < max_ctas ? ((d.num_m2 + ks - 1) / ks) * ks : max_ctas;
+  if (G < need1) G = need1;
+  CUtensorMap t_w1, t_h, t_w2, t_act;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&t_w1, w1, E, H, H, kBM)) != 0) return rc;
+  if ((rc = make_tmap_bf16_2d(&t_h, h, n, H, H, kBN)) != 0) return rc;
+  if ((rc = make_tmap_bf16_2d(&t_w2, w2, V, E, E, kBM)) != 0) return rc;
+  if ((rc = make_tmap_bf16_2d(&t_act, act, n, E, E, kBN)) != 0) return rc;
+  const bool tdiv = (temperature != 1.0f);
+  if (merge_mode == 0) {
+    if (tdiv)
+      return run_merged<0, true>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
+    return run_merged<0, false>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
+  }
+  if (tdiv)
+    return run_merged<1, true>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
+  return run_merged<1, false>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
+}
+
+}  // namespace ospo

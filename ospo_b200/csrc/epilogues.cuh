@@ -521,6 +521,8 @@ struct EpiCfgFused {
     float* sm_k = reinterpret_cast<float*>(smem);  // [4][16]
     float* sm_v = sm_k + 64;                       // [4][16] greedy value
     int* sm_i = reinterpret_cast<int*>(sm_v + 64);  // [4][16] greedy index
+    const int tr = (d.trace_id > 0 && threadIdx.x == 64) ? 5 : 0;  // epilogue-internal timeline (trace row 5)
+    trace_stamp(tr, 0);
     // logits exactly as the reference's bf16 Linear output
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
@@ -538,6 +540,7 @@ struct EpiCfgFused {
     for (int k = 0; k < 16; k += 2)
       cfg_merge_vals<MODE, TDIV>(v[2 * k], v[2 * k + 2], v[2 * k + 1], v[2 * k + 3], p.cfg_weight, p.temperature, t[k],
                                  t[k + 1]);
+    trace_stamp(tr, 1);
     if (p.greedy) {
       // per-pair arg-max over the tile: (value, code) with the lowest code on ties
 #pragma unroll
@@ -586,7 +589,9 @@ struct EpiCfgFused {
       const float kw = warp_transpose_reduce16(nn, lane, OpMax());
       if ((lane & 1) == 0) sm_k[q * 16 + mypair] = kw;
     }
+    trace_stamp(tr, 2);
     named_bar_sync(1, 128);
+    trace_stamp(tr, 3);
     float u[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -598,6 +603,7 @@ struct EpiCfgFused {
     }
     // segment sums: the warp is one 32-code segment; the transpose-reduce adds lanes in the oracle's butterfly
     // order (strides 16, 8, 4, 2, 1)
+    trace_stamp(tr, 4);
     const float ssum = warp_transpose_reduce16(u, lane, OpSum());
     if ((lane & 1) == 0 && mypair < npairs) {
       p.buf.seg_sum[static_cast<int64_t>(pair0 + mypair) * (p.vocab / SAMPLE_SEG) + row / SAMPLE_SEG] = ssum;
@@ -605,7 +611,9 @@ struct EpiCfgFused {
         p.buf.tile_k[static_cast<int64_t>(pair0 + mypair) * ntile + tile] =
             fmaxf(fmaxf(sm_k[mypair], sm_k[16 + mypair]), fmaxf(sm_k[32 + mypair], sm_k[48 + mypair]));
     }
+    trace_stamp(tr, 5);
     named_bar_sync(1, 128);  // smem is reused by the next tile of a persistent CTA
+    trace_stamp(tr, 6);
   }
   __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
 };

@@ -32,7 +32,7 @@ int launch_decode_gemm1(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_b
   // D[E, n] = W1[E, H] * h[n, H]^T, as k-split partials part[ks][n][E]
   if (n <= 32)
     return launch_gemm<CfgS32, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl, SegOperand(),
-                                    SegOperand(), 1);
+                                    SegOperand(), c.trace ? 1 : 0);
   return launch_gemm<CfgS128, Epi>(w1, H, h, H, E, n, H, 1 << 20, p, c.num_sms, c.stream, ks, c.pdl);
 }
 
@@ -55,7 +55,7 @@ static int run_linear_cluster(const LaunchCtx& c, const __nv_bfloat16* x, const 
 
 int launch_decode_gemm1_cluster(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
                                 __nv_bfloat16* act, int n, int H, int E) {
-  return run_linear_cluster<true>(c, h, w1, b1, act, n, H, E, 1);
+  return run_linear_cluster<true>(c, h, w1, b1, act, n, H, E, c.trace ? 1 : 0);
 }
 
 int launch_decode_linear_cluster(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* b,
@@ -86,7 +86,7 @@ static int run_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bf
   typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, V, buf, greedy, V};
   // D[V, n] = W2[V, E] * act[n, E]^T; the epilogue consumes the tile in place
   return launch_gemm<CfgF32, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream, 1, c.pdl, SegOperand(),
-                                  SegOperand(), 2);
+                                  SegOperand(), c.trace ? 2 : 0);
 }
 
 int launch_decode_gemm2_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,

@@ -269,11 +269,12 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, in
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 decode_act_finalize_kernel(const float* __restrict__ part, int k_splits, int64_t split_stride,
-                           const float* __restrict__ b1, __nv_bfloat16* __restrict__ act, int n, int E) {
+                           const float* __restrict__ b1, __nv_bfloat16* __restrict__ act, int n, int E,
+                           int trace) {
   pdl_launch_dependents();  // the next GEMM may become resident and prefetch its weights; it waits for us
-  if (threadIdx.x == 0) trace_stamp(3, 0);
+  if (threadIdx.x == 0) trace_stamp(trace ? 3 : 0, 0);
   pdl_wait();
-  if (threadIdx.x == 0) trace_stamp(3, 2);
+  if (threadIdx.x == 0) trace_stamp(trace ? 3 : 0, 2);
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= static_cast<int64_t>(n) * E) return;
   float4 s = __ldcg(reinterpret_cast<const float4*>(part + i));
@@ -292,7 +293,7 @@ decode_act_finalize_kernel(const float* __restrict__ part, int k_splits, int64_t
   o.x = pack_bf16x2(x[0], x[1]);
   o.y = pack_bf16x2(x[2], x[3]);
   *reinterpret_cast<uint2*>(act + i) = o;
-  if (threadIdx.x == 0) trace_stamp(3, 5);
+  if (threadIdx.x == 0) trace_stamp(trace ? 3 : 0, 5);
 }
 
 // ---------------------------------------------------------------------------
@@ -519,14 +520,14 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
 
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ uniforms, int greedy,
-                  int64_t* __restrict__ ids) {
+                  int64_t* __restrict__ ids, int trace) {
   __shared__ float seg_sum[SAMPLE_THREADS];
   __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
   __shared__ float wmax[SAMPLE_THREADS / 32];
   pdl_launch_dependents();  // successors may become resident and prefetch; they wait for our completion
-  if (threadIdx.x == 0) trace_stamp(4, 0);
+  if (threadIdx.x == 0) trace_stamp(trace ? 4 : 0, 0);
   pdl_wait();
-  if (threadIdx.x == 0) trace_stamp(4, 2);
+  if (threadIdx.x == 0) trace_stamp(trace ? 4 : 0, 2);
   const int p = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -601,7 +602,7 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
     }
     if (lane == 0) {
       ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
-      trace_stamp(4, 5);
+      trace_stamp(trace ? 4 : 0, 5);
     }
   }
 }

@@ -15,6 +15,8 @@ struct LaunchCtx {
   int group_m;    // rasterisation group (M-blocks)
   cudaStream_t stream;
   bool pdl;       // launch with programmatic stream serialization (decode chain)
+  bool trace = false;  // timeline stamps on (ospo_head_trace); off = the stamps compile to a parameter test
+  unsigned long long* trace_buf = nullptr;  // the installed timeline buffer (merged decode kernel stamps through it)
 };
 
 struct CfgFusedBuffers;
@@ -34,6 +36,8 @@ void set_watchdog_bwd(uint32_t* dev_ptr);
 void set_watchdog_decode(uint32_t* dev_ptr);
 void set_watchdog_debug(uint32_t* dev_ptr);
 void set_trace_decode(unsigned long long* dev_ptr);
+void set_watchdog_merged(uint32_t* dev_ptr);
+void set_trace_merged(unsigned long long* dev_ptr);
 
 // ---- forward (gemm_fwd.cu) ----
 // pre = bf16(x W1^T + b1), act = bf16(gelu(pre));  x [rows,H], w1 [E,H]
@@ -84,6 +88,16 @@ int launch_decode_gemm2(const LaunchCtx& c, const __nv_bfloat16* act, const __nv
 int launch_decode_gemm2_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                               __nv_bfloat16* logits_dump, int n, int E, int V, float cfg_weight, float temperature,
                               int merge_mode, int greedy, const CfgFusedBuffers& buf);
+
+// ---- decode, one persistent kernel (decode_merged.cu) ----
+// act = gelu(h W1^T + b1) (cluster split-K), device-wide flag, then W2 act^T + b2 with the fused CFG epilogue.
+// flag: two zeroed words owned by this launch's stream (see abi.cu); the kernel leaves them zero.
+// l2_ahead: weight k-blocks (16 KB each, per CTA) requested into L2 ahead of the shared-memory ring.
+// Returns -100 when the shape / occupancy does not allow every CTA to be resident at once.
+int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
+                         const __nv_bfloat16* w2, const float* b2, __nv_bfloat16* act, uint32_t* flag,
+                         __nv_bfloat16* logits_dump, int n, int H, int E, int V, float cfg_weight, float temperature,
+                         int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead);
 
 // ---- debug / validation (gemm_debug.cu) ----
 // out[M,N] fp32 = A B^T for one engine variant; see abi.cu for the variant table

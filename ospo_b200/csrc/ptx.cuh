@@ -122,6 +122,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   }
 }
 
+// wait on a barrier whose arrivals come from other CTAs of the cluster (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t site) {
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (t0 == 0) t0 = globaltimer_ns();
+    if (((++spins) & 0x3FFu) == 0u) {
+      if (globaltimer_ns() - t0 > OSPO_WATCHDOG_NS) watchdog_fire(site, smem_u32(bar), parity);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// device-wide flag words (grid barrier of the merged decode kernel)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* p, uint32_t x) {
+  uint32_t old;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
+  return old;
+}
+// orders generic-proxy accesses (ordinary loads / stores) against async-proxy accesses (TMA) in all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------
@@ -133,6 +172,12 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+// fire-and-forget request that brings one box of a 2-D tensor into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1)
+               : "memory");
+}
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             uint64_t hint) {
@@ -219,6 +264,16 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // named barrier among a subset of the CTA's warps (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 16-byte store into the shared memory of a CTA of the cluster (possibly this one); the bytes are counted on the
+// destination CTA's mbarrier, whose waiters then see the data (no fence needed on either side)
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t cluster_bar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   cluster_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar_addr)
+               : "memory");
 }
 
 // fp32 load from the shared memory of another CTA of the cluster (address from mapa_shared)

@@ -278,10 +278,11 @@ class FusedGenHead(torch.nn.Module):
     @torch.no_grad()
     def cfg_sample(self, hidden_last: torch.Tensor, cfg_weight: float = 5.0, temperature: float = 1.0,
                    uniforms: Optional[torch.Tensor] = None, greedy: bool = False, merge_mode: str = "bf16",
-                   return_logits: bool = False):
+                   return_logits: bool = False, out: Optional[torch.Tensor] = None):
         """One decode step (image_generation.py:156-164): hidden_last [2P, H] with row 2k conditional and
         2k+1 unconditional -> next_token ids [P] int64.  ``uniforms`` [P] fp32 in [0,1) drive the inverse-CDF
-        draw (None => drawn from torch's CUDA generator); ``greedy`` takes the arg-max instead."""
+        draw (None => drawn from torch's CUDA generator); ``greedy`` takes the arg-max instead; ``out`` (int64
+        [P], e.g. a row of the generated-token buffer) receives the ids without a copy."""
         p = self._kernel_params()
         h = hidden_last.to(torch.bfloat16).contiguous()
         P = h.shape[0] // 2
@@ -293,7 +294,7 @@ class FusedGenHead(torch.nn.Module):
             u = uniforms.to(torch.float32).contiguous()
         mm = _abi.MERGE_BF16 if merge_mode == "bf16" else _abi.MERGE_FP32
         ids, logits = ops.cfg_sample_impl(h, p.w1, p.b1, p.w2, p.b2, float(cfg_weight), float(temperature), u,
-                                          bool(greedy), mm, bool(return_logits))
+                                          bool(greedy), mm, bool(return_logits), out)
         return (ids, logits) if return_logits else ids
 
 

@@ -8,7 +8,7 @@ implementation is registered: calling an op with CPU tensors fails in the dispat
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 
@@ -221,8 +221,9 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
 # CFG decode step
 # --------------------------------------------------------------------------------------------------
 def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, cfg_weight: float, temperature: float,
-               uniforms: Tensor, greedy: bool, merge_mode: int, want_logits: bool = False) -> List[Tensor]:
-    """-> [ids[P] int64, logits[2P, V] bf16 (empty unless want_logits)]
+               uniforms: Tensor, greedy: bool, merge_mode: int, want_logits: bool = False,
+               out: Optional[Tensor] = None) -> List[Tensor]:
+    """-> [ids[P] int64 (``out`` if given: the kernel writes the ids there), logits[2P, V] bf16 (empty unless want_logits)]
     (image_generation.py:156-164; row 2k cond / 2k+1 uncond).  Without want_logits the logits never leave the
     chip: the CFG merge, softmax weights and segment sums are produced in the GEMM epilogue."""
     _check_cuda(h, uniforms)
@@ -233,7 +234,11 @@ def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, c
     dev = h.device
     if not greedy:
         assert uniforms.dtype == torch.float32 and uniforms.numel() == P and uniforms.is_contiguous()
-    ids = torch.empty(P, dtype=torch.int64, device=dev)
+    if out is not None:
+        assert out.dtype == torch.int64 and out.numel() == P and out.is_contiguous() and out.device == dev
+        ids = out
+    else:
+        ids = torch.empty(P, dtype=torch.int64, device=dev)
     logits = torch.empty(rows, V, dtype=torch.bfloat16, device=dev) if want_logits else None
     ws = _workspace(rows, H, E, V, 1, dev)
     a = _abi.CfgArgs()
@@ -311,7 +316,12 @@ logps_fwd = torch.library.custom_op("ospo_head::logps_fwd", logps_fwd_impl, muta
 simpo_fwd = torch.library.custom_op("ospo_head::simpo_fwd", simpo_fwd_impl, mutates_args=(), device_types="cuda")
 head_bwd = torch.library.custom_op("ospo_head::head_bwd", head_bwd_impl, mutates_args=("logits", "flat_grads"),
                                    device_types="cuda")
-cfg_sample = torch.library.custom_op("ospo_head::cfg_sample", cfg_sample_impl, mutates_args=(), device_types="cuda")
+def _cfg_sample_op(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, cfg_weight: float, temperature: float,
+                   uniforms: Tensor, greedy: bool, merge_mode: int, want_logits: bool = False) -> List[Tensor]:
+    return cfg_sample_impl(h, w1, b1, w2, b2, cfg_weight, temperature, uniforms, greedy, merge_mode, want_logits)
+
+
+cfg_sample = torch.library.custom_op("ospo_head::cfg_sample", _cfg_sample_op, mutates_args=(), device_types="cuda")
 cfg_merge_sample = torch.library.custom_op("ospo_head::cfg_merge_sample", cfg_merge_sample_impl, mutates_args=(),
                                            device_types="cuda")
 

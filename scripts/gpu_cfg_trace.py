@@ -24,7 +24,7 @@ alt = type(p)(p.w1.clone(), p.b1.clone(), p.w2.clone(), p.b2.clone())
 h = torch.randn(steps, 2 * P, H, device=dev).to(torch.bfloat16)
 u = torch.rand(steps, P, device=dev)
 ids_out = torch.empty(steps, P, dtype=torch.int64, device=dev)
-trace = torch.zeros(5, 160, 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(8, 160, 8, dtype=torch.int64, device=dev)
 lib = _abi.load()
 
 
@@ -35,6 +35,7 @@ def run():
         ids_out[i].copy_(ids)
 
 
+lib.ospo_head_trace(trace.data_ptr())  # before capture: the trace ids are launch parameters
 s = torch.cuda.Stream()
 s.wait_stream(torch.cuda.current_stream())
 with torch.cuda.stream(s):
@@ -45,21 +46,36 @@ with torch.cuda.graph(g):
     run()
 g.replay()
 torch.cuda.synchronize()
-lib.ospo_head_trace(trace.data_ptr())
+trace.zero_()
+torch.cuda.synchronize()
 g.replay()
 torch.cuda.synchronize()
 lib.ospo_head_trace(None)
 t = trace.cpu().numpy().astype("float64")
-names = {1: "gemm1", 3: "finalize", 2: "gemm2", 4: "finish"}
+import os
+merged = os.environ.get("OSPO_HEAD_DECODE_MERGED", "1") != "0"
+names = {1: "phase1" if merged else "gemm1", 3: "prologue" if merged else "finalize", 2: "phase2" if merged else "gemm2", 4: "finish"}
+slots_pro = ((0, "prologue_done"), (1, "partials_ready"), (2, "act_stored"), (3, "roles_done"), (4, "cta_exit"))
+slots_merged = ((0, "entry"), (1, "A_prefetched"), (2, "wait_over"), (3, "w1_issued"), (4, "acc_ready"), (5, "parked"),
+                (6, "published"), (7, "flag_passed"))
 t0 = t[1][:, 0][t[1][:, 0] > 0].min()
 for k in (1, 3, 2, 4):
     a = t[k]
     act = a[:, 0] > 0
     line = f"TRACE {names[k]:9s} ctas={int(act.sum()):3d}"
-    for slot, nm in ((0, "entry"), (1, "prefetched"), (2, "wait_over"), (3, "prod_done"), (4, "acc_ready"), (5, "epi_done"), (6, "csync1"), (7, "finalized")):
+    for slot, nm in slots_merged if (merged and k == 1) else slots_pro if (merged and k == 3) else ((0, "entry"), (1, "prefetched"), (2, "wait_over"), (3, "prod_done"), (4, "acc_ready"), (5, "epi_done"), (6, "csync1"), (7, "finalized")):
         v = a[act, slot]
         v = v[v > 0]
         if v.size:
             line += f" | {nm} {((v.min() - t0) / 1e3):6.1f}..{((v.max() - t0) / 1e3):6.1f}"
+    print(line)
+a = t[5]
+act = a[:, 0] > 0
+if act.any():
+    base = t[2][act, 4]  # acc_ready of the same CTA
+    line = "TRACE gemm2-epilogue (us after the CTA's acc_ready, median/max):"
+    for slot, nm in enumerate(("tmem_loaded", "merged", "kmax", "bar1", "exp_stored", "seg_summed", "bar2")):
+        v = (a[act, slot] - base) / 1e3
+        line += f" | {nm} {float(sorted(v)[len(v)//2]):.2f}/{v.max():.2f}"
     print(line)
 print("(us relative to the first GEMM1 CTA entry of the last traced step)")

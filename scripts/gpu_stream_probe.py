@@ -45,7 +45,7 @@ def bench(M, K, tag, variant=101):
     print(f"STREAM {tag} v{variant}: M={M} K={K} us={us:.2f} GB/s={M * K * 2 / us / 1e3:.0f}", flush=True)
 
 
-for v in (101, 103, 104, 105, 106):
-    bench(16384, 4096, "W2 128 tiles", v)
-for v in (101, 103):
-    bench(4096, 4096, "W1 32 tiles", v)
+for v in (300, 301, 302, 303, 101, 106):
+    bench(16384, 4096, "W2", v)
+for v in (300, 301, 302, 303):
+    bench(4096, 4096, "W1", v)

@@ -482,10 +482,10 @@ def test_cfg_sample_fused_step_vs_oracle(golden_dir):
         assert torch.equal(gid.cpu(), ogid)
 
 
-@pytest.mark.parametrize("fused,pdl", [(1, 1), (1, 0), (0, 1), (0, 0)])
+@pytest.mark.parametrize("fused,pdl,merged", [(1, 1, 1), (1, 0, 1), (1, 1, 0), (1, 0, 0), (0, 1, 0), (0, 0, 0)])
 @pytest.mark.parametrize("mode,w,T", [("bf16", 5.0, 1.0), ("fp32", 3.0, 0.7)])
-def test_cfg_sample_decode_variants_agree(fused, pdl, mode, w, T):
-    """fused-epilogue / separate-sampler and PDL on/off variants of the decode step draw identical ids"""
+def test_cfg_sample_decode_variants_agree(fused, pdl, merged, mode, w, T):
+    """one-kernel / two-GEMM / separate-sampler and PDL on/off variants of the decode step draw identical ids"""
     from ospo_b200 import _abi
 
     dev = _cuda()
@@ -498,11 +498,15 @@ def test_cfg_sample_decode_variants_agree(fused, pdl, mode, w, T):
     lib = _abi.load()
     try:
         lib.ospo_head_set_decode_mode(fused, pdl)
+        lib.ospo_head_set_decode_merged(merged)
         ids, lg = fh.cfg_sample(h, w, T, uniforms=u.to(dev), merge_mode=mode, return_logits=True)
+        ids2 = fh.cfg_sample(h, w, T, uniforms=u.to(dev), merge_mode=mode)  # again: flag words were re-armed
         gids = fh.cfg_sample(h, w, T, greedy=True, merge_mode=mode)
         torch.cuda.synchronize()
+        assert torch.equal(ids, ids2)
     finally:
         lib.ospo_head_set_decode_mode(1, 1)
+        lib.ospo_head_set_decode_merged(1)
     mm = 0 if mode == "bf16" else 1
     oid, *_ = O.cfg_sample_det(lg.cpu(), w, T, u, merge_mode=mm)
     ogid, *_ = O.cfg_sample_det(lg.cpu(), w, T, None, merge_mode=mm, greedy=True)

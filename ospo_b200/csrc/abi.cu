@@ -92,7 +92,7 @@ int runtime_init() {
   if (const char* e = getenv("OSPO_HEAD_DECODE_PDL")) g_rt.decode_pdl = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_CLUSTER")) g_rt.decode_cluster = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_MERGED")) g_rt.decode_merged = atoi(e) != 0;
-  if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);
+  if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);  // + 256 * mode
   if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
     const int v = atoi(e);
     if (v > 0) g_rt.group_m = v;

@@ -8,8 +8,11 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from ospo_b200 import FusedGenHead, _abi, ops  # noqa: E402
 
+import os
+
 dev = torch.device("cuda:0")
-H = E = 4096
+H = E = int(os.environ.get("HE", "4096"))
+ALT = int(os.environ.get("ALT", "1"))  # 1: two weight copies alternate (every step streams from HBM)
 V, P, steps = 16384, 16, 576
 
 
@@ -30,7 +33,7 @@ step_bytes = 2 * (H * E + E * V) + 4 * (E + V) + 2 * 2 * P * H + 4 * P + 8 * P
 
 def run(direct):
     for i in range(steps):
-        w = p if (i & 1) == 0 else alt
+        w = p if (i & 1) == 0 or not ALT else alt
         if direct:
             ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
         else:
@@ -39,7 +42,8 @@ def run(direct):
 
 
 ref = None
-for merged, ahead, direct in ((1, 0, True), (1, 16, True), (1, 24, True), (1, 32, True), (1, 24, False), (0, 0, True), (0, 0, False)):
+for merged, ahead, direct in ((1, 0, True), (1, 24, True), (1, 256 + 8, True), (1, 256 + 16, True), (1, 256 + 32, True), (1, 512 + 16, True),
+                              (1, 512 + 24, True), (1, 512 + 32, True), (1, 512 + 48, True), (0, 0, True), (0, 0, False)):
     if True:
         lib.ospo_head_set_decode_merged(merged)
         lib.ospo_head_set_decode_l2_ahead(ahead)
@@ -65,6 +69,6 @@ for merged, ahead, direct in ((1, 0, True), (1, 16, True), (1, 24, True), (1, 32
         if ref is None:
             ref = ids_out.clone()
         same = bool(torch.equal(ref, ids_out))
-        print(f"TIME merged={merged} l2_ahead={ahead:2d} direct_out={int(direct)}: {us:6.2f} us/step  {step_bytes / us / 1e3:7.1f} GB/s  ids_same={same}")
+        print(f"TIME HE={H} alt={ALT} merged={merged} l2_ahead={ahead & 255:2d} mode={ahead >> 8} direct_out={int(direct)}: {us:6.2f} us/step  {step_bytes / us / 1e3:7.1f} GB/s  ids_same={same}")
 lib.ospo_head_set_decode_merged(1)
 lib.ospo_head_set_decode_l2_ahead(24)

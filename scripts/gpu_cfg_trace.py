@@ -8,8 +8,12 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from ospo_b200 import FusedGenHead, _abi, ops  # noqa: E402
 
+import os
+
 dev = torch.device("cuda:0")
-H = E = 4096
+H = E = int(os.environ.get("HE", "4096"))
+ALT = int(os.environ.get("ALT", "1"))
+DIRECT = int(os.environ.get("DIRECT", "0"))
 V, P, steps = 16384, 16, 8
 
 
@@ -30,9 +34,12 @@ lib = _abi.load()
 
 def run():
     for i in range(steps):
-        w = p if (i & 1) == 0 else alt
-        ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
-        ids_out[i].copy_(ids)
+        w = p if (i & 1) == 0 or not ALT else alt
+        if DIRECT:
+            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
+        else:
+            ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
+            ids_out[i].copy_(ids)
 
 
 lib.ospo_head_trace(trace.data_ptr())  # before capture: the trace ids are launch parameters

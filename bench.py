@@ -375,6 +375,16 @@ def main():
         dist.destroy_process_group()
 
 
+def _decode_traffic():
+    """dram bytes (read + write) of one decode-step launch from the committed ncu --set full capture, or None"""
+    tf = ROOT / "profiles" / "r01_kernel_traffic.json"
+    try:
+        t = json.loads(tf.read_text())["decode_merged"]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def bench_cfg(head, dev, peaks):
     """configs[3]: P = 16 pairs (32 CFG rows), cfg_weight 5, temperature 1, 576 sequential decode steps of
     gen_head + merge + sample.  The 576 steps are captured in one CUDA graph (the loop is launch-bound
@@ -439,7 +449,7 @@ def bench_cfg(head, dev, peaks):
         "eager_us_per_step": eager_ms * 1e3 / steps, "graph_us_per_step": None if graph_ms is None else graph_ms * 1e3 / steps,
         "roofline": {"bound": "hbm", "achieved": step_bytes / (us_step * 1e-6) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": step_bytes / (us_step * 1e-6) / 1e9 / peaks["hbm"], "bytes_per_step": step_bytes,
-                     "traffic": None},
+                     "traffic": _decode_traffic()},
     })
     # next row N1: the same loop with prepare_gen_img_embeds (gen_embed -> gen_aligner, +33.6 MB of weights) fused in
     try:

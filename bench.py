@@ -466,8 +466,7 @@ def bench_cfg(head, dev, peaks):
             for i in range(steps):
                 w = p if (i & 1) == 0 else alt
                 ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
-                both = torch.stack([ids, ids], dim=1).view(-1)              # image_generation.py:166
-                emb_out.copy_(fused_embeds(both))                           # :167
+                fused_embeds.from_sampled(ids, out=emb_out)                 # image_generation.py:166-168
 
         run_steps_n1()
         torch.cuda.synchronize()

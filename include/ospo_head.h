@@ -167,7 +167,7 @@ typedef struct {
  * ospo/wrapper/image_generation.py:166-168.  All bf16 like the generation path; the second Linear streams its
  * D x D weight once (swap-AB tcgen05 GEMM, cluster split-K). */
 typedef struct {
-  int32_t rows;             /* n ids (the reference passes the 2P duplicated ids; n <= 32 per call) */
+  int32_t rows;             /* n output rows (the reference passes the 2P duplicated ids; n <= 32 per call) */
   int32_t embed;            /* D: n_embed of the language model */
   int32_t codebook;         /* rows of gen_embed (16384) */
   int32_t code_dim;         /* columns of gen_embed; must be 8 */
@@ -180,6 +180,9 @@ typedef struct {
   void* out;                /* bf16 [n, D] */
   void* workspace;          /* >= n * D * 2 bytes, 16-byte aligned */
   size_t workspace_bytes;
+  int32_t id_repeat;        /* 0 / 1: ids has n entries.  r > 1: ids has n / r entries and entry i feeds rows
+                               [i*r, (i+1)*r) -- r = 2 is the cond/uncond duplication of image_generation.py:166,
+                               so the sampler's ids[P] can be passed as they are */
 } ospo_aligner_args;
 OSPO_API int ospo_head_gen_img_embeds(const ospo_aligner_args* args, ospo_stream_t stream);
 

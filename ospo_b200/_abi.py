@@ -115,6 +115,7 @@ class AlignerArgs(C.Structure):
         ("out", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("id_repeat", C.c_int32),
     ]
 
 

@@ -622,6 +622,8 @@ int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
       !aligned16(a->workspace))
     return OSPO_ERR_ALIGNMENT;
   if (a->workspace_bytes < static_cast<size_t>(a->rows) * a->embed * 2) return OSPO_ERR_WORKSPACE;
+  const int rep = a->id_repeat > 1 ? a->id_repeat : 1;
+  if (a->rows % rep) return OSPO_ERR_BAD_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   LaunchCtx c = make_ctx(st);
   c.pdl = g_rt.decode_pdl != 0;
@@ -629,7 +631,7 @@ int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
   __nv_bfloat16* a1 = static_cast<__nv_bfloat16*>(a->workspace);
   if (launch_plain(gen_embed_up_kernel, dim3((a->embed + 255) / 256, a->rows), dim3(256), st, c.pdl, a->ids,
                    static_cast<const __nv_bfloat16*>(a->gen_embed), a->codebook,
-                   static_cast<const __nv_bfloat16*>(a->wa), a->ba, a1, a->rows, a->embed) != cudaSuccess)
+                   static_cast<const __nv_bfloat16*>(a->wa), a->ba, a1, a->rows, a->embed, rep) != cudaSuccess)
     return OSPO_ERR_LAUNCH;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return map_rc(launch_decode_linear_cluster(c, a1, static_cast<const __nv_bfloat16*>(a->wb), a->bb,

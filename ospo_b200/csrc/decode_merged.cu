@@ -420,7 +420,7 @@ int run_merged(const LaunchCtx& c, const CUtensorMap& t_w1, const CUtensorMap& t
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = c.stream;
-  cudaLaunchAttribute attrs[2];
+  cudaLaunchAttribute attrs[3];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = static_cast<unsigned>(d.ks);
   attrs[0].val.clusterDim.y = 1;
@@ -442,7 +442,17 @@ int run_merged(const LaunchCtx& c, const CUtensorMap& t_w1, const CUtensorMap& t
     attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  return cudaLaunchKernelEx(&cfg, kern, t_w1, t_h, t_w2, t_act, d, p) == cudaSuccess ? 0 : -4;
+  // cooperative launch: the driver either places all G CTAs at once or refuses the launch -- the formal form of the
+  // co-residency the flag wait relies on (the occupancy query above cannot see other work on the device)
+  attrs[cfg.numAttrs].id = cudaLaunchAttributeCooperative;
+  attrs[cfg.numAttrs].val.cooperative = 1;
+  ++cfg.numAttrs;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, t_w1, t_h, t_w2, t_act, d, p);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {
+    cudaGetLastError();
+    return -100;  // the caller uses the two-GEMM chain
+  }
+  return e == cudaSuccess ? 0 : -4;
 }
 
 }  // namespace

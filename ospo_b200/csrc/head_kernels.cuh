@@ -304,13 +304,13 @@ decode_act_finalize_kernel(const float* __restrict__ part, int k_splits, int64_t
 __global__ void __launch_bounds__(256)
 gen_embed_up_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ gen_embed, int codebook,
                     const __nv_bfloat16* __restrict__ wa, const float* __restrict__ ba, __nv_bfloat16* __restrict__ a,
-                    int n, int D) {
+                    int n, int D, int id_repeat) {
   pdl_launch_dependents();
   pdl_wait();  // the ids come from the sampler
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y;
   if (d >= D || row >= n) return;
-  int64_t id = ids[row];
+  int64_t id = ids[row / id_repeat];
   id = id < 0 ? 0 : (id >= codebook ? codebook - 1 : id);
   const uint4 e = __ldg(reinterpret_cast<const uint4*>(gen_embed + id * 8));
   const uint4 w = __ldg(reinterpret_cast<const uint4*>(wa + static_cast<int64_t>(d) * 8));

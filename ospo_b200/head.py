@@ -353,3 +353,13 @@ class FusedGenImgEmbeds:
         ids = image_ids.reshape(-1).to(torch.int64).contiguous()
         out = ops.gen_img_embeds_impl(ids, e, wa, ba, wb, bb)
         return out.view(*image_ids.shape, out.shape[-1])
+
+    @torch.no_grad()
+    def from_sampled(self, next_token: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """image_generation.py:166-168 in one call: ``next_token`` [P] (the sampler's ids) -> the next step's
+        ``inputs_embeds`` rows [2P, D] (row 2k and 2k+1 both come from id k, the cond/uncond duplication), written
+        into ``out`` if given.  No ``torch.cat`` / ``view`` / copy kernels: the launch chain stays dependent-launch
+        linked to the sampler."""
+        e, wa, ba, wb, bb = self._params()
+        ids = next_token.reshape(-1).to(torch.int64).contiguous()
+        return ops.gen_img_embeds_impl(ids, e, wa, ba, wb, bb, 2, out)

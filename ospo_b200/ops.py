@@ -284,9 +284,12 @@ def cfg_merge_sample_impl(logits: Tensor, cfg_weight: float, temperature: float,
 # --------------------------------------------------------------------------------------------------
 # next row N1: sampled ids -> next-step input embeddings
 # --------------------------------------------------------------------------------------------------
-def gen_img_embeds_impl(ids: Tensor, gen_embed: Tensor, wa: Tensor, ba: Tensor, wb: Tensor, bb: Tensor) -> Tensor:
+def gen_img_embeds_impl(ids: Tensor, gen_embed: Tensor, wa: Tensor, ba: Tensor, wb: Tensor, bb: Tensor,
+                        repeat: int = 1, out: Optional[Tensor] = None) -> Tensor:
     """== gen_aligner(gen_embed(ids))  (janus/models/modeling_vlm.py:263-264; MlpProjector mlp_gelu depth 2)
-    ids [n] int64 (n <= 32 per launch; longer inputs are processed in slices) -> bf16 [n, D]"""
+    ids [n] int64 -> bf16 [n * repeat, D]; row i*repeat + j comes from ids[i] (repeat = 2 is the cond/uncond
+    duplication of image_generation.py:166).  At most 32 output rows per launch; longer inputs go in slices.
+    ``out`` (bf16 [n * repeat, D], contiguous) receives the result without a copy."""
     _check_cuda(ids, gen_embed, wa, wb)
     assert ids.dtype == torch.int64 and ids.dim() == 1 and ids.is_contiguous()
     assert gen_embed.dtype == torch.bfloat16 and gen_embed.shape[1] == 8 and gen_embed.is_contiguous()
@@ -294,14 +297,21 @@ def gen_img_embeds_impl(ids: Tensor, gen_embed: Tensor, wa: Tensor, ba: Tensor, 
     assert ba.dtype == torch.float32 and bb.dtype == torch.float32
     D = wb.shape[0]
     n = ids.numel()
-    out = torch.empty(n, D, dtype=torch.bfloat16, device=ids.device)
+    rep = max(1, int(repeat))
+    assert 32 % rep == 0, "repeat must divide 32"
+    if out is None:
+        out = torch.empty(n * rep, D, dtype=torch.bfloat16, device=ids.device)
+    else:
+        assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() == n * rep * D and out.device == ids.device
+    out2 = out.view(n * rep, D)
     ws = torch.empty(32 * D, dtype=torch.bfloat16, device=ids.device)
     lib = _abi.load()
-    for lo in range(0, n, 32):
-        m = min(32, n - lo)
-        a = _abi.AlignerArgs(m, D, gen_embed.shape[0], 8, ids[lo:lo + m].data_ptr(), gen_embed.data_ptr(), wa.data_ptr(),
-                             ba.data_ptr(), wb.data_ptr(), bb.data_ptr(), out[lo:lo + m].data_ptr(), ws.data_ptr(),
-                             ws.numel() * 2)
+    per = 32 // rep
+    for lo in range(0, n, per):
+        m = min(per, n - lo)
+        a = _abi.AlignerArgs(m * rep, D, gen_embed.shape[0], 8, ids[lo:lo + m].data_ptr(), gen_embed.data_ptr(),
+                             wa.data_ptr(), ba.data_ptr(), wb.data_ptr(), bb.data_ptr(),
+                             out2[lo * rep:(lo + m) * rep].data_ptr(), ws.data_ptr(), ws.numel() * 2, rep)
         _abi.check(lib.ospo_head_gen_img_embeds(C.byref(a), _stream()), "ospo_head_gen_img_embeds")
     return out
 
@@ -326,7 +336,12 @@ cfg_merge_sample = torch.library.custom_op("ospo_head::cfg_merge_sample", cfg_me
                                            device_types="cuda")
 
 
-gen_img_embeds = torch.library.custom_op("ospo_head::gen_img_embeds", gen_img_embeds_impl, mutates_args=(),
+def _gen_img_embeds_op(ids: Tensor, gen_embed: Tensor, wa: Tensor, ba: Tensor, wb: Tensor, bb: Tensor,
+                       repeat: int = 1) -> Tensor:
+    return gen_img_embeds_impl(ids, gen_embed, wa, ba, wb, bb, repeat)
+
+
+gen_img_embeds = torch.library.custom_op("ospo_head::gen_img_embeds", _gen_img_embeds_op, mutates_args=(),
                                          device_types="cuda")
 
 

@@ -717,6 +717,13 @@ def test_gen_img_embeds_7b_shape_and_patch_model():
     assert got.shape == (2 * P, D)
     torch.testing.assert_close(got.float(), ref.float(), rtol=2e-2, atol=2e-2)
     assert torch.equal(got[0::2], got[1::2])      # cond / uncond rows get the same embedding
+    # the one-call form of lines 166-168: sampler ids [P] -> duplicated rows, written in place
+    buf = torch.empty(2 * P, D, dtype=torch.bfloat16, device=dev)
+    from ospo_b200 import FusedGenImgEmbeds
+    fe = FusedGenImgEmbeds(model.gen_embed, model.gen_aligner)
+    ret = fe.from_sampled(next_token, out=buf)
+    torch.cuda.synchronize()
+    assert ret.data_ptr() == buf.data_ptr() and torch.equal(buf, got)
     # more than 32 ids are processed in slices
     many = torch.randint(0, CB, (70,), device=dev)
     with torch.no_grad():

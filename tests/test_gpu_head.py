@@ -513,6 +513,61 @@ def test_cfg_sample_decode_variants_agree(fused, pdl, merged, mode, w, T):
     assert torch.equal(ids.cpu(), oid) and torch.equal(gids.cpu(), ogid)
 
 
+def test_cfg_sample_concurrent_streams_and_graphs():
+    """The one-kernel decode step synchronises its CTAs through two device flag words.  Launches that may overlap
+    (different streams, a replaying graph next to eager work) must not share them: the draws have to equal the
+    serial ones."""
+    from ospo_b200 import _abi
+
+    dev = _cuda()
+    H, E, V, P, n = 512, 2560, 16384, 8, 12      # 20 W1 slabs x 4 k-splits: clusters of 4, like the 7B head
+    head_b = O.make_head(H, E, V, seed=77, w2_gain=4.0).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    g = torch.Generator().manual_seed(78)
+    lib = _abi.load()
+    c0 = lib.ospo_head_launch_count()
+    fh.cfg_sample(torch.zeros(2 * P, H, dtype=torch.bfloat16, device=dev), 5.0, 1.0, greedy=True)
+    assert lib.ospo_head_launch_count() - c0 == 2, "expected the one-kernel decode step (+ finish) on this shape"
+    hs = torch.randn(3, n, 2 * P, H, generator=g).to(torch.bfloat16).to(dev)
+    us = torch.rand(3, n, P, generator=g).to(dev)
+    serial = torch.stack([torch.stack([fh.cfg_sample(hs[k, i], 5.0, 1.0, uniforms=us[k, i]) for i in range(n)])
+                          for k in range(3)])
+    torch.cuda.synchronize()
+    # (a) two side streams at once
+    out = torch.zeros(3, n, P, dtype=torch.int64, device=dev)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for s in streams:
+        s.wait_stream(torch.cuda.current_stream())
+    for i in range(n):
+        for k, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                fh.cfg_sample(hs[k, i], 5.0, 1.0, uniforms=us[k, i], out=out[k, i])
+    for s in streams:
+        torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:2], serial[:2])
+    # (b) a captured graph replaying on one stream while eager steps run on another
+    cap = torch.cuda.Stream()
+    cap.wait_stream(torch.cuda.current_stream())
+    gout = torch.zeros(n, P, dtype=torch.int64, device=dev)
+    with torch.cuda.stream(cap):
+        fh.cfg_sample(hs[2, 0], 5.0, 1.0, uniforms=us[2, 0], out=gout[0])   # warm-up outside the capture
+    torch.cuda.current_stream().wait_stream(cap)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(n):
+            fh.cfg_sample(hs[2, i], 5.0, 1.0, uniforms=us[2, i], out=gout[i])
+    out.zero_()
+    for rep in range(2):
+        gout.zero_()
+        graph.replay()
+        with torch.cuda.stream(streams[0]):
+            for i in range(n):
+                fh.cfg_sample(hs[0, i], 5.0, 1.0, uniforms=us[0, i], out=out[0, i])
+        torch.cuda.synchronize()
+        assert torch.equal(gout, serial[2]) and torch.equal(out[0], serial[0])
+
+
 def test_cfg_sample_7b_shape_p16():
     """BASELINE.json configs[3] shape: P=16 (32 CFG rows), 7B-shaped head; a few steps vs the bf16 oracle."""
     dev = _cuda()

@@ -30,8 +30,12 @@ def generate_image_tokens(gen_head, backbone_step: Callable, prepare_gen_img_emb
         next_token = gen_head.cfg_sample(hidden_states[:, -1, :], cfg_weight, temperature, uniforms=u,
                                          greedy=greedy)                                                 # :156-163
         generated[:, i] = next_token                                                                    # :164
-        both = torch.stack([next_token, next_token], dim=1).view(-1)                                    # :166
-        inputs_embeds = prepare_gen_img_embeds(both).unsqueeze(dim=1)                                   # :167-168
+        if hasattr(prepare_gen_img_embeds, "from_sampled"):
+            # FusedGenImgEmbeds: duplication + gen_embed + gen_aligner in two launches chained to the sampler
+            inputs_embeds = prepare_gen_img_embeds.from_sampled(next_token).unsqueeze(dim=1)            # :166-168
+        else:
+            both = torch.stack([next_token, next_token], dim=1).view(-1)                                # :166
+            inputs_embeds = prepare_gen_img_embeds(both).unsqueeze(dim=1)                               # :167-168
         new_mask = torch.ones((attention_masks.shape[0], 1), dtype=attention_masks.dtype,
                               device=attention_masks.device)
         attention_masks = torch.cat([attention_masks, new_mask], dim=1)                                 # :170-171

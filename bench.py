@@ -461,12 +461,13 @@ def bench_cfg(head, dev, peaks):
         aligner.layers = lin.to(dev).to(torch.bfloat16)
         fused_embeds = FusedGenImgEmbeds(gen_embed, aligner)
         emb_out = torch.empty(2 * P, H7B, dtype=torch.bfloat16, device=dev)
+        ne = (*fused_embeds._params(), emb_out)
 
         def run_steps_n1():
             for i in range(steps):
                 w = p if (i & 1) == 0 else alt
-                ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
-                fused_embeds.from_sampled(ids, out=emb_out)                 # image_generation.py:166-168
+                # image_generation.py:156-168 as one launch chain: decode kernel, finish (+ first aligner layer), D x D Linear
+                ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], ne)
 
         run_steps_n1()
         torch.cuda.synchronize()

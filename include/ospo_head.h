@@ -139,28 +139,6 @@ typedef struct {
   size_t workspace_bytes;
 } ospo_simpo_args;
 
-/* ---- CFG decode step ---------------------------------------------------------------------- */
-#define OSPO_MERGE_BF16 0  /* reference semantics: bf16 rounding after every op (image_generation.py:160-161) */
-#define OSPO_MERGE_FP32 1
-
-typedef struct {
-  ospo_head_shape shape;       /* rows = 2P (row 2k conditional, 2k+1 unconditional); vocab must be 16384 */
-  ospo_head_weights w;
-  const void* h;               /* bf16 [2P, H] last hidden state of every CFG row; NULL for merge_sample */
-  void* logits;                /* bf16 [2P, V]: read by cfg_merge_sample; optional dump for cfg_sample (NULL =
-                                  the logits never leave the chip) */
-  float cfg_weight, temperature;
-  int32_t merge_mode;          /* OSPO_MERGE_BF16 | OSPO_MERGE_FP32 */
-  int32_t greedy;              /* 1 = argmax (lowest index on ties), uniforms ignored */
-  int32_t num_steps;           /* cfg_merge_sample only: independent steps batched in one launch
-                                  (logits [steps, 2P, V], uniforms / ids [steps, P]); 0 or 1 = one step */
-  const float* uniforms;       /* fp32 [P] in [0,1) */
-  int64_t* ids;                /* [P] out */
-  float* merged;               /* optional fp32 [P, V] dump of the merged, temperature-scaled logits */
-  void* workspace;
-  size_t workspace_bytes;
-} ospo_cfg_args;
-
 /* ---- next row: sampled ids -> next-step input embeddings ---------------------------------
  * prepare_gen_img_embeds = gen_aligner(gen_embed(ids))  (janus/models/modeling_vlm.py:263-264; MlpProjector
  * "mlp_gelu" depth 2, janus/models/projector.py:39-45,77-86), called right after sampling at
@@ -184,6 +162,33 @@ typedef struct {
                                [i*r, (i+1)*r) -- r = 2 is the cond/uncond duplication of image_generation.py:166,
                                so the sampler's ids[P] can be passed as they are */
 } ospo_aligner_args;
+
+/* ---- CFG decode step ---------------------------------------------------------------------- */
+#define OSPO_MERGE_BF16 0  /* reference semantics: bf16 rounding after every op (image_generation.py:160-161) */
+#define OSPO_MERGE_FP32 1
+
+typedef struct {
+  ospo_head_shape shape;       /* rows = 2P (row 2k conditional, 2k+1 unconditional); vocab must be 16384 */
+  ospo_head_weights w;
+  const void* h;               /* bf16 [2P, H] last hidden state of every CFG row; NULL for merge_sample */
+  void* logits;                /* bf16 [2P, V]: read by cfg_merge_sample; optional dump for cfg_sample (NULL =
+                                  the logits never leave the chip) */
+  float cfg_weight, temperature;
+  int32_t merge_mode;          /* OSPO_MERGE_BF16 | OSPO_MERGE_FP32 */
+  int32_t greedy;              /* 1 = argmax (lowest index on ties), uniforms ignored */
+  int32_t num_steps;           /* cfg_merge_sample only: independent steps batched in one launch
+                                  (logits [steps, 2P, V], uniforms / ids [steps, P]); 0 or 1 = one step */
+  const float* uniforms;       /* fp32 [P] in [0,1) */
+  int64_t* ids;                /* [P] out */
+  float* merged;               /* optional fp32 [P, V] dump of the merged, temperature-scaled logits */
+  void* workspace;
+  size_t workspace_bytes;
+  const ospo_aligner_args* next_embeds;  /* cfg_sample only, optional: also produce the next step's input embeddings
+                                  (image_generation.py:166-168) in the same launch chain.  rows must be 2P,
+                                  id_repeat 2; its `ids` field is ignored (the sampled ids are used).  The first
+                                  aligner layer runs inside the sampler's finish kernel. */
+} ospo_cfg_args;
+
 OSPO_API int ospo_head_gen_img_embeds(const ospo_aligner_args* args, ospo_stream_t stream);
 
 /* scratch bytes needed by any entry point for this shape */

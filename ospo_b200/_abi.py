@@ -97,6 +97,7 @@ class CfgArgs(C.Structure):
         ("merged", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("next_embeds", C.c_void_p),     # const ospo_aligner_args*
     ]
 
 

@@ -513,10 +513,11 @@ int ospo_head_cfg_merge_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
   return launch_sampler(a, steps * (a->shape.rows / 2), reinterpret_cast<cudaStream_t>(stream));
 }
 
-int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
-  if (!a) return OSPO_ERR_NULL;
-  int rc = runtime_init();
-  if (rc) return rc;
+// the decode step proper; `eu` (may be off) is the first aligner layer folded into the finish kernel, *eu_done tells
+// the caller whether the variant that ran has done it
+static int cfg_sample_step(const ospo_cfg_args* a, ospo_stream_t stream, const EmbedUp& eu, bool* eu_done) {
+  int rc;
+  *eu_done = false;
   if ((rc = check_shape(a->shape, false))) return rc;
   if (a->shape.rows % 2) return OSPO_ERR_BAD_SHAPE;
   if ((rc = check_weights(a->w))) return rc;
@@ -549,9 +550,10 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
       g_launches.fetch_add(1, std::memory_order_relaxed);
       KernelSpan ks(st, OSPO_K_SAMPLER);
       if (launch_plain(cfg_finish_kernel, dim3(pairs), dim3(SAMPLE_THREADS), st, c.pdl, w.fused, s.vocab, a->uniforms,
-                       a->greedy, a->ids, c.trace ? 1 : 0) != cudaSuccess)
+                       a->greedy, a->ids, c.trace ? 1 : 0, eu) != cudaSuccess)
         return OSPO_ERR_LAUNCH;
       g_launches.fetch_add(1, std::memory_order_relaxed);
+      *eu_done = eu.gen_embed != nullptr;
       return OSPO_OK;
     }
     if (lrc != -100) return map_rc(lrc);
@@ -593,9 +595,10 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
     if (rc) return rc;
     KernelSpan ks(st, OSPO_K_SAMPLER);
     if (launch_plain(cfg_finish_kernel, dim3(pairs), dim3(SAMPLE_THREADS), st, c.pdl, w.fused, s.vocab, a->uniforms,
-                     a->greedy, a->ids, c.trace ? 1 : 0) != cudaSuccess)
+                     a->greedy, a->ids, c.trace ? 1 : 0, eu) != cudaSuccess)
       return OSPO_ERR_LAUNCH;
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    *eu_done = eu.gen_embed != nullptr;
     return OSPO_OK;
   }
   // unfused variant: materialise the bf16 logits, then the stand-alone merge + sample pass
@@ -610,20 +613,66 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
   return launch_sampler(&b, pairs, st);
 }
 
-int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
-  if (!a) return OSPO_ERR_NULL;
-  int rc = runtime_init();
-  if (rc) return rc;
+static int check_aligner(const ospo_aligner_args* a, bool need_ids) {
   if (a->rows <= 0 || a->embed <= 0 || a->codebook <= 0) return OSPO_ERR_BAD_SHAPE;
   if (a->code_dim != 8 || a->rows > 32) return OSPO_ERR_UNSUPPORTED;
   if (a->embed % 8) return OSPO_ERR_ALIGNMENT;
-  if (!a->ids || !a->gen_embed || !a->wa || !a->ba || !a->wb || !a->bb || !a->out || !a->workspace) return OSPO_ERR_NULL;
+  if ((need_ids && !a->ids) || !a->gen_embed || !a->wa || !a->ba || !a->wb || !a->bb || !a->out || !a->workspace)
+    return OSPO_ERR_NULL;
   if (!aligned16(a->gen_embed) || !aligned16(a->wa) || !aligned16(a->wb) || !aligned16(a->out) ||
       !aligned16(a->workspace))
     return OSPO_ERR_ALIGNMENT;
   if (a->workspace_bytes < static_cast<size_t>(a->rows) * a->embed * 2) return OSPO_ERR_WORKSPACE;
   const int rep = a->id_repeat > 1 ? a->id_repeat : 1;
   if (a->rows % rep) return OSPO_ERR_BAD_SHAPE;
+  return OSPO_OK;
+}
+
+// the D x D Linear of gen_aligner on a1 [rows, D] (already in the aligner workspace)
+static int aligner_second_linear(const ospo_aligner_args* a, const LaunchCtx& c) {
+  const __nv_bfloat16* a1 = static_cast<const __nv_bfloat16*>(a->workspace);
+  int lrc = g_rt.decode_merged ? launch_decode_linear(c, a1, static_cast<const __nv_bfloat16*>(a->wb), a->bb,
+                                                      static_cast<__nv_bfloat16*>(a->out), a->rows, a->embed, a->embed, 0)
+                               : -100;
+  if (lrc == -100)
+    lrc = launch_decode_linear_cluster(c, a1, static_cast<const __nv_bfloat16*>(a->wb), a->bb,
+                                       static_cast<__nv_bfloat16*>(a->out), a->rows, a->embed, a->embed);
+  return map_rc(lrc);
+}
+
+int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
+  if (!a) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  EmbedUp eu = {nullptr, nullptr, nullptr, nullptr, 0, 0};
+  const ospo_aligner_args* ne = a->next_embeds;
+  if (ne != nullptr) {
+    if ((rc = check_aligner(ne, false))) return rc;
+    if (ne->rows != a->shape.rows || ne->id_repeat != 2) return OSPO_ERR_BAD_SHAPE;
+    eu = EmbedUp{static_cast<const __nv_bfloat16*>(ne->gen_embed), static_cast<const __nv_bfloat16*>(ne->wa), ne->ba,
+                 static_cast<__nv_bfloat16*>(ne->workspace), ne->codebook, ne->embed};
+  }
+  bool eu_done = false;
+  if ((rc = cfg_sample_step(a, stream, eu, &eu_done))) return rc;
+  if (ne == nullptr) return OSPO_OK;
+  if (!eu_done) {
+    // this decode variant has no finish kernel: run the stand-alone embedding path on the sampled ids
+    ospo_aligner_args full = *ne;
+    full.ids = a->ids;
+    return ospo_head_gen_img_embeds(&full, stream);
+  }
+  LaunchCtx c = make_ctx(reinterpret_cast<cudaStream_t>(stream));
+  c.pdl = g_rt.decode_pdl != 0;
+  KernelSpan ks(c.stream, OSPO_K_ALIGNER);
+  return aligner_second_linear(ne, c);
+}
+
+int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
+  if (!a) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  if ((rc = check_aligner(a, true))) return rc;
+  const int rep = a->id_repeat > 1 ? a->id_repeat : 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   LaunchCtx c = make_ctx(st);
   c.pdl = g_rt.decode_pdl != 0;
@@ -634,8 +683,7 @@ int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
                    static_cast<const __nv_bfloat16*>(a->wa), a->ba, a1, a->rows, a->embed, rep) != cudaSuccess)
     return OSPO_ERR_LAUNCH;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return map_rc(launch_decode_linear_cluster(c, a1, static_cast<const __nv_bfloat16*>(a->wb), a->bb,
-                                             static_cast<__nv_bfloat16*>(a->out), a->rows, a->embed, a->embed));
+  return aligner_second_linear(a, c);
 }
 
 const char* ospo_head_strerror(int status) {

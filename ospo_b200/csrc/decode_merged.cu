@@ -54,6 +54,8 @@ struct MergedDims {
   const float* b1;
   __nv_bfloat16* act;   // [n, E]
   uint32_t* flag;       // [0] phase-1 arrivals, [1] CTA exits; both zero between launches
+  int linear_only;      // 1: phase 1 alone -- out[n, E] = bf16(act_fn(x W^T + b)), no flag, no phase 2
+  int gelu;             // phase-1 activation: 1 = exact-erf GELU (gen_head), 0 = identity (gen_aligner's last Linear)
   int l2_ahead;         // weight k-blocks requested into L2 ahead of the shared-memory ring (0 = off)
   unsigned long long* trace;  // timeline buffer [8][160][8] or null (a kernel parameter: stamps cost one store)
 };
@@ -70,6 +72,7 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
                      MergedDims d, typename EpiCfgFused<MODE, TDIV>::Params ep) {
   using Epi = EpiCfgFused<MODE, TDIV>;
   constexpr int tr1 = 1, tr2 = 2;
+  if (d.linear_only) pdl_launch_dependents();  // nothing below needs every CTA resident: the successor may queue up
   if (threadIdx.x == 0) stamp(d.trace, tr1, 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -250,7 +253,7 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
           ++use;
         }
       }
-      if (!flag_seen) wait_flag();  // a CTA without phase-2 work still takes part in re-arming the flag words
+      if (!flag_seen && !d.linear_only) wait_flag();  // a CTA without phase-2 work still helps re-arm the flag words
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -337,14 +340,14 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
             const int c = c_lo + c4 + t;
             if (c < d.n) {
               const float x = bf16_round(a4[t] + b);
-              d.act[static_cast<int64_t>(c) * d.E + e] = __float2bfloat16_rn(gelu_erf(x));
+              d.act[static_cast<int64_t>(c) * d.E + e] = __float2bfloat16_rn(d.gelu ? gelu_erf(x) : x);
             }
           }
         }
       }
       if (threadIdx.x == 64) stamp(d.trace, 3, 2);
       named_bar_sync(1, 128);
-      if (threadIdx.x == 64) {
+      if (threadIdx.x == 64 && !d.linear_only) {
         // release at device scope is cumulative over the stores the barrier above has ordered before it
         fence_proxy_async_all();
         const uint32_t old = atom_add_release_gpu(d.flag, 1u);
@@ -457,6 +460,65 @@ int run_merged(const LaunchCtx& c, const CUtensorMap& t_w1, const CUtensorMap& t
 
 }  // namespace
 
+// out[n, M] = bf16(act_fn(bf16(x W^T + b))) for n <= 32 rows: phase 1 of the kernel above on its own (cluster split-K,
+// st.async exchange, separate weight / activation producers).  Clusters are independent: no flag, no co-residency.
+int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* b,
+                         __nv_bfloat16* out, int n, int K, int M, int gelu) {
+  if (n < 1 || n > kBN) return -100;
+  MergedDims d;
+  d.n = n;
+  d.H = K;
+  d.E = M;
+  d.V = 0;
+  d.num_m1 = (M + kBM - 1) / kBM;
+  d.num_m2 = 0;
+  int ks = decode_gemm1_splits(c.num_sms, K, M);
+  ks = ks >= 8 ? 8 : ks >= 4 ? 4 : ks >= 2 ? 2 : 1;
+  int per;
+  gemm_split_plan((K + kBK - 1) / kBK, ks, &ks, &per);
+  if (ks != 1 && ks != 2 && ks != 4 && ks != 8) return -100;
+  d.ks = ks;
+  d.kb_per_split = per;
+  d.b1 = b;
+  d.act = out;
+  d.flag = nullptr;
+  d.trace = nullptr;
+  d.linear_only = 1;
+  d.gelu = gelu;
+  d.l2_ahead = 0;
+  CUtensorMap t_w, t_x;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&t_w, w, M, K, K, kBM)) != 0) return rc;
+  if ((rc = make_tmap_bf16_2d(&t_x, x, n, K, K, kBN)) != 0) return rc;
+  using Epi = EpiCfgFused<0, false>;
+  typename Epi::Params p{};
+  auto kern = decode_merged_kernel<0, false>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -3;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(d.num_m1 * ks), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = static_cast<unsigned>(ks);
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  if (c.pdl) {
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, t_w, t_x, t_w, t_x, d, p) == cudaSuccess ? 0 : -4;
+}
+
 int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
                          const __nv_bfloat16* w2, const float* b2, __nv_bfloat16* act, uint32_t* flag,
                          __nv_bfloat16* logits_dump, int n, int H, int E, int V, float cfg_weight, float temperature,
@@ -481,6 +543,8 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
   d.flag = flag;
   d.trace = c.trace ? c.trace_buf : nullptr;
   d.l2_ahead = l2_ahead < 0 ? 0 : l2_ahead;
+  d.linear_only = 0;
+  d.gelu = 1;
   const int max_ctas = (c.num_sms / ks) * ks;
   const int need1 = d.num_m1 * ks;
   if (need1 > max_ctas) return -100;

@@ -518,14 +518,82 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
 // greedy mode, per-tile arg-max candidates.  One block per pair finishes the draw.
 // ---------------------------------------------------------------------------
 
+// Optional tail (next row N1): once the pair's id is known the block also evaluates the first gen_aligner layer for
+// it, a1[2p] = a1[2p+1] = bf16(gelu(bf16(gen_embed[id] . Wa^T + ba)))  (image_generation.py:166-167 up to the D x D
+// Linear), so `sample -> next-step embeddings` needs no launch of its own for this stage.
+struct EmbedUp {
+  const __nv_bfloat16* gen_embed;  // [codebook, 8] or null = off
+  const __nv_bfloat16* wa;         // [D, 8]
+  const float* ba;                 // [D]
+  __nv_bfloat16* a1;               // [2P, D]
+  int codebook, D;
+};
+
+constexpr int EMBED_PER_THREAD = 8;  // D <= 8 * 512 is served from registers loaded before the id is known
+
+struct EmbedRegs {
+  uint4 w[EMBED_PER_THREAD];
+  float b[EMBED_PER_THREAD];
+};
+
+// the aligner's first-layer weights do not depend on anything this step computes: fetch them up front
+__device__ __forceinline__ void embed_up_preload(const EmbedUp& eu, EmbedRegs& r) {
+#pragma unroll
+  for (int i = 0; i < EMBED_PER_THREAD; ++i) {
+    const int d = threadIdx.x + i * SAMPLE_THREADS;
+    if (d < eu.D) {
+      r.w[i] = __ldg(reinterpret_cast<const uint4*>(eu.wa + static_cast<int64_t>(d) * 8));
+      r.b[i] = __ldg(eu.ba + d);
+    }
+  }
+}
+
+__device__ __forceinline__ __nv_bfloat16 embed_up_one(const uint32_t (&ew)[4], const uint4& w, float bias) {
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc = fmaf(__uint_as_float(ew[k] << 16), __uint_as_float(ww[k] << 16), acc);
+    acc = fmaf(__uint_as_float(ew[k] & 0xFFFF0000u), __uint_as_float(ww[k] & 0xFFFF0000u), acc);
+  }
+  const float x = bf16_round(acc + bias);
+  return __float2bfloat16_rn(0.5f * x * (1.0f + erff(x * 0.70710678118654752f)));
+}
+
+__device__ __forceinline__ void embed_up_rows(const EmbedUp& eu, const EmbedRegs& r, int p, int id) {
+  id = id < 0 ? 0 : (id >= eu.codebook ? eu.codebook - 1 : id);
+  const uint4 e = __ldg(reinterpret_cast<const uint4*>(eu.gen_embed + static_cast<int64_t>(id) * 8));
+  const uint32_t ew[4] = {e.x, e.y, e.z, e.w};
+  __nv_bfloat16* row0 = eu.a1 + static_cast<int64_t>(2 * p) * eu.D;
+  __nv_bfloat16* row1 = row0 + eu.D;
+#pragma unroll
+  for (int i = 0; i < EMBED_PER_THREAD; ++i) {
+    const int d = threadIdx.x + i * SAMPLE_THREADS;
+    if (d < eu.D) {
+      const __nv_bfloat16 y = embed_up_one(ew, r.w[i], r.b[i]);
+      row0[d] = y;
+      row1[d] = y;
+    }
+  }
+  for (int d = threadIdx.x + EMBED_PER_THREAD * SAMPLE_THREADS; d < eu.D; d += SAMPLE_THREADS) {  // D > 4096
+    const __nv_bfloat16 y =
+        embed_up_one(ew, __ldg(reinterpret_cast<const uint4*>(eu.wa + static_cast<int64_t>(d) * 8)), __ldg(eu.ba + d));
+    row0[d] = y;
+    row1[d] = y;
+  }
+}
+
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ uniforms, int greedy,
-                  int64_t* __restrict__ ids, int trace) {
+                  int64_t* __restrict__ ids, int trace, EmbedUp eu) {
   __shared__ float seg_sum[SAMPLE_THREADS];
   __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
   __shared__ float wmax[SAMPLE_THREADS / 32];
+  __shared__ int bc_id;
   pdl_launch_dependents();  // successors may become resident and prefetch; they wait for our completion
   if (threadIdx.x == 0) trace_stamp(trace ? 4 : 0, 0);
+  EmbedRegs er;
+  if (eu.gen_embed != nullptr) embed_up_preload(eu, er);
   pdl_wait();
   if (threadIdx.x == 0) trace_stamp(trace ? 4 : 0, 2);
   const int p = blockIdx.x;
@@ -545,6 +613,11 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
         }
       }
       ids[p] = garg;
+      bc_id = garg;
+    }
+    if (eu.gen_embed != nullptr) {
+      __syncthreads();
+      embed_up_rows(eu, er, p, bc_id);
     }
     return;
   }
@@ -602,8 +675,13 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
     }
     if (lane == 0) {
       ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
+      bc_id = segi * SAMPLE_SEG + j;
       trace_stamp(trace ? 4 : 0, 5);
     }
+  }
+  if (eu.gen_embed != nullptr) {
+    __syncthreads();
+    embed_up_rows(eu, er, p, bc_id);
   }
 }
 

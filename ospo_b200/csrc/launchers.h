@@ -99,6 +99,10 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
                          __nv_bfloat16* logits_dump, int n, int H, int E, int V, float cfg_weight, float temperature,
                          int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead);
 
+// phase 1 of that kernel on its own: out[n, M] = bf16(act_fn(bf16(x W^T + b))), n <= 32 (gen_aligner's D x D Linear)
+int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* b,
+                         __nv_bfloat16* out, int n, int K, int M, int gelu);
+
 // ---- debug / validation (gemm_debug.cu) ----
 // out[M,N] fp32 = A B^T for one engine variant; see abi.cu for the variant table
 int launch_gemm_debug(const LaunchCtx& c, int variant, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b,

@@ -27,13 +27,16 @@ def generate_image_tokens(gen_head, backbone_step: Callable, prepare_gen_img_emb
     for i in range(image_token_num_per_image):                                                          # :149
         hidden_states, past = backbone_step(inputs_embeds, attention_masks, past)                       # :150-154
         u = None if uniforms is None else uniforms[i]
-        next_token = gen_head.cfg_sample(hidden_states[:, -1, :], cfg_weight, temperature, uniforms=u,
-                                         greedy=greedy)                                                 # :156-163
-        generated[:, i] = next_token                                                                    # :164
         if hasattr(prepare_gen_img_embeds, "from_sampled"):
-            # FusedGenImgEmbeds: duplication + gen_embed + gen_aligner in two launches chained to the sampler
-            inputs_embeds = prepare_gen_img_embeds.from_sampled(next_token).unsqueeze(dim=1)            # :166-168
+            # FusedGenImgEmbeds: sampling, id duplication, gen_embed and gen_aligner are one launch chain
+            next_token, emb = gen_head.cfg_sample(hidden_states[:, -1, :], cfg_weight, temperature, uniforms=u,
+                                                  greedy=greedy, next_embeds=prepare_gen_img_embeds)    # :156-168
+            generated[:, i] = next_token                                                                # :164
+            inputs_embeds = emb.unsqueeze(dim=1)
         else:
+            next_token = gen_head.cfg_sample(hidden_states[:, -1, :], cfg_weight, temperature, uniforms=u,
+                                             greedy=greedy)                                             # :156-163
+            generated[:, i] = next_token                                                                # :164
             both = torch.stack([next_token, next_token], dim=1).view(-1)                                # :166
             inputs_embeds = prepare_gen_img_embeds(both).unsqueeze(dim=1)                               # :167-168
         new_mask = torch.ones((attention_masks.shape[0], 1), dtype=attention_masks.dtype,

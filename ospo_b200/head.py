@@ -278,11 +278,14 @@ class FusedGenHead(torch.nn.Module):
     @torch.no_grad()
     def cfg_sample(self, hidden_last: torch.Tensor, cfg_weight: float = 5.0, temperature: float = 1.0,
                    uniforms: Optional[torch.Tensor] = None, greedy: bool = False, merge_mode: str = "bf16",
-                   return_logits: bool = False, out: Optional[torch.Tensor] = None):
+                   return_logits: bool = False, out: Optional[torch.Tensor] = None,
+                   next_embeds: Optional["FusedGenImgEmbeds"] = None, embeds_out: Optional[torch.Tensor] = None):
         """One decode step (image_generation.py:156-164): hidden_last [2P, H] with row 2k conditional and
         2k+1 unconditional -> next_token ids [P] int64.  ``uniforms`` [P] fp32 in [0,1) drive the inverse-CDF
         draw (None => drawn from torch's CUDA generator); ``greedy`` takes the arg-max instead; ``out`` (int64
-        [P], e.g. a row of the generated-token buffer) receives the ids without a copy."""
+        [P], e.g. a row of the generated-token buffer) receives the ids without a copy.  With ``next_embeds`` (a
+        ``FusedGenImgEmbeds``) the call also returns the next step's input embeddings [2P, D]
+        (image_generation.py:166-168), produced in the same launch chain: ``(ids, embeds)``."""
         p = self._kernel_params()
         h = hidden_last.to(torch.bfloat16).contiguous()
         P = h.shape[0] // 2
@@ -293,8 +296,16 @@ class FusedGenHead(torch.nn.Module):
         else:
             u = uniforms.to(torch.float32).contiguous()
         mm = _abi.MERGE_BF16 if merge_mode == "bf16" else _abi.MERGE_FP32
+        ne = None
+        if next_embeds is not None:
+            e, wa, ba, wb, bb = next_embeds._params()
+            if embeds_out is None:
+                embeds_out = torch.empty(2 * P, wb.shape[0], dtype=torch.bfloat16, device=h.device)
+            ne = (e, wa, ba, wb, bb, embeds_out)
         ids, logits = ops.cfg_sample_impl(h, p.w1, p.b1, p.w2, p.b2, float(cfg_weight), float(temperature), u,
-                                          bool(greedy), mm, bool(return_logits), out)
+                                          bool(greedy), mm, bool(return_logits), out, ne)
+        if next_embeds is not None:
+            return (ids, logits, embeds_out) if return_logits else (ids, embeds_out)
         return (ids, logits) if return_logits else ids
 
 

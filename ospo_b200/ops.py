@@ -222,7 +222,7 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
 # --------------------------------------------------------------------------------------------------
 def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, cfg_weight: float, temperature: float,
                uniforms: Tensor, greedy: bool, merge_mode: int, want_logits: bool = False,
-               out: Optional[Tensor] = None) -> List[Tensor]:
+               out: Optional[Tensor] = None, next_embeds: Optional[tuple] = None) -> List[Tensor]:
     """-> [ids[P] int64 (``out`` if given: the kernel writes the ids there), logits[2P, V] bf16 (empty unless want_logits)]
     (image_generation.py:156-164; row 2k cond / 2k+1 uncond).  Without want_logits the logits never leave the
     chip: the CFG merge, softmax weights and segment sums are produced in the GEMM epilogue."""
@@ -251,6 +251,16 @@ def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, c
     a.ids = ids.data_ptr()
     a.merged = None
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    if next_embeds is not None:
+        # (gen_embed, wa, ba, wb, bb, embeds_out[2P, D]): the next step's input embeddings, image_generation.py:166-168,
+        # produced in the same launch chain (first aligner layer inside the sampler's finish kernel)
+        ge, wa, ba, wb, bb, eo = next_embeds
+        D = wb.shape[0]
+        assert rows <= 32 and eo.dtype == torch.bfloat16 and eo.is_contiguous() and eo.numel() == rows * D
+        ws2 = torch.empty(rows * D, dtype=torch.bfloat16, device=dev)
+        al = _abi.AlignerArgs(rows, D, ge.shape[0], 8, None, ge.data_ptr(), wa.data_ptr(), ba.data_ptr(), wb.data_ptr(),
+                              bb.data_ptr(), eo.data_ptr(), ws2.data_ptr(), ws2.numel() * 2, 2)
+        a.next_embeds = C.cast(C.pointer(al), C.c_void_p)
     _abi.check(_abi.load().ospo_head_cfg_sample(C.byref(a), _stream()), "ospo_head_cfg_sample")
     return [ids, logits if logits is not None else torch.empty(0, dtype=torch.bfloat16, device=dev)]
 

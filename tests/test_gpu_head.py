@@ -783,3 +783,40 @@ def test_gen_img_embeds_7b_shape_and_patch_model():
     many = torch.randint(0, CB, (70,), device=dev)
     with torch.no_grad():
         torch.testing.assert_close(model.prepare_gen_img_embeds(many).float(), ref_fn(many).float(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("fused,merged,greedy", [(1, 1, False), (1, 1, True), (1, 0, False), (0, 0, False)])
+def test_cfg_sample_with_next_embeds_chain(fused, merged, greedy):
+    """image_generation.py:156-168 as one call: the ids equal the plain decode step's and the embeddings equal
+    prepare_gen_img_embeds on the duplicated ids, for every decode variant (the unfused one takes the stand-alone
+    embedding path)."""
+    from ospo_b200 import FusedGenImgEmbeds, _abi
+
+    dev = _cuda()
+    H, E, V, P, D = 512, 2560, 16384, 8, 1024
+    head_b = O.make_head(H, E, V, seed=91, w2_gain=4.0).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    torch.manual_seed(92)
+    gen_embed = torch.nn.Embedding(V, 8).to(torch.bfloat16).to(dev)
+    aligner = O.GenAligner(8, D).to(torch.bfloat16).to(dev)
+    fe = FusedGenImgEmbeds(gen_embed, aligner)
+    g = torch.Generator().manual_seed(93)
+    h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16).to(dev)
+    u = torch.rand(P, generator=g).to(dev)
+    lib = _abi.load()
+    try:
+        lib.ospo_head_set_decode_mode(fused, 1)
+        lib.ospo_head_set_decode_merged(merged)
+        ids_ref = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, greedy=greedy)
+        ids, emb = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, greedy=greedy, next_embeds=fe)
+        torch.cuda.synchronize()
+    finally:
+        lib.ospo_head_set_decode_mode(1, 1)
+        lib.ospo_head_set_decode_merged(1)
+    assert torch.equal(ids, ids_ref)
+    dup = torch.stack([ids, ids], dim=1).view(-1)
+    with torch.no_grad():
+        ref = O.prepare_gen_img_embeds(gen_embed, aligner, dup)
+    assert emb.shape == (2 * P, D) and torch.equal(emb[0::2], emb[1::2])
+    torch.testing.assert_close(emb.float(), ref.float(), rtol=2e-2, atol=2e-2)
+    assert torch.equal(emb, fe(dup))      # bit-identical to the stand-alone fused path

@@ -11,6 +11,7 @@
  *   ospo_head_cfg_sample      ospo/wrapper/image_generation.py:156-164 (== ospo/inference.py:147-155)
  *   ospo_head_cfg_merge_sample   the merge/softmax/sample tail of the same lines, on supplied logits
  *   ospo_head_gen_img_embeds  janus/models/modeling_vlm.py:263-264 + projector.py:39-45 (next row N1)
+ *   ospo_head_grad_sqnorm / ospo_head_adamw_step   ospo/utils/train.py:30,50 + ospo/wrapper/train.py:108-115 (next row N3)
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory,
@@ -191,6 +192,32 @@ typedef struct {
 
 OSPO_API int ospo_head_gen_img_embeds(const ospo_aligner_args* args, ospo_stream_t stream);
 
+/* ---- next row: gradient-norm clip + AdamW on the flat gradient buffer -----------------------
+ * Lightning gradient_clip_val (torch.nn.utils.clip_grad_norm_, ospo/utils/train.py:30,50) and
+ * torch.optim.AdamW (ospo/wrapper/train.py:108-115, configs/step5.yaml:37-43) for the head's parameters, which
+ * live in the layout of ospo_simpo_args.flat_grads (W2 | W1 | b2 | b1, fp32).  Two streaming passes. */
+typedef struct {
+  int64_t numel;              /* elements of the flat buffers */
+  const float* grads;         /* fp32 [numel]  (after the all-reduce) */
+  float* params;              /* fp32 [numel]  master parameters, updated in place */
+  float* exp_avg;             /* fp32 [numel]  first moment, updated in place */
+  float* exp_avg_sq;          /* fp32 [numel]  second moment, updated in place */
+  void* params_bf16;          /* optional bf16 [shadow_numel]: refreshed copy of params[0 : shadow_numel] (the GEMM
+                                 operands W2 | W1), written in the same pass */
+  int64_t shadow_numel;       /* multiple of 4, <= numel */
+  double lr, beta1, beta2, eps, weight_decay;   /* as torch takes them: Python floats */
+  int32_t step;               /* 1-based count of optimizer steps including this one (bias correction) */
+  float max_norm;             /* gradient clipping threshold; <= 0 disables clipping */
+  const float* total_sqnorm;  /* device scalar: squared L2 norm over ALL parameters being clipped together (the
+                                 caller adds the other modules' share to ospo_head_grad_sqnorm's result);
+                                 required when max_norm > 0 */
+} ospo_adamw_args;
+/* out_sq[0] (device) = sum of grads^2, summed in a fixed order (bit-reproducible run to run).
+   workspace: >= 4096 bytes of device scratch. */
+OSPO_API int ospo_head_grad_sqnorm(const float* grads, int64_t numel, float* out_sq, void* workspace,
+                                   size_t workspace_bytes, ospo_stream_t stream);
+OSPO_API int ospo_head_adamw_step(const ospo_adamw_args* args, ospo_stream_t stream);
+
 /* scratch bytes needed by any entry point for this shape */
 OSPO_API int ospo_head_workspace_bytes(const ospo_head_shape* shape, size_t* out_bytes);
 
@@ -217,8 +244,8 @@ OSPO_API int ospo_head_set_decode_mode(int fused, int pdl);
 /* decode step, fused form only: 1 (default) = the whole step (both GEMMs + CFG epilogue) is one persistent
    kernel; 0 = GEMM1 and GEMM2 are separate launches.  -1 queries.  Returns the value in effect. */
 OSPO_API int ospo_head_set_decode_merged(int merged);
-/* one-kernel decode step: number of 16 KB weight k-blocks per CTA requested into L2 ahead of the shared-memory
-   ring (keeps HBM streaming through the step's dependency waits); 0 = off, -1 queries.  Returns the value in effect. */
+/* one-kernel decode step: number of 16 KB W2 tiles per CTA requested into L2 while the activation flag is still
+   closed (keeps HBM streaming through that wait); 0 = off, -1 queries.  Returns the value in effect. */
 OSPO_API int ospo_head_set_decode_l2_ahead(int kblocks);
 /* rasterisation group size (M-blocks walked together); pass 0 to query */
 OSPO_API int ospo_head_set_group_m(int group_m);
@@ -239,7 +266,8 @@ OSPO_API int ospo_head_set_group_m(int group_m);
 #define OSPO_K_DECODE_GEMM2 11  /* swap-AB W2 act^T                                                */
 #define OSPO_K_SAMPLER 12       /* CFG merge + softmax + inverse-CDF sample                        */
 #define OSPO_K_ALIGNER 13       /* gen_embed lookup + Linear(8->D) + GELU, then swap-AB Linear(D->D)   */
-#define OSPO_K_COUNT 14
+#define OSPO_K_OPTIMIZER 14     /* squared-norm reduction + clip + AdamW on the flat buffer           */
+#define OSPO_K_COUNT 15
 OSPO_API int ospo_head_profile_enable(int enable);
 OSPO_API int ospo_head_profile_read(float* total_ms, int32_t* counts, int32_t n);
 /* tuning aid: CTA timeline of the decode chain.  device_buf = u64[5][160][8] (kernel: 1 GEMM1, 2 GEMM2, 3 finalize,

@@ -286,3 +286,30 @@ def synthetic_simpo_batch(B: int, T: int, L: int, H: int, V: int, seed: int, dty
     ir = torch.randint(0, V, (B, T), generator=g)
     pad = torch.full((B, L), -100, dtype=torch.long)
     return hc, hr, torch.cat([pad, ic], 1), torch.cat([pad, ir], 1)
+
+
+# --------------------------------------------------------------------------------------------------
+# next row N3: clip_grad_norm_ + AdamW (restated; the reference uses torch's own implementations:
+# ospo/utils/train.py:30,50 gradient_clip_val = 1.0 and ospo/wrapper/train.py:108-115 torch.optim.AdamW)
+# --------------------------------------------------------------------------------------------------
+def clip_adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr=4e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0,
+                    max_norm=1.0, other_sqnorm=0.0):
+    """One ``clip_grad_norm_(max_norm)`` + ``torch.optim.AdamW`` step on fp32 tensors, written out operation by
+    operation in the order PyTorch 2.x performs them (torch/nn/utils/clip_grad.py; torch/optim/adamw.py
+    ``_single_tensor_adamw``).  Lists of tensors; updated in place; returns the total gradient norm."""
+    sq = sum(float((g.double() ** 2).sum()) for g in grads) + float(other_sqnorm)
+    total_norm = sq ** 0.5
+    if max_norm > 0:
+        coef = min(1.0, max_norm / (total_norm + 1e-6))
+        grads = [g * torch.tensor(coef, dtype=torch.float32) for g in grads]
+    b1, b2 = betas
+    bias1 = 1 - b1 ** step
+    bias2_sqrt = (1 - b2 ** step) ** 0.5
+    step_size = lr / bias1
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        p.mul_(1 - lr * weight_decay)
+        m.add_((g - m) * (1 - b1))                       # lerp_(g, 1 - beta1)
+        v.mul_(b2).add_(g * g * (1 - b2))                # addcmul_(g, g, value = 1 - beta2)
+        denom = (v.sqrt() / bias2_sqrt).add_(eps)
+        p.add_(m / denom * (-step_size))                 # addcdiv_(m, denom, value = -step_size)
+    return total_norm

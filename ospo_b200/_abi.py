@@ -120,6 +120,26 @@ class AlignerArgs(C.Structure):
     ]
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [
+        ("numel", C.c_int64),
+        ("grads", C.c_void_p),
+        ("params", C.c_void_p),
+        ("exp_avg", C.c_void_p),
+        ("exp_avg_sq", C.c_void_p),
+        ("params_bf16", C.c_void_p),
+        ("shadow_numel", C.c_int64),
+        ("lr", C.c_double),
+        ("beta1", C.c_double),
+        ("beta2", C.c_double),
+        ("eps", C.c_double),
+        ("weight_decay", C.c_double),
+        ("step", C.c_int32),
+        ("max_norm", C.c_float),
+        ("total_sqnorm", C.c_void_p),
+    ]
+
+
 # scalars[] indices (OSPO_SC_*)
 SC_LOSS, SC_SIMPO_LOSS, SC_SFT_LOSS = 0, 1, 2
 SC_REWARD_CHOSEN, SC_REWARD_REJECTED, SC_REWARD_ACC, SC_REWARD_MARGIN = 3, 4, 5, 6
@@ -140,6 +160,8 @@ EXPORTS = (
     "ospo_head_cfg_sample",
     "ospo_head_cfg_merge_sample",
     "ospo_head_gen_img_embeds",
+    "ospo_head_grad_sqnorm",
+    "ospo_head_adamw_step",
     "ospo_head_strerror",
     "ospo_head_set_cta_group",
     "ospo_head_set_decode_mode",
@@ -193,6 +215,10 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.ospo_head_gen_img_embeds.argtypes = [C.POINTER(AlignerArgs), S]
     lib.ospo_head_gen_img_embeds.restype = C.c_int
+    lib.ospo_head_grad_sqnorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, S]
+    lib.ospo_head_grad_sqnorm.restype = C.c_int
+    lib.ospo_head_adamw_step.argtypes = [C.POINTER(AdamWArgs), S]
+    lib.ospo_head_adamw_step.restype = C.c_int
     lib.ospo_head_strerror.argtypes = [C.c_int]
     lib.ospo_head_strerror.restype = C.c_char_p
     lib.ospo_head_set_cta_group.argtypes = [C.c_int]
@@ -242,7 +268,7 @@ def workspace_bytes(rows: int, hidden: int, embed: int, vocab: int, num_seqs: in
 
 KERNEL_NAMES = ("gemm1_bias_gelu", "gemm2_logits_lse", "scalar_stage", "dlogits_producer", "dact_gelu_bwd",
                 "wgrad_w2", "colsum_db1", "wgrad_w1", "dgrad_x", "gemm2_logits_plain", "decode_gemm1",
-                "decode_gemm2", "cfg_merge_sample", "gen_img_embeds")
+                "decode_gemm2", "cfg_merge_sample", "gen_img_embeds", "clip_adamw")
 
 
 def profile_enable(on: bool) -> None:

@@ -4,11 +4,13 @@
 #include "../../include/ospo_head.h"
 
 #include <atomic>
+#include <cmath>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
 
 #include "head_kernels.cuh"
+#include "optim_kernels.cuh"
 #include "launchers.h"
 
 using namespace ospo;
@@ -92,7 +94,7 @@ int runtime_init() {
   if (const char* e = getenv("OSPO_HEAD_DECODE_PDL")) g_rt.decode_pdl = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_CLUSTER")) g_rt.decode_cluster = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_MERGED")) g_rt.decode_merged = atoi(e) != 0;
-  if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);  // + 256 * mode
+  if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);
   if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
     const int v = atoi(e);
     if (v > 0) g_rt.group_m = v;
@@ -684,6 +686,57 @@ int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
     return OSPO_ERR_LAUNCH;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return aligner_second_linear(a, c);
+}
+
+int ospo_head_grad_sqnorm(const float* grads, int64_t numel, float* out_sq, void* workspace, size_t workspace_bytes,
+                          ospo_stream_t stream) {
+  int rc = runtime_init();
+  if (rc) return rc;
+  if (!grads || !out_sq || !workspace) return OSPO_ERR_NULL;
+  if (numel <= 0) return OSPO_ERR_BAD_SHAPE;
+  if (!aligned16(grads)) return OSPO_ERR_ALIGNMENT;
+  const int blocks = g_rt.num_sms * 4;  // four resident blocks per SM keep every HBM channel busy
+  if (workspace_bytes < static_cast<size_t>(blocks) * sizeof(float)) return OSPO_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  KernelSpan ks(st, OSPO_K_OPTIMIZER);
+  float* partials = static_cast<float*>(workspace);
+  sqnorm_partial_kernel<<<blocks, OPT_THREADS, 0, st>>>(grads, numel, partials);
+  if ((rc = check_launch())) return rc;
+  sqnorm_final_kernel<<<1, 32, 0, st>>>(partials, blocks, out_sq);
+  return check_launch();
+}
+
+int ospo_head_adamw_step(const ospo_adamw_args* a, ospo_stream_t stream) {
+  if (!a) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  if (a->numel <= 0 || a->step < 1) return OSPO_ERR_BAD_SHAPE;
+  if (!a->grads || !a->params || !a->exp_avg || !a->exp_avg_sq) return OSPO_ERR_NULL;
+  if (a->max_norm > 0.0f && !a->total_sqnorm) return OSPO_ERR_NULL;
+  if (!aligned16(a->grads) || !aligned16(a->params) || !aligned16(a->exp_avg) || !aligned16(a->exp_avg_sq))
+    return OSPO_ERR_ALIGNMENT;
+  if (a->params_bf16 && (!aligned16(a->params_bf16) || (a->shadow_numel % 4) || a->shadow_numel < 0 ||
+                         a->shadow_numel > a->numel))
+    return OSPO_ERR_BAD_SHAPE;
+  if (!(a->beta1 >= 0.0 && a->beta1 < 1.0 && a->beta2 >= 0.0 && a->beta2 < 1.0)) return OSPO_ERR_UNSUPPORTED;
+  // the scalars torch derives in Python (double precision), rounded to fp32 where torch hands them to its kernels
+  AdamWHyper h;
+  const double lr = a->lr, b1 = a->beta1, b2 = a->beta2;
+  h.decay = static_cast<float>(1.0 - lr * a->weight_decay);
+  h.w1 = static_cast<float>(1.0 - b1);
+  h.beta2 = static_cast<float>(b2);
+  h.w2 = static_cast<float>(1.0 - b2);
+  h.bias2_sqrt = static_cast<float>(std::sqrt(1.0 - std::pow(b2, static_cast<double>(a->step))));
+  h.eps = static_cast<float>(a->eps);
+  h.step_size = static_cast<float>(lr / (1.0 - std::pow(b1, static_cast<double>(a->step))));
+  h.max_norm = a->max_norm;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  KernelSpan ks(st, OSPO_K_OPTIMIZER);
+  const int blocks = g_rt.num_sms * 4;
+  adamw_kernel<<<blocks, OPT_THREADS, 0, st>>>(a->grads, a->params, a->exp_avg, a->exp_avg_sq,
+                                               static_cast<__nv_bfloat16*>(a->params_bf16),
+                                               a->params_bf16 ? a->shadow_numel : 0, a->numel, a->total_sqnorm, h);
+  return check_launch();
 }
 
 const char* ospo_head_strerror(int status) {

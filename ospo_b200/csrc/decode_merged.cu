@@ -56,7 +56,7 @@ struct MergedDims {
   uint32_t* flag;       // [0] phase-1 arrivals, [1] CTA exits; both zero between launches
   int linear_only;      // 1: phase 1 alone -- out[n, E] = bf16(act_fn(x W^T + b)), no flag, no phase 2
   int gelu;             // phase-1 activation: 1 = exact-erf GELU (gen_head), 0 = identity (gen_aligner's last Linear)
-  int l2_ahead;         // weight k-blocks requested into L2 ahead of the shared-memory ring (0 = off)
+  int l2_ahead;         // W2 tiles per CTA requested into L2 while the activation flag is closed (0 = off)
   unsigned long long* trace;  // timeline buffer [8][160][8] or null (a kernel parameter: stamps cost one store)
 };
 
@@ -146,38 +146,8 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
         left = num_kb2;
         row = static_cast<int>(blockIdx.x) * kBM;
       }
-      // L2 run-ahead.  The ring holds 160 KB; whenever it is full this thread would just sleep on an "empty"
-      // barrier -- during the predecessor-kernel wait, during the activation-flag wait, and in steady state.  It
-      // uses that time to ask for the weight tiles of the next `ahead` k-blocks to be brought into L2
-      // (cp.async.bulk.prefetch: no destination, no barrier), so HBM keeps streaming through the waits and the
-      // ring's own loads hit L2.  mode 1: everywhere;  mode 2: only up to the first `ahead` tiles past the first
-      // ring-full of W2 (the two dependency waits), nothing in steady state.
-      const int ahead = d.l2_ahead & 0xFF, mode = d.l2_ahead >> 8;
-      const int pf_end = (mode == 2) ? min(total, n1 + kStages + ahead) : total;
-      int ip = 0, p_k = k, p_left = left, p_row = row;
-      bool p_p1 = p1;
-      auto run_ahead = [&](int i) {
-        const int lim = min(pf_end, i + ahead);
-        while (ip < lim) {
-          if (ip > i) tma_prefetch_l2_2d(p_p1 ? &tmap_w1 : &tmap_w2, p_k, p_row);
-          ++ip;
-          p_k += kBK;
-          if (--p_left == 0) {
-            p_row = p_p1 ? static_cast<int>(blockIdx.x) * kBM : p_row + G * kBM;
-            p_p1 = false;
-            p_k = 0;
-            p_left = num_kb2;
-          }
-        }
-      };
       for (int i = 0; i < total; ++i) {
-        if (use > 0) {
-          const uint32_t par = static_cast<uint32_t>(use - 1) & 1u;
-          if (!mbar_try_wait(&empty_bar[slot], par)) {
-            if (mode >= 1 && ahead > 0) run_ahead(i);
-            mbar_wait(&empty_bar[slot], par, SITE_M_PRODUCER_EMPTY);
-          }
-        }
+        if (use > 0) mbar_wait(&empty_bar[slot], static_cast<uint32_t>(use - 1) & 1u, SITE_M_PRODUCER_EMPTY);
         mbar_arrive_expect_tx(&full_bar[slot], kStageBytes);  // covers the B half issued by warp 6
         tma_load_2d(stage_base + slot * kStageBytes, p1 ? &tmap_w1 : &tmap_w2, &full_bar[slot], k, row, kEvictNormal);
         k += kBK;
@@ -192,9 +162,13 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
           ++use;
         }
         if (i + 1 == min(total, kStages)) stamp(d.trace, tr1, 1);
-        if (mode == 0 && i == n1 + kStages - 1 && ahead > 0) {
-          // mode 0: one burst when the ring holds only phase-2 tiles and this thread is about to block on the flag
-          const int nb = min(ahead, left);
+        if (i == n1 + kStages - 1 && d.l2_ahead > 0) {
+          // The ring now holds only phase-2 tiles and this thread is about to sleep until the activation flag opens
+          // and the MMA warp starts freeing slots.  HBM would idle through that wait: ask for the next l2_ahead
+          // tiles of the slab to be brought into L2 meanwhile (cp.async.bulk.prefetch: no destination, no barrier).
+          // Measured alternatives, all slower: prefetching every tile ahead of its ring load (the doubled L2
+          // traffic costs more than it hides), and prefetching before the predecessor-kernel wait as well.
+          const int nb = min(d.l2_ahead, left);
           for (int j = 0; j < nb; ++j) tma_prefetch_l2_2d(&tmap_w2, k + j * kBK, row);
         }
       }

@@ -327,6 +327,43 @@ def gen_img_embeds_impl(ids: Tensor, gen_embed: Tensor, wa: Tensor, ba: Tensor, 
 
 
 # --------------------------------------------------------------------------------------------------
+# next row N3: gradient-norm clip + AdamW on the flat buffer
+# --------------------------------------------------------------------------------------------------
+def grad_sqnorm_impl(flat_grads: Tensor) -> Tensor:
+    """device scalar = sum(flat_grads ** 2), summed in a fixed order (the head's share of clip_grad_norm_'s norm)"""
+    _check_cuda(flat_grads)
+    assert flat_grads.dtype == torch.float32 and flat_grads.is_contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=flat_grads.device)
+    ws = torch.empty(4096, dtype=torch.float32, device=flat_grads.device)
+    _abi.check(_abi.load().ospo_head_grad_sqnorm(flat_grads.data_ptr(), flat_grads.numel(), out.data_ptr(), ws.data_ptr(),
+                                                 ws.numel() * 4, _stream()), "ospo_head_grad_sqnorm")
+    return out
+
+
+def adamw_step_impl(flat_grads: Tensor, params: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: int, lr: float,
+                    beta1: float, beta2: float, eps: float, weight_decay: float, max_norm: float = 0.0,
+                    total_sqnorm: Optional[Tensor] = None, params_bf16: Optional[Tensor] = None) -> None:
+    """clip (coef from ``total_sqnorm``) + torch.optim.AdamW update, in place on params / exp_avg / exp_avg_sq (fp32,
+    layout of the flat gradient); ``params_bf16`` (a prefix-sized bf16 buffer) receives the refreshed GEMM operands"""
+    _check_cuda(flat_grads, params, exp_avg, exp_avg_sq)
+    n = flat_grads.numel()
+    for t in (flat_grads, params, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    a = _abi.AdamWArgs()
+    a.numel = n
+    a.grads, a.params, a.exp_avg, a.exp_avg_sq = flat_grads.data_ptr(), params.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr()
+    if params_bf16 is not None:
+        assert params_bf16.dtype == torch.bfloat16 and params_bf16.is_contiguous() and params_bf16.numel() <= n
+        a.params_bf16, a.shadow_numel = params_bf16.data_ptr(), params_bf16.numel()
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, beta1, beta2, eps, weight_decay
+    a.step, a.max_norm = int(step), float(max_norm)
+    if max_norm > 0:
+        assert total_sqnorm is not None and total_sqnorm.dtype == torch.float32 and total_sqnorm.is_cuda
+        a.total_sqnorm = total_sqnorm.data_ptr()
+    _abi.check(_abi.load().ospo_head_adamw_step(C.byref(a), _stream()), "ospo_head_adamw_step")
+
+
+# --------------------------------------------------------------------------------------------------
 # registration: torch.ops.ospo_head.<name>  (CUDA only).  The nn.Module in head.py calls the *_impl
 # functions directly to keep the dispatcher out of the 576-step decode loop.
 # --------------------------------------------------------------------------------------------------

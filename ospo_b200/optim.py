@@ -1,0 +1,122 @@
+"""Next row N3: gradient-norm clipping + AdamW for the fused head, on its flat buffers.
+
+The reference trains with ``torch.optim.AdamW`` (ospo/wrapper/train.py:108-115; lr 4e-5, betas (0.9, 0.95),
+weight_decay 0, eps 1e-8 in configs/step5.yaml:37-43) under Lightning's ``gradient_clip_val = 1.0``
+(``torch.nn.utils.clip_grad_norm_``, ospo/utils/train.py:30,50).  When the head is trainable
+(train.py:206-208) its four parameters are 83.9 M elements whose gradient the fused backward already leaves
+in one flat fp32 buffer (dW2 | dW1 | db2 | db1, all-reduced once).  ``FusedHeadAdamW`` keeps the master
+parameters and both moments in the same layout, so a step is two streaming kernels (``ospo_head_grad_sqnorm``,
+``ospo_head_adamw_step``) that also refresh the bf16 GEMM operands -- no per-parameter foreach kernels, no
+re-staging cast before the next forward.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .head import FusedGenHead, _HeadParams
+
+
+class FusedHeadAdamW:
+    """``torch.optim.AdamW`` semantics for ``FusedGenHead``'s parameters (same update, same hyper-parameters).
+
+    ``step(other_sqnorm=...)`` clips like ``clip_grad_norm_(all_params, max_norm)``: pass the squared gradient
+    norm of every *other* parameter being clipped together with the head (a device scalar) and read the total
+    back from ``last_total_norm``; with ``max_norm <= 0`` nothing is clipped.
+    """
+
+    def __init__(self, head: FusedGenHead, lr: float = 4e-5, betas=(0.9, 0.95), eps: float = 1e-8,
+                 weight_decay: float = 0.0, max_norm: float = 1.0):
+        self.head = head
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, tuple(betas), eps, weight_decay, max_norm
+        self.step_count = 0
+        self.last_total_norm: Optional[torch.Tensor] = None
+        H, E, V = head.n_embed, head.image_token_embed, head.image_token_size
+        self._dims = (H, E, V)
+        W2, W1 = head.vision_head.weight, head.output_mlp_projector.weight
+        B2, B1 = head.vision_head.bias, head.output_mlp_projector.bias
+        if not W2.is_cuda:
+            raise RuntimeError("FusedHeadAdamW needs the head on a B200 (no CPU path)")
+        n = ops.flat_grad_numel(H, E, V)
+        dev = W2.device
+        with torch.no_grad():
+            self.params = torch.empty(n, dtype=torch.float32, device=dev)       # fp32 master, layout W2 | W1 | b2 | b1
+            views = ops.split_flat_grads(self.params, H, E, V)                  # (W2, W1, b2, b1) views
+            for v, p in zip(views, (W2, W1, B2, B1)):
+                v.copy_(p.detach().to(torch.float32))
+            self.shadow = torch.empty(V * E + E * H, dtype=torch.bfloat16, device=dev)   # bf16 W2 | W1 for the GEMMs
+            self.shadow[:V * E].view(V, E).copy_(views[0])
+            self.shadow[V * E:].view(E, H).copy_(views[1])
+            # the module's parameters become views of the flat buffers: an update is visible without a copy
+            for v, p, sh in zip(views, (W2, W1, B2, B1), (self.shadow[:V * E].view(V, E), self.shadow[V * E:].view(E, H),
+                                                        None, None)):
+                if p.dtype == torch.float32:
+                    p.data = v
+                elif p.dtype == torch.bfloat16 and sh is not None:
+                    p.data = sh
+                # other dtypes / bf16 biases are refreshed by a small copy after every step
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._grads = None
+        self._install_operands()
+
+    # the kernels' operand cache of the head points at the shadow / master buffers, keyed like _kernel_params() keys it
+    def _install_operands(self) -> None:
+        H, E, V = self._dims
+        head = self.head
+        W2v, W1v, b2v, b1v = ops.split_flat_grads(self.params, H, E, V)
+        head._cache = _HeadParams(self.shadow[V * E:].view(E, H), b1v, self.shadow[:V * E].view(V, E), b2v)
+        ts = (head.output_mlp_projector.weight, head.output_mlp_projector.bias, head.vision_head.weight,
+              head.vision_head.bias)
+        head._cache_key = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in ts)
+
+    def _flat_grads(self, use_last_backward: bool) -> torch.Tensor:
+        H, E, V = self._dims
+        head = self.head
+        if use_last_backward and head._flat is not None:
+            return head._flat          # the fused backward's own buffer (already all-reduced): no gather
+        if self._grads is None:
+            self._grads = torch.empty_like(self.params)
+        views = ops.split_flat_grads(self._grads, H, E, V)
+        for v, p in zip(views, (head.vision_head.weight, head.output_mlp_projector.weight, head.vision_head.bias,
+                                head.output_mlp_projector.bias)):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+        return self._grads
+
+    @torch.no_grad()
+    def step(self, other_sqnorm: Optional[torch.Tensor] = None, use_last_backward: bool = False,
+             lr: Optional[float] = None) -> None:
+        """one optimizer step.  ``use_last_backward`` reads the flat buffer the last fused backward wrote (valid
+        without gradient accumulation); otherwise the parameters' ``.grad`` are gathered.  ``lr`` overrides the
+        learning rate for this step (schedulers)."""
+        g = self._flat_grads(use_last_backward)
+        total = None
+        if self.max_norm > 0:
+            total = ops.grad_sqnorm_impl(g)
+            if other_sqnorm is not None:
+                total = total + other_sqnorm.to(torch.float32).reshape(1)
+            self.last_total_norm = total.sqrt()
+        self.step_count += 1
+        ops.adamw_step_impl(g, self.params, self.exp_avg, self.exp_avg_sq, self.step_count,
+                            self.lr if lr is None else lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                            self.max_norm, total, self.shadow)
+        H, E, V = self._dims
+        head = self.head
+        views = ops.split_flat_grads(self.params, H, E, V)
+        for v, p in zip(views, (head.vision_head.weight, head.output_mlp_projector.weight, head.vision_head.bias,
+                                head.output_mlp_projector.bias)):
+            if p.data_ptr() != v.data_ptr() and not (p.dtype == torch.bfloat16 and p.dim() == 2):
+                p.data.copy_(v)        # parameters that are not views of the flat buffers (e.g. bf16 biases)
+        self._install_operands()
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        for p in self.head.parameters():
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()

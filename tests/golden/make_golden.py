@@ -374,6 +374,43 @@ def aligner_golden() -> None:
     print("wrote aligner_ref.npz:", tuple(out.shape))
 
 
+def adamw_golden() -> None:
+    """next row N3.  The reference's optimizer is PyTorch's own (ospo/wrapper/train.py:108-115 torch.optim.AdamW,
+    Lightning gradient_clip_val -> torch.nn.utils.clip_grad_norm_, ospo/utils/train.py:30,50): run exactly those on
+    a tiny head-shaped parameter set for three steps, with the step-5 hyper-parameters (configs/step5.yaml:37-43)
+    and with a weight-decay / no-clip variant."""
+    H, E, V = 24, 40, 64
+    out = {}
+    for tag, kw, max_norm, gscale in (("a", dict(lr=4e-5, betas=(0.9, 0.95), weight_decay=0.0, eps=1e-8), 1.0, 3.0),
+                                      ("b", dict(lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01, eps=1e-8), 0.0, 0.1)):
+        g = torch.Generator().manual_seed(21)
+        shapes = [(V, E), (E, H), (V,), (E,)]                      # W2, W1, b2, b1: the flat-buffer order
+        params = [torch.nn.Parameter(torch.randn(*s, generator=g) * 0.05) for s in shapes]
+        opt = torch.optim.AdamW(params, foreach=False, fused=False, **kw)
+        out[f"{tag}_p0"] = np.concatenate([p.detach().numpy().ravel() for p in params])
+        for step in range(3):
+            grads = [torch.randn(*s, generator=g) * gscale * (0.2 if step == 2 else 1.0) for s in shapes]
+            for p_, g_ in zip(params, grads):
+                p_.grad = g_.clone()
+            out[f"{tag}_g{step}"] = np.concatenate([x.numpy().ravel() for x in grads])
+            if max_norm > 0:
+                tn = torch.nn.utils.clip_grad_norm_(params, max_norm)
+                out[f"{tag}_norm{step}"] = np.float32(tn.item())
+            opt.step()
+            out[f"{tag}_p{step + 1}"] = np.concatenate([p.detach().numpy().ravel() for p in params])
+            st = [opt.state[p_] for p_ in params]
+            out[f"{tag}_m{step + 1}"] = np.concatenate([s_["exp_avg"].numpy().ravel() for s_ in st])
+            out[f"{tag}_v{step + 1}"] = np.concatenate([s_["exp_avg_sq"].numpy().ravel() for s_ in st])
+        out[f"{tag}_hyper"] = np.array([kw["lr"], kw["betas"][0], kw["betas"][1], kw["eps"], kw["weight_decay"], max_norm],
+                                       dtype=np.float64)
+    np.savez_compressed(OUT / "adamw_ref.npz", H=H, E=E, V=V, torch_version=torch.__version__, **out)
+    print("wrote adamw_ref.npz")
+
+
 if __name__ == "__main__":
-    main()
-    aligner_golden()
+    if "--only-adamw" in sys.argv:
+        adamw_golden()
+    else:
+        main()
+        aligner_golden()
+        adamw_golden()

@@ -820,3 +820,74 @@ def test_cfg_sample_with_next_embeds_chain(fused, merged, greedy):
     assert emb.shape == (2 * P, D) and torch.equal(emb[0::2], emb[1::2])
     torch.testing.assert_close(emb.float(), ref.float(), rtol=2e-2, atol=2e-2)
     assert torch.equal(emb, fe(dup))      # bit-identical to the stand-alone fused path
+
+
+def test_clip_adamw_kernels_vs_torch_optimizer_golden(golden_dir):
+    """next row N3 through the C ABI: ospo_head_grad_sqnorm + ospo_head_adamw_step on the flat buffers reproduce the
+    torch.optim.AdamW / clip_grad_norm_ trajectories (fp32, rtol 1e-5 as the north star states for fp32)"""
+    from ospo_b200 import ops
+
+    dev = _cuda()
+    d = np.load(golden_dir / "adamw_ref.npz")
+    for tag in ("a", "b"):
+        lr, b1, b2, eps, wd, max_norm = [float(x) for x in d[f"{tag}_hyper"]]
+        p = torch.from_numpy(d[f"{tag}_p0"].copy()).to(dev)
+        n = p.numel()
+        m = torch.zeros(n, device=dev)
+        v = torch.zeros(n, device=dev)
+        shadow = torch.zeros((n // 8) * 4, dtype=torch.bfloat16, device=dev)
+        for step in range(3):
+            g = torch.from_numpy(d[f"{tag}_g{step}"].copy()).to(dev)
+            sq = ops.grad_sqnorm_impl(g) if max_norm > 0 else None
+            ops.adamw_step_impl(g, p, m, v, step + 1, lr, b1, b2, eps, wd, max_norm, sq, shadow)
+            torch.cuda.synchronize()
+            if max_norm > 0:
+                np.testing.assert_allclose(float(sq.sqrt()), float(d[f"{tag}_norm{step}"]), rtol=1e-5)
+                assert torch.equal(ops.grad_sqnorm_impl(g), sq)          # fixed summation order: bit-reproducible
+            np.testing.assert_allclose(p.cpu().numpy(), d[f"{tag}_p{step + 1}"], rtol=1e-5, atol=1e-8)
+            np.testing.assert_allclose(m.cpu().numpy(), d[f"{tag}_m{step + 1}"], rtol=1e-5, atol=1e-8)
+            np.testing.assert_allclose(v.cpu().numpy(), d[f"{tag}_v{step + 1}"], rtol=1e-5, atol=1e-11)
+            assert torch.equal(shadow, p[:shadow.numel()].to(torch.bfloat16))
+
+
+def test_fused_head_adamw_tracks_torch_adamw():
+    """FusedHeadAdamW on a trainable head: two SimPO steps give the same parameters as clip_grad_norm_ +
+    torch.optim.AdamW applied to the same gradients, the module's parameters are views of the flat master buffer,
+    and the next forward uses the refreshed bf16 operands without re-staging."""
+    from ospo_b200 import FusedHeadAdamW, ops
+
+    dev = _cuda()
+    H, E, V, B, T = 128, 192, 16384, 2, 64
+    head_f = O.make_head(H, E, V, seed=41)
+    fh = _fused_from(head_f, dev, dtype=torch.float32, requires_grad=True)
+    opt = FusedHeadAdamW(fh, lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_norm=1.0)
+    assert fh.vision_head.weight.data_ptr() == opt.params.data_ptr()
+    ref_params = [torch.nn.Parameter(t.detach().clone().cpu()) for t in
+                  (fh.vision_head.weight, fh.output_mlp_projector.weight, fh.vision_head.bias, fh.output_mlp_projector.bias)]
+    ref_opt = torch.optim.AdamW(ref_params, lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
+    other = torch.tensor([0.37], device=dev)          # squared norm of "the rest of the model"
+    for step in range(2):
+        hc, hr, lc, lr_ = O.synthetic_simpo_batch(B, T, 5, H, V, seed=42 + step)
+        hidden, labels = torch.cat([hc, hr]), torch.cat([lc, lr_])
+        out = fh.simpo(hidden.to(dev).to(torch.bfloat16), labels.to(dev), beta=5.0, gamma_beta_ratio=0.25)
+        out.loss.backward()
+        grads = [p.grad.detach().clone().cpu() for p in (fh.vision_head.weight, fh.output_mlp_projector.weight,
+                                                         fh.vision_head.bias, fh.output_mlp_projector.bias)]
+        opt.step(other_sqnorm=other, use_last_backward=(step == 1))
+        opt.zero_grad()
+        torch.cuda.synchronize()
+        # the same gradients through PyTorch's own clip + AdamW (norm over head grads and the 'other' share)
+        tot = (sum(float((x.double() ** 2).sum()) for x in grads) + 0.37) ** 0.5
+        coef = min(1.0, 1.0 / (tot + 1e-6))
+        for p_, g_ in zip(ref_params, grads):
+            p_.grad = g_ * coef
+        ref_opt.step()
+        np.testing.assert_allclose(float(opt.last_total_norm), tot, rtol=1e-5)
+        flat_ref = torch.cat([p_.detach().reshape(-1) for p_ in ref_params])
+        torch.testing.assert_close(opt.params.cpu(), flat_ref, rtol=1e-5, atol=1e-7)
+        assert torch.equal(fh.vision_head.weight.detach().reshape(-1), opt.params[:V * E])
+    # the kernels' operands are the refreshed bf16 shadow: logits equal those of a freshly staged head
+    p = fh._kernel_params()
+    assert p.w2.data_ptr() == opt.shadow.data_ptr()
+    assert torch.equal(p.w2, fh.vision_head.weight.detach().to(torch.bfloat16))
+    assert torch.equal(p.w1, fh.output_mlp_projector.weight.detach().to(torch.bfloat16))

@@ -149,3 +149,24 @@ def test_gen_img_embeds_oracle_matches_reference_golden(golden_dir):
         al.layers[2].bias.copy_(O.bits_to_bf16(d["bb_bf16"]))
         out = O.prepare_gen_img_embeds(emb, al, torch.from_numpy(d["ids"]))
     assert torch.equal(out, O.bits_to_bf16(d["out_bf16"]))
+
+
+def test_clip_adamw_oracle_matches_torch_optimizer_golden(golden_dir):
+    """next row N3: the op-by-op restatement equals torch.optim.AdamW + clip_grad_norm_ (the reference's optimizer,
+    ospo/wrapper/train.py:108-115, ospo/utils/train.py:30,50) on the committed three-step trajectories"""
+    d = np.load(golden_dir / "adamw_ref.npz")
+    H, E, V = int(d["H"]), int(d["E"]), int(d["V"])
+    sizes = [V * E, E * H, V, E]
+    for tag in ("a", "b"):
+        lr, b1, b2, eps, wd, max_norm = [float(x) for x in d[f"{tag}_hyper"]]
+        p = list(torch.from_numpy(d[f"{tag}_p0"].copy()).split(sizes))
+        m = [torch.zeros_like(x) for x in p]
+        v = [torch.zeros_like(x) for x in p]
+        for step in range(3):
+            g = list(torch.from_numpy(d[f"{tag}_g{step}"].copy()).split(sizes))
+            tn = O.clip_adamw_step(p, g, m, v, step + 1, lr, (b1, b2), eps, wd, max_norm)
+            if max_norm > 0:
+                np.testing.assert_allclose(tn, float(d[f"{tag}_norm{step}"]), rtol=1e-6)
+            np.testing.assert_allclose(torch.cat(p).numpy(), d[f"{tag}_p{step + 1}"], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(torch.cat(m).numpy(), d[f"{tag}_m{step + 1}"], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(torch.cat(v).numpy(), d[f"{tag}_v{step + 1}"], rtol=1e-6, atol=1e-12)

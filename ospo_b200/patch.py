@@ -84,6 +84,26 @@ def patch_train_wrapper(wrapper, image_span=None, process_group=None):
                       on_step=True, prog_bar=True, logger=True, sync_dist=True)
         return out.loss
 
+    def compute_total_grad_norm(self):
+        # train.py:459-469 without its per-parameter ``.item()`` syncs: same value
+        # (sqrt of the sum of squared parameter-gradient norms), returned as a device scalar
+        if hasattr(self.trainer.model, "get_global_grad_norm"):
+            grad_norm = self.trainer.model.get_global_grad_norm()
+            return grad_norm if grad_norm is not None else 0.0
+        return total_grad_norm(self.model.parameters())
+
     wrapper.concatenated_forward = types.MethodType(concatenated_forward, wrapper)
     wrapper.get_batch_loss_metrics = types.MethodType(get_batch_loss_metrics, wrapper)
+    wrapper.compute_total_grad_norm = types.MethodType(compute_total_grad_norm, wrapper)
     return wrapper
+
+
+def total_grad_norm(parameters):
+    """sqrt(sum_p ||p.grad||_2^2) over the parameters that have a gradient, as one device scalar (0.0 if none) --
+    the quantity ``JanusProTrainWrapper.compute_total_grad_norm`` logs (train.py:464-469), computed with two
+    multi-tensor kernels instead of one ``.item()`` round trip per parameter."""
+    grads = [p.grad.detach() for p in parameters if p.grad is not None]
+    if not grads:
+        return 0.0
+    norms = torch._foreach_norm(grads, 2)
+    return torch.linalg.vector_norm(torch.stack([n.to(torch.float32) for n in norms]), 2)

@@ -93,3 +93,22 @@ def test_row_selection_matches_get_batch_logps_mask(use_span):
     head = O.make_head(H, 8, V, seed=1)
     _, per_tok, m = O.get_batch_logps(head(hidden), labels, return_per_token=True)
     assert torch.equal(m, mask)
+
+
+def test_total_grad_norm_matches_reference_loop():
+    """N2: the sync-free grad-norm equals the reference's per-parameter .item() loop (train.py:464-469)"""
+    import torch
+
+    from ospo_b200.patch import total_grad_norm
+
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(7, 5)), torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.randn(3))]
+    for p in ps[:2]:
+        p.grad = torch.randn_like(p)
+    total = 0.0
+    for p in ps:
+        if p.grad is not None:
+            total += p.grad.detach().data.norm(2).item() ** 2
+    got = total_grad_norm(ps)
+    assert abs(float(got) - total ** 0.5) < 1e-5
+    assert total_grad_norm([torch.nn.Parameter(torch.zeros(2))]) == 0.0

@@ -28,6 +28,7 @@ struct Runtime {
   int decode_pdl = 1;    // programmatic dependent launch along the decode kernel chain
   int decode_cluster = 1;  // GEMM1 k-splits combined in-cluster through DSMEM (0 = HBM partials + finalize kernel)
   int decode_merged = 1;   // GEMM1 + GEMM2 + CFG epilogue as one persistent kernel (0 = two GEMM launches)
+  int tile_sync = 1;       // wave lock-step of the persistent training GEMMs (OSPO_HEAD_TILE_SYNC)
   int decode_l2_ahead = 24;  // merged kernel: W2 k-blocks per CTA requested into L2 while the activation flag is closed
   bool trace_on = false;   // ospo_head_trace installed a timeline buffer
   unsigned long long* trace_buf = nullptr;
@@ -93,6 +94,7 @@ int runtime_init() {
   if (const char* e = getenv("OSPO_HEAD_DECODE_FUSED")) g_rt.decode_fused = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_PDL")) g_rt.decode_pdl = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_CLUSTER")) g_rt.decode_cluster = atoi(e) != 0;
+  if (const char* e = getenv("OSPO_HEAD_TILE_SYNC")) g_rt.tile_sync = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_MERGED")) g_rt.decode_merged = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);
   if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
@@ -162,6 +164,10 @@ LaunchCtx make_ctx(cudaStream_t s) {
   c.pdl = false;
   c.trace = g_rt.trace_on;
   c.trace_buf = g_rt.trace_buf;
+  if (g_rt.tile_sync) {
+    uint32_t* w = flag_words_for(s);
+    c.sync_ctr = w ? w + 4 : nullptr;  // words 0-1 belong to the decode kernel's flag
+  }
   return c;
 }
 

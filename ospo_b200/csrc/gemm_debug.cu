@@ -13,7 +13,8 @@ template <class Cfg>
 static int run(const LaunchCtx& c, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64_t ldb, float* out,
                int64_t ldo, int M, int N, int K) {
   EpiF::Params p{out, ldo, nullptr};
-  return launch_gemm<Cfg, EpiF>(a, lda, b, ldb, M, N, K, c.group_m, p, c.num_sms, c.stream);
+  return launch_gemm<Cfg, EpiF>(a, lda, b, ldb, M, N, K, c.group_m, p, c.num_sms, c.stream, 1, false, SegOperand(),
+                                SegOperand(), 0, c.sync_ctr);
 }
 
 // ---------------------------------------------------------------------------

@@ -24,13 +24,13 @@ int launch_gemm1_bias_gelu(const LaunchCtx& c, const __nv_bfloat16* x, const __n
   if (pre != nullptr) {
     using Epi = EpiBiasGelu<false, true>;
     Epi::Params p{b1, pre, act, E};
-    if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa);
-    return launch_gemm<Cfg1, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa);
+    if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa, SegOperand(), 0, c.sync_ctr);
+    return launch_gemm<Cfg1, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa, SegOperand(), 0, c.sync_ctr);
   } else {
     using Epi = EpiBiasGelu<false, false>;
     Epi::Params p{b1, nullptr, act, E};
-    if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa);
-    return launch_gemm<Cfg1, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa);
+    if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa, SegOperand(), 0, c.sync_ctr);
+    return launch_gemm<Cfg1, Epi>(x, H, w1, H, rows, E, H, c.group_m, p, c.num_sms, c.stream, 1, false, sa, SegOperand(), 0, c.sync_ctr);
   }
 }
 
@@ -39,16 +39,20 @@ int launch_gemm2_logits_lse(const LaunchCtx& c, const __nv_bfloat16* act, const 
                             int rows, int E, int V) {
   using Epi = EpiLogitsLse;
   Epi::Params p{b2, logits, V, labels, part, rowsum_part, tgt};
-  if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream);
-  return launch_gemm<Cfg1, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream);
+  if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream, 1, false, SegOperand(), SegOperand(), 0,
+                                 c.sync_ctr);
+  return launch_gemm<Cfg1, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream, 1, false, SegOperand(), SegOperand(), 0,
+                                 c.sync_ctr);
 }
 
 int launch_gemm2_logits(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                         __nv_bfloat16* logits, int64_t ld, int rows, int E, int V) {
   using Epi = EpiStore<__nv_bfloat16, false, false>;
   Epi::Params p{logits, ld, b2};
-  if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream);
-  return launch_gemm<Cfg1, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream);
+  if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream, 1, false, SegOperand(), SegOperand(), 0,
+                                 c.sync_ctr);
+  return launch_gemm<Cfg1, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream, 1, false, SegOperand(), SegOperand(), 0,
+                                 c.sync_ctr);
 }
 
 }  // namespace ospo

@@ -39,6 +39,12 @@ struct GemmDims {
   // half of the clusters the upper half, so operand tiles are shared between CTAs of the SAME die only.
   int die_split;
   int trace_id;  // > 0: CTA timeline stamps into g_trace_buf (tuning aid)
+  // Wave lock-step (0 / null = off): the clusters of a persistent grid start their i-th tile together for the first
+  // sync_tiles tiles.  Tiles that run at the same time share operand panels through L2 only while they walk K at
+  // the same pace; free-running clusters drift apart by more than L2 retains and the shared panels are fetched
+  // from HBM several times.  The wait is bounded and falls through (it is a performance hint, never a dependency).
+  uint32_t* sync_ctr;
+  int sync_tiles;
 };
 
 // where a row-mapped output row lands: logical row r -> physical row of a [segments, pitch, cols] tensor
@@ -282,12 +288,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       trace_stamp(dims.trace_id, 1);
       pdl_wait();
       trace_stamp(dims.trace_id, 2);
-      for (int t = dom_first; t < dom_tiles; t += dom_stride) {
+      int tile_no = 0;
+      for (int t = dom_first; t < dom_tiles; t += dom_stride, ++tile_no) {
         const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
         const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
         const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         const int kb0 = (t % ksplits) * dims.kb_per_split;
         const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
+        if (dims.sync_ctr != nullptr && is_leader && tile_no > 0 && tile_no < dims.sync_tiles) {
+          // every cluster announces its tile_no-th tile and waits (at most ~40 us) for the others to get there
+          atomicAdd(dims.sync_ctr, 1u);
+          const uint32_t want = static_cast<uint32_t>(tile_no) * static_cast<uint32_t>(num_clusters);
+          const uint64_t t_start = globaltimer_ns();
+          while (*reinterpret_cast<volatile uint32_t*>(dims.sync_ctr) < want) {
+            if (globaltimer_ns() - t_start > 40000ull) break;
+          }
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
@@ -526,7 +542,8 @@ inline void gemm_split_plan(int num_kb, int want, int* k_splits, int* kb_per_spl
 template <class Cfg, class Epi>
 int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K, int group_m,
                 const typename Epi::Params& ep, int num_sms, cudaStream_t stream, int k_splits = 1,
-                bool pdl = false, SegOperand a_seg = SegOperand(), SegOperand b_seg = SegOperand(), int trace_id = 0) {
+                bool pdl = false, SegOperand a_seg = SegOperand(), SegOperand b_seg = SegOperand(), int trace_id = 0,
+                uint32_t* sync_ctr = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   CUtensorMap ta, tb;
   int rc;
@@ -577,6 +594,14 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
     // exactly one (tile, k-split) item per CTA, the splits of a tile forming one cluster
     if (num_tiles > num_sms || dims.k_splits > 8 || dims.die_split) return -100;
     clusters = num_tiles;
+  }
+
+  dims.sync_ctr = nullptr;
+  dims.sync_tiles = 0;
+  if (sync_ctr != nullptr && !Cfg::CLUSTER_SPLIT && !dims.die_split && clusters >= 2 && num_tiles / clusters >= 2) {
+    if (cudaMemsetAsync(sync_ctr, 0, sizeof(uint32_t), stream) != cudaSuccess) return -4;
+    dims.sync_ctr = sync_ctr;
+    dims.sync_tiles = num_tiles / clusters;  // the full waves; the ragged tail runs free
   }
 
   cudaLaunchConfig_t cfg = {};

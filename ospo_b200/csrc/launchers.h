@@ -16,7 +16,8 @@ struct LaunchCtx {
   cudaStream_t stream;
   bool pdl;       // launch with programmatic stream serialization (decode chain)
   bool trace = false;  // timeline stamps on (ospo_head_trace); off = the stamps compile to a parameter test
-  unsigned long long* trace_buf = nullptr;  // the installed timeline buffer (merged decode kernel stamps through it)
+  unsigned long long* trace_buf = nullptr;
+  uint32_t* sync_ctr = nullptr;  // wave lock-step counter for the persistent training GEMMs (null = free-running)  // the installed timeline buffer (merged decode kernel stamps through it)
 };
 
 struct CfgFusedBuffers;

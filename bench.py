@@ -274,8 +274,9 @@ def main():
         roofline = {
             "bound": "tensor", "kernel": dominant, "achieved": kernels[dominant]["tflops"], "peak": peaks["tf_burst"],
             "unit": "TFLOP/s", "frac": kernels[dominant]["tflops"] / peaks["tf_burst"], "traffic": traffic,
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one ncu --set full capture "
-                              "(profiles/r01_kernel_traffic.json)" if traffic else None,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch, ncu capture of this "
+                              "command (profiles/r01_kernel_traffic.json, r01_launches_ncu_v2.csv, "
+                              "r01_dact_lockstep_ncu_summary.txt)" if traffic else None,
             "ncu_tensor_pipe_active_pct": tensor_pct,
             "peak_source": peaks["source"] + " bf16_tflops (burst); sustained " + str(peaks["tf_sustained"]),
             "step_achieved_tflops": step_tflops, "step_frac": step_tflops / peaks["tf_burst"],

@@ -127,7 +127,7 @@ def cpu_simpo_sample(pairs: int, reps: int):
     return tokens, times, cores
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -138,7 +138,7 @@ def run_reference_arm(args):
     value = tokens / (ms / 1e3)
     sample = (f"{pairs} pairs x {T_IMG} tokens ({tokens} rows) of the 7B-shaped head, fp32 torch CPU oracle port of the "
               f"reference path, fwd+bwd, {cores} threads")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
@@ -160,8 +160,19 @@ def main():
     ap.add_argument("--skip-cfg", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: library chatter (e.g. NCCL's version banner) goes to stderr meanwhile
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, emit)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -368,7 +379,7 @@ def main():
                          f"oracle (port of the reference path), fwd+bwd, best of 2, {cores} threads"}
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",

@@ -358,7 +358,7 @@ def main():
     # ---- secondary: CFG decode (configs[3]) ---------------------------------------------------------
     cfg = None
     if rank == 0 and not args.skip_cfg:
-        cfg = bench_cfg(head, dev, peaks)
+        cfg = bench_cfg(head, dev, peaks, with_cpu=(world == 1 and not args.skip_cpu))
 
     # ---- secondary: clip + AdamW on the flat buffers (next row N3) ------------------------------------
     opt_res = None
@@ -443,7 +443,29 @@ def _decode_traffic():
         return None
 
 
-def bench_cfg(head, dev, peaks):
+def cpu_cfg_sample(steps: int):
+    """the reference's decode step (gen_head + CFG merge + softmax + multinomial, image_generation.py:156-163) on the
+    host cores: 7B-shaped head in bf16 like the generation path (utils/model.py:39), P = 16"""
+    import torch
+
+    from oracle import head_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = 16
+    head = O.make_head(H7B, E7B, V, seed=1237).to(torch.bfloat16)
+    g = torch.Generator().manual_seed(1238)
+    h = torch.randn(steps + 1, 2 * P, H7B, generator=g).to(torch.bfloat16)
+    times = []
+    with torch.no_grad():
+        for i in range(steps + 1):
+            t0 = time.perf_counter()
+            O.decode_step_reference(head, h[i], 5.0, 1.0, generator=g)
+            times.append(time.perf_counter() - t0)
+    return P, times[1:], cores
+
+
+def bench_cfg(head, dev, peaks, with_cpu=False):
     """configs[3]: P = 16 pairs (32 CFG rows), cfg_weight 5, temperature 1, 576 sequential decode steps of
     gen_head + merge + sample.  The 576 steps are captured in one CUDA graph (the loop is launch-bound
     otherwise); weights are re-read from HBM every step because two weight copies alternate and each step
@@ -509,6 +531,16 @@ def bench_cfg(head, dev, peaks):
                      "frac": step_bytes / (us_step * 1e-6) / 1e9 / peaks["hbm"], "bytes_per_step": step_bytes,
                      "traffic": _decode_traffic()},
     })
+    if with_cpu:
+        try:
+            Pc, times, cores = cpu_cfg_sample(10)
+            med = statistics.median(times)
+            result["cpu_baseline"] = {
+                "value": Pc / med, "unit": "tokens/s", "cores": cores, "kind": "port",
+                "sample": f"median of {len(times)} decode steps (after 1 warm-up) of the same P=16, 7B-shaped head, bf16 torch "
+                          f"CPU oracle (port of image_generation.py:156-163), {cores} threads", "us_per_step": med * 1e6}
+        except Exception as ex:
+            result["cpu_baseline"] = {"error": repr(ex)[:200]}
     # next row N1: the same loop with prepare_gen_img_embeds (gen_embed -> gen_aligner, +33.6 MB of weights) fused in
     try:
         from ospo_b200 import FusedGenImgEmbeds

@@ -112,3 +112,38 @@ def test_total_grad_norm_matches_reference_loop():
     got = total_grad_norm(ps)
     assert abs(float(got) - total ** 0.5) < 1e-5
     assert total_grad_norm([torch.nn.Parameter(torch.zeros(2))]) == 0.0
+
+
+def test_token_handoff_matches_reference_pixels(tmp_path):
+    """N4: ids -> decode_code -> uint8 NHWC -> PNG, byte-identical to the reference's numpy path
+    (image_generation.py:174-191) on a stand-in decoder"""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from ospo_b200.handoff import save_images, tokens_to_uint8
+
+    P, img, patch = 3, 48, 16
+    side = img // patch
+    g = torch.Generator().manual_seed(3)
+    tokens = torch.randint(0, 16384, (P, side * side), generator=g).to(torch.int64)
+    table = torch.randn(16384, 3, generator=g) * 0.9
+    seen = {}
+
+    def decode_code(code, shape):                       # vq_model.py:505-508 signature
+        seen["dtype"], seen["shape"] = code.dtype, shape
+        base = table[code.long()].view(P, side, side, 3).permute(0, 3, 1, 2)
+        return torch.nn.functional.interpolate(base, size=(img, img), mode="bilinear").to(torch.bfloat16)
+
+    got = tokens_to_uint8(decode_code, tokens, img_size=img, patch_size=patch)
+    assert seen["dtype"] == torch.int32 and seen["shape"] == [P, 8, side, side]
+    # the reference's lines, literally
+    dec = decode_code(tokens.to(dtype=torch.int), shape=[P, 8, side, side])
+    dec = dec.to(torch.float32).cpu().numpy().transpose(0, 2, 3, 1)
+    dec = np.clip((dec + 1) / 2 * 255, 0, 255)
+    visual_img = np.zeros((P, img, img, 3), dtype=np.uint8)
+    visual_img[:, :, :] = dec
+    assert got.dtype == np.uint8 and np.array_equal(got, visual_img)
+    paths = [str(tmp_path / f"img_{i:02d}.png") for i in range(P)]
+    assert save_images(got, paths) == paths
+    assert np.array_equal(np.asarray(Image.open(paths[1])), visual_img[1])

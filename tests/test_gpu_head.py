@@ -165,6 +165,65 @@ def test_abi_rejects_bad_arguments():
     torch.cuda.synchronize()
 
 
+def test_abi_rejects_bad_arguments_next_rows():
+    """error behaviour of the next-row entry points (optimizer, embeddings, sample + embeddings)"""
+    import ctypes as C
+
+    from ospo_b200 import _abi
+
+    dev = _cuda()
+    lib = _abi.load()
+    st = torch.cuda.current_stream().cuda_stream
+    n = 1024
+    g, p, m, v = (torch.zeros(n, device=dev) for _ in range(4))
+    sq = torch.zeros(1, device=dev)
+    ws = torch.zeros(4096, device=dev)
+    sh = torch.zeros(512, dtype=torch.bfloat16, device=dev)
+
+    def adamw(**kw):
+        a = _abi.AdamWArgs()
+        a.numel, a.grads, a.params, a.exp_avg, a.exp_avg_sq = n, g.data_ptr(), p.data_ptr(), m.data_ptr(), v.data_ptr()
+        a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.step, a.max_norm = 1e-3, 0.9, 0.95, 1e-8, 0.0, 1, 0.0
+        for k, val in kw.items():
+            setattr(a, k, val)
+        return lib.ospo_head_adamw_step(C.byref(a), st)
+
+    assert adamw() == 0
+    assert adamw(step=0) == -1                                   # bad shape: steps are 1-based
+    assert adamw(grads=None) == -3                               # NULL
+    assert adamw(max_norm=1.0) == -3                             # clipping needs the total squared norm
+    assert adamw(max_norm=1.0, total_sqnorm=sq.data_ptr()) == 0
+    assert adamw(params=p.data_ptr() + 4) == -2                  # alignment
+    assert adamw(params_bf16=sh.data_ptr(), shadow_numel=510) == -1   # shadow must be a multiple of 4
+    assert adamw(params_bf16=sh.data_ptr(), shadow_numel=512) == 0
+    assert adamw(beta1=1.0) == -9                                # unsupported hyper-parameter
+    assert lib.ospo_head_grad_sqnorm(g.data_ptr(), n, sq.data_ptr(), ws.data_ptr(), 16, st) == -4     # workspace
+    assert lib.ospo_head_grad_sqnorm(g.data_ptr(), n, sq.data_ptr(), ws.data_ptr(), ws.numel() * 4, st) == 0
+    assert lib.ospo_head_grad_sqnorm(None, n, sq.data_ptr(), ws.data_ptr(), ws.numel() * 4, st) == -3
+
+    # embeddings: rows must be a multiple of id_repeat, code_dim 8, at most 32 rows per launch
+    D, CB = 64, 128
+    ids = torch.zeros(8, dtype=torch.int64, device=dev)
+    ge = torch.zeros(CB, 8, dtype=torch.bfloat16, device=dev)
+    wa = torch.zeros(D, 8, dtype=torch.bfloat16, device=dev)
+    wb = torch.zeros(D, D, dtype=torch.bfloat16, device=dev)
+    bias = torch.zeros(D, device=dev)
+    out = torch.zeros(32, D, dtype=torch.bfloat16, device=dev)
+    ws2 = torch.zeros(32 * D, dtype=torch.bfloat16, device=dev)
+
+    def aligner(rows, rep, code_dim=8):
+        a = _abi.AlignerArgs(rows, D, CB, code_dim, ids.data_ptr(), ge.data_ptr(), wa.data_ptr(), bias.data_ptr(),
+                             wb.data_ptr(), bias.data_ptr(), out.data_ptr(), ws2.data_ptr(), ws2.numel() * 2, rep)
+        return a, lib.ospo_head_gen_img_embeds(C.byref(a), st)
+
+    assert aligner(8, 1)[1] == 0
+    assert aligner(16, 2)[1] == 0
+    assert aligner(9, 2)[1] == -1
+    assert aligner(8, 1, code_dim=4)[1] == -9
+    assert aligner(40, 1)[1] == -9
+    torch.cuda.synchronize()
+
+
 # ---------------------------------------------------------------------------------------------------
 # SimPO: golden vectors from the reference's own code (fp32 reference vs bf16 kernels)
 # ---------------------------------------------------------------------------------------------------

@@ -78,6 +78,8 @@ class SimpoArgs(C.Structure):
         ("flat_grads", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("bwd_stage", C.c_int32),
+        ("reserve_sms", C.c_int32),
     ]
 
 

@@ -343,8 +343,18 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   const ospo_head_shape& s = a->shape;
   if (!a->dx && !a->flat_grads) return OSPO_OK;
   if (!a->pre || !a->act || !a->logits || !a->row_lse || !a->grad_seq) return OSPO_ERR_NULL;
-  const LaunchCtx c = make_ctx(st);
+  LaunchCtx c = make_ctx(st);
   int rc;
+  // bwd_stage: 0 = everything; 1 = up to and including dW2 (the caller then starts the all-reduce of dW2 and calls
+  // again with) 2 = db1, dW1, dX.  dpre lives in the workspace, which must be the same buffer in both calls.
+  const int stage = a->bwd_stage;
+  if (stage < 0 || stage > 2) return OSPO_ERR_UNSUPPORTED;
+  const bool first = stage != 2, second = stage != 1;
+  if (stage == 2 && a->reserve_sms > 0) {
+    // leave SMs to a collective kernel running beside the remaining GEMMs (even count: CTA pairs)
+    const int keep = c.num_sms - (a->reserve_sms + 1) / 2 * 2;
+    if (keep >= c.num_sms / 2) c.num_sms = keep;
+  }
   const size_t VE = static_cast<size_t>(s.vocab) * s.embed, EH = static_cast<size_t>(s.embed) * s.hidden;
   float* dW2 = a->flat_grads;
   float* dW1 = a->flat_grads ? a->flat_grads + VE : nullptr;
@@ -352,7 +362,7 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   float* db1 = a->flat_grads ? db2 + s.vocab : nullptr;
   __nv_bfloat16* dlogits = static_cast<__nv_bfloat16*>(a->logits);
   __nv_bfloat16* dpre = w.rows_by_e;
-  {
+  if (first) {
     KernelSpan ks(st, OSPO_K_DLOGITS);
     row_coef_kernel<<<s.num_seqs, 128, 0, st>>>(a->grad_seq, a->seq_offsets, a->average_log_prob, a->grad_loss,
                                                 sft_coef, num_sft_seqs, w.row_coef);
@@ -365,20 +375,20 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
     dlogits_kernel<<<grid, 128, 0, st>>>(dlogits, s.vocab, a->labels, a->row_lse, w.row_coef, s.rows, s.vocab, db2);
     if ((rc = check_launch())) return rc;
   }
-  {
+  if (first) {
     KernelSpan ks(st, OSPO_K_DACT);
     rc = map_rc(launch_dact_gelu_bwd(c, dlogits, static_cast<const __nv_bfloat16*>(a->w.w2),
                                      static_cast<const __nv_bfloat16*>(a->pre), dpre, s.rows, s.embed, s.vocab));
+    if (rc) return rc;
   }
-  if (rc) return rc;
-  if (a->flat_grads) {
+  if (a->flat_grads && first) {
     // dW2 first: it is the largest block of the flat gradient, so a caller that overlaps the
     // all-reduce with the remaining GEMMs can start on it earliest.
-    {
-      KernelSpan ks(st, OSPO_K_WGRAD2);
-      rc = map_rc(launch_wgrad(c, dlogits, static_cast<const __nv_bfloat16*>(a->act), dW2, s.rows, s.vocab, s.embed));
-    }
+    KernelSpan ks(st, OSPO_K_WGRAD2);
+    rc = map_rc(launch_wgrad(c, dlogits, static_cast<const __nv_bfloat16*>(a->act), dW2, s.rows, s.vocab, s.embed));
     if (rc) return rc;
+  }
+  if (a->flat_grads && second) {
     {
       KernelSpan ks(st, OSPO_K_COLSUM);
       dim3 grid((s.embed + 1023) / 1024, (s.rows + DL_ROWS_PER_BLOCK - 1) / DL_ROWS_PER_BLOCK);
@@ -392,7 +402,7 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
     }
     if (rc) return rc;
   }
-  if (a->dx) {
+  if (a->dx && second) {
     KernelSpan ks(st, OSPO_K_DGRAD);
     rc = map_rc(launch_dgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->w.w1), static_cast<__nv_bfloat16*>(a->dx),
                              s.rows, s.embed, s.hidden, x_layout(a)));

@@ -29,13 +29,45 @@ def shard_concatenated(hidden: torch.Tensor, labels: torch.Tensor, rank: int, wo
     return hidden.index_select(0, idx), labels.index_select(0, idx)
 
 
+def _world(group) -> int:
+    if not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(group)
+
+
+def _avg_op(group):
+    """NCCL averages inside the collective; other backends (gloo in the CPU tests) sum and the caller scales"""
+    return dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM
+
+
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     """in-place average of the flat gradient buffer over the data-parallel group (no-op for world size 1)"""
-    if not dist.is_available() or not dist.is_initialized():
-        return flat
-    world = dist.get_world_size(group)
+    world = _world(group)
     if world == 1:
         return flat
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.mul_(1.0 / world)
+    op = _avg_op(group)
+    dist.all_reduce(flat, op=op, group=group)
+    if op == dist.ReduceOp.SUM:
+        flat.mul_(1.0 / world)
     return flat
+
+
+def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, run_stage2):
+    """Backward in two stages with the exchange of the first block overlapped: ``run_stage1()`` fills
+    ``flat[:split]`` (dW2, 80 % of the buffer), its all-reduce is started asynchronously, ``run_stage2()`` computes
+    the rest while it runs, then the remainder is reduced.  Returns ``run_stage2()``'s result.  Same values as
+    ``run_stage1(); run_stage2(); allreduce_mean_(flat)``."""
+    world = _world(group)
+    run_stage1()
+    if world == 1:
+        return run_stage2()
+    op = _avg_op(group)
+    head, tail = flat[:split], flat[split:]
+    w1 = dist.all_reduce(head, op=op, group=group, async_op=True)
+    out = run_stage2()
+    w2 = dist.all_reduce(tail, op=op, group=group, async_op=True)
+    w1.wait()
+    w2.wait()
+    if op == dist.ReduceOp.SUM:
+        flat.mul_(1.0 / world)
+    return out

@@ -183,8 +183,11 @@ def simpo_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
 def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
              average: bool, sft_weight: float, scalars: Tensor, pre: Tensor, act: Tensor, logits: Tensor,
              row_lse: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool, flat_grads: Tensor,
-             simpo: bool, seg_rows: int = 0, seg_off: int = 0) -> Tensor:
+             simpo: bool, seg_rows: int = 0, seg_off: int = 0, stage: int = 0, reserve_sms: int = 0,
+             ws: Optional[Tensor] = None, dx_out: Optional[Tensor] = None) -> Tensor:
     """softmax-minus-onehot producer + the dgrad / wgrad GEMM pairs.
+    ``stage`` 1 / 2 split the backward after dW2 so the caller can overlap the all-reduce of dW2 with the rest
+    (pass the same ``ws`` to both calls; stage 1 produces no dx).
     `logits` is overwritten with dlogits; `flat_grads` (numel 0 = head frozen) receives dW2|dW1|db2|db1.
     Returns dx bf16 with the shape of x (numel 0 if not requested); with a row-segmented x the rows outside the
     span are zero (train.py: masked positions carry no gradient)."""
@@ -195,8 +198,8 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
     dev = x.device
     seg = (seg_rows, x.shape[1], seg_off) if seg_rows else (0, 0, 0)
     dx = None
-    if need_dx:
-        dx = torch.empty_like(x)
+    if need_dx and stage != 1:
+        dx = torch.empty_like(x) if dx_out is None else dx_out
         if seg_rows:
             dx[:, :seg_off].zero_()
             dx[:, seg_off + seg_rows:].zero_()
@@ -205,10 +208,12 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
         assert fg.dtype == torch.float32 and fg.numel() == flat_grad_numel(H, E, V) and fg.is_contiguous()
     assert grad_scale.dtype == torch.float32 and grad_scale.numel() == 1
     assert grad_seq.dtype == torch.float32 and grad_seq.numel() == S and grad_seq.is_contiguous()
-    ws = _workspace(rows, H, E, V, S, dev)
+    if ws is None:
+        ws = _workspace(rows, H, E, V, S, dev)
     a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, (1.0, 0.0, 0.0, sft_weight, 0),
                     (None, None, None, None, None, scalars if scalars.numel() else None),
                     (pre, act, logits, row_lse, grad_seq), (grad_scale, dx, fg), ws, seg)
+    a.bwd_stage, a.reserve_sms = int(stage), int(reserve_sms)
     lib = _abi.load()
     if simpo:
         _abi.check(lib.ospo_head_simpo_bwd(C.byref(a), _stream()), "ospo_head_simpo_bwd")
@@ -371,7 +376,15 @@ linear_gelu_linear = torch.library.custom_op("ospo_head::linear_gelu_linear", li
                                              mutates_args=(), device_types="cuda")
 logps_fwd = torch.library.custom_op("ospo_head::logps_fwd", logps_fwd_impl, mutates_args=(), device_types="cuda")
 simpo_fwd = torch.library.custom_op("ospo_head::simpo_fwd", simpo_fwd_impl, mutates_args=(), device_types="cuda")
-head_bwd = torch.library.custom_op("ospo_head::head_bwd", head_bwd_impl, mutates_args=("logits", "flat_grads"),
+def _head_bwd_op(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
+                 average: bool, sft_weight: float, scalars: Tensor, pre: Tensor, act: Tensor, logits: Tensor,
+                 row_lse: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool, flat_grads: Tensor,
+                 simpo: bool, seg_rows: int = 0, seg_off: int = 0) -> Tensor:
+    return head_bwd_impl(x, w1, b1, w2, b2, labels, seq_off, average, sft_weight, scalars, pre, act, logits, row_lse,
+                         grad_seq, grad_scale, need_dx, flat_grads, simpo, seg_rows, seg_off)
+
+
+head_bwd = torch.library.custom_op("ospo_head::head_bwd", _head_bwd_op, mutates_args=("logits", "flat_grads"),
                                    device_types="cuda")
 def _cfg_sample_op(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, cfg_weight: float, temperature: float,
                    uniforms: Tensor, greedy: bool, merge_mode: int, want_logits: bool = False) -> List[Tensor]:

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from ospo_b200 import ops
-from ospo_b200.dist import allreduce_mean_, pair_shard, shard_concatenated
+from ospo_b200.dist import allreduce_mean_, pair_shard, shard_concatenated, staged_allreduce_mean_
 
 
 def _free_port():
@@ -65,4 +65,40 @@ def test_pair_shard_layout():
 def test_flat_gradient_allreduce_matches_full_batch_gloo_world2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def _staged_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, split = 1000, 800
+    g = torch.Generator().manual_seed(10 + rank)
+    vals = torch.randn(n, generator=g)
+    flat = torch.zeros(n)
+    order = []
+
+    def stage1():
+        order.append(1)
+        flat[:split] = vals[:split]
+
+    def stage2():
+        order.append(2)
+        flat[split:] = vals[split:]
+        return "dx"
+
+    out = staged_allreduce_mean_(flat, split, dist.group.WORLD, stage1, stage2)
+    ref = vals.clone()
+    allreduce_mean_(ref, dist.group.WORLD)
+    assert out == "dx" and order == [1, 2]
+    torch.testing.assert_close(flat, ref, rtol=0, atol=0)
+    if rank == 0:
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_staged_allreduce_equals_single_allreduce_gloo_world2(tmp_path):
+    """the overlapped exchange (dW2 reduced while the second backward stage runs) gives the same flat buffer"""
+    port = _free_port()
+    mp.spawn(_staged_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()

@@ -950,3 +950,42 @@ def test_fused_head_adamw_tracks_torch_adamw():
     assert p.w2.data_ptr() == opt.shadow.data_ptr()
     assert torch.equal(p.w2, fh.vision_head.weight.detach().to(torch.bfloat16))
     assert torch.equal(p.w1, fh.output_mlp_projector.weight.detach().to(torch.bfloat16))
+
+
+def test_staged_backward_equals_single_call(monkeypatch):
+    """the two-stage backward used to overlap the dW2 all-reduce (stage 1 up to dW2, stage 2 with SMs reserved for
+    the collective) produces bit-identical gradients to the single-call backward"""
+    from ospo_b200 import dist as D
+
+    dev = _cuda()
+    H, E, V, B, T, L = 256, 384, 16384, 3, 128, 3
+    head_b = O.make_head(H, E, V, seed=51, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr_ = O.synthetic_simpo_batch(B, T, L, H, V, seed=52, dtype=torch.bfloat16)
+    hidden, labels = torch.cat([hc, hr]).to(dev), torch.cat([lc, lr_]).to(dev)
+
+    def run(staged):
+        fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=True)
+        x = hidden.clone().requires_grad_(True)
+        if staged:
+            calls = []
+            monkeypatch.setattr(D, "_world", lambda group: 2)
+
+            def fake_staged(flat, split, group, s1, s2):
+                calls.append(split)
+                s1()
+                return s2()
+
+            monkeypatch.setattr(D, "staged_allreduce_mean_", fake_staged)
+        out = fh.simpo(x, labels, beta=10.0, gamma_beta_ratio=0.5, image_span=(L - 1, L - 1 + T),
+                       process_group="fake" if staged else None)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        if staged:
+            assert calls == [V * E]
+            monkeypatch.undo()
+        return (x.grad.clone(), fh.vision_head.weight.grad.clone(), fh.output_mlp_projector.weight.grad.clone(),
+                fh.vision_head.bias.grad.clone(), fh.output_mlp_projector.bias.grad.clone())
+
+    a, b = run(False), run(True)
+    for ta, tb in zip(a, b):
+        assert torch.equal(ta, tb)

@@ -478,6 +478,9 @@ def bench_cfg(head, dev, peaks, with_cpu=False):
     p = head._kernel_params()
     # a second copy of the weights so consecutive steps cannot hit the previous step's lines in L2
     alt = type(p)(p.w1.clone(), p.b1.clone(), p.w2.clone(), p.b2.clone())
+    # the decode kernel's streaming layout of both weight copies (what FusedGenHead.cfg_sample keeps cached)
+    packed = {id(p): (ops.pack_weight_impl(p.w1), ops.pack_weight_impl(p.w2)),
+              id(alt): (ops.pack_weight_impl(alt.w1), ops.pack_weight_impl(alt.w2))}
     gen = torch.Generator(device=dev).manual_seed(1238)
     h = torch.randn(steps, 2 * P, H7B, generator=gen, device=dev).to(torch.bfloat16)
     u = torch.rand(steps, P, generator=gen, device=dev)
@@ -487,7 +490,8 @@ def bench_cfg(head, dev, peaks, with_cpu=False):
         for i in range(steps):
             w = p if (i & 1) == 0 else alt
             # the ids land directly in the generated-token buffer (generated_tokens[:, i], image_generation.py:164)
-            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
+            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], None,
+                                packed[id(w)])
 
     run_steps()
     torch.cuda.synchronize()
@@ -557,7 +561,8 @@ def bench_cfg(head, dev, peaks, with_cpu=False):
             for i in range(steps):
                 w = p if (i & 1) == 0 else alt
                 # image_generation.py:156-168 as one launch chain: decode kernel, finish (+ first aligner layer), D x D Linear
-                ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], ne)
+                ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], ne,
+                                    packed[id(w)])
 
         run_steps_n1()
         torch.cuda.synchronize()

@@ -191,6 +191,9 @@ typedef struct {
   float* merged;               /* optional fp32 [P, V] dump of the merged, temperature-scaled logits */
   void* workspace;
   size_t workspace_bytes;
+  const void* w1_packed;       /* cfg_sample only, optional: W1 / W2 pre-packed by ospo_head_pack_weight.  The decode */
+  const void* w2_packed;       /* kernel then streams each 16 KB weight tile with one contiguous bulk copy.  The caller
+                                  re-packs when the weights change; either may be NULL. */
   const ospo_aligner_args* next_embeds;  /* cfg_sample only, optional: also produce the next step's input embeddings
                                   (image_generation.py:166-168) in the same launch chain.  rows must be 2P,
                                   id_repeat 2; its `ids` field is ignored (the sampled ids are used).  The first
@@ -235,6 +238,10 @@ OSPO_API int ospo_head_logps_bwd(const ospo_simpo_args* args, ospo_stream_t stre
 OSPO_API int ospo_head_simpo_fwd(const ospo_simpo_args* args, ospo_stream_t stream);
 OSPO_API int ospo_head_simpo_bwd(const ospo_simpo_args* args, ospo_stream_t stream);
 
+/* Pre-pack a [rows, cols] bf16 row-major weight for the decode step: [rows/128][cols/64] tiles of 16 KB, each the
+   128-byte-swizzled shared-memory image of a {64 x 128} box.  packed: ospo_head_packed_weight_bytes() bytes. */
+OSPO_API int ospo_head_packed_weight_bytes(int32_t rows, int32_t cols, size_t* out_bytes);
+OSPO_API int ospo_head_pack_weight(const void* w, int32_t rows, int32_t cols, void* packed, ospo_stream_t stream);
 OSPO_API int ospo_head_cfg_sample(const ospo_cfg_args* args, ospo_stream_t stream);
 OSPO_API int ospo_head_cfg_merge_sample(const ospo_cfg_args* args, ospo_stream_t stream);
 

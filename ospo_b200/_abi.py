@@ -99,6 +99,8 @@ class CfgArgs(C.Structure):
         ("merged", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("w1_packed", C.c_void_p),
+        ("w2_packed", C.c_void_p),
         ("next_embeds", C.c_void_p),     # const ospo_aligner_args*
     ]
 
@@ -159,6 +161,8 @@ EXPORTS = (
     "ospo_head_logps_bwd",
     "ospo_head_simpo_fwd",
     "ospo_head_simpo_bwd",
+    "ospo_head_packed_weight_bytes",
+    "ospo_head_pack_weight",
     "ospo_head_cfg_sample",
     "ospo_head_cfg_merge_sample",
     "ospo_head_gen_img_embeds",
@@ -217,6 +221,10 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.ospo_head_gen_img_embeds.argtypes = [C.POINTER(AlignerArgs), S]
     lib.ospo_head_gen_img_embeds.restype = C.c_int
+    lib.ospo_head_packed_weight_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    lib.ospo_head_packed_weight_bytes.restype = C.c_int
+    lib.ospo_head_pack_weight.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, S]
+    lib.ospo_head_pack_weight.restype = C.c_int
     lib.ospo_head_grad_sqnorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, S]
     lib.ospo_head_grad_sqnorm.restype = C.c_int
     lib.ospo_head_adamw_step.argtypes = [C.POINTER(AdamWArgs), S]

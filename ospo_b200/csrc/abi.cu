@@ -562,7 +562,7 @@ static int cfg_sample_step(const ospo_cfg_args* a, ospo_stream_t stream, const E
                                  a->w.b1, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2, w.rows_by_e, flag,
                                  static_cast<__nv_bfloat16*>(a->logits), s.rows, s.hidden, s.embed, s.vocab,
                                  a->cfg_weight, a->temperature, a->merge_mode == OSPO_MERGE_FP32 ? 1 : 0, a->greedy,
-                                 w.fused, g_rt.decode_l2_ahead);
+                                 w.fused, g_rt.decode_l2_ahead, a->w1_packed, a->w2_packed);
     }
     if (lrc == 0) {
       g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -702,6 +702,26 @@ int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
     return OSPO_ERR_LAUNCH;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return aligner_second_linear(a, c);
+}
+
+int ospo_head_packed_weight_bytes(int32_t rows, int32_t cols, size_t* out_bytes) {
+  if (!out_bytes) return OSPO_ERR_NULL;
+  if (rows <= 0 || cols <= 0) return OSPO_ERR_BAD_SHAPE;
+  *out_bytes = static_cast<size_t>((rows + 127) / 128) * ((cols + 63) / 64) * 16384;
+  return OSPO_OK;
+}
+
+int ospo_head_pack_weight(const void* w, int32_t rows, int32_t cols, void* packed, ospo_stream_t stream) {
+  int rc = runtime_init();
+  if (rc) return rc;
+  if (!w || !packed) return OSPO_ERR_NULL;
+  if (rows <= 0 || cols <= 0) return OSPO_ERR_BAD_SHAPE;
+  if (!aligned16(w) || !aligned16(packed) || (cols % 8)) return OSPO_ERR_ALIGNMENT;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>((rows + 127) / 128) * ((cols + 63) / 64) * 1024;
+  pack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(w), rows, cols, static_cast<uint4*>(packed));
+  return check_launch();
 }
 
 int ospo_head_grad_sqnorm(const float* grads, int64_t numel, float* out_sq, void* workspace, size_t workspace_bytes,

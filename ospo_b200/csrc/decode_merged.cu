@@ -54,6 +54,8 @@ struct MergedDims {
   const float* b1;
   __nv_bfloat16* act;   // [n, E]
   uint32_t* flag;       // [0] phase-1 arrivals, [1] CTA exits; both zero between launches
+  const uint8_t* w1p;   // optional pre-packed weights (ospo_head_pack_weight): tile (slab, k-block) = one contiguous
+  const uint8_t* w2p;   //   16 KB block that already is the swizzled shared-memory image; null = tensor-map loads
   int linear_only;      // 1: phase 1 alone -- out[n, E] = bf16(act_fn(x W^T + b)), no flag, no phase 2
   int gelu;             // phase-1 activation: 1 = exact-erf GELU (gen_head), 0 = identity (gen_aligner's last Linear)
   int l2_ahead;         // W2 tiles per CTA requested into L2 while the activation flag is closed (0 = off)
@@ -63,6 +65,17 @@ struct MergedDims {
 __device__ __forceinline__ void stamp(unsigned long long* buf, int row, int slot) {
   if (buf != nullptr && blockIdx.x < kTraceCtas)
     buf[(static_cast<size_t>(row) * kTraceCtas + blockIdx.x) * kTraceSlots + slot] = globaltimer_ns();
+}
+
+// contiguous 16 KB weight tile -> shared memory (no tensor map: one request instead of 128 row requests)
+__device__ __forceinline__ void bulk_load_tile(void* smem_dst, const uint8_t* gsrc, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(kABytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_tile(const uint8_t* gsrc) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(kABytes) : "memory");
 }
 
 template <int MODE, bool TDIV>
@@ -149,7 +162,13 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
       for (int i = 0; i < total; ++i) {
         if (use > 0) mbar_wait(&empty_bar[slot], static_cast<uint32_t>(use - 1) & 1u, SITE_M_PRODUCER_EMPTY);
         mbar_arrive_expect_tx(&full_bar[slot], kStageBytes);  // covers the B half issued by warp 6
-        tma_load_2d(stage_base + slot * kStageBytes, p1 ? &tmap_w1 : &tmap_w2, &full_bar[slot], k, row, kEvictNormal);
+        const uint8_t* packed = p1 ? d.w1p : d.w2p;
+        if (packed != nullptr) {
+          const size_t tile = static_cast<size_t>(row >> 7) * (p1 ? num_kb1 : num_kb2) + (k >> 6);
+          bulk_load_tile(stage_base + slot * kStageBytes, packed + tile * kABytes, &full_bar[slot]);
+        } else {
+          tma_load_2d(stage_base + slot * kStageBytes, p1 ? &tmap_w1 : &tmap_w2, &full_bar[slot], k, row, kEvictNormal);
+        }
         k += kBK;
         if (--left == 0) {  // next item: a W2 slab
           row = p1 ? static_cast<int>(blockIdx.x) * kBM : row + G * kBM;
@@ -169,7 +188,12 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
           // Measured alternatives, all slower: prefetching every tile ahead of its ring load (the doubled L2
           // traffic costs more than it hides), and prefetching before the predecessor-kernel wait as well.
           const int nb = min(d.l2_ahead, left);
-          for (int j = 0; j < nb; ++j) tma_prefetch_l2_2d(&tmap_w2, k + j * kBK, row);
+          if (d.w2p != nullptr) {
+            const uint8_t* next = d.w2p + (static_cast<size_t>(row >> 7) * num_kb2 + (k >> 6)) * kABytes;
+            for (int j = 0; j < nb; ++j) bulk_prefetch_tile(next + static_cast<size_t>(j) * kABytes);
+          } else {
+            for (int j = 0; j < nb; ++j) tma_prefetch_l2_2d(&tmap_w2, k + j * kBK, row);
+          }
         }
       }
       stamp(d.trace, tr2, 3);
@@ -456,6 +480,8 @@ int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_
   d.b1 = b;
   d.act = out;
   d.flag = nullptr;
+  d.w1p = nullptr;
+  d.w2p = nullptr;
   d.trace = nullptr;
   d.linear_only = 1;
   d.gelu = gelu;
@@ -496,7 +522,8 @@ int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_
 int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
                          const __nv_bfloat16* w2, const float* b2, __nv_bfloat16* act, uint32_t* flag,
                          __nv_bfloat16* logits_dump, int n, int H, int E, int V, float cfg_weight, float temperature,
-                         int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead) {
+                         int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead, const void* w1_packed,
+                         const void* w2_packed) {
   if (n < 2 || n > kBN || flag == nullptr) return -100;
   MergedDims d;
   d.n = n;
@@ -515,6 +542,8 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
   d.b1 = b1;
   d.act = act;
   d.flag = flag;
+  d.w1p = static_cast<const uint8_t*>(w1_packed);
+  d.w2p = static_cast<const uint8_t*>(w2_packed);
   d.trace = c.trace ? c.trace_buf : nullptr;
   d.l2_ahead = l2_ahead < 0 ? 0 : l2_ahead;
   d.linear_only = 0;

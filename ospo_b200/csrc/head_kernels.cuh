@@ -326,6 +326,37 @@ gen_embed_up_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __rest
 }
 
 // ---------------------------------------------------------------------------
+// Weight pre-packing for the decode step: W [rows, cols] bf16 row-major -> tiles [slab = rows/128][kb = cols/64] of
+// 16 KB, each the exact shared-memory image TMA would produce for a {64 cols x 128 rows} box with 128-byte swizzle
+// (row r at byte r*128, its 16-byte chunk c stored at chunk position c ^ (r & 7)).  The decode kernel then pulls a
+// tile with ONE contiguous bulk copy instead of 128 row requests: better DRAM locality (6.5 vs 6.1 TB/s streamed,
+// scripts/gpu_stream_probe.py) and no tensor-map traffic.  One thread moves one 16-byte chunk.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const __nv_bfloat16* __restrict__ w, int rows, int cols, uint4* __restrict__ packed) {
+  const int num_kb = (cols + 63) / 64;
+  const int64_t chunk = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // over tiles x 128 rows x 8 chunks
+  const int64_t total = static_cast<int64_t>((rows + 127) / 128) * num_kb * 1024;
+  if (chunk >= total) return;
+  const int c = static_cast<int>(chunk & 7);
+  const int r = static_cast<int>((chunk >> 3) & 127);
+  const int64_t tile = chunk >> 10;
+  const int kb = static_cast<int>(tile % num_kb);
+  const int64_t slab = tile / num_kb;
+  const int64_t row = slab * 128 + r;
+  const int col = kb * 64 + c * 8;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (row < rows && col + 8 <= cols) {
+    v = __ldg(reinterpret_cast<const uint4*>(w + row * cols + col));
+  } else if (row < rows && col < cols) {
+    __nv_bfloat16 tmp[8];
+    for (int j = 0; j < 8; ++j) tmp[j] = (col + j < cols) ? w[row * cols + col + j] : __float2bfloat16_rn(0.0f);
+    v = *reinterpret_cast<const uint4*>(tmp);
+  }
+  packed[tile * 1024 + r * 8 + (c ^ (r & 7))] = v;
+}
+
+// ---------------------------------------------------------------------------
 // CFG merge + temperature + softmax + inverse-CDF sampling on bf16 logits [2P, V]
 // (row 2k = conditional, row 2k+1 = unconditional: ospo/wrapper/image_generation.py:135-141,157-158).
 //   merge_mode 0 (reference bf16 semantics, op-by-op rounding, image_generation.py:160-161):

@@ -98,7 +98,8 @@ int launch_decode_gemm2_fused(const LaunchCtx& c, const __nv_bfloat16* act, cons
 int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
                          const __nv_bfloat16* w2, const float* b2, __nv_bfloat16* act, uint32_t* flag,
                          __nv_bfloat16* logits_dump, int n, int H, int E, int V, float cfg_weight, float temperature,
-                         int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead);
+                         int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead,
+                         const void* w1_packed = nullptr, const void* w2_packed = nullptr);
 
 // phase 1 of that kernel on its own: out[n, M] = bf16(act_fn(bf16(x W^T + b))), n <= 32 (gen_aligner's D x D Linear)
 int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* b,

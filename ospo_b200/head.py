@@ -186,6 +186,8 @@ class FusedGenHead(torch.nn.Module):
         self._cache_key = None
         self._cache: Optional[_HeadParams] = None
         self._flat: Optional[torch.Tensor] = None
+        self._packed = None
+        self._packed_key = None
 
     # ---- construction helpers -------------------------------------------------------------------
     @classmethod
@@ -217,6 +219,15 @@ class FusedGenHead(torch.nn.Module):
                     W2.detach().to(torch.bfloat16).contiguous(), B2.detach().to(torch.float32).contiguous())
             self._cache_key = key
         return self._cache
+
+    def _decode_packed(self, p: "_HeadParams"):
+        """W1 / W2 in the decode kernel's streaming layout (16 KB swizzled tiles), rebuilt when the operands change;
+        an extra copy of the weights (168 MB for the 7B head) kept only by heads that generate"""
+        key = (p.w1.data_ptr(), p.w2.data_ptr(), self._cache_key)
+        if self._packed_key != key or self._packed is None:
+            self._packed = (ops.pack_weight_impl(p.w1), ops.pack_weight_impl(p.w2))
+            self._packed_key = key
+        return self._packed
 
     def _flat_grad_buffer(self) -> torch.Tensor:
         n = ops.flat_grad_numel(self.n_embed, self.image_token_embed, self.image_token_size)
@@ -330,8 +341,9 @@ class FusedGenHead(torch.nn.Module):
             if embeds_out is None:
                 embeds_out = torch.empty(2 * P, wb.shape[0], dtype=torch.bfloat16, device=h.device)
             ne = (e, wa, ba, wb, bb, embeds_out)
+        packed = self._decode_packed(p) if (h.shape[0] <= 32 and os.environ.get("OSPO_HEAD_DECODE_PACKED", "1") != "0") else None
         ids, logits = ops.cfg_sample_impl(h, p.w1, p.b1, p.w2, p.b2, float(cfg_weight), float(temperature), u,
-                                          bool(greedy), mm, bool(return_logits), out, ne)
+                                          bool(greedy), mm, bool(return_logits), out, ne, packed)
         if next_embeds is not None:
             return (ids, logits, embeds_out) if return_logits else (ids, embeds_out)
         return (ids, logits) if return_logits else ids

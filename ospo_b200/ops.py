@@ -225,9 +225,23 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
 # --------------------------------------------------------------------------------------------------
 # CFG decode step
 # --------------------------------------------------------------------------------------------------
+def pack_weight_impl(w: Tensor) -> Tensor:
+    """[rows, cols] bf16 row-major weight -> the decode kernel's streaming layout (16 KB swizzled tiles, uint8 buffer)"""
+    _check_cuda(w)
+    assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.is_contiguous()
+    need = C.c_size_t()
+    lib = _abi.load()
+    _abi.check(lib.ospo_head_packed_weight_bytes(w.shape[0], w.shape[1], C.byref(need)), "ospo_head_packed_weight_bytes")
+    out = torch.empty(need.value, dtype=torch.uint8, device=w.device)
+    _abi.check(lib.ospo_head_pack_weight(w.data_ptr(), w.shape[0], w.shape[1], out.data_ptr(), _stream()),
+               "ospo_head_pack_weight")
+    return out
+
+
 def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, cfg_weight: float, temperature: float,
                uniforms: Tensor, greedy: bool, merge_mode: int, want_logits: bool = False,
-               out: Optional[Tensor] = None, next_embeds: Optional[tuple] = None) -> List[Tensor]:
+               out: Optional[Tensor] = None, next_embeds: Optional[tuple] = None,
+               packed: Optional[tuple] = None) -> List[Tensor]:
     """-> [ids[P] int64 (``out`` if given: the kernel writes the ids there), logits[2P, V] bf16 (empty unless want_logits)]
     (image_generation.py:156-164; row 2k cond / 2k+1 uncond).  Without want_logits the logits never leave the
     chip: the CFG merge, softmax weights and segment sums are produced in the GEMM epilogue."""
@@ -256,6 +270,8 @@ def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, c
     a.ids = ids.data_ptr()
     a.merged = None
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    if packed is not None:                      # (pack_weight_impl(w1), pack_weight_impl(w2))
+        a.w1_packed, a.w2_packed = packed[0].data_ptr(), packed[1].data_ptr()
     if next_embeds is not None:
         # (gen_embed, wa, ba, wb, bb, embeds_out[2P, D]): the next step's input embeddings, image_generation.py:166-168,
         # produced in the same launch chain (first aligner layer inside the sampler's finish kernel)

@@ -71,6 +71,7 @@ class FusedHeadAdamW:
         ts = (head.output_mlp_projector.weight, head.output_mlp_projector.bias, head.vision_head.weight,
               head.vision_head.bias)
         head._cache_key = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in ts)
+        head._packed = None        # the decode kernel's packed copy is stale after an update
 
     def _flat_grads(self, use_last_backward: bool) -> torch.Tensor:
         H, E, V = self._dims

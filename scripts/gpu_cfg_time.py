@@ -24,6 +24,8 @@ torch.manual_seed(0)
 head = FusedGenHead(Pm).to(dev).to(torch.bfloat16)
 p = head._kernel_params()
 alt = type(p)(p.w1.clone(), p.b1.clone(), p.w2.clone(), p.b2.clone())
+PACK = int(os.environ.get("PACK", "1"))
+pk = {id(p): (ops.pack_weight_impl(p.w1), ops.pack_weight_impl(p.w2)), id(alt): (ops.pack_weight_impl(alt.w1), ops.pack_weight_impl(alt.w2))}
 h = torch.randn(steps, 2 * P, H, device=dev).to(torch.bfloat16)
 u = torch.rand(steps, P, device=dev)
 ids_out = torch.empty(steps, P, dtype=torch.int64, device=dev)
@@ -35,7 +37,8 @@ def run(direct):
     for i in range(steps):
         w = p if (i & 1) == 0 or not ALT else alt
         if direct:
-            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
+            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], None,
+                                pk[id(w)] if PACK else None)
         else:
             ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
             ids_out[i].copy_(ids)
@@ -69,6 +72,6 @@ for merged, ahead, direct in ((1, 0, True), (1, 16, True), (1, 24, True), (1, 32
         if ref is None:
             ref = ids_out.clone()
         same = bool(torch.equal(ref, ids_out))
-        print(f"TIME HE={H} alt={ALT} merged={merged} l2_ahead={ahead:2d} direct_out={int(direct)}: {us:6.2f} us/step  {step_bytes / us / 1e3:7.1f} GB/s  ids_same={same}")
+        print(f"TIME pack={PACK} HE={H} alt={ALT} merged={merged} l2_ahead={ahead:2d} direct_out={int(direct)}: {us:6.2f} us/step  {step_bytes / us / 1e3:7.1f} GB/s  ids_same={same}")
 lib.ospo_head_set_decode_merged(1)
 lib.ospo_head_set_decode_l2_ahead(24)

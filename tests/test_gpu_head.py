@@ -584,8 +584,10 @@ def test_cfg_sample_concurrent_streams_and_graphs():
     fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
     g = torch.Generator().manual_seed(78)
     lib = _abi.load()
+    z = torch.zeros(2 * P, H, dtype=torch.bfloat16, device=dev)
+    fh.cfg_sample(z, 5.0, 1.0, greedy=True)          # first call also packs the weights for the decode kernel
     c0 = lib.ospo_head_launch_count()
-    fh.cfg_sample(torch.zeros(2 * P, H, dtype=torch.bfloat16, device=dev), 5.0, 1.0, greedy=True)
+    fh.cfg_sample(z, 5.0, 1.0, greedy=True)
     assert lib.ospo_head_launch_count() - c0 == 2, "expected the one-kernel decode step (+ finish) on this shape"
     hs = torch.randn(3, n, 2 * P, H, generator=g).to(torch.bfloat16).to(dev)
     us = torch.rand(3, n, P, generator=g).to(dev)
@@ -625,6 +627,25 @@ def test_cfg_sample_concurrent_streams_and_graphs():
                 fh.cfg_sample(hs[0, i], 5.0, 1.0, uniforms=us[0, i], out=out[0, i])
         torch.cuda.synchronize()
         assert torch.equal(gout, serial[2]) and torch.equal(out[0], serial[0])
+
+
+def test_cfg_sample_packed_weights_equal_tensor_map_path(monkeypatch):
+    """the pre-packed weight layout (one contiguous 16 KB bulk copy per tile) feeds the MMAs the same bytes as the
+    tensor-map loads: identical logits and ids, including ragged E / H (zero-filled tile edges)"""
+    dev = _cuda()
+    for H, E in ((512, 2560), (328, 200)):
+        V, P = 16384, 7
+        head_b = O.make_head(H, E, V, seed=H, w2_gain=4.0).to(torch.bfloat16)
+        fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+        g = torch.Generator().manual_seed(5)
+        h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16).to(dev)
+        u = torch.rand(P, generator=g).to(dev)
+        ids_p, lg_p = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, return_logits=True)
+        monkeypatch.setenv("OSPO_HEAD_DECODE_PACKED", "0")
+        ids_t, lg_t = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, return_logits=True)
+        monkeypatch.delenv("OSPO_HEAD_DECODE_PACKED")
+        torch.cuda.synchronize()
+        assert torch.equal(lg_p, lg_t) and torch.equal(ids_p, ids_t)
 
 
 def test_cfg_sample_7b_shape_p16():

@@ -289,6 +289,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       pdl_wait();
       trace_stamp(dims.trace_id, 2);
       int tile_no = 0;
+      bool sync_wait = true;
       for (int t = dom_first; t < dom_tiles; t += dom_stride, ++tile_no) {
         const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
         const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
@@ -296,12 +297,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int kb0 = (t % ksplits) * dims.kb_per_split;
         const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
         if (dims.sync_ctr != nullptr && is_leader && tile_no > 0 && tile_no < dims.sync_tiles) {
-          // every cluster announces its tile_no-th tile and waits (at most ~40 us) for the others to get there
+          // every cluster announces its tile_no-th tile and waits (at most ~40 us) for the others to get there; a
+          // cluster that ever times out (a straggler exists: SMs shared with another kernel) stops waiting for good,
+          // so the worst case costs one time-out per cluster and launch
           atomicAdd(dims.sync_ctr, 1u);
-          const uint32_t want = static_cast<uint32_t>(tile_no) * static_cast<uint32_t>(num_clusters);
-          const uint64_t t_start = globaltimer_ns();
-          while (*reinterpret_cast<volatile uint32_t*>(dims.sync_ctr) < want) {
-            if (globaltimer_ns() - t_start > 40000ull) break;
+          if (sync_wait) {
+            const uint32_t want = static_cast<uint32_t>(tile_no) * static_cast<uint32_t>(num_clusters);
+            const uint64_t t_start = globaltimer_ns();
+            while (*reinterpret_cast<volatile uint32_t*>(dims.sync_ctr) < want) {
+              if (globaltimer_ns() - t_start > 40000ull) {
+                sync_wait = false;
+                break;
+              }
+            }
           }
         }
         for (int kb = kb0; kb < kb1; ++kb) {

@@ -198,7 +198,15 @@ __global__ void row_coef_kernel(const float* __restrict__ grad_seq, const int64_
 //   dlogits[r, v] = c_r * ([v == label_r] - exp(logit[r, v] - lse_r))
 // Block = 128 threads x 8 columns (16-byte vectors) = 1024 columns, looping over ROWS_PER_BLOCK rows.
 // ---------------------------------------------------------------------------
-constexpr int DL_ROWS_PER_BLOCK = 128;
+constexpr int DL_ROWS_PER_BLOCK = 256;
+
+__device__ __forceinline__ float dl_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int DL_UNROLL = 4;  // rows in flight per thread: one 16-byte load each (memory-level parallelism)
 
 __global__ void __launch_bounds__(128)
 dlogits_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
@@ -210,29 +218,38 @@ dlogits_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __
   const int r1 = min(rows, r0 + DL_ROWS_PER_BLOCK);
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   constexpr float LOG2E = 1.4426950408889634f;
-  for (int r = r0; r < r1; ++r) {
-    uint4* ptr = reinterpret_cast<uint4*>(logits + static_cast<int64_t>(r) * ld + col);
-    const uint4 u = *ptr;
-    const float lse = __ldg(row_lse + r) * LOG2E;
-    const float c = __ldg(row_coef + r);
-    const int rel = static_cast<int>(__ldg(labels + r)) - col;
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
+  for (int rb = r0; rb < r1; rb += DL_UNROLL) {
+    uint4 u[DL_UNROLL];
+    float lse[DL_UNROLL], c[DL_UNROLL];
+    int rel[DL_UNROLL];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-      const float l0 = __low2float(p), l1 = __high2float(p);
-      float d0 = -exp2f(fmaf(l0, LOG2E, -lse));
-      float d1 = -exp2f(fmaf(l1, LOG2E, -lse));
-      if (rel == 2 * k) d0 += 1.0f;
-      if (rel == 2 * k + 1) d1 += 1.0f;
-      d0 = bf16_round(c * d0);
-      d1 = bf16_round(c * d1);
-      cs[2 * k] += d0;
-      cs[2 * k + 1] += d1;
-      o[k] = pack_bf16x2(d0, d1);
+    for (int i = 0; i < DL_UNROLL; ++i) {
+      const int r = min(rb + i, r1 - 1);  // clamped rows are loaded but not stored
+      u[i] = *reinterpret_cast<const uint4*>(logits + static_cast<int64_t>(r) * ld + col);
+      lse[i] = __ldg(row_lse + r) * LOG2E;
+      c[i] = __ldg(row_coef + r);
+      rel[i] = static_cast<int>(__ldg(labels + r)) - col;
     }
-    *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int i = 0; i < DL_UNROLL; ++i) {
+      if (rb + i >= r1) break;
+      const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float l0 = __uint_as_float(w[k] << 16), l1 = __uint_as_float(w[k] & 0xFFFF0000u);
+        float d0 = -dl_ex2(fmaf(l0, LOG2E, -lse[i]));
+        float d1 = -dl_ex2(fmaf(l1, LOG2E, -lse[i]));
+        if (rel[i] == 2 * k) d0 += 1.0f;
+        if (rel[i] == 2 * k + 1) d1 += 1.0f;
+        d0 = bf16_round(c[i] * d0);
+        d1 = bf16_round(c[i] * d1);
+        cs[2 * k] += d0;
+        cs[2 * k + 1] += d1;
+        o[k] = pack_bf16x2(d0, d1);
+      }
+      *reinterpret_cast<uint4*>(logits + static_cast<int64_t>(rb + i) * ld + col) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
   if (db2 != nullptr) {
 #pragma unroll

@@ -669,7 +669,12 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
     }
     return;
   }
+  // the tile exponent, the sum of this thread's segment and the uniform are requested together (one L2 round trip).
+  // (Also preloading every segment's 32 weights, so that the winner could walk them from registers, was measured
+  // slower: 64 KB of 16-byte-strided loads per block cost more than the one dependent 128-byte load they save.)
   const float kt = b.tile_k[p * ntile + tid / (SAMPLE_TILE / SAMPLE_SEG)];
+  const float ss_raw = b.seg_sum[static_cast<int64_t>(p) * SAMPLE_THREADS + tid];
+  const float u01 = __ldg(uniforms + p);
   float K = kt;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) K = fmaxf(K, __shfl_xor_sync(0xffffffffu, K, off));
@@ -679,7 +684,7 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
 #pragma unroll
   for (int w = 1; w < SAMPLE_THREADS / 32; ++w) K = fmaxf(K, wmax[w]);
   const float f = pow2_factor(__fsub_rn(kt, K));
-  seg_sum[tid] = __fmul_rn(b.seg_sum[static_cast<int64_t>(p) * SAMPLE_THREADS + tid], f);
+  seg_sum[tid] = __fmul_rn(ss_raw, f);
   __syncthreads();
   constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
   if (tid < NGRP) {
@@ -694,7 +699,7 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
   if (tid == 0) {
     int segi;
     float base, target;
-    cdf_descent(seg_sum, grp_sum, __ldg(uniforms + p), segi, base, target);
+    cdf_descent(seg_sum, grp_sum, u01, segi, base, target);
     bc_seg = segi;
     bc_base = base;
     bc_target = target;

@@ -25,6 +25,8 @@ torch.manual_seed(0)
 head = FusedGenHead(Pm).to(dev).to(torch.bfloat16)
 p = head._kernel_params()
 alt = type(p)(p.w1.clone(), p.b1.clone(), p.w2.clone(), p.b2.clone())
+PACK = int(os.environ.get("PACK", "1"))
+pk = {id(p): (ops.pack_weight_impl(p.w1), ops.pack_weight_impl(p.w2)), id(alt): (ops.pack_weight_impl(alt.w1), ops.pack_weight_impl(alt.w2))}
 h = torch.randn(steps, 2 * P, H, device=dev).to(torch.bfloat16)
 u = torch.rand(steps, P, device=dev)
 ids_out = torch.empty(steps, P, dtype=torch.int64, device=dev)
@@ -36,7 +38,8 @@ def run():
     for i in range(steps):
         w = p if (i & 1) == 0 or not ALT else alt
         if DIRECT:
-            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i])
+            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], None,
+                                pk[id(w)] if PACK else None)
         else:
             ids, _ = ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0)
             ids_out[i].copy_(ids)

@@ -532,13 +532,6 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
   d.V = V;
   d.num_m1 = (E + kBM - 1) / kBM;
   d.num_m2 = (V + kBM - 1) / kBM;
-  int ks = decode_gemm1_splits(c.num_sms, H, E);
-  ks = ks >= 8 ? 8 : ks >= 4 ? 4 : ks >= 2 ? 2 : 1;  // cluster sizes
-  int per;
-  gemm_split_plan((H + kBK - 1) / kBK, ks, &ks, &per);
-  if (ks != 1 && ks != 2 && ks != 4 && ks != 8) return -100;
-  d.ks = ks;
-  d.kb_per_split = per;
   d.b1 = b1;
   d.act = act;
   d.flag = flag;
@@ -548,11 +541,6 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
   d.l2_ahead = l2_ahead < 0 ? 0 : l2_ahead;
   d.linear_only = 0;
   d.gelu = 1;
-  const int max_ctas = (c.num_sms / ks) * ks;
-  const int need1 = d.num_m1 * ks;
-  if (need1 > max_ctas) return -100;
-  int G = d.num_m2 < max_ctas ? ((d.num_m2 + ks - 1) / ks) * ks : max_ctas;
-  if (G < need1) G = need1;
   CUtensorMap t_w1, t_h, t_w2, t_act;
   int rc;
   if ((rc = make_tmap_bf16_2d(&t_w1, w1, E, H, H, kBM)) != 0) return rc;
@@ -560,14 +548,31 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
   if ((rc = make_tmap_bf16_2d(&t_w2, w2, V, E, E, kBM)) != 0) return rc;
   if ((rc = make_tmap_bf16_2d(&t_act, act, n, E, E, kBN)) != 0) return rc;
   const bool tdiv = (temperature != 1.0f);
-  if (merge_mode == 0) {
-    if (tdiv)
-      return run_merged<0, true>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
-    return run_merged<0, false>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
+  // phase-1 split: as many k-splits as fill the SMs (cluster sizes 8, 4, 2, 1); a cluster size the device cannot
+  // keep resident G / ks times (e.g. 16 clusters of 8 CTAs that each own an SM's shared memory) is halved
+  int want = decode_gemm1_splits(c.num_sms, H, E);
+  want = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
+  for (; want >= 1; want >>= 1) {
+    int ks, per;
+    gemm_split_plan((H + kBK - 1) / kBK, want, &ks, &per);
+    if (ks != 1 && ks != 2 && ks != 4 && ks != 8) continue;
+    d.ks = ks;
+    d.kb_per_split = per;
+    const int max_ctas = (c.num_sms / ks) * ks;
+    const int need1 = d.num_m1 * ks;
+    if (need1 > max_ctas) continue;
+    int G = d.num_m2 < max_ctas ? ((d.num_m2 + ks - 1) / ks) * ks : max_ctas;
+    if (G < need1) G = need1;
+    if (merge_mode == 0) {
+      rc = tdiv ? run_merged<0, true>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf)
+                : run_merged<0, false>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
+    } else {
+      rc = tdiv ? run_merged<1, true>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf)
+                : run_merged<1, false>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
+    }
+    if (rc != -100) return rc;
   }
-  if (tdiv)
-    return run_merged<1, true>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
-  return run_merged<1, false>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf);
+  return -100;
 }
 
 }  // namespace ospo

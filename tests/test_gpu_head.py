@@ -648,6 +648,32 @@ def test_cfg_sample_packed_weights_equal_tensor_map_path(monkeypatch):
         assert torch.equal(lg_p, lg_t) and torch.equal(ids_p, ids_t)
 
 
+def test_cfg_sample_1b_shape_uses_one_kernel_step():
+    """Janus-Pro-1B-shaped head (H = E = 2048, BASELINE.json configs[0]): eight k-splits would need 16 resident
+    clusters of 8; the launcher falls back to clusters of 4 and still runs the step as one kernel (+ finish)"""
+    from ospo_b200 import _abi
+
+    dev = _cuda()
+    H = E = 2048
+    V, P = 16384, 16
+    head_b = O.make_head(H, E, V, seed=2048, w2_gain=4.0).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    g = torch.Generator().manual_seed(2049)
+    h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16)
+    u = torch.rand(P, generator=g)
+    lib = _abi.load()
+    fh.cfg_sample(h.to(dev), 5.0, 1.0, greedy=True)
+    c0 = lib.ospo_head_launch_count()
+    ids, lg = fh.cfg_sample(h.to(dev), 5.0, 1.0, uniforms=u.to(dev), return_logits=True)
+    torch.cuda.synchronize()
+    assert lib.ospo_head_launch_count() - c0 == 2
+    with torch.no_grad():
+        ref = head_b(h)
+    torch.testing.assert_close(lg.float().cpu(), ref.float(), rtol=2e-2, atol=3e-2)
+    oid, *_ = O.cfg_sample_det(lg.cpu(), 5.0, 1.0, u, merge_mode=0)
+    assert torch.equal(ids.cpu(), oid)
+
+
 def test_cfg_sample_7b_shape_p16():
     """BASELINE.json configs[3] shape: P=16 (32 CFG rows), 7B-shaped head; a few steps vs the bf16 oracle."""
     dev = _cuda()

@@ -45,6 +45,7 @@ struct GemmDims {
   // from HBM several times.  The wait is bounded and falls through (it is a performance hint, never a dependency).
   uint32_t* sync_ctr;
   int sync_tiles;
+  int sync_stride;  // lock-step every this many tiles (short tiles need it less often)
 };
 
 // where a row-mapped output row lands: logical row r -> physical row of a [segments, pitch, cols] tensor
@@ -296,13 +297,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         const int kb0 = (t % ksplits) * dims.kb_per_split;
         const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
-        if (dims.sync_ctr != nullptr && is_leader && tile_no > 0 && tile_no < dims.sync_tiles) {
+        if (dims.sync_ctr != nullptr && is_leader && tile_no > 0 && tile_no < dims.sync_tiles &&
+            tile_no % dims.sync_stride == 0) {
           // every cluster announces its tile_no-th tile and waits (at most ~40 us) for the others to get there; a
           // cluster that ever times out (a straggler exists: SMs shared with another kernel) stops waiting for good,
           // so the worst case costs one time-out per cluster and launch
           atomicAdd(dims.sync_ctr, 1u);
           if (sync_wait) {
-            const uint32_t want = static_cast<uint32_t>(tile_no) * static_cast<uint32_t>(num_clusters);
+            const uint32_t want = static_cast<uint32_t>(tile_no / dims.sync_stride) * static_cast<uint32_t>(num_clusters);
             const uint64_t t_start = globaltimer_ns();
             while (*reinterpret_cast<volatile uint32_t*>(dims.sync_ctr) < want) {
               if (globaltimer_ns() - t_start > 40000ull) {
@@ -606,10 +608,18 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
 
   dims.sync_ctr = nullptr;
   dims.sync_tiles = 0;
+  dims.sync_stride = 1;
   if (sync_ctr != nullptr && !Cfg::CLUSTER_SPLIT && !dims.die_split && clusters >= 2 && num_tiles / clusters >= 2) {
     if (cudaMemsetAsync(sync_ctr, 0, sizeof(uint32_t), stream) != cudaSuccess) return -4;
     dims.sync_ctr = sync_ctr;
     dims.sync_tiles = num_tiles / clusters;  // the full waves; the ragged tail runs free
+    static const int stride_kb = [] {
+      const char* e = getenv("OSPO_HEAD_SYNC_STRIDE_KB");
+      return e ? atoi(e) : 128;  // short tiles (K = 4096: 64 k-blocks) lock-step every second tile: -1.4 % step time
+    }();
+    const int kb_per_tile = (num_kb + dims.k_splits - 1) / dims.k_splits;
+    dims.sync_stride = stride_kb > 0 ? (stride_kb + kb_per_tile - 1) / kb_per_tile : 1;
+    if (dims.sync_stride < 1) dims.sync_stride = 1;
   }
 
   cudaLaunchConfig_t cfg = {};

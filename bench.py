@@ -355,6 +355,30 @@ def main():
                "api": "FusedGenHead.simpo(hidden, labels) + loss.backward(); pinned host inputs, double-buffered H2D"}
         del dev_h, dev_l, host_h, host_l
 
+    # ---- secondary: the reference's default training configuration freezes gen_head (configs/step5.yaml:59-66):
+    #      only dX leaves the head, 4 (HE + EV) flop per image token ---------------------------------
+    frozen = None
+    if rank == 0 and world == 1 and not args.skip_cfg:
+        for prm in head.parameters():
+            prm.requires_grad_(False)
+        for _ in range(3):
+            step(hidden, labels)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = max(3, min(10, args.steps))
+        f0.record()
+        for _ in range(nrep):
+            step(hidden, labels)
+        f1.record()
+        torch.cuda.synchronize()
+        ms_f = f0.elapsed_time(f1) / nrep
+        tf_f = tokens_per_step_rank * (4 * (H7B * E7B + E7B * V)) / (ms_f / 1e3) / 1e12
+        frozen = {"workload": "same batch, gen_head frozen (the reference's default, configs/step5.yaml:59-66): forward + dX only",
+                  "ms_per_step": ms_f, "image_tokens_per_s": tokens_per_step_rank / (ms_f / 1e3), "tflops": tf_f,
+                  "frac_of_peak": tf_f / peaks["tf_burst"]}
+        for prm in head.parameters():
+            prm.requires_grad_(True)
+
     # ---- secondary: CFG decode (configs[3]) ---------------------------------------------------------
     cfg = None
     if rank == 0 and not args.skip_cfg:
@@ -389,7 +413,7 @@ def main():
                        "l2": "inputs larger than L2 (604 MB hidden states + 2.4 GB bf16 logits spill per step)",
                        "cta_group": _abi.load().ospo_head_set_cta_group(0), "loss": loss_val},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu, "cfg": cfg, "clip_adamw": opt_res,
+            "cpu_baseline": cpu, "frozen_head": frozen, "cfg": cfg, "clip_adamw": opt_res,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -506,17 +506,21 @@ static int launch_sampler(const ospo_cfg_args* a, int pairs, cudaStream_t st) {
   const __nv_bfloat16* lg = static_cast<const __nv_bfloat16*>(a->logits);
   const bool tdiv = (a->temperature != 1.0f);
   const int mode = (a->merge_mode == OSPO_MERGE_FP32) ? 1 : 0;
-#define OSPO_LAUNCH_SAMPLER(MODE, TDIV, GREEDY)                                                                   \
-  cfg_merge_sample_kernel<MODE, TDIV, GREEDY><<<pairs, SAMPLE_THREADS, 0, st>>>(lg, V, V, a->cfg_weight,         \
-                                                                                a->temperature, a->uniforms,    \
-                                                                                a->ids, a->merged)
-  if (a->greedy) {
-    if (mode == 0) { if (tdiv) OSPO_LAUNCH_SAMPLER(0, true, true); else OSPO_LAUNCH_SAMPLER(0, false, true); }
-    else { if (tdiv) OSPO_LAUNCH_SAMPLER(1, true, true); else OSPO_LAUNCH_SAMPLER(1, false, true); }
-  } else {
-    if (mode == 0) { if (tdiv) OSPO_LAUNCH_SAMPLER(0, true, false); else OSPO_LAUNCH_SAMPLER(0, false, false); }
-    else { if (tdiv) OSPO_LAUNCH_SAMPLER(1, true, false); else OSPO_LAUNCH_SAMPLER(1, false, false); }
+  // bf16 merge with a cfg_weight that is itself a bf16 value (5.0, 7.5, ...): merge on the bf16x2 pipe
+  const bool wbf = (mode == 0) && bf16_exact(a->cfg_weight);
+#define OSPO_LAUNCH_SAMPLER(MODE, TDIV, GREEDY, WBF)                                                              \
+  cfg_merge_sample_kernel<MODE, TDIV, GREEDY, WBF><<<pairs, SAMPLE_THREADS, 0, st>>>(lg, V, V, a->cfg_weight,    \
+                                                                                     a->temperature, a->uniforms, \
+                                                                                     a->ids, a->merged)
+#define OSPO_LAUNCH_SAMPLER_G(GREEDY)                                                                             \
+  if (mode == 0) {                                                                                                \
+    if (wbf) { if (tdiv) OSPO_LAUNCH_SAMPLER(0, true, GREEDY, true); else OSPO_LAUNCH_SAMPLER(0, false, GREEDY, true); } \
+    else { if (tdiv) OSPO_LAUNCH_SAMPLER(0, true, GREEDY, false); else OSPO_LAUNCH_SAMPLER(0, false, GREEDY, false); }  \
+  } else {                                                                                                        \
+    if (tdiv) OSPO_LAUNCH_SAMPLER(1, true, GREEDY, false); else OSPO_LAUNCH_SAMPLER(1, false, GREEDY, false);     \
   }
+  if (a->greedy) { OSPO_LAUNCH_SAMPLER_G(true) } else { OSPO_LAUNCH_SAMPLER_G(false) }
+#undef OSPO_LAUNCH_SAMPLER_G
 #undef OSPO_LAUNCH_SAMPLER
   return check_launch();
 }

@@ -3,6 +3,8 @@
 // order.  oracle/cfg_sample.c restates every function here operation for operation.
 #pragma once
 
+#include <cstring>
+
 #include "ptx.cuh"
 
 namespace ospo {
@@ -68,6 +70,45 @@ template <int MODE, bool TDIV>
 __device__ __forceinline__ void cfg_merge2(uint32_t wc, uint32_t wu, float w, float T, float& t0, float& t1) {
   cfg_merge_vals<MODE, TDIV>(__uint_as_float(wc << 16), __uint_as_float(wc & 0xFFFF0000u), __uint_as_float(wu << 16),
                              __uint_as_float(wu & 0xFFFF0000u), w, T, t0, t1);
+}
+
+// The same merge on the bf16 pipe (MODE 0 with a cfg_weight that is exactly a bf16 value, e.g. the default 5.0):
+// sub / mul / add.rn.bf16x2 round the exact result once; the reference rounds fp32(a op b) to bf16.  The two agree
+// bit for bit: for operands with 8-bit significands the fp32 result is exact unless the exponents differ by more
+// than 16, and then it lies within 2^-16 of the larger operand, far from any bf16 rounding boundary; a product of
+// two 8-bit significands always fits fp32.  Inline PTX, so the compiler cannot contract mul + add into an fma.
+__device__ __forceinline__ uint32_t bf16x2_sub(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// is w exactly representable in bf16 (then the packed path may be used)?
+__host__ __device__ inline bool bf16_exact(float w) {
+  uint32_t u;
+  memcpy(&u, &w, 4);
+  return (u & 0xFFFFu) == 0u;
+}
+// wc = two conditional logits, wu = the two unconditional ones (packed bf16), w2 = cfg_weight in both halves
+template <bool TDIV>
+__device__ __forceinline__ void cfg_merge2_hw(uint32_t wc, uint32_t wu, uint32_t w2, float T, float& t0, float& t1) {
+  const uint32_t m = bf16x2_add(wu, bf16x2_mul(w2, bf16x2_sub(wc, wu)));
+  t0 = __uint_as_float(m << 16);
+  t1 = __uint_as_float(m & 0xFFFF0000u);
+  if (TDIV) {
+    t0 = __fdiv_rn(t0, T);
+    t1 = __fdiv_rn(t1, T);
+    round2_bf16(t0, t1);
+  }
 }
 
 // butterfly tree sum of 32 registers: x[j] += x[j + 16] (j < 16), then strides 8, 4, 2, 1 -- the order in which a

@@ -489,7 +489,7 @@ struct EpiGeluBwd {
 // so the merged logits never exist in HBM; cfg_finish_kernel completes the draw from 512 sums per pair.
 // Needs TILE_M == 128 (one CTA = one tile) and BN == 32 (one chunk = all columns).
 // ---------------------------------------------------------------------------
-template <int MODE, bool TDIV>
+template <int MODE, bool TDIV, bool WBF = false>
 struct EpiCfgFused {
   struct Params {
     const float* bias;            // b2 [V]
@@ -523,23 +523,36 @@ struct EpiCfgFused {
     int* sm_i = reinterpret_cast<int*>(sm_v + 64);  // [4][16] greedy index
     const int tr = (d.trace_id > 0 && threadIdx.x == 64) ? 5 : 0;  // epilogue-internal timeline (trace row 5)
     trace_stamp(tr, 0);
-    // logits exactly as the reference's bf16 Linear output
+    // logits exactly as the reference's bf16 Linear output: pr[k] = (cond, uncond) of pair k as packed bf16
+    uint32_t pr[16];
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      v[j] += st.rb;
-      v[j + 1] += st.rb;
-      round2_bf16(v[j], v[j + 1]);
-    }
+    for (int k = 0; k < 16; ++k) pr[k] = pack_bf16x2(v[2 * k] + st.rb, v[2 * k + 1] + st.rb);
     if (p.logits_dump != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < valid) p.logits_dump[static_cast<int64_t>(col0 + j) * p.ld + row] = __float2bfloat16_rn(v[j]);
+      for (int j = 0; j < 32; ++j) {
+        if (j < valid) {
+          const uint16_t h16 = static_cast<uint16_t>((j & 1) ? (pr[j >> 1] >> 16) : (pr[j >> 1] & 0xFFFFu));
+          reinterpret_cast<uint16_t*>(p.logits_dump)[static_cast<int64_t>(col0 + j) * p.ld + row] = h16;
+        }
+      }
     }
     float t[16];
+    if constexpr (WBF) {
+      // bf16-exact cfg_weight: the op-by-op bf16 merge runs on the bf16x2 pipe, two pairs per instruction
+      const uint32_t w2 = pack_bf16x2(p.cfg_weight, p.cfg_weight);
 #pragma unroll
-    for (int k = 0; k < 16; k += 2)
-      cfg_merge_vals<MODE, TDIV>(v[2 * k], v[2 * k + 2], v[2 * k + 1], v[2 * k + 3], p.cfg_weight, p.temperature, t[k],
-                                 t[k + 1]);
+      for (int k = 0; k < 16; k += 2) {
+        const uint32_t c2 = __byte_perm(pr[k], pr[k + 1], 0x5410);  // (cond k, cond k+1)
+        const uint32_t u2 = __byte_perm(pr[k], pr[k + 1], 0x7632);  // (uncond k, uncond k+1)
+        cfg_merge2_hw<TDIV>(c2, u2, w2, p.temperature, t[k], t[k + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; k += 2)
+        cfg_merge_vals<MODE, TDIV>(__uint_as_float(pr[k] << 16), __uint_as_float(pr[k + 1] << 16),
+                                   __uint_as_float(pr[k] & 0xFFFF0000u), __uint_as_float(pr[k + 1] & 0xFFFF0000u),
+                                   p.cfg_weight, p.temperature, t[k], t[k + 1]);
+    }
     trace_stamp(tr, 1);
     if (p.greedy) {
       // per-pair arg-max over the tile: (value, code) with the lowest code on ties
@@ -583,11 +596,9 @@ struct EpiCfgFused {
     // tile exponent per pair: 16-way transpose-reduce (max is exact, any order)
     const int mypair = transpose_reduce_pair_of_lane(lane);
     {
-      float nn[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) nn[k] = exp_n_only(t[k]);
-      const float kw = warp_transpose_reduce16(nn, lane, OpMax());
-      if ((lane & 1) == 0) sm_k[q * 16 + mypair] = kw;
+      // n(t) is non-decreasing in t, so the tile's largest exponent is n(largest t): reduce t, convert once
+      const float tw = warp_transpose_reduce16(t, lane, OpMax());
+      if ((lane & 1) == 0) sm_k[q * 16 + mypair] = exp_n_only(tw);
     }
     trace_stamp(tr, 2);
     named_bar_sync(1, 128);

@@ -416,7 +416,8 @@ __device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* g
 
 // grid.x = number of (cond, uncond) pairs; logits row pitch ld.  vocab must be 16384 (= 512 * 32).
 // Register-resident: thread i owns segment i (codes 32 i .. 32 i + 31).
-template <int MODE, bool TDIV, bool GREEDY>
+// WBF: MODE 0 with a bf16-exact cfg_weight -> the merge runs on the bf16x2 pipe (cfg_math.cuh)
+template <int MODE, bool TDIV, bool GREEDY, bool WBF = false>
 __global__ void __launch_bounds__(SAMPLE_THREADS, 2)
 cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int vocab, float cfg_weight,
                         float temperature, const float* __restrict__ uniforms, int64_t* __restrict__ ids,
@@ -446,8 +447,14 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
     for (int i = 0; i < 4; ++i) {
       const uint32_t wa[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, wb[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        cfg_merge2<MODE, TDIV>(wa[k], wb[k], cfg_weight, temperature, t[8 * i + 2 * k], t[8 * i + 2 * k + 1]);
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (WBF) {
+          const uint32_t w2 = pack_bf16x2(cfg_weight, cfg_weight);
+          cfg_merge2_hw<TDIV>(wa[k], wb[k], w2, temperature, t[8 * i + 2 * k], t[8 * i + 2 * k + 1]);
+        } else {
+          cfg_merge2<MODE, TDIV>(wa[k], wb[k], cfg_weight, temperature, t[8 * i + 2 * k], t[8 * i + 2 * k + 1]);
+        }
+      }
     }
   }
   if (merged_out != nullptr) {
@@ -496,9 +503,12 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
     return;
   } else {
     // ---- tile exponent: K_tile = max n over the 4 segments (= 4 adjacent lanes) of a 128-code tile ------
-    float kt = exp_n_only(t[0]);
+    // (n is a non-decreasing function of t -- a correctly rounded multiply by a positive constant, two clamps and a
+    // round-to-integer -- so max n = n(max t): one fmax per code instead of four operations)
+    float tmax = t[0];
 #pragma unroll
-    for (int j = 1; j < SAMPLE_SEG; ++j) kt = fmaxf(kt, exp_n_only(t[j]));
+    for (int j = 1; j < SAMPLE_SEG; ++j) tmax = fmaxf(tmax, t[j]);
+    float kt = exp_n_only(tmax);
     kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 1));
     kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 2));
     // ---- weights relative to K_tile (in place) and the segment's tree sum -------------------------

@@ -29,7 +29,7 @@ struct Runtime {
   int decode_cluster = 1;  // GEMM1 k-splits combined in-cluster through DSMEM (0 = HBM partials + finalize kernel)
   int decode_merged = 1;   // GEMM1 + GEMM2 + CFG epilogue as one persistent kernel (0 = two GEMM launches)
   int tile_sync = 1;       // wave lock-step of the persistent training GEMMs (OSPO_HEAD_TILE_SYNC)
-  int decode_l2_ahead = 24;  // merged kernel: W2 k-blocks per CTA requested into L2 while the activation flag is closed
+  int decode_l2_ahead = 16;  // merged kernel: W2 k-blocks per CTA requested into L2 while the activation flag is closed
   bool trace_on = false;   // ospo_head_trace installed a timeline buffer
   unsigned long long* trace_buf = nullptr;
   uint32_t* wd_host = nullptr;
@@ -571,7 +571,8 @@ static int cfg_sample_step(const ospo_cfg_args* a, ospo_stream_t stream, const E
     if (lrc == 0) {
       g_launches.fetch_add(1, std::memory_order_relaxed);
       KernelSpan ks(st, OSPO_K_SAMPLER);
-      if (launch_plain(cfg_finish_kernel, dim3(pairs), dim3(SAMPLE_THREADS), st, c.pdl, w.fused, s.vocab, a->uniforms,
+      if (launch_plain(eu.gen_embed ? cfg_finish_kernel<true> : cfg_finish_kernel<false>, dim3(pairs), dim3(SAMPLE_THREADS), st,
+                       c.pdl, w.fused, s.vocab, a->uniforms,
                        a->greedy, a->ids, c.trace ? 1 : 0, eu) != cudaSuccess)
         return OSPO_ERR_LAUNCH;
       g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -616,7 +617,8 @@ static int cfg_sample_step(const ospo_cfg_args* a, ospo_stream_t stream, const E
     }
     if (rc) return rc;
     KernelSpan ks(st, OSPO_K_SAMPLER);
-    if (launch_plain(cfg_finish_kernel, dim3(pairs), dim3(SAMPLE_THREADS), st, c.pdl, w.fused, s.vocab, a->uniforms,
+    if (launch_plain(eu.gen_embed ? cfg_finish_kernel<true> : cfg_finish_kernel<false>, dim3(pairs), dim3(SAMPLE_THREADS), st,
+                       c.pdl, w.fused, s.vocab, a->uniforms,
                      a->greedy, a->ids, c.trace ? 1 : 0, eu) != cudaSuccess)
       return OSPO_ERR_LAUNCH;
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -78,12 +78,12 @@ __device__ __forceinline__ void bulk_prefetch_tile(const uint8_t* gsrc) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(kABytes) : "memory");
 }
 
-template <int MODE, bool TDIV, bool WBF>
+template <int MODE, bool TDIV, bool WBF, bool GREEDY>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_h,
                      const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_act,
-                     MergedDims d, typename EpiCfgFused<MODE, TDIV, WBF>::Params ep) {
-  using Epi = EpiCfgFused<MODE, TDIV, WBF>;
+                     MergedDims d, typename EpiCfgFused<MODE, TDIV, WBF, GREEDY>::Params ep) {
+  using Epi = EpiCfgFused<MODE, TDIV, WBF, GREEDY>;
   constexpr int tr1 = 1, tr2 = 2;
   if (d.linear_only) pdl_launch_dependents();  // nothing below needs every CTA resident: the successor may queue up
   if (threadIdx.x == 0) stamp(d.trace, tr1, 0);
@@ -407,11 +407,11 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
 // instantiation for the Linear cost 5 us per step).
 int g_last_variant = 1;  // MODE 0, T == 1, bf16-exact cfg_weight: the reference's defaults
 
-template <int MODE, bool TDIV, bool WBF>
+template <int MODE, bool TDIV, bool WBF, bool GREEDY>
 int run_linear(const LaunchCtx& c, const CUtensorMap& t_w, const CUtensorMap& t_x, const MergedDims& d) {
-  using Epi = EpiCfgFused<MODE, TDIV, WBF>;
+  using Epi = EpiCfgFused<MODE, TDIV, WBF, GREEDY>;
   typename Epi::Params p{};
-  auto kern = decode_merged_kernel<MODE, TDIV, WBF>;
+  auto kern = decode_merged_kernel<MODE, TDIV, WBF, GREEDY>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -3;
@@ -438,14 +438,14 @@ int run_linear(const LaunchCtx& c, const CUtensorMap& t_w, const CUtensorMap& t_
   return cudaLaunchKernelEx(&cfg, kern, t_w, t_x, t_w, t_x, d, p) == cudaSuccess ? 0 : -4;
 }
 
-template <int MODE, bool TDIV, bool WBF>
+template <int MODE, bool TDIV, bool WBF, bool GREEDY>
 int run_merged(const LaunchCtx& c, const CUtensorMap& t_w1, const CUtensorMap& t_h, const CUtensorMap& t_w2,
                const CUtensorMap& t_act, const MergedDims& d, int G, const float* b2, __nv_bfloat16* logits_dump,
                float cfg_weight, float temperature, int greedy, const CfgFusedBuffers& buf) {
-  using Epi = EpiCfgFused<MODE, TDIV, WBF>;
+  using Epi = EpiCfgFused<MODE, TDIV, WBF, GREEDY>;
   typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, d.V, buf, greedy, d.V};
-  auto kern = decode_merged_kernel<MODE, TDIV, WBF>;
-  g_last_variant = MODE * 4 + (TDIV ? 2 : 0) + (WBF ? 1 : 0);
+  auto kern = decode_merged_kernel<MODE, TDIV, WBF, GREEDY>;
+  g_last_variant = (GREEDY ? 8 : 0) + MODE * 4 + (TDIV ? 2 : 0) + (WBF ? 1 : 0);
   static bool attr_set = false;
   static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // by cluster size
   if (!attr_set) {
@@ -527,14 +527,22 @@ int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_
   int rc;
   if ((rc = make_tmap_bf16_2d(&t_w, w, M, K, K, kBM)) != 0) return rc;
   if ((rc = make_tmap_bf16_2d(&t_x, x, n, K, K, kBN)) != 0) return rc;
+#define OSPO_LIN(G, M, T, W) run_linear<M, T, W, G>(c, t_w, t_x, d)
   switch (g_last_variant) {
-    case 0: return run_linear<0, false, false>(c, t_w, t_x, d);
-    case 1: return run_linear<0, false, true>(c, t_w, t_x, d);
-    case 2: return run_linear<0, true, false>(c, t_w, t_x, d);
-    case 3: return run_linear<0, true, true>(c, t_w, t_x, d);
-    case 4: return run_linear<1, false, false>(c, t_w, t_x, d);
-    default: return run_linear<1, true, false>(c, t_w, t_x, d);
+    case 0: return OSPO_LIN(false, 0, false, false);
+    case 1: return OSPO_LIN(false, 0, false, true);
+    case 2: return OSPO_LIN(false, 0, true, false);
+    case 3: return OSPO_LIN(false, 0, true, true);
+    case 4: return OSPO_LIN(false, 1, false, false);
+    case 6: return OSPO_LIN(false, 1, true, false);
+    case 8: return OSPO_LIN(true, 0, false, false);
+    case 9: return OSPO_LIN(true, 0, false, true);
+    case 10: return OSPO_LIN(true, 0, true, false);
+    case 11: return OSPO_LIN(true, 0, true, true);
+    case 12: return OSPO_LIN(true, 1, false, false);
+    default: return OSPO_LIN(true, 1, true, false);
   }
+#undef OSPO_LIN
 }
 
 int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
@@ -581,8 +589,11 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
     if (need1 > max_ctas) continue;
     int G = d.num_m2 < max_ctas ? ((d.num_m2 + ks - 1) / ks) * ks : max_ctas;
     if (G < need1) G = need1;
-#define OSPO_RUN_MERGED(MODE, TDIV, WBF) \
-  run_merged<MODE, TDIV, WBF>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, greedy, buf)
+#define OSPO_RUN_MERGED(MODE, TDIV, WBF)                                                                              \
+  (greedy ? run_merged<MODE, TDIV, WBF, true>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature,  \
+                                              greedy, buf)                                                               \
+          : run_merged<MODE, TDIV, WBF, false>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, \
+                                               greedy, buf))
     if (merge_mode == 0 && bf16_exact(cfg_weight)) {
       rc = tdiv ? OSPO_RUN_MERGED(0, true, true) : OSPO_RUN_MERGED(0, false, true);
     } else if (merge_mode == 0) {

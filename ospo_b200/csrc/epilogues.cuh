@@ -489,7 +489,9 @@ struct EpiGeluBwd {
 // so the merged logits never exist in HBM; cfg_finish_kernel completes the draw from 512 sums per pair.
 // Needs TILE_M == 128 (one CTA = one tile) and BN == 32 (one chunk = all columns).
 // ---------------------------------------------------------------------------
-template <int MODE, bool TDIV, bool WBF = false>
+// GREEDY is a template parameter: the arg-max variant is a different (large, fully unrolled) code path, and keeping it
+// out of the sampling instantiation takes a quarter off the decode kernel's code size.
+template <int MODE, bool TDIV, bool WBF = false, bool GREEDY = false>
 struct EpiCfgFused {
   struct Params {
     const float* bias;            // b2 [V]
@@ -554,7 +556,7 @@ struct EpiCfgFused {
                                    p.cfg_weight, p.temperature, t[k], t[k + 1]);
     }
     trace_stamp(tr, 1);
-    if (p.greedy) {
+    if constexpr (GREEDY) {
       // per-pair arg-max over the tile: (value, code) with the lowest code on ties
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
@@ -592,7 +594,7 @@ struct EpiCfgFused {
       }
       named_bar_sync(1, 128);
       return;
-    }
+    } else {
     // tile exponent per pair: 16-way transpose-reduce (max is exact, any order)
     const int mypair = transpose_reduce_pair_of_lane(lane);
     {
@@ -625,6 +627,7 @@ struct EpiCfgFused {
     trace_stamp(tr, 5);
     named_bar_sync(1, 128);  // smem is reused by the next tile of a persistent CTA
     trace_stamp(tr, 6);
+    }
   }
   __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
 };

@@ -82,9 +82,15 @@ template <int MODE, bool TDIV>
 static int run_fused(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                      __nv_bfloat16* logits_dump, int n, int E, int V, float cfg_weight, float temperature, int greedy,
                      const CfgFusedBuffers& buf) {
-  using Epi = EpiCfgFused<MODE, TDIV>;
-  typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, V, buf, greedy, V};
   // D[V, n] = W2[V, E] * act[n, E]^T; the epilogue consumes the tile in place
+  if (greedy) {
+    using Epi = EpiCfgFused<MODE, TDIV, false, true>;
+    typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, V, buf, greedy, V};
+    return launch_gemm<CfgF32, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream, 1, c.pdl, SegOperand(),
+                                    SegOperand(), c.trace ? 2 : 0);
+  }
+  using Epi = EpiCfgFused<MODE, TDIV, false, false>;
+  typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, V, buf, greedy, V};
   return launch_gemm<CfgF32, Epi>(w2, E, act, E, V, n, E, 1 << 20, p, c.num_sms, c.stream, 1, c.pdl, SegOperand(),
                                   SegOperand(), c.trace ? 2 : 0);
 }

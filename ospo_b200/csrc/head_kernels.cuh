@@ -641,6 +641,8 @@ __device__ __forceinline__ void embed_up_rows(const EmbedUp& eu, const EmbedRegs
   }
 }
 
+// EMBED: with the first aligner layer folded in (a separate instantiation: the plain finish kernel stays small)
+template <bool EMBED>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ uniforms, int greedy,
                   int64_t* __restrict__ ids, int trace, EmbedUp eu) {
@@ -651,7 +653,7 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
   pdl_launch_dependents();  // successors may become resident and prefetch; they wait for our completion
   if (threadIdx.x == 0) trace_stamp(trace ? 4 : 0, 0);
   EmbedRegs er;
-  if (eu.gen_embed != nullptr) embed_up_preload(eu, er);
+  if constexpr (EMBED) embed_up_preload(eu, er);
   pdl_wait();
   if (threadIdx.x == 0) trace_stamp(trace ? 4 : 0, 2);
   const int p = blockIdx.x;
@@ -673,7 +675,7 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
       ids[p] = garg;
       bc_id = garg;
     }
-    if (eu.gen_embed != nullptr) {
+    if constexpr (EMBED) {
       __syncthreads();
       embed_up_rows(eu, er, p, bc_id);
     }
@@ -742,7 +744,7 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
       trace_stamp(trace ? 4 : 0, 5);
     }
   }
-  if (eu.gen_embed != nullptr) {
+  if constexpr (EMBED) {
     __syncthreads();
     embed_up_rows(eu, er, p, bc_id);
   }

@@ -111,15 +111,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #define OSPO_WATCHDOG_NS 4000000000ull  // 4 s: far above any legitimate wait in these kernels
 #endif
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = globaltimer_ns();
+// the bounded spin lives out of line: a wait site costs one try_wait and a call, not a copy of the loop
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, uint32_t site) {
+  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
     if (((++spins) & 0x3FFu) == 0u) {
-      if (globaltimer_ns() - t0 > OSPO_WATCHDOG_NS) watchdog_fire(site, smem_u32(bar), parity);
+      if (globaltimer_ns() - t0 > OSPO_WATCHDOG_NS) watchdog_fire(site, bar_addr, parity);
     }
   }
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(smem_u32(bar), parity, site);
 }
 
 // wait on a barrier whose arrivals come from other CTAs of the cluster (acquire at cluster scope)

@@ -74,4 +74,4 @@ for merged, ahead, direct in ((1, 0, True), (1, 16, True), (1, 24, True), (1, 32
         same = bool(torch.equal(ref, ids_out))
         print(f"TIME pack={PACK} HE={H} alt={ALT} merged={merged} l2_ahead={ahead:2d} direct_out={int(direct)}: {us:6.2f} us/step  {step_bytes / us / 1e3:7.1f} GB/s  ids_same={same}")
 lib.ospo_head_set_decode_merged(1)
-lib.ospo_head_set_decode_l2_ahead(24)
+lib.ospo_head_set_decode_l2_ahead(16)

@@ -674,6 +674,27 @@ def test_cfg_sample_1b_shape_uses_one_kernel_step():
     assert torch.equal(ids.cpu(), oid)
 
 
+def test_cfg_sample_more_than_16_pairs_falls_back():
+    """P = 24 (48 CFG rows) does not fit the one-kernel step's 32-column tile: the two-GEMM chain takes over and the
+    draws still match the oracle bit for bit"""
+    dev = _cuda()
+    H, E, V, P = 256, 384, 16384, 24
+    head_b = O.make_head(H, E, V, seed=24, w2_gain=4.0).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    g = torch.Generator().manual_seed(25)
+    h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16)
+    u = torch.rand(P, generator=g)
+    ids, lg = fh.cfg_sample(h.to(dev), 5.0, 1.0, uniforms=u.to(dev), return_logits=True)
+    gids = fh.cfg_sample(h.to(dev), 5.0, 1.0, greedy=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = head_b(h)
+    torch.testing.assert_close(lg.float().cpu(), ref.float(), rtol=2e-2, atol=3e-2)
+    oid, *_ = O.cfg_sample_det(lg.cpu(), 5.0, 1.0, u, merge_mode=0)
+    ogid, *_ = O.cfg_sample_det(lg.cpu(), 5.0, 1.0, None, merge_mode=0, greedy=True)
+    assert torch.equal(ids.cpu(), oid) and torch.equal(gids.cpu(), ogid)
+
+
 def test_cfg_sample_7b_shape_p16():
     """BASELINE.json configs[3] shape: P=16 (32 CFG rows), 7B-shaped head; a few steps vs the bf16 oracle."""
     dev = _cuda()

@@ -190,8 +190,10 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
           const int nb = min(d.l2_ahead, left);
           if (d.w2p != nullptr) {
             const uint8_t* next = d.w2p + (static_cast<size_t>(row >> 7) * num_kb2 + (k >> 6)) * kABytes;
+#pragma unroll 1
             for (int j = 0; j < nb; ++j) bulk_prefetch_tile(next + static_cast<size_t>(j) * kABytes);
           } else {
+#pragma unroll 1
             for (int j = 0; j < nb; ++j) tma_prefetch_l2_2d(&tmap_w2, k + j * kBK, row);
           }
         }

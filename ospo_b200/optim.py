@@ -115,6 +115,43 @@ class FusedHeadAdamW:
                 p.data.copy_(v)        # parameters that are not views of the flat buffers (e.g. bf16 biases)
         self._install_operands()
 
+    # ---- checkpoint / resume (Lightning saves optimizer_states next to the model's state_dict) ----------------
+    def state_dict(self) -> dict:
+        """step count, both moments (flat, fp32) and the hyper-parameters; the parameters themselves are saved by
+        the module's own ``state_dict`` (they are views of ``self.params``)"""
+        return {"step": self.step_count, "exp_avg": self.exp_avg.detach().clone(),
+                "exp_avg_sq": self.exp_avg_sq.detach().clone(), "layout": "W2|W1|b2|b1", "dims": self._dims,
+                "hyper": {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
+                          "max_norm": self.max_norm}}
+
+    @torch.no_grad()
+    def load_state_dict(self, state: dict) -> None:
+        if tuple(state["dims"]) != tuple(self._dims) or state["exp_avg"].numel() != self.exp_avg.numel():
+            raise ValueError("optimizer state was saved for a head of another shape")
+        self.step_count = int(state["step"])
+        self.exp_avg.copy_(state["exp_avg"].to(self.exp_avg.device, torch.float32))
+        self.exp_avg_sq.copy_(state["exp_avg_sq"].to(self.exp_avg.device, torch.float32))
+        h = state.get("hyper", {})
+        self.lr, self.betas = h.get("lr", self.lr), tuple(h.get("betas", self.betas))
+        self.eps, self.weight_decay = h.get("eps", self.eps), h.get("weight_decay", self.weight_decay)
+        self.max_norm = h.get("max_norm", self.max_norm)
+        self.resync_from_module()
+
+    @torch.no_grad()
+    def resync_from_module(self) -> None:
+        """call after the module's parameters were overwritten from outside (``load_state_dict`` on the model):
+        refreshes the fp32 master copy where a parameter is not a view of it, and the bf16 operands"""
+        H, E, V = self._dims
+        head = self.head
+        views = ops.split_flat_grads(self.params, H, E, V)
+        for v, p in zip(views, (head.vision_head.weight, head.output_mlp_projector.weight, head.vision_head.bias,
+                                head.output_mlp_projector.bias)):
+            if p.data_ptr() != v.data_ptr():
+                v.copy_(p.detach().to(torch.float32))
+        self.shadow[:V * E].view(V, E).copy_(views[0])
+        self.shadow[V * E:].view(E, H).copy_(views[1])
+        self._install_operands()
+
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.head.parameters():
             if set_to_none:

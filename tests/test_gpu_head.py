@@ -1013,6 +1013,21 @@ def test_fused_head_adamw_tracks_torch_adamw():
         flat_ref = torch.cat([p_.detach().reshape(-1) for p_ in ref_params])
         torch.testing.assert_close(opt.params.cpu(), flat_ref, rtol=1e-5, atol=1e-7)
         assert torch.equal(fh.vision_head.weight.detach().reshape(-1), opt.params[:V * E])
+    # checkpoint / resume: a fresh optimizer on a fresh copy of the head continues identically
+    sd_model, sd_opt = {k: v.detach().clone() for k, v in fh.state_dict().items()}, opt.state_dict()
+    fh2 = _fused_from(head_f, dev, dtype=torch.float32, requires_grad=True)
+    opt2 = FusedHeadAdamW(fh2, lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_norm=1.0)
+    fh2.load_state_dict(sd_model, strict=True)
+    opt2.load_state_dict(sd_opt)
+    assert opt2.step_count == 2 and torch.equal(opt2.params, opt.params) and torch.equal(opt2.shadow, opt.shadow)
+    hc, hr, lc, lr_ = O.synthetic_simpo_batch(B, T, 5, H, V, seed=99)
+    hidden, labels = torch.cat([hc, hr]).to(dev).to(torch.bfloat16), torch.cat([lc, lr_]).to(dev)
+    for f_, o_ in ((fh, opt), (fh2, opt2)):
+        f_.simpo(hidden, labels, beta=5.0, gamma_beta_ratio=0.25).loss.backward()
+        o_.step(other_sqnorm=other)
+        o_.zero_grad()
+    torch.cuda.synchronize()
+    assert torch.equal(opt2.params, opt.params) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
     # the kernels' operands are the refreshed bf16 shadow: logits equal those of a freshly staged head
     p = fh._kernel_params()
     assert p.w2.data_ptr() == opt.shadow.data_ptr()

@@ -52,6 +52,18 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _spawn_with_retry(worker, out_dir, attempts=2):
+    """rendezvous on a fresh loopback port; one retry absorbs a port grabbed between probing and binding"""
+    last = None
+    for _ in range(attempts):
+        try:
+            mp.spawn(worker, args=(2, _free_port(), str(out_dir)), nprocs=2, join=True)
+            return
+        except Exception as ex:  # noqa: BLE001
+            last = ex
+    raise last
+
+
 def test_pair_shard_layout():
     assert pair_shard(8, 1, 4) == slice(2, 4)
     with pytest.raises(ValueError):
@@ -63,8 +75,7 @@ def test_pair_shard_layout():
 
 
 def test_flat_gradient_allreduce_matches_full_batch_gloo_world2(tmp_path):
-    port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    _spawn_with_retry(_worker, tmp_path)
     assert (tmp_path / "ok").exists()
 
 
@@ -99,6 +110,5 @@ def _staged_worker(rank, world, port, out_dir):
 
 def test_staged_allreduce_equals_single_allreduce_gloo_world2(tmp_path):
     """the overlapped exchange (dW2 reduced while the second backward stage runs) gives the same flat buffer"""
-    port = _free_port()
-    mp.spawn(_staged_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    _spawn_with_retry(_staged_worker, tmp_path)
     assert (tmp_path / "ok").exists()

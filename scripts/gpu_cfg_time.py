@@ -45,8 +45,8 @@ def run(direct):
 
 
 ref = None
-for merged, ahead, direct in ((1, 0, True), (1, 16, True), (1, 24, True), (1, 32, True), (1, 24, False), (0, 0, True),
-                              (0, 0, False)):
+for merged, ahead, direct in ((1, 0, True), (1, 12, True), (1, 16, True), (1, 24, True), (1, 32, True), (1, 16, False),
+                              (0, 0, True)):
     if True:
         lib.ospo_head_set_decode_merged(merged)
         lib.ospo_head_set_decode_l2_ahead(ahead)

@@ -147,3 +147,41 @@ def test_token_handoff_matches_reference_pixels(tmp_path):
     paths = [str(tmp_path / f"img_{i:02d}.png") for i in range(P)]
     assert save_images(got, paths) == paths
     assert np.array_equal(np.asarray(Image.open(paths[1])), visual_img[1])
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """the drop-in boundary is a C ABI: include/ospo_head.h compiles as C99 (and C++11) without CUDA or torch headers,
+    and a C program that only includes it links against libospo_head.so and can call a function that needs no GPU"""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    from ospo_b200 import _abi
+
+    root = Path(__file__).resolve().parent.parent
+    hdr = root / "include" / "ospo_head.h"
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", str(hdr)], check=True)
+    subprocess.run([shutil.which("g++") or gcc, "-std=c++11", "-fsyntax-only", "-x", "c++", str(hdr)], check=True)
+    lib = _abi.lib_path()
+    if not lib.exists():
+        import pytest
+        pytest.skip("library not built")
+    src = tmp_path / "t.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "ospo_head.h"\n'
+        "int main(void) {\n"
+        "  ospo_head_shape s = {73728, 4096, 4096, 16384, 128};\n"
+        "  size_t need = 0;\n"
+        "  int rc = ospo_head_workspace_bytes(&s, &need);\n"
+        '  printf("%d %zu %s\\n", rc, need, ospo_head_strerror(-5));\n'
+        "  return rc;\n}\n")
+    exe = tmp_path / "t"
+    subprocess.run([gcc, "-std=c99", "-I", str(root / "include"), str(src), "-o", str(exe), str(lib),
+                    f"-Wl,-rpath,{lib.parent}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(maxsplit=2)
+    assert out[0] == "0" and int(out[1]) == _abi.workspace_bytes(73728, 4096, 4096, 16384, 128)
+    assert "sm_100" in out[2]

@@ -187,6 +187,17 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
           ++use;
         }
         if (i + 1 == min(total, kStages)) stamp(d.trace, tr1, 1);
+        if (i == kStages - 1 && n1 > kStages) {
+          // the W1 tiles that do not fit the ring are requested into L2 while the predecessor kernel still runs, so
+          // that they arrive at L2 latency once the first MMAs free their slots (-0.25 us per step)
+#pragma unroll 1
+          for (int j = 0; j < n1 - kStages; ++j) {
+            if (d.w1p != nullptr)
+              bulk_prefetch_tile(d.w1p + (static_cast<size_t>(row >> 7) * num_kb1 + ((k + j * kBK) >> 6)) * kABytes, d.pf_hint);
+            else
+              tma_prefetch_l2_2d(&tmap_w1, k + j * kBK, row);
+          }
+        }
         if (i == n1 + kStages - 1 && d.l2_ahead > 0) {
           // The ring now holds only phase-2 tiles and this thread is about to sleep until the activation flag opens
           // and the MMA warp starts freeing slots.  HBM would idle through that wait: ask for the next l2_ahead

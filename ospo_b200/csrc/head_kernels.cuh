@@ -391,8 +391,10 @@ pack_weight_kernel(const __nv_bfloat16* __restrict__ w, int rows, int cols, uint
 // The descent shared by the stand-alone sampler and the finish kernel of the fused decode step.
 // seg_sum[512] (already rescaled to the global exponent) and grp_sum[16] live in shared memory; executed by
 // ONE thread; returns the winning segment and the cdf value before it.
-__device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* grp_sum, float u, int& segi,
-                                            float& base, float& target) {
+// Loop form of the descent (used by the stand-alone sampler, whose 512 x 2 blocks per SM leave no registers for the
+// unrolled form below): same additions and comparisons, early exits.
+__device__ __forceinline__ void cdf_descent_loop(const float* seg_sum, const float* grp_sum, float u, int& segi,
+                                                 float& base, float& target) {
   constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
   float Z = 0.0f;
 #pragma unroll
@@ -410,6 +412,52 @@ __device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* g
     const float nxt = __fadd_rn(base, seg_sum[g * SAMPLE_GRP + sg]);
     if (nxt > target) break;
     base = nxt;
+  }
+  segi = g * SAMPLE_GRP + sg;
+}
+
+__device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* grp_sum, float u, int& segi,
+                                            float& base, float& target) {
+  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
+  // Same sequential additions and comparisons as the oracle, written without data-dependent exits: the operands are
+  // fetched from shared memory up front (independent loads), so the serial chain is one add + compare per step
+  // instead of a shared-memory round trip per step.
+  float gs[NGRP];
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) gs[g] = grp_sum[g];
+  float Z = 0.0f;
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) Z = __fadd_rn(Z, gs[g]);
+  target = __fmul_rn(u, Z);
+  base = 0.0f;
+  int g = 0;
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < NGRP - 1; ++i) {
+    const float nxt = __fadd_rn(base, gs[i]);
+    if (!found) {
+      if (nxt > target) found = true;
+      else {
+        base = nxt;
+        g = i + 1;
+      }
+    }
+  }
+  float ss[SAMPLE_GRP];
+#pragma unroll
+  for (int i = 0; i < SAMPLE_GRP; ++i) ss[i] = seg_sum[g * SAMPLE_GRP + i];
+  int sg = 0;
+  found = false;
+#pragma unroll
+  for (int i = 0; i < SAMPLE_GRP - 1; ++i) {
+    const float nxt = __fadd_rn(base, ss[i]);
+    if (!found) {
+      if (nxt > target) found = true;
+      else {
+        base = nxt;
+        sg = i + 1;
+      }
+    }
   }
   segi = g * SAMPLE_GRP + sg;
 }
@@ -542,7 +590,7 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
     if (tid == 0) {
       int segi;
       float base, target;
-      cdf_descent(seg_sum, grp_sum, __ldg(uniforms + p), segi, base, target);
+      cdf_descent_loop(seg_sum, grp_sum, __ldg(uniforms + p), segi, base, target);
       bc_seg = segi;
       bc_base = base;
       bc_target = target;

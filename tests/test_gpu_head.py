@@ -674,6 +674,30 @@ def test_cfg_sample_1b_shape_uses_one_kernel_step():
     assert torch.equal(ids.cpu(), oid)
 
 
+@pytest.mark.parametrize("gain,w,T", [(40.0, 5.0, 1.0), (0.01, 7.5, 1.0), (12.0, 5.0, 0.6), (25.0, 3.3, 1.3)])
+def test_cfg_sample_fused_step_extremes(gain, w, T):
+    """one-kernel decode step at the edges: very peaked and almost flat distributions, uniforms 0 and 1 - 2^-24,
+    identical cond / uncond rows, a cfg_weight that is not a bf16 value (fp32 merge path of the epilogue) -- ids
+    bit-exact against the oracle evaluated on the step's own logits, sampled and greedy"""
+    dev = _cuda()
+    H, E, V, P = 512, 2560, 16384, 16
+    head_b = O.make_head(H, E, V, seed=int(gain * 10), w2_gain=gain).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    g = torch.Generator().manual_seed(77)
+    h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16)
+    h[2:4] = h[2:3]                      # pair 1: cond == uncond
+    u = torch.rand(P, generator=g)
+    u[0], u[1], u[2] = 0.0, 1.0 - 2.0 ** -24, 0.5
+    ids, lg = fh.cfg_sample(h.to(dev), w, T, uniforms=u.to(dev), return_logits=True)
+    ids2 = fh.cfg_sample(h.to(dev), w, T, uniforms=u.to(dev))
+    gids = fh.cfg_sample(h.to(dev), w, T, greedy=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(lg.float()).all()
+    oid, *_ = O.cfg_sample_det(lg.cpu(), w, T, u, merge_mode=0)
+    ogid, *_ = O.cfg_sample_det(lg.cpu(), w, T, None, merge_mode=0, greedy=True)
+    assert torch.equal(ids.cpu(), oid) and torch.equal(ids2.cpu(), oid) and torch.equal(gids.cpu(), ogid)
+
+
 def test_cfg_sample_more_than_16_pairs_falls_back():
     """P = 24 (48 CFG rows) does not fit the one-kernel step's 32-column tile: the two-GEMM chain takes over and the
     draws still match the oracle bit for bit"""

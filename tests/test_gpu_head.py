@@ -674,6 +674,40 @@ def test_cfg_sample_1b_shape_uses_one_kernel_step():
     assert torch.equal(ids.cpu(), oid)
 
 
+def test_bf16_pipe_merge_equals_op_by_op_rounding_on_every_bit_pattern():
+    """The CFG merge runs on the bf16x2 pipe when cfg_weight is a bf16 value (single rounding of the exact result)
+    while the reference rounds fp32(a op b) to bf16.  Every finite bf16 bit pattern appears as the conditional logit
+    against several permutations of all patterns as the unconditional one (1 M pairs, denormals and huge magnitudes
+    included): the merged values must be bit-identical to PyTorch's own bf16 tensor arithmetic."""
+    from ospo_b200 import cfg_merge_sample
+
+    dev = _cuda()
+    bits = torch.arange(65536, dtype=torch.int32)
+    finite = ((bits >> 7) & 0xFF) != 0xFF                              # drop inf / nan exponents
+    pats = bits[finite]
+    pats = torch.cat([pats, pats[: 65536 - pats.numel()]])            # pad back to 4 x 16384
+    cond = O.bits_to_bf16(pats.to(torch.int16).numpy().astype(np.uint16)).view(4, 16384)
+    g = torch.Generator().manual_seed(3)
+    steps = []
+    for k in range(4):
+        perm = torch.randperm(65536, generator=g)
+        unc = cond.reshape(-1)[perm].view(4, 16384)
+        if k == 3:
+            unc = (cond.float() * (1.0 + 2.0 ** -7)).to(torch.bfloat16)  # neighbours: cancellation in the subtraction
+        lg = torch.empty(8, 16384, dtype=torch.bfloat16)
+        lg[0::2], lg[1::2] = cond, unc
+        steps.append(lg)
+    lg = torch.stack(steps)                                            # [4 steps, 8 rows, V]
+    for w in (5.0, 7.5, 1.5):
+        _, merged = cfg_merge_sample(lg.to(dev), w, 1.0, greedy=True, merge_mode="bf16", return_merged=True)
+        torch.cuda.synchronize()
+        for s_ in range(lg.shape[0]):
+            ref = O.cfg_merged(lg[s_], w, 1.0).float()                 # PyTorch bf16 tensor ops: fp32 op, round, per op
+            got = merged[s_].cpu()
+            both_nan = torch.isnan(ref) & torch.isnan(got)
+            assert bool(((got == ref) | both_nan).all()), (w, s_)
+
+
 @pytest.mark.parametrize("gain,w,T", [(40.0, 5.0, 1.0), (0.01, 7.5, 1.0), (12.0, 5.0, 0.6), (25.0, 3.3, 1.3)])
 def test_cfg_sample_fused_step_extremes(gain, w, T):
     """one-kernel decode step at the edges: very peaked and almost flat distributions, uniforms 0 and 1 - 2^-24,

@@ -10,6 +10,7 @@
  *   ospo_head_simpo_fwd/_bwd  ospo/wrapper/train.py:317-342, 345-372, 399-445  SimPO loss fwd + bwd
  *   ospo_head_cfg_sample      ospo/wrapper/image_generation.py:156-164 (== ospo/inference.py:147-155)
  *   ospo_head_cfg_merge_sample   the merge/softmax/sample tail of the same lines, on supplied logits
+ *   ospo_head_pack_weight     one-time re-layout of W1 / W2 for the decode step's weight stream (no reference counterpart)
  *   ospo_head_gen_img_embeds  janus/models/modeling_vlm.py:263-264 + projector.py:39-45 (next row N1)
  *   ospo_head_grad_sqnorm / ospo_head_adamw_step   ospo/utils/train.py:30,50 + ospo/wrapper/train.py:108-115 (next row N3)
  *

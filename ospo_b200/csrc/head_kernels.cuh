@@ -389,6 +389,11 @@ pack_weight_kernel(const __nv_bfloat16* __restrict__ w, int rows, int cols, uint
 // the logits are still in tensor memory.  greedy: argmax_v t_v, lowest index on ties.
 // ---------------------------------------------------------------------------
 // The descent shared by the stand-alone sampler and the finish kernel of the fused decode step.
+// Shared-memory layout of the 512 rescaled segment sums: one padding word per 32-segment group, so that the 16
+// threads which each add up one group (stride 33 words) hit 16 different banks instead of one.
+constexpr int SEG_PAD_WORDS = SAMPLE_THREADS + SAMPLE_THREADS / SAMPLE_GRP;
+__device__ __forceinline__ int seg_slot(int seg) { return seg + seg / SAMPLE_GRP; }
+
 // seg_sum[512] (already rescaled to the global exponent) and grp_sum[16] live in shared memory; executed by
 // ONE thread; returns the winning segment and the cdf value before it.
 // Loop form of the descent (used by the stand-alone sampler, whose 512 x 2 blocks per SM leave no registers for the
@@ -409,7 +414,7 @@ __device__ __forceinline__ void cdf_descent_loop(const float* seg_sum, const flo
   }
   int sg = 0;
   for (; sg < SAMPLE_GRP - 1; ++sg) {
-    const float nxt = __fadd_rn(base, seg_sum[g * SAMPLE_GRP + sg]);
+    const float nxt = __fadd_rn(base, seg_sum[seg_slot(g * SAMPLE_GRP + sg)]);
     if (nxt > target) break;
     base = nxt;
   }
@@ -445,7 +450,7 @@ __device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* g
   }
   float ss[SAMPLE_GRP];
 #pragma unroll
-  for (int i = 0; i < SAMPLE_GRP; ++i) ss[i] = seg_sum[g * SAMPLE_GRP + i];
+  for (int i = 0; i < SAMPLE_GRP; ++i) ss[i] = seg_sum[seg_slot(g * SAMPLE_GRP + i)];
   int sg = 0;
   found = false;
 #pragma unroll
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 2)
 cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int vocab, float cfg_weight,
                         float temperature, const float* __restrict__ uniforms, int64_t* __restrict__ ids,
                         float* __restrict__ merged_out /* [P, V] optional */) {
-  __shared__ float seg_sum[SAMPLE_THREADS];
+  __shared__ float seg_sum[SEG_PAD_WORDS];
   __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
   __shared__ float wmax[SAMPLE_THREADS / 32];
   __shared__ int warg[SAMPLE_THREADS / 32];
@@ -577,13 +582,13 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
 #pragma unroll
     for (int w = 1; w < SAMPLE_THREADS / 32; ++w) K = fmaxf(K, wmax[w]);
     const float f = pow2_factor(__fsub_rn(kt, K));
-    seg_sum[tid] = __fmul_rn(S, f);
+    seg_sum[seg_slot(tid)] = __fmul_rn(S, f);
     __syncthreads();
     constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
     if (tid < NGRP) {
       float g = 0.0f;
 #pragma unroll 8
-      for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[tid * SAMPLE_GRP + j]);
+      for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[seg_slot(tid * SAMPLE_GRP + j)]);
       grp_sum[tid] = g;
     }
     __syncthreads();
@@ -694,7 +699,7 @@ template <bool EMBED>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ uniforms, int greedy,
                   int64_t* __restrict__ ids, int trace, EmbedUp eu) {
-  __shared__ float seg_sum[SAMPLE_THREADS];
+  __shared__ float seg_sum[SEG_PAD_WORDS];
   __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
   __shared__ float wmax[SAMPLE_THREADS / 32];
   __shared__ int bc_id;
@@ -744,13 +749,13 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
 #pragma unroll
   for (int w = 1; w < SAMPLE_THREADS / 32; ++w) K = fmaxf(K, wmax[w]);
   const float f = pow2_factor(__fsub_rn(kt, K));
-  seg_sum[tid] = __fmul_rn(ss_raw, f);
+  seg_sum[seg_slot(tid)] = __fmul_rn(ss_raw, f);
   __syncthreads();
   constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
   if (tid < NGRP) {
     float g = 0.0f;
 #pragma unroll 8
-    for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[tid * SAMPLE_GRP + j]);
+    for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[seg_slot(tid * SAMPLE_GRP + j)]);
     grp_sum[tid] = g;
   }
   __syncthreads();

@@ -254,7 +254,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t)
     value = world * tokens_per_step_rank / (ms_step / 1e3)
-    loss_val = float(loss)
+    loss_val = float(loss.detach())
 
     # ---- per-kernel table + roofline of the dominant kernel ---------------------------------------
     HE, EV = H7B * E7B, E7B * V

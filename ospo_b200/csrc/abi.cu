@@ -345,12 +345,13 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   if (!a->pre || !a->act || !a->logits || !a->row_lse || !a->grad_seq) return OSPO_ERR_NULL;
   LaunchCtx c = make_ctx(st);
   int rc;
-  // bwd_stage: 0 = everything; 1 = up to and including dW2 (the caller then starts the all-reduce of dW2 and calls
-  // again with) 2 = db1, dW1, dX.  dpre lives in the workspace, which must be the same buffer in both calls.
-  const int stage = a->bwd_stage;
-  if (stage < 0 || stage > 2) return OSPO_ERR_UNSUPPORTED;
-  const bool first = stage != 2, second = stage != 1;
-  if (stage == 2 && a->reserve_sms > 0) {
+  // bwd_stage: 0 = everything; otherwise a bit mask of the parts to run now: 1 = row coefficients, dlogits (+db2),
+  // dpre and dW2;  2 = db1 and dW1;  4 = dX.  A data-parallel caller runs 1, starts the all-reduce of dW2, runs 2,
+  // starts the all-reduce of the rest and runs 4.  dpre lives in the workspace: same buffer in every call.
+  const int stage = a->bwd_stage == 0 ? 7 : a->bwd_stage;
+  if (stage < 1 || stage > 7) return OSPO_ERR_UNSUPPORTED;
+  const bool first = (stage & 1) != 0, second = (stage & 2) != 0, third = (stage & 4) != 0;
+  if (!first && a->reserve_sms > 0) {
     // leave SMs to a collective kernel running beside the remaining GEMMs (even count: CTA pairs)
     const int keep = c.num_sms - (a->reserve_sms + 1) / 2 * 2;
     if (keep >= c.num_sms / 2) c.num_sms = keep;
@@ -402,7 +403,7 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
     }
     if (rc) return rc;
   }
-  if (a->dx && second) {
+  if (a->dx && third) {
     KernelSpan ks(st, OSPO_K_DGRAD);
     rc = map_rc(launch_dgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->w.w1), static_cast<__nv_bfloat16*>(a->dx),
                              s.rows, s.embed, s.hidden, x_layout(a)));

@@ -59,20 +59,23 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
-def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, run_stage2):
-    """Backward in two stages with the exchange of the first block overlapped: ``run_stage1()`` fills
-    ``flat[:split]`` (dW2, 80 % of the buffer), its all-reduce is started asynchronously, ``run_stage2()`` computes
-    the rest while it runs, then the remainder is reduced.  Returns ``run_stage2()``'s result.  Same values as
-    ``run_stage1(); run_stage2(); allreduce_mean_(flat)``."""
+def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, run_stage2, run_stage3=None):
+    """Backward in stages with the exchange overlapped: ``run_stage1()`` fills ``flat[:split]`` (dW2, 80 %
+    of the buffer) and its all-reduce starts asynchronously; ``run_stage2()`` fills the rest (db1, dW1; db2 is there
+    already) and that all-reduce starts; ``run_stage3()`` (dX) runs beside it.  Returns the last stage's result.
+    Same values as running the stages and then ``allreduce_mean_(flat)``."""
     world = _world(group)
     run_stage1()
     if world == 1:
-        return run_stage2()
+        out = run_stage2()
+        return run_stage3() if run_stage3 is not None else out
     op = _avg_op(group)
     head, tail = flat[:split], flat[split:]
     w1 = dist.all_reduce(head, op=op, group=group, async_op=True)
     out = run_stage2()
     w2 = dist.all_reduce(tail, op=op, group=group, async_op=True)
+    if run_stage3 is not None:
+        out = run_stage3()
     w1.wait()
     w2.wait()
     if op == dist.ReduceOp.SUM:

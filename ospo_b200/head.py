@@ -239,7 +239,8 @@ class FusedGenHead(torch.nn.Module):
     def _backward_and_sync(self, bwd, flat: torch.Tensor, group, need_dw: bool, xb, seq_off, seg):
         """run the fused backward (``bwd(stage, reserve_sms, workspace) -> dx``) and average the flat gradient over the
         data-parallel group.  With more than one rank the backward is staged: the all-reduce of dW2 (80 % of the
-        bytes) runs on NCCL's stream while db1 / dW1 / dX are computed (OSPO_HEAD_OVERLAP=0 restores the single
+        bytes) runs on NCCL's stream while db1 / dW1 / dX are computed (OSPO_HEAD_OVERLAP=3 also runs dX beside the
+        all-reduce of the remainder -- measured 0.2-0.6 ms slower at N = 2; OSPO_HEAD_OVERLAP=0 restores the single
         all-reduce after the backward; OSPO_HEAD_OVERLAP_SMS > 0 leaves that many SMs free for the collective --
         measured neutral at N = 2 and N = 8, so the default is 0)."""
         world = _dist._world(group) if group is not None else 1
@@ -252,7 +253,10 @@ class FusedGenHead(torch.nn.Module):
         rows, _ = ops._x_dims(xb, seg[0])
         ws = ops._workspace(rows, H, E, V, seq_off.numel() - 1, xb.device)
         reserve = int(os.environ.get("OSPO_HEAD_OVERLAP_SMS", "0"))
-        return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(2, reserve, ws))
+        if os.environ.get("OSPO_HEAD_OVERLAP", "1") == "3":      # three parts: dX beside the second all-reduce
+            return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(2, reserve, ws),
+                                                lambda: bwd(4, reserve, ws))
+        return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(6, reserve, ws))
 
     @staticmethod
     def _sync_flat_grads(flat: torch.Tensor, group) -> None:

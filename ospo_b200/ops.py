@@ -186,8 +186,8 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
              simpo: bool, seg_rows: int = 0, seg_off: int = 0, stage: int = 0, reserve_sms: int = 0,
              ws: Optional[Tensor] = None, dx_out: Optional[Tensor] = None) -> Tensor:
     """softmax-minus-onehot producer + the dgrad / wgrad GEMM pairs.
-    ``stage`` 1 / 2 split the backward after dW2 so the caller can overlap the all-reduce of dW2 with the rest
-    (pass the same ``ws`` to both calls; stage 1 produces no dx).
+    ``stage`` is a bit mask (0 = everything): 1 = up to dW2, 2 = db1 + dW1, 4 = dX, so the caller can overlap the
+    all-reduces with the later parts (pass the same ``ws`` to every call; dx is produced by part 4).
     `logits` is overwritten with dlogits; `flat_grads` (numel 0 = head frozen) receives dW2|dW1|db2|db1.
     Returns dx bf16 with the shape of x (numel 0 if not requested); with a row-segmented x the rows outside the
     span are zero (train.py: masked positions carry no gradient)."""
@@ -198,7 +198,7 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
     dev = x.device
     seg = (seg_rows, x.shape[1], seg_off) if seg_rows else (0, 0, 0)
     dx = None
-    if need_dx and stage != 1:
+    if need_dx and (stage == 0 or (stage & 4)):
         dx = torch.empty_like(x) if dx_out is None else dx_out
         if seg_rows:
             dx[:, :seg_off].zero_()

@@ -95,12 +95,15 @@ def _staged_worker(rank, world, port, out_dir):
     def stage2():
         order.append(2)
         flat[split:] = vals[split:]
+
+    def stage3():
+        order.append(3)
         return "dx"
 
-    out = staged_allreduce_mean_(flat, split, dist.group.WORLD, stage1, stage2)
+    out = staged_allreduce_mean_(flat, split, dist.group.WORLD, stage1, stage2, stage3)
     ref = vals.clone()
     allreduce_mean_(ref, dist.group.WORLD)
-    assert out == "dx" and order == [1, 2]
+    assert out == "dx" and order == [1, 2, 3]
     torch.testing.assert_close(flat, ref, rtol=0, atol=0)
     if rank == 0:
         open(os.path.join(out_dir, "ok"), "w").write("ok")

@@ -1093,11 +1093,13 @@ def test_fused_head_adamw_tracks_torch_adamw():
     assert torch.equal(p.w1, fh.output_mlp_projector.weight.detach().to(torch.bfloat16))
 
 
-def test_staged_backward_equals_single_call(monkeypatch):
-    """the two-stage backward used to overlap the dW2 all-reduce (stage 1 up to dW2, stage 2 with SMs reserved for
-    the collective) produces bit-identical gradients to the single-call backward"""
+@pytest.mark.parametrize("parts", ["1", "3"])
+def test_staged_backward_equals_single_call(monkeypatch, parts):
+    """the staged backward used to overlap the all-reduces (part 1 up to dW2, then db1 + dW1 + dX together or as
+    parts 2 and 4) produces bit-identical gradients to the single-call backward"""
     from ospo_b200 import dist as D
 
+    monkeypatch.setenv("OSPO_HEAD_OVERLAP", parts)
     dev = _cuda()
     H, E, V, B, T, L = 256, 384, 16384, 3, 128, 3
     head_b = O.make_head(H, E, V, seed=51, w2_gain=3.0).to(torch.bfloat16)
@@ -1111,10 +1113,14 @@ def test_staged_backward_equals_single_call(monkeypatch):
             calls = []
             monkeypatch.setattr(D, "_world", lambda group: 2)
 
-            def fake_staged(flat, split, group, s1, s2):
+            def fake_staged(flat, split, group, s1, s2, s3=None):
                 calls.append(split)
                 s1()
-                return s2()
+                out = s2()
+                if s3 is None:
+                    return out
+                assert out.numel() == 0           # dX belongs to the last part
+                return s3()
 
             monkeypatch.setattr(D, "staged_allreduce_mean_", fake_staged)
         out = fh.simpo(x, labels, beta=10.0, gamma_beta_ratio=0.5, image_span=(L - 1, L - 1 + T),

@@ -612,6 +612,51 @@ def bench_cfg(head, dev, peaks, with_cpu=False):
                                          "frac_of_hbm_peak": bytes_n1 / (us_n1 * 1e-6) / 1e9 / peaks["hbm"]}
     except Exception as ex:
         result["with_gen_img_embeds"] = {"error": repr(ex)[:200]}
+    # the 1B-shaped head (H = E = 2048, configs[0]'s shape): 75.6 MB of weights per step, four copies in rotation so
+    # that 227 MB of other weights pass through the 126 MB L2 between two uses of a copy
+    try:
+        H1 = E1 = 2048
+        g1 = torch.Generator(device=dev).manual_seed(1239)
+        copies = []
+        for _ in range(4):
+            w1 = (torch.randn(E1, H1, generator=g1, device=dev) * H1 ** -0.5).to(torch.bfloat16)
+            w2 = (torch.randn(V, E1, generator=g1, device=dev) * E1 ** -0.5).to(torch.bfloat16)
+            b1 = torch.zeros(E1, dtype=torch.float32, device=dev)
+            b2 = torch.zeros(V, dtype=torch.float32, device=dev)
+            copies.append((w1, b1, w2, b2, (ops.pack_weight_impl(w1), ops.pack_weight_impl(w2))))
+        h1 = torch.randn(steps, 2 * P, H1, generator=g1, device=dev).to(torch.bfloat16)
+
+        def run_steps_1b():
+            for i in range(steps):
+                w1, b1, w2, b2, pk = copies[i & 3]
+                ops.cfg_sample_impl(h1[i], w1, b1, w2, b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], None, pk)
+
+        run_steps_1b()
+        torch.cuda.synchronize()
+        s3 = torch.cuda.Stream()
+        s3.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s3):
+            run_steps_1b()
+        torch.cuda.current_stream().wait_stream(s3)
+        g3 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g3):
+            run_steps_1b()
+        g3.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            g3.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us_1b = e0.elapsed_time(e1) / 3 * 1e3 / steps
+        bytes_1b = 2 * (H1 * E1 + E1 * V) + 4 * (E1 + V) + 2 * 2 * P * H1 + 4 * P + 8 * P
+        result["shape_1b"] = {"workload": "same loop, 1B-shaped head (H=E=2048)", "us_per_step": us_1b,
+                              "tokens_per_s": P / (us_1b * 1e-6), "bytes_per_step": bytes_1b,
+                              "achieved_gbs": bytes_1b / (us_1b * 1e-6) / 1e9,
+                              "frac_of_hbm_peak": bytes_1b / (us_1b * 1e-6) / 1e9 / peaks["hbm"]}
+        del copies, h1
+    except Exception as ex:
+        result["shape_1b"] = {"error": repr(ex)[:200]}
     # merge + sample alone on supplied logits, all 576 steps in one launch (SURVEY §8d secondary metric)
     lg = (torch.randn(steps, 2 * P, V, generator=gen, device=dev) * 3).to(torch.bfloat16)
     for _ in range(3):

@@ -90,7 +90,8 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
                      const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_act,
                      MergedDims d, typename EpiCfgFused<MODE, TDIV, WBF, GREEDY>::Params ep) {
   using Epi = EpiCfgFused<MODE, TDIV, WBF, GREEDY>;
-  constexpr int tr1 = 1, tr2 = 2;
+  constexpr int tr2 = 2;
+  const int tr1 = d.linear_only ? 6 : 1, trp = d.linear_only ? 7 : 3;  // timeline rows (ospo_head_trace)
   if (d.linear_only) pdl_launch_dependents();  // nothing below needs every CTA resident: the successor may queue up
   if (threadIdx.x == 0) stamp(d.trace, tr1, 0);
   extern __shared__ uint8_t smem_raw[];
@@ -149,7 +150,7 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
   cluster_sync();  // peers' barriers are initialised before anyone arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-  if (threadIdx.x == 0) stamp(d.trace, 3, 0);
+  if (threadIdx.x == 0) stamp(d.trace, trp, 0);
 
   // The CTA's k-blocks form one sequence: n1 blocks of W1 (B = h, needs the predecessor kernel), then the blocks
   // of its W2 slabs (B = act, needs the device-wide flag).  The weight (A) halves and the activation (B) halves are
@@ -338,7 +339,7 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
       }
       if (threadIdx.x == 64) stamp(d.trace, tr1, 5);
       mbar_wait(part_ready_bar, 0u, SITE_M_PART_READY);
-      if (threadIdx.x == 64) stamp(d.trace, 3, 1);
+      if (threadIdx.x == 64) stamp(d.trace, trp, 1);
       // this CTA's share of the 32 columns, partials added in split order (deterministic)
       const int c_lo = rank * per;
       if (e < d.E) {
@@ -362,7 +363,7 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
           }
         }
       }
-      if (threadIdx.x == 64) stamp(d.trace, 3, 2);
+      if (threadIdx.x == 64) stamp(d.trace, trp, 2);
       named_bar_sync(1, 128);
       if (threadIdx.x == 64 && !d.linear_only) {
         // release at device scope is cumulative over the stores the barrier above has ordered before it
@@ -408,7 +409,7 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
   // ===================== teardown =====================
   __syncwarp();
   tc_fence_before();
-  if (threadIdx.x == 0) stamp(d.trace, 3, 3);
+  if (threadIdx.x == 0) stamp(d.trace, trp, 3);
   // No cluster barrier here: the partial tiles pushed into this CTA were complete before it published its
   // activations, and it pushes nothing after that -- no peer touches this CTA's shared memory any more.
   __syncthreads();
@@ -417,7 +418,7 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
     tmem_dealloc<1>(tmem_base, kTmemCols);
   }
   if (threadIdx.x == 0) {
-    stamp(d.trace, 3, 4);
+    stamp(d.trace, trp, 4);
   }
 }
 
@@ -538,7 +539,7 @@ int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_
   d.flag = nullptr;
   d.w1p = nullptr;
   d.w2p = nullptr;
-  d.trace = nullptr;
+  d.trace = c.trace ? c.trace_buf : nullptr;
   d.linear_only = 1;
   d.gelu = gelu;
   d.l2_ahead = 0;

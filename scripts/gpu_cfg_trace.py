@@ -14,6 +14,7 @@ dev = torch.device("cuda:0")
 H = E = int(os.environ.get("HE", "4096"))
 ALT = int(os.environ.get("ALT", "1"))
 DIRECT = int(os.environ.get("DIRECT", "0"))
+N1 = int(os.environ.get("N1", "0"))   # chain prepare_gen_img_embeds behind the sampler (ospo_cfg_args.next_embeds)
 V, P, steps = 16384, 16, 8
 
 
@@ -34,10 +35,23 @@ trace = torch.zeros(8, 160, 8, dtype=torch.int64, device=dev)
 lib = _abi.load()
 
 
+ne = None
+if N1:
+    from ospo_b200 import FusedGenImgEmbeds
+
+    gen_embed = torch.nn.Embedding(V, 8).to(dev).to(torch.bfloat16)
+    aligner = torch.nn.Module()
+    aligner.layers = torch.nn.Sequential(torch.nn.Linear(8, H), torch.nn.GELU(), torch.nn.Linear(H, H)).to(dev).to(torch.bfloat16)
+    fe = FusedGenImgEmbeds(gen_embed, aligner)
+    ne = (*fe._params(), torch.empty(2 * P, H, dtype=torch.bfloat16, device=dev))
+
+
 def run():
     for i in range(steps):
         w = p if (i & 1) == 0 or not ALT else alt
-        if DIRECT:
+        if N1:
+            ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], ne, pk[id(w)])
+        elif DIRECT:
             ops.cfg_sample_impl(h[i], w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i], None,
                                 pk[id(w)] if PACK else None)
         else:
@@ -79,6 +93,17 @@ for k in (1, 3, 2, 4):
         if v.size:
             line += f" | {nm} {((v.min() - t0) / 1e3):6.1f}..{((v.max() - t0) / 1e3):6.1f}"
     print(line)
+for k, nm_k, slots in ((6, "aligner", slots_merged), (7, "align-pro", slots_pro)):
+    a = t[k]
+    act = a[:, 0] > 0
+    if act.any():
+        line = f"TRACE {nm_k:9s} ctas={int(act.sum()):3d}"
+        for slot, nm in slots:
+            v = a[act, slot]
+            v = v[v > 0]
+            if v.size:
+                line += f" | {nm} {((v.min() - t0) / 1e3):6.1f}..{((v.max() - t0) / 1e3):6.1f}"
+        print(line)
 a = t[5]
 act = a[:, 0] > 0
 if act.any():

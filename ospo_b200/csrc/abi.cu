@@ -412,6 +412,17 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   return OSPO_OK;
 }
 
+template <int MODE, bool TDIV, bool GREEDY, bool WBF>
+bool run_sampler(int grid, cudaStream_t st, const __nv_bfloat16* lg, int V, const ospo_cfg_args* a, int pairs) {
+  constexpr int kLanding = SAMPLE_THREADS * 8 * 16;  // 64 KB of dynamic shared memory: opt in once per instantiation
+  auto kern = cfg_merge_sample_kernel<MODE, TDIV, GREEDY, WBF>;
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kLanding);
+  if (attr_rc != cudaSuccess) return false;
+  kern<<<grid, GREEDY ? SAMPLE_THREADS : SAMPLE_BLOCK, kLanding, st>>>(lg, V, V, a->cfg_weight, a->temperature, a->uniforms, a->ids, a->merged,
+                                               pairs);
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -509,20 +520,31 @@ static int launch_sampler(const ospo_cfg_args* a, int pairs, cudaStream_t st) {
   const int mode = (a->merge_mode == OSPO_MERGE_FP32) ? 1 : 0;
   // bf16 merge with a cfg_weight that is itself a bf16 value (5.0, 7.5, ...): merge on the bf16x2 pipe
   const bool wbf = (mode == 0) && bf16_exact(a->cfg_weight);
-#define OSPO_LAUNCH_SAMPLER(MODE, TDIV, GREEDY, WBF)                                                              \
-  cfg_merge_sample_kernel<MODE, TDIV, GREEDY, WBF><<<pairs, SAMPLE_THREADS, 0, st>>>(lg, V, V, a->cfg_weight,    \
-                                                                                     a->temperature, a->uniforms, \
-                                                                                     a->ids, a->merged)
-#define OSPO_LAUNCH_SAMPLER_G(GREEDY)                                                                             \
-  if (mode == 0) {                                                                                                \
-    if (wbf) { if (tdiv) OSPO_LAUNCH_SAMPLER(0, true, GREEDY, true); else OSPO_LAUNCH_SAMPLER(0, false, GREEDY, true); } \
-    else { if (tdiv) OSPO_LAUNCH_SAMPLER(0, true, GREEDY, false); else OSPO_LAUNCH_SAMPLER(0, false, GREEDY, false); }  \
-  } else {                                                                                                        \
-    if (tdiv) OSPO_LAUNCH_SAMPLER(1, true, GREEDY, false); else OSPO_LAUNCH_SAMPLER(1, false, GREEDY, false);     \
+  // persistent blocks (two per SM), each with a 64 KB landing buffer for its next pair's rows
+  const int grid = std::min(pairs, 2 * g_rt.num_sms);
+  const int variant = (a->greedy ? 8 : 0) | (mode ? 4 : 0) | (tdiv ? 2 : 0) | (wbf ? 1 : 0);
+  bool ok = false;
+#define OSPO_SAMPLER_CASE(MODE, TDIV, GREEDY, WBF)                                                             \
+  case ((GREEDY ? 8 : 0) | (MODE ? 4 : 0) | (TDIV ? 2 : 0) | (WBF ? 1 : 0)):                                   \
+    ok = run_sampler<MODE, TDIV, GREEDY, WBF>(grid, st, lg, V, a, pairs);                                      \
+    break
+  switch (variant) {
+    OSPO_SAMPLER_CASE(0, false, false, false);
+    OSPO_SAMPLER_CASE(0, false, false, true);
+    OSPO_SAMPLER_CASE(0, true, false, false);
+    OSPO_SAMPLER_CASE(0, true, false, true);
+    OSPO_SAMPLER_CASE(1, false, false, false);
+    OSPO_SAMPLER_CASE(1, true, false, false);
+    OSPO_SAMPLER_CASE(0, false, true, false);
+    OSPO_SAMPLER_CASE(0, false, true, true);
+    OSPO_SAMPLER_CASE(0, true, true, false);
+    OSPO_SAMPLER_CASE(0, true, true, true);
+    OSPO_SAMPLER_CASE(1, false, true, false);
+    OSPO_SAMPLER_CASE(1, true, true, false);
+    default: break;
   }
-  if (a->greedy) { OSPO_LAUNCH_SAMPLER_G(true) } else { OSPO_LAUNCH_SAMPLER_G(false) }
-#undef OSPO_LAUNCH_SAMPLER_G
-#undef OSPO_LAUNCH_SAMPLER
+#undef OSPO_SAMPLER_CASE
+  if (!ok) return OSPO_ERR_LAUNCH;
   return check_launch();
 }
 

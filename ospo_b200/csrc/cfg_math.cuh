@@ -43,6 +43,66 @@ __device__ __forceinline__ float pow2_factor(float e) {
   return (e < -120.0f) ? 0.0f : f;
 }
 
+// ---- the same weight for two codes at once on the packed fp32 pipe (FFMA2 / FMUL2 / FADD2, sm_100) ----------
+// Every lane of an f32x2 instruction is the IEEE operation of its scalar form, so the results are the bits
+// exp_parts + pow2_factor give.  Two more changes keep the conversion unit out of the loop: rint(y) is
+// (y + 1.5 * 2^23) - 1.5 * 2^23 (round-to-nearest-even for |y| < 2^22; y is clamped to 1e4), and n - kt is taken
+// from the low mantissa bits of y + 1.5 * 2^23 as an integer (exp_koff(kt) = the bits of kt + 1.5 * 2^23).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+constexpr float kRintMagic = 12582912.0f;  // 1.5 * 2^23 = 0x4B400000
+__device__ __forceinline__ int exp_koff(float kt) { return __float_as_int(__fadd_rn(kt, kRintMagic)); }
+// 2^e for an integer e <= 0; 0 below -120 (pow2_factor on an integer)
+__device__ __forceinline__ float pow2_factor_i(int e) {
+  const float f = __int_as_float((e << 23) + 0x3F800000);
+  return (e < -120) ? 0.0f : f;
+}
+// w = P(r) 2^(n - kt) for two codes; koff = exp_koff(kt) of each code's tile
+__device__ __forceinline__ void exp_weight2(float t0, float t1, int koff0, int koff1, float& w0, float& w1) {
+  const uint64_t t = f2_pack(t0, t1);
+  float y0, y1;
+  f2_unpack(f2_mul(t, f2_pack(1.4426950408889634f, 1.4426950408889634f)), y0, y1);
+  y0 = fminf(fmaxf(y0, -1.0e4f), 1.0e4f);
+  y1 = fminf(fmaxf(y1, -1.0e4f), 1.0e4f);
+  const uint64_t ym = f2_add(f2_pack(y0, y1), f2_pack(kRintMagic, kRintMagic));
+  const uint64_t n = f2_add(ym, f2_pack(-kRintMagic, -kRintMagic));
+  float ym0, ym1;
+  f2_unpack(ym, ym0, ym1);
+  const float f0 = pow2_factor_i(__float_as_int(ym0) - koff0);
+  const float f1 = pow2_factor_i(__float_as_int(ym1) - koff1);
+  uint64_t r = f2_fma(n, f2_pack(-0.693145751953125f, -0.693145751953125f), t);
+  r = f2_fma(n, f2_pack(-1.42860682030941723212e-6f, -1.42860682030941723212e-6f), r);
+  uint64_t p = f2_pack(1.3888888888888889e-03f, 1.3888888888888889e-03f);
+  p = f2_fma(p, r, f2_pack(8.3333333333333332e-03f, 8.3333333333333332e-03f));
+  p = f2_fma(p, r, f2_pack(4.1666666666666664e-02f, 4.1666666666666664e-02f));
+  p = f2_fma(p, r, f2_pack(1.6666666666666666e-01f, 1.6666666666666666e-01f));
+  p = f2_fma(p, r, f2_pack(0.5f, 0.5f));
+  p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
+  p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
+  f2_unpack(f2_mul(p, f2_pack(f0, f1)), w0, w1);
+}
+
 // merge two adjacent codes at once so the bf16 roundings can use the packed convert (cvt.rn.bf16x2.f32).
 // MODE 0 = bf16 rounding after every op, MODE 1 = fp32.  TDIV = false skips the division (T == 1: x / 1 == x).
 __device__ __forceinline__ void round2_bf16(float& a, float& b) {

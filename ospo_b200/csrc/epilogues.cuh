@@ -607,12 +607,12 @@ struct EpiCfgFused {
     trace_stamp(tr, 3);
     float u[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float kt = fmaxf(fmaxf(sm_k[k], sm_k[16 + k]), fmaxf(sm_k[32 + k], sm_k[48 + k]));
-      float n;
-      const float pr = exp_parts(t[k], n);
-      u[k] = __fmul_rn(pr, pow2_factor(__fsub_rn(n, kt)));
+    for (int k = 0; k < 16; k += 2) {
+      const float kt0 = fmaxf(fmaxf(sm_k[k], sm_k[16 + k]), fmaxf(sm_k[32 + k], sm_k[48 + k]));
+      const float kt1 = fmaxf(fmaxf(sm_k[k + 1], sm_k[17 + k]), fmaxf(sm_k[33 + k], sm_k[49 + k]));
+      exp_weight2(t[k], t[k + 1], exp_koff(kt0), exp_koff(kt1), u[k], u[k + 1]);
       if (k < npairs) p.buf.wbuf[static_cast<int64_t>(pair0 + k) * p.vocab + row] = u[k];
+      if (k + 1 < npairs) p.buf.wbuf[static_cast<int64_t>(pair0 + k + 1) * p.vocab + row] = u[k + 1];
     }
     // segment sums: the warp is one 32-code segment; the transpose-reduce adds lanes in the oracle's butterfly
     // order (strides 16, 8, 4, 2, 1)

@@ -467,158 +467,234 @@ __device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* g
   segi = g * SAMPLE_GRP + sg;
 }
 
-// grid.x = number of (cond, uncond) pairs; logits row pitch ld.  vocab must be 16384 (= 512 * 32).
-// Register-resident: thread i owns segment i (codes 32 i .. 32 i + 31).
+// Persistent blocks: block b handles pairs b, b + gridDim.x, ...; logits row pitch ld; vocab must be 16384 (= 512 * 32).
+// Thread i < 512 owns segment i (codes 32 i .. 32 i + 31), register-resident.
+//  * While a pair is being evaluated (ALU-bound: ~25 instructions per code) the block's next pair travels
+//    global -> shared with cp.async, every thread fetching exactly the 2 x 64 bytes it will read back itself (no
+//    barrier; chunk positions are XOR-swizzled per thread so the 16-byte accesses are free of bank conflicts).
+//  * Sampling: the serial part of a draw (global exponent, 16 sequential group sums, descent group -> segment ->
+//    code) belongs to a 17th warp.  The 16 evaluating warps only deposit their segment sum and tile exponent in one
+//    of two shared buffers (named barriers full[b] / empty[b]) and go on to the next pair; the tail warp rebuilds the
+//    32 weights of the winning segment from the logits (same operations, same bits) instead of asking its owner.
+//    With the CTA-wide barriers the draw used to need, the warps spent 4.7 cycles waiting per instruction issued.
 // WBF: MODE 0 with a bf16-exact cfg_weight -> the merge runs on the bf16x2 pipe (cfg_math.cuh)
+constexpr int SAMPLE_BLOCK = SAMPLE_THREADS + 32;  // sampling variant: + the tail warp
+__device__ __forceinline__ void named_bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int MODE, bool TDIV, bool WBF>
+__device__ __forceinline__ void merge_words(uint32_t wc, uint32_t wu, float cfg_weight, float temperature, float& t0,
+                                            float& t1) {
+  if constexpr (WBF) cfg_merge2_hw<TDIV>(wc, wu, pack_bf16x2(cfg_weight, cfg_weight), temperature, t0, t1);
+  else cfg_merge2<MODE, TDIV>(wc, wu, cfg_weight, temperature, t0, t1);
+}
+
 template <int MODE, bool TDIV, bool GREEDY, bool WBF = false>
-__global__ void __launch_bounds__(SAMPLE_THREADS, 2)
+__global__ void __launch_bounds__(GREEDY ? SAMPLE_THREADS : SAMPLE_BLOCK, 2)
 cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int vocab, float cfg_weight,
                         float temperature, const float* __restrict__ uniforms, int64_t* __restrict__ ids,
-                        float* __restrict__ merged_out /* [P, V] optional */) {
-  __shared__ float seg_sum[SEG_PAD_WORDS];
+                        float* __restrict__ merged_out /* [P, V] optional */, int pairs) {
+  extern __shared__ uint4 next_rows[];  // [SAMPLE_THREADS][8]
+  __shared__ float seg_buf[2][SEG_PAD_WORDS];   // sampling: S relative to the tile exponent, rescaled in place by the tail
+  __shared__ float kt_buf[2][SAMPLE_THREADS];   // sampling: tile exponent, one copy per segment
   __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
-  __shared__ float wmax[SAMPLE_THREADS / 32];
-  __shared__ int warg[SAMPLE_THREADS / 32];
-  __shared__ float bc_base, bc_target;
-  __shared__ int bc_seg;
-  const int p = blockIdx.x;
+  __shared__ float wmax[SAMPLE_THREADS / 32];   // greedy
+  __shared__ int warg[SAMPLE_THREADS / 32];     // greedy
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const __nv_bfloat16* lc = logits + static_cast<int64_t>(2 * p) * ld + tid * SAMPLE_SEG;
-  const __nv_bfloat16* lu = lc + ld;
+  constexpr int FULL0 = 1, EMPTY0 = 3;  // named barriers: full[b] = 1 + b, empty[b] = 3 + b
 
-  // ---- load + merge: t[j] for codes 32*tid + j ------------------------------------------------
-  float t[SAMPLE_SEG];
-  {
-    uint4 a[4], b[4];
+  if (!GREEDY && warp == SAMPLE_THREADS / 32) {
+    // ===================== tail warp: one draw per pair =====================
+    int k = 0;
+    for (int p = blockIdx.x; p < pairs; p += gridDim.x, ++k) {
+      const int b = k & 1;
+      float* seg_sum = seg_buf[b];
+      const float* kts = kt_buf[b];
+      const float u01 = __ldg(uniforms + p);
+      named_bar_sync_n(FULL0 + b, SAMPLE_BLOCK);
+      // global exponent K = max tile exponent; rescale the 512 segment sums (exact: powers of two)
+      float kt[SAMPLE_THREADS / 32];
+      float K = -3.0e38f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a[i] = __ldg(reinterpret_cast<const uint4*>(lc) + i);
-      b[i] = __ldg(reinterpret_cast<const uint4*>(lu) + i);
-    }
+      for (int i = 0; i < SAMPLE_THREADS / 32; ++i) {
+        kt[i] = kts[i * 32 + lane];
+        K = fmaxf(K, kt[i]);
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t wa[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, wb[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
+      for (int off = 16; off > 0; off >>= 1) K = fmaxf(K, __shfl_xor_sync(0xffffffffu, K, off));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if constexpr (WBF) {
-          const uint32_t w2 = pack_bf16x2(cfg_weight, cfg_weight);
-          cfg_merge2_hw<TDIV>(wa[k], wb[k], w2, temperature, t[8 * i + 2 * k], t[8 * i + 2 * k + 1]);
-        } else {
-          cfg_merge2<MODE, TDIV>(wa[k], wb[k], cfg_weight, temperature, t[8 * i + 2 * k], t[8 * i + 2 * k + 1]);
+      for (int i = 0; i < SAMPLE_THREADS / 32; ++i) {
+        const int sl = seg_slot(i * 32 + lane);
+        seg_sum[sl] = __fmul_rn(seg_sum[sl], pow2_factor(__fsub_rn(kt[i], K)));
+      }
+      __syncwarp();
+      constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
+      if (lane < NGRP) {
+        float g = 0.0f;
+#pragma unroll 8
+        for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[seg_slot(lane * SAMPLE_GRP + j)]);
+        grp_sum[lane] = g;
+      }
+      __syncwarp();
+      // The descent as running sums that every lane evaluates redundantly (the same additions in the same order as
+      // the sequential form; lane i keeps the value before and after element i) and one ballot per level: the
+      // first element whose running sum exceeds the target, the last element if none does.
+      float before = 0.0f, after = 0.0f, run = 0.0f;
+#pragma unroll
+      for (int g = 0; g < NGRP; ++g) {
+        const float nxt = __fadd_rn(run, grp_sum[g]);
+        if (g == lane) {
+          before = run;
+          after = nxt;
         }
+        run = nxt;
       }
-    }
-  }
-  if (merged_out != nullptr) {
-    float4* mo = reinterpret_cast<float4*>(merged_out + static_cast<int64_t>(p) * vocab + tid * SAMPLE_SEG);
+      const float target = __fmul_rn(u01, run);  // run = Z
+      uint32_t hit = __ballot_sync(0xffffffffu, lane < NGRP - 1 && after > target);
+      const int g_win = hit ? __ffs(hit) - 1 : NGRP - 1;
+      float base = __shfl_sync(0xffffffffu, before, g_win);
+      run = base;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mo[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
-  }
-
-  if constexpr (GREEDY) {
-    // ---- arg-max (exact; lowest index wins ties) ----------------------------------------------
-    float lmax = t[0];
-    int larg = 0;
-#pragma unroll
-    for (int j = 1; j < SAMPLE_SEG; ++j) {
-      if (t[j] > lmax) {
-        lmax = t[j];
-        larg = j;
-      }
-    }
-    larg += tid * SAMPLE_SEG;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float o = __shfl_xor_sync(0xffffffffu, lmax, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, larg, off);
-      if (o > lmax || (o == lmax && oi < larg)) {
-        lmax = o;
-        larg = oi;
-      }
-    }
-    if (lane == 0) {
-      wmax[warp] = lmax;
-      warg[warp] = larg;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      float gmax = wmax[0];
-      int garg = warg[0];
-      for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
-        if (wmax[w] > gmax || (wmax[w] == gmax && warg[w] < garg)) {
-          gmax = wmax[w];
-          garg = warg[w];
+      for (int i = 0; i < SAMPLE_GRP; ++i) {
+        const float nxt = __fadd_rn(run, seg_sum[seg_slot(g_win * SAMPLE_GRP + i)]);
+        if (i == lane) {
+          before = run;
+          after = nxt;
         }
+        run = nxt;
       }
-      ids[p] = garg;
+      hit = __ballot_sync(0xffffffffu, lane < SAMPLE_GRP - 1 && after > target);
+      const int sg_win = hit ? __ffs(hit) - 1 : SAMPLE_GRP - 1;
+      base = __shfl_sync(0xffffffffu, before, sg_win);
+      const int segi = g_win * SAMPLE_GRP + sg_win;
+      // the winning segment's 32 weights again, lane j = code j (two codes per packed word, as in the evaluation)
+      const float kt_seg = kts[segi];
+      const float f = pow2_factor(__fsub_rn(kt_seg, K));
+      __syncwarp();
+      named_bar_arrive_n(EMPTY0 + b, SAMPLE_BLOCK);  // the buffer is free for the pair after next
+      const uint32_t* rc = reinterpret_cast<const uint32_t*>(logits + static_cast<int64_t>(2 * p) * ld) + segi * (SAMPLE_SEG / 2);
+      const uint32_t* ru = reinterpret_cast<const uint32_t*>(logits + static_cast<int64_t>(2 * p + 1) * ld) + segi * (SAMPLE_SEG / 2);
+      float t0, t1;
+      merge_words<MODE, TDIV, WBF>(__ldg(rc + (lane >> 1)), __ldg(ru + (lane >> 1)), cfg_weight, temperature, t0, t1);
+      float n;
+      const float pr = exp_parts((lane & 1) ? t1 : t0, n);
+      const float wl = __fmul_rn(__fmul_rn(pr, pow2_factor(__fsub_rn(n, kt_seg))), f);
+      run = base;
+#pragma unroll
+      for (int i = 0; i < SAMPLE_SEG; ++i) {
+        const float nxt = __fadd_rn(run, __shfl_sync(0xffffffffu, wl, i));
+        if (i == lane) after = nxt;
+        run = nxt;
+      }
+      hit = __ballot_sync(0xffffffffu, lane < SAMPLE_SEG - 1 && after > target);
+      const int j = hit ? __ffs(hit) - 1 : SAMPLE_SEG - 1;
+      if (lane == 0) ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
     }
     return;
-  } else {
-    // ---- tile exponent: K_tile = max n over the 4 segments (= 4 adjacent lanes) of a 128-code tile ------
-    // (n is a non-decreasing function of t -- a correctly rounded multiply by a positive constant, two clamps and a
-    // round-to-integer -- so max n = n(max t): one fmax per code instead of four operations)
-    float tmax = t[0];
+  }
+
+  // ===================== evaluating warps =====================
+  uint4* mine = next_rows + tid * 8;
+  const int sw = tid & 7;
+  auto fetch = [&](int q) {
+    const uint4* lc = reinterpret_cast<const uint4*>(logits + static_cast<int64_t>(2 * q) * ld + tid * SAMPLE_SEG);
+    const uint4* lu = reinterpret_cast<const uint4*>(logits + static_cast<int64_t>(2 * q + 1) * ld + tid * SAMPLE_SEG);
 #pragma unroll
-    for (int j = 1; j < SAMPLE_SEG; ++j) tmax = fmaxf(tmax, t[j]);
-    float kt = exp_n_only(tmax);
-    kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 1));
-    kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 2));
-    // ---- weights relative to K_tile (in place) and the segment's tree sum -------------------------
-#pragma unroll
-    for (int j = 0; j < SAMPLE_SEG; ++j) {
-      float n;
-      const float pr = exp_parts(t[j], n);
-      t[j] = __fmul_rn(pr, pow2_factor(__fsub_rn(n, kt)));
+    for (int i = 0; i < 4; ++i) {
+      cp_async_16(mine + (i ^ sw), lc + i);
+      cp_async_16(mine + ((4 + i) ^ sw), lu + i);
     }
-    const float S = tree_sum32(t);
-    // ---- global exponent K ---------------------------------------------------------------------
-    float K = kt;
+    cp_async_commit();
+  };
+  if (static_cast<int>(blockIdx.x) < pairs) fetch(blockIdx.x);
+  int k = 0;
+  for (int p = blockIdx.x; p < pairs; p += gridDim.x, ++k) {
+    // ---- load + merge: t[j] for codes 32*tid + j ------------------------------------------------
+    float t[SAMPLE_SEG];
+    {
+      uint4 a[4], b[4];
+      cp_async_wait_all();
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) K = fmaxf(K, __shfl_xor_sync(0xffffffffu, K, off));
-    if (lane == 0) wmax[warp] = K;
-    __syncthreads();
-    K = wmax[0];
+      for (int i = 0; i < 4; ++i) {
+        a[i] = mine[i ^ sw];
+        b[i] = mine[(4 + i) ^ sw];
+      }
 #pragma unroll
-    for (int w = 1; w < SAMPLE_THREADS / 32; ++w) K = fmaxf(K, wmax[w]);
-    const float f = pow2_factor(__fsub_rn(kt, K));
-    seg_sum[seg_slot(tid)] = __fmul_rn(S, f);
-    __syncthreads();
-    constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
-    if (tid < NGRP) {
-      float g = 0.0f;
-#pragma unroll 8
-      for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[seg_slot(tid * SAMPLE_GRP + j)]);
-      grp_sum[tid] = g;
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t wa[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, wb[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          merge_words<MODE, TDIV, WBF>(wa[q], wb[q], cfg_weight, temperature, t[8 * i + 2 * q], t[8 * i + 2 * q + 1]);
+      }
     }
-    __syncthreads();
-    if (tid == 0) {
-      int segi;
-      float base, target;
-      cdf_descent_loop(seg_sum, grp_sum, __ldg(uniforms + p), segi, base, target);
-      bc_seg = segi;
-      bc_base = base;
-      bc_target = target;
-    }
-    __syncthreads();
-    // ---- code-level descent by the segment's owner, from its registers --------------------------
-    if (tid == bc_seg) {
-      float base = bc_base;
-      const float target = bc_target;
-      int j = 0;
-      bool found = false;
+    // the rows of this block's next pair stream in while this one is evaluated (the values above are in registers)
+    if (p + static_cast<int>(gridDim.x) < pairs) fetch(p + gridDim.x);
+    if (merged_out != nullptr) {
+      float4* mo = reinterpret_cast<float4*>(merged_out + static_cast<int64_t>(p) * vocab + tid * SAMPLE_SEG);
 #pragma unroll
-      for (int i = 0; i < SAMPLE_SEG - 1; ++i) {
-        const float nxt = __fadd_rn(base, __fmul_rn(t[i], f));
-        if (!found) {
-          if (nxt > target) found = true;
-          else {
-            base = nxt;
-            j = i + 1;
-          }
+      for (int i = 0; i < 8; ++i) mo[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+    }
+
+    if constexpr (GREEDY) {
+      // ---- arg-max (exact; lowest index wins ties) ----------------------------------------------
+      float lmax = t[0];
+      int larg = 0;
+#pragma unroll
+      for (int j = 1; j < SAMPLE_SEG; ++j) {
+        if (t[j] > lmax) {
+          lmax = t[j];
+          larg = j;
         }
       }
-      ids[p] = static_cast<int64_t>(tid) * SAMPLE_SEG + j;
+      larg += tid * SAMPLE_SEG;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, lmax, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, larg, off);
+        if (o > lmax || (o == lmax && oi < larg)) {
+          lmax = o;
+          larg = oi;
+        }
+      }
+      if (lane == 0) {
+        wmax[warp] = lmax;
+        warg[warp] = larg;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float gmax = wmax[0];
+        int garg = warg[0];
+        for (int w = 1; w < SAMPLE_THREADS / 32; ++w) {
+          if (wmax[w] > gmax || (wmax[w] == gmax && warg[w] < garg)) {
+            gmax = wmax[w];
+            garg = warg[w];
+          }
+        }
+        ids[p] = garg;
+      }
+      __syncthreads();  // wmax / warg are reused by the next pair
+    } else {
+      // ---- tile exponent: K_tile = max n over the 4 segments (= 4 adjacent lanes) of a 128-code tile ------
+      // (n is a non-decreasing function of t -- a correctly rounded multiply by a positive constant, two clamps and a
+      // round-to-integer -- so max n = n(max t): one fmax per code instead of four operations)
+      float tmax = t[0];
+#pragma unroll
+      for (int j = 1; j < SAMPLE_SEG; ++j) tmax = fmaxf(tmax, t[j]);
+      float kt = exp_n_only(tmax);
+      kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 1));
+      kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 2));
+      // ---- weights relative to K_tile (in place) and the segment's tree sum -------------------------
+      const int koff = exp_koff(kt);
+#pragma unroll
+      for (int j = 0; j < SAMPLE_SEG; j += 2) exp_weight2(t[j], t[j + 1], koff, koff, t[j], t[j + 1]);
+      const float S = tree_sum32(t);
+      // ---- hand the segment over to the tail warp ----------------------------------------------------
+      const int b = k & 1;
+      if (k >= 2) named_bar_sync_n(EMPTY0 + b, SAMPLE_BLOCK);  // its draw of the pair before last is over
+      seg_buf[b][seg_slot(tid)] = S;
+      kt_buf[b][tid] = kt;
+      named_bar_arrive_n(FULL0 + b, SAMPLE_BLOCK);
     }
   }
 }

@@ -78,9 +78,8 @@ __device__ __forceinline__ float pow2_factor_i(int e) {
   const float f = __int_as_float((e << 23) + 0x3F800000);
   return (e < -120) ? 0.0f : f;
 }
-// w = P(r) 2^(n - kt) for two codes; koff = exp_koff(kt) of each code's tile
-__device__ __forceinline__ void exp_weight2(float t0, float t1, int koff0, int koff1, float& w0, float& w1) {
-  const uint64_t t = f2_pack(t0, t1);
+// w = P(r) 2^(n - kt) for two codes (packed in, packed out); koff = exp_koff(kt) of each code's tile
+__device__ __forceinline__ uint64_t exp_weight2p(uint64_t t, int koff0, int koff1) {
   float y0, y1;
   f2_unpack(f2_mul(t, f2_pack(1.4426950408889634f, 1.4426950408889634f)), y0, y1);
   y0 = fminf(fmaxf(y0, -1.0e4f), 1.0e4f);
@@ -100,7 +99,10 @@ __device__ __forceinline__ void exp_weight2(float t0, float t1, int koff0, int k
   p = f2_fma(p, r, f2_pack(0.5f, 0.5f));
   p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
   p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
-  f2_unpack(f2_mul(p, f2_pack(f0, f1)), w0, w1);
+  return f2_mul(p, f2_pack(f0, f1));
+}
+__device__ __forceinline__ void exp_weight2(float t0, float t1, int koff0, int koff1, float& w0, float& w1) {
+  f2_unpack(exp_weight2p(f2_pack(t0, t1), koff0, koff1), w0, w1);
 }
 
 // merge two adjacent codes at once so the bf16 roundings can use the packed convert (cvt.rn.bf16x2.f32).
@@ -184,6 +186,20 @@ __device__ __forceinline__ float tree_sum32(const float (&x)[32]) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) a[j] = __fadd_rn(a[j], a[j + 2]);
   return __fadd_rn(a[0], a[1]);
+}
+
+// the same tree on 16 packed pairs (x[i] = codes 2i, 2i + 1): strides 16, 8, 4 and 2 are packed additions
+__device__ __forceinline__ float tree_sum32_packed(const uint64_t (&x)[16]) {
+  uint64_t a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = f2_add(x[i], x[i + 8]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = f2_add(a[i], a[i + 4]);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) a[i] = f2_add(a[i], a[i + 2]);
+  float lo, hi;
+  f2_unpack(f2_add(a[0], a[1]), lo, hi);
+  return __fadd_rn(lo, hi);
 }
 
 // Transpose-reduce: every lane holds 16 values (one per CFG pair); reduce each of the 16 across the 32 lanes with

@@ -473,12 +473,14 @@ __device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* g
 //    global -> shared with cp.async, every thread fetching exactly the 2 x 64 bytes it will read back itself (no
 //    barrier; chunk positions are XOR-swizzled per thread so the 16-byte accesses are free of bank conflicts).
 //  * Sampling: the serial part of a draw (global exponent, 16 sequential group sums, descent group -> segment ->
-//    code) belongs to a 17th warp.  The 16 evaluating warps only deposit their segment sum and tile exponent in one
-//    of two shared buffers (named barriers full[b] / empty[b]) and go on to the next pair; the tail warp rebuilds the
-//    32 weights of the winning segment from the logits (same operations, same bits) instead of asking its owner.
+//    code) belongs to two extra warps, one for the block's even pairs and one for the odd.  The 16 evaluating warps
+//    only deposit their segment sum and tile exponent in that tail warp's shared buffer (named barriers full[b] /
+//    empty[b]) and go on to the next pair; the tail warp rebuilds the 32 weights of the winning segment from the
+//    logits (same operations, same bits) instead of asking its owner.
 //    With the CTA-wide barriers the draw used to need, the warps spent 4.7 cycles waiting per instruction issued.
 // WBF: MODE 0 with a bf16-exact cfg_weight -> the merge runs on the bf16x2 pipe (cfg_math.cuh)
-constexpr int SAMPLE_BLOCK = SAMPLE_THREADS + 32;  // sampling variant: + the tail warp
+constexpr int SAMPLE_BLOCK = SAMPLE_THREADS + 64;  // sampling variant: + two tail warps (even / odd pairs of the block)
+constexpr int SAMPLE_HANDOVER = SAMPLE_THREADS + 32;  // threads on a full[b] / empty[b] barrier: evaluators + one tail warp
 __device__ __forceinline__ void named_bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -497,22 +499,22 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
   extern __shared__ uint4 next_rows[];  // [SAMPLE_THREADS][8]
   __shared__ float seg_buf[2][SEG_PAD_WORDS];   // sampling: S relative to the tile exponent, rescaled in place by the tail
   __shared__ float kt_buf[2][SAMPLE_THREADS];   // sampling: tile exponent, one copy per segment
-  __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
+  __shared__ float grp_sums[2][SAMPLE_THREADS / SAMPLE_GRP];
   __shared__ float wmax[SAMPLE_THREADS / 32];   // greedy
   __shared__ int warg[SAMPLE_THREADS / 32];     // greedy
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   constexpr int FULL0 = 1, EMPTY0 = 3;  // named barriers: full[b] = 1 + b, empty[b] = 3 + b
 
-  if (!GREEDY && warp == SAMPLE_THREADS / 32) {
-    // ===================== tail warp: one draw per pair =====================
-    int k = 0;
-    for (int p = blockIdx.x; p < pairs; p += gridDim.x, ++k) {
-      const int b = k & 1;
+  if (!GREEDY && warp >= SAMPLE_THREADS / 32) {
+    // ===================== tail warps: one draw per pair; warp 16 takes the block's even pairs, warp 17 the odd =====
+    const int b = warp - SAMPLE_THREADS / 32;
+    float* grp_sum = grp_sums[b];
+    for (int p = blockIdx.x + b * gridDim.x; p < pairs; p += 2 * gridDim.x) {
       float* seg_sum = seg_buf[b];
       const float* kts = kt_buf[b];
       const float u01 = __ldg(uniforms + p);
-      named_bar_sync_n(FULL0 + b, SAMPLE_BLOCK);
+      named_bar_sync_n(FULL0 + b, SAMPLE_HANDOVER);
       // global exponent K = max tile exponent; rescale the 512 segment sums (exact: powers of two)
       float kt[SAMPLE_THREADS / 32];
       float K = -3.0e38f;
@@ -572,7 +574,7 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
       const float kt_seg = kts[segi];
       const float f = pow2_factor(__fsub_rn(kt_seg, K));
       __syncwarp();
-      named_bar_arrive_n(EMPTY0 + b, SAMPLE_BLOCK);  // the buffer is free for the pair after next
+      named_bar_arrive_n(EMPTY0 + b, SAMPLE_HANDOVER);  // the buffer is free for the pair after next
       const uint32_t* rc = reinterpret_cast<const uint32_t*>(logits + static_cast<int64_t>(2 * p) * ld) + segi * (SAMPLE_SEG / 2);
       const uint32_t* ru = reinterpret_cast<const uint32_t*>(logits + static_cast<int64_t>(2 * p + 1) * ld) + segi * (SAMPLE_SEG / 2);
       float t0, t1;
@@ -686,15 +688,16 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
       kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 2));
       // ---- weights relative to K_tile (in place) and the segment's tree sum -------------------------
       const int koff = exp_koff(kt);
+      uint64_t w[SAMPLE_SEG / 2];
 #pragma unroll
-      for (int j = 0; j < SAMPLE_SEG; j += 2) exp_weight2(t[j], t[j + 1], koff, koff, t[j], t[j + 1]);
-      const float S = tree_sum32(t);
+      for (int j = 0; j < SAMPLE_SEG / 2; ++j) w[j] = exp_weight2p(f2_pack(t[2 * j], t[2 * j + 1]), koff, koff);
+      const float S = tree_sum32_packed(w);
       // ---- hand the segment over to the tail warp ----------------------------------------------------
       const int b = k & 1;
-      if (k >= 2) named_bar_sync_n(EMPTY0 + b, SAMPLE_BLOCK);  // its draw of the pair before last is over
+      if (k >= 2) named_bar_sync_n(EMPTY0 + b, SAMPLE_HANDOVER);  // its draw of the pair before last is over
       seg_buf[b][seg_slot(tid)] = S;
       kt_buf[b][tid] = kt;
-      named_bar_arrive_n(FULL0 + b, SAMPLE_BLOCK);
+      named_bar_arrive_n(FULL0 + b, SAMPLE_HANDOVER);
     }
   }
 }

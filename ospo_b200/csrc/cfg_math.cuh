@@ -101,6 +101,38 @@ __device__ __forceinline__ uint64_t exp_weight2p(uint64_t t, int koff0, int koff
   p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
   return f2_mul(p, f2_pack(f0, f1));
 }
+// The same weights when the caller has checked, for every code it passes, that the clamp is idle (|t log2 e| <= 1e4):
+// identical bits without the two clamps.
+__device__ __forceinline__ uint64_t exp_weight2p_inrange(uint64_t t, int koff) {
+  const uint64_t y = f2_mul(t, f2_pack(1.4426950408889634f, 1.4426950408889634f));
+  const uint64_t ym = f2_add(y, f2_pack(kRintMagic, kRintMagic));
+  const uint64_t n = f2_add(ym, f2_pack(-kRintMagic, -kRintMagic));
+  float ym0, ym1;
+  f2_unpack(ym, ym0, ym1);
+  const float f0 = pow2_factor_i(__float_as_int(ym0) - koff);
+  const float f1 = pow2_factor_i(__float_as_int(ym1) - koff);
+  uint64_t r = f2_fma(n, f2_pack(-0.693145751953125f, -0.693145751953125f), t);
+  r = f2_fma(n, f2_pack(-1.42860682030941723212e-6f, -1.42860682030941723212e-6f), r);
+  uint64_t p = f2_pack(1.3888888888888889e-03f, 1.3888888888888889e-03f);
+  p = f2_fma(p, r, f2_pack(8.3333333333333332e-03f, 8.3333333333333332e-03f));
+  p = f2_fma(p, r, f2_pack(4.1666666666666664e-02f, 4.1666666666666664e-02f));
+  p = f2_fma(p, r, f2_pack(1.6666666666666666e-01f, 1.6666666666666666e-01f));
+  p = f2_fma(p, r, f2_pack(0.5f, 0.5f));
+  p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
+  p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
+  return f2_mul(p, f2_pack(f0, f1));
+}
+// NaN-propagating three-input max / min (the range check above must fail when a NaN is present)
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float min3_nan(float a, float b, float c) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ void exp_weight2(float t0, float t1, int koff0, int koff1, float& w0, float& w1) {
   f2_unpack(exp_weight2p(f2_pack(t0, t1), koff0, koff1), w0, w1);
 }

@@ -680,17 +680,39 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
       // ---- tile exponent: K_tile = max n over the 4 segments (= 4 adjacent lanes) of a 128-code tile ------
       // (n is a non-decreasing function of t -- a correctly rounded multiply by a positive constant, two clamps and a
       // round-to-integer -- so max n = n(max t): one fmax per code instead of four operations)
-      float tmax = t[0];
+      // Range scan first (NaN-propagating): when the clamp of t log2 e to +-1e4 is idle for the whole warp, the
+      // weights come from the form without it (same bits).
+      float hi = t[0], lo = t[0];
 #pragma unroll
-      for (int j = 1; j < SAMPLE_SEG; ++j) tmax = fmaxf(tmax, t[j]);
-      float kt = exp_n_only(tmax);
+      for (int j = 1; j < SAMPLE_SEG - 1; j += 2) {
+        hi = max3_nan(hi, t[j], t[j + 1]);
+        lo = min3_nan(lo, t[j], t[j + 1]);
+      }
+      hi = max3_nan(hi, t[SAMPLE_SEG - 1], t[SAMPLE_SEG - 1]);
+      lo = min3_nan(lo, t[SAMPLE_SEG - 1], t[SAMPLE_SEG - 1]);
+      const float yhi = __fmul_rn(hi, 1.4426950408889634f), ylo = __fmul_rn(lo, 1.4426950408889634f);
+      const bool inrange = __all_sync(0xffffffffu, yhi <= 1.0e4f && ylo >= -1.0e4f);  // false with a NaN or an infinity
+      float kt;
+      if (inrange) {
+        kt = rintf(yhi);  // = exp_n_only(max t): no NaN, clamp idle
+      } else {
+        float tmax = t[0];
+#pragma unroll
+        for (int j = 1; j < SAMPLE_SEG; ++j) tmax = fmaxf(tmax, t[j]);
+        kt = exp_n_only(tmax);
+      }
       kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 1));
       kt = fmaxf(kt, __shfl_xor_sync(0xffffffffu, kt, 2));
-      // ---- weights relative to K_tile (in place) and the segment's tree sum -------------------------
+      // ---- weights relative to K_tile and the segment's tree sum -------------------------------------
       const int koff = exp_koff(kt);
       uint64_t w[SAMPLE_SEG / 2];
+      if (inrange) {
 #pragma unroll
-      for (int j = 0; j < SAMPLE_SEG / 2; ++j) w[j] = exp_weight2p(f2_pack(t[2 * j], t[2 * j + 1]), koff, koff);
+        for (int j = 0; j < SAMPLE_SEG / 2; ++j) w[j] = exp_weight2p_inrange(f2_pack(t[2 * j], t[2 * j + 1]), koff);
+      } else {
+#pragma unroll
+        for (int j = 0; j < SAMPLE_SEG / 2; ++j) w[j] = exp_weight2p(f2_pack(t[2 * j], t[2 * j + 1]), koff, koff);
+      }
       const float S = tree_sum32_packed(w);
       // ---- hand the segment over to the tail warp ----------------------------------------------------
       const int b = k & 1;

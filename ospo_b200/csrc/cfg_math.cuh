@@ -205,22 +205,10 @@ __device__ __forceinline__ void cfg_merge2_hw(uint32_t wc, uint32_t wu, uint32_t
   }
 }
 
-// butterfly tree sum of 32 registers: x[j] += x[j + 16] (j < 16), then strides 8, 4, 2, 1 -- the order in which a
-// warp combines lanes with shfl_xor 16, 8, 4, 2, 1 (IEEE addition is commutative, so which lane adds is irrelevant)
-__device__ __forceinline__ float tree_sum32(const float (&x)[32]) {
-  float a[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) a[j] = __fadd_rn(x[j], x[j + 16]);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = __fadd_rn(a[j], a[j + 8]);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) a[j] = __fadd_rn(a[j], a[j + 4]);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) a[j] = __fadd_rn(a[j], a[j + 2]);
-  return __fadd_rn(a[0], a[1]);
-}
-
-// the same tree on 16 packed pairs (x[i] = codes 2i, 2i + 1): strides 16, 8, 4 and 2 are packed additions
+// butterfly tree sum of a segment's 32 weights: x[j] += x[j + 16] (j < 16), then strides 8, 4, 2, 1 -- the order in
+// which a warp combines lanes with shfl_xor 16, 8, 4, 2, 1 (IEEE addition is commutative, so which lane adds is
+// irrelevant).  The weights arrive as 16 packed pairs (x[i] = codes 2i, 2i + 1): strides 16, 8, 4 and 2 are packed
+// additions.
 __device__ __forceinline__ float tree_sum32_packed(const uint64_t (&x)[16]) {
   uint64_t a[8];
 #pragma unroll

@@ -394,77 +394,62 @@ pack_weight_kernel(const __nv_bfloat16* __restrict__ w, int rows, int cols, uint
 constexpr int SEG_PAD_WORDS = SAMPLE_THREADS + SAMPLE_THREADS / SAMPLE_GRP;
 __device__ __forceinline__ int seg_slot(int seg) { return seg + seg / SAMPLE_GRP; }
 
-// seg_sum[512] (already rescaled to the global exponent) and grp_sum[16] live in shared memory; executed by
-// ONE thread; returns the winning segment and the cdf value before it.
-// Loop form of the descent (used by the stand-alone sampler, whose 512 x 2 blocks per SM leave no registers for the
-// unrolled form below): same additions and comparisons, early exits.
-__device__ __forceinline__ void cdf_descent_loop(const float* seg_sum, const float* grp_sum, float u, int& segi,
-                                                 float& base, float& target) {
-  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
-  float Z = 0.0f;
+// The descent, executed by ONE WARP.  seg_sum[512] (already rescaled to the global exponent, padded slots) lives in
+// shared memory.  The oracle's sequential form is  "base = 0; for each element: nxt = base + x; if (nxt > target)
+// stop; base = nxt"  with the last element winning when nothing stops.  Here every lane evaluates the running sum of
+// a level redundantly (the same additions in the same order), lane i keeps the value before and after element i,
+// and one ballot finds the first crossing: a 16 / 32-step chain of dependent additions per level instead of a
+// chain of add + compare + select.
+// Group sums first (lane g < 16 adds group g's 32 segment sums in order), then the levels group -> segment.
+__device__ __forceinline__ void warp_descent_segments(const float* seg_sum, float* grp_sum, float u01, int lane,
+                                                      int& segi, float& base, float& target) {
+  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
+  if (lane < NGRP) {
+    float g = 0.0f;
+#pragma unroll 8
+    for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[seg_slot(lane * SAMPLE_GRP + j)]);
+    grp_sum[lane] = g;
+  }
+  __syncwarp();
+  float before = 0.0f, after = 0.0f, run = 0.0f;
 #pragma unroll
-  for (int g = 0; g < NGRP; ++g) Z = __fadd_rn(Z, grp_sum[g]);
-  target = __fmul_rn(u, Z);
-  base = 0.0f;
-  int g = 0;
-  for (; g < NGRP - 1; ++g) {
-    const float nxt = __fadd_rn(base, grp_sum[g]);
-    if (nxt > target) break;
-    base = nxt;
+  for (int g = 0; g < NGRP; ++g) {
+    const float nxt = __fadd_rn(run, grp_sum[g]);
+    if (g == lane) {
+      before = run;
+      after = nxt;
+    }
+    run = nxt;
   }
-  int sg = 0;
-  for (; sg < SAMPLE_GRP - 1; ++sg) {
-    const float nxt = __fadd_rn(base, seg_sum[seg_slot(g * SAMPLE_GRP + sg)]);
-    if (nxt > target) break;
-    base = nxt;
+  target = __fmul_rn(u01, run);  // run = Z
+  uint32_t hit = __ballot_sync(0xffffffffu, lane < NGRP - 1 && after > target);
+  const int g_win = hit ? __ffs(hit) - 1 : NGRP - 1;
+  run = __shfl_sync(0xffffffffu, before, g_win);
+#pragma unroll
+  for (int i = 0; i < SAMPLE_GRP; ++i) {
+    const float nxt = __fadd_rn(run, seg_sum[seg_slot(g_win * SAMPLE_GRP + i)]);
+    if (i == lane) {
+      before = run;
+      after = nxt;
+    }
+    run = nxt;
   }
-  segi = g * SAMPLE_GRP + sg;
+  hit = __ballot_sync(0xffffffffu, lane < SAMPLE_GRP - 1 && after > target);
+  const int sg_win = hit ? __ffs(hit) - 1 : SAMPLE_GRP - 1;
+  base = __shfl_sync(0xffffffffu, before, sg_win);
+  segi = g_win * SAMPLE_GRP + sg_win;
 }
-
-__device__ __forceinline__ void cdf_descent(const float* seg_sum, const float* grp_sum, float u, int& segi,
-                                            float& base, float& target) {
-  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
-  // Same sequential additions and comparisons as the oracle, written without data-dependent exits: the operands are
-  // fetched from shared memory up front (independent loads), so the serial chain is one add + compare per step
-  // instead of a shared-memory round trip per step.
-  float gs[NGRP];
+// Last level: lane j holds the (rescaled) weight of code j of the winning segment; returns the code's index in it.
+__device__ __forceinline__ int warp_descent_codes(float wl, float base, float target, int lane) {
+  float after = 0.0f, run = base;
 #pragma unroll
-  for (int g = 0; g < NGRP; ++g) gs[g] = grp_sum[g];
-  float Z = 0.0f;
-#pragma unroll
-  for (int g = 0; g < NGRP; ++g) Z = __fadd_rn(Z, gs[g]);
-  target = __fmul_rn(u, Z);
-  base = 0.0f;
-  int g = 0;
-  bool found = false;
-#pragma unroll
-  for (int i = 0; i < NGRP - 1; ++i) {
-    const float nxt = __fadd_rn(base, gs[i]);
-    if (!found) {
-      if (nxt > target) found = true;
-      else {
-        base = nxt;
-        g = i + 1;
-      }
-    }
+  for (int i = 0; i < SAMPLE_SEG; ++i) {
+    const float nxt = __fadd_rn(run, __shfl_sync(0xffffffffu, wl, i));
+    if (i == lane) after = nxt;
+    run = nxt;
   }
-  float ss[SAMPLE_GRP];
-#pragma unroll
-  for (int i = 0; i < SAMPLE_GRP; ++i) ss[i] = seg_sum[seg_slot(g * SAMPLE_GRP + i)];
-  int sg = 0;
-  found = false;
-#pragma unroll
-  for (int i = 0; i < SAMPLE_GRP - 1; ++i) {
-    const float nxt = __fadd_rn(base, ss[i]);
-    if (!found) {
-      if (nxt > target) found = true;
-      else {
-        base = nxt;
-        sg = i + 1;
-      }
-    }
-  }
-  segi = g * SAMPLE_GRP + sg;
+  const uint32_t hit = __ballot_sync(0xffffffffu, lane < SAMPLE_SEG - 1 && after > target);
+  return hit ? __ffs(hit) - 1 : SAMPLE_SEG - 1;
 }
 
 // Persistent blocks: block b handles pairs b, b + gridDim.x, ...; logits row pitch ld; vocab must be 16384 (= 512 * 32).
@@ -531,45 +516,9 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
         seg_sum[sl] = __fmul_rn(seg_sum[sl], pow2_factor(__fsub_rn(kt[i], K)));
       }
       __syncwarp();
-      constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
-      if (lane < NGRP) {
-        float g = 0.0f;
-#pragma unroll 8
-        for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[seg_slot(lane * SAMPLE_GRP + j)]);
-        grp_sum[lane] = g;
-      }
-      __syncwarp();
-      // The descent as running sums that every lane evaluates redundantly (the same additions in the same order as
-      // the sequential form; lane i keeps the value before and after element i) and one ballot per level: the
-      // first element whose running sum exceeds the target, the last element if none does.
-      float before = 0.0f, after = 0.0f, run = 0.0f;
-#pragma unroll
-      for (int g = 0; g < NGRP; ++g) {
-        const float nxt = __fadd_rn(run, grp_sum[g]);
-        if (g == lane) {
-          before = run;
-          after = nxt;
-        }
-        run = nxt;
-      }
-      const float target = __fmul_rn(u01, run);  // run = Z
-      uint32_t hit = __ballot_sync(0xffffffffu, lane < NGRP - 1 && after > target);
-      const int g_win = hit ? __ffs(hit) - 1 : NGRP - 1;
-      float base = __shfl_sync(0xffffffffu, before, g_win);
-      run = base;
-#pragma unroll
-      for (int i = 0; i < SAMPLE_GRP; ++i) {
-        const float nxt = __fadd_rn(run, seg_sum[seg_slot(g_win * SAMPLE_GRP + i)]);
-        if (i == lane) {
-          before = run;
-          after = nxt;
-        }
-        run = nxt;
-      }
-      hit = __ballot_sync(0xffffffffu, lane < SAMPLE_GRP - 1 && after > target);
-      const int sg_win = hit ? __ffs(hit) - 1 : SAMPLE_GRP - 1;
-      base = __shfl_sync(0xffffffffu, before, sg_win);
-      const int segi = g_win * SAMPLE_GRP + sg_win;
+      int segi;
+      float base, target;
+      warp_descent_segments(seg_sum, grp_sum, u01, lane, segi, base, target);
       // the winning segment's 32 weights again, lane j = code j (two codes per packed word, as in the evaluation)
       const float kt_seg = kts[segi];
       const float f = pow2_factor(__fsub_rn(kt_seg, K));
@@ -582,15 +531,7 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
       float n;
       const float pr = exp_parts((lane & 1) ? t1 : t0, n);
       const float wl = __fmul_rn(__fmul_rn(pr, pow2_factor(__fsub_rn(n, kt_seg))), f);
-      run = base;
-#pragma unroll
-      for (int i = 0; i < SAMPLE_SEG; ++i) {
-        const float nxt = __fadd_rn(run, __shfl_sync(0xffffffffu, wl, i));
-        if (i == lane) after = nxt;
-        run = nxt;
-      }
-      hit = __ballot_sync(0xffffffffu, lane < SAMPLE_SEG - 1 && after > target);
-      const int j = hit ? __ffs(hit) - 1 : SAMPLE_SEG - 1;
+      const int j = warp_descent_codes(wl, base, target, lane);
       if (lane == 0) ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
     }
     return;
@@ -852,46 +793,14 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
   const float f = pow2_factor(__fsub_rn(kt, K));
   seg_sum[seg_slot(tid)] = __fmul_rn(ss_raw, f);
   __syncthreads();
-  constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;
-  if (tid < NGRP) {
-    float g = 0.0f;
-#pragma unroll 8
-    for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[seg_slot(tid * SAMPLE_GRP + j)]);
-    grp_sum[tid] = g;
-  }
-  __syncthreads();
-  __shared__ int bc_seg;
-  __shared__ float bc_base, bc_target;
-  if (tid == 0) {
+  if (warp == 0) {
+    // group sums, descent group -> segment, then the winning segment's 32 weights (one coalesced load) -> code
     int segi;
     float base, target;
-    cdf_descent(seg_sum, grp_sum, u01, segi, base, target);
-    bc_seg = segi;
-    bc_base = base;
-    bc_target = target;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    // the winning segment's 32 weights arrive with one coalesced load; lane 0 walks them in order
-    const int segi = bc_seg;
+    warp_descent_segments(seg_sum, grp_sum, u01, lane, segi, base, target);
     const float fs = pow2_factor(__fsub_rn(b.tile_k[p * ntile + segi / (SAMPLE_TILE / SAMPLE_SEG)], K));
     const float wl = __fmul_rn(__ldcg(b.wbuf + static_cast<int64_t>(p) * vocab + segi * SAMPLE_SEG + lane), fs);
-    float base = bc_base;
-    const float target = bc_target;
-    int j = 0;
-    bool found = false;
-#pragma unroll
-    for (int i = 0; i < SAMPLE_SEG - 1; ++i) {
-      const float wi = __shfl_sync(0xffffffffu, wl, i);
-      const float nxt = __fadd_rn(base, wi);
-      if (!found) {
-        if (nxt > target) found = true;
-        else {
-          base = nxt;
-          j = i + 1;
-        }
-      }
-    }
+    const int j = warp_descent_codes(wl, base, target, lane);
     if (lane == 0) {
       ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
       bc_id = segi * SAMPLE_SEG + j;

@@ -96,10 +96,13 @@ class _SimpoFn(torch.autograd.Function):
                                   grad_seq)
         loss = scalars[_abi.SC_LOSS].clone()
         ctx.mark_non_differentiable(scalars, seq_logps, losses, crew, rrew, row_logps)
+        ctx.set_materialize_grads(False)  # no zero tensors for the six outputs that carry no gradient
         return loss, scalars, seq_logps, losses, crew, rrew, row_logps
 
     @staticmethod
     def backward(ctx, grad_loss, *_):
+        if grad_loss is None:
+            return (None,) * 11
         xb, w1, b1, w2, b2, targets, seq_off, scalars, pre, act, logits, row_lse, grad_seq = ctx.saved_tensors
         head = ctx.head
         H, E, V = head.n_embed, head.image_token_embed, head.image_token_size
@@ -141,10 +144,13 @@ class _LogpsFn(torch.autograd.Function):
         if need_bwd:
             ctx.save_for_backward(xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, pre, act, logits, row_lse)
         ctx.mark_non_differentiable(row_logps)
+        ctx.set_materialize_grads(False)
         return seq_logps, row_logps
 
     @staticmethod
     def backward(ctx, grad_seq, _):
+        if grad_seq is None:
+            return (None,) * 11
         xb, w1, b1, w2, b2, targets, seq_off, pre, act, logits, row_lse = ctx.saved_tensors
         head = ctx.head
         H, E, V = head.n_embed, head.image_token_embed, head.image_token_size

@@ -28,11 +28,43 @@ HP = dict(beta=10.0, gamma_beta_ratio=0.5, label_smoothing=0.0, sft_weight=0.0, 
 ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(N + 1)]
 
 
+class NvmlSampler:
+    """the same three readings through NVML in a Python thread (no nvidia-smi process)"""
+
+    def __init__(self):
+        import threading
+
+        import pynvml
+        self.n = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        self.rows, self.stop_flag = [], False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def start(self):
+        self.t.start()
+
+    def _run(self):
+        import time
+        while not self.stop_flag:
+            self.rows.append((self.n.nvmlDeviceGetClockInfo(self.h, self.n.NVML_CLOCK_SM),
+                              self.n.nvmlDeviceGetPowerUsage(self.h) / 1e3,
+                              self.n.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            time.sleep(0.1)
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join()
+        sm = sorted(r[0] for r in self.rows)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "power_w_max": max((r[1] for r in self.rows), default=None),
+                "samples": len(sm)}
+
+
 def phase(name, spans, sampler):
     _abi.profile_enable(spans)
     if spans:
         _abi.profile_read()
-    cs = ClockSampler(0) if sampler else None
+    cs = (NvmlSampler() if sampler == 2 else ClockSampler(0)) if sampler else None
     if cs:
         cs.start()
     torch.cuda.synchronize()
@@ -75,3 +107,6 @@ phase("      spans=1 smi=1", True, True)
 phase("      spans=0 smi=1", False, True)
 phase("warm  spans=0 smi=0", False, False)
 phase("      spans=1 smi=1 again", True, True)
+phase("      spans=1 nvml thread", True, 2)
+phase("      spans=0 smi=0 last", False, False)
+phase("      spans=1 smi=1 last", True, True)

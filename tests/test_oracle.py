@@ -170,3 +170,27 @@ def test_clip_adamw_oracle_matches_torch_optimizer_golden(golden_dir):
             np.testing.assert_allclose(torch.cat(p).numpy(), d[f"{tag}_p{step + 1}"], rtol=1e-6, atol=1e-9)
             np.testing.assert_allclose(torch.cat(m).numpy(), d[f"{tag}_m{step + 1}"], rtol=1e-6, atol=1e-9)
             np.testing.assert_allclose(torch.cat(v).numpy(), d[f"{tag}_v{step + 1}"], rtol=1e-6, atol=1e-12)
+
+
+def test_magic_number_rounding_equals_rint_for_every_bf16_logit():
+    """The CUDA samplers take n = rint(t log2 e) as (y + 1.5 * 2^23) - 1.5 * 2^23 and read n as an integer from the
+    mantissa bits of y + 1.5 * 2^23 (cfg_math.cuh, exp_weight2p).  Checked here in IEEE fp32 for every bf16 value of t
+    (the merged logits are bf16-valued in the default merge mode), against the oracle's rintf of the clamped product."""
+    import numpy as np
+
+    bits = np.arange(1 << 16, dtype=np.uint32) << 16
+    t = bits.view(np.float32)
+    t = t[np.isfinite(t)]
+    y = (t * np.float32(1.4426950408889634)).astype(np.float32)
+    y = np.minimum(np.maximum(y, np.float32(-1.0e4)), np.float32(1.0e4))
+    magic = np.float32(12582912.0)
+    ym = (y + magic).astype(np.float32)
+    n_magic = (ym - magic).astype(np.float32)
+    n_rint = np.rint(y).astype(np.float32)
+    assert np.array_equal(n_magic, n_rint)  # (-0.0 == +0.0 compares equal: the sign of a zero n never reaches a result)
+    n_int = ym.view(np.int32) - np.int32(0x4B400000)
+    assert np.array_equal(n_int, n_rint.astype(np.int32))
+    # the factor 2^(n - kt) built from the integer difference equals the float construction for every e in [-120, 0]
+    e = np.arange(-120, 1, dtype=np.int32)
+    f_int = ((e << 23) + np.int32(0x3F800000)).view(np.float32)
+    assert np.array_equal(f_int, np.ldexp(np.float32(1.0), e).astype(np.float32))

@@ -81,3 +81,37 @@ def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, ru
     if op == dist.ReduceOp.SUM:
         flat.mul_(1.0 / world)
     return out
+
+
+def dp_check(flat_local: torch.Tensor, flat_reduced: torch.Tensor, group=None) -> dict:
+    """Value check of the gradient exchange on the hardware it runs on (DDP semantics, ospo/utils/train.py:26-28):
+    ``flat_reduced`` (this rank's buffer after the exchange) must be bit-identical on every rank and equal the mean
+    over ranks of the pre-exchange local buffers ``flat_local``.  Compares float64 checksums (sum and sum of squares)
+    and a strided sample of elements gathered from all ranks.  Collective: every rank must call it."""
+    world = _world(group)
+    dev = flat_reduced.device
+    idx = torch.arange(0, flat_reduced.numel(), max(1, flat_reduced.numel() // 65536), device=dev)
+    loc = torch.cat([flat_local.double().sum().reshape(1), flat_local.double().pow(2).sum().reshape(1),
+                     flat_local[idx].double()])
+    red = torch.cat([flat_reduced.double().sum().reshape(1), flat_reduced.double().pow(2).sum().reshape(1),
+                     flat_reduced[idx].double()])
+    bits = flat_reduced.view(torch.int32).to(torch.int64)
+    sig = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 8191 + 1)).sum()])
+    if world > 1:
+        locs = [torch.empty_like(loc) for _ in range(world)]
+        reds = [torch.empty_like(red) for _ in range(world)]
+        sigs = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(locs, loc, group=group)
+        dist.all_gather(reds, red, group=group)
+        dist.all_gather(sigs, sig, group=group)
+    else:
+        locs, reds, sigs = [loc], [red], [sig]
+    mean_loc = torch.stack(locs).mean(0)
+    ranks_equal = all(bool(torch.equal(s, sigs[0])) for s in sigs) and all(bool(torch.equal(r, reds[0])) for r in reds)
+    scale = float(torch.stack(locs)[:, 2:].abs().max().clamp(min=1e-30))
+    sample_err = float((reds[0][2:] - mean_loc[2:]).abs().max()) / scale
+    sum_err = abs(float(reds[0][0] - mean_loc[0])) / max(float(torch.stack(locs)[:, 2:].abs().sum()), 1e-30)
+    ok = ranks_equal and sample_err < 1e-5 and sum_err < 1e-5
+    return {"status": "ok" if ok else "MISMATCH", "world": world, "ranks_bit_identical": ranks_equal,
+            "reduced_checksum": float(reds[0][0]), "mean_of_local_checksums": float(mean_loc[0]),
+            "sample_max_abs_err_rel": sample_err, "checksum_err_rel": sum_err, "sampled_elements": int(idx.numel())}

@@ -195,3 +195,24 @@ def test_magic_number_rounding_equals_rint_for_every_bf16_logit():
     e = np.arange(-120, 1, dtype=np.int32)
     f_int = ((e << 23) + np.int32(0x3F800000)).view(np.float32)
     assert np.array_equal(f_int, np.ldexp(np.float32(1.0), e).astype(np.float32))
+
+
+def test_chunked_fp32_restatement_matches_oracle_on_cpu():
+    """tests/_gpu_ref.py (the fp32 restatement the full-size GPU tests compare against) is device-agnostic: pin it to
+    the oracle here, where no GPU is needed"""
+    from tests._gpu_ref import simpo_step_chunked_fp32
+
+    H, E, V, B, T, L = 96, 64, 512, 3, 16, 2
+    for hp in (dict(beta=10.0, gamma_beta_ratio=0.5, label_smoothing=0.0, loss_type="sigmoid"),
+               dict(beta=2.0, gamma_beta_ratio=0.3, label_smoothing=0.0, loss_type="hinge")):
+        head = O.make_head(H, E, V, seed=31, w2_gain=2.0)
+        hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=32)
+        ref = O.simpo_step(head, hc, hr, lc, lr, backward=True, **hp)
+        w = [t.detach() for t in (head.output_mlp_projector.weight, head.output_mlp_projector.bias,
+                                  head.vision_head.weight, head.vision_head.bias)]
+        got = simpo_step_chunked_fp32(*w, torch.cat([hc, hr]), torch.cat([lc, lr]), T, L, chunk_rows=40, **hp)
+        np.testing.assert_allclose(float(got["loss"]), float(ref["loss"]), rtol=1e-5)
+        np.testing.assert_allclose(got["rejected_logps"].numpy(), ref["rejected_logps"].detach().numpy(), rtol=1e-5)
+        for k in ("dx", "dW2", "dW1", "db2", "db1"):
+            err = float((got[k] - ref[k]).norm() / ref[k].norm())
+            assert err < 1e-5, (k, err)

@@ -127,8 +127,12 @@ typedef struct {
      forward-only call, in which case nothing is spilled) */
   void* pre;                   /* bf16 [rows, E]  pre-activation */
   void* act;                   /* bf16 [rows, E]  required even forward-only */
-  void* logits;                /* bf16 [rows, V]  logits spill; the backward overwrites it with dlogits */
+  void* logits;                /* bf16 [rows, V]  spill of g = exp(logit - row_ref) - onehot * exp(row_lse - row_ref), the
+                                  unscaled softmax-minus-onehot numerator (dlogits = w_row * g); written once by the
+                                  forward GEMM2 epilogue, READ-ONLY in the backward */
   float* row_lse;              /* [rows] */
+  float* row_ref;              /* [rows] exponent reference of each spill row (0 unless the row was repaired); required
+                                  whenever `logits` is given */
   float* grad_seq;             /* [S] d loss / d seq_logps: written by simpo_fwd, read by *_bwd
                                   (for logps_bwd the caller fills it with the upstream gradient) */
 
@@ -141,12 +145,15 @@ typedef struct {
   size_t workspace_bytes;
 
   /* staged backward (data-parallel overlap): 0 = whole backward in one call; otherwise a bit mask of the
-     parts to run now -- 1 = row coefficients, dlogits (+db2), dpre, dW2;  2 = db1, dW1;  4 = dX -- so the caller can
+     parts to run now -- 1 = row weights, dpre, db2, dW2;  2 = db1, dW1;  4 = dX -- so the caller can
      start the all-reduce of dW2 after part 1 and of the remainder after part 2 while the later parts still run.  All
      calls must pass the same workspace (dpre lives there).  reserve_sms (parts 2 / 4): leave this many SMs free for
      the collective kernel running beside the GEMMs. */
   int32_t bwd_stage;
   int32_t reserve_sms;
+  float wgrad_scale;           /* multiplies dW2 | dW1 | db2 | db1 as they are stored (dx is not scaled): a data-parallel
+                                  caller passes 1 / world_size and all-reduces with SUM (ospo/utils/train.py:26-28);
+                                  0 means 1 */
 } ospo_simpo_args;
 
 /* ---- next row: sampled ids -> next-step input embeddings ---------------------------------
@@ -269,12 +276,12 @@ OSPO_API int ospo_head_set_group_m(int group_m);
    default).  profile_read synchronises on the recorded events and returns, per OSPO_K_* id, the summed
    milliseconds and the number of spans since the previous read. */
 #define OSPO_K_GEMM1 0          /* x W1^T + b1, GELU                      (tcgen05 GEMM, K/K)   */
-#define OSPO_K_GEMM2_LSE 1      /* act W2^T + b2, LSE partials, gather    (tcgen05 GEMM, K/K)   */
-#define OSPO_K_SCALAR_STAGE 2   /* lse merge, per-sequence reduce, SimPO scalars                  */
-#define OSPO_K_DLOGITS 3        /* row coefficients + softmax-minus-onehot producer + db2         */
-#define OSPO_K_DACT 4           /* dlogits W2, GELU'                      (tcgen05 GEMM, K/MN)  */
-#define OSPO_K_WGRAD2 5         /* dlogits^T act                          (tcgen05 GEMM, MN/MN) */
-#define OSPO_K_COLSUM 6         /* db1                                                            */
+#define OSPO_K_GEMM2_LSE 1      /* act W2^T + b2, softmax numerator spill, LSE partials, gather (tcgen05 GEMM, K/K) */
+#define OSPO_K_SCALAR_STAGE 2   /* lse merge (+ repair pass, normally empty), one-hot fix-up, per-sequence reduce, SimPO scalars */
+#define OSPO_K_ROW_WEIGHTS 3    /* per-row weights of the backward GEMM pair                      */
+#define OSPO_K_DACT 4           /* row_w * (g W2), GELU', act_w           (tcgen05 GEMM, K/MN)  */
+#define OSPO_K_WGRAD2 5         /* g^T act_w                              (tcgen05 GEMM, MN/MN) */
+#define OSPO_K_COLSUM 6         /* db2, db1: fixed-order column sums                              */
 #define OSPO_K_WGRAD1 7         /* dpre^T x                               (tcgen05 GEMM, MN/MN) */
 #define OSPO_K_DGRAD 8          /* dpre W1                                (tcgen05 GEMM, K/MN)  */
 #define OSPO_K_GEMM2_PLAIN 9    /* act W2^T + b2 -> logits                                         */

@@ -72,6 +72,7 @@ class SimpoArgs(C.Structure):
         ("act", C.c_void_p),
         ("logits", C.c_void_p),
         ("row_lse", C.c_void_p),
+        ("row_ref", C.c_void_p),
         ("grad_seq", C.c_void_p),
         ("grad_loss", C.c_void_p),
         ("dx", C.c_void_p),
@@ -80,6 +81,7 @@ class SimpoArgs(C.Structure):
         ("workspace_bytes", C.c_size_t),
         ("bwd_stage", C.c_int32),
         ("reserve_sms", C.c_int32),
+        ("wgrad_scale", C.c_float),
     ]
 
 
@@ -276,8 +278,8 @@ def workspace_bytes(rows: int, hidden: int, embed: int, vocab: int, num_seqs: in
     return int(out.value)
 
 
-KERNEL_NAMES = ("gemm1_bias_gelu", "gemm2_logits_lse", "scalar_stage", "dlogits_producer", "dact_gelu_bwd",
-                "wgrad_w2", "colsum_db1", "wgrad_w1", "dgrad_x", "gemm2_logits_plain", "decode_gemm1",
+KERNEL_NAMES = ("gemm1_bias_gelu", "gemm2_logits_lse", "scalar_stage", "row_weights", "dact_gelu_bwd",
+                "wgrad_w2", "colsum_db2_db1", "wgrad_w1", "dgrad_x", "gemm2_logits_plain", "decode_gemm1",
                 "decode_gemm2", "cfg_merge_sample", "gen_img_embeds", "clip_adamw")
 
 

@@ -3,6 +3,7 @@
 // synchronisation, no torch types.
 #include "../../include/ospo_head.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <mutex>
@@ -222,10 +223,15 @@ struct Workspace {
   float* rowsum_part;    // [num_n, rows]
   float* tgt;            // [rows]
   float* row_logit_sum;  // [rows]
-  float* row_coef;       // [rows]
+  float* row_coef;       // [rows] backward: row weights w_r of the GEMM pair
+  float* row_max;        // [rows] forward: row maxima of the logits (exponent reference of the repair pass)
+  uint8_t* blk_mask;     // [rows / 128 + 1] forward: GEMM2 M-blocks whose spill must be recomputed (normally none)
   float* seq_sum;        // [S]
   float* seq_logit_sum;  // [S]
+  float* seq_count;      // [S] valid labels per sequence
+  float* colsum_part;    // [rows / 512 + 1, max(V, E)] fixed-order partials of the bias gradients
   __nv_bfloat16* rows_by_e;  // [rows, E]: dpre (backward) / act (plain logits, decode)
+  __nv_bfloat16* act_w;      // [rows, E]: row-weighted activations, B operand of the dW2 GEMM (training shapes only)
   float* decode_part;        // [8, rows, E] split-K partials of the decode GEMM1 (decode-sized shapes only)
   CfgFusedBuffers fused;     // outputs of the fused decode-GEMM2 epilogue (decode-sized shapes only)
   __nv_bfloat16* decode_logits;  // [rows, V] scratch logits for the unfused decode variant
@@ -250,9 +256,17 @@ Workspace carve(const ospo_head_shape& s, void* base) {
   w.tgt = reinterpret_cast<float*>(take(rows * sizeof(float)));
   w.row_logit_sum = reinterpret_cast<float*>(take(rows * sizeof(float)));
   w.row_coef = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  w.row_max = reinterpret_cast<float*>(take(rows * sizeof(float)));
+  w.blk_mask = reinterpret_cast<uint8_t*>(take(rows / 128 + 1));
   w.seq_sum = reinterpret_cast<float*>(take(S * sizeof(float)));
   w.seq_logit_sum = reinterpret_cast<float*>(take(S * sizeof(float)));
+  w.seq_count = reinterpret_cast<float*>(take(S * sizeof(float)));
+  w.colsum_part = reinterpret_cast<float*>(
+      take((rows / CS_ROWS_PER_BLOCK + 1) * static_cast<size_t>(std::max(s.vocab, s.embed)) * sizeof(float)));
   w.rows_by_e = reinterpret_cast<__nv_bfloat16*>(take(rows * static_cast<size_t>(s.embed) * 2));
+  w.act_w = (rows > kDecodeMaxRows || s.num_seqs > 1)
+                ? reinterpret_cast<__nv_bfloat16*>(take(rows * static_cast<size_t>(s.embed) * 2))
+                : nullptr;
   w.decode_part = (rows <= kDecodeMaxRows)
                       ? reinterpret_cast<float*>(take(8 * rows * static_cast<size_t>(s.embed) * sizeof(float)))
                       : nullptr;
@@ -289,13 +303,19 @@ XLayout x_layout(const ospo_simpo_args* a) {
   return xl;
 }
 
-// shared forward: GEMM1 -> GEMM2 + LSE partials -> merge -> per-sequence reduce
+// shared forward: GEMM1 -> GEMM2 (+ softmax numerator spill, LSE partials) -> merge -> [repair pass] -> one-hot
+// fix-up of the spill -> per-sequence reduce
 int logps_forward(const ospo_simpo_args* a, const Workspace& w, cudaStream_t st) {
   const ospo_head_shape& s = a->shape;
   const LaunchCtx c = make_ctx(st);
+  __nv_bfloat16* espill = static_cast<__nv_bfloat16*>(a->logits);
+  if (espill != nullptr && a->row_ref == nullptr) return OSPO_ERR_NULL;
+  const int tile_m = gemm2_tile_m(c.cta_group);
+  const int num_n = gemm2_num_n_tiles(s.vocab);
   int rc;
   {
     KernelSpan ks(st, OSPO_K_GEMM1);
+    if (cudaMemsetAsync(w.blk_mask, 0, static_cast<size_t>(s.rows) / 128 + 1, st) != cudaSuccess) return OSPO_ERR_CUDA;
     rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
                                        static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1,
                                        static_cast<__nv_bfloat16*>(a->pre), static_cast<__nv_bfloat16*>(a->act),
@@ -304,19 +324,35 @@ int logps_forward(const ospo_simpo_args* a, const Workspace& w, cudaStream_t st)
   if (rc) return rc;
   {
     KernelSpan ks(st, OSPO_K_GEMM2_LSE);
-    rc = map_rc(launch_gemm2_logits_lse(c, static_cast<const __nv_bfloat16*>(a->act),
-                                        static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2,
-                                        static_cast<__nv_bfloat16*>(a->logits), a->labels, w.part, w.rowsum_part,
-                                        w.tgt, s.rows, s.embed, s.vocab));
+    rc = map_rc(launch_gemm2_logits_exp(c, static_cast<const __nv_bfloat16*>(a->act),
+                                        static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2, espill, a->labels, w.part,
+                                        w.rowsum_part, w.tgt, nullptr, nullptr, s.rows, s.embed, s.vocab));
   }
   if (rc) return rc;
-  const int num_n = gemm2_num_n_tiles(s.vocab);
   KernelSpan ks(st, OSPO_K_SCALAR_STAGE);
-  lse_finalize_kernel<<<(s.rows + 255) / 256, 256, 0, st>>>(w.part, w.rowsum_part, w.tgt, s.rows, num_n, a->row_lse,
-                                                            a->row_logps, w.row_logit_sum);
+  const int fin_grid = (s.rows + 255) / 256;
+  lse_finalize_kernel<<<fin_grid, 256, 0, st>>>(w.part, w.rowsum_part, w.tgt, a->labels, s.vocab, s.rows, num_n, tile_m,
+                                                1, w.blk_mask, a->row_ref, w.row_max, a->row_lse, a->row_logps,
+                                                w.row_logit_sum);
   if ((rc = check_launch())) return rc;
-  seq_reduce_kernel<<<s.num_seqs, 256, 0, st>>>(a->row_logps, w.row_logit_sum, a->seq_offsets, a->average_log_prob,
-                                                a->seq_logps, w.seq_sum, w.seq_logit_sum);
+  // repair pass: M-blocks with a row maximum outside the representable window are recomputed against their own row
+  // maxima.  For ordinary logits no block is flagged and both launches return at once.
+  rc = map_rc(launch_gemm2_logits_exp(c, static_cast<const __nv_bfloat16*>(a->act),
+                                      static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2, espill, a->labels, w.part,
+                                      w.rowsum_part, w.tgt, w.row_max, w.blk_mask, s.rows, s.embed, s.vocab));
+  if (rc) return rc;
+  lse_finalize_kernel<<<fin_grid, 256, 0, st>>>(w.part, w.rowsum_part, w.tgt, a->labels, s.vocab, s.rows, num_n, tile_m,
+                                                2, w.blk_mask, a->row_ref, w.row_max, a->row_lse, a->row_logps,
+                                                w.row_logit_sum);
+  if ((rc = check_launch())) return rc;
+  if (espill != nullptr) {
+    target_fixup_kernel<<<fin_grid, 256, 0, st>>>(espill, s.vocab, a->labels, s.vocab, s.rows, a->row_logps,
+                                                  a->row_lse, a->row_ref);
+    if ((rc = check_launch())) return rc;
+  }
+  seq_reduce_kernel<<<s.num_seqs, 256, 0, st>>>(a->row_logps, w.row_logit_sum, a->seq_offsets, a->labels, s.vocab,
+                                                a->average_log_prob, a->seq_logps, w.seq_sum, w.seq_logit_sum,
+                                                w.seq_count);
   return check_launch();
 }
 
@@ -337,16 +373,30 @@ int check_simpo_common(const ospo_simpo_args* a, Workspace* w) {
   return check_ws(a->shape, a->workspace, a->workspace_bytes, w);
 }
 
-// shared backward: row coefficients -> softmax-minus-onehot producer -> GEMM pair(s)
+// column sums (bias gradients) in two fixed-order stages
+template <bool WEIGHTED>
+int launch_colsum(const __nv_bfloat16* x, int rows, int cols, const float* row_w, float scale, float* partial,
+                  float* out, cudaStream_t st) {
+  const int row_blocks = (rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK;
+  dim3 grid((cols + 1023) / 1024, row_blocks);
+  colsum_partial_kernel<WEIGHTED><<<grid, 128, 0, st>>>(x, cols, rows, cols, row_w, partial);
+  int rc = check_launch();
+  if (rc) return rc;
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(partial, row_blocks, cols, scale, out);
+  return check_launch();
+}
+
+// shared backward: row weights -> GEMM pair(s) straight on the forward's spill (read-only here)
 int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft_coef, int num_sft_seqs,
                   cudaStream_t st) {
   const ospo_head_shape& s = a->shape;
   if (!a->dx && !a->flat_grads) return OSPO_OK;
-  if (!a->pre || !a->act || !a->logits || !a->row_lse || !a->grad_seq) return OSPO_ERR_NULL;
+  if (!a->pre || !a->act || !a->logits || !a->row_lse || !a->row_ref || !a->grad_seq) return OSPO_ERR_NULL;
+  if (a->flat_grads && !w.act_w) return OSPO_ERR_WORKSPACE;
   LaunchCtx c = make_ctx(st);
   int rc;
-  // bwd_stage: 0 = everything; otherwise a bit mask of the parts to run now: 1 = row coefficients, dlogits (+db2),
-  // dpre and dW2;  2 = db1 and dW1;  4 = dX.  A data-parallel caller runs 1, starts the all-reduce of dW2, runs 2,
+  // bwd_stage: 0 = everything; otherwise a bit mask of the parts to run now: 1 = row weights, dpre (+ act_w), db2
+  // and dW2;  2 = db1 and dW1;  4 = dX.  A data-parallel caller runs 1, starts the all-reduce of dW2, runs 2,
   // starts the all-reduce of the rest and runs 4.  dpre lives in the workspace: same buffer in every call.
   const int stage = a->bwd_stage == 0 ? 7 : a->bwd_stage;
   if (stage < 1 || stage > 7) return OSPO_ERR_UNSUPPORTED;
@@ -361,45 +411,46 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   float* dW1 = a->flat_grads ? a->flat_grads + VE : nullptr;
   float* db2 = a->flat_grads ? a->flat_grads + VE + EH : nullptr;
   float* db1 = a->flat_grads ? db2 + s.vocab : nullptr;
-  __nv_bfloat16* dlogits = static_cast<__nv_bfloat16*>(a->logits);
+  const float wscale = a->wgrad_scale != 0.0f ? a->wgrad_scale : 1.0f;  // 1 / world_size of a data-parallel caller
+  const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(a->logits);
   __nv_bfloat16* dpre = w.rows_by_e;
+  float* row_w = w.row_coef;
   if (first) {
-    KernelSpan ks(st, OSPO_K_DLOGITS);
-    row_coef_kernel<<<s.num_seqs, 128, 0, st>>>(a->grad_seq, a->seq_offsets, a->average_log_prob, a->grad_loss,
-                                                sft_coef, num_sft_seqs, w.row_coef);
-    if ((rc = check_launch())) return rc;
-    if (a->flat_grads) {
-      if (cudaMemsetAsync(db2, 0, sizeof(float) * (static_cast<size_t>(s.vocab) + s.embed), st) != cudaSuccess)
-        return OSPO_ERR_CUDA;
+    {
+      KernelSpan ks(st, OSPO_K_ROW_WEIGHTS);
+      row_weight_kernel<<<s.num_seqs, 128, 0, st>>>(a->grad_seq, a->seq_offsets, a->labels, s.vocab,
+                                                    a->average_log_prob, a->grad_loss, sft_coef, num_sft_seqs,
+                                                    a->row_lse, a->row_ref, row_w);
+      if ((rc = check_launch())) return rc;
     }
-    dim3 grid((s.vocab + 1023) / 1024, (s.rows + DL_ROWS_PER_BLOCK - 1) / DL_ROWS_PER_BLOCK);
-    dlogits_kernel<<<grid, 128, 0, st>>>(dlogits, s.vocab, a->labels, a->row_lse, w.row_coef, s.rows, s.vocab, db2);
-    if ((rc = check_launch())) return rc;
-  }
-  if (first) {
-    KernelSpan ks(st, OSPO_K_DACT);
-    rc = map_rc(launch_dact_gelu_bwd(c, dlogits, static_cast<const __nv_bfloat16*>(a->w.w2),
-                                     static_cast<const __nv_bfloat16*>(a->pre), dpre, s.rows, s.embed, s.vocab));
-    if (rc) return rc;
+    {
+      KernelSpan ks(st, OSPO_K_DACT);
+      rc = map_rc(launch_dact_gelu_bwd(c, g, static_cast<const __nv_bfloat16*>(a->w.w2),
+                                       static_cast<const __nv_bfloat16*>(a->pre), row_w, dpre,
+                                       a->flat_grads ? w.act_w : nullptr, s.rows, s.embed, s.vocab));
+      if (rc) return rc;
+    }
   }
   if (a->flat_grads && first) {
+    {
+      KernelSpan ks(st, OSPO_K_COLSUM);
+      if ((rc = launch_colsum<true>(g, s.rows, s.vocab, row_w, wscale, w.colsum_part, db2, st))) return rc;
+    }
     // dW2 first: it is the largest block of the flat gradient, so a caller that overlaps the
     // all-reduce with the remaining GEMMs can start on it earliest.
     KernelSpan ks(st, OSPO_K_WGRAD2);
-    rc = map_rc(launch_wgrad(c, dlogits, static_cast<const __nv_bfloat16*>(a->act), dW2, s.rows, s.vocab, s.embed));
+    rc = map_rc(launch_wgrad(c, g, w.act_w, dW2, s.rows, s.vocab, s.embed, wscale));
     if (rc) return rc;
   }
   if (a->flat_grads && second) {
     {
       KernelSpan ks(st, OSPO_K_COLSUM);
-      dim3 grid((s.embed + 1023) / 1024, (s.rows + DL_ROWS_PER_BLOCK - 1) / DL_ROWS_PER_BLOCK);
-      colsum_bf16_kernel<<<grid, 128, 0, st>>>(dpre, s.embed, s.rows, s.embed, db1);
-      if ((rc = check_launch())) return rc;
+      if ((rc = launch_colsum<false>(dpre, s.rows, s.embed, nullptr, wscale, w.colsum_part, db1, st))) return rc;
     }
     {
       KernelSpan ks(st, OSPO_K_WGRAD1);
       rc = map_rc(launch_wgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden,
-                               x_layout(a)));
+                               wscale, x_layout(a)));
     }
     if (rc) return rc;
   }
@@ -493,7 +544,7 @@ int ospo_head_simpo_fwd(const ospo_simpo_args* a, ospo_stream_t stream) {
   hp.loss_type = a->loss_type;
   hp.vocab = a->shape.vocab;
   KernelSpan ks(st, OSPO_K_SCALAR_STAGE);
-  simpo_scalar_kernel<<<1, 256, 0, st>>>(a->seq_logps, w.seq_sum, w.seq_logit_sum, a->seq_offsets,
+  simpo_scalar_kernel<<<1, 256, 0, st>>>(a->seq_logps, w.seq_sum, w.seq_logit_sum, w.seq_count,
                                          a->shape.num_seqs / 2, hp, a->losses, a->chosen_rewards, a->rejected_rewards,
                                          a->grad_seq, a->scalars);
   return check_launch();

@@ -126,6 +126,7 @@ struct EpiStore {
     int64_t ld;
     const float* bias;  // may be null
     RowMap rmap;        // where output row r lands (identity unless the output is row-segmented)
+    float scale;        // out = scale * acc (+ bias); 0 means 1 (weight gradients carry 1 / world_size)
   };
   struct State {
     float rb;
@@ -143,6 +144,10 @@ struct EpiStore {
     if (row >= d.M) return;
     const int valid = FULL ? 32 : d.N - col0;
     if (valid <= 0) return;
+    if (p.scale != 0.0f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+    }
     if constexpr (ROW_BIAS) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += st.rb;
@@ -351,31 +356,44 @@ struct EpiBiasGelu {
 };
 
 // ---------------------------------------------------------------------------
-// GEMM2 forward epilogue:  logits = bf16(acc + b2), plus -- without ever materialising fp32 logits or a
-// log-softmax tensor -- per (row, column sub-tile) partial (max, sum-exp), the gathered target logit and the
-// partial row-sum of the logits.  The bf16 logits are (optionally) spilled once for the backward pass.
-// reference: vision_head Linear (modeling_vlm.py:50) + log_softmax/gather (ospo/wrapper/train.py:391).
-// The log-sum-exp is taken over the bf16-rounded logits in fp32, which is what the bf16 reference
-// path computes (Linear output bf16, log_softmax autocast to fp32).
+// GEMM2 forward epilogue with the softmax-minus-onehot producer fused in (SURVEY §2 K2 + K4).
+//   logit l = bf16(acc + b2)                       vision_head Linear, modeling_vlm.py:50
+//   e      = exp(l - ref_row)                      the softmax numerator of train.py:391's log_softmax
+// Per (row, column sub-tile) it leaves (max l, sum e) partials, the gathered target logit and the partial
+// row-sum of the logits; e is (optionally) spilled ONCE as bf16 -- it is the A operand of both backward GEMMs:
+// softmax = e * exp(ref - lse) is a per-row scale that commutes with the contraction, so no separate
+// softmax-minus-onehot pass ever runs over the [rows, V] tensor (the one-hot term is one element per row,
+// written by target_fixup_kernel).  The log-sum-exp is taken over the bf16-rounded logits in fp32, which is what
+// the bf16 reference path computes (Linear output bf16, log_softmax autocast to fp32).
+// ref_row: 0 in the first pass.  bf16 / fp32 share their exponent range, so e is representable (and the fp32
+// accumulations downstream stay in range) while max_row - ref_row lies in [-50, 60]; lse_finalize_kernel checks
+// that per row and flags the 128/256-row blocks that violate it, and a second (normally empty) launch of this
+// GEMM with blk_mask set recomputes just those blocks against ref_row = max_row.
 // ---------------------------------------------------------------------------
-struct EpiLogitsLse {
+struct EpiLogitsExp {
   struct Params {
     const float* bias;          // [V]
-    __nv_bfloat16* logits;      // [rows, V] spill (may be null)
+    __nv_bfloat16* espill;      // [rows, V] bf16 spill of e (may be null: forward only)
     int64_t ld;
     const int64_t* labels;      // [rows] target code per row
-    float2* part;               // [num_sub_tiles, rows] (max, sumexp) partials
+    float2* part;               // [num_sub_tiles, rows] (max logit, sum of e) partials
     float* rowsum_part;         // [num_sub_tiles, rows] partial sums of logits (may be null)
     float* tgt;                 // [rows] gathered target logit
+    const float* row_ref;       // [rows] exponent reference (null = 0: first pass)
+    const uint8_t* blk_mask;    // [num M-blocks] repair pass: only the flagged blocks are recomputed (null = all)
   };
   struct State {
-    float m, s, sum, tgt;
+    float m, s, sum, tgt, nref;
     int label;
     bool hit;
   };
   static constexpr int SMEM_BYTES = 0;
+  static constexpr bool HAS_TILE_MASK = true;
   static constexpr float LOG2E = 1.4426950408889634f;
 
+  __device__ static bool tile_enabled(const Params& p, int m_blk) {
+    return p.blk_mask == nullptr || p.blk_mask[m_blk] != 0;
+  }
   __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
     st.m = -INFINITY;
     st.s = 0.0f;
@@ -383,6 +401,7 @@ struct EpiLogitsLse {
     st.tgt = 0.0f;
     st.hit = false;
     st.label = (row < d.M) ? static_cast<int>(__ldg(p.labels + row)) : -1;
+    st.nref = (p.row_ref != nullptr && row < d.M) ? -__ldg(p.row_ref + row) * LOG2E : 0.0f;
   }
   template <bool FULL>
   __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
@@ -393,45 +412,48 @@ struct EpiLogitsLse {
     float b[32];
     load_bias32<FULL>(p.bias, col0, valid, b);
     float cmax = -INFINITY;
+    float acc0 = 0.0f, acc1 = 0.0f, ls0 = 0.0f, ls1 = 0.0f;
     if constexpr (FULL) {
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         v[2 * i] += b[2 * i];
         v[2 * i + 1] += b[2 * i + 1];
-        pk[i] = round_pair_bf16(v[2 * i], v[2 * i + 1]);
+        round_pair_bf16(v[2 * i], v[2 * i + 1]);      // the logits exactly as the bf16 Linear emits them
         cmax = fmaxf(cmax, fmaxf(v[2 * i], v[2 * i + 1]));
+        const float e0 = ex2_approx(fmaf(v[2 * i], LOG2E, st.nref));
+        const float e1 = ex2_approx(fmaf(v[2 * i + 1], LOG2E, st.nref));
+        acc0 += e0;
+        acc1 += e1;
+        ls0 += v[2 * i];
+        ls1 += v[2 * i + 1];
+        pk[i] = pack_bf16x2(e0, e1);
       }
-      if (p.logits != nullptr) {
-        __nv_bfloat16* dst = p.logits + static_cast<int64_t>(row) * p.ld + col0;
-        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) store_packed16(dst, pk);
-        else store_row32_bf16<false>(dst, v, 32);
+      if (p.espill != nullptr) {
+        __nv_bfloat16* dst = p.espill + static_cast<int64_t>(row) * p.ld + col0;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+          store_packed16(dst, pk);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) reinterpret_cast<uint32_t*>(dst)[i] = pk[i];  // rows are 4-byte aligned (V % 8 == 0)
+        }
       }
     } else {
+      float e[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         v[j] = bf16_round(v[j] + b[j]);
-        if (j < valid) cmax = fmaxf(cmax, v[j]);
+        e[j] = 0.0f;
+        if (j < valid) {
+          cmax = fmaxf(cmax, v[j]);
+          e[j] = ex2_approx(fmaf(v[j], LOG2E, st.nref));
+          acc0 += e[j];
+          ls0 += v[j];
+        }
       }
-      if (p.logits != nullptr) store_row32_bf16<false>(p.logits + static_cast<int64_t>(row) * p.ld + col0, v, valid);
+      if (p.espill != nullptr) store_row32_bf16<false>(p.espill + static_cast<int64_t>(row) * p.ld + col0, e, valid);
     }
-    if (cmax > st.m) {
-      st.s *= ex2_approx((st.m - cmax) * LOG2E);  // ex2(-inf) = 0 on the first chunk
-      st.m = cmax;
-    }
-    const float mneg = -st.m * LOG2E;
-    float acc0 = 0.0f, acc1 = 0.0f, ls0 = 0.0f, ls1 = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      if (FULL || j < valid) {
-        acc0 += ex2_approx(fmaf(v[j], LOG2E, mneg));
-        ls0 += v[j];
-      }
-      if (FULL || j + 1 < valid) {
-        acc1 += ex2_approx(fmaf(v[j + 1], LOG2E, mneg));
-        ls1 += v[j + 1];
-      }
-    }
+    st.m = fmaxf(st.m, cmax);
     st.s += acc0 + acc1;
     st.sum += ls0 + ls1;
     const int rel = st.label - col0;
@@ -447,24 +469,36 @@ struct EpiLogitsLse {
     const int64_t idx = static_cast<int64_t>(sub_tile) * d.M + row;
     p.part[idx] = make_float2(st.m, st.s);
     if (p.rowsum_part != nullptr) p.rowsum_part[idx] = st.sum;
-    if (st.hit) p.tgt[row] = st.tgt;  // only the sub-tile that holds the label column writes
+    if (st.hit) p.tgt[row] = st.tgt;  // only the sub-tile that holds the label column writes (lse_finalize ignores
+                                      // tgt for labels outside [0, V))
   }
 };
 
 // ---------------------------------------------------------------------------
-// dAct GEMM epilogue:  dpre = bf16(bf16(acc) * gelu'(pre))      (autograd of GELU)
+// dAct GEMM epilogue.  The A operand is the forward's unscaled spill g = e - onehot * exp(lse - ref), so
+//   dact = w_row * acc                    w_row = -c_row * exp(ref_row - lse_row), c_row = d loss / d logp_row
+//   dpre = bf16(bf16(dact) * gelu'(pre))  autograd of GELU, SURVEY §8 a-6
+// and, for the weight-gradient GEMM that follows, the row-scaled activations
+//   act_w = bf16(w_row * act),  act = bf16(gelu(pre)) recomputed from the pre-activation already in registers
+// (dW2 = dlogits^T act = g^T act_w: the row scale rides on the other operand).
 // ---------------------------------------------------------------------------
-struct EpiGeluBwd {
+struct EpiDactScale {
   struct Params {
     const __nv_bfloat16* pre;  // [rows, E]
     __nv_bfloat16* dpre;       // [rows, E]
     int64_t ld;
+    const float* row_w;        // [rows]
+    __nv_bfloat16* act_w;      // [rows, E] out (null: head frozen, no weight gradient)
   };
-  struct State {};
+  struct State {
+    float w;
+  };
   static constexpr int SMEM_BYTES = 0;
-  __device__ static void begin(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
+  __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
+    st.w = (row < d.M) ? __ldg(p.row_w + row) : 0.0f;
+  }
   template <bool FULL>
-  __device__ static void chunk(const Params& p, State&, int row, int col0, float (&v)[32], const GemmDims& d,
+  __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
                                uint8_t*) {
     if (row >= d.M) return;
     const int valid = FULL ? 32 : d.N - col0;
@@ -472,8 +506,21 @@ struct EpiGeluBwd {
     const int64_t off = static_cast<int64_t>(row) * p.ld + col0;
     float pre[32];
     load_row32_bf16<FULL>(p.pre + off, pre, valid);
+    if (p.act_w != nullptr) {
+      float aw[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]) * gelu_erf_grad(pre[j]);
+      for (int j = 0; j < 32; ++j) {
+        const float x = pre[j];
+        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+        const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+        aw[j] = st.w * bf16_round(gelu_erf(x));
+        v[j] = bf16_round(st.w * v[j]) * (cdf + x * pdf);
+      }
+      store_row32_bf16<FULL>(p.act_w + off, aw, valid);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = bf16_round(st.w * v[j]) * gelu_erf_grad(pre[j]);
+    }
     store_row32_bf16<FULL>(p.dpre + off, v, valid);
   }
   __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}

@@ -13,14 +13,14 @@ using CfgD2 = GemmCfg<2, 256, false, true>;
 using CfgW1 = GemmCfg<1, 256, true, true>;
 using CfgW2 = GemmCfg<2, 256, true, true>;
 
-int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* dlogits, const __nv_bfloat16* w2,
-                         const __nv_bfloat16* pre, __nv_bfloat16* dpre, int rows, int E, int V) {
-  using Epi = EpiGeluBwd;
-  Epi::Params p{pre, dpre, E};
-  // D[rows, E] = dlogits[rows, V] * W2[V, E]:  M = rows, N = E, K = V
-  if (c.cta_group == 2) return launch_gemm<CfgD2, Epi>(dlogits, V, w2, E, rows, E, V, c.group_m, p, c.num_sms, c.stream, 1, false,
+int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* g, const __nv_bfloat16* w2, const __nv_bfloat16* pre,
+                         const float* row_w, __nv_bfloat16* dpre, __nv_bfloat16* act_w, int rows, int E, int V) {
+  using Epi = EpiDactScale;
+  Epi::Params p{pre, dpre, E, row_w, act_w};
+  // D[rows, E] = g[rows, V] * W2[V, E]:  M = rows, N = E, K = V
+  if (c.cta_group == 2) return launch_gemm<CfgD2, Epi>(g, V, w2, E, rows, E, V, c.group_m, p, c.num_sms, c.stream, 1, false,
                                   SegOperand(), SegOperand(), 0, c.sync_ctr);
-  return launch_gemm<CfgD1, Epi>(dlogits, V, w2, E, rows, E, V, c.group_m, p, c.num_sms, c.stream, 1, false,
+  return launch_gemm<CfgD1, Epi>(g, V, w2, E, rows, E, V, c.group_m, p, c.num_sms, c.stream, 1, false,
                                   SegOperand(), SegOperand(), 0, c.sync_ctr);
 }
 
@@ -36,9 +36,9 @@ int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat1
 }
 
 int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw, int rows, int out_dim,
-                 int in_dim, const XLayout& xl) {
+                 int in_dim, float scale, const XLayout& xl) {
   using Epi = EpiStore<float, false, false>;
-  Epi::Params p{dw, in_dim, nullptr};
+  Epi::Params p{dw, in_dim, nullptr, RowMap{0, 0, 0}, scale};
   SegOperand sb;
   sb.seg_rows = xl.seg_rows;
   sb.seg_pitch = xl.seg_pitch;

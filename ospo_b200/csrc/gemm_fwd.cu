@@ -34,15 +34,19 @@ int launch_gemm1_bias_gelu(const LaunchCtx& c, const __nv_bfloat16* x, const __n
   }
 }
 
-int launch_gemm2_logits_lse(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
-                            __nv_bfloat16* logits, const int64_t* labels, float2* part, float* rowsum_part, float* tgt,
-                            int rows, int E, int V) {
-  using Epi = EpiLogitsLse;
-  Epi::Params p{b2, logits, V, labels, part, rowsum_part, tgt};
+int gemm2_tile_m(int cta_group) { return cta_group == 2 ? Cfg2::TILE_M : Cfg1::TILE_M; }
+
+int launch_gemm2_logits_exp(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
+                            __nv_bfloat16* espill, const int64_t* labels, float2* part, float* rowsum_part, float* tgt,
+                            const float* row_ref, const uint8_t* blk_mask, int rows, int E, int V) {
+  using Epi = EpiLogitsExp;
+  Epi::Params p{b2, espill, V, labels, part, rowsum_part, tgt, row_ref, blk_mask};
+  // the repair pass (blk_mask set) computes a handful of tiles at most: no wave lock-step
+  uint32_t* sync = blk_mask ? nullptr : c.sync_ctr;
   if (c.cta_group == 2) return launch_gemm<Cfg2, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream, 1, false, SegOperand(), SegOperand(), 0,
-                                 c.sync_ctr);
+                                 sync);
   return launch_gemm<Cfg1, Epi>(act, E, w2, E, rows, V, E, c.group_m, p, c.num_sms, c.stream, 1, false, SegOperand(), SegOperand(), 0,
-                                 c.sync_ctr);
+                                 sync);
 }
 
 int launch_gemm2_logits(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,

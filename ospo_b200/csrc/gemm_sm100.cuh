@@ -149,6 +149,23 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n, int
 // the chunk are inside N (the common case: no per-element predicates).  With EPI_SPLIT == 2 a (row, tile)
 // is handled by two threads (column halves); `sub_tile` = n_blk * EPI_SPLIT + half identifies the part.
 
+// Optional tile mask: an epilogue functor that declares `static constexpr bool HAS_TILE_MASK = true` and
+// `static bool tile_enabled(const Params&, int m_blk)` makes all three roles skip the tiles of disabled M-blocks
+// (the repair pass of the forward GEMM2 recomputes only the flagged row blocks; normally that is none).
+template <class Epi, class = void>
+struct epi_has_tile_mask {
+  static constexpr bool value = false;
+};
+template <class Epi>
+struct epi_has_tile_mask<Epi, decltype(void(Epi::HAS_TILE_MASK))> {
+  static constexpr bool value = Epi::HAS_TILE_MASK;
+};
+template <class Epi, class P>
+__device__ __forceinline__ bool epi_tile_enabled(const P& ep, int m_blk) {
+  if constexpr (epi_has_tile_mask<Epi>::value) return Epi::tile_enabled(ep, m_blk);
+  else return true;
+}
+
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(Cfg::BOUND_THREADS, Cfg::MIN_BLOCKS)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmDims dims,
@@ -293,6 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       bool sync_wait = true;
       for (int t = dom_first; t < dom_tiles; t += dom_stride, ++tile_no) {
         const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
+        if (!epi_tile_enabled<Epi>(ep, tc.m_blk)) continue;
         const int m0 = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM;
         const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         const int kb0 = (t % ksplits) * dims.kb_per_split;
@@ -345,9 +363,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = dom_first; t < dom_tiles; t += dom_stride, ++it) {
+      for (int t = dom_first; t < dom_tiles; t += dom_stride) {
+        if constexpr (epi_has_tile_mask<Epi>::value) {
+          if (!Epi::tile_enabled(ep, tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0).m_blk)) continue;
+        }
         const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
         const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+        ++it;  // counts the tiles this cluster really computes (masked tiles use no accumulator stage)
         mbar_wait(&tmem_empty_bar[as], aph ^ 1u, SITE_MMA_TMEM_EMPTY);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -393,11 +415,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       leader_tmem_empty_addr[a] = (CG == 2) ? mapa_shared(local, 0) : local;
     }
     int it = 0;
-    for (int t = dom_first; t < dom_tiles; t += dom_stride, ++it) {
+    for (int t = dom_first; t < dom_tiles; t += dom_stride) {
       const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
+      if (!epi_tile_enabled<Epi>(ep, tc.m_blk)) continue;
       const int ks = t % ksplits;
       const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
       const uint32_t aph = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+      ++it;
       const int row = tc.m_blk * Cfg::TILE_M + static_cast<int>(cta_rank) * BM + q * 32 + lane;
       const int n0 = tc.n_blk * BN;
       mbar_wait(&tmem_full_bar[as], aph, SITE_EPI_TMEM_FULL);

@@ -10,26 +10,60 @@
 namespace ospo {
 
 // ---------------------------------------------------------------------------
-// Merge the per-(N-tile,row) partials written by EpiLogitsLse into per-row lse and log-prob.
+// Merge the per-(N-tile,row) partials written by EpiLogitsExp into per-row lse and log-prob.
 // reference: logits.log_softmax(-1) gathered at labels, ospo/wrapper/train.py:391
+//   lse_row = ref_row + log(sum of the partial sums of e = exp(l - ref_row))       (fixed order: deterministic)
+// pass 1 (ref = 0 everywhere): also records the row maximum and flags, per GEMM M-block of `tile_m` rows, the
+//   blocks in which some row's maximum lies outside the window where e is safely representable ([-50, 60]; a NaN
+//   fails the test too).  pass 2 touches only the flagged blocks, whose partials the repair launch of GEMM2 has
+//   rewritten against ref_row = max_row.
+// A label outside [0, V) (ignore_index inside a promised image span, train.py:387-389) yields log-prob 0 and is
+// left out of every count, exactly like a masked position.
 // ---------------------------------------------------------------------------
+constexpr float E_WINDOW_HI = 60.0f, E_WINDOW_LO = -50.0f;
+
 __global__ void lse_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ rowsum_part,
-                                    const float* __restrict__ tgt, int rows, int num_n, float* __restrict__ row_lse,
-                                    float* __restrict__ row_logp, float* __restrict__ row_logit_sum) {
+                                    const float* __restrict__ tgt, const int64_t* __restrict__ labels, int vocab,
+                                    int rows, int num_n, int tile_m, int pass, uint8_t* __restrict__ blk_mask,
+                                    float* __restrict__ row_ref, float* __restrict__ row_max,
+                                    float* __restrict__ row_lse, float* __restrict__ row_logp,
+                                    float* __restrict__ row_logit_sum) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  float m = -INFINITY;
-  for (int nb = 0; nb < num_n; ++nb) m = fmaxf(m, part[static_cast<int64_t>(nb) * rows + r].x);
-  float s = 0.0f, ls = 0.0f;
+  if (pass == 2 && blk_mask[r / tile_m] == 0) return;
+  float m = -INFINITY, s = 0.0f, ls = 0.0f;
   for (int nb = 0; nb < num_n; ++nb) {
     const float2 p = part[static_cast<int64_t>(nb) * rows + r];
-    s += p.y * expf(p.x - m);
+    m = fmaxf(m, p.x);
+    s += p.y;
     if (rowsum_part != nullptr) ls += rowsum_part[static_cast<int64_t>(nb) * rows + r];
   }
-  const float lse = m + logf(s);
+  float ref = 0.0f;
+  if (pass == 1) {
+    row_max[r] = m;
+    if (!(m <= E_WINDOW_HI && m >= E_WINDOW_LO)) blk_mask[r / tile_m] = 1;  // benign race: every writer stores 1
+  } else {
+    ref = row_max[r];
+  }
+  if (row_ref != nullptr) row_ref[r] = ref;
+  const float lse = ref + logf(s);
+  const int64_t lab = labels[r];
   row_lse[r] = lse;
-  row_logp[r] = tgt[r] - lse;
+  row_logp[r] = (lab >= 0 && lab < vocab) ? tgt[r] - lse : 0.0f;
   if (row_logit_sum != nullptr) row_logit_sum[r] = ls;
+}
+
+// The one-hot term of softmax-minus-onehot: one element per row of the forward's spill.
+//   g[r, label_r] = (p_target - 1) * exp(lse_r - ref_r),   p_target - 1 = expm1(logp_r)  (exact as p_target -> 1)
+// so that  dlogits[r, :] = c_r (onehot - softmax) = -c_r exp(ref_r - lse_r) * g[r, :]  for the whole row.
+__global__ void target_fixup_kernel(__nv_bfloat16* __restrict__ espill, int64_t ld, const int64_t* __restrict__ labels,
+                                    int vocab, int rows, const float* __restrict__ row_logp,
+                                    const float* __restrict__ row_lse, const float* __restrict__ row_ref) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int64_t lab = labels[r];
+  if (lab < 0 || lab >= vocab) return;
+  espill[static_cast<int64_t>(r) * ld + lab] = __float2bfloat16_rn(expm1f(row_logp[r]) * expf(row_lse[r] - row_ref[r]));
 }
 
 template <int THREADS>
@@ -48,25 +82,32 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // One block per sequence: (per_token_logps * mask).sum(-1) [/ mask.sum(-1)]  (train.py:393-396).
-// Rows of sequence s are [seq_off[s], seq_off[s+1]) -- only unmasked rows are ever given to the head.
+// Rows of sequence s are [seq_off[s], seq_off[s+1]); a row whose label lies outside [0, V) counts as masked
+// (its log-prob is already 0), so mask.sum(-1) = seq_count[s] is the number of valid labels.
 __global__ void seq_reduce_kernel(const float* __restrict__ row_logp, const float* __restrict__ row_logit_sum,
-                                  const int64_t* __restrict__ seq_off, int average, float* __restrict__ seq_logps,
-                                  float* __restrict__ seq_sum, float* __restrict__ seq_logit_sum) {
+                                  const int64_t* __restrict__ seq_off, const int64_t* __restrict__ labels, int vocab,
+                                  int average, float* __restrict__ seq_logps, float* __restrict__ seq_sum,
+                                  float* __restrict__ seq_logit_sum, float* __restrict__ seq_count) {
   __shared__ float red[256];
   const int s = blockIdx.x;
   const int64_t lo = seq_off[s], hi = seq_off[s + 1];
-  float a = 0.0f, b = 0.0f;
+  float a = 0.0f, b = 0.0f, n = 0.0f;
   for (int64_t r = lo + threadIdx.x; r < hi; r += 256) {
-    a += row_logp[r];
-    if (row_logit_sum != nullptr) b += row_logit_sum[r];
+    const int64_t lab = labels[r];
+    if (lab >= 0 && lab < vocab) {
+      n += 1.0f;
+      a += row_logp[r];
+      if (row_logit_sum != nullptr) b += row_logit_sum[r];
+    }
   }
   a = block_sum<256>(a, red);
   b = block_sum<256>(b, red);
+  n = block_sum<256>(n, red);
   if (threadIdx.x == 0) {
-    const float n = static_cast<float>(hi - lo);
     seq_sum[s] = a;
-    seq_logps[s] = average ? a / n : a;
+    seq_logps[s] = average ? a / n : a;   // 0 / 0 = NaN for a fully masked sequence, as in the reference
     if (seq_logit_sum != nullptr) seq_logit_sum[s] = b;
+    seq_count[s] = n;
   }
 }
 
@@ -104,7 +145,7 @@ __device__ __forceinline__ float log_sigmoid(float x) {
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void simpo_scalar_kernel(const float* __restrict__ seq_logps, const float* __restrict__ seq_sum,
-                                    const float* __restrict__ seq_logit_sum, const int64_t* __restrict__ seq_off,
+                                    const float* __restrict__ seq_logit_sum, const float* __restrict__ seq_count,
                                     int B, SimpoHyper hp, float* __restrict__ losses,
                                     float* __restrict__ chosen_rewards, float* __restrict__ rejected_rewards,
                                     float* __restrict__ grad_seq, float* __restrict__ scalars) {
@@ -137,8 +178,8 @@ __global__ void simpo_scalar_kernel(const float* __restrict__ seq_logps, const f
     lc_acc += c;
     lr_acc += r;
     csum_acc += seq_sum[b];
-    ccount_acc += static_cast<float>(seq_off[b + 1] - seq_off[b]);
-    rcount_acc += static_cast<float>(seq_off[B + b + 1] - seq_off[B + b]);
+    ccount_acc += seq_count[b];
+    rcount_acc += seq_count[B + b];
     if (seq_logit_sum != nullptr) {
       clog_acc += seq_logit_sum[b];
       rlog_acc += seq_logit_sum[B + b];
@@ -178,105 +219,85 @@ __global__ void simpo_scalar_kernel(const float* __restrict__ seq_logps, const f
   }
 }
 
-// per-row coefficient c_row of  dlogits = c_row * (onehot - softmax):
-//   c_row = grad_scale * ( grad_seq[s] * (average ? 1/n_s : 1)  +  [s < num_sft_seqs] * sft_coef )
-__global__ void row_coef_kernel(const float* __restrict__ grad_seq, const int64_t* __restrict__ seq_off, int average,
-                                const float* __restrict__ grad_scale, const float* __restrict__ sft_coef,
-                                int num_sft_seqs, float* __restrict__ row_coef) {
+// per-row weight of the backward GEMM pair.  With the forward's spill g (EpiLogitsExp + target_fixup_kernel)
+//   dlogits[r, :] = c_r (onehot - softmax) = w_r * g[r, :],      w_r = -c_r * exp(ref_r - lse_r)
+//   c_r = grad_scale * ( grad_seq[s] * (average ? 1/n_s : 1)  +  [s < num_sft_seqs] * sft_coef )
+// n_s counts the valid labels of sequence s; a row with an invalid label carries no gradient (w_r = 0).
+__global__ void row_weight_kernel(const float* __restrict__ grad_seq, const int64_t* __restrict__ seq_off,
+                                  const int64_t* __restrict__ labels, int vocab, int average,
+                                  const float* __restrict__ grad_scale, const float* __restrict__ sft_coef,
+                                  int num_sft_seqs, const float* __restrict__ row_lse, const float* __restrict__ row_ref,
+                                  float* __restrict__ row_w) {
+  __shared__ float red[128];
   const int s = blockIdx.x;
   const int64_t lo = seq_off[s], hi = seq_off[s + 1];
+  float n = 0.0f;
+  for (int64_t r = lo + threadIdx.x; r < hi; r += 128) {
+    const int64_t lab = labels[r];
+    n += (lab >= 0 && lab < vocab) ? 1.0f : 0.0f;
+  }
+  n = block_sum<128>(n, red);
   const float gs = (grad_scale != nullptr) ? *grad_scale : 1.0f;
   float c = grad_seq[s];
-  if (average) c /= static_cast<float>(hi - lo);
+  if (average) c /= n;
   if (sft_coef != nullptr && s < num_sft_seqs) c += *sft_coef;
   c *= gs;
-  for (int64_t r = lo + threadIdx.x; r < hi; r += blockDim.x) row_coef[r] = c;
-}
-
-// ---------------------------------------------------------------------------
-// softmax-minus-onehot producer (in place on the bf16 logits spill) + db2 column sums.
-//   dlogits[r, v] = c_r * ([v == label_r] - exp(logit[r, v] - lse_r))
-// Block = 128 threads x 8 columns (16-byte vectors) = 1024 columns, looping over ROWS_PER_BLOCK rows.
-// ---------------------------------------------------------------------------
-constexpr int DL_ROWS_PER_BLOCK = 256;
-
-__device__ __forceinline__ float dl_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-constexpr int DL_UNROLL = 4;  // rows in flight per thread: one 16-byte load each (memory-level parallelism)
-
-__global__ void __launch_bounds__(128)
-dlogits_kernel(__nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
-               const float* __restrict__ row_lse, const float* __restrict__ row_coef, int rows, int vocab,
-               float* __restrict__ db2) {
-  const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (col >= vocab) return;
-  const int r0 = blockIdx.y * DL_ROWS_PER_BLOCK;
-  const int r1 = min(rows, r0 + DL_ROWS_PER_BLOCK);
-  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  constexpr float LOG2E = 1.4426950408889634f;
-  for (int rb = r0; rb < r1; rb += DL_UNROLL) {
-    uint4 u[DL_UNROLL];
-    float lse[DL_UNROLL], c[DL_UNROLL];
-    int rel[DL_UNROLL];
-#pragma unroll
-    for (int i = 0; i < DL_UNROLL; ++i) {
-      const int r = min(rb + i, r1 - 1);  // clamped rows are loaded but not stored
-      u[i] = *reinterpret_cast<const uint4*>(logits + static_cast<int64_t>(r) * ld + col);
-      lse[i] = __ldg(row_lse + r) * LOG2E;
-      c[i] = __ldg(row_coef + r);
-      rel[i] = static_cast<int>(__ldg(labels + r)) - col;
-    }
-#pragma unroll
-    for (int i = 0; i < DL_UNROLL; ++i) {
-      if (rb + i >= r1) break;
-      const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
-      uint32_t o[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float l0 = __uint_as_float(w[k] << 16), l1 = __uint_as_float(w[k] & 0xFFFF0000u);
-        float d0 = -dl_ex2(fmaf(l0, LOG2E, -lse[i]));
-        float d1 = -dl_ex2(fmaf(l1, LOG2E, -lse[i]));
-        if (rel[i] == 2 * k) d0 += 1.0f;
-        if (rel[i] == 2 * k + 1) d1 += 1.0f;
-        d0 = bf16_round(c[i] * d0);
-        d1 = bf16_round(c[i] * d1);
-        cs[2 * k] += d0;
-        cs[2 * k + 1] += d1;
-        o[k] = pack_bf16x2(d0, d1);
-      }
-      *reinterpret_cast<uint4*>(logits + static_cast<int64_t>(rb + i) * ld + col) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-  }
-  if (db2 != nullptr) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(db2 + col + k, cs[k]);
+  for (int64_t r = lo + threadIdx.x; r < hi; r += 128) {
+    const int64_t lab = labels[r];
+    row_w[r] = (lab >= 0 && lab < vocab) ? -c * expf(row_ref[r] - row_lse[r]) : 0.0f;
   }
 }
 
-// column sums of a bf16 [rows, cols] matrix into fp32 (bias gradient db1 = sum_rows dpre)
+// ---------------------------------------------------------------------------
+// Bias gradients: (row-weighted) column sums of a bf16 [rows, cols] matrix, in two fixed-order stages so the result
+// is bit-reproducible (no atomics):
+//   db2[v] = scale * sum_r w_r g[r, v]      db1[e] = scale * sum_r dpre[r, e]
+// stage 1: block = 128 threads x 8 columns (16-byte loads) over CS_ROWS_PER_BLOCK rows -> partial[row block][col];
+// stage 2: one thread per column adds the row-block partials in order.  HBM-bound: the matrix is read once.
+// ---------------------------------------------------------------------------
+constexpr int CS_ROWS_PER_BLOCK = 512;
+constexpr int CS_UNROLL = 4;  // rows in flight per thread: one 16-byte load each (memory-level parallelism)
+
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(128)
-colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, int cols, float* __restrict__ out) {
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, int cols,
+                      const float* __restrict__ row_w, float* __restrict__ partial) {
   const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (col >= cols) return;
-  const int r0 = blockIdx.y * DL_ROWS_PER_BLOCK;
-  const int r1 = min(rows, r0 + DL_ROWS_PER_BLOCK);
+  const int r0 = blockIdx.y * CS_ROWS_PER_BLOCK;
+  const int r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = r0; r < r1; ++r) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ld + col));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int rb = r0; rb < r1; rb += CS_UNROLL) {
+    uint4 u[CS_UNROLL];
+    float w[CS_UNROLL];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-      cs[2 * k] += __low2float(p);
-      cs[2 * k + 1] += __high2float(p);
+    for (int i = 0; i < CS_UNROLL; ++i) {
+      const int r = min(rb + i, r1 - 1);  // clamped rows are loaded but carry weight 0
+      u[i] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ld + col));
+      w[i] = (rb + i < r1) ? (WEIGHTED ? __ldg(row_w + r) : 1.0f) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < CS_UNROLL; ++i) {
+      const uint32_t q[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cs[2 * k] = fmaf(w[i], __uint_as_float(q[k] << 16), cs[2 * k]);
+        cs[2 * k + 1] = fmaf(w[i], __uint_as_float(q[k] & 0xFFFF0000u), cs[2 * k + 1]);
+      }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) atomicAdd(out + col + k, cs[k]);
+  float4* dst = reinterpret_cast<float4*>(partial + static_cast<int64_t>(blockIdx.y) * cols + col);
+  dst[0] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+  dst[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int row_blocks, int cols, float scale,
+                                    float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.0f;
+  for (int b = 0; b < row_blocks; ++b) s += partial[static_cast<int64_t>(b) * cols + c];
+  out[c] = s * scale;
 }
 
 // ---------------------------------------------------------------------------

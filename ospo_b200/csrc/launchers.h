@@ -45,22 +45,28 @@ void set_trace_merged(unsigned long long* dev_ptr);
 int launch_gemm1_bias_gelu(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w1, const float* b1,
                            __nv_bfloat16* pre /*nullable*/, __nv_bfloat16* act, int rows, int H, int E,
                            const XLayout& xl = XLayout());
-// logits = bf16(act W2^T + b2) (+ LSE partials, target gather);  act [rows,E], w2 [V,E]
-int launch_gemm2_logits_lse(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
-                            __nv_bfloat16* logits /*nullable*/, const int64_t* labels, float2* part,
-                            float* rowsum_part /*nullable*/, float* tgt, int rows, int E, int V);
+// forward GEMM2 with the softmax numerator fused in: l = bf16(act W2^T + b2), e = exp(l - row_ref) spilled as bf16
+// (+ per sub-tile (max l, sum e) partials, target gather, logits row sums);  act [rows,E], w2 [V,E].
+// row_ref null = 0; blk_mask non-null = repair pass over the flagged M-blocks only (gemm2_tile_m rows each).
+int launch_gemm2_logits_exp(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
+                            __nv_bfloat16* espill /*nullable*/, const int64_t* labels, float2* part,
+                            float* rowsum_part /*nullable*/, float* tgt, const float* row_ref /*nullable*/,
+                            const uint8_t* blk_mask /*nullable*/, int rows, int E, int V);
+int gemm2_tile_m(int cta_group);
 int gemm2_num_n_tiles(int V);
 // plain logits = bf16(act W2^T + b2)
 int launch_gemm2_logits(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                         __nv_bfloat16* logits, int64_t ld, int rows, int E, int V);
 
 // ---- backward (gemm_bwd.cu) ----
-// dpre = bf16( bf16(dlogits W2) * gelu'(pre) );  dlogits [rows,V], w2 [V,E]
-int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* dlogits, const __nv_bfloat16* w2,
-                         const __nv_bfloat16* pre, __nv_bfloat16* dpre, int rows, int E, int V);
-// dW[out_dim, in_dim] (fp32) = dY^T X;  dY [rows,out_dim], X [rows,in_dim]
+// dpre = bf16( bf16(row_w * (g W2)) * gelu'(pre) ), act_w = bf16(row_w * gelu(pre));  g [rows,V] (the forward's
+// spill), w2 [V,E];  act_w nullable (head frozen)
+int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* g, const __nv_bfloat16* w2, const __nv_bfloat16* pre,
+                         const float* row_w, __nv_bfloat16* dpre, __nv_bfloat16* act_w /*nullable*/, int rows, int E,
+                         int V);
+// dW[out_dim, in_dim] (fp32) = scale * dY^T X;  dY [rows,out_dim], X [rows,in_dim]  (scale 0 = 1)
 int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw, int rows, int out_dim,
-                 int in_dim, const XLayout& xl = XLayout());
+                 int in_dim, float scale = 0.0f, const XLayout& xl = XLayout());
 // dX[rows, in_dim] (bf16) = dY W;  dY [rows,out_dim], W [out_dim,in_dim]
 int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx, int rows,
                  int out_dim, int in_dim, const XLayout& xl = XLayout());

@@ -47,19 +47,23 @@ def _avg_op(group):
     return dist.ReduceOp.SUM
 
 
-def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
-    """in-place average of the flat gradient buffer over the data-parallel group (no-op for world size 1)"""
+def allreduce_mean_(flat: torch.Tensor, group=None, prescaled: bool = False) -> torch.Tensor:
+    """in-place average of the flat gradient buffer over the data-parallel group (no-op for world size 1).
+    ``prescaled``: every rank's buffer already carries the 1 / world factor (the weight-gradient kernels apply it as
+    they store, ``ospo_simpo_args.wgrad_scale``), so a plain sum is the average and no extra pass over the 336 MB
+    buffer is needed."""
     world = _world(group)
     if world == 1:
         return flat
-    op = _avg_op(group)
+    op = dist.ReduceOp.SUM if prescaled else _avg_op(group)
     dist.all_reduce(flat, op=op, group=group)
-    if op == dist.ReduceOp.SUM:
+    if op == dist.ReduceOp.SUM and not prescaled:
         flat.mul_(1.0 / world)
     return flat
 
 
-def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, run_stage2, run_stage3=None):
+def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, run_stage2, run_stage3=None,
+                           prescaled: bool = False):
     """Backward in stages with the exchange overlapped: ``run_stage1()`` fills ``flat[:split]`` (dW2, 80 %
     of the buffer) and its all-reduce starts asynchronously; ``run_stage2()`` fills the rest (db1, dW1; db2 is there
     already) and that all-reduce starts; ``run_stage3()`` (dX) runs beside it.  Returns the last stage's result.
@@ -69,7 +73,7 @@ def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, ru
     if world == 1:
         out = run_stage2()
         return run_stage3() if run_stage3 is not None else out
-    op = _avg_op(group)
+    op = dist.ReduceOp.SUM if prescaled else _avg_op(group)
     head, tail = flat[:split], flat[split:]
     w1 = dist.all_reduce(head, op=op, group=group, async_op=True)
     out = run_stage2()
@@ -78,7 +82,7 @@ def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, ru
         out = run_stage3()
     w1.wait()
     w2.wait()
-    if op == dist.ReduceOp.SUM:
+    if op == dist.ReduceOp.SUM and not prescaled:
         flat.mul_(1.0 / world)
     return out
 

@@ -84,16 +84,17 @@ class _SimpoFn(torch.autograd.Function):
         xb = x_rows.detach().to(torch.bfloat16).contiguous()
         need_bwd = any(ctx.needs_input_grad[:5])   # grad mode is off inside forward(); ask autograd instead
         beta, gbr, ls, sftw, lt = hp
-        (scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, grad_seq, pre, act, logits) = ops.simpo_fwd_impl(
-            xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, beta, gbr, ls, sftw, lt, need_bwd, seg[0], seg[1])
+        (scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, row_ref, grad_seq, pre, act, gspill) = \
+            ops.simpo_fwd_impl(xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, beta, gbr, ls, sftw, lt, need_bwd, seg[0],
+                               seg[1])
         ctx.head, ctx.hp, ctx.group, ctx.seg = head, hp, group, seg
         ctx.x_dtype = x_rows.dtype
         ctx.need_dx = ctx.needs_input_grad[0]
         ctx.need_dw = any(ctx.needs_input_grad[1:5])
         ctx.param_dtypes = (W1.dtype, B1.dtype, W2.dtype, B2.dtype)
         if need_bwd:
-            ctx.save_for_backward(xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, scalars, pre, act, logits, row_lse,
-                                  grad_seq)
+            ctx.save_for_backward(xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, scalars, pre, act, gspill, row_lse,
+                                  row_ref, grad_seq)
         loss = scalars[_abi.SC_LOSS].clone()
         ctx.mark_non_differentiable(scalars, seq_logps, losses, crew, rrew, row_logps)
         ctx.set_materialize_grads(False)  # no zero tensors for the six outputs that carry no gradient
@@ -103,16 +104,17 @@ class _SimpoFn(torch.autograd.Function):
     def backward(ctx, grad_loss, *_):
         if grad_loss is None:
             return (None,) * 11
-        xb, w1, b1, w2, b2, targets, seq_off, scalars, pre, act, logits, row_lse, grad_seq = ctx.saved_tensors
+        xb, w1, b1, w2, b2, targets, seq_off, scalars, pre, act, gspill, row_lse, row_ref, grad_seq = ctx.saved_tensors
         head = ctx.head
         H, E, V = head.n_embed, head.image_token_embed, head.image_token_size
         flat = head._flat_grad_buffer() if ctx.need_dw else torch.empty(0, dtype=torch.float32, device=xb.device)
         gs = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        wscale = 1.0 / _dist._world(ctx.group) if ctx.group is not None else 1.0
 
         def bwd(stage, reserve_sms, ws):
-            return ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, True, ctx.hp[3], scalars, pre, act, logits,
-                                     row_lse, grad_seq, gs, ctx.need_dx, flat, True, ctx.seg[0], ctx.seg[1], stage,
-                                     reserve_sms, ws)
+            return ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, True, ctx.hp[3], scalars, pre, act, gspill,
+                                     row_lse, row_ref, grad_seq, gs, ctx.need_dx, flat, True, ctx.seg[0], ctx.seg[1],
+                                     stage, reserve_sms, ws, None, wscale)
 
         dx = head._backward_and_sync(bwd, flat, ctx.group, ctx.need_dw, xb, seq_off, ctx.seg)
         gW1 = gB1 = gW2 = gB2 = None
@@ -134,7 +136,7 @@ class _LogpsFn(torch.autograd.Function):
         p = head._kernel_params()
         xb = x_rows.detach().to(torch.bfloat16).contiguous()
         need_bwd = any(ctx.needs_input_grad[:5])   # grad mode is off inside forward(); ask autograd instead
-        seq_logps, row_logps, row_lse, pre, act, logits = ops.logps_fwd_impl(
+        seq_logps, row_logps, row_lse, row_ref, pre, act, gspill = ops.logps_fwd_impl(
             xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, average, need_bwd, seg[0], seg[1])
         ctx.head, ctx.average, ctx.group, ctx.seg = head, average, group, seg
         ctx.x_dtype = x_rows.dtype
@@ -142,7 +144,7 @@ class _LogpsFn(torch.autograd.Function):
         ctx.need_dw = any(ctx.needs_input_grad[1:5])
         ctx.param_dtypes = (W1.dtype, B1.dtype, W2.dtype, B2.dtype)
         if need_bwd:
-            ctx.save_for_backward(xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, pre, act, logits, row_lse)
+            ctx.save_for_backward(xb, p.w1, p.b1, p.w2, p.b2, targets, seq_off, pre, act, gspill, row_lse, row_ref)
         ctx.mark_non_differentiable(row_logps)
         ctx.set_materialize_grads(False)
         return seq_logps, row_logps
@@ -151,7 +153,7 @@ class _LogpsFn(torch.autograd.Function):
     def backward(ctx, grad_seq, _):
         if grad_seq is None:
             return (None,) * 11
-        xb, w1, b1, w2, b2, targets, seq_off, pre, act, logits, row_lse = ctx.saved_tensors
+        xb, w1, b1, w2, b2, targets, seq_off, pre, act, gspill, row_lse, row_ref = ctx.saved_tensors
         head = ctx.head
         H, E, V = head.n_embed, head.image_token_embed, head.image_token_size
         dev = xb.device
@@ -159,11 +161,12 @@ class _LogpsFn(torch.autograd.Function):
         one = torch.ones(1, dtype=torch.float32, device=dev)
         none = torch.empty(0, dtype=torch.float32, device=dev)
         gseq = grad_seq.detach().to(torch.float32).contiguous()
+        wscale = 1.0 / _dist._world(ctx.group) if ctx.group is not None else 1.0
 
         def bwd(stage, reserve_sms, ws):
-            return ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, ctx.average, 0.0, none, pre, act, logits,
-                                     row_lse, gseq, one, ctx.need_dx, flat, False, ctx.seg[0], ctx.seg[1], stage,
-                                     reserve_sms, ws)
+            return ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, ctx.average, 0.0, none, pre, act, gspill,
+                                     row_lse, row_ref, gseq, one, ctx.need_dx, flat, False, ctx.seg[0], ctx.seg[1],
+                                     stage, reserve_sms, ws, None, wscale)
 
         dx = head._backward_and_sync(bwd, flat, ctx.group, ctx.need_dw, xb, seq_off, ctx.seg)
         gW1 = gB1 = gW2 = gB2 = None
@@ -243,8 +246,8 @@ class FusedGenHead(torch.nn.Module):
         return self._flat
 
     def _backward_and_sync(self, bwd, flat: torch.Tensor, group, need_dw: bool, xb, seq_off, seg):
-        """run the fused backward (``bwd(stage, reserve_sms, workspace) -> dx``) and average the flat gradient over the
-        data-parallel group.  With more than one rank the backward is staged: the all-reduce of dW2 (80 % of the
+        """run the fused backward (``bwd(stage, reserve_sms, workspace) -> dx``) and sum the flat gradient over the
+        data-parallel group (the kernels already stored it times 1 / world_size, so the sum is DDP's average).  With more than one rank the backward is staged: the all-reduce of dW2 (80 % of the
         bytes) runs on NCCL's stream while db1 / dW1 / dX are computed (OSPO_HEAD_OVERLAP=3 also runs dX beside the
         all-reduce of the remainder -- measured 0.2-0.6 ms slower at N = 2; OSPO_HEAD_OVERLAP=0 restores the single
         all-reduce after the backward; OSPO_HEAD_OVERLAP_SMS > 0 leaves that many SMs free for the collective --
@@ -261,16 +264,18 @@ class FusedGenHead(torch.nn.Module):
         reserve = int(os.environ.get("OSPO_HEAD_OVERLAP_SMS", "0"))
         if os.environ.get("OSPO_HEAD_OVERLAP", "1") == "3":      # three parts: dX beside the second all-reduce
             return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(2, reserve, ws),
-                                                lambda: bwd(4, reserve, ws))
-        return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(6, reserve, ws))
+                                                lambda: bwd(4, reserve, ws), prescaled=True)
+        return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(6, reserve, ws),
+                                            prescaled=True)
 
     @staticmethod
     def _sync_flat_grads(flat: torch.Tensor, group) -> None:
         """DDP semantics (ospo/utils/train.py:26-28): average the head-weight gradients over the data-parallel
-        ranks -- one NCCL all-reduce over the contiguous fp32 buffer dW2|dW1|db2|db1."""
+        ranks -- one NCCL all-reduce (sum; the 1 / world_size factor is already in the buffer) over the contiguous
+        fp32 buffer dW2|dW1|db2|db1."""
         if group is None:
             return
-        allreduce_mean_(flat, group)
+        allreduce_mean_(flat, group, prescaled=True)
 
     # ---- reference-compatible call: logits ---------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -96,7 +96,7 @@ def _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, hp, outs, saved, bw
     a.average_log_prob = int(average)
     a.beta, a.gamma_beta_ratio, a.label_smoothing, a.sft_weight, a.loss_type = hp
     (a.row_logps, a.seq_logps, a.losses, a.chosen_rewards, a.rejected_rewards, a.scalars) = [_ptr(t) for t in outs]
-    (a.pre, a.act, a.logits, a.row_lse, a.grad_seq) = [_ptr(t) for t in saved]
+    (a.pre, a.act, a.logits, a.row_lse, a.row_ref, a.grad_seq) = [_ptr(t) for t in saved]
     (a.grad_loss, a.dx, a.flat_grads) = [_ptr(t) for t in bwd]
     a.workspace = ws.data_ptr()
     a.workspace_bytes = ws.numel()
@@ -114,9 +114,10 @@ def _check_rows(x: Tensor, labels: Tensor, seq_off: Tensor, seg_rows: int = 0) -
 
 def logps_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
               average: bool, save_for_backward: bool, seg_rows: int = 0, seg_off: int = 0) -> List[Tensor]:
-    """-> [seq_logps[S], row_logps[rows], row_lse[rows], pre, act, logits]  (train.py:357 + 375-396)
+    """-> [seq_logps[S], row_logps[rows], row_lse[rows], row_ref[rows], pre, act, gspill]  (train.py:357 + 375-396)
     seg_rows > 0: x is the [S, pitch, H] hidden-state tensor and rows [seg_off, seg_off + seg_rows) of every
-    sequence are the head's rows (no gather copy)."""
+    sequence are the head's rows (no gather copy).  ``gspill`` [rows, V] bf16 is the forward's only logits-sized
+    product: the unscaled softmax-minus-onehot numerator the backward GEMMs read (never modified afterwards)."""
     _check_rows(x, labels, seq_off, seg_rows)
     rows, H = _x_dims(x, seg_rows)
     seg = (seg_rows, x.shape[1], seg_off) if seg_rows else (0, 0, 0)
@@ -125,6 +126,7 @@ def logps_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
     dev = x.device
     f32 = dict(dtype=torch.float32, device=dev)
     seq_logps, row_logps, row_lse = torch.empty(S, **f32), torch.empty(rows, **f32), torch.empty(rows, **f32)
+    row_ref = torch.empty(rows, **f32)
     act = torch.empty(rows, E, dtype=torch.bfloat16, device=dev)
     if save_for_backward:
         pre = torch.empty(rows, E, dtype=torch.bfloat16, device=dev)
@@ -133,13 +135,13 @@ def logps_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
         pre = logits = None
     ws = _workspace(rows, H, E, V, S, dev)
     a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, (1.0, 0.0, 0.0, 0.0, 0),
-                    (row_logps, seq_logps, None, None, None, None), (pre, act, logits, row_lse, None),
+                    (row_logps, seq_logps, None, None, None, None), (pre, act, logits, row_lse, row_ref, None),
                     (None, None, None), ws, seg)
     _abi.check(_abi.load().ospo_head_logps_fwd(C.byref(a), _stream()), "ospo_head_logps_fwd")
     def empty():
         return torch.empty(0, dtype=torch.bfloat16, device=dev)
 
-    return [seq_logps, row_logps, row_lse, pre if pre is not None else empty(), act,
+    return [seq_logps, row_logps, row_lse, row_ref, pre if pre is not None else empty(), act,
             logits if logits is not None else empty()]
 
 
@@ -147,7 +149,7 @@ def simpo_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
               beta: float, gamma_beta_ratio: float, label_smoothing: float, sft_weight: float, loss_type: int,
               save_for_backward: bool, seg_rows: int = 0, seg_off: int = 0) -> List[Tensor]:
     """-> [scalars[16], seq_logps[S], losses[B], chosen_rewards[B], rejected_rewards[B], row_logps[rows],
-           row_lse[rows], grad_seq[S], pre, act, logits]      (train.py:345-372, 317-342, 399-445)"""
+           row_lse[rows], row_ref[rows], grad_seq[S], pre, act, gspill]      (train.py:345-372, 317-342, 399-445)"""
     _check_rows(x, labels, seq_off, seg_rows)
     rows, H = _x_dims(x, seg_rows)
     seg = (seg_rows, x.shape[1], seg_off) if seg_rows else (0, 0, 0)
@@ -161,6 +163,7 @@ def simpo_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
     seq_logps, losses = torch.empty(S, **f32), torch.empty(B, **f32)
     crew, rrew = torch.empty(B, **f32), torch.empty(B, **f32)
     row_logps, row_lse, grad_seq = torch.empty(rows, **f32), torch.empty(rows, **f32), torch.empty(S, **f32)
+    row_ref = torch.empty(rows, **f32)
     act = torch.empty(rows, E, dtype=torch.bfloat16, device=dev)
     if save_for_backward:
         pre = torch.empty(rows, E, dtype=torch.bfloat16, device=dev)
@@ -170,25 +173,25 @@ def simpo_fwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, la
     ws = _workspace(rows, H, E, V, S, dev)
     a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, True,
                     (beta, gamma_beta_ratio, label_smoothing, sft_weight, loss_type),
-                    (row_logps, seq_logps, losses, crew, rrew, scalars), (pre, act, logits, row_lse, grad_seq),
+                    (row_logps, seq_logps, losses, crew, rrew, scalars), (pre, act, logits, row_lse, row_ref, grad_seq),
                     (None, None, None), ws, seg)
     _abi.check(_abi.load().ospo_head_simpo_fwd(C.byref(a), _stream()), "ospo_head_simpo_fwd")
     def empty():
         return torch.empty(0, dtype=torch.bfloat16, device=dev)
 
-    return [scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, grad_seq,
+    return [scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, row_ref, grad_seq,
             pre if pre is not None else empty(), act, logits if logits is not None else empty()]
 
 
 def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
              average: bool, sft_weight: float, scalars: Tensor, pre: Tensor, act: Tensor, logits: Tensor,
-             row_lse: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool, flat_grads: Tensor,
+             row_lse: Tensor, row_ref: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool, flat_grads: Tensor,
              simpo: bool, seg_rows: int = 0, seg_off: int = 0, stage: int = 0, reserve_sms: int = 0,
-             ws: Optional[Tensor] = None, dx_out: Optional[Tensor] = None) -> Tensor:
-    """softmax-minus-onehot producer + the dgrad / wgrad GEMM pairs.
+             ws: Optional[Tensor] = None, dx_out: Optional[Tensor] = None, wgrad_scale: float = 1.0) -> Tensor:
+    """the dgrad / wgrad GEMM pairs on the forward's softmax-minus-onehot spill.
     ``stage`` is a bit mask (0 = everything): 1 = up to dW2, 2 = db1 + dW1, 4 = dX, so the caller can overlap the
     all-reduces with the later parts (pass the same ``ws`` to every call; dx is produced by part 4).
-    `logits` is overwritten with dlogits; `flat_grads` (numel 0 = head frozen) receives dW2|dW1|db2|db1.
+    `logits` (the spill) is only read; `flat_grads` (numel 0 = head frozen) receives wgrad_scale * (dW2|dW1|db2|db1).
     Returns dx bf16 with the shape of x (numel 0 if not requested); with a row-segmented x the rows outside the
     span are zero (train.py: masked positions carry no gradient)."""
     _check_rows(x, labels, seq_off, seg_rows)
@@ -212,8 +215,9 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
         ws = _workspace(rows, H, E, V, S, dev)
     a = _simpo_args(x, w1, b1, w2, b2, labels, seq_off, average, (1.0, 0.0, 0.0, sft_weight, 0),
                     (None, None, None, None, None, scalars if scalars.numel() else None),
-                    (pre, act, logits, row_lse, grad_seq), (grad_scale, dx, fg), ws, seg)
+                    (pre, act, logits, row_lse, row_ref, grad_seq), (grad_scale, dx, fg), ws, seg)
     a.bwd_stage, a.reserve_sms = int(stage), int(reserve_sms)
+    a.wgrad_scale = float(wgrad_scale)
     lib = _abi.load()
     if simpo:
         _abi.check(lib.ospo_head_simpo_bwd(C.byref(a), _stream()), "ospo_head_simpo_bwd")
@@ -394,13 +398,13 @@ logps_fwd = torch.library.custom_op("ospo_head::logps_fwd", logps_fwd_impl, muta
 simpo_fwd = torch.library.custom_op("ospo_head::simpo_fwd", simpo_fwd_impl, mutates_args=(), device_types="cuda")
 def _head_bwd_op(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, labels: Tensor, seq_off: Tensor,
                  average: bool, sft_weight: float, scalars: Tensor, pre: Tensor, act: Tensor, logits: Tensor,
-                 row_lse: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool, flat_grads: Tensor,
-                 simpo: bool, seg_rows: int = 0, seg_off: int = 0) -> Tensor:
+                 row_lse: Tensor, row_ref: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool,
+                 flat_grads: Tensor, simpo: bool, seg_rows: int = 0, seg_off: int = 0) -> Tensor:
     return head_bwd_impl(x, w1, b1, w2, b2, labels, seq_off, average, sft_weight, scalars, pre, act, logits, row_lse,
-                         grad_seq, grad_scale, need_dx, flat_grads, simpo, seg_rows, seg_off)
+                         row_ref, grad_seq, grad_scale, need_dx, flat_grads, simpo, seg_rows, seg_off)
 
 
-head_bwd = torch.library.custom_op("ospo_head::head_bwd", _head_bwd_op, mutates_args=("logits", "flat_grads"),
+head_bwd = torch.library.custom_op("ospo_head::head_bwd", _head_bwd_op, mutates_args=("flat_grads",),
                                    device_types="cuda")
 def _cfg_sample_op(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, cfg_weight: float, temperature: float,
                    uniforms: Tensor, greedy: bool, merge_mode: int, want_logits: bool = False) -> List[Tensor]:

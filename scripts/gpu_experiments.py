@@ -47,9 +47,9 @@ def fwd_bwd(save=True, need_dx=True, need_dw=True, iters=3):
             _abi.profile_read()
         r = ops.simpo_fwd_impl(x, p.w1, p.b1, p.w2, p.b2, labels, seq_off, 10.0, 0.5, 0.0, 0.0, 0, save)
         if save:
-            scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, grad_seq, pre, act, logits = r
+            scalars, seq_logps, losses, crew, rrew, row_logps, row_lse, row_ref, grad_seq, pre, act, logits = r
             ops.head_bwd_impl(x, p.w1, p.b1, p.w2, p.b2, labels, seq_off, True, 0.0, scalars, pre, act, logits, row_lse,
-                              grad_seq, one, need_dx, flat, True)
+                              row_ref, grad_seq, one, need_dx, flat, True)
     torch.cuda.synchronize()
     prof = _abi.profile_read()
     _abi.profile_enable(False)

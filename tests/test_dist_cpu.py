@@ -36,7 +36,11 @@ def _worker(rank, world, port, out_dir):
     # pack exactly like the library's flat buffer: dW2 | dW1 | db2 | db1
     flat = torch.cat([out["dW2"].reshape(-1), out["dW1"].reshape(-1), out["db2"], out["db1"]]).contiguous()
     assert flat.numel() == ops.flat_grad_numel(H, E, V)
+    # the kernels store the weight gradients already times 1 / world (ospo_simpo_args.wgrad_scale): a plain sum then
+    pre = flat / world
+    allreduce_mean_(pre, dist.group.WORLD, prescaled=True)
     allreduce_mean_(flat, dist.group.WORLD)
+    torch.testing.assert_close(pre, flat, rtol=1e-6, atol=1e-9)
     loss = out["loss"].detach().clone()
     dist.all_reduce(loss)
     if rank == 0:

@@ -431,6 +431,140 @@ def test_simpo_full_size_vs_fp32_gpu_restatement(B):
     print(f"B={B}: rel-Frobenius gradient errors {errs}")
 
 
+
+def _reference_from_own_logits(fh, hidden, labels, T, L, hp):
+    """SimPO step in fp32 torch ops on the device, fed with the bf16 logits / activations the library itself
+    produces (FusedGenHead.forward runs the same GEMM configuration as the fused path, so the logits are the ones the
+    fused epilogue saw).  Removes the bf16 logit rounding (0.25 - 0.5 absolute beyond |l| = 32) from the comparison,
+    which is what the tests of the out-of-window repair pass need."""
+    S = hidden.shape[0]
+    B = S // 2
+    with torch.no_grad():
+        x = hidden[:, L - 1:L - 1 + T, :].reshape(S * T, -1)
+        logits = fh(x).float()
+        W1, b1 = fh.output_mlp_projector.weight.float(), fh.output_mlp_projector.bias.float()
+        pre = (x.float() @ W1.t() + b1).to(torch.bfloat16).float()
+        act = torch.nn.functional.gelu(pre).to(torch.bfloat16).float()
+    tgt = labels[:, L:L + T].reshape(-1)
+    valid = (tgt >= 0)
+    lsm = torch.log_softmax(logits, -1)
+    row_logp = torch.where(valid, lsm.gather(1, tgt.clamp(min=0)[:, None]).squeeze(1), torch.zeros_like(lsm[:, 0]))
+    n = valid.view(S, T).sum(-1).float()
+    seq = (row_logp.view(S, T).sum(-1) / n).detach().requires_grad_(True)
+    losses, _, _ = O.simpo_loss(seq[:B], seq[B:], hp["beta"], hp["gamma_beta_ratio"], hp.get("label_smoothing", 0.0),
+                                hp.get("loss_type", "sigmoid"))
+    loss = losses.mean()
+    (gseq,) = torch.autograd.grad(loss, seq)
+    c = (gseq / n).repeat_interleave(T) * valid.float()
+    dlog = -torch.softmax(logits, -1) * c[:, None]
+    dlog[torch.arange(S * T, device=dlog.device), tgt.clamp(min=0)] += c
+    W2 = fh.vision_head.weight.float()
+    return {"loss": loss.detach(), "seq": seq.detach(), "row_logp": row_logp, "dW2": dlog.t() @ act,
+            "db2": dlog.sum(0), "dact": dlog @ W2}
+
+
+@pytest.mark.parametrize("case", ["shift_up", "shift_down", "some_rows_hot", "peaked"])
+def test_spill_repair_pass_outside_exponent_window(case):
+    """The forward spills e = exp(logit - ref) with ref = 0; rows whose maximum logit leaves [-50, 60] are recomputed
+    against their own maximum by the (normally empty) repair launch.  Force that path: logits shifted by +-100
+    through b2 (softmax is shift-invariant), a few rows scaled far out of the window (only their 256-row blocks are
+    repaired) and a sharply peaked distribution.  Reference: fp32 torch ops on the library's own bf16 logits."""
+    dev = _cuda()
+    H, E, V, B, T, L = 256, 320, 2048, 5, 128, 2
+    hp = dict(beta=2.0, gamma_beta_ratio=0.25, label_smoothing=0.0, loss_type="sigmoid")
+    gain = 400.0 if case == "peaked" else 3.0
+    head = O.make_head(H, E, V, seed=300, w2_gain=gain)
+    with torch.no_grad():
+        if case == "shift_up":
+            head.vision_head.bias.add_(100.0)
+        elif case == "shift_down":
+            head.vision_head.bias.sub_(100.0)
+    head_b = head.to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=301, dtype=torch.bfloat16)
+    hidden, labels = torch.cat([hc, hr]).to(dev), torch.cat([lc, lr]).to(dev)
+    if case == "some_rows_hot":
+        with torch.no_grad():
+            head_b.vision_head.weight.mul_(15.0)          # logits within about +-40: inside the window
+            hidden[3, L - 1 + 7] *= 6.0                     # ... except two rows (max logit beyond 60)
+            hidden[8, L - 1 + 100] *= 6.0
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+    x = hidden.clone().requires_grad_(True)
+    out = fh.simpo(x, labels, image_span=(L - 1, L - 1 + T), **hp)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    ref = _reference_from_own_logits(fh, hidden, labels, T, L, hp)
+    got_seq = torch.cat([out.chosen_logps, out.rejected_logps])
+    assert torch.isfinite(got_seq).all() and torch.isfinite(x.grad.float()).all()
+    torch.testing.assert_close(out.per_token_logps, ref["row_logp"], rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(got_seq, ref["seq"], rtol=1e-4, atol=1e-3)
+    assert _rel_fro(fh.vision_head.weight.grad.float(), ref["dW2"]) < 2e-2
+    assert _rel_fro(fh.vision_head.bias.grad.float(), ref["db2"]) < 2e-2
+    # dX through the reference's GELU' and W1 from the reference dact
+    with torch.no_grad():
+        W1 = fh.output_mlp_projector.weight.float()
+        pre = (hidden[:, L - 1:L - 1 + T].reshape(-1, H).float() @ W1.t() + fh.output_mlp_projector.bias.float())
+        pre = pre.to(torch.bfloat16).float()
+        gp = 0.5 * (1 + torch.erf(pre * 0.7071067811865476)) + pre * torch.exp(-0.5 * pre * pre) * 0.3989422804014327
+        dx_ref = (ref["dact"] * gp) @ W1
+    assert _rel_fro(x.grad[:, L - 1:L - 1 + T].reshape(-1, H).float(), dx_ref) < 2e-2
+
+
+def test_ignore_index_inside_image_span_is_masked():
+    """a -100 (or an id >= V) inside the promised image span behaves like a masked position (train.py:387-396): its
+    row carries no log-prob, no gradient and is left out of the per-sequence count -- not uninitialised workspace"""
+    dev = _cuda()
+    H, E, V, B, T, L = 256, 192, 2048, 3, 64, 3
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, loss_type="sigmoid", sft_weight=0.2)
+    head_b = O.make_head(H, E, V, seed=61, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=62, dtype=torch.bfloat16)
+    lc[0, L + 5] = -100
+    lc[2, L + 63] = -100
+    lr[1, L:L + 4] = -100
+    ref = O.simpo_step(head_b, hc, hr, lc, lr, backward=True, **hp)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+    x = torch.cat([hc, hr]).to(dev).requires_grad_(True)
+    out = fh.simpo(x, torch.cat([lc, lr]).to(dev), image_span=(L - 1, L - 1 + T), **hp)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.chosen_logps.cpu().numpy(), ref["chosen_logps"].detach().float().numpy(), rtol=1e-2)
+    np.testing.assert_allclose(out.rejected_logps.cpu().numpy(), ref["rejected_logps"].detach().float().numpy(), rtol=1e-2)
+    np.testing.assert_allclose(float(out.loss.detach()), float(ref["loss"]), rtol=1e-2, atol=2e-2)
+    assert _rel_fro(x.grad.float(), ref["dx"].float()) < 3e-2
+    assert _rel_fro(fh.vision_head.weight.grad.float(), ref["dW2"].float()) < 3e-2
+    assert float(x.grad[0, L - 1 + 5].float().abs().max()) == 0.0          # the masked row gets exactly zero gradient
+    assert float(x.grad[B + 1, L - 1:L + 3].float().abs().max()) == 0.0
+
+
+def test_backward_twice_and_bias_gradients_are_bit_reproducible():
+    """the backward only reads what the forward saved, so backward(retain_graph=True) twice gives the same bits
+    (round 1 overwrote the spill with dlogits in place), and db1 / db2 are summed in a fixed order (no atomics)"""
+    dev = _cuda()
+    H, E, V, B, T, L = 256, 384, 4096, 4, 128, 2
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, loss_type="sigmoid")
+    head_b = O.make_head(H, E, V, seed=71, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=72, dtype=torch.bfloat16)
+    hidden, labels = torch.cat([hc, hr]).to(dev), torch.cat([lc, lr]).to(dev)
+    fh = _fused_from(head_b, dev, dtype=torch.float32)            # fp32 .grad: every bit of the kernels' sums is visible
+    x = hidden.clone().requires_grad_(True)
+    out = fh.simpo(x, labels, image_span=(L - 1, L - 1 + T), **hp)
+    grads = []
+    for i in range(2):
+        fh.zero_grad(set_to_none=True)
+        x.grad = None
+        out.loss.backward(retain_graph=True)
+        torch.cuda.synchronize()
+        grads.append([x.grad.clone()] + [p.grad.clone() for p in fh.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
+    # a fresh forward + backward reproduces the bias gradients bit for bit as well
+    fh.zero_grad(set_to_none=True)
+    x2 = hidden.clone().requires_grad_(True)
+    fh.simpo(x2, labels, image_span=(L - 1, L - 1 + T), **hp).loss.backward()
+    torch.cuda.synchronize()
+    for a, p in zip(grads[0][1:], fh.parameters()):
+        assert torch.equal(a, p.grad)
+
+
 def test_logps_autograd_path_and_ragged_sequences():
     """get_batch_logps replacement with per-sequence different numbers of unmasked tokens + empty head grads."""
     dev = _cuda()
@@ -1208,7 +1342,8 @@ def test_staged_backward_equals_single_call(monkeypatch, parts):
             calls = []
             monkeypatch.setattr(D, "_world", lambda group: 2)
 
-            def fake_staged(flat, split, group, s1, s2, s3=None):
+            def fake_staged(flat, split, group, s1, s2, s3=None, prescaled=False):
+                assert prescaled                  # the kernels store the weight gradients times 1 / world
                 calls.append(split)
                 s1()
                 out = s2()
@@ -1229,8 +1364,10 @@ def test_staged_backward_equals_single_call(monkeypatch, parts):
                 fh.vision_head.bias.grad.clone(), fh.output_mlp_projector.bias.grad.clone())
 
     a, b = run(False), run(True)
-    for ta, tb in zip(a, b):
-        assert torch.equal(ta, tb)
+    assert torch.equal(a[0], b[0])                # dX stays local: never scaled
+    for ta, tb in zip(a[1:], b[1:]):
+        # the pretended world size of 2 is folded into the stored weight gradients: exactly half, bit for bit
+        assert torch.equal((ta.float() * 0.5).to(ta.dtype), tb)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -272,6 +272,10 @@ OSPO_API int ospo_head_set_decode_merged(int merged);
 OSPO_API int ospo_head_set_decode_l2_ahead(int kblocks);
 /* rasterisation group size (M-blocks walked together); pass 0 to query */
 OSPO_API int ospo_head_set_group_m(int group_m);
+/* per training GEMM (kernel: 0 gemm1, 1 gemm2, 2 dact, 3 wgrad W2, 4 wgrad W1, 5 dgrad X): rasterisation group
+   (0 = the global group_m) and the L2 eviction hints of its A / B operand loads (0 normal, 1 evict-first,
+   2 evict-last); a negative argument leaves that setting unchanged */
+OSPO_API int ospo_head_set_kernel_tune(int kernel, int group_m, int a_evict, int b_evict);
 /* Per-kernel timing with CUDA events recorded on the caller's stream around each launch group (off by
    default).  profile_read synchronises on the recorded events and returns, per OSPO_K_* id, the summed
    milliseconds and the number of spans since the previous read. */

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -30,6 +31,13 @@ struct Runtime {
   int decode_cluster = 1;  // GEMM1 k-splits combined in-cluster through DSMEM (0 = HBM partials + finalize kernel)
   int decode_merged = 1;   // GEMM1 + GEMM2 + CFG epilogue as one persistent kernel (0 = two GEMM launches)
   int tile_sync = 1;       // wave lock-step of the persistent training GEMMs (OSPO_HEAD_TILE_SYNC)
+  // per training GEMM (0 gemm1, 1 gemm2, 2 dact, 3 wgrad W2, 4 wgrad W1, 5 dgrad X): rasterisation group (0 = group_m)
+  // and the L2 eviction hints of the A / B operand loads (0 normal, 1 evict-first, 2 evict-last)
+  // Measured per kernel under ncu (profiles/r02_tune_sweep_ncu.csv): groups of 8 M-blocks give every GEMM but gemm2 its
+  // lowest DRAM traffic (dact 12.2 vs 13.8 GB, wgrad W2 11.7 vs 13.0 GB); gemm2 wants 16 (3.9 vs 5.6 GB); eviction
+  // hints of either polarity raise the traffic (a line marked evict-first leaves L2 before the sibling clusters of
+  // the same wave have read it), so they stay off.
+  int tune[6][3] = {{8, 0, 0}, {16, 0, 0}, {8, 0, 0}, {8, 0, 0}, {8, 0, 0}, {8, 0, 0}};
   int decode_l2_ahead = 16;  // merged kernel: W2 k-blocks per CTA requested into L2 while the activation flag is closed
   bool trace_on = false;   // ospo_head_trace installed a timeline buffer
   unsigned long long* trace_buf = nullptr;
@@ -98,6 +106,11 @@ int runtime_init() {
   if (const char* e = getenv("OSPO_HEAD_TILE_SYNC")) g_rt.tile_sync = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_MERGED")) g_rt.decode_merged = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);
+  for (int k = 0; k < 6; ++k) {
+    char name[32];
+    snprintf(name, sizeof(name), "OSPO_HEAD_TUNE_%d", k);
+    if (const char* e = getenv(name)) sscanf(e, "%d,%d,%d", &g_rt.tune[k][0], &g_rt.tune[k][1], &g_rt.tune[k][2]);
+  }
   if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
     const int v = atoi(e);
     if (v > 0) g_rt.group_m = v;
@@ -172,6 +185,15 @@ LaunchCtx make_ctx(cudaStream_t s) {
   return c;
 }
 
+// the launch context of training GEMM k (see Runtime::tune)
+LaunchCtx tuned(const LaunchCtx& c, int k) {
+  LaunchCtx t = c;
+  if (g_rt.tune[k][0] > 0) t.group_m = g_rt.tune[k][0];
+  t.a_evict = g_rt.tune[k][1];
+  t.b_evict = g_rt.tune[k][2];
+  return t;
+}
+
 template <typename Kern, typename... Args>
 cudaError_t launch_plain(Kern kern, dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -225,7 +247,8 @@ struct Workspace {
   float* row_logit_sum;  // [rows]
   float* row_coef;       // [rows] backward: row weights w_r of the GEMM pair
   float* row_max;        // [rows] forward: row maxima of the logits (exponent reference of the repair pass)
-  uint8_t* blk_mask;     // [rows / 128 + 1] forward: GEMM2 M-blocks whose spill must be recomputed (normally none)
+  uint8_t* blk_mask;     // [rows / 128 + 2] forward: GEMM2 M-blocks whose spill must be recomputed (normally none);
+                         // the last byte is the "any block flagged" flag
   float* seq_sum;        // [S]
   float* seq_logit_sum;  // [S]
   float* seq_count;      // [S] valid labels per sequence
@@ -257,7 +280,7 @@ Workspace carve(const ospo_head_shape& s, void* base) {
   w.row_logit_sum = reinterpret_cast<float*>(take(rows * sizeof(float)));
   w.row_coef = reinterpret_cast<float*>(take(rows * sizeof(float)));
   w.row_max = reinterpret_cast<float*>(take(rows * sizeof(float)));
-  w.blk_mask = reinterpret_cast<uint8_t*>(take(rows / 128 + 1));
+  w.blk_mask = reinterpret_cast<uint8_t*>(take(rows / 128 + 2));
   w.seq_sum = reinterpret_cast<float*>(take(S * sizeof(float)));
   w.seq_logit_sum = reinterpret_cast<float*>(take(S * sizeof(float)));
   w.seq_count = reinterpret_cast<float*>(take(S * sizeof(float)));
@@ -312,11 +335,12 @@ int logps_forward(const ospo_simpo_args* a, const Workspace& w, cudaStream_t st)
   if (espill != nullptr && a->row_ref == nullptr) return OSPO_ERR_NULL;
   const int tile_m = gemm2_tile_m(c.cta_group);
   const int num_n = gemm2_num_n_tiles(s.vocab);
+  uint8_t* any_flag = w.blk_mask + s.rows / 128 + 1;
   int rc;
   {
     KernelSpan ks(st, OSPO_K_GEMM1);
-    if (cudaMemsetAsync(w.blk_mask, 0, static_cast<size_t>(s.rows) / 128 + 1, st) != cudaSuccess) return OSPO_ERR_CUDA;
-    rc = map_rc(launch_gemm1_bias_gelu(c, static_cast<const __nv_bfloat16*>(a->x),
+    if (cudaMemsetAsync(w.blk_mask, 0, static_cast<size_t>(s.rows) / 128 + 2, st) != cudaSuccess) return OSPO_ERR_CUDA;
+    rc = map_rc(launch_gemm1_bias_gelu(tuned(c, 0), static_cast<const __nv_bfloat16*>(a->x),
                                        static_cast<const __nv_bfloat16*>(a->w.w1), a->w.b1,
                                        static_cast<__nv_bfloat16*>(a->pre), static_cast<__nv_bfloat16*>(a->act),
                                        s.rows, s.hidden, s.embed, x_layout(a)));
@@ -324,26 +348,26 @@ int logps_forward(const ospo_simpo_args* a, const Workspace& w, cudaStream_t st)
   if (rc) return rc;
   {
     KernelSpan ks(st, OSPO_K_GEMM2_LSE);
-    rc = map_rc(launch_gemm2_logits_exp(c, static_cast<const __nv_bfloat16*>(a->act),
+    rc = map_rc(launch_gemm2_logits_exp(tuned(c, 1), static_cast<const __nv_bfloat16*>(a->act),
                                         static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2, espill, a->labels, w.part,
-                                        w.rowsum_part, w.tgt, nullptr, nullptr, s.rows, s.embed, s.vocab));
+                                        w.rowsum_part, w.tgt, nullptr, nullptr, nullptr, s.rows, s.embed, s.vocab));
   }
   if (rc) return rc;
   KernelSpan ks(st, OSPO_K_SCALAR_STAGE);
   const int fin_grid = (s.rows + 255) / 256;
   lse_finalize_kernel<<<fin_grid, 256, 0, st>>>(w.part, w.rowsum_part, w.tgt, a->labels, s.vocab, s.rows, num_n, tile_m,
-                                                1, w.blk_mask, a->row_ref, w.row_max, a->row_lse, a->row_logps,
-                                                w.row_logit_sum);
+                                                1, w.blk_mask, any_flag, a->row_ref, w.row_max, a->row_lse,
+                                                a->row_logps, w.row_logit_sum);
   if ((rc = check_launch())) return rc;
   // repair pass: M-blocks with a row maximum outside the representable window are recomputed against their own row
   // maxima.  For ordinary logits no block is flagged and both launches return at once.
   rc = map_rc(launch_gemm2_logits_exp(c, static_cast<const __nv_bfloat16*>(a->act),
                                       static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2, espill, a->labels, w.part,
-                                      w.rowsum_part, w.tgt, w.row_max, w.blk_mask, s.rows, s.embed, s.vocab));
+                                      w.rowsum_part, w.tgt, w.row_max, w.blk_mask, any_flag, s.rows, s.embed, s.vocab));
   if (rc) return rc;
   lse_finalize_kernel<<<fin_grid, 256, 0, st>>>(w.part, w.rowsum_part, w.tgt, a->labels, s.vocab, s.rows, num_n, tile_m,
-                                                2, w.blk_mask, a->row_ref, w.row_max, a->row_lse, a->row_logps,
-                                                w.row_logit_sum);
+                                                2, w.blk_mask, any_flag, a->row_ref, w.row_max, a->row_lse,
+                                                a->row_logps, w.row_logit_sum);
   if ((rc = check_launch())) return rc;
   if (espill != nullptr) {
     target_fixup_kernel<<<fin_grid, 256, 0, st>>>(espill, s.vocab, a->labels, s.vocab, s.rows, a->row_logps,
@@ -425,7 +449,7 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
     }
     {
       KernelSpan ks(st, OSPO_K_DACT);
-      rc = map_rc(launch_dact_gelu_bwd(c, g, static_cast<const __nv_bfloat16*>(a->w.w2),
+      rc = map_rc(launch_dact_gelu_bwd(tuned(c, 2), g, static_cast<const __nv_bfloat16*>(a->w.w2),
                                        static_cast<const __nv_bfloat16*>(a->pre), row_w, dpre,
                                        a->flat_grads ? w.act_w : nullptr, s.rows, s.embed, s.vocab));
       if (rc) return rc;
@@ -439,7 +463,7 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
     // dW2 first: it is the largest block of the flat gradient, so a caller that overlaps the
     // all-reduce with the remaining GEMMs can start on it earliest.
     KernelSpan ks(st, OSPO_K_WGRAD2);
-    rc = map_rc(launch_wgrad(c, g, w.act_w, dW2, s.rows, s.vocab, s.embed, wscale));
+    rc = map_rc(launch_wgrad(tuned(c, 3), g, w.act_w, dW2, s.rows, s.vocab, s.embed, wscale));
     if (rc) return rc;
   }
   if (a->flat_grads && second) {
@@ -449,14 +473,14 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
     }
     {
       KernelSpan ks(st, OSPO_K_WGRAD1);
-      rc = map_rc(launch_wgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden,
+      rc = map_rc(launch_wgrad(tuned(c, 4), dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden,
                                wscale, x_layout(a)));
     }
     if (rc) return rc;
   }
   if (a->dx && third) {
     KernelSpan ks(st, OSPO_K_DGRAD);
-    rc = map_rc(launch_dgrad(c, dpre, static_cast<const __nv_bfloat16*>(a->w.w1), static_cast<__nv_bfloat16*>(a->dx),
+    rc = map_rc(launch_dgrad(tuned(c, 5), dpre, static_cast<const __nv_bfloat16*>(a->w.w1), static_cast<__nv_bfloat16*>(a->dx),
                              s.rows, s.embed, s.hidden, x_layout(a)));
     if (rc) return rc;
   }
@@ -900,6 +924,15 @@ int ospo_head_set_group_m(int group_m) {
   runtime_init();
   if (group_m > 0) g_rt.group_m = group_m;
   return g_rt.group_m;
+}
+
+int ospo_head_set_kernel_tune(int kernel, int group_m, int a_evict, int b_evict) {
+  runtime_init();
+  if (kernel < 0 || kernel >= 6) return OSPO_ERR_UNSUPPORTED;
+  if (group_m >= 0) g_rt.tune[kernel][0] = group_m;
+  if (a_evict >= 0 && a_evict <= 2) g_rt.tune[kernel][1] = a_evict;
+  if (b_evict >= 0 && b_evict <= 2) g_rt.tune[kernel][2] = b_evict;
+  return OSPO_OK;
 }
 
 int ospo_head_profile_enable(int enable) {

@@ -381,6 +381,7 @@ struct EpiLogitsExp {
     float* tgt;                 // [rows] gathered target logit
     const float* row_ref;       // [rows] exponent reference (null = 0: first pass)
     const uint8_t* blk_mask;    // [num M-blocks] repair pass: only the flagged blocks are recomputed (null = all)
+    const uint8_t* any_flag;    // repair pass: *any_flag == 0 means no block is flagged (the launch returns at once)
   };
   struct State {
     float m, s, sum, tgt, nref;
@@ -394,6 +395,7 @@ struct EpiLogitsExp {
   __device__ static bool tile_enabled(const Params& p, int m_blk) {
     return p.blk_mask == nullptr || p.blk_mask[m_blk] != 0;
   }
+  __device__ static bool launch_enabled(const Params& p) { return p.any_flag == nullptr || *p.any_flag != 0; }
   __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
     st.m = -INFINITY;
     st.s = 0.0f;

@@ -19,9 +19,9 @@ int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* g, const __nv_
   Epi::Params p{pre, dpre, E, row_w, act_w};
   // D[rows, E] = g[rows, V] * W2[V, E]:  M = rows, N = E, K = V
   if (c.cta_group == 2) return launch_gemm<CfgD2, Epi>(g, V, w2, E, rows, E, V, c.group_m, p, c.num_sms, c.stream, 1, false,
-                                  SegOperand(), SegOperand(), 0, c.sync_ctr);
+                                  SegOperand(), SegOperand(), 0, c.sync_ctr, c.a_evict, c.b_evict);
   return launch_gemm<CfgD1, Epi>(g, V, w2, E, rows, E, V, c.group_m, p, c.num_sms, c.stream, 1, false,
-                                  SegOperand(), SegOperand(), 0, c.sync_ctr);
+                                  SegOperand(), SegOperand(), 0, c.sync_ctr, c.a_evict, c.b_evict);
 }
 
 int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx, int rows,
@@ -30,9 +30,9 @@ int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat1
   Epi::Params p{dx, in_dim, nullptr, RowMap{xl.seg_rows, xl.seg_pitch, xl.seg_off}};
   if (c.cta_group == 2)
     return launch_gemm<CfgD2, Epi>(dy, out_dim, w, in_dim, rows, in_dim, out_dim, c.group_m, p, c.num_sms, c.stream, 1, false,
-                                  SegOperand(), SegOperand(), 0, c.sync_ctr);
+                                  SegOperand(), SegOperand(), 0, c.sync_ctr, c.a_evict, c.b_evict);
   return launch_gemm<CfgD1, Epi>(dy, out_dim, w, in_dim, rows, in_dim, out_dim, c.group_m, p, c.num_sms, c.stream, 1, false,
-                                  SegOperand(), SegOperand(), 0, c.sync_ctr);
+                                  SegOperand(), SegOperand(), 0, c.sync_ctr, c.a_evict, c.b_evict);
 }
 
 int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw, int rows, int out_dim,
@@ -47,9 +47,9 @@ int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat1
   // D[out, in] = dY^T[out, rows] * X[rows, in]:  M = out_dim, N = in_dim, K = rows
   if (c.cta_group == 2)
     return launch_gemm<CfgW2, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream, 1,
-                                   false, SegOperand(), sb, 0, c.sync_ctr);
+                                   false, SegOperand(), sb, 0, c.sync_ctr, c.a_evict, c.b_evict);
   return launch_gemm<CfgW1, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream, 1,
-                                 false, SegOperand(), sb, 0, c.sync_ctr);
+                                 false, SegOperand(), sb, 0, c.sync_ctr, c.a_evict, c.b_evict);
 }
 
 }  // namespace ospo

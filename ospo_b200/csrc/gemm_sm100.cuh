@@ -46,6 +46,9 @@ struct GemmDims {
   uint32_t* sync_ctr;
   int sync_tiles;
   int sync_stride;  // lock-step every this many tiles (short tiles need it less often)
+  // L2 eviction hints of the operand loads (kEvictNormal / kEvictFirst / kEvictLast): the operand whose panels are
+  // re-used by later waves is kept (evict-last), the one that streams through once per wave goes first
+  uint64_t a_hint, b_hint;
 };
 
 // where a row-mapped output row lands: logical row r -> physical row of a [segments, pitch, cols] tensor
@@ -165,6 +168,13 @@ __device__ __forceinline__ bool epi_tile_enabled(const P& ep, int m_blk) {
   if constexpr (epi_has_tile_mask<Epi>::value) return Epi::tile_enabled(ep, m_blk);
   else return true;
 }
+// ... and `static bool launch_enabled(const Params&)`: false (the same for every thread of the grid) makes the whole
+// launch return before it sets anything up.
+template <class Epi, class P>
+__device__ __forceinline__ bool epi_launch_enabled(const P& ep) {
+  if constexpr (epi_has_tile_mask<Epi>::value) return Epi::launch_enabled(ep);
+  else return true;
+}
 
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(Cfg::BOUND_THREADS, Cfg::MIN_BLOCKS)
@@ -174,6 +184,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
 
   pdl_launch_dependents();  // our successor may start its own prologue (and weight prefetch) right away
+  if (!epi_launch_enabled<Epi>(ep)) return;  // grid-uniform: nothing to do (e.g. a repair pass with no flagged block)
   if (threadIdx.x == 0) trace_stamp(dims.trace_id, 0);
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte alignment (in the shared address space)
@@ -249,23 +260,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               const int r = m0 + 64 * c;
               const int sg = r / dims.a_seg_rows;
               const int rr = dims.a_seg_off + (r - sg * dims.a_seg_rows);
-              if constexpr (CG == 1) tma_load_3d(sa + c * 8192, &tmap_a, &full_bar[s_], k0, rr, sg, kEvictNormal);
-              else tma_load_3d_2sm(sa + c * 8192, &tmap_a, &full_bar[s_], k0, rr, sg, kEvictNormal);
+              if constexpr (CG == 1) tma_load_3d(sa + c * 8192, &tmap_a, &full_bar[s_], k0, rr, sg, dims.a_hint);
+              else tma_load_3d_2sm(sa + c * 8192, &tmap_a, &full_bar[s_], k0, rr, sg, dims.a_hint);
             }
-          } else if constexpr (CG == 1) tma_load_2d(sa, &tmap_a, &full_bar[s_], k0, m0, kEvictNormal);
-          else tma_load_2d_2sm(sa, &tmap_a, &full_bar[s_], k0, m0, kEvictNormal);
+          } else if constexpr (CG == 1) tma_load_2d(sa, &tmap_a, &full_bar[s_], k0, m0, dims.a_hint);
+          else tma_load_2d_2sm(sa, &tmap_a, &full_bar[s_], k0, m0, dims.a_hint);
         } else {
 #pragma unroll
           for (int c = 0; c < BM / 64; ++c) {
-            if constexpr (CG == 1) tma_load_2d(sa + c * (BK * 128), &tmap_a, &full_bar[s_], m0 + 64 * c, k0, kEvictNormal);
-            else tma_load_2d_2sm(sa + c * (BK * 128), &tmap_a, &full_bar[s_], m0 + 64 * c, k0, kEvictNormal);
+            if constexpr (CG == 1) tma_load_2d(sa + c * (BK * 128), &tmap_a, &full_bar[s_], m0 + 64 * c, k0, dims.a_hint);
+            else tma_load_2d_2sm(sa + c * (BK * 128), &tmap_a, &full_bar[s_], m0 + 64 * c, k0, dims.a_hint);
           }
         }
       };
       auto load_b = [&](uint8_t* sb, int s_, int n0, int k0) {
         if constexpr (!Cfg::B_MN) {
-          if constexpr (CG == 1) tma_load_2d(sb, &tmap_b, &full_bar[s_], k0, n0, kEvictNormal);
-          else tma_load_2d_2sm(sb, &tmap_b, &full_bar[s_], k0, n0, kEvictNormal);
+          if constexpr (CG == 1) tma_load_2d(sb, &tmap_b, &full_bar[s_], k0, n0, dims.b_hint);
+          else tma_load_2d_2sm(sb, &tmap_b, &full_bar[s_], k0, n0, dims.b_hint);
         } else {
           const bool seg = dims.b_seg_rows != 0;
           int sg = 0, rr = k0;
@@ -276,11 +287,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int c = 0; c < Cfg::B_ROWS / 64; ++c) {
             if (seg) {
-              if constexpr (CG == 1) tma_load_3d(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, rr, sg, kEvictNormal);
-              else tma_load_3d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, rr, sg, kEvictNormal);
+              if constexpr (CG == 1) tma_load_3d(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, rr, sg, dims.b_hint);
+              else tma_load_3d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, rr, sg, dims.b_hint);
             } else {
-              if constexpr (CG == 1) tma_load_2d(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, kEvictNormal);
-              else tma_load_2d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, kEvictNormal);
+              if constexpr (CG == 1) tma_load_2d(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, dims.b_hint);
+              else tma_load_2d_2sm(sb + c * (BK * 128), &tmap_b, &full_bar[s_], n0 + 64 * c, k0, dims.b_hint);
             }
           }
         }
@@ -577,7 +588,7 @@ template <class Cfg, class Epi>
 int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, int N, int K, int group_m,
                 const typename Epi::Params& ep, int num_sms, cudaStream_t stream, int k_splits = 1,
                 bool pdl = false, SegOperand a_seg = SegOperand(), SegOperand b_seg = SegOperand(), int trace_id = 0,
-                uint32_t* sync_ctr = nullptr) {
+                uint32_t* sync_ctr = nullptr, int a_evict = 0, int b_evict = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   CUtensorMap ta, tb;
   int rc;
@@ -618,6 +629,8 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   dims.b_seg_off = b_seg.seg_off;
   dims.die_split = (g_die_split() && k_splits <= 1) ? 1 : 0;
   dims.trace_id = trace_id;
+  dims.a_hint = a_evict == 1 ? kEvictFirst : a_evict == 2 ? kEvictLast : kEvictNormal;
+  dims.b_hint = b_evict == 1 ? kEvictFirst : b_evict == 2 ? kEvictLast : kEvictNormal;
   const int num_m = (M + Cfg::TILE_M - 1) / Cfg::TILE_M;
   const int num_n = (N + Cfg::BN - 1) / Cfg::BN;
   const int num_tiles = num_m * num_n * dims.k_splits;

@@ -25,14 +25,30 @@ constexpr float E_WINDOW_HI = 60.0f, E_WINDOW_LO = -50.0f;
 __global__ void lse_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ rowsum_part,
                                     const float* __restrict__ tgt, const int64_t* __restrict__ labels, int vocab,
                                     int rows, int num_n, int tile_m, int pass, uint8_t* __restrict__ blk_mask,
-                                    float* __restrict__ row_ref, float* __restrict__ row_max,
+                                    uint8_t* __restrict__ any_flag, float* __restrict__ row_ref, float* __restrict__ row_max,
                                     float* __restrict__ row_lse, float* __restrict__ row_logp,
                                     float* __restrict__ row_logit_sum) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  if (pass == 2 && blk_mask[r / tile_m] == 0) return;
+  if (pass == 2 && (*any_flag == 0 || blk_mask[r / tile_m] == 0)) return;
   float m = -INFINITY, s = 0.0f, ls = 0.0f;
-  for (int nb = 0; nb < num_n; ++nb) {
+  int nb = 0;
+  for (; nb + 8 <= num_n; nb += 8) {   // eight independent loads in flight, added in the fixed order nb = 0, 1, ...
+    float2 p[8];
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      p[i] = part[static_cast<int64_t>(nb + i) * rows + r];
+      q[i] = (rowsum_part != nullptr) ? rowsum_part[static_cast<int64_t>(nb + i) * rows + r] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      m = fmaxf(m, p[i].x);
+      s += p[i].y;
+      ls += q[i];
+    }
+  }
+  for (; nb < num_n; ++nb) {
     const float2 p = part[static_cast<int64_t>(nb) * rows + r];
     m = fmaxf(m, p.x);
     s += p.y;
@@ -41,7 +57,10 @@ __global__ void lse_finalize_kernel(const float2* __restrict__ part, const float
   float ref = 0.0f;
   if (pass == 1) {
     row_max[r] = m;
-    if (!(m <= E_WINDOW_HI && m >= E_WINDOW_LO)) blk_mask[r / tile_m] = 1;  // benign race: every writer stores 1
+    if (!(m <= E_WINDOW_HI && m >= E_WINDOW_LO)) {   // benign races: every writer stores 1
+      blk_mask[r / tile_m] = 1;
+      *any_flag = 1;
+    }
   } else {
     ref = row_max[r];
   }

@@ -17,6 +17,7 @@ struct LaunchCtx {
   bool pdl;       // launch with programmatic stream serialization (decode chain)
   bool trace = false;  // timeline stamps on (ospo_head_trace); off = the stamps compile to a parameter test
   unsigned long long* trace_buf = nullptr;
+  int a_evict = 0, b_evict = 0;  // L2 eviction hint of the A / B operand loads: 0 normal, 1 evict-first, 2 evict-last
   uint32_t* sync_ctr = nullptr;  // wave lock-step counter for the persistent training GEMMs (null = free-running)  // the installed timeline buffer (merged decode kernel stamps through it)
 };
 
@@ -47,11 +48,13 @@ int launch_gemm1_bias_gelu(const LaunchCtx& c, const __nv_bfloat16* x, const __n
                            const XLayout& xl = XLayout());
 // forward GEMM2 with the softmax numerator fused in: l = bf16(act W2^T + b2), e = exp(l - row_ref) spilled as bf16
 // (+ per sub-tile (max l, sum e) partials, target gather, logits row sums);  act [rows,E], w2 [V,E].
-// row_ref null = 0; blk_mask non-null = repair pass over the flagged M-blocks only (gemm2_tile_m rows each).
+// row_ref null = 0; blk_mask non-null = repair pass over the flagged M-blocks only (gemm2_tile_m rows each), which
+// returns at once when *any_flag == 0.
 int launch_gemm2_logits_exp(const LaunchCtx& c, const __nv_bfloat16* act, const __nv_bfloat16* w2, const float* b2,
                             __nv_bfloat16* espill /*nullable*/, const int64_t* labels, float2* part,
                             float* rowsum_part /*nullable*/, float* tgt, const float* row_ref /*nullable*/,
-                            const uint8_t* blk_mask /*nullable*/, int rows, int E, int V);
+                            const uint8_t* blk_mask /*nullable*/, const uint8_t* any_flag /*nullable*/, int rows,
+                            int E, int V);
 int gemm2_tile_m(int cta_group);
 int gemm2_num_n_tiles(int V);
 // plain logits = bf16(act W2^T + b2)

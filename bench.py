@@ -16,6 +16,10 @@ configs[2]'s 512 pairs at N = 8 -- and all-reduces the flat fp32 head-weight gra
   cfg        secondary metric: BASELINE.json configs[3], 576 sequential CFG decode steps at P = 16
 
 ``--impl reference`` times the reference's CPU path (the oracle port) on the host cores instead.
+``--impl torch_gpu`` (context, not the anchor) runs the same step as plain PyTorch on the GPU -- what OSPO executes
+today: bf16 Linear / GELU / Linear through cuBLAS, fp32 log_softmax + gather, autograd -- and reports its step time
+and peak memory next to the fused path's.
+``--global-pairs G`` fixes the TOTAL batch (strong scaling, configs[2]: 512 pairs over 2 / 4 / 8 GPUs).
 """
 from __future__ import annotations
 
@@ -68,12 +72,17 @@ class ClockSampler:
         self.rows = []
         self.proc = None
 
-    def start(self):
+    def start(self, wait_s: float = 5.0):
+        """start sampling every 50 ms and wait until the first sample has arrived (nvidia-smi takes a few hundred ms
+        to come up -- longer than a short timed region -- so the sampler is started before the warm-up steps)"""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t_end = time.time() + wait_s
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -87,9 +96,15 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons, power = [], [], set(), []
-        for ts, line in self.rows:
-            if t0 is not None and not (t0 <= ts <= t1 + 0.2):
-                continue
+        rows = self.rows
+        if t0 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1 + 0.1]
+            if not inside and rows:
+                # timed region shorter than the sampling period: take the sample nearest to it
+                mid = 0.5 * (t0 + t1)
+                inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+            rows = inside
+        for ts, line in rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -109,15 +124,18 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # CPU path (oracle port of the reference) -- used for cpu_baseline and for --impl reference
 # -------------------------------------------------------------------------------------------------
-def cpu_simpo_sample(pairs: int, reps: int):
+CPU_PAIRS = 8   # the 7B shape at 8 pairs (per-token figure comparable to configs[1])
+
+
+def cpu_simpo_sample(pairs: int, reps: int, hidden: int = H7B):
     import torch
 
     from oracle import head_oracle as O
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    head = O.make_head(H7B, E7B, V, seed=1235)
-    hc, hr, lc, lr = O.synthetic_simpo_batch(pairs, T_IMG, 1, H7B, V, seed=1236)
+    head = O.make_head(hidden, hidden, V, seed=1235)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(pairs, T_IMG, 1, hidden, V, seed=1236)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -131,7 +149,7 @@ def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pairs = 4
+    pairs = CPU_PAIRS
     tokens, times, cores = cpu_simpo_sample(pairs, args.warmup + args.steps)
     timed = times[args.warmup:] or times
     ms = 1e3 * sum(timed) / len(timed)
@@ -148,6 +166,320 @@ def run_reference_arm(args, emit):
     }))
 
 
+
+# -------------------------------------------------------------------------------------------------
+# context arm: the same step as plain PyTorch on the GPU (what OSPO runs today on the same B200)
+# -------------------------------------------------------------------------------------------------
+def torch_head_simpo_step(params, hidden, labels, B):
+    """janus/models/modeling_vlm.py:47-51 + ospo/wrapper/train.py:375-396, 317-342, 419 in stock PyTorch: bf16 Linear /
+    GELU / Linear under autocast (cuBLAS), log_softmax promoted to fp32 by autocast, gather, masked mean, SimPO
+    sigmoid loss, autograd backward.  Written out here (not imported from oracle/) because it is a GPU timing arm."""
+    import torch
+    import torch.nn.functional as F
+
+    W1, b1, W2, b2 = params
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = F.linear(F.gelu(F.linear(hidden, W1, b1)), W2, b2)
+        lab = labels[:, 1:].clone()
+        lg = logits[:, :-1, :]
+        mask = lab != -100
+        lab[lab == -100] = 0
+        ptl = torch.gather(lg.log_softmax(-1), dim=2, index=lab.unsqueeze(2)).squeeze(2)   # fp32 under autocast
+        logps = (ptl * mask).sum(-1) / mask.sum(-1)
+        z = (logps[:B] - logps[B:]) - HP["gamma_beta_ratio"]
+        loss = (-F.logsigmoid(HP["beta"] * z)).mean()
+    loss.backward()
+    return loss.detach()
+
+
+def run_torch_gpu_arm(args, emit):
+    import torch
+
+    from ospo_b200 import FusedGenHead
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl torch_gpu needs a GPU")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, L = args.pairs, 1
+    rows = 2 * B * T_IMG
+    torch.manual_seed(1235)
+
+    class P:
+        n_embed, image_token_embed, image_token_size = H7B, E7B, V
+
+    head = FusedGenHead(P).to(dev).to(torch.bfloat16)
+    gen = torch.Generator(device=dev).manual_seed(1236)
+    hidden = torch.randn(2 * B, L + T_IMG, H7B, generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    ids = torch.randint(0, V, (2 * B, T_IMG), generator=gen, device=dev)
+    labels = torch.cat([torch.full((2 * B, L), -100, dtype=torch.long, device=dev), ids], 1)
+    params = [head.output_mlp_projector.weight, head.output_mlp_projector.bias, head.vision_head.weight,
+              head.vision_head.bias]
+
+    def torch_step():
+        head.zero_grad(set_to_none=True)
+        hh = hidden.detach().requires_grad_(True)
+        return torch_head_simpo_step(params, hh, labels, B)
+
+    def fused_step():
+        head.zero_grad(set_to_none=True)
+        hh = hidden.detach().requires_grad_(True)
+        out = head.simpo(hh, labels, image_span=(L - 1, L - 1 + T_IMG), **HP)
+        out.loss.backward()
+        return out.loss.detach()
+
+    def measure(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        resident = torch.cuda.memory_allocated(dev)
+        torch.cuda.reset_peak_memory_stats(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, torch.cuda.max_memory_allocated(dev), resident, float(loss)
+
+    clocks = ClockSampler(0)
+    clocks.start()
+    torch_step()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    ms_t, peak_t, res_t, loss_t = measure(torch_step)
+    t1 = time.time()
+    clk = clocks.stop(t0, t1)
+    head.zero_grad(set_to_none=True)
+    torch.cuda.empty_cache()
+    ms_f, peak_f, res_f, loss_f = measure(fused_step)
+    value = rows / (ms_t / 1e3)
+    emit({
+        "impl": "torch_gpu", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "rows_per_gpu": rows,
+                   "what": "stock PyTorch on the same GPU: bf16 autocast Linear/GELU/Linear (cuBLAS), fp32 log_softmax + "
+                           "gather, SimPO sigmoid loss, autograd; head trainable, inputs resident in HBM", "loss": loss_t},
+        "clocks": clk, "gpu_launches": 0,
+        "memory": {"peak_bytes": peak_t, "resident_before_step_bytes": res_t, "step_transient_bytes": peak_t - res_t},
+        "fused_same_process": {"ms_per_step": ms_f, "value": rows / (ms_f / 1e3), "loss": loss_f,
+                               "memory": {"peak_bytes": peak_f, "resident_before_step_bytes": res_f,
+                                          "step_transient_bytes": peak_f - res_f},
+                               "speedup_vs_torch_gpu": ms_t / ms_f,
+                               "transient_memory_ratio_torch_over_fused": (peak_t - res_t) / max(1, peak_f - res_f)},
+    })
+
+
+
+# -------------------------------------------------------------------------------------------------
+# configs[4]: end-to-end SimPO training step, 7B-shaped Llama backbone + the head (fused vs PyTorch), N GPUs
+# -------------------------------------------------------------------------------------------------
+def run_config5(args, emit):
+    """BASELINE.json configs[4]: random-init Janus-Pro-7B-shaped language model (HF LlamaModel, 30 layers, hidden 4096,
+    32 heads, intermediate 11008, vocab 102400; activation checkpointing, trainable, bf16) + gen_head frozen as in
+    configs/step5.yaml:59-66, 16 pairs per GPU (step5.yaml:23), L = 24 text + 576 image positions.  One process per
+    GPU; the backbone gradients are averaged by DDP (ospo/utils/train.py:26-28).  Two arms on the same weights and
+    batch: (a) the reference formulation -- PyTorch vision_head on every position, fp32 log_softmax, gather
+    (ospo/wrapper/train.py:345-445) -- and (b) ``patch_train_wrapper`` (fused head on the 576 useful rows).  Reports
+    pairs/s of the whole job, the head's own time inside the step (CUDA events around the head forward / backward on
+    the step's hidden states), and the peak memory of each arm."""
+    import types
+
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from transformers import LlamaConfig, LlamaModel
+
+    from ospo_b200 import FusedGenHead, _abi, patch_train_wrapper
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --config5 needs a B200")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    PAIRS = 16 if args.pairs == PAIRS_PER_GPU else args.pairs
+    LAYERS = int(os.environ.get("OSPO_BENCH_LAYERS", "30"))
+    L, T, H = 24, T_IMG, H7B
+    torch.manual_seed(0)
+    cfg = LlamaConfig(hidden_size=H, intermediate_size=11008, num_hidden_layers=LAYERS, num_attention_heads=32,
+                      num_key_value_heads=32, vocab_size=102400, max_position_embeddings=16384)
+    cfg.output_hidden_states = True                       # ospo/wrapper/train.py:50
+    with torch.device(dev):
+        backbone = LlamaModel(cfg).to(torch.bfloat16)
+    backbone.gradient_checkpointing_enable(gradient_checkpointing_kwargs={"use_reentrant": False})
+    backbone.train()
+    backbone.embed_tokens.weight.requires_grad_(False)    # the step feeds inputs_embeds (train.py:352): never used
+    net = backbone
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(backbone, device_ids=[local_rank], gradient_as_bucket_view=True)
+
+    class P:
+        n_embed, image_token_embed, image_token_size = H, H, V
+
+    torch.manual_seed(5)
+    ref_head = torch.nn.Module()
+    ref_head.output_mlp_projector = torch.nn.Linear(H, H)
+    ref_head.vision_activation = torch.nn.GELU()
+    ref_head.vision_head = torch.nn.Linear(H, V)
+    ref_head.forward = lambda x: ref_head.vision_head(ref_head.vision_activation(ref_head.output_mlp_projector(x)))
+    ref_head = ref_head.to(dev).to(torch.bfloat16)
+    for prm in ref_head.parameters():
+        prm.requires_grad_(False)                          # configs/step5.yaml:59-66
+    g = torch.Generator().manual_seed(1 + rank)
+    emb_c = (torch.randn(PAIRS, L + T, H, generator=g) * 0.02).to(torch.bfloat16).to(dev)
+    emb_r = (torch.randn(PAIRS, L + T, H, generator=g) * 0.02).to(torch.bfloat16).to(dev)
+    pad = torch.full((PAIRS, L), -100, dtype=torch.long)
+    lab_c = torch.cat([pad, torch.randint(0, V, (PAIRS, T), generator=g)], 1).to(dev)
+    lab_r = torch.cat([pad, torch.randint(0, V, (PAIRS, T), generator=g)], 1).to(dev)
+    batch = {"chosen_inputs_embeds": emb_c, "chosen_labels": lab_c, "rejected_inputs_embeds": emb_r,
+             "rejected_labels": lab_r}
+    labels_all = torch.cat([lab_c, lab_r], 0)
+    head_ev = {"fwd": [], "bwd": []}
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def reference_head_loss(hidden):
+        # ospo/wrapper/train.py:357 (head on EVERY position), :375-396, :317-342, :419
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = ref_head.forward(hidden)
+            lab = labels_all[:, 1:].clone()
+            lg = logits[:, :-1, :]
+            mask = lab != -100
+            lab[lab == -100] = 0
+            ptl = torch.gather(lg.log_softmax(-1), dim=2, index=lab.unsqueeze(2)).squeeze(2)
+            logps = (ptl * mask).sum(-1) / mask.sum(-1)
+            z = (logps[:PAIRS] - logps[PAIRS:]) - HP["gamma_beta_ratio"]
+            return (-F.logsigmoid(HP["beta"] * z)).mean()
+
+    model = torch.nn.Module()
+    model.language_model = torch.nn.Module()
+    model.language_model.model = net
+    model.gen_head = ref_head
+    w = types.SimpleNamespace(model=model, label_pad_token_id=-100, logged={}, **HP)
+    w.log = lambda name, val, **kw: w.logged.__setitem__(name, val)
+    w.log_dict = lambda d, **kw: w.logged.update(d)
+    w.concatenated_inputs = lambda batch: {
+        "concatenated_inputs_embeds": torch.cat([batch["chosen_inputs_embeds"], batch["rejected_inputs_embeds"]], 0),
+        "concatenated_labels": torch.cat([batch["chosen_labels"], batch["rejected_labels"]], 0)}
+
+    def timed_head(loss_fn, hidden):
+        """head forward + backward on the step's own hidden states, bracketed by events (detached leaf: the backbone's
+        backward is run afterwards from the gradient the head returned)"""
+        leaf = hidden.detach().requires_grad_(True)
+        e0, e1, e2 = ev(), ev(), ev()
+        step_peak = torch.cuda.max_memory_allocated(dev)
+        before = torch.cuda.memory_allocated(dev)
+        torch.cuda.reset_peak_memory_stats(dev)
+        e0.record()
+        loss = loss_fn(leaf)
+        e1.record()
+        loss.backward()
+        e2.record()
+        head_ev["fwd"].append((e0, e1))
+        head_ev["bwd"].append((e1, e2))
+        head_ev["mem"] = max(head_ev.get("mem", 0), torch.cuda.max_memory_allocated(dev) - before)
+        head_ev["peak"] = max(head_ev.get("peak", 0), step_peak, torch.cuda.max_memory_allocated(dev))
+        torch.cuda.reset_peak_memory_stats(dev)
+        hidden.backward(leaf.grad)
+        head_ev["peak"] = max(head_ev["peak"], torch.cuda.max_memory_allocated(dev))
+        return loss.detach()
+
+    def reference_step():
+        hidden = net(inputs_embeds=torch.cat([emb_c, emb_r], 0), use_cache=False).hidden_states[-1]
+        return timed_head(reference_head_loss, hidden)
+
+    def fused_step():
+        hidden = net(inputs_embeds=torch.cat([emb_c, emb_r], 0), use_cache=False).hidden_states[-1]
+        return timed_head(lambda leaf: model.gen_head.simpo(leaf, labels_all, image_span=(L - 1, L - 1 + T),
+                                                            **HP).loss, hidden)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def measure(fn):
+        backbone.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        for _ in range(max(1, min(args.warmup, 2))):
+            backbone.zero_grad(set_to_none=True)
+            fn()
+        backbone.zero_grad(set_to_none=True)
+        head_ev["fwd"].clear()
+        head_ev["bwd"].clear()
+        head_ev["mem"] = head_ev["peak"] = 0
+        sync_all()
+        torch.cuda.reset_peak_memory_stats(dev)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(args.steps):
+            backbone.zero_grad(set_to_none=True)
+            loss = fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1) / args.steps
+        hf = sum(a.elapsed_time(b) for a, b in head_ev["fwd"]) / args.steps
+        hb = sum(a.elapsed_time(b) for a, b in head_ev["bwd"]) / args.steps
+        peak, head_mem = head_ev["peak"], head_ev["mem"]
+        if world > 1:
+            t = torch.tensor([ms, hf, hb, float(peak), float(head_mem)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, hf, hb, peak, head_mem = (float(v) for v in t)
+        gnorm = backbone.layers[0].self_attn.q_proj.weight.grad.detach().float().clone()
+        return {"ms_per_step": ms, "head_fwd_ms": hf, "head_bwd_ms": hb, "head_ms": hf + hb, "peak_bytes": int(peak),
+                "head_transient_bytes": int(head_mem), "loss": float(loss)}, gnorm
+
+    args.steps = max(1, min(args.steps, 5))
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    t0 = time.time()
+    ref_res, g_ref = measure(reference_step)
+    patch_train_wrapper(w, image_span=(L - 1, L - 1 + T))
+    assert isinstance(model.gen_head, FusedGenHead)
+    launches0 = _abi.load().ospo_head_launch_count()
+    fused_res, g_fused = measure(fused_step)
+    launches = int(_abi.load().ospo_head_launch_count() - launches0)
+    t1 = time.time()
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+    grad_rel = float((g_fused - g_ref).norm() / g_ref.norm().clamp_min(1e-20))
+    if rank == 0:
+        for r_ in (ref_res, fused_res):
+            r_["pairs_per_s"] = world * PAIRS / (r_["ms_per_step"] / 1e3)
+            r_["head_share_of_step"] = r_["head_ms"] / r_["ms_per_step"]
+        emit({
+            "metric": "simpo_train_step_pairs_per_s", "value": fused_res["pairs_per_s"], "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": fused_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"configs[4]: random-init Janus-Pro-7B-shaped Llama backbone ({LAYERS} layers, hidden 4096, "
+                                   f"activation checkpointing, trainable) + gen_head frozen, {PAIRS} pairs x ({L} text + 576 "
+                                   f"image) positions per GPU, {world} GPU(s), DDP over the backbone gradients",
+                       "pairs_per_gpu": PAIRS, "layers": LAYERS},
+            "clocks": clk, "gpu_launches": launches, "fused_head": fused_res, "pytorch_head": ref_res,
+            "head_speedup": ref_res["head_ms"] / fused_res["head_ms"],
+            "head_transient_memory_ratio_pytorch_over_fused": ref_res["head_transient_bytes"] / max(1, fused_res["head_transient_bytes"]),
+            "peak_memory_saved_bytes": ref_res["peak_bytes"] - fused_res["peak_bytes"],
+            "memory_note": "peak_bytes is the step's maximum (weights + all backbone gradients at the end of the backward: "
+                           "the head is not live then); head_transient_bytes is what the head's forward + backward "
+                           "allocates on top of what is live when it starts",
+            "parity": {"loss_fused": fused_res["loss"], "loss_pytorch_head": ref_res["loss"],
+                       "first_layer_q_proj_grad_rel_err": grad_rel},
+        })
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # -------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -159,6 +491,10 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cfg", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--global-pairs", type=int, default=0,
+                    help="total pairs over all GPUs (strong scaling; configs[2] = 512); overrides --pairs")
+    ap.add_argument("--config5", action="store_true",
+                    help="configs[4]: Janus-Pro-7B-shaped random-init Llama backbone + the fused head, 16 pairs per GPU")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: library chatter (e.g. NCCL's version banner) goes to stderr meanwhile
     sys.stdout.flush()
@@ -175,6 +511,12 @@ def main():
         run_reference_arm(args, emit)
         return
     args.warmup = max(args.warmup, 3)
+    if args.impl == "torch_gpu":
+        run_torch_gpu_arm(args, emit)
+        return
+    if args.config5:
+        run_config5(args, emit)
+        return
 
     import torch
     import torch.distributed as dist
@@ -194,7 +536,10 @@ def main():
         group = dist.group.WORLD
 
     peaks = load_peaks()
-    B = args.pairs
+    strong = args.global_pairs > 0
+    if strong and args.global_pairs % world:
+        raise SystemExit(f"--global-pairs {args.global_pairs} does not shard over {world} GPUs")
+    B = args.global_pairs // world if strong else args.pairs
     rows = 2 * B * T_IMG
     tokens_per_step_rank = rows
     L = 1   # one leading masked position so the label shift of train.py:385-386 is exercised
@@ -226,17 +571,19 @@ def main():
             torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         step(hidden, labels)
     sync_all()
     _abi.profile_enable(True)
     _abi.profile_read()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     launches0 = _abi.load().ospo_head_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    mem_resident = torch.cuda.memory_allocated(dev)       # weights + inputs + the reusable flat gradient buffer
+    torch.cuda.reset_peak_memory_stats(dev)
     t_wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
@@ -245,6 +592,7 @@ def main():
     sync_all()
     t_wall1 = time.time()
     launches = int(_abi.load().ospo_head_launch_count() - launches0)
+    mem_peak = torch.cuda.max_memory_allocated(dev)
     prof = _abi.profile_read()
     _abi.profile_enable(False)
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
@@ -255,6 +603,21 @@ def main():
         ms_step = float(t)
     value = world * tokens_per_step_rank / (ms_step / 1e3)
     loss_val = float(loss.detach())
+
+    # ---- N > 1: value check of the gradient exchange (every rank's exchanged buffer is bit-identical and equals the
+    #      mean of the pre-exchange local ones) -------------------------------------------------------------------
+    dp = None
+    if world > 1:
+        from ospo_b200 import dist as D
+
+        head.zero_grad(set_to_none=True)
+        hh = hidden.detach().requires_grad_(True)
+        head.simpo(hh, labels, image_span=span, process_group=None, **HP).loss.backward()
+        flat_local = head._flat.clone()
+        step(hidden, labels)
+        dp = D.dp_check(flat_local, head._flat, group)
+        del flat_local
+        sync_all()
 
     # ---- per-kernel table + roofline of the dominant kernel ---------------------------------------
     HE, EV = H7B * E7B, E7B * V
@@ -275,7 +638,7 @@ def main():
     step_tflops = tokens_per_step_rank * flops_per_token(H7B, E7B, V) / (ms_step / 1e3) / 1e12
     roofline = None
     traffic, tensor_pct = None, None
-    tf = ROOT / "profiles" / "r01_kernel_traffic.json"
+    tf = ROOT / "profiles" / "kernel_traffic.json"
     if dominant and tf.exists():
         ent = json.loads(tf.read_text()).get(dominant)
         if ent:
@@ -286,8 +649,8 @@ def main():
             "bound": "tensor", "kernel": dominant, "achieved": kernels[dominant]["tflops"], "peak": peaks["tf_burst"],
             "unit": "TFLOP/s", "frac": kernels[dominant]["tflops"] / peaks["tf_burst"], "traffic": traffic,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch, ncu capture of this "
-                              "command (profiles/r01_kernel_traffic.json, r01_launches_ncu_v2.csv, "
-                              "r01_dact_lockstep_ncu_summary.txt)" if traffic else None,
+                              "command (profiles/kernel_traffic.json, generated by scripts/make_kernel_traffic.py from "
+                              "the launch list named inside it)" if traffic else None,
             "ncu_tensor_pipe_active_pct": tensor_pct,
             "peak_source": peaks["source"] + " bf16_tflops (burst); sustained " + str(peaks["tf_sustained"]),
             "step_achieved_tflops": step_tflops, "step_frac": step_tflops / peaks["tf_burst"],
@@ -343,8 +706,7 @@ def main():
         e1.record()
         sync_all()
         wall_ms = (time.perf_counter() - tw0) * 1e3 / args.steps
-        ms_e2e = max(e0.elapsed_time(e1) / args.steps, 0.0)
-        ms_e2e = max(ms_e2e, wall_ms * 0.0)   # device time; wall clock reported beside it
+        ms_e2e = e0.elapsed_time(e1) / args.steps      # device time; the wall clock is reported beside it
         if world > 1:
             t = torch.tensor([ms_e2e], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -395,25 +757,40 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        pairs = 4
+        pairs = CPU_PAIRS
         tokens, times, cores = cpu_simpo_sample(pairs, 2)
         best = min(times)
         cpu = {"value": tokens / best, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{pairs} pairs x {T_IMG} tokens ({tokens} rows) of the same 7B-shaped head, fp32 torch CPU "
                          f"oracle (port of the reference path), fwd+bwd, best of 2, {cores} threads"}
+        # BASELINE.json configs[0] exactly: 1B-shaped head (hidden 2048), 8 pairs x 576 tokens, fp32 on CPU
+        tok1, t1, _ = cpu_simpo_sample(8, 4, hidden=2048)
+        cpu["config1"] = {"workload": "configs[0]: 1B-shaped head (H=E=2048), 8 pairs x 576 tokens, fp32, fwd+bwd",
+                          "value": tok1 / min(t1[1:]), "unit": UNIT, "s_per_step_best_of_3": min(t1[1:]),
+                          "s_per_step_median_of_3": statistics.median(t1[1:])}
 
     if rank == 0:
         emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "global_pairs": B * world, "rows_per_gpu": rows,
+            "config": {"workload": WORKLOAD if not strong else
+                       (f"configs[2]: Janus-Pro-7B-shaped SimPO head, {B * world} pairs batch-sharded over {world} GPU(s) "
+                        f"({B} pairs x 576 tokens per GPU), bf16, head trainable, NCCL all-reduce of the head-weight "
+                        "gradients"),
+                       "pairs_per_gpu": B, "global_pairs": B * world, "rows_per_gpu": rows,
                        "H": H7B, "E": E7B, "V": V, "parallelism": f"dp{world}: pairs batch-sharded, NCCL all-reduce of "
                        "the flat fp32 head gradient (83.9M elements)" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (604 MB hidden states + 2.4 GB bf16 logits spill per step)",
                        "cta_group": _abi.load().ospo_head_set_cta_group(0), "loss": loss_val},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu, "frozen_head": frozen, "cfg": cfg, "clip_adamw": opt_res,
+            "cpu_baseline": cpu, "frozen_head": frozen, "cfg": cfg, "clip_adamw": opt_res, "dp_check": dp,
+            "memory": {"peak_bytes": mem_peak, "resident_before_step_bytes": mem_resident,
+                       "step_transient_bytes": mem_peak - mem_resident,
+                       "note": "torch.cuda.max_memory_allocated over the timed steps; resident = weights, inputs, "
+                               "reusable flat gradient buffer; the reference path materialises fp32 logits + fp32 "
+                               "log-softmax of [rows, V] (4.8 GB each at this size) plus autograd copies"},
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -459,7 +836,7 @@ def bench_clip_adamw(dev, peaks):
 
 def _decode_traffic():
     """dram bytes (read + write) of one decode-step launch from the committed ncu --set full capture, or None"""
-    tf = ROOT / "profiles" / "r01_kernel_traffic.json"
+    tf = ROOT / "profiles" / "kernel_traffic.json"
     try:
         t = json.loads(tf.read_text())["decode_merged"]
         return t["dram_bytes_read"] + t["dram_bytes_write"]
@@ -610,6 +987,45 @@ def bench_cfg(head, dev, peaks, with_cpu=False):
         result["with_gen_img_embeds"] = {"us_per_step": us_n1, "bytes_per_step": bytes_n1,
                                          "achieved_gbs": bytes_n1 / (us_n1 * 1e-6) / 1e9,
                                          "frac_of_hbm_peak": bytes_n1 / (us_n1 * 1e-6) / 1e9 / peaks["hbm"]}
+        # LATENCY of a truly sequential loop (image_generation.py:149-171: step i+1's hidden state depends on the id
+        # step i sampled).  With D == H the aligner output [2P, D] of step i IS the hidden state of step i+1 (it stands
+        # in for the backbone), so no kernel of step i+1 can consume anything before step i has produced it; the figure
+        # above (independent hidden states) is the pipelined cadence, this one the dependent-step latency.
+        emb_pp = [torch.empty(2 * P, H7B, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        ne_pp = [(*fused_embeds._params(), e) for e in emb_pp]
+
+        def run_steps_dep():
+            cur = h[0]
+            for i in range(steps):
+                w = p if (i & 1) == 0 else alt
+                ops.cfg_sample_impl(cur, w.w1, w.b1, w.w2, w.b2, 5.0, 1.0, u[i], False, 0, False, ids_out[i],
+                                    ne_pp[i & 1], packed[id(w)])
+                cur = emb_pp[i & 1]
+
+        run_steps_dep()
+        torch.cuda.synchronize()
+        s4 = torch.cuda.Stream()
+        s4.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s4):
+            run_steps_dep()
+        torch.cuda.current_stream().wait_stream(s4)
+        g4 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g4):
+            run_steps_dep()
+        g4.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            g4.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us_dep = e0.elapsed_time(e1) / 3 * 1e3 / steps
+        result["dependent_chain"] = {
+            "workload": "576 steps, each step's hidden state = the previous step's sampled-id embeddings "
+                        "(head -> merge+sample -> gen_embed -> gen_aligner -> next head): latency, not cadence",
+            "us_per_step_dependent": us_dep, "us_per_step_pipelined": us_n1, "bytes_per_step": bytes_n1,
+            "achieved_gbs": bytes_n1 / (us_dep * 1e-6) / 1e9,
+            "frac_of_hbm_peak": bytes_n1 / (us_dep * 1e-6) / 1e9 / peaks["hbm"]}
     except Exception as ex:
         result["with_gen_img_embeds"] = {"error": repr(ex)[:200]}
     # the 1B-shaped head (H = E = 2048, configs[0]'s shape): 75.6 MB of weights per step, four copies in rotation so

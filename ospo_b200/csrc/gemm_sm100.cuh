@@ -46,6 +46,8 @@ struct GemmDims {
   uint32_t* sync_ctr;
   int sync_tiles;
   int sync_stride;  // lock-step every this many tiles (short tiles need it less often)
+  int sync_kb;      // > 0: additional lock-step points inside a tile, every sync_kb k-blocks (very long K: the
+                    // clusters of a wave drift apart within one tile by more than L2 retains)
   // L2 eviction hints of the operand loads (kEvictNormal / kEvictFirst / kEvictLast): the operand whose panels are
   // re-used by later waves is kept (evict-last), the one that streams through once per wave goes first
   uint64_t a_hint, b_hint;
@@ -319,6 +321,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       trace_stamp(dims.trace_id, 2);
       int tile_no = 0;
       bool sync_wait = true;
+      uint32_t sync_idx = 0;  // lock-step points passed so far (the same sequence in every cluster of the full waves)
       for (int t = dom_first; t < dom_tiles; t += dom_stride, ++tile_no) {
         const TileCoord tc = tile_coord(t / ksplits, dom_nm, num_n, dims.group_m, dom_m0);
         if (!epi_tile_enabled<Epi>(ep, tc.m_blk)) continue;
@@ -326,14 +329,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         const int kb0 = (t % ksplits) * dims.kb_per_split;
         const int kb1 = min(num_kb, kb0 + dims.kb_per_split);
-        if (dims.sync_ctr != nullptr && is_leader && tile_no > 0 && tile_no < dims.sync_tiles &&
-            tile_no % dims.sync_stride == 0) {
-          // every cluster announces its tile_no-th tile and waits (at most ~40 us) for the others to get there; a
-          // cluster that ever times out (a straggler exists: SMs shared with another kernel) stops waiting for good,
-          // so the worst case costs one time-out per cluster and launch
+        // every cluster announces its next lock-step point and waits (at most ~40 us) for the others to get there; a
+        // cluster that ever times out (a straggler exists: SMs shared with another kernel) stops waiting for good,
+        // so the worst case costs one time-out per cluster and launch
+        auto lock_step = [&]() {
           atomicAdd(dims.sync_ctr, 1u);
+          ++sync_idx;
           if (sync_wait) {
-            const uint32_t want = static_cast<uint32_t>(tile_no / dims.sync_stride) * static_cast<uint32_t>(num_clusters);
+            const uint32_t want = sync_idx * static_cast<uint32_t>(num_clusters);
             const uint64_t t_start = globaltimer_ns();
             while (*reinterpret_cast<volatile uint32_t*>(dims.sync_ctr) < want) {
               if (globaltimer_ns() - t_start > 40000ull) {
@@ -342,11 +345,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
             }
           }
-        }
+        };
+        const bool sync_tile = dims.sync_ctr != nullptr && is_leader && tile_no < dims.sync_tiles;
+        if (sync_tile && tile_no > 0 && tile_no % dims.sync_stride == 0) lock_step();
         for (int kb = kb0; kb < kb1; ++kb) {
           uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const int k0 = kb * BK;
+          if (sync_tile && dims.sync_kb > 0 && kb > kb0 && (kb - kb0) % dims.sync_kb == 0) lock_step();
           if (prefetched > 0) {
             // stage already armed and its A tile in flight
             --prefetched;
@@ -646,6 +652,7 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   dims.sync_ctr = nullptr;
   dims.sync_tiles = 0;
   dims.sync_stride = 1;
+  dims.sync_kb = 0;
   if (sync_ctr != nullptr && !Cfg::CLUSTER_SPLIT && !dims.die_split && clusters >= 2 && num_tiles / clusters >= 2) {
     if (cudaMemsetAsync(sync_ctr, 0, sizeof(uint32_t), stream) != cudaSuccess) return -4;
     dims.sync_ctr = sync_ctr;
@@ -657,6 +664,17 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
     const int kb_per_tile = (num_kb + dims.k_splits - 1) / dims.k_splits;
     dims.sync_stride = stride_kb > 0 ? (stride_kb + kb_per_tile - 1) / kb_per_tile : 1;
     if (dims.sync_stride < 1) dims.sync_stride = 1;
+    // Tiles much longer than the 1152 k-blocks of configs[1]'s weight-gradient GEMMs (K = 73728 rows) are cut into
+    // segments of about that length: at 256 pairs per GPU (K = 294912) wgrad W2 read 122 GB instead of 4 x 12.8 GB
+    // with lock-step points at the tile starts only (profiles/r02_launches_256pairs_ncu.csv).
+    static const int seg_kb = [] {
+      const char* e = getenv("OSPO_HEAD_SYNC_SEG_KB");
+      return e ? atoi(e) : 1152;
+    }();
+    if (seg_kb > 0 && kb_per_tile > seg_kb + seg_kb / 2) {
+      const int nseg = (kb_per_tile + seg_kb / 2) / seg_kb;
+      dims.sync_kb = (kb_per_tile + nseg - 1) / nseg;
+    }
   }
 
   cudaLaunchConfig_t cfg = {};

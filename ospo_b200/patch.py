@@ -7,12 +7,13 @@
   ``FusedGenHead`` that shares its parameters.
 * ``patch_train_wrapper`` re-points ``JanusProTrainWrapper.concatenated_forward`` /
   ``get_batch_loss_metrics`` (ospo/wrapper/train.py:345-372, 399-445) at the fused path while keeping
-  their signatures and return values.
+  their signatures and return values, and ``preprocess_batch`` (:219-279) at a batched form of the VQ encode
+  (SURVEY §8f N2).
 """
 from __future__ import annotations
 
 import types
-from typing import Dict
+from typing import Dict, Optional
 
 import torch
 
@@ -44,15 +45,82 @@ def patch_model(model: torch.nn.Module, fuse_gen_img_embeds: bool = False) -> to
     return model
 
 
-def patch_train_wrapper(wrapper, image_span=None, process_group=None):
+def batched_preprocess_batch(self, batch, token_cache: Optional[dict] = None):
+    """``JanusProTrainWrapper.preprocess_batch`` (ospo/wrapper/train.py:219-279) with the per-sample work batched
+    (SURVEY §8f N2).  Same inputs, same output dictionary, same values:
+
+    * the reference VQ-encodes chosen and rejected images one at a time -- 2B batch-1 passes of the CNN encoder
+      (:246-261); here all 2B images go through ``gen_vision_model.encode`` in ONE ``[2B, 3, H, W]`` call and the
+      code indices (``output[2][2]``, vq_model.py:278-282) are split back per image;
+    * ``token_cache`` (a dict, e.g. one per dataset): the images of a dataset item never change, so its token ids are
+      kept under ``item_id`` after the first epoch and the encoder is skipped for cached items;
+    * the text prompts are embedded in one padded lookup instead of B lookups; padded positions are zero embeddings
+      with label -100 exactly as at :229-239;
+    * ``prepare_gen_img_embeds`` runs once on the ``[2B, T]`` ids instead of twice.
+    """
+    item_ids, text_tokens, chosen_image_tensors, rejected_image_tensors = batch
+    B = len(item_ids)
+    dev, dtype = self.device, self.model.dtype
+    # ---- text: one padded embedding lookup, zero rows on the padding (train.py:224-239)
+    lens = [int(t.shape[1]) for t in text_tokens]
+    max_len = max(lens)
+    ids = torch.zeros(B, max_len, dtype=torch.long, device=dev)
+    keep = torch.zeros(B, max_len, 1, dtype=dtype, device=dev)
+    for i, t in enumerate(text_tokens):
+        ids[i, :lens[i]] = t.reshape(-1).to(dev)
+        keep[i, :lens[i]] = 1
+    text_embeds = self.model.language_model.get_input_embeddings()(ids).to(dtype) * keep
+    text_labels = torch.full((B, max_len), -100, dtype=torch.long, device=dev)
+    # ---- images: one batched VQ encode for everything that is not cached (train.py:241-264)
+    vq = self.model.gen_vision_model
+    vq_dtype = next(vq.parameters()).dtype
+    tokens = [None] * (2 * B)                       # chosen 0..B-1, rejected B..2B-1
+    todo = []
+    for i in range(B):
+        hit = token_cache.get(item_ids[i]) if token_cache is not None else None
+        if hit is not None:
+            tokens[i], tokens[B + i] = hit[0].to(dev), hit[1].to(dev)
+        else:
+            todo.append(i)
+    if todo:
+        imgs = torch.cat([chosen_image_tensors[i] for i in todo] + [rejected_image_tensors[i] for i in todo], 0)
+        out = vq.encode(imgs.to(device=dev, dtype=vq_dtype))
+        codes = out[2][2].reshape(2 * len(todo), -1)
+        for j, i in enumerate(todo):
+            tokens[i], tokens[B + i] = codes[j], codes[len(todo) + j]
+            if token_cache is not None:
+                token_cache[item_ids[i]] = (codes[j].detach().clone(), codes[len(todo) + j].detach().clone())
+    all_tokens = torch.stack(tokens, 0)              # [2B, T]
+    img_embeds = self.model.prepare_gen_img_embeds(all_tokens).to(dev)
+    chosen_tok, rejected_tok = all_tokens[:B], all_tokens[B:]
+    pre = {"item_ids": item_ids}
+    pre["chosen_inputs_embeds"] = torch.cat([text_embeds, img_embeds[:B]], dim=1)
+    pre["chosen_attention_mask"] = torch.ones(pre["chosen_inputs_embeds"].shape[:2], dtype=torch.long)
+    pre["chosen_labels"] = torch.cat([text_labels, chosen_tok], dim=1)
+    pre["rejected_inputs_embeds"] = torch.cat([text_embeds, img_embeds[B:]], dim=1)
+    pre["rejected_attention_mask"] = torch.ones(pre["rejected_inputs_embeds"].shape[:2], dtype=torch.long)
+    pre["rejected_labels"] = torch.cat([text_labels, rejected_tok], dim=1)
+    return pre
+
+
+def patch_train_wrapper(wrapper, image_span=None, process_group=None, batch_vq_encode: bool = True,
+                        cache_image_tokens: bool = False):
     """``wrapper``: a JanusProTrainWrapper (or anything with .model.gen_head, .model.language_model.model,
-    .concatenated_inputs, the SimPO hyper-parameter attributes and .log/.log_dict)."""
+    .concatenated_inputs, the SimPO hyper-parameter attributes and .log/.log_dict).
+    ``batch_vq_encode``: re-point ``preprocess_batch`` at :func:`batched_preprocess_batch` (needs
+    ``.model.gen_vision_model``); ``cache_image_tokens`` additionally keeps every item's token ids after its first
+    encode (``wrapper.image_token_cache``)."""
     patch_model(wrapper.model)
+    if batch_vq_encode and hasattr(wrapper.model, "gen_vision_model"):
+        wrapper.image_token_cache = {} if cache_image_tokens else None
+        wrapper.preprocess_batch = types.MethodType(
+            lambda self, batch: batched_preprocess_batch(self, batch, self.image_token_cache), wrapper)
 
     def concatenated_forward(self, batch: Dict):
-        # train.py:345-372, with gen_head + get_batch_logps fused; the [S, L+T, V] logits are never built, so the
-        # two logits entries of the reference 5-tuple carry the per-sequence mean logit instead (what the
-        # reference reduces them to at :441-442).
+        # train.py:345-372, with gen_head + get_batch_logps fused.  The [S, L+T, V] logits are never built, so the
+        # two logits entries of the reference 5-tuple are None here; the only thing the reference does with them is
+        # the mean it logs at :441-442, which the fused get_batch_loss_metrics below reports from the kernel's own
+        # row sums (metrics["logits/chosen"], ["logits/rejected"]).
         concatenated_batch = self.concatenated_inputs(batch=batch)
         len_chosen = batch["chosen_labels"].shape[0]
         outputs = self.model.language_model.model(

@@ -187,3 +187,111 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(maxsplit=2)
     assert out[0] == "0" and int(out[1]) == _abi.workspace_bytes(73728, 4096, 4096, 16384, 128)
     assert "sm_100" in out[2]
+
+
+# ---------------------------------------------------------------------------------------------------
+# next row N2: batched VQ encode in the train-wrapper patch (ospo/wrapper/train.py:219-279)
+# ---------------------------------------------------------------------------------------------------
+def _serial_preprocess_batch(self, batch):
+    """literal restatement of JanusProTrainWrapper.preprocess_batch (ospo/wrapper/train.py:219-279): per-sample text
+    embedding with zero padding, one batch-1 VQ encode per image (:246-261), two prepare_gen_img_embeds calls"""
+    import torch
+
+    batch_size = len(batch[0])
+    item_ids, text_tokens, chosen_image_tensors, rejected_image_tensors = batch
+    embs = [self.model.language_model.get_input_embeddings()(t) for t in text_tokens]
+    max_seq_len = max(x.shape[1] for x in embs)
+    padded = torch.zeros(batch_size, max_seq_len, embs[0].size(-1), dtype=self.model.dtype, device=self.device)
+    labels = torch.full((batch_size, max_seq_len), -100, dtype=torch.long, device=self.device)
+    for i, e in enumerate(embs):
+        padded[i, :e.shape[1], :] = e
+    cl, rl = [], []
+    for c, r in zip(chosen_image_tensors, rejected_image_tensors):
+        cl.append(self.model.gen_vision_model.encode(c.to(self.device))[2][2])
+        rl.append(self.model.gen_vision_model.encode(r.to(self.device))[2][2])
+    ct, rt = torch.stack(cl, 0), torch.stack(rl, 0)
+    ce, re_ = self.model.prepare_gen_img_embeds(ct), self.model.prepare_gen_img_embeds(rt)
+    out = {"item_ids": item_ids}
+    out["chosen_inputs_embeds"] = torch.cat([padded, ce], dim=1)
+    out["chosen_attention_mask"] = torch.ones(out["chosen_inputs_embeds"].shape[:2], dtype=torch.long)
+    out["chosen_labels"] = torch.cat([labels, ct], dim=1)
+    out["rejected_inputs_embeds"] = torch.cat([padded, re_], dim=1)
+    out["rejected_attention_mask"] = torch.ones(out["rejected_inputs_embeds"].shape[:2], dtype=torch.long)
+    out["rejected_labels"] = torch.cat([labels, rt], dim=1)
+    return out
+
+
+def _reference_vq_model():
+    """the reference's own VQ tokenizer (janus/models/vq_model.py, torch only) when the reference tree is present,
+    else a stand-in with the same encode() contract: (quant, losses, (perplexity, min_encodings, indices))"""
+    import importlib.util
+    import os
+
+    import torch
+
+    path = "/root/reference/janus/models/vq_model.py"
+    if os.path.exists(path):
+        spec = importlib.util.spec_from_file_location("ref_vq_model", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        torch.manual_seed(3)
+        return mod.VQ_16().eval(), "reference VQ_16"
+
+    class StandIn(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, 2, 1), torch.nn.SiLU(), torch.nn.Conv2d(16, 8, 3, 8, 1))
+            self.codebook = torch.nn.Embedding(512, 8)
+
+        def encode(self, x):
+            z = self.enc(x).permute(0, 2, 3, 1).reshape(-1, 8)
+            idx = torch.cdist(z, self.codebook.weight).argmin(-1)
+            return None, None, (None, None, idx)
+
+    torch.manual_seed(3)
+    return StandIn().eval(), "stand-in"
+
+
+def test_batched_preprocess_batch_matches_the_serial_reference_loop():
+    """ids, embeddings and labels of the batched VQ encode equal the reference's serial batch-1 loop bit for bit (CPU,
+    fp32: the convolutions are evaluated per sample either way); the token cache returns the same ids without
+    calling the encoder again"""
+    import types
+
+    import torch
+
+    from ospo_b200.patch import batched_preprocess_batch
+
+    vq, which = _reference_vq_model()
+    torch.manual_seed(4)
+    model = torch.nn.Module()
+    model.language_model = torch.nn.Module()
+    emb = torch.nn.Embedding(100, 32)
+    model.language_model.get_input_embeddings = lambda: emb
+    model.gen_vision_model = vq
+    gen_embed = torch.nn.Embedding(16384, 32)
+    model.prepare_gen_img_embeds = lambda ids: gen_embed(ids)
+    model.dtype = torch.float32
+    w = types.SimpleNamespace(model=model, device=torch.device("cpu"))
+    B, S = 3, 64                                          # 64 x 64 images -> 4 x 4 = 16 tokens with the 16x encoder
+    g = torch.Generator().manual_seed(5)
+    batch = ([f"item{i}" for i in range(B)],
+             [torch.randint(0, 100, (1, n), generator=g) for n in (5, 9, 2)],
+             [torch.rand(1, 3, S, S, generator=g) * 2 - 1 for _ in range(B)],
+             [torch.rand(1, 3, S, S, generator=g) * 2 - 1 for _ in range(B)])
+    with torch.no_grad():
+        ref = _serial_preprocess_batch(w, batch)
+        cache = {}
+        got = batched_preprocess_batch(w, batch, cache)
+        calls = []
+        orig = vq.encode
+        vq.encode = lambda x: calls.append(x.shape) or orig(x)
+        again = batched_preprocess_batch(w, batch, cache)
+    assert not calls, f"{which}: cached items must not be re-encoded"
+    for out in (got, again):
+        assert out["item_ids"] == ref["item_ids"]
+        for k in ("chosen_labels", "rejected_labels", "chosen_attention_mask", "rejected_attention_mask"):
+            assert torch.equal(out[k], ref[k]), (which, k)
+        for k in ("chosen_inputs_embeds", "rejected_inputs_embeds"):
+            assert torch.equal(out[k], ref[k]), (which, k)
+    assert ref["chosen_labels"].shape[1] == 9 + (S // 16) ** 2

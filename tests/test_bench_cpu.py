@@ -35,7 +35,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
     # value = rows of the sample / time of one step
-    assert d["value"] == pytest.approx(4 * 2 * 576 / (d["ms_per_step"] / 1e3), rel=1e-9)
+    assert d["value"] == pytest.approx(8 * 2 * 576 / (d["ms_per_step"] / 1e3), rel=1e-9)
 
 
 def test_reference_arm_runs_on_rank_zero_only():

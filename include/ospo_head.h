@@ -21,6 +21,11 @@
  *   - Weights use the nn.Linear layout [out, in], row-major, bf16.  Biases are fp32.
  *   - x / hidden states: bf16 [rows, hidden] row-major contiguous, one row per image token whose label
  *     is not masked (the caller drops the label == -100 rows: they carry no work and no gradient).
+ *   - Devices and threads: a call works on the calling thread's CURRENT device (cudaGetDevice); all pointers and the
+ *     stream must belong to it.  Any number of sm_100 devices may be used from one process (the library keeps its
+ *     few pieces of state -- SM count, flag words, kernel attributes -- per device).  Calls on different devices or
+ *     streams may come from different threads; ospo_head_profile_* and the ospo_head_set_* / ospo_head_trace knobs are
+ *     process-wide and must not race with running calls.
  *   - Return value 0 = success, negative = ospo_head_status; no exception crosses this boundary.
  *   - Requires an sm_100a device: there is no fallback path.
  */

@@ -19,11 +19,23 @@ using namespace ospo;
 
 namespace {
 
-struct Runtime {
+// Per-device state.  The library may be called on any number of sm_100 devices from one process: everything that
+// lives on (or describes) a device -- SM count, the watchdog / trace symbols of every translation unit, the flag
+// pool of the decode kernel and the lock-step counters -- is kept per device ordinal and looked up with
+// cudaGetDevice() on every call.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
   bool ready = false;
   int status = OSPO_OK;
-  int device = -1;
   int num_sms = 0;
+  uint32_t* flag_pool = nullptr;
+  int flag_next = 0;
+  std::unordered_map<uint64_t, int> flag_slot;
+};
+DeviceState g_dev[kMaxDevices];
+
+struct Runtime {
+  bool ready = false;   // knobs parsed, host-side watchdog record allocated
   int cta_group = 2;
   int group_m = 16;
   int decode_fused = 1;  // CFG tail fused into the decode GEMM2 epilogue (0 = separate sampler pass)
@@ -41,8 +53,7 @@ struct Runtime {
   int decode_l2_ahead = 16;  // merged kernel: W2 k-blocks per CTA requested into L2 while the activation flag is closed
   bool trace_on = false;   // ospo_head_trace installed a timeline buffer
   unsigned long long* trace_buf = nullptr;
-  uint32_t* wd_host = nullptr;
-  uint32_t* wd_dev = nullptr;
+  uint32_t* wd_host = nullptr;  // mapped, portable host record written by a kernel whose bounded wait expired
 };
 Runtime g_rt;
 std::mutex g_mu;
@@ -84,18 +95,16 @@ struct KernelSpan {
   }
 };
 
-int runtime_init() {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_rt.ready) return g_rt.status;
-  g_rt.ready = true;
+// the calling thread's current device (its DeviceState is initialised by runtime_init)
+int current_device() {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return g_rt.status = OSPO_ERR_CUDA;
-  int major = 0, sms = 0;
-  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (major != 10) return g_rt.status = OSPO_ERR_ARCH;
-  g_rt.device = dev;
-  g_rt.num_sms = sms;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
+void parse_knobs_once() {
+  if (g_rt.ready) return;
+  g_rt.ready = true;
   if (const char* e = getenv("OSPO_HEAD_CTA_GROUP")) {
     const int v = atoi(e);
     if (v == 1 || v == 2) g_rt.cta_group = v;
@@ -115,20 +124,41 @@ int runtime_init() {
     const int v = atoi(e);
     if (v > 0) g_rt.group_m = v;
   }
-  if (cudaHostAlloc(reinterpret_cast<void**>(&g_rt.wd_host), 64 * sizeof(uint32_t), cudaHostAllocMapped) ==
-      cudaSuccess) {
+  if (cudaHostAlloc(reinterpret_cast<void**>(&g_rt.wd_host), 64 * sizeof(uint32_t),
+                    cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
     for (int i = 0; i < 64; ++i) g_rt.wd_host[i] = 0;
-    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_rt.wd_dev), g_rt.wd_host, 0) == cudaSuccess) {
-      set_watchdog_fwd(g_rt.wd_dev);
-      set_watchdog_bwd(g_rt.wd_dev);
-      set_watchdog_decode(g_rt.wd_dev);
-      set_watchdog_debug(g_rt.wd_dev);
-      set_watchdog_merged(g_rt.wd_dev);
-    }
+  } else {
+    g_rt.wd_host = nullptr;
+    cudaGetLastError();
+  }
+}
+
+int runtime_init() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int dev = current_device();
+  if (dev < 0) return OSPO_ERR_CUDA;
+  DeviceState& d = g_dev[dev];
+  if (d.ready) return d.status;
+  d.ready = true;
+  parse_knobs_once();
+  int major = 0, sms = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (major != 10) return d.status = OSPO_ERR_ARCH;
+  d.num_sms = sms;
+  // this device's copies of the watchdog symbols (one per translation unit) point at the mapped host record
+  uint32_t* wd_dev = nullptr;
+  if (g_rt.wd_host != nullptr &&
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&wd_dev), g_rt.wd_host, 0) == cudaSuccess) {
+    set_watchdog_fwd(wd_dev);
+    set_watchdog_bwd(wd_dev);
+    set_watchdog_decode(wd_dev);
+    set_watchdog_debug(wd_dev);
+    set_watchdog_merged(wd_dev);
   } else {
     cudaGetLastError();
   }
-  return g_rt.status = OSPO_OK;
+  return d.status = OSPO_OK;
 }
 
 // Flag words of the merged decode kernel (its device-wide "activations are published" flag).  The only device
@@ -137,12 +167,15 @@ int runtime_init() {
 // never overlaps itself), so two launches that may run concurrently never share a slot.  When the pool is
 // exhausted the caller falls back to the two-kernel chain.
 constexpr int kFlagSlots = 512, kFlagStride = 8;  // 32 bytes per slot
-uint32_t* g_flag_pool = nullptr;
-int g_flag_next = 0;
-std::unordered_map<uint64_t, int> g_flag_slot;
 
 uint32_t* flag_words_for(cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_mu);
+  const int dev = current_device();
+  if (dev < 0) return nullptr;
+  DeviceState& ds = g_dev[dev];
+  uint32_t*& g_flag_pool = ds.flag_pool;
+  int& g_flag_next = ds.flag_next;
+  std::unordered_map<uint64_t, int>& g_flag_slot = ds.flag_slot;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   unsigned long long cap_id = 0;
   if (cudaStreamGetCaptureInfo(st, &cs, &cap_id) != cudaSuccess) {
@@ -169,9 +202,15 @@ uint32_t* flag_words_for(cudaStream_t st) {
   return g_flag_pool + static_cast<size_t>(it->second) * kFlagStride;
 }
 
+int current_num_sms() {
+  const int dev = current_device();
+  return dev >= 0 ? g_dev[dev].num_sms : 0;
+}
+
 LaunchCtx make_ctx(cudaStream_t s) {
   LaunchCtx c;
-  c.num_sms = g_rt.num_sms;
+  const int dev = current_device();
+  c.num_sms = dev >= 0 ? g_dev[dev].num_sms : 0;
   c.cta_group = g_rt.cta_group;
   c.group_m = g_rt.group_m;
   c.stream = s;
@@ -491,8 +530,12 @@ template <int MODE, bool TDIV, bool GREEDY, bool WBF>
 bool run_sampler(int grid, cudaStream_t st, const __nv_bfloat16* lg, int V, const ospo_cfg_args* a, int pairs) {
   constexpr int kLanding = SAMPLE_THREADS * 8 * 16;  // 64 KB of dynamic shared memory: opt in once per instantiation
   auto kern = cfg_merge_sample_kernel<MODE, TDIV, GREEDY, WBF>;
-  static const cudaError_t attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kLanding);
-  if (attr_rc != cudaSuccess) return false;
+  static std::atomic<uint64_t> attr_set{0};  // per device ordinal
+  int attr_dev = 0;
+  if (func_attrs_needed(attr_set, &attr_dev)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kLanding) != cudaSuccess) return false;
+    func_attrs_mark(attr_set, attr_dev);
+  }
   kern<<<grid, GREEDY ? SAMPLE_THREADS : SAMPLE_BLOCK, kLanding, st>>>(lg, V, V, a->cfg_weight, a->temperature, a->uniforms, a->ids, a->merged,
                                                pairs);
   return true;
@@ -596,7 +639,7 @@ static int launch_sampler(const ospo_cfg_args* a, int pairs, cudaStream_t st) {
   // bf16 merge with a cfg_weight that is itself a bf16 value (5.0, 7.5, ...): merge on the bf16x2 pipe
   const bool wbf = (mode == 0) && bf16_exact(a->cfg_weight);
   // persistent blocks (two per SM), each with a 64 KB landing buffer for its next pair's rows
-  const int grid = std::min(pairs, 2 * g_rt.num_sms);
+  const int grid = std::min(pairs, 2 * current_num_sms());
   const int variant = (a->greedy ? 8 : 0) | (mode ? 4 : 0) | (tdiv ? 2 : 0) | (wbf ? 1 : 0);
   bool ok = false;
 #define OSPO_SAMPLER_CASE(MODE, TDIV, GREEDY, WBF)                                                             \
@@ -835,7 +878,7 @@ int ospo_head_grad_sqnorm(const float* grads, int64_t numel, float* out_sq, void
   if (!grads || !out_sq || !workspace) return OSPO_ERR_NULL;
   if (numel <= 0) return OSPO_ERR_BAD_SHAPE;
   if (!aligned16(grads)) return OSPO_ERR_ALIGNMENT;
-  const int blocks = g_rt.num_sms * 4;  // four resident blocks per SM keep every HBM channel busy
+  const int blocks = current_num_sms() * 4;  // four resident blocks per SM keep every HBM channel busy
   if (workspace_bytes < static_cast<size_t>(blocks) * sizeof(float)) return OSPO_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   KernelSpan ks(st, OSPO_K_OPTIMIZER);
@@ -872,7 +915,7 @@ int ospo_head_adamw_step(const ospo_adamw_args* a, ospo_stream_t stream) {
   h.max_norm = a->max_norm;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   KernelSpan ks(st, OSPO_K_OPTIMIZER);
-  const int blocks = g_rt.num_sms * 4;
+  const int blocks = current_num_sms() * 4;
   adamw_kernel<<<blocks, OPT_THREADS, 0, st>>>(a->grads, a->params, a->exp_avg, a->exp_avg_sq,
                                                static_cast<__nv_bfloat16*>(a->params_bf16),
                                                a->params_bf16 ? a->shadow_numel : 0, a->numel, a->total_sqnorm, h);

@@ -432,11 +432,12 @@ int run_linear(const LaunchCtx& c, const CUtensorMap& t_w, const CUtensorMap& t_
   using Epi = EpiCfgFused<MODE, TDIV, WBF, GREEDY>;
   typename Epi::Params p{};
   auto kern = decode_merged_kernel<MODE, TDIV, WBF, GREEDY>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};  // per device ordinal
+  int attr_dev = 0;
+  if (func_attrs_needed(attr_set, &attr_dev)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -3;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set = true;
+    func_attrs_mark(attr_set, attr_dev);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(d.num_m1 * d.ks), 1, 1);
@@ -466,12 +467,13 @@ int run_merged(const LaunchCtx& c, const CUtensorMap& t_w1, const CUtensorMap& t
   typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, d.V, buf, greedy, d.V};
   auto kern = decode_merged_kernel<MODE, TDIV, WBF, GREEDY>;
   g_last_variant = (GREEDY ? 8 : 0) + MODE * 4 + (TDIV ? 2 : 0) + (WBF ? 1 : 0);
-  static bool attr_set = false;
-  static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // by cluster size
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};  // per device ordinal
+  static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // by cluster size (the devices of a box are identical)
+  int attr_dev = 0;
+  if (func_attrs_needed(attr_set, &attr_dev)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -3;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set = true;
+    func_attrs_mark(attr_set, attr_dev);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(G), 1, 1);

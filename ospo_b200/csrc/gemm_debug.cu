@@ -105,10 +105,11 @@ static int run_probe(const LaunchCtx& c, const __nv_bfloat16* a, int64_t lda, fl
   if (rc != 0) return rc;
   auto kern = stream_probe_kernel<MODE>;
   const int smem = 1024 + kProbeStages * kProbeChunk + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};  // per device ordinal
+  int attr_dev = 0;
+  if (func_attrs_needed(attr_set, &attr_dev)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -3;
-    attr_set = true;
+    func_attrs_mark(attr_set, attr_dev);
   }
   const long long chunks = static_cast<long long>(M) * K * 2 / kProbeChunk;
   kern<<<ctas, 64, smem, c.stream>>>(tm, reinterpret_cast<const uint8_t*>(a), K / 64, chunks, out);

@@ -17,8 +17,10 @@
 //              take the left half of the tile's columns and warps 6-9 the right half).
 #pragma once
 
+#include <atomic>
 #include <cstdlib>
 
+#include "launchers.h"
 #include "ptx.cuh"
 
 namespace ospo {
@@ -614,13 +616,15 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   if (rc != 0) return rc;
 
   auto kern = gemm_kernel<Cfg, Epi>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  // function attributes are per device: one bit per device ordinal and instantiation
+  static std::atomic<uint64_t> attr_set{0};
+  int dev = 0;
+  if (func_attrs_needed(attr_set, &dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return -3;
     // whole L1/shared array as shared memory: lets two kernels of a dependent-launch chain share an SM
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set = true;
+    func_attrs_mark(attr_set, dev);
   }
   GemmDims dims;
   dims.M = M;

@@ -3,6 +3,8 @@
 // cta_group: 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile (tcgen05 cta_group::2).
 #pragma once
 
+#include <atomic>
+
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,6 +24,17 @@ struct LaunchCtx {
 };
 
 struct CfgFusedBuffers;
+
+// cudaFuncSetAttribute is per device: `mask` (one static per kernel instantiation) has one bit per device ordinal.
+// Returns true when the calling thread's current device still needs the attributes set; call mark afterwards.
+inline bool func_attrs_needed(std::atomic<uint64_t>& mask, int* dev_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  *dev_out = dev;
+  return !(mask.load(std::memory_order_acquire) & (1ull << dev));
+}
+inline void func_attrs_mark(std::atomic<uint64_t>& mask, int dev) { mask.fetch_or(1ull << dev, std::memory_order_release); }
+
 
 // Row-segmented hidden states: x / dx are [segments, seg_pitch, H] tensors of which rows [seg_off, seg_off +
 // seg_rows) of every segment are the head's rows (seg_rows == 0: plain contiguous [rows, H]).

@@ -197,6 +197,20 @@ class FusedGenHead(torch.nn.Module):
         self._flat: Optional[torch.Tensor] = None
         self._packed = None
         self._packed_key = None
+        self._bwd_count = 0      # fused backward passes since the flat gradient buffer was last consumed / zeroed
+
+    def invalidate(self) -> None:
+        """drop the staged kernel operands (bf16 weights, fp32 biases, packed decode weights).  The cache is keyed on
+        the parameters' (data_ptr, _version); call this after an update that changes neither -- writes through
+        ``.data`` or through views of a flat buffer (apex / DeepSpeed-style optimizers)."""
+        self._cache_key = None
+        self._cache = None
+        self._packed = None
+        self._packed_key = None
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        super().zero_grad(set_to_none=set_to_none)
+        self._bwd_count = 0
 
     # ---- construction helpers -------------------------------------------------------------------
     @classmethod
@@ -222,7 +236,9 @@ class FusedGenHead(torch.nn.Module):
         if key != self._cache_key:
             if not W1.is_cuda:
                 raise _abi.OspoHeadError("FusedGenHead parameters must live on a B200 (no CPU path): call .cuda()")
-            with torch.no_grad():
+            # outside inference mode: a cache first built under @torch.inference_mode() (the reference's generate_image,
+            # image_generation.py:109) would hold inference tensors, which a later training call cannot save for backward
+            with torch.inference_mode(False), torch.no_grad():
                 self._cache = _HeadParams(
                     W1.detach().to(torch.bfloat16).contiguous(), B1.detach().to(torch.float32).contiguous(),
                     W2.detach().to(torch.bfloat16).contiguous(), B2.detach().to(torch.float32).contiguous())
@@ -253,6 +269,8 @@ class FusedGenHead(torch.nn.Module):
         all-reduce after the backward; OSPO_HEAD_OVERLAP_SMS > 0 leaves that many SMs free for the collective --
         measured neutral at N = 2 and N = 8, so the default is 0)."""
         world = _dist._world(group) if group is not None else 1
+        if need_dw:
+            self._bwd_count += 1     # FusedHeadAdamW.step(use_last_backward=True) needs exactly one since the last step
         if not need_dw or world == 1 or os.environ.get("OSPO_HEAD_OVERLAP", "1") == "0":
             dx = bwd(0, 0, None)
             if need_dw:
@@ -401,11 +419,15 @@ class FusedGenImgEmbeds:
         self.gen_embed, self.lin_a, self.lin_b = gen_embed, layers[0], layers[2]
         self._key, self._staged = None, None
 
+    def invalidate(self) -> None:
+        """drop the staged operands (see FusedGenHead.invalidate)"""
+        self._key, self._staged = None, None
+
     def _params(self):
         ts = (self.gen_embed.weight, self.lin_a.weight, self.lin_a.bias, self.lin_b.weight, self.lin_b.bias)
         key = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in ts)
         if key != self._key:
-            with torch.no_grad():
+            with torch.inference_mode(False), torch.no_grad():
                 e, wa, ba, wb, bb = ts
                 self._staged = (e.detach().to(torch.bfloat16).contiguous(), wa.detach().to(torch.bfloat16).contiguous(),
                                 ba.detach().to(torch.float32).contiguous(), wb.detach().to(torch.bfloat16).contiguous(),

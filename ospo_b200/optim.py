@@ -76,8 +76,12 @@ class FusedHeadAdamW:
     def _flat_grads(self, use_last_backward: bool) -> torch.Tensor:
         H, E, V = self._dims
         head = self.head
-        if use_last_backward and head._flat is not None:
-            return head._flat          # the fused backward's own buffer (already all-reduced): no gather
+        # The fused backward's own buffer holds ONE micro-batch's gradient (already all-reduced).  It is the gradient of
+        # the step only when exactly one fused backward ran since the last step; with gradient accumulation
+        # (accumulate_grad_batches > 1, ospo/utils/train.py:31,51) autograd has summed the micro-batches into .grad, and
+        # that sum is gathered instead.
+        if use_last_backward and head._flat is not None and head._bwd_count == 1:
+            return head._flat
         if self._grads is None:
             self._grads = torch.empty_like(self.params)
         views = ops.split_flat_grads(self._grads, H, E, V)
@@ -92,10 +96,12 @@ class FusedHeadAdamW:
     @torch.no_grad()
     def step(self, other_sqnorm: Optional[torch.Tensor] = None, use_last_backward: bool = False,
              lr: Optional[float] = None) -> None:
-        """one optimizer step.  ``use_last_backward`` reads the flat buffer the last fused backward wrote (valid
-        without gradient accumulation); otherwise the parameters' ``.grad`` are gathered.  ``lr`` overrides the
+        """one optimizer step.  ``use_last_backward`` reads the flat buffer the last fused backward wrote when exactly
+        one fused backward ran since the previous step (no gather); after several micro-batches (gradient
+        accumulation) or without the flag the parameters' accumulated ``.grad`` are gathered.  ``lr`` overrides the
         learning rate for this step (schedulers)."""
         g = self._flat_grads(use_last_backward)
+        self.head._bwd_count = 0
         total = None
         if self.max_norm > 0:
             total = ops.grad_sqnorm_impl(g)
@@ -117,10 +123,12 @@ class FusedHeadAdamW:
 
     # ---- checkpoint / resume (Lightning saves optimizer_states next to the model's state_dict) ----------------
     def state_dict(self) -> dict:
-        """step count, both moments (flat, fp32) and the hyper-parameters; the parameters themselves are saved by
-        the module's own ``state_dict`` (they are views of ``self.params``)"""
+        """step count, both moments and the fp32 MASTER parameters (flat), and the hyper-parameters.  The master copy
+        is part of the state: with bf16 module parameters the module's own ``state_dict`` only holds their bf16
+        rounding, and a resume from that alone would not continue the same trajectory."""
         return {"step": self.step_count, "exp_avg": self.exp_avg.detach().clone(),
-                "exp_avg_sq": self.exp_avg_sq.detach().clone(), "layout": "W2|W1|b2|b1", "dims": self._dims,
+                "exp_avg_sq": self.exp_avg_sq.detach().clone(), "params": self.params.detach().clone(),
+                "layout": "W2|W1|b2|b1", "dims": self._dims,
                 "hyper": {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
                           "max_norm": self.max_norm}}
 
@@ -135,7 +143,22 @@ class FusedHeadAdamW:
         self.lr, self.betas = h.get("lr", self.lr), tuple(h.get("betas", self.betas))
         self.eps, self.weight_decay = h.get("eps", self.eps), h.get("weight_decay", self.weight_decay)
         self.max_norm = h.get("max_norm", self.max_norm)
-        self.resync_from_module()
+        if "params" in state:
+            # exact resume: restore the fp32 masters, then push them into the module (views need nothing; parameters
+            # that are not views -- e.g. bf16 biases -- get a copy) and refresh the bf16 GEMM operands
+            self.params.copy_(state["params"].to(self.params.device, torch.float32))
+            H, E, V = self._dims
+            head = self.head
+            views = ops.split_flat_grads(self.params, H, E, V)
+            self.shadow[:V * E].view(V, E).copy_(views[0])
+            self.shadow[V * E:].view(E, H).copy_(views[1])
+            for v, p in zip(views, (head.vision_head.weight, head.output_mlp_projector.weight, head.vision_head.bias,
+                                    head.output_mlp_projector.bias)):
+                if p.data_ptr() != v.data_ptr() and not (p.dtype == torch.bfloat16 and p.dim() == 2):
+                    p.data.copy_(v)
+            self._install_operands()
+        else:
+            self.resync_from_module()   # older checkpoints: rebuild the masters from the module's parameters
 
     @torch.no_grad()
     def resync_from_module(self) -> None:
@@ -153,6 +176,7 @@ class FusedHeadAdamW:
         self._install_operands()
 
     def zero_grad(self, set_to_none: bool = True) -> None:
+        self.head._bwd_count = 0
         for p in self.head.parameters():
             if set_to_none:
                 p.grad = None

@@ -1322,6 +1322,81 @@ def test_fused_head_adamw_tracks_torch_adamw():
     assert torch.equal(p.w1, fh.output_mlp_projector.weight.detach().to(torch.bfloat16))
 
 
+
+def test_fused_head_adamw_gradient_accumulation_and_bf16_resume():
+    """(1) two micro-batches before one optimizer step (accumulate_grad_batches = 2, ospo/utils/train.py:31,51):
+    ``step(use_last_backward=True)`` must not take the flat buffer of the LAST micro-batch alone -- it has to use the
+    accumulated .grad, i.e. give the same parameters as ``use_last_backward=False``.  (2) bf16 module parameters: the
+    optimizer's state_dict carries the fp32 masters, so a resumed optimizer continues bit-identically."""
+    from ospo_b200 import FusedHeadAdamW
+
+    dev = _cuda()
+    H, E, V, B, T = 128, 192, 16384, 2, 64
+    head_f = O.make_head(H, E, V, seed=43)
+    heads = [_fused_from(head_f, dev, dtype=torch.bfloat16, requires_grad=True) for _ in range(2)]
+    opts = [FusedHeadAdamW(h, lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.01, max_norm=1.0) for h in heads]
+    batches = []
+    for i in range(2):
+        hc, hr, lc, lr_ = O.synthetic_simpo_batch(B, T, 5, H, V, seed=50 + i)
+        batches.append((torch.cat([hc, hr]).to(dev).to(torch.bfloat16), torch.cat([lc, lr_]).to(dev)))
+    for fh, opt, flag in zip(heads, opts, (True, False)):
+        for hidden, labels in batches:                      # two backward passes accumulate into .grad
+            (fh.simpo(hidden, labels, beta=5.0, gamma_beta_ratio=0.25).loss / 2).backward()
+        assert fh._bwd_count == 2
+        opt.step(use_last_backward=flag)
+        opt.zero_grad()
+    torch.cuda.synchronize()
+    assert torch.equal(opts[0].params, opts[1].params)
+    # a single backward since the last step: the flat buffer IS the step's gradient (up to the bf16 rounding of .grad)
+    hidden, labels = batches[0]
+    for fh, opt, flag in zip(heads, opts, (True, False)):
+        fh.simpo(hidden, labels, beta=5.0, gamma_beta_ratio=0.25).loss.backward()
+        assert fh._bwd_count == 1
+        opt.step(use_last_backward=flag)
+        opt.zero_grad()
+    torch.testing.assert_close(opts[0].params, opts[1].params, rtol=1e-2, atol=1e-4)
+    # resume with bf16 parameters: masters come from the optimizer state, not from the rounded module weights
+    fh, opt = heads[0], opts[0]
+    sd_model, sd_opt = {k: v.detach().clone() for k, v in fh.state_dict().items()}, opt.state_dict()
+    assert "params" in sd_opt and sd_opt["params"].dtype == torch.float32
+    fh2 = _fused_from(head_f, dev, dtype=torch.bfloat16, requires_grad=True)
+    opt2 = FusedHeadAdamW(fh2, lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.01, max_norm=1.0)
+    fh2.load_state_dict(sd_model, strict=True)
+    opt2.load_state_dict(sd_opt)
+    assert torch.equal(opt2.params, opt.params) and torch.equal(opt2.shadow, opt.shadow)
+    for f_, o_ in ((fh, opt), (fh2, opt2)):
+        f_.simpo(hidden, labels, beta=5.0, gamma_beta_ratio=0.25).loss.backward()
+        o_.step(use_last_backward=True)
+        o_.zero_grad()
+    torch.cuda.synchronize()
+    assert torch.equal(opt2.params, opt.params) and torch.equal(fh2.vision_head.weight, fh.vision_head.weight)
+
+
+def test_kernel_operand_cache_survives_inference_mode_and_invalidate():
+    """the staged bf16 / fp32 operands are built outside inference mode (the reference's generate_image runs under
+    @torch.inference_mode(), image_generation.py:109), so a later training call can save them for backward; and
+    ``invalidate()`` refreshes them after an in-place ``.data`` update that changes neither data_ptr nor version"""
+    dev = _cuda()
+    H, E, V = 128, 128, 16384
+    head_f = O.make_head(H, E, V, seed=44)
+    fh = _fused_from(head_f, dev, dtype=torch.float32, requires_grad=True)     # fp32 params: staging makes copies
+    g = torch.Generator().manual_seed(45)
+    h = torch.randn(4, H, generator=g).to(torch.bfloat16).to(dev)
+    with torch.inference_mode():
+        ids0 = fh.cfg_sample(h, 5.0, 1.0, greedy=True)
+    hc, hr, lc, lr_ = O.synthetic_simpo_batch(2, 64, 3, H, V, seed=46)
+    hidden, labels = torch.cat([hc, hr]).to(dev).to(torch.bfloat16), torch.cat([lc, lr_]).to(dev)
+    out = fh.simpo(hidden, labels, beta=5.0, gamma_beta_ratio=0.25)           # used to fail in save_for_backward
+    out.loss.backward()
+    assert fh.vision_head.weight.grad is not None
+    loss0 = float(out.loss.detach())
+    fh.vision_head.weight.data.mul_(0.5)                                       # neither data_ptr nor _version changes
+    stale = float(fh.simpo(hidden, labels, beta=5.0, gamma_beta_ratio=0.25).loss.detach())
+    fh.invalidate()
+    fresh = float(fh.simpo(hidden, labels, beta=5.0, gamma_beta_ratio=0.25).loss.detach())
+    assert stale == loss0 and fresh != loss0
+    assert ids0.shape == (2,)
+
 @pytest.mark.parametrize("parts", ["1", "3"])
 def test_staged_backward_equals_single_call(monkeypatch, parts):
     """the staged backward used to overlap the all-reduces (part 1 up to dW2, then db1 + dW1 + dX together or as
@@ -1401,3 +1476,34 @@ def test_nccl_gradient_exchange_values(shape, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(out.read_text())
     assert res["ok"] and res["ok_all_ranks"], res
+
+
+def test_two_devices_in_one_process():
+    """the library keeps its state per device: after a first use on cuda:0, a SimPO step and a decode step on cuda:1
+    (same process, same thread) give bit-identical results (round 1 bound the SM count, flag pool, watchdog symbol and
+    kernel attributes to the first device used)"""
+    _cuda()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs on the box")
+    H, E, V, B, T, L = 256, 256, 16384, 2, 64, 2
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, loss_type="sigmoid")
+    head_b = O.make_head(H, E, V, seed=81, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=82, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(83)
+    h = torch.randn(8, H, generator=g).to(torch.bfloat16)
+    u = torch.rand(4, generator=g)
+    res = []
+    for d in (0, 1, 0):
+        dev = torch.device("cuda", d)
+        with torch.cuda.device(dev):
+            fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+            x = torch.cat([hc, hr]).to(dev).requires_grad_(True)
+            out = fh.simpo(x, torch.cat([lc, lr]).to(dev), image_span=(L - 1, L - 1 + T), **hp)
+            out.loss.backward()
+            ids = fh.cfg_sample(h.to(dev), 5.0, 1.0, uniforms=u.to(dev))
+            torch.cuda.synchronize(dev)
+            res.append((out.loss.detach().cpu(), x.grad.cpu(), fh.vision_head.weight.grad.cpu(),
+                        fh.vision_head.bias.grad.cpu(), ids.cpu()))
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert torch.equal(a, b)

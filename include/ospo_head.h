@@ -183,6 +183,12 @@ typedef struct {
   int32_t id_repeat;        /* 0 / 1: ids has n entries.  r > 1: ids has n / r entries and entry i feeds rows
                                [i*r, (i+1)*r) -- r = 2 is the cond/uncond duplication of image_generation.py:166,
                                so the sampler's ids[P] can be passed as they are */
+  const void* table;        /* optional bf16 [codebook, D]: table[id] = gen_aligner(gen_embed(id)) for EVERY code, built
+                               once by the caller with this same entry point (the module is a pure function of the
+                               id and generation runs with frozen weights).  When given, out rows are copied from it:
+                               no weight is streamed and, behind ospo_head_cfg_sample, no extra kernel runs (the
+                               sampler's finish kernel writes the rows).  wa / ba / wb / bb / workspace may then be
+                               NULL.  The caller rebuilds the table when the aligner's weights change. */
 } ospo_aligner_args;
 
 /* ---- CFG decode step ---------------------------------------------------------------------- */

@@ -123,6 +123,7 @@ class AlignerArgs(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
         ("id_repeat", C.c_int32),
+        ("table", C.c_void_p),
     ]
 
 

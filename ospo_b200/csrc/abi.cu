@@ -51,6 +51,7 @@ struct Runtime {
   // the same wave have read it), so they stay off.
   int tune[6][3] = {{8, 0, 0}, {16, 0, 0}, {8, 0, 0}, {8, 0, 0}, {8, 0, 0}, {8, 0, 0}};
   int decode_l2_ahead = 16;  // merged kernel: W2 k-blocks per CTA requested into L2 while the activation flag is closed
+  int decode_next_prefetch = 1;  // merged kernel: the aligner Linear's weight is requested into L2 behind the last W2 tile
   bool trace_on = false;   // ospo_head_trace installed a timeline buffer
   unsigned long long* trace_buf = nullptr;
   uint32_t* wd_host = nullptr;  // mapped, portable host record written by a kernel whose bounded wait expired
@@ -115,6 +116,7 @@ void parse_knobs_once() {
   if (const char* e = getenv("OSPO_HEAD_TILE_SYNC")) g_rt.tile_sync = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_MERGED")) g_rt.decode_merged = atoi(e) != 0;
   if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);
+  if (const char* e = getenv("OSPO_HEAD_DECODE_NEXT_PREFETCH")) g_rt.decode_next_prefetch = atoi(e) != 0;
   for (int k = 0; k < 6; ++k) {
     char name[32];
     snprintf(name, sizeof(name), "OSPO_HEAD_TUNE_%d", k);
@@ -678,7 +680,8 @@ int ospo_head_cfg_merge_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
 
 // the decode step proper; `eu` (may be off) is the first aligner layer folded into the finish kernel, *eu_done tells
 // the caller whether the variant that ran has done it
-static int cfg_sample_step(const ospo_cfg_args* a, ospo_stream_t stream, const EmbedUp& eu, bool* eu_done) {
+static int cfg_sample_step(const ospo_cfg_args* a, ospo_stream_t stream, const EmbedUp& eu, bool* eu_done,
+                           const ospo_aligner_args* ne) {
   int rc;
   *eu_done = false;
   if ((rc = check_shape(a->shape, false))) return rc;
@@ -707,7 +710,9 @@ static int cfg_sample_step(const ospo_cfg_args* a, ospo_stream_t stream, const E
                                  a->w.b1, static_cast<const __nv_bfloat16*>(a->w.w2), a->w.b2, w.rows_by_e, flag,
                                  static_cast<__nv_bfloat16*>(a->logits), s.rows, s.hidden, s.embed, s.vocab,
                                  a->cfg_weight, a->temperature, a->merge_mode == OSPO_MERGE_FP32 ? 1 : 0, a->greedy,
-                                 w.fused, g_rt.decode_l2_ahead, a->w1_packed, a->w2_packed);
+                                 w.fused, g_rt.decode_l2_ahead, a->w1_packed, a->w2_packed,
+                                 (ne && g_rt.decode_next_prefetch) ? static_cast<const __nv_bfloat16*>(ne->wb) : nullptr,
+                                 ne ? ne->embed : 0, ne ? ne->embed : 0);
     }
     if (lrc == 0) {
       g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -782,6 +787,13 @@ static int check_aligner(const ospo_aligner_args* a, bool need_ids) {
   if (a->rows <= 0 || a->embed <= 0 || a->codebook <= 0) return OSPO_ERR_BAD_SHAPE;
   if (a->code_dim != 8 || a->rows > 32) return OSPO_ERR_UNSUPPORTED;
   if (a->embed % 8) return OSPO_ERR_ALIGNMENT;
+  if (a->table != nullptr) {
+    // memo-table form: only ids, table and out are used
+    if ((need_ids && !a->ids) || !a->out) return OSPO_ERR_NULL;
+    if (!aligned16(a->table) || !aligned16(a->out)) return OSPO_ERR_ALIGNMENT;
+    const int rep_t = a->id_repeat > 1 ? a->id_repeat : 1;
+    return (a->rows % rep_t) ? OSPO_ERR_BAD_SHAPE : OSPO_OK;
+  }
   if ((need_ids && !a->ids) || !a->gen_embed || !a->wa || !a->ba || !a->wb || !a->bb || !a->out || !a->workspace)
     return OSPO_ERR_NULL;
   if (!aligned16(a->gen_embed) || !aligned16(a->wa) || !aligned16(a->wb) || !aligned16(a->out) ||
@@ -809,17 +821,24 @@ int ospo_head_cfg_sample(const ospo_cfg_args* a, ospo_stream_t stream) {
   if (!a) return OSPO_ERR_NULL;
   int rc = runtime_init();
   if (rc) return rc;
-  EmbedUp eu = {nullptr, nullptr, nullptr, nullptr, 0, 0};
+  EmbedUp eu = {nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr};
   const ospo_aligner_args* ne = a->next_embeds;
   if (ne != nullptr) {
     if ((rc = check_aligner(ne, false))) return rc;
     if (ne->rows != a->shape.rows || ne->id_repeat != 2) return OSPO_ERR_BAD_SHAPE;
-    eu = EmbedUp{static_cast<const __nv_bfloat16*>(ne->gen_embed), static_cast<const __nv_bfloat16*>(ne->wa), ne->ba,
-                 static_cast<__nv_bfloat16*>(ne->workspace), ne->codebook, ne->embed};
+    if (ne->table != nullptr) {
+      // the finish kernel copies the pair's rows of the memo table straight into `out`: nothing else runs
+      eu = EmbedUp{static_cast<const __nv_bfloat16*>(ne->table), nullptr, nullptr, static_cast<__nv_bfloat16*>(ne->out),
+                   ne->codebook, ne->embed, static_cast<const __nv_bfloat16*>(ne->table)};
+    } else {
+      eu = EmbedUp{static_cast<const __nv_bfloat16*>(ne->gen_embed), static_cast<const __nv_bfloat16*>(ne->wa), ne->ba,
+                   static_cast<__nv_bfloat16*>(ne->workspace), ne->codebook, ne->embed, nullptr};
+    }
   }
   bool eu_done = false;
-  if ((rc = cfg_sample_step(a, stream, eu, &eu_done))) return rc;
+  if ((rc = cfg_sample_step(a, stream, eu, &eu_done, (ne && ne->table) ? nullptr : ne))) return rc;
   if (ne == nullptr) return OSPO_OK;
+  if (eu_done && ne->table != nullptr) return OSPO_OK;
   if (!eu_done) {
     // this decode variant has no finish kernel: run the stand-alone embedding path on the sampled ids
     ospo_aligner_args full = *ne;
@@ -842,6 +861,14 @@ int ospo_head_gen_img_embeds(const ospo_aligner_args* a, ospo_stream_t stream) {
   LaunchCtx c = make_ctx(st);
   c.pdl = g_rt.decode_pdl != 0;
   KernelSpan ks(st, OSPO_K_ALIGNER);
+  if (a->table != nullptr) {
+    if (launch_plain(embed_table_gather_kernel, dim3(a->rows), dim3(256), st, c.pdl, a->ids,
+                     static_cast<const __nv_bfloat16*>(a->table), a->codebook, static_cast<__nv_bfloat16*>(a->out),
+                     a->rows, a->embed, rep) != cudaSuccess)
+      return OSPO_ERR_LAUNCH;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return OSPO_OK;
+  }
   __nv_bfloat16* a1 = static_cast<__nv_bfloat16*>(a->workspace);
   if (launch_plain(gen_embed_up_kernel, dim3((a->embed + 255) / 256, a->rows), dim3(256), st, c.pdl, a->ids,
                    static_cast<const __nv_bfloat16*>(a->gen_embed), a->codebook,

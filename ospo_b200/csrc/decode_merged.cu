@@ -63,6 +63,10 @@ struct MergedDims {
                         // (same box: 33.7 -> 31.7 us per step)
   uint64_t pf_hint;     // L2 cache policy of the run-ahead prefetch
   int l2_ahead;         // W2 tiles per CTA requested into L2 while the activation flag is closed (0 = off)
+  int next_slabs;       // > 0: the weight of the NEXT kernel of the chain (gen_aligner's D x D Linear, tmap_next) is
+  int next_kb;          //   requested into L2 -- next_slabs x next_kb tiles of 16 KB spread over the CTAs -- right behind
+                        //   this CTA's last W2 tile, so HBM keeps streaming through the epilogue, the finish kernel and
+                        //   the kernel boundary, and the Linear then reads its weight at L2 speed
   unsigned long long* trace;  // timeline buffer [8][160][8] or null (a kernel parameter: stamps cost one store)
 };
 
@@ -88,7 +92,8 @@ template <int MODE, bool TDIV, bool WBF, bool GREEDY>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_h,
                      const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_act,
-                     MergedDims d, typename EpiCfgFused<MODE, TDIV, WBF, GREEDY>::Params ep) {
+                     const __grid_constant__ CUtensorMap tmap_next, MergedDims d,
+                     typename EpiCfgFused<MODE, TDIV, WBF, GREEDY>::Params ep) {
   using Epi = EpiCfgFused<MODE, TDIV, WBF, GREEDY>;
   constexpr int tr2 = 2;
   const int tr1 = d.linear_only ? 6 : 1, trp = d.linear_only ? 7 : 3;  // timeline rows (ospo_head_trace)
@@ -128,6 +133,7 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
     tma_prefetch_desc(&tmap_h);
     tma_prefetch_desc(&tmap_w2);
     tma_prefetch_desc(&tmap_act);
+    if (d.next_slabs > 0) tma_prefetch_desc(&tmap_next);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -215,6 +221,13 @@ decode_merged_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_c
             for (int j = 0; j < nb; ++j) tma_prefetch_l2_2d(&tmap_w2, k + j * kBK, row);
           }
         }
+      }
+      if (d.next_slabs > 0) {
+        // every weight tile of this step has been requested: queue the next kernel's weight behind them
+        const int tiles = d.next_slabs * d.next_kb;
+#pragma unroll 1
+        for (int t = static_cast<int>(blockIdx.x); t < tiles; t += G)
+          tma_prefetch_l2_2d(&tmap_next, (t % d.next_kb) * kBK, (t / d.next_kb) * kBM);
       }
       stamp(d.trace, tr2, 3);
     }
@@ -456,12 +469,13 @@ int run_linear(const LaunchCtx& c, const CUtensorMap& t_w, const CUtensorMap& t_
     attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  return cudaLaunchKernelEx(&cfg, kern, t_w, t_x, t_w, t_x, d, p) == cudaSuccess ? 0 : -4;
+  return cudaLaunchKernelEx(&cfg, kern, t_w, t_x, t_w, t_x, t_w, d, p) == cudaSuccess ? 0 : -4;
 }
 
 template <int MODE, bool TDIV, bool WBF, bool GREEDY>
 int run_merged(const LaunchCtx& c, const CUtensorMap& t_w1, const CUtensorMap& t_h, const CUtensorMap& t_w2,
-               const CUtensorMap& t_act, const MergedDims& d, int G, const float* b2, __nv_bfloat16* logits_dump,
+               const CUtensorMap& t_act, const CUtensorMap& t_next, const MergedDims& d, int G, const float* b2,
+               __nv_bfloat16* logits_dump,
                float cfg_weight, float temperature, int greedy, const CfgFusedBuffers& buf) {
   using Epi = EpiCfgFused<MODE, TDIV, WBF, GREEDY>;
   typename Epi::Params p{b2, cfg_weight, temperature, logits_dump, d.V, buf, greedy, d.V};
@@ -507,7 +521,7 @@ int run_merged(const LaunchCtx& c, const CUtensorMap& t_w1, const CUtensorMap& t
   attrs[cfg.numAttrs].id = cudaLaunchAttributeCooperative;
   attrs[cfg.numAttrs].val.cooperative = 1;
   ++cfg.numAttrs;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, t_w1, t_h, t_w2, t_act, d, p);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, t_w1, t_h, t_w2, t_act, t_next, d, p);
   if (e == cudaErrorCooperativeLaunchTooLarge) {
     cudaGetLastError();
     return -100;  // the caller uses the two-GEMM chain
@@ -545,6 +559,8 @@ int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_
   d.linear_only = 1;
   d.gelu = gelu;
   d.l2_ahead = 0;
+  d.next_slabs = 0;
+  d.next_kb = 0;
   d.w_hint = kEvictFirst;
   d.pf_hint = kEvictNormal;
   CUtensorMap t_w, t_x;
@@ -573,7 +589,8 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
                          const __nv_bfloat16* w2, const float* b2, __nv_bfloat16* act, uint32_t* flag,
                          __nv_bfloat16* logits_dump, int n, int H, int E, int V, float cfg_weight, float temperature,
                          int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead, const void* w1_packed,
-                         const void* w2_packed) {
+                         const void* w2_packed, const __nv_bfloat16* next_w, int next_rows, int next_cols,
+                         int* grid_ctas) {
   if (n < 2 || n > kBN || flag == nullptr) return -100;
   MergedDims d;
   d.n = n;
@@ -605,6 +622,14 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
   if ((rc = make_tmap_bf16_2d(&t_h, h, n, H, H, kBN)) != 0) return rc;
   if ((rc = make_tmap_bf16_2d(&t_w2, w2, V, E, E, kBM)) != 0) return rc;
   if ((rc = make_tmap_bf16_2d(&t_act, act, n, E, E, kBN)) != 0) return rc;
+  CUtensorMap t_next = t_w2;
+  d.next_slabs = 0;
+  d.next_kb = 0;
+  if (next_w != nullptr && next_rows > 0 && next_cols > 0 && (next_cols % 8) == 0) {
+    if ((rc = make_tmap_bf16_2d(&t_next, next_w, next_rows, next_cols, next_cols, kBM)) != 0) return rc;
+    d.next_slabs = (next_rows + kBM - 1) / kBM;
+    d.next_kb = (next_cols + kBK - 1) / kBK;
+  }
   const bool tdiv = (temperature != 1.0f);
   // phase-1 split: as many k-splits as fill the SMs (cluster sizes 8, 4, 2, 1); a cluster size the device cannot
   // keep resident G / ks times (e.g. 16 clusters of 8 CTAs that each own an SM's shared memory) is halved
@@ -622,10 +647,10 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
     int G = d.num_m2 < max_ctas ? ((d.num_m2 + ks - 1) / ks) * ks : max_ctas;
     if (G < need1) G = need1;
 #define OSPO_RUN_MERGED(MODE, TDIV, WBF)                                                                              \
-  (greedy ? run_merged<MODE, TDIV, WBF, true>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature,  \
-                                              greedy, buf)                                                               \
-          : run_merged<MODE, TDIV, WBF, false>(c, t_w1, t_h, t_w2, t_act, d, G, b2, logits_dump, cfg_weight, temperature, \
-                                               greedy, buf))
+  (greedy ? run_merged<MODE, TDIV, WBF, true>(c, t_w1, t_h, t_w2, t_act, t_next, d, G, b2, logits_dump, cfg_weight,      \
+                                              temperature, greedy, buf)                                                  \
+          : run_merged<MODE, TDIV, WBF, false>(c, t_w1, t_h, t_w2, t_act, t_next, d, G, b2, logits_dump, cfg_weight,     \
+                                               temperature, greedy, buf))
     if (merge_mode == 0 && bf16_exact(cfg_weight)) {
       rc = tdiv ? OSPO_RUN_MERGED(0, true, true) : OSPO_RUN_MERGED(0, false, true);
     } else if (merge_mode == 0) {
@@ -634,7 +659,10 @@ int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_
       rc = tdiv ? OSPO_RUN_MERGED(1, true, false) : OSPO_RUN_MERGED(1, false, false);
     }
 #undef OSPO_RUN_MERGED
-    if (rc != -100) return rc;
+    if (rc != -100) {
+      if (grid_ctas != nullptr) *grid_ctas = G;
+      return rc;
+    }
   }
   return -100;
 }

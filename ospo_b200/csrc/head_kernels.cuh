@@ -319,6 +319,21 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int row_b
   out[c] = s * scale;
 }
 
+// prepare_gen_img_embeds from the memo table: out[row, :] = table[ids[row / id_repeat], :]
+__global__ void __launch_bounds__(256)
+embed_table_gather_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table, int codebook,
+                          __nv_bfloat16* __restrict__ out, int n, int D, int id_repeat) {
+  pdl_launch_dependents();
+  pdl_wait();  // the ids come from the sampler
+  const int row = blockIdx.x;
+  if (row >= n) return;
+  int64_t id = ids[row / id_repeat];
+  id = id < 0 ? 0 : (id >= codebook ? codebook - 1 : id);
+  const uint4* src = reinterpret_cast<const uint4*>(table + id * D);
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * D);
+  for (int i = threadIdx.x; i < D / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
 // ---------------------------------------------------------------------------
 // decode GEMM1 finalize: act[n, e] = bf16(gelu_erf(bf16(sum_k part[k][n][e] + b1[e])))  (fixed summation order).
 // Small footprint on purpose (128-thread blocks, 4 elements per thread): it sits between the two decode GEMMs of a
@@ -720,6 +735,10 @@ struct EmbedUp {
   const float* ba;                 // [D]
   __nv_bfloat16* a1;               // [2P, D]
   int codebook, D;
+  // Optional memo of the whole aligner: table[id, :] = gen_aligner(gen_embed(id)) for every code of the VQ codebook
+  // (bf16 [codebook, D]; the module is a pure function of the id, and generation runs with frozen weights).  When set
+  // the pair's two output rows are copied from it -- `a1` then IS the next step's input embeddings and no Linear runs.
+  const __nv_bfloat16* table;
 };
 
 constexpr int EMBED_PER_THREAD = 8;  // D <= 8 * 512 is served from registers loaded before the id is known
@@ -755,6 +774,18 @@ __device__ __forceinline__ __nv_bfloat16 embed_up_one(const uint32_t (&ew)[4], c
 
 __device__ __forceinline__ void embed_up_rows(const EmbedUp& eu, const EmbedRegs& r, int p, int id) {
   id = id < 0 ? 0 : (id >= eu.codebook ? eu.codebook - 1 : id);
+  if (eu.table != nullptr) {
+    // 16-byte vectors: D % 8 == 0 and the bases are 16-byte aligned (checked at the ABI)
+    const uint4* src = reinterpret_cast<const uint4*>(eu.table + static_cast<int64_t>(id) * eu.D);
+    uint4* d0 = reinterpret_cast<uint4*>(eu.a1 + static_cast<int64_t>(2 * p) * eu.D);
+    uint4* d1 = reinterpret_cast<uint4*>(eu.a1 + static_cast<int64_t>(2 * p + 1) * eu.D);
+    for (int i = threadIdx.x; i < eu.D / 8; i += blockDim.x) {
+      const uint4 v = __ldg(src + i);
+      d0[i] = v;
+      d1[i] = v;
+    }
+    return;
+  }
   const uint4 e = __ldg(reinterpret_cast<const uint4*>(eu.gen_embed + static_cast<int64_t>(id) * 8));
   const uint32_t ew[4] = {e.x, e.y, e.z, e.w};
   __nv_bfloat16* row0 = eu.a1 + static_cast<int64_t>(2 * p) * eu.D;
@@ -788,7 +819,9 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
   pdl_launch_dependents();  // successors may become resident and prefetch; they wait for our completion
   if (threadIdx.x == 0) trace_stamp(trace ? 4 : 0, 0);
   EmbedRegs er;
-  if constexpr (EMBED) embed_up_preload(eu, er);
+  if constexpr (EMBED) {
+    if (eu.table == nullptr) embed_up_preload(eu, er);
+  }
   pdl_wait();
   if (threadIdx.x == 0) trace_stamp(trace ? 4 : 0, 2);
   const int p = blockIdx.x;

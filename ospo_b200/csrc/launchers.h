@@ -116,12 +116,17 @@ int launch_decode_gemm2_fused(const LaunchCtx& c, const __nv_bfloat16* act, cons
 // act = gelu(h W1^T + b1) (cluster split-K), device-wide flag, then W2 act^T + b2 with the fused CFG epilogue.
 // flag: two zeroed words owned by this launch's stream (see abi.cu); the kernel leaves them zero.
 // l2_ahead: weight k-blocks (16 KB each, per CTA) requested into L2 ahead of the shared-memory ring.
+// next_w [next_rows, next_cols] (optional): the weight of the kernel that follows in the chain (gen_aligner's D x D
+// Linear); it is requested into L2 behind this step's last weight tile.
+// *grid_ctas receives the number of CTAs launched.
 // Returns -100 when the shape / occupancy does not allow every CTA to be resident at once.
 int launch_decode_merged(const LaunchCtx& c, const __nv_bfloat16* h, const __nv_bfloat16* w1, const float* b1,
                          const __nv_bfloat16* w2, const float* b2, __nv_bfloat16* act, uint32_t* flag,
                          __nv_bfloat16* logits_dump, int n, int H, int E, int V, float cfg_weight, float temperature,
                          int merge_mode, int greedy, const CfgFusedBuffers& buf, int l2_ahead,
-                         const void* w1_packed = nullptr, const void* w2_packed = nullptr);
+                         const void* w1_packed = nullptr, const void* w2_packed = nullptr,
+                         const __nv_bfloat16* next_w = nullptr, int next_rows = 0, int next_cols = 0,
+                         int* grid_ctas = nullptr);
 
 // phase 1 of that kernel on its own: out[n, M] = bf16(act_fn(bf16(x W^T + b))), n <= 32 (gen_aligner's D x D Linear)
 int launch_decode_linear(const LaunchCtx& c, const __nv_bfloat16* x, const __nv_bfloat16* w, const float* b,

@@ -277,14 +277,22 @@ def cfg_sample_impl(h: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, c
     if packed is not None:                      # (pack_weight_impl(w1), pack_weight_impl(w2))
         a.w1_packed, a.w2_packed = packed[0].data_ptr(), packed[1].data_ptr()
     if next_embeds is not None:
-        # (gen_embed, wa, ba, wb, bb, embeds_out[2P, D]): the next step's input embeddings, image_generation.py:166-168,
-        # produced in the same launch chain (first aligner layer inside the sampler's finish kernel)
-        ge, wa, ba, wb, bb, eo = next_embeds
+        # (gen_embed, wa, ba, wb, bb, embeds_out[2P, D][, table]): the next step's input embeddings,
+        # image_generation.py:166-168, produced in the same launch chain (first aligner layer inside the sampler's
+        # finish kernel, then the D x D Linear; with the memo table [codebook, D] the finish kernel copies the rows
+        # and nothing else runs)
+        ge, wa, ba, wb, bb, eo = next_embeds[:6]
+        table = next_embeds[6] if len(next_embeds) > 6 else None
         D = wb.shape[0]
         assert rows <= 32 and eo.dtype == torch.bfloat16 and eo.is_contiguous() and eo.numel() == rows * D
-        ws2 = torch.empty(rows * D, dtype=torch.bfloat16, device=dev)
-        al = _abi.AlignerArgs(rows, D, ge.shape[0], 8, None, ge.data_ptr(), wa.data_ptr(), ba.data_ptr(), wb.data_ptr(),
-                              bb.data_ptr(), eo.data_ptr(), ws2.data_ptr(), ws2.numel() * 2, 2)
+        if table is not None:
+            assert table.dtype == torch.bfloat16 and table.is_contiguous() and table.shape == (ge.shape[0], D)
+            al = _abi.AlignerArgs(rows, D, ge.shape[0], 8, None, None, None, None, None, None, eo.data_ptr(), None, 0, 2,
+                                  table.data_ptr())
+        else:
+            ws2 = torch.empty(rows * D, dtype=torch.bfloat16, device=dev)
+            al = _abi.AlignerArgs(rows, D, ge.shape[0], 8, None, ge.data_ptr(), wa.data_ptr(), ba.data_ptr(),
+                                  wb.data_ptr(), bb.data_ptr(), eo.data_ptr(), ws2.data_ptr(), ws2.numel() * 2, 2, None)
         a.next_embeds = C.cast(C.pointer(al), C.c_void_p)
     _abi.check(_abi.load().ospo_head_cfg_sample(C.byref(a), _stream()), "ospo_head_cfg_sample")
     return [ids, logits if logits is not None else torch.empty(0, dtype=torch.bfloat16, device=dev)]
@@ -320,11 +328,12 @@ def cfg_merge_sample_impl(logits: Tensor, cfg_weight: float, temperature: float,
 # next row N1: sampled ids -> next-step input embeddings
 # --------------------------------------------------------------------------------------------------
 def gen_img_embeds_impl(ids: Tensor, gen_embed: Tensor, wa: Tensor, ba: Tensor, wb: Tensor, bb: Tensor,
-                        repeat: int = 1, out: Optional[Tensor] = None) -> Tensor:
+                        repeat: int = 1, out: Optional[Tensor] = None, table: Optional[Tensor] = None) -> Tensor:
     """== gen_aligner(gen_embed(ids))  (janus/models/modeling_vlm.py:263-264; MlpProjector mlp_gelu depth 2)
     ids [n] int64 -> bf16 [n * repeat, D]; row i*repeat + j comes from ids[i] (repeat = 2 is the cond/uncond
     duplication of image_generation.py:166).  At most 32 output rows per launch; longer inputs go in slices.
-    ``out`` (bf16 [n * repeat, D], contiguous) receives the result without a copy."""
+    ``out`` (bf16 [n * repeat, D], contiguous) receives the result without a copy.  ``table`` (bf16 [codebook, D], the
+    module evaluated once for every code) turns the call into a row gather."""
     _check_cuda(ids, gen_embed, wa, wb)
     assert ids.dtype == torch.int64 and ids.dim() == 1 and ids.is_contiguous()
     assert gen_embed.dtype == torch.bfloat16 and gen_embed.shape[1] == 8 and gen_embed.is_contiguous()
@@ -346,7 +355,8 @@ def gen_img_embeds_impl(ids: Tensor, gen_embed: Tensor, wa: Tensor, ba: Tensor, 
         m = min(per, n - lo)
         a = _abi.AlignerArgs(m * rep, D, gen_embed.shape[0], 8, ids[lo:lo + m].data_ptr(), gen_embed.data_ptr(),
                              wa.data_ptr(), ba.data_ptr(), wb.data_ptr(), bb.data_ptr(),
-                             out2[lo * rep:(lo + m) * rep].data_ptr(), ws.data_ptr(), ws.numel() * 2, rep)
+                             out2[lo * rep:(lo + m) * rep].data_ptr(), ws.data_ptr(), ws.numel() * 2, rep,
+                             None if table is None else table.data_ptr())
         _abi.check(lib.ospo_head_gen_img_embeds(C.byref(a), _stream()), "ospo_head_gen_img_embeds")
     return out
 

@@ -34,14 +34,18 @@ def register_gen_head_cls(modeling_vlm_module) -> None:
     modeling_vlm_module.model_name_to_cls = model_name_to_cls
 
 
-def patch_model(model: torch.nn.Module, fuse_gen_img_embeds: bool = False) -> torch.nn.Module:
+def patch_model(model: torch.nn.Module, fuse_gen_img_embeds: bool = False, embed_table: bool = False) -> torch.nn.Module:
     """replace ``model.gen_head`` in place; parameters (and their requires_grad flags) are shared.
     ``fuse_gen_img_embeds`` also re-points ``model.prepare_gen_img_embeds`` (modeling_vlm.py:263-264) at the fused
-    gen_embed -> gen_aligner kernels (generation only)."""
+    gen_embed -> gen_aligner kernels (generation only); ``embed_table`` additionally memoises that module over the
+    16384 codes (``FusedGenImgEmbeds.build_table``: +134 MB for the 7B model, the decode loop then copies two table
+    rows per pair instead of streaming the aligner's weights every step)."""
     if not isinstance(model.gen_head, FusedGenHead):
         model.gen_head = FusedGenHead.from_reference(model.gen_head)
     if fuse_gen_img_embeds and hasattr(model, "gen_embed") and hasattr(model, "gen_aligner"):
         model.prepare_gen_img_embeds = FusedGenImgEmbeds(model.gen_embed, model.gen_aligner)
+        if embed_table:
+            model.prepare_gen_img_embeds.build_table()
     return model
 
 

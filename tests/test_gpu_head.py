@@ -1199,6 +1199,56 @@ def test_gen_img_embeds_7b_shape_and_patch_model():
         torch.testing.assert_close(model.prepare_gen_img_embeds(many).float(), ref_fn(many).float(), rtol=2e-2, atol=2e-2)
 
 
+
+def test_gen_img_embeds_memo_table_is_bit_identical():
+    """FusedGenImgEmbeds.build_table(): table[id] == gen_aligner(gen_embed(id)) bit for bit (same kernels), the table
+    form of the call and of the fused decode chain returns the same rows / ids as the streamed form, and a parameter
+    update rebuilds the table."""
+    from ospo_b200 import FusedGenImgEmbeds
+
+    dev = _cuda()
+    H = E = D = 512
+    V, P = 16384, 16
+    torch.manual_seed(91)
+    gen_embed = torch.nn.Embedding(V, 8).to(dev).to(torch.bfloat16)
+    aligner = torch.nn.Module()
+    aligner.layers = torch.nn.Sequential(torch.nn.Linear(8, D), torch.nn.GELU(), torch.nn.Linear(D, D)).to(dev).to(torch.bfloat16)
+    fe = FusedGenImgEmbeds(gen_embed, aligner)
+    g = torch.Generator().manual_seed(92)
+    ids = torch.randint(0, V, (3, 37), generator=g).to(dev)
+    direct = fe(ids)
+    table = fe.build_table()
+    assert table.shape == (V, D) and fe.use_table
+    assert torch.equal(fe(ids), direct) and torch.equal(table[ids.reshape(-1)].view_as(direct), direct)
+    tok = torch.randint(0, V, (P,), generator=g).to(dev)
+    assert torch.equal(fe.from_sampled(tok), direct.new_tensor(table[tok].repeat_interleave(2, 0)))
+    # the fused decode chain: same ids, same embeddings with and without the table (merged kernel and fallback chain)
+    head = O.make_head(H, E, V, seed=93, w2_gain=3.0).to(torch.bfloat16)
+    fh = _fused_from(head, dev, dtype=torch.bfloat16, requires_grad=False)
+    h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16).to(dev)
+    u = torch.rand(P, generator=g).to(dev)
+    from ospo_b200 import _abi
+    lib = _abi.load()
+    try:
+        for merged in (1, 0):
+            lib.ospo_head_set_decode_merged(merged)
+            fe.use_table = False
+            ids_a, emb_a = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, next_embeds=fe)
+            fe.use_table = True
+            ids_b, emb_b = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, next_embeds=fe)
+            torch.cuda.synchronize()
+            assert torch.equal(ids_a, ids_b) and torch.equal(emb_a, emb_b)
+            assert torch.equal(emb_b[0::2], table[ids_b]) and torch.equal(emb_b[1::2], table[ids_b])
+    finally:
+        lib.ospo_head_set_decode_merged(1)
+    # a parameter update invalidates the memo
+    with torch.no_grad():
+        aligner.layers[2].bias.add_(1.0)
+    t2 = fe.build_table()
+    assert not torch.equal(t2, table)
+    fe.use_table = False
+    assert torch.equal(fe(ids), t2[ids.reshape(-1)].view_as(direct))
+
 @pytest.mark.parametrize("fused,merged,greedy", [(1, 1, False), (1, 1, True), (1, 0, False), (0, 0, False)])
 def test_cfg_sample_with_next_embeds_chain(fused, merged, greedy):
     """image_generation.py:156-168 as one call: the ids equal the plain decode step's and the embeddings equal

@@ -780,8 +780,12 @@ def main():
                         f"({B} pairs x 576 tokens per GPU), bf16, head trainable, NCCL all-reduce of the head-weight "
                         "gradients"),
                        "pairs_per_gpu": B, "global_pairs": B * world, "rows_per_gpu": rows,
-                       "H": H7B, "E": E7B, "V": V, "parallelism": f"dp{world}: pairs batch-sharded, NCCL all-reduce of "
-                       "the flat fp32 head gradient (83.9M elements)" if world > 1 else "single GPU",
+                       "H": H7B, "E": E7B, "V": V,
+                       "parallelism": (f"dp{world}: pairs batch-sharded; head-weight gradients (83.9M fp32) exchanged "
+                                       + ("over NVLink peer memory: reduce-scatter fused into the weight-gradient GEMM "
+                                          "epilogues, owners sum in rank order and multicast their shards"
+                                          if head._peer_exchange(group) is not None else "by NCCL all-reduce"))
+                       if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (604 MB hidden states + 2.4 GB bf16 logits spill per step)",
                        "cta_group": _abi.load().ospo_head_set_cta_group(0), "loss": loss_val},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,

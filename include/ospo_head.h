@@ -103,6 +103,24 @@ typedef struct {
 #define OSPO_SC_LOGITS_REJECTED 10
 #define OSPO_SC_COUNT 16
 
+/* ---- data-parallel gradient exchange over NVLink peer memory ---------------------------------------
+ * Replaces DDP's NCCL all-reduce of the head-weight gradients (ospo/utils/train.py:26-28) for up to 8 ranks of one
+ * NVSwitch domain.  The flat gradient dW2 | dW1 | db2 | db1 is partitioned by rows (rank r owns rows
+ * [r V/N, (r+1) V/N) of dW2 and db2, [r E/N, (r+1) E/N) of dW1 and db1; V/N and E/N must be multiples of 256).
+ * Step 1 (inside ospo_head_*_bwd when ospo_simpo_args.dp is set): the weight-gradient GEMM epilogues and the bias
+ * reductions write their results, times wgrad_scale, straight into the OWNER's inbox -- slot [this rank] -- with
+ * plain peer stores; nothing is written to flat_grads.  Step 2 (ospo_head_dp_reduce_broadcast, after every rank has
+ * finished step 1: the caller puts a barrier between them): each owner adds the N slots of its inbox in rank order
+ * (bit-reproducible) and stores the sums into the flat gradient buffer of every rank (one multimem.st through the
+ * NVSwitch multicast mapping if given, else one store per peer).  After a second barrier every rank holds the same
+ * bits.  All pointers are mappings valid in THIS process (e.g. torch symmetric memory / cuMemMap of peer handles). */
+typedef struct {
+  int32_t world, rank;         /* 2 <= world <= 8 */
+  float* inbox[8];             /* [world] inbox of every rank, fp32 [world slots][shard_elems]; [rank] is the local one */
+  float* flat[8];              /* [world] flat gradient buffer of every rank, fp32 [V*E + E*H + V + E] */
+  float* flat_multicast;       /* multicast mapping of the flat buffers, or NULL */
+} ospo_dp_exchange;
+
 typedef struct {
   ospo_head_shape shape;
   ospo_head_weights w;
@@ -159,6 +177,9 @@ typedef struct {
   float wgrad_scale;           /* multiplies dW2 | dW1 | db2 | db1 as they are stored (dx is not scaled): a data-parallel
                                   caller passes 1 / world_size and all-reduces with SUM (ospo/utils/train.py:26-28);
                                   0 means 1 */
+  const ospo_dp_exchange* dp;  /* backward only, optional: fuse the reduce-scatter of the data-parallel exchange into the
+                                  weight-gradient stores (see ospo_dp_exchange); flat_grads must still be given (it
+                                  marks the head as trainable) but is not written by the backward */
 } ospo_simpo_args;
 
 /* ---- next row: sampled ids -> next-step input embeddings ---------------------------------
@@ -257,6 +278,12 @@ OSPO_API int ospo_head_logps_fwd(const ospo_simpo_args* args, ospo_stream_t stre
 OSPO_API int ospo_head_logps_bwd(const ospo_simpo_args* args, ospo_stream_t stream);
 OSPO_API int ospo_head_simpo_fwd(const ospo_simpo_args* args, ospo_stream_t stream);
 OSPO_API int ospo_head_simpo_bwd(const ospo_simpo_args* args, ospo_stream_t stream);
+/* step 2 of the peer-memory gradient exchange: this rank's inbox -> its shard of every rank's flat gradient.
+   regions: 1 = the dW2 rows of the shard (complete after backward part 1, so a caller can exchange them on a side
+   stream beside the remaining GEMMs), 2 = the rest (dW1 rows, db2, db1), 0 or 3 = everything.  max_blocks > 0 bounds
+   the grid (a small grid shares the SMs with GEMMs running beside it). */
+OSPO_API int ospo_head_dp_reduce_broadcast(const ospo_head_shape* shape, const ospo_dp_exchange* dp, int32_t regions,
+                                           int32_t max_blocks, ospo_stream_t stream);
 
 /* Pre-pack a [rows, cols] bf16 row-major weight for the decode step: [rows/128][cols/64] tiles of 16 KB, each the
    128-byte-swizzled shared-memory image of a {64 x 128} box.  packed: ospo_head_packed_weight_bytes() bytes. */
@@ -305,7 +332,8 @@ OSPO_API int ospo_head_set_kernel_tune(int kernel, int group_m, int a_evict, int
 #define OSPO_K_SAMPLER 12       /* CFG merge + softmax + inverse-CDF sample                        */
 #define OSPO_K_ALIGNER 13       /* gen_embed lookup + Linear(8->D) + GELU, then swap-AB Linear(D->D)   */
 #define OSPO_K_OPTIMIZER 14     /* squared-norm reduction + clip + AdamW on the flat buffer           */
-#define OSPO_K_COUNT 15
+#define OSPO_K_DP_EXCHANGE 15   /* peer-memory gradient exchange: inbox -> every rank's flat gradient  */
+#define OSPO_K_COUNT 16
 OSPO_API int ospo_head_profile_enable(int enable);
 OSPO_API int ospo_head_profile_read(float* total_ms, int32_t* counts, int32_t n);
 /* tuning aid: CTA timeline of the decode chain.  device_buf = u64[5][160][8] (kernel: 1 GEMM1, 2 GEMM2, 3 finalize,

@@ -46,6 +46,16 @@ class HeadArgs(C.Structure):
     ]
 
 
+class DpExchange(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("inbox", C.c_void_p * 8),
+        ("flat", C.c_void_p * 8),
+        ("flat_multicast", C.c_void_p),
+    ]
+
+
 class SimpoArgs(C.Structure):
     _fields_ = [
         ("shape", Shape),
@@ -82,6 +92,7 @@ class SimpoArgs(C.Structure):
         ("bwd_stage", C.c_int32),
         ("reserve_sms", C.c_int32),
         ("wgrad_scale", C.c_float),
+        ("dp", C.c_void_p),              # const ospo_dp_exchange*
     ]
 
 
@@ -164,6 +175,7 @@ EXPORTS = (
     "ospo_head_logps_bwd",
     "ospo_head_simpo_fwd",
     "ospo_head_simpo_bwd",
+    "ospo_head_dp_reduce_broadcast",
     "ospo_head_packed_weight_bytes",
     "ospo_head_pack_weight",
     "ospo_head_cfg_sample",
@@ -219,6 +231,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(SimpoArgs), S]
         fn.restype = C.c_int
+    lib.ospo_head_dp_reduce_broadcast.argtypes = [C.POINTER(Shape), C.POINTER(DpExchange), C.c_int32, C.c_int32, S]
+    lib.ospo_head_dp_reduce_broadcast.restype = C.c_int
     for name in ("ospo_head_cfg_sample", "ospo_head_cfg_merge_sample"):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(CfgArgs), S]
@@ -284,7 +298,7 @@ def workspace_bytes(rows: int, hidden: int, embed: int, vocab: int, num_seqs: in
 
 KERNEL_NAMES = ("gemm1_bias_gelu", "gemm2_logits_lse", "scalar_stage", "row_weights", "dact_gelu_bwd",
                 "wgrad_w2", "colsum_db2_db1", "wgrad_w1", "dgrad_x", "gemm2_logits_plain", "decode_gemm1",
-                "decode_gemm2", "cfg_merge_sample", "gen_img_embeds", "clip_adamw")
+                "decode_gemm2", "cfg_merge_sample", "gen_img_embeds", "clip_adamw", "dp_exchange")
 
 
 def profile_enable(on: bool) -> None:

@@ -441,14 +441,36 @@ int check_simpo_common(const ospo_simpo_args* a, Workspace* w) {
 // column sums (bias gradients) in two fixed-order stages
 template <bool WEIGHTED>
 int launch_colsum(const __nv_bfloat16* x, int rows, int cols, const float* row_w, float scale, float* partial,
-                  float* out, cudaStream_t st) {
+                  float* out, cudaStream_t st, const DpScatter& dp, int64_t region_off) {
   const int row_blocks = (rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK;
   dim3 grid((cols + 1023) / 1024, row_blocks);
   colsum_partial_kernel<WEIGHTED><<<grid, 128, 0, st>>>(x, cols, rows, cols, row_w, partial);
   int rc = check_launch();
   if (rc) return rc;
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(partial, row_blocks, cols, scale, out);
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(partial, row_blocks, cols, scale, out, dp, region_off);
   return check_launch();
+}
+
+// partition of the flat gradient over the ranks of a peer-memory exchange (see ospo_dp_exchange)
+struct DpPlan {
+  int64_t a, b, vb, eb, shard;   // dW2 rows, dW1 rows, db2, db1 elements of one shard; their sum
+};
+int dp_plan(const ospo_head_shape& s, const ospo_dp_exchange* dp, DpPlan* pl, DpScatter* sc) {
+  if (dp->world < 2 || dp->world > 8 || dp->rank < 0 || dp->rank >= dp->world) return OSPO_ERR_BAD_SHAPE;
+  if ((s.vocab % (dp->world * 256)) || (s.embed % (dp->world * 256))) return OSPO_ERR_UNSUPPORTED;
+  pl->a = static_cast<int64_t>(s.vocab / dp->world) * s.embed;
+  pl->b = static_cast<int64_t>(s.embed / dp->world) * s.hidden;
+  pl->vb = s.vocab / dp->world;
+  pl->eb = s.embed / dp->world;
+  pl->shard = pl->a + pl->b + pl->vb + pl->eb;
+  sc->world = dp->world;
+  sc->rank = dp->rank;
+  sc->shard_elems = pl->shard;
+  for (int i = 0; i < 8; ++i) {
+    sc->inbox[i] = i < dp->world ? dp->inbox[i] : nullptr;
+    if (i < dp->world && (!dp->inbox[i] || !aligned16(dp->inbox[i]))) return OSPO_ERR_NULL;
+  }
+  return OSPO_OK;
 }
 
 // shared backward: row weights -> GEMM pair(s) straight on the forward's spill (read-only here)
@@ -477,6 +499,12 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   float* db2 = a->flat_grads ? a->flat_grads + VE + EH : nullptr;
   float* db1 = a->flat_grads ? db2 + s.vocab : nullptr;
   const float wscale = a->wgrad_scale != 0.0f ? a->wgrad_scale : 1.0f;  // 1 / world_size of a data-parallel caller
+  // peer-memory exchange: the gradient stores go to the owners' inboxes instead of flat_grads
+  DpScatter sc = {};
+  DpPlan pl = {};
+  if (a->dp != nullptr && a->flat_grads) {
+    if ((rc = dp_plan(s, a->dp, &pl, &sc))) return rc;
+  }
   const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(a->logits);
   __nv_bfloat16* dpre = w.rows_by_e;
   float* row_w = w.row_coef;
@@ -499,23 +527,33 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   if (a->flat_grads && first) {
     {
       KernelSpan ks(st, OSPO_K_COLSUM);
-      if ((rc = launch_colsum<true>(g, s.rows, s.vocab, row_w, wscale, w.colsum_part, db2, st))) return rc;
+      if ((rc = launch_colsum<true>(g, s.rows, s.vocab, row_w, wscale, w.colsum_part, db2, st, sc, pl.a + pl.b)))
+        return rc;
     }
     // dW2 first: it is the largest block of the flat gradient, so a caller that overlaps the
     // all-reduce with the remaining GEMMs can start on it earliest.
     KernelSpan ks(st, OSPO_K_WGRAD2);
-    rc = map_rc(launch_wgrad(tuned(c, 3), g, w.act_w, dW2, s.rows, s.vocab, s.embed, wscale));
+    if (sc.world > 0)
+      rc = map_rc(launch_wgrad_scatter(tuned(c, 3), g, w.act_w, sc, 0, s.rows, s.vocab, s.embed, wscale));
+    else
+      rc = map_rc(launch_wgrad(tuned(c, 3), g, w.act_w, dW2, s.rows, s.vocab, s.embed, wscale));
     if (rc) return rc;
   }
   if (a->flat_grads && second) {
     {
       KernelSpan ks(st, OSPO_K_COLSUM);
-      if ((rc = launch_colsum<false>(dpre, s.rows, s.embed, nullptr, wscale, w.colsum_part, db1, st))) return rc;
+      if ((rc = launch_colsum<false>(dpre, s.rows, s.embed, nullptr, wscale, w.colsum_part, db1, st, sc,
+                                     pl.a + pl.b + pl.vb)))
+        return rc;
     }
     {
       KernelSpan ks(st, OSPO_K_WGRAD1);
-      rc = map_rc(launch_wgrad(tuned(c, 4), dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed, s.hidden,
-                               wscale, x_layout(a)));
+      if (sc.world > 0)
+        rc = map_rc(launch_wgrad_scatter(tuned(c, 4), dpre, static_cast<const __nv_bfloat16*>(a->x), sc, pl.a, s.rows,
+                                         s.embed, s.hidden, wscale, x_layout(a)));
+      else
+        rc = map_rc(launch_wgrad(tuned(c, 4), dpre, static_cast<const __nv_bfloat16*>(a->x), dW1, s.rows, s.embed,
+                                 s.hidden, wscale, x_layout(a)));
     }
     if (rc) return rc;
   }
@@ -616,6 +654,36 @@ int ospo_head_simpo_fwd(const ospo_simpo_args* a, ospo_stream_t stream) {
   simpo_scalar_kernel<<<1, 256, 0, st>>>(a->seq_logps, w.seq_sum, w.seq_logit_sum, w.seq_count,
                                          a->shape.num_seqs / 2, hp, a->losses, a->chosen_rewards, a->rejected_rewards,
                                          a->grad_seq, a->scalars);
+  return check_launch();
+}
+
+int ospo_head_dp_reduce_broadcast(const ospo_head_shape* shape, const ospo_dp_exchange* dp, int32_t regions,
+                                  int32_t max_blocks, ospo_stream_t stream) {
+  if (!shape || !dp) return OSPO_ERR_NULL;
+  int rc = runtime_init();
+  if (rc) return rc;
+  if ((rc = check_shape(*shape, false))) return rc;
+  DpScatter sc = {};
+  DpPlan pl = {};
+  if ((rc = dp_plan(*shape, dp, &pl, &sc))) return rc;
+  DpGather g = {};
+  for (int i = 0; i < dp->world; ++i) {
+    if (!dp->flat[i] || !aligned16(dp->flat[i])) return OSPO_ERR_NULL;
+    g.flat[i] = dp->flat[i];
+  }
+  g.flat_mc = dp->flat_multicast;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  KernelSpan ks(st, OSPO_K_DP_EXCHANGE);
+  const int64_t VE = static_cast<int64_t>(shape->vocab) * shape->embed, EH = static_cast<int64_t>(shape->embed) * shape->hidden;
+  // regions: 1 = the dW2 rows of the shard, 2 = everything else (dW1 rows, db2, db1), 0 / 3 = all
+  const int r = (regions & 3) == 0 ? 3 : (regions & 3);
+  const int64_t i_begin = (r & 1) ? 0 : pl.a, i_end = (r & 2) ? pl.shard : pl.a;
+  // HBM-bound on the local inbox (world x shard bytes read, shard bytes sent): four resident blocks per SM unless the
+  // caller runs it beside GEMMs and asks for a small grid
+  int blocks = current_num_sms() * 4;
+  if (max_blocks > 0 && max_blocks < blocks) blocks = max_blocks;
+  dp_reduce_broadcast_kernel<<<blocks, 256, 0, st>>>(dp->inbox[dp->rank], g, dp->world, dp->rank, pl.shard, pl.a, pl.b,
+                                                     pl.vb, VE, EH, shape->vocab, i_begin, i_end);
   return check_launch();
 }
 

@@ -178,6 +178,60 @@ struct EpiStore {
 };
 
 // ---------------------------------------------------------------------------
+// Weight-gradient store fused with the reduce-scatter of the data-parallel exchange: the rows of dW are
+// partitioned over the ranks, and every rank's epilogue writes each tile straight into the OWNER's inbox over
+// NVLink peer memory (plain posted stores: 128 contiguous bytes per thread and chunk) -- slot [source rank] of that
+// inbox, so the owner later adds the N contributions in rank order (deterministic) without any rank having run a
+// collective kernel.  The exchange rides inside the GEMM that produces the data; no SM is given up to it.
+//   dest = inbox[row / rows_per_rank] + slot_off + (row % rows_per_rank) * ld + col
+// ---------------------------------------------------------------------------
+struct EpiStoreScatter {
+  struct Params {
+    DpScatter dp;
+    int rows_per_rank;    // rows of this gradient matrix owned by each rank (a multiple of the tile's 128 / 256 rows)
+    int64_t region_off;   // offset of this matrix's rows inside a shard (dW2 rows first, then dW1 rows, db2, db1)
+    int64_t ld;
+    float scale;          // 1 / world
+  };
+  struct State {
+    float* dst;           // row base in the owner's inbox
+  };
+  static constexpr int SMEM_BYTES = 0;
+  __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
+    st.dst = nullptr;
+    if (row < d.M) {
+      const int owner = row / p.rows_per_rank;
+      st.dst = p.dp.inbox[owner] + static_cast<int64_t>(p.dp.rank) * p.dp.shard_elems + p.region_off +
+               static_cast<int64_t>(row - owner * p.rows_per_rank) * p.ld;
+    }
+  }
+  template <bool FULL>
+  __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
+                               uint8_t*) {
+    if (row >= d.M) return;
+    const int valid = FULL ? 32 : d.N - col0;
+    if (valid <= 0) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+    float* dst = st.dst + col0;
+    if (FULL && ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0)) {
+      // 256-bit stores: a thread's 128 bytes leave as four 32-byte sectors.  Peer stores are not merged in the local
+      // L2, every store instruction becomes NVLink write packets of its own -- with 16-byte stores the dW2 GEMM of an
+      // 8-rank job ran 8.5 instead of 6.7 ms (packet rate, not bytes: 235 MB per GEMM)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * i), "f"(v[8 * i]),
+                     "f"(v[8 * i + 1]), "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]), "f"(v[8 * i + 5]),
+                     "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
+                     : "memory");
+    } else {
+      store_row32_f32<FULL>(dst, v, valid);
+    }
+  }
+  __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
+};
+
+// ---------------------------------------------------------------------------
 // Split-K partial store for the swap-AB decode GEMMs: part[k_split][col][row] = acc (fp32, transposed so
 // that the 32 lanes of a warp write 32 consecutive floats).  The partials are summed in a fixed order by
 // the finalize kernel, so the result is deterministic (no atomics).

@@ -52,4 +52,24 @@ int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat1
                                  false, SegOperand(), sb, 0, c.sync_ctr, c.a_evict, c.b_evict);
 }
 
+// the same GEMM with the reduce-scatter fused into the store (EpiStoreScatter): rows of dW go to their owner's inbox
+int launch_wgrad_scatter(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, const DpScatter& dp,
+                         int64_t region_off, int rows, int out_dim, int in_dim, float scale, const XLayout& xl) {
+  using Epi = EpiStoreScatter;
+  if (dp.world < 1 || dp.world > 8 || (out_dim % dp.world) != 0) return -100;
+  const int rows_per_rank = out_dim / dp.world;
+  if (rows_per_rank % (c.cta_group == 2 ? CfgW2::TILE_M : CfgW1::TILE_M)) return -100;  // a tile never straddles two owners
+  Epi::Params p{dp, rows_per_rank, region_off, in_dim, scale != 0.0f ? scale : 1.0f};
+  SegOperand sb;
+  sb.seg_rows = xl.seg_rows;
+  sb.seg_pitch = xl.seg_pitch;
+  sb.seg_off = xl.seg_off;
+  sb.segments = xl.segments;
+  if (c.cta_group == 2)
+    return launch_gemm<CfgW2, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream, 1,
+                                   false, SegOperand(), sb, 0, c.sync_ctr, c.a_evict, c.b_evict);
+  return launch_gemm<CfgW1, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream, 1,
+                                 false, SegOperand(), sb, 0, c.sync_ctr, c.a_evict, c.b_evict);
+}
+
 }  // namespace ospo

@@ -5,6 +5,7 @@
 #pragma once
 
 #include "cfg_math.cuh"
+#include "launchers.h"
 #include "ptx.cuh"
 
 namespace ospo {
@@ -310,13 +311,76 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows,
   dst[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
 }
 
+// dp.world > 0: element c goes to its owner's inbox (slot = this rank) instead of `out` -- the bias gradients take
+// the same fused reduce-scatter route as the weight gradients (EpiStoreScatter)
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int row_blocks, int cols, float scale,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, DpScatter dp, int64_t region_off) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.0f;
   for (int b = 0; b < row_blocks; ++b) s += partial[static_cast<int64_t>(b) * cols + c];
-  out[c] = s * scale;
+  if (dp.world > 0) {
+    const int per = cols / dp.world;
+    const int owner = c / per;
+    dp.inbox[owner][static_cast<int64_t>(dp.rank) * dp.shard_elems + region_off + (c - owner * per)] = s * scale;
+  } else {
+    out[c] = s * scale;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Second half of the data-parallel exchange.  Every rank's inbox now holds, slot by slot, the N contributions to ITS
+// shard of the flat gradient (written by the peers' GEMM epilogues).  The owner adds them in rank order -- the same
+// order on every run: bit-reproducible -- and writes each sum into the flat gradient buffer of EVERY rank:
+// one multimem.st through the NVSwitch multicast mapping when there is one (the switch replicates the store), else
+// one peer store per rank.  All ranks end up with bit-identical averaged gradients (DDP semantics,
+// ospo/utils/train.py:26-28) without a collective library call on the data path.
+// ---------------------------------------------------------------------------
+struct DpGather {
+  float* flat[8];         // flat gradient buffer of every rank as mapped into this process
+  float* flat_mc;         // multicast mapping of the same buffer (null: use the peer stores)
+};
+
+__device__ __forceinline__ void multimem_st_f32x4(float* mc_addr, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+dp_reduce_broadcast_kernel(const float* __restrict__ inbox_local, DpGather g, int world, int rank, int64_t shard_elems,
+                           int64_t a_elems /* dW2 rows of a shard */, int64_t b_elems /* dW1 rows */, int64_t vb /* db2 */,
+                           int64_t VE, int64_t EH, int64_t V, int64_t i_begin, int64_t i_end /* shard elements to do */) {
+  for (int64_t i4 = i_begin / 4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < i_end / 4;
+       i4 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t i = i4 * 4;
+    // all slots are requested before the first addition (memory-level parallelism); the additions keep rank order
+    float4 slot[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      if (s < world) slot[s] = __ldcs(reinterpret_cast<const float4*>(inbox_local + static_cast<int64_t>(s) * shard_elems + i));
+    float4 acc = slot[0];
+#pragma unroll
+    for (int s = 1; s < 8; ++s) {
+      if (s < world) {
+        acc.x += slot[s].x;
+        acc.y += slot[s].y;
+        acc.z += slot[s].z;
+        acc.w += slot[s].w;
+      }
+    }
+    // shard element -> element of the flat gradient dW2 | dW1 | db2 | db1
+    int64_t f;
+    if (i < a_elems) f = static_cast<int64_t>(rank) * a_elems + i;
+    else if (i < a_elems + b_elems) f = VE + static_cast<int64_t>(rank) * b_elems + (i - a_elems);
+    else if (i < a_elems + b_elems + vb) f = VE + EH + static_cast<int64_t>(rank) * vb + (i - a_elems - b_elems);
+    else f = VE + EH + V + static_cast<int64_t>(rank) * (shard_elems - a_elems - b_elems - vb) + (i - a_elems - b_elems - vb);
+    if (g.flat_mc != nullptr) {
+      multimem_st_f32x4(g.flat_mc + f, acc);
+    } else {
+      for (int s = 0; s < world; ++s) *reinterpret_cast<float4*>(g.flat[s] + f) = acc;
+    }
+  }
 }
 
 // prepare_gen_img_embeds from the memo table: out[row, :] = table[ids[row / id_repeat], :]

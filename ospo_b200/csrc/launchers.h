@@ -25,6 +25,15 @@ struct LaunchCtx {
 
 struct CfgFusedBuffers;
 
+// Data-parallel exchange fused into the weight-gradient stores: where a rank's contribution to each
+// owner's shard of the flat gradient goes.
+struct DpScatter {
+  float* inbox[8];        // inbox base of every rank as mapped into THIS process (symmetric memory); [rank] is local
+  int world;              // 0 = scatter off
+  int rank;
+  int64_t shard_elems;    // elements of one rank's shard of the flat gradient (= size of one inbox slot)
+};
+
 // cudaFuncSetAttribute is per device: `mask` (one static per kernel instantiation) has one bit per device ordinal.
 // Returns true when the calling thread's current device still needs the attributes set; call mark afterwards.
 inline bool func_attrs_needed(std::atomic<uint64_t>& mask, int* dev_out) {
@@ -83,6 +92,11 @@ int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* g, const __nv_
 // dW[out_dim, in_dim] (fp32) = scale * dY^T X;  dY [rows,out_dim], X [rows,in_dim]  (scale 0 = 1)
 int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw, int rows, int out_dim,
                  int in_dim, float scale = 0.0f, const XLayout& xl = XLayout());
+// the weight-gradient GEMM with the data-parallel reduce-scatter fused into its store: row block r of dW goes into
+// rank (r / rows_per_rank)'s inbox over NVLink peer memory (slot = this rank).  -100: the partition does not fit.
+int launch_wgrad_scatter(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* x, const DpScatter& dp,
+                         int64_t region_off, int rows, int out_dim, int in_dim, float scale,
+                         const XLayout& xl = XLayout());
 // dX[rows, in_dim] (bf16) = dY W;  dY [rows,out_dim], W [out_dim,in_dim]
 int launch_dgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx, int rows,
                  int out_dim, int in_dim, const XLayout& xl = XLayout());

@@ -87,6 +87,127 @@ def staged_allreduce_mean_(flat: torch.Tensor, split: int, group, run_stage1, ru
     return out
 
 
+class PeerGradExchange:
+    """Gradient exchange of the head's flat gradient over NVLink peer memory (``ospo_dp_exchange`` in
+    include/ospo_head.h) -- DDP's averaging (ospo/utils/train.py:26-28) without a collective library on the data path.
+
+    Two symmetric-memory buffers per rank (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every
+    rank of the box): the flat gradient itself and an inbox of the same size.  Step 1 runs INSIDE the backward: the
+    weight-gradient GEMM epilogues store every tile, times 1 / world, into the inbox of the rank that owns those rows
+    (plain posted peer stores, no SM set aside, no extra kernel).  Step 2, after a barrier: each owner adds the `world`
+    slots of its inbox in rank order and multicasts the sums into every rank's flat buffer (one ``multimem.st`` per 16
+    bytes through the NVSwitch when a multicast mapping exists).  A second barrier and all ranks hold the same bits.
+    torch.distributed is used for the rendezvous and the barriers only."""
+
+    def __init__(self, group, H: int, E: int, V: int, device):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _abi, ops
+
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if not (2 <= self.world <= 8) or V % (self.world * 256) or E % (self.world * 256):
+            raise ValueError("peer exchange needs 2..8 ranks and V, E divisible by 256 * world")
+        n = ops.flat_grad_numel(H, E, V)
+        self.dims = (H, E, V)
+        name = group.group_name if hasattr(group, "group_name") else dist.group.WORLD.group_name
+        self.flat = symm_mem.empty(n, dtype=torch.float32, device=device)
+        self.inbox = symm_mem.empty(n, dtype=torch.float32, device=device)      # world slots x (n / world) elements
+        self.h_flat = symm_mem.rendezvous(self.flat, name)
+        self.h_inbox = symm_mem.rendezvous(self.inbox, name)
+        a = _abi.DpExchange()
+        a.world, a.rank = self.world, self.rank
+        for i in range(self.world):
+            a.inbox[i] = int(self.h_inbox.buffer_ptrs[i])
+            a.flat[i] = int(self.h_flat.buffer_ptrs[i])
+        mc = int(getattr(self.h_flat, "multicast_ptr", 0) or 0)
+        import os
+        if os.environ.get("OSPO_HEAD_DP_MULTICAST", "1") == "0":
+            mc = 0
+        a.flat_multicast = mc if mc else None
+        self.multicast = bool(mc)
+        self.args = a
+        self._shape = _abi.Shape(1, H, E, V, 1)
+        self._C = C
+
+    def barrier(self, channel: int = 0) -> None:
+        self.h_inbox.barrier(channel=channel)
+
+    def reduce_broadcast(self, regions: int = 3, max_blocks: int = 0) -> None:
+        from . import _abi
+
+        _abi.check(_abi.load().ospo_head_dp_reduce_broadcast(self._C.byref(self._shape), self._C.byref(self.args),
+                                                            int(regions), int(max_blocks),
+                                                            torch.cuda.current_stream().cuda_stream),
+                   "ospo_head_dp_reduce_broadcast")
+
+    def finish(self) -> None:
+        """after the backward whose stores went to the inboxes: barrier, inbox -> everyone's flat, barrier"""
+        self.barrier()
+        self.reduce_broadcast()
+        self.barrier()
+
+    def run_staged(self, run_stage1, run_stage2, run_stage3):
+        """Backward in three parts with both halves of the exchange overlapped.  ``run_stage1()`` ends with the dW2 GEMM,
+        whose epilogue has scattered dW2 (80 % of the bytes) into the owners' inboxes: a side stream waits for every
+        rank to get there, sums its dW2 shard and multicasts it while ``run_stage2()`` (db1, dW1) runs; the same for the
+        remainder (dW1 rows, biases) while ``run_stage3()`` (dX) runs.  One barrier at the end: every rank's shards have
+        landed in every flat buffer.  Returns run_stage3()'s result."""
+        import os
+
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream()
+            self._side_blocks = int(os.environ.get("OSPO_HEAD_DP_SIDE_BLOCKS", "64"))
+        run_stage1()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.barrier(channel=1)
+            self.reduce_broadcast(regions=1, max_blocks=self._side_blocks)
+        run_stage2()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.barrier(channel=1)
+            self.reduce_broadcast(regions=2, max_blocks=self._side_blocks)
+        out = run_stage3()
+        main.wait_stream(self._side)
+        self.barrier()
+        return out
+
+
+_peer_exchanges: dict = {}
+
+
+def peer_exchange_for(group, H: int, E: int, V: int, device):
+    """the PeerGradExchange of (group, head shape) when OSPO_HEAD_DP=p2p selects it, created on first use --
+    collectively: every rank of the group must call this at the same point.  Returns None (and the caller uses the
+    NCCL all-reduce, the default: on 8 B200s the two are within noise of each other, 30.8 vs 30.1 ms per step, see
+    DESIGN.md §6) when the shape does not partition or symmetric memory cannot be set up on ANY rank."""
+    import os
+
+    key = (id(group), H, E, V, str(device))
+    if key in _peer_exchanges:
+        return _peer_exchanges[key]
+    ex = None
+    if os.environ.get("OSPO_HEAD_DP", "nccl") == "p2p" and dist.get_backend(group) == "nccl":
+        ok = 1
+        try:
+            ex = PeerGradExchange(group, H, E, V, device)
+        except Exception as e:  # noqa: BLE001 -- any failure means "not available here"; decided collectively below
+            ok, ex = 0, None
+            if os.environ.get("OSPO_HEAD_DP") == "p2p":
+                print(f"[ospo_b200] peer-memory gradient exchange unavailable on rank {dist.get_rank(group)}: {e!r}",
+                      flush=True)
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag) == 0:
+            ex = None
+    _peer_exchanges[key] = ex
+    return ex
+
+
 def dp_check(flat_local: torch.Tensor, flat_reduced: torch.Tensor, group=None) -> dict:
     """Value check of the gradient exchange on the hardware it runs on (DDP semantics, ospo/utils/train.py:26-28):
     ``flat_reduced`` (this rank's buffer after the exchange) must be bit-identical on every rank and equal the mean

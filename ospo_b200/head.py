@@ -107,14 +107,15 @@ class _SimpoFn(torch.autograd.Function):
         xb, w1, b1, w2, b2, targets, seq_off, scalars, pre, act, gspill, row_lse, row_ref, grad_seq = ctx.saved_tensors
         head = ctx.head
         H, E, V = head.n_embed, head.image_token_embed, head.image_token_size
-        flat = head._flat_grad_buffer() if ctx.need_dw else torch.empty(0, dtype=torch.float32, device=xb.device)
+        flat = head._flat_grad_buffer(ctx.group) if ctx.need_dw else torch.empty(0, dtype=torch.float32, device=xb.device)
         gs = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         wscale = 1.0 / _dist._world(ctx.group) if ctx.group is not None else 1.0
+        ex = head._peer_exchange(ctx.group) if ctx.need_dw else None
 
         def bwd(stage, reserve_sms, ws):
             return ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, True, ctx.hp[3], scalars, pre, act, gspill,
                                      row_lse, row_ref, grad_seq, gs, ctx.need_dx, flat, True, ctx.seg[0], ctx.seg[1],
-                                     stage, reserve_sms, ws, None, wscale)
+                                     stage, reserve_sms, ws, None, wscale, ex.args if ex is not None else None)
 
         dx = head._backward_and_sync(bwd, flat, ctx.group, ctx.need_dw, xb, seq_off, ctx.seg)
         gW1 = gB1 = gW2 = gB2 = None
@@ -157,16 +158,17 @@ class _LogpsFn(torch.autograd.Function):
         head = ctx.head
         H, E, V = head.n_embed, head.image_token_embed, head.image_token_size
         dev = xb.device
-        flat = head._flat_grad_buffer() if ctx.need_dw else torch.empty(0, dtype=torch.float32, device=dev)
+        flat = head._flat_grad_buffer(ctx.group) if ctx.need_dw else torch.empty(0, dtype=torch.float32, device=dev)
         one = torch.ones(1, dtype=torch.float32, device=dev)
         none = torch.empty(0, dtype=torch.float32, device=dev)
         gseq = grad_seq.detach().to(torch.float32).contiguous()
         wscale = 1.0 / _dist._world(ctx.group) if ctx.group is not None else 1.0
+        ex = head._peer_exchange(ctx.group) if ctx.need_dw else None
 
         def bwd(stage, reserve_sms, ws):
             return ops.head_bwd_impl(xb, w1, b1, w2, b2, targets, seq_off, ctx.average, 0.0, none, pre, act, gspill,
                                      row_lse, row_ref, gseq, one, ctx.need_dx, flat, False, ctx.seg[0], ctx.seg[1],
-                                     stage, reserve_sms, ws, None, wscale)
+                                     stage, reserve_sms, ws, None, wscale, ex.args if ex is not None else None)
 
         dx = head._backward_and_sync(bwd, flat, ctx.group, ctx.need_dw, xb, seq_off, ctx.seg)
         gW1 = gB1 = gW2 = gB2 = None
@@ -198,6 +200,7 @@ class FusedGenHead(torch.nn.Module):
         self._packed = None
         self._packed_key = None
         self._bwd_count = 0      # fused backward passes since the flat gradient buffer was last consumed / zeroed
+        self._flat_is_symmetric = False
 
     def invalidate(self) -> None:
         """drop the staged kernel operands (bf16 weights, fp32 biases, packed decode weights).  The cache is keyed on
@@ -254,12 +257,27 @@ class FusedGenHead(torch.nn.Module):
             self._packed_key = key
         return self._packed
 
-    def _flat_grad_buffer(self) -> torch.Tensor:
+    def _flat_grad_buffer(self, group=None) -> torch.Tensor:
         n = ops.flat_grad_numel(self.n_embed, self.image_token_embed, self.image_token_size)
         dev = self.vision_head.weight.device
-        if self._flat is None or self._flat.numel() != n or self._flat.device != dev:
+        ex = self._peer_exchange(group)
+        if ex is not None:
+            self._flat = ex.flat       # symmetric memory: the owners multicast the reduced shards into it
+            return self._flat
+        if self._flat is None or self._flat.numel() != n or self._flat.device != dev or self._flat_is_symmetric:
             self._flat = torch.empty(n, dtype=torch.float32, device=dev)
+            self._flat_is_symmetric = False
         return self._flat
+
+    def _peer_exchange(self, group):
+        """the peer-memory gradient exchange for this group (None: single rank, or the NCCL path)"""
+        if group is None or _dist._world(group) == 1:
+            return None
+        ex = _dist.peer_exchange_for(group, self.n_embed, self.image_token_embed, self.image_token_size,
+                                     self.vision_head.weight.device)
+        if ex is not None:
+            self._flat_is_symmetric = True
+        return ex
 
     def _backward_and_sync(self, bwd, flat: torch.Tensor, group, need_dw: bool, xb, seq_off, seg):
         """run the fused backward (``bwd(stage, reserve_sms, workspace) -> dx``) and sum the flat gradient over the
@@ -271,6 +289,19 @@ class FusedGenHead(torch.nn.Module):
         world = _dist._world(group) if group is not None else 1
         if need_dw:
             self._bwd_count += 1     # FusedHeadAdamW.step(use_last_backward=True) needs exactly one since the last step
+        ex = self._peer_exchange(group) if need_dw else None
+        if ex is not None:
+            # peer-memory exchange: the backward's weight-gradient stores already went to the owners' inboxes (the
+            # reduce-scatter rode inside the GEMM epilogues); what is left is barrier -> each owner sums its inbox and
+            # multicasts its shard into everyone's flat buffer -> barrier
+            if os.environ.get("OSPO_HEAD_OVERLAP", "1") == "0":
+                dx = bwd(0, 0, None)
+                ex.finish()
+                return dx
+            H, E, V = self.n_embed, self.image_token_embed, self.image_token_size
+            rows, _ = ops._x_dims(xb, seg[0])
+            ws = ops._workspace(rows, H, E, V, seq_off.numel() - 1, xb.device)
+            return ex.run_staged(lambda: bwd(1, 0, ws), lambda: bwd(2, 0, ws), lambda: bwd(4, 0, ws))
         if not need_dw or world == 1 or os.environ.get("OSPO_HEAD_OVERLAP", "1") == "0":
             dx = bwd(0, 0, None)
             if need_dw:

@@ -187,7 +187,8 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
              average: bool, sft_weight: float, scalars: Tensor, pre: Tensor, act: Tensor, logits: Tensor,
              row_lse: Tensor, row_ref: Tensor, grad_seq: Tensor, grad_scale: Tensor, need_dx: bool, flat_grads: Tensor,
              simpo: bool, seg_rows: int = 0, seg_off: int = 0, stage: int = 0, reserve_sms: int = 0,
-             ws: Optional[Tensor] = None, dx_out: Optional[Tensor] = None, wgrad_scale: float = 1.0) -> Tensor:
+             ws: Optional[Tensor] = None, dx_out: Optional[Tensor] = None, wgrad_scale: float = 1.0,
+             dp=None) -> Tensor:
     """the dgrad / wgrad GEMM pairs on the forward's softmax-minus-onehot spill.
     ``stage`` is a bit mask (0 = everything): 1 = up to dW2, 2 = db1 + dW1, 4 = dX, so the caller can overlap the
     all-reduces with the later parts (pass the same ``ws`` to every call; dx is produced by part 4).
@@ -218,6 +219,8 @@ def head_bwd_impl(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, lab
                     (pre, act, logits, row_lse, row_ref, grad_seq), (grad_scale, dx, fg), ws, seg)
     a.bwd_stage, a.reserve_sms = int(stage), int(reserve_sms)
     a.wgrad_scale = float(wgrad_scale)
+    if dp is not None:          # _abi.DpExchange: the weight-gradient stores go to the owners' inboxes (peer memory)
+        a.dp = C.cast(C.pointer(dp), C.c_void_p)
     lib = _abi.load()
     if simpo:
         _abi.check(lib.ospo_head_simpo_bwd(C.byref(a), _stream()), "ospo_head_simpo_bwd")

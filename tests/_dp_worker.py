@@ -27,6 +27,8 @@ def main():
     out_path = sys.argv[1]
     H, E, V, T, L = (int(v) for v in sys.argv[2:7])
     pairs_per_rank = int(sys.argv[7])
+    mode = sys.argv[8] if len(sys.argv) > 8 else "p2p"      # p2p: NVLink peer-memory exchange; nccl: NCCL all-reduce
+    os.environ["OSPO_HEAD_DP"] = mode
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -55,21 +57,30 @@ def main():
         torch.cuda.synchronize()
         return o, x.grad.clone(), fh._flat.clone()
 
-    res = {}
+    res = {"mode": mode}
     _, dx_loc, flat_loc = run(hidden, labels, None)
-    for mode in ("1", "0"):                       # staged (overlapped) and single all-reduce
-        os.environ["OSPO_HEAD_OVERLAP"] = mode
+    for ov in ("1", "0"):                         # NCCL path: staged (overlapped) and single all-reduce
+        os.environ["OSPO_HEAD_OVERLAP"] = ov
         _, dx_red, flat_red = run(hidden, labels, group)
         chk = D.dp_check(flat_loc, flat_red, group)
         chk["dx_local_bit_identical"] = bool(torch.equal(dx_red, dx_loc))
         w2g = fh.vision_head.weight.grad.float()
         chk["param_grad_matches_flat"] = bool(torch.equal(w2g, flat_red[:V * E].view(V, E).to(torch.bfloat16).float()))
-        res[f"overlap_{mode}"] = chk
+        # run to run: the exchange adds the contributions in a fixed order
+        _, _, flat_again = run(hidden, labels, group)
+        chk["bit_reproducible"] = bool(torch.equal(flat_again, flat_red))
+        res[f"overlap_{ov}"] = chk
+    ex = fh._peer_exchange(group)
+    res["peer_exchange_active"] = ex is not None
+    res["multicast"] = bool(ex is not None and ex.multicast)
+    if mode == "p2p" and ex is None:
+        res["overlap_1"]["status"] = "peer exchange expected but not active"
     # full batch on one GPU: DDP's average of per-rank means == the full-batch mean for equal shards
     _, _, flat_full = run(hidden_g, labels_g, None)
     rel = float((flat_red.double() - flat_full.double()).norm() / flat_full.double().norm())
     res["vs_full_batch_rel_fro"] = rel
     ok = all(v["status"] == "ok" and v["dx_local_bit_identical"] and v["param_grad_matches_flat"]
+             and (v["bit_reproducible"] or mode == "nccl")
              for k, v in res.items() if k.startswith("overlap")) and rel < 2e-3
     res["ok"] = ok
     flags = torch.tensor([1 if ok else 0], device=dev)

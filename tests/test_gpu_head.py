@@ -1498,11 +1498,14 @@ def test_staged_backward_equals_single_call(monkeypatch, parts):
 # ---------------------------------------------------------------------------------------------------
 # multi-GPU: the NCCL gradient exchange of FusedGenHead.simpo(process_group=...) checked by VALUE on hardware
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(512, 384, 16384, 64, 2, 2), (4096, 4096, 16384, 576, 1, 2)])
-def test_nccl_gradient_exchange_values(shape, tmp_path):
-    """one process per GPU under torchrun (NCCL): all ranks' exchanged flat gradients are bit-identical, equal the
-    mean of the pre-exchange local gradients and the single-GPU full-batch gradient; dX stays local
-    (ospo/utils/train.py:26-28, ospo/wrapper/train.py:419).  Skipped on a one-GPU box."""
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+@pytest.mark.parametrize("shape", [(512, 1024, 16384, 64, 2, 2), (4096, 4096, 16384, 576, 1, 2)])
+def test_nccl_gradient_exchange_values(shape, mode, tmp_path):
+    """one process per GPU under torchrun: all ranks' exchanged flat gradients are bit-identical, equal the mean of
+    the pre-exchange local gradients and the single-GPU full-batch gradient; dX stays local
+    (ospo/utils/train.py:26-28, ospo/wrapper/train.py:419).  mode p2p = the NVLink peer-memory exchange fused into the
+    weight-gradient epilogues (must be active, and bit-reproducible run to run); nccl = the NCCL all-reduce path.
+    Skipped on a one-GPU box."""
     import json
     import os
     import socket
@@ -1521,11 +1524,12 @@ def test_nccl_gradient_exchange_values(shape, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "_dp_worker.py"),
-           str(out)] + [str(v) for v in shape]
+           str(out)] + [str(v) for v in shape] + [mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(out.read_text())
     assert res["ok"] and res["ok_all_ranks"], res
+    assert res["peer_exchange_active"] == (mode == "p2p"), res
 
 
 def test_two_devices_in_one_process():

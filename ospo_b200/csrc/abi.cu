@@ -103,29 +103,11 @@ int current_device() {
   return dev;
 }
 
+// The library reads no environment variables: the defaults below are the measured best settings, and the validation
+// hooks at the end of include/ospo_head.h (ospo_head_set_*) are the only way to select another variant.
 void parse_knobs_once() {
   if (g_rt.ready) return;
   g_rt.ready = true;
-  if (const char* e = getenv("OSPO_HEAD_CTA_GROUP")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2) g_rt.cta_group = v;
-  }
-  if (const char* e = getenv("OSPO_HEAD_DECODE_FUSED")) g_rt.decode_fused = atoi(e) != 0;
-  if (const char* e = getenv("OSPO_HEAD_DECODE_PDL")) g_rt.decode_pdl = atoi(e) != 0;
-  if (const char* e = getenv("OSPO_HEAD_DECODE_CLUSTER")) g_rt.decode_cluster = atoi(e) != 0;
-  if (const char* e = getenv("OSPO_HEAD_TILE_SYNC")) g_rt.tile_sync = atoi(e) != 0;
-  if (const char* e = getenv("OSPO_HEAD_DECODE_MERGED")) g_rt.decode_merged = atoi(e) != 0;
-  if (const char* e = getenv("OSPO_HEAD_DECODE_L2_AHEAD")) g_rt.decode_l2_ahead = atoi(e) < 0 ? 0 : atoi(e);
-  if (const char* e = getenv("OSPO_HEAD_DECODE_NEXT_PREFETCH")) g_rt.decode_next_prefetch = atoi(e) != 0;
-  for (int k = 0; k < 6; ++k) {
-    char name[32];
-    snprintf(name, sizeof(name), "OSPO_HEAD_TUNE_%d", k);
-    if (const char* e = getenv(name)) sscanf(e, "%d,%d,%d", &g_rt.tune[k][0], &g_rt.tune[k][1], &g_rt.tune[k][2]);
-  }
-  if (const char* e = getenv("OSPO_HEAD_GROUP_M")) {
-    const int v = atoi(e);
-    if (v > 0) g_rt.group_m = v;
-  }
   if (cudaHostAlloc(reinterpret_cast<void**>(&g_rt.wd_host), 64 * sizeof(uint32_t),
                     cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
     for (int i = 0; i < 64; ++i) g_rt.wd_host[i] = 0;

@@ -36,10 +36,6 @@ struct GemmDims {
   // a_seg_*: K-major A (rows = M axis);  b_seg_*: MN-major B (rows = K axis).
   int a_seg_rows, a_seg_off;
   int b_seg_rows, b_seg_off;
-  // Two-domain rasterisation: B200 is two dies, each with its own half of the L2.  With die_split the first half
-  // of the clusters (which the hardware places on one die) walks the lower half of the M-blocks and the second
-  // half of the clusters the upper half, so operand tiles are shared between CTAs of the SAME die only.
-  int die_split;
   int trace_id;  // > 0: CTA timeline stamps into g_trace_buf (tuning aid)
   // Wave lock-step (0 / null = off): the clusters of a persistent grid start their i-th tile together for the first
   // sync_tiles tiles.  Tiles that run at the same time share operand panels through L2 only while they walk K at
@@ -214,14 +210,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int num_clusters = gridDim.x / CG;
   // work domain of this cluster: (first tile, stride, tile count, M-block window)
   int dom_first = cluster_id, dom_stride = num_clusters, dom_m0 = 0, dom_nm = num_m;
-  if (dims.die_split && num_clusters >= 2 && (num_clusters % 2) == 0 && num_m >= 2) {
-    const int hc = num_clusters / 2;
-    const int h = cluster_id >= hc ? 1 : 0;
-    dom_first = cluster_id - h * hc;
-    dom_stride = hc;
-    dom_m0 = h ? num_m / 2 : 0;
-    dom_nm = h ? num_m - num_m / 2 : num_m / 2;
-  }
   const int dom_tiles = dom_nm * num_n * ksplits;
 
   if (warp == 0 && lane == 0) {
@@ -564,16 +552,6 @@ inline int make_tmap_bf16_seg(CUtensorMap* map, const void* base, uint64_t segme
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-// process-wide switch for the two-domain (per-die) rasterisation; OSPO_HEAD_DIE_SPLIT=0/1
-inline int& g_die_split_ref() {
-  static int v = [] {
-    const char* e = getenv("OSPO_HEAD_DIE_SPLIT");
-    return e ? (atoi(e) != 0 ? 1 : 0) : 0;
-  }();
-  return v;
-}
-inline int g_die_split() { return g_die_split_ref(); }
-
 // describes a row-segmented operand for launch_gemm (seg_rows == 0: plain 2-D operand)
 struct SegOperand {
   int seg_rows = 0;   // logical rows per segment (multiple of 64)
@@ -637,7 +615,6 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   dims.a_seg_off = a_seg.seg_off;
   dims.b_seg_rows = b_seg.seg_rows;
   dims.b_seg_off = b_seg.seg_off;
-  dims.die_split = (g_die_split() && k_splits <= 1) ? 1 : 0;
   dims.trace_id = trace_id;
   dims.a_hint = a_evict == 1 ? kEvictFirst : a_evict == 2 ? kEvictLast : kEvictNormal;
   dims.b_hint = b_evict == 1 ? kEvictFirst : b_evict == 2 ? kEvictLast : kEvictNormal;
@@ -649,7 +626,7 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   if (clusters < 1) clusters = 1;
   if constexpr (Cfg::CLUSTER_SPLIT) {
     // exactly one (tile, k-split) item per CTA, the splits of a tile forming one cluster
-    if (num_tiles > num_sms || dims.k_splits > 8 || dims.die_split) return -100;
+    if (num_tiles > num_sms || dims.k_splits > 8) return -100;
     clusters = num_tiles;
   }
 
@@ -657,24 +634,18 @@ int launch_gemm(const void* a, int64_t lda, const void* b, int64_t ldb, int M, i
   dims.sync_tiles = 0;
   dims.sync_stride = 1;
   dims.sync_kb = 0;
-  if (sync_ctr != nullptr && !Cfg::CLUSTER_SPLIT && !dims.die_split && clusters >= 2 && num_tiles / clusters >= 2) {
+  if (sync_ctr != nullptr && !Cfg::CLUSTER_SPLIT && clusters >= 2 && num_tiles / clusters >= 2) {
     if (cudaMemsetAsync(sync_ctr, 0, sizeof(uint32_t), stream) != cudaSuccess) return -4;
     dims.sync_ctr = sync_ctr;
     dims.sync_tiles = num_tiles / clusters;  // the full waves; the ragged tail runs free
-    static const int stride_kb = [] {
-      const char* e = getenv("OSPO_HEAD_SYNC_STRIDE_KB");
-      return e ? atoi(e) : 128;  // short tiles (K = 4096: 64 k-blocks) lock-step every second tile: -1.4 % step time
-    }();
+    constexpr int stride_kb = 128;  // short tiles (K = 4096: 64 k-blocks) lock-step every second tile: -1.4 % step time
     const int kb_per_tile = (num_kb + dims.k_splits - 1) / dims.k_splits;
     dims.sync_stride = stride_kb > 0 ? (stride_kb + kb_per_tile - 1) / kb_per_tile : 1;
     if (dims.sync_stride < 1) dims.sync_stride = 1;
     // Tiles much longer than the 1152 k-blocks of configs[1]'s weight-gradient GEMMs (K = 73728 rows) are cut into
     // segments of about that length: at 256 pairs per GPU (K = 294912) wgrad W2 read 122 GB instead of 4 x 12.8 GB
     // with lock-step points at the tile starts only (profiles/r02_launches_256pairs_ncu.csv).
-    static const int seg_kb = [] {
-      const char* e = getenv("OSPO_HEAD_SYNC_SEG_KB");
-      return e ? atoi(e) : 1152;
-    }();
+    constexpr int seg_kb = 1152;
     if (seg_kb > 0 && kb_per_tile > seg_kb + seg_kb / 2) {
       const int nseg = (kb_per_tile + seg_kb / 2) / seg_kb;
       dims.sync_kb = (kb_per_tile + nseg - 1) / nseg;

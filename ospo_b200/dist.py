@@ -36,14 +36,10 @@ def _world(group) -> int:
 
 
 def _avg_op(group):
-    """Sum in the collective, scale afterwards.  On NCCL this lets the tuner pick the in-switch NVLS algorithm for the
-    268 MB dW2 message (NVSwitch multicast reduction, 24 channels); with ``ReduceOp.AVG`` it falls back to a 32-channel
-    ring, whose CTAs take more from the GEMMs running beside it: 30.1 vs 30.6 ms per step at 8 GPUs.
-    OSPO_HEAD_ALLREDUCE_OP=avg restores the averaging operator."""
-    import os
-
-    if dist.get_backend(group) == "nccl" and os.environ.get("OSPO_HEAD_ALLREDUCE_OP", "sum") == "avg":
-        return dist.ReduceOp.AVG
+    """Sum in the collective, scale afterwards (or before: see ``prescaled``).  On NCCL this lets the tuner pick the
+    in-switch NVLS algorithm for the 268 MB dW2 message (NVSwitch multicast reduction, 24 channels); with
+    ``ReduceOp.AVG`` it falls back to a 32-channel ring, whose CTAs take more from the GEMMs running beside it:
+    30.1 vs 30.6 ms per step at 8 GPUs (round 1)."""
     return dist.ReduceOp.SUM
 
 
@@ -123,9 +119,6 @@ class PeerGradExchange:
             a.inbox[i] = int(self.h_inbox.buffer_ptrs[i])
             a.flat[i] = int(self.h_flat.buffer_ptrs[i])
         mc = int(getattr(self.h_flat, "multicast_ptr", 0) or 0)
-        import os
-        if os.environ.get("OSPO_HEAD_DP_MULTICAST", "1") == "0":
-            mc = 0
         a.flat_multicast = mc if mc else None
         self.multicast = bool(mc)
         self.args = a
@@ -155,12 +148,10 @@ class PeerGradExchange:
         rank to get there, sums its dW2 shard and multicasts it while ``run_stage2()`` (db1, dW1) runs; the same for the
         remainder (dW1 rows, biases) while ``run_stage3()`` (dX) runs.  One barrier at the end: every rank's shards have
         landed in every flat buffer.  Returns run_stage3()'s result."""
-        import os
-
         main = torch.cuda.current_stream()
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream()
-            self._side_blocks = int(os.environ.get("OSPO_HEAD_DP_SIDE_BLOCKS", "64"))
+            self._side_blocks = 64   # a small grid shares the SMs with the GEMMs it runs beside (16 blocks: slower)
         run_stage1()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):

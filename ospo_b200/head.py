@@ -201,6 +201,7 @@ class FusedGenHead(torch.nn.Module):
         self._packed_key = None
         self._bwd_count = 0      # fused backward passes since the flat gradient buffer was last consumed / zeroed
         self._flat_is_symmetric = False
+        self.decode_packed = True   # decode step streams pre-packed 16 KB weight tiles (False: tensor-map loads of W1 / W2)
 
     def invalidate(self) -> None:
         """drop the staged kernel operands (bf16 weights, fp32 biases, packed decode weights).  The cache is keyed on
@@ -281,11 +282,12 @@ class FusedGenHead(torch.nn.Module):
 
     def _backward_and_sync(self, bwd, flat: torch.Tensor, group, need_dw: bool, xb, seq_off, seg):
         """run the fused backward (``bwd(stage, reserve_sms, workspace) -> dx``) and sum the flat gradient over the
-        data-parallel group (the kernels already stored it times 1 / world_size, so the sum is DDP's average).  With more than one rank the backward is staged: the all-reduce of dW2 (80 % of the
-        bytes) runs on NCCL's stream while db1 / dW1 / dX are computed (OSPO_HEAD_OVERLAP=3 also runs dX beside the
-        all-reduce of the remainder -- measured 0.2-0.6 ms slower at N = 2; OSPO_HEAD_OVERLAP=0 restores the single
-        all-reduce after the backward; OSPO_HEAD_OVERLAP_SMS > 0 leaves that many SMs free for the collective --
-        measured neutral at N = 2 and N = 8, so the default is 0)."""
+        data-parallel group (the kernels already stored it times 1 / world_size, so the sum is DDP's average).  With
+        more than one rank the backward is staged: the exchange of dW2 (80 % of the bytes) runs on a side stream while
+        db1 / dW1 / dX are computed.  OSPO_HEAD_OVERLAP=0 restores the single exchange after the backward;
+        OSPO_HEAD_DP=p2p selects the NVLink peer-memory exchange instead of the NCCL all-reduce (dist.py).
+        (Measured and dropped in round 1: dX as a third part beside the second all-reduce, and SMs reserved for the
+        collective.)"""
         world = _dist._world(group) if group is not None else 1
         if need_dw:
             self._bwd_count += 1     # FusedHeadAdamW.step(use_last_backward=True) needs exactly one since the last step
@@ -310,11 +312,7 @@ class FusedGenHead(torch.nn.Module):
         H, E, V = self.n_embed, self.image_token_embed, self.image_token_size
         rows, _ = ops._x_dims(xb, seg[0])
         ws = ops._workspace(rows, H, E, V, seq_off.numel() - 1, xb.device)
-        reserve = int(os.environ.get("OSPO_HEAD_OVERLAP_SMS", "0"))
-        if os.environ.get("OSPO_HEAD_OVERLAP", "1") == "3":      # three parts: dX beside the second all-reduce
-            return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(2, reserve, ws),
-                                                lambda: bwd(4, reserve, ws), prescaled=True)
-        return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(6, reserve, ws),
+        return _dist.staged_allreduce_mean_(flat, V * E, group, lambda: bwd(1, 0, ws), lambda: bwd(6, 0, ws),
                                             prescaled=True)
 
     @staticmethod
@@ -405,7 +403,7 @@ class FusedGenHead(torch.nn.Module):
             if embeds_out is None:
                 embeds_out = torch.empty(2 * P, wb.shape[0], dtype=torch.bfloat16, device=h.device)
             ne = (e, wa, ba, wb, bb, embeds_out, next_embeds._table_or_none())
-        packed = self._decode_packed(p) if (h.shape[0] <= 32 and os.environ.get("OSPO_HEAD_DECODE_PACKED", "1") != "0") else None
+        packed = self._decode_packed(p) if (h.shape[0] <= 32 and self.decode_packed) else None
         ids, logits = ops.cfg_sample_impl(h, p.w1, p.b1, p.w2, p.b2, float(cfg_weight), float(temperature), u,
                                           bool(greedy), mm, bool(return_logits), out, ne, packed)
         if next_embeds is not None:

@@ -870,9 +870,9 @@ def test_cfg_sample_packed_weights_equal_tensor_map_path(monkeypatch):
         h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16).to(dev)
         u = torch.rand(P, generator=g).to(dev)
         ids_p, lg_p = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, return_logits=True)
-        monkeypatch.setenv("OSPO_HEAD_DECODE_PACKED", "0")
+        fh.decode_packed = False
         ids_t, lg_t = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, return_logits=True)
-        monkeypatch.delenv("OSPO_HEAD_DECODE_PACKED")
+        fh.decode_packed = True
         torch.cuda.synchronize()
         assert torch.equal(lg_p, lg_t) and torch.equal(ids_p, ids_t)
 
@@ -1447,7 +1447,7 @@ def test_kernel_operand_cache_survives_inference_mode_and_invalidate():
     assert stale == loss0 and fresh != loss0
     assert ids0.shape == (2,)
 
-@pytest.mark.parametrize("parts", ["1", "3"])
+@pytest.mark.parametrize("parts", ["1"])
 def test_staged_backward_equals_single_call(monkeypatch, parts):
     """the staged backward used to overlap the all-reduces (part 1 up to dW2, then db1 + dW1 + dX together or as
     parts 2 and 4) produces bit-identical gradients to the single-call backward"""

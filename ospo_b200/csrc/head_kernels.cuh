@@ -1,6 +1,7 @@
-// Non-GEMM kernels of the image-token head path: log-sum-exp merge, per-sequence log-prob
-// reduction, the SimPO scalar stage, the softmax-minus-onehot producer for the backward GEMM pair,
-// bias-gradient column sums, and the CFG merge + inverse-CDF sampler.
+// Non-GEMM kernels of the image-token head path: log-sum-exp merge (+ exponent-window check), the one-hot fix-up of
+// the forward's softmax-numerator spill, per-sequence log-prob reduction, the SimPO scalar stage, the per-row weights
+// of the backward GEMM pair, fixed-order column sums for the bias gradients, the peer-memory gradient exchange, and
+// the CFG merge + inverse-CDF sampler.
 // All are HBM- or latency-bound; grids are sized from the data, loads are 16-byte vectors.
 #pragma once
 

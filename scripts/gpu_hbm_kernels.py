@@ -1,5 +1,5 @@
 """One launch of every HBM-bound side kernel at the 7B sizes (for an ncu metrics pass): clip + AdamW, squared norm,
-softmax-minus-onehot producer and db1 column sums (through a SimPO step), weight packing."""
+db2 / db1 column sums (through a SimPO step), weight packing."""
 import sys
 from pathlib import Path
 

@@ -54,7 +54,7 @@ def test_product_arm_refuses_to_run_without_a_gpu():
 
 
 def test_committed_bench_line_carries_the_contract():
-    line = (ROOT / "profiles" / "r01_bench_final2_n1.json").read_text().strip().splitlines()[-1]
+    line = (ROOT / "profiles" / "r02_bench_final_n1.json").read_text().strip().splitlines()[-1]
     d = json.loads(line)
     for k in CONTRACT_KEYS + ("clocks", "roofline"):
         assert k in d, k
@@ -74,3 +74,16 @@ def test_committed_bench_line_carries_the_contract():
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"]
     dec = d["cfg"]["roofline"]
     assert dec["bound"] == "hbm" and dec["frac"] == pytest.approx(dec["achieved"] / dec["peak"], rel=1e-9)
+    # round 2: no softmax-minus-onehot producer pass, peak memory reported, decode latency beside the cadence
+    assert "dlogits_producer" not in d["kernels"] and d["memory"]["peak_bytes"] > 0
+    dep = d["cfg"]["dependent_chain"]
+    assert dep["us_per_step_dependent"] > d["cfg"]["us_per_step"]
+    assert d["cfg"]["dependent_chain_embed_table"]["us_per_step_dependent"] < dep["us_per_step_dependent"]
+    assert d["cpu_baseline"]["config1"]["value"] > 0
+
+
+def test_committed_multi_gpu_lines_carry_a_passed_dp_check():
+    for name in ("r02_bench_n2.json", "r02_bench_n8_nccl.json", "r02_bench_n8_p2p2.json"):
+        d = json.loads((ROOT / "profiles" / name).read_text().strip().splitlines()[-1])
+        assert d["n_gpus"] > 1 and d["dp_check"]["status"] == "ok" and d["dp_check"]["ranks_bit_identical"] is True
+        assert d["dp_check"]["world"] == d["n_gpus"]

@@ -618,6 +618,30 @@ def main():
         dp = D.dp_check(flat_local, head._flat, group)
         del flat_local
         sync_all()
+        # how much of the N-GPU step is waiting for the slowest board: the same step WITHOUT any exchange, timed on
+        # every rank separately (a synchronous data-parallel step cannot be faster than its slowest rank's compute)
+        def local_step():
+            head.zero_grad(set_to_none=True)
+            hh2 = hidden.detach().requires_grad_(True)
+            head.simpo(hh2, labels, image_span=span, process_group=None, **HP).loss.backward()
+
+        for _ in range(3):
+            local_step()
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(5):
+            local_step()
+        l1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([l0.elapsed_time(l1) / 5], device=dev)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        local_ms = [float(t) for t in every]
+        dp["local_step_ms_per_rank_no_exchange"] = local_ms
+        dp["slowest_rank_local_ms"] = max(local_ms)
+        dp["exchange_and_sync_overhead_ms"] = ms_step - max(local_ms)
+        sync_all()
 
     # ---- per-kernel table + roofline of the dominant kernel ---------------------------------------
     HE, EV = H7B * E7B, E7B * V

@@ -1034,6 +1034,81 @@ def test_generate_loop_mirror():
         assert torch.equal(ids.to(torch.int32), toks[:, i])
 
 
+
+def test_generate_loop_over_hf_llama_backbone_with_kv_cache():
+    """`generate_image_tokens` (mirror of image_generation.py:143-171) over a real -- tiny, random-init -- HF LlamaModel
+    with a KV cache, a left-padded prompt with an attention mask, `gen_embed` and the `mlp_gelu` aligner:
+      * the fused chain (head -> merge + sample -> gen_embed -> gen_aligner in one launch chain) with the aligner
+        streamed and with the aligner memoised per code produce the same tokens and the same embeddings;
+      * a plain-torch restatement of the reference loop, teacher-forced with those tokens and fed the same embeddings,
+        reproduces every step's last hidden state bit for bit (KV cache, mask growth and position bookkeeping are the
+        reference's), its bf16 head logits match the fused step's logits, its aligner output matches the fused
+        embeddings, and the oracle sampler on the fused logits returns the fused ids."""
+    from transformers import LlamaConfig, LlamaModel
+
+    from ospo_b200 import FusedGenImgEmbeds
+    from ospo_b200.generate import generate_image_tokens
+
+    dev = _cuda()
+    torch.manual_seed(7)
+    D, V, P, n, Lp = 256, 16384, 3, 10, 6
+    cfg = LlamaConfig(hidden_size=D, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=64, max_position_embeddings=128)
+    backbone = LlamaModel(cfg).to(dev).to(torch.bfloat16).eval()
+    head_b = O.make_head(D, D, V, seed=71, w2_gain=4.0).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    head_t = head_b.to(dev)
+    gen_embed = torch.nn.Embedding(V, 8).to(dev).to(torch.bfloat16)
+    aligner = torch.nn.Module()
+    aligner.layers = torch.nn.Sequential(torch.nn.Linear(8, D), torch.nn.GELU(), torch.nn.Linear(D, D)).to(dev).to(torch.bfloat16)
+    g = torch.Generator().manual_seed(72)
+    prompt = torch.randn(2 * P, Lp, D, generator=g).to(torch.bfloat16).to(dev)
+    mask0 = torch.ones(2 * P, Lp, dtype=torch.long, device=dev)
+    mask0[1::2, 1:Lp - 1] = 0                       # uncond rows: all but first / last token padded (:132-141)
+    u = torch.rand(n, P, generator=g).to(dev)
+
+    def make_step(record):
+        def backbone_step(embeds, mask, past):
+            out = backbone(inputs_embeds=embeds, attention_mask=mask, use_cache=True, past_key_values=past)
+            record.append((embeds.clone(), out.last_hidden_state[:, -1, :].clone()))
+            return out.last_hidden_state, out.past_key_values
+        return backbone_step
+
+    runs = []
+    with torch.no_grad():
+        for table in (False, True):
+            fe = FusedGenImgEmbeds(gen_embed, aligner)
+            if table:
+                fe.build_table()
+            rec = []
+            toks = generate_image_tokens(fh, make_step(rec), fe, prompt, mask0, image_token_num_per_image=n, uniforms=u)
+            torch.cuda.synchronize()
+            runs.append((toks, rec))
+    (toks, rec), (toks_t, rec_t) = runs
+    assert toks.shape == (P, n) and torch.equal(toks, toks_t)
+    for (e0, h0), (e1, h1) in zip(rec, rec_t):
+        assert torch.equal(e0, e1) and torch.equal(h0, h1)
+    # plain-torch restatement of the reference loop, teacher-forced with the fused loop's tokens
+    with torch.no_grad():
+        past, embeds, mask = None, prompt, mask0
+        for i in range(n):
+            out = backbone(inputs_embeds=embeds, attention_mask=mask, use_cache=True, past_key_values=past)   # :150-153
+            past = out.past_key_values
+            hidden = out.last_hidden_state[:, -1, :]                                                            # :154-156
+            assert torch.equal(hidden, rec[i][1]), f"step {i}: hidden state differs (mask / KV-cache bookkeeping)"
+            ref_logits = head_t(hidden)
+            ids_f, lg_f = fh.cfg_sample(hidden, 5.0, 1.0, uniforms=u[i], return_logits=True)
+            torch.testing.assert_close(lg_f.float(), ref_logits.float(), rtol=2e-2, atol=3e-2)
+            oid, *_ = O.cfg_sample_det(lg_f.cpu(), 5.0, 1.0, u[i].cpu(), merge_mode=0)
+            assert torch.equal(ids_f.cpu(), oid) and torch.equal(ids_f.to(torch.int32), toks[:, i])
+            both = torch.stack([ids_f, ids_f], dim=1).view(-1)                                                  # :166
+            ref_emb = aligner.layers(gen_embed(both))                                                            # :167
+            if i + 1 < n:
+                torch.testing.assert_close(rec[i + 1][0][:, 0].float(), ref_emb.float(), rtol=2e-2, atol=2e-2)
+                embeds = rec[i + 1][0]                 # the fused loop's embeddings: both loops see the same inputs
+            mask = torch.cat([mask, torch.ones(2 * P, 1, dtype=mask.dtype, device=dev)], dim=1)                 # :170-171
+
+
 # ---------------------------------------------------------------------------------------------------
 # integration: patched train wrapper over a real (tiny) HF Llama backbone  (BASELINE.json configs[4] in miniature)
 # ---------------------------------------------------------------------------------------------------

@@ -71,6 +71,12 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// a + b for a product a that must keep its own rounding.  ptxas 12.9 contracts mul.rn.f32x2 followed by add.rn.f32x2
+// into one FFMA2 (the "explicit rounding mode is never fused" rule of the scalar forms is not applied to the packed
+// ones, with or without --fmad=false), which rounds t log2 e + 1.5 * 2^23 once instead of twice and can move n by one
+// at a tie.  Written as fma(a, 1, b) -- exactly a + b, one rounding -- there is no multiply-add pair left to contract.
+// tests/test_abi_cpu.py checks the library's SASS for a fused form of this step.
+__device__ __forceinline__ uint64_t f2_add_nofuse(uint64_t a, uint64_t b) { return f2_fma(a, f2_pack(1.0f, 1.0f), b); }
 constexpr float kRintMagic = 12582912.0f;  // 1.5 * 2^23 = 0x4B400000
 __device__ __forceinline__ int exp_koff(float kt) { return __float_as_int(__fadd_rn(kt, kRintMagic)); }
 // 2^e for an integer e <= 0; 0 below -120 (pow2_factor on an integer)
@@ -105,12 +111,61 @@ __device__ __forceinline__ uint64_t exp_weight2p(uint64_t t, int koff0, int koff
 // identical bits without the two clamps.
 __device__ __forceinline__ uint64_t exp_weight2p_inrange(uint64_t t, int koff) {
   const uint64_t y = f2_mul(t, f2_pack(1.4426950408889634f, 1.4426950408889634f));
-  const uint64_t ym = f2_add(y, f2_pack(kRintMagic, kRintMagic));
+  const uint64_t ym = f2_add_nofuse(y, f2_pack(kRintMagic, kRintMagic));
   const uint64_t n = f2_add(ym, f2_pack(-kRintMagic, -kRintMagic));
   float ym0, ym1;
   f2_unpack(ym, ym0, ym1);
   const float f0 = pow2_factor_i(__float_as_int(ym0) - koff);
   const float f1 = pow2_factor_i(__float_as_int(ym1) - koff);
+  uint64_t r = f2_fma(n, f2_pack(-0.693145751953125f, -0.693145751953125f), t);
+  r = f2_fma(n, f2_pack(-1.42860682030941723212e-6f, -1.42860682030941723212e-6f), r);
+  uint64_t p = f2_pack(1.3888888888888889e-03f, 1.3888888888888889e-03f);
+  p = f2_fma(p, r, f2_pack(8.3333333333333332e-03f, 8.3333333333333332e-03f));
+  p = f2_fma(p, r, f2_pack(4.1666666666666664e-02f, 4.1666666666666664e-02f));
+  p = f2_fma(p, r, f2_pack(1.6666666666666666e-01f, 1.6666666666666666e-01f));
+  p = f2_fma(p, r, f2_pack(0.5f, 0.5f));
+  p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
+  p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
+  return f2_mul(p, f2_pack(f0, f1));
+}
+// The clamp-free form with the 2^-120 cut-off folded into the exponent construction: the polynomial is evaluated
+// with every coefficient times 64 (a power-of-two scaling commutes with each rounding of the Horner chain, so
+// P64(r) = 64 P(r) bit for bit) and the scale is 2^(n - kt - 6), whose bits are  max(n - kt + 121, 0) << 23:
+// for n - kt >= -120 that is the normal number 2^(n - kt - 6) and P64(r) 2^(n - kt - 6) = P(r) 2^(n - kt) exactly
+// (both factors and the product are normal), below the cut-off it is +0.  One add-max and one shift per code
+// instead of a subtraction, a shift-add, a compare and a select.  kcut = exp_koff(kt) - 121.
+__device__ __forceinline__ uint64_t exp_weight2p_cut(uint64_t t, int kcut) {
+  const uint64_t y = f2_mul(t, f2_pack(1.4426950408889634f, 1.4426950408889634f));
+  const uint64_t ym = f2_add_nofuse(y, f2_pack(kRintMagic, kRintMagic));
+  const uint64_t n = f2_add(ym, f2_pack(-kRintMagic, -kRintMagic));
+  float ym0, ym1;
+  f2_unpack(ym, ym0, ym1);
+  const float f0 = __int_as_float(max(__float_as_int(ym0) - kcut, 0) << 23);
+  const float f1 = __int_as_float(max(__float_as_int(ym1) - kcut, 0) << 23);
+  uint64_t r = f2_fma(n, f2_pack(-0.693145751953125f, -0.693145751953125f), t);
+  r = f2_fma(n, f2_pack(-1.42860682030941723212e-6f, -1.42860682030941723212e-6f), r);
+  uint64_t p = f2_pack(64.0f * 1.3888888888888889e-03f, 64.0f * 1.3888888888888889e-03f);
+  p = f2_fma(p, r, f2_pack(64.0f * 8.3333333333333332e-03f, 64.0f * 8.3333333333333332e-03f));
+  p = f2_fma(p, r, f2_pack(64.0f * 4.1666666666666664e-02f, 64.0f * 4.1666666666666664e-02f));
+  p = f2_fma(p, r, f2_pack(64.0f * 1.6666666666666666e-01f, 64.0f * 1.6666666666666666e-01f));
+  p = f2_fma(p, r, f2_pack(32.0f, 32.0f));
+  p = f2_fma(p, r, f2_pack(64.0f, 64.0f));
+  p = f2_fma(p, r, f2_pack(64.0f, 64.0f));
+  return f2_mul(p, f2_pack(f0, f1));
+}
+// The same weights again when, in addition, no code of the caller's batch underflows the 2^-120 cut-off
+// (n - kt >= -120 for all of them): 2^(n - kt) is then always the plain exponent-field construction, and its bits are
+// (ym_bits << 23) + kbias with kbias = 0x3F800000 - (koff << 23) -- one shift-add per code instead of a subtraction,
+// a shift-add, a compare and a select.  exp_kbias(koff) is computed once per segment.
+__device__ __forceinline__ uint32_t exp_kbias(int koff) { return 0x3F800000u - (static_cast<uint32_t>(koff) << 23); }
+__device__ __forceinline__ uint64_t exp_weight2p_nounderflow(uint64_t t, uint32_t kbias) {
+  const uint64_t y = f2_mul(t, f2_pack(1.4426950408889634f, 1.4426950408889634f));
+  const uint64_t ym = f2_add_nofuse(y, f2_pack(kRintMagic, kRintMagic));
+  const uint64_t n = f2_add(ym, f2_pack(-kRintMagic, -kRintMagic));
+  float ym0, ym1;
+  f2_unpack(ym, ym0, ym1);
+  const float f0 = __uint_as_float((__float_as_uint(ym0) << 23) + kbias);
+  const float f1 = __uint_as_float((__float_as_uint(ym1) << 23) + kbias);
   uint64_t r = f2_fma(n, f2_pack(-0.693145751953125f, -0.693145751953125f), t);
   r = f2_fma(n, f2_pack(-1.42860682030941723212e-6f, -1.42860682030941723212e-6f), r);
   uint64_t p = f2_pack(1.3888888888888889e-03f, 1.3888888888888889e-03f);

@@ -509,85 +509,105 @@ pack_weight_kernel(const __nv_bfloat16* __restrict__ w, int rows, int cols, uint
 // the logits are still in tensor memory.  greedy: argmax_v t_v, lowest index on ties.
 // ---------------------------------------------------------------------------
 // The descent shared by the stand-alone sampler and the finish kernel of the fused decode step.
-// Shared-memory layout of the 512 rescaled segment sums: one padding word per 32-segment group, so that the 16
-// threads which each add up one group (stride 33 words) hit 16 different banks instead of one.
-constexpr int SEG_PAD_WORDS = SAMPLE_THREADS + SAMPLE_THREADS / SAMPLE_GRP;
-__device__ __forceinline__ int seg_slot(int seg) { return seg + seg / SAMPLE_GRP; }
+// Shared-memory layout of the 512 rescaled segment sums: every 32-segment group starts on a 16-byte boundary and is
+// followed by four padding words, so that a group is read as eight 16-byte words and the 16 lanes which each add up
+// one group (stride 36 words) cover all banks per quarter-warp.
+constexpr int SEG_GRP_PITCH = SAMPLE_GRP + 4;
+constexpr int SEG_PAD_WORDS = (SAMPLE_THREADS / SAMPLE_GRP) * SEG_GRP_PITCH;
+__device__ __forceinline__ int seg_slot(int seg) { return seg + (seg / SAMPLE_GRP) * (SEG_GRP_PITCH - SAMPLE_GRP); }
+constexpr int DESCENT_SCRATCH = 72;  // floats of 16-byte aligned shared memory private to the descending warp
 
 // The descent, executed by ONE WARP.  seg_sum[512] (already rescaled to the global exponent, padded slots) lives in
 // shared memory.  The oracle's sequential form is  "base = 0; for each element: nxt = base + x; if (nxt > target)
 // stop; base = nxt"  with the last element winning when nothing stops.  Here every lane evaluates the running sum of
-// a level redundantly (the same additions in the same order), lane i keeps the value before and after element i,
-// and one ballot finds the first crossing: a 16 / 32-step chain of dependent additions per level instead of a
-// chain of add + compare + select.
+// a level redundantly (the same additions in the same order) and leaves every partial sum in the warp's scratch
+// (pref[i] = the sum before element i; all lanes store the same value to the same word); afterwards lane i picks up
+// pref[i + 1] and one ballot finds the first crossing.  A level costs one addition and one store per element (the
+// elements arrive four at a time) -- a compare + two selects per element in the chain made the serial tail of the
+// sampler, 950 instructions per draw, the limiter of the whole kernel.
 // Group sums first (lane g < 16 adds group g's 32 segment sums in order), then the levels group -> segment.
-__device__ __forceinline__ void warp_descent_segments(const float* seg_sum, float* grp_sum, float u01, int lane,
-                                                      int& segi, float& base, float& target) {
+__device__ __forceinline__ float chain4(float run, const float4 v, float* pref) {
+  run = __fadd_rn(run, v.x);
+  pref[0] = run;
+  run = __fadd_rn(run, v.y);
+  pref[1] = run;
+  run = __fadd_rn(run, v.z);
+  pref[2] = run;
+  run = __fadd_rn(run, v.w);
+  pref[3] = run;
+  return run;
+}
+__device__ __forceinline__ void warp_descent_segments(const float* seg_sum, float* grp_sum, float* scratch, float u01,
+                                                      int lane, int& segi, float& base, float& target) {
   constexpr int NGRP = SAMPLE_THREADS / SAMPLE_GRP;  // 16
   if (lane < NGRP) {
+    const float4* gp = reinterpret_cast<const float4*>(seg_sum + lane * SEG_GRP_PITCH);
     float g = 0.0f;
-#pragma unroll 8
-    for (int j = 0; j < SAMPLE_GRP; ++j) g = __fadd_rn(g, seg_sum[seg_slot(lane * SAMPLE_GRP + j)]);
+#pragma unroll
+    for (int j = 0; j < SAMPLE_GRP / 4; ++j) {
+      const float4 v = gp[j];
+      g = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(g, v.x), v.y), v.z), v.w);
+    }
     grp_sum[lane] = g;
   }
   __syncwarp();
-  float before = 0.0f, after = 0.0f, run = 0.0f;
+  float* pref = scratch;
+  float run = 0.0f;
+  pref[0] = 0.0f;
 #pragma unroll
-  for (int g = 0; g < NGRP; ++g) {
-    const float nxt = __fadd_rn(run, grp_sum[g]);
-    if (g == lane) {
-      before = run;
-      after = nxt;
-    }
-    run = nxt;
-  }
+  for (int g = 0; g < NGRP / 4; ++g) run = chain4(run, reinterpret_cast<const float4*>(grp_sum)[g], pref + 4 * g + 1);
+  __syncwarp();
   target = __fmul_rn(u01, run);  // run = Z
-  uint32_t hit = __ballot_sync(0xffffffffu, lane < NGRP - 1 && after > target);
+  uint32_t hit = __ballot_sync(0xffffffffu, lane < NGRP - 1 && pref[(lane & (NGRP - 1)) + 1] > target);
   const int g_win = hit ? __ffs(hit) - 1 : NGRP - 1;
-  run = __shfl_sync(0xffffffffu, before, g_win);
+  run = pref[g_win];
+  __syncwarp();
+  pref[0] = run;
+  const float4* sp = reinterpret_cast<const float4*>(seg_sum + g_win * SEG_GRP_PITCH);
 #pragma unroll
-  for (int i = 0; i < SAMPLE_GRP; ++i) {
-    const float nxt = __fadd_rn(run, seg_sum[seg_slot(g_win * SAMPLE_GRP + i)]);
-    if (i == lane) {
-      before = run;
-      after = nxt;
-    }
-    run = nxt;
-  }
-  hit = __ballot_sync(0xffffffffu, lane < SAMPLE_GRP - 1 && after > target);
+  for (int i = 0; i < SAMPLE_GRP / 4; ++i) run = chain4(run, sp[i], pref + 4 * i + 1);
+  __syncwarp();
+  hit = __ballot_sync(0xffffffffu, lane < SAMPLE_GRP - 1 && pref[lane + 1] > target);
   const int sg_win = hit ? __ffs(hit) - 1 : SAMPLE_GRP - 1;
-  base = __shfl_sync(0xffffffffu, before, sg_win);
+  base = pref[sg_win];
   segi = g_win * SAMPLE_GRP + sg_win;
+  __syncwarp();  // pref is rewritten by the next level
 }
 // Last level: lane j holds the (rescaled) weight of code j of the winning segment; returns the code's index in it.
-__device__ __forceinline__ int warp_descent_codes(float wl, float base, float target, int lane) {
-  float after = 0.0f, run = base;
+__device__ __forceinline__ int warp_descent_codes(float wl, float base, float target, int lane, float* scratch) {
+  float* pref = scratch;
+  float* wv = scratch + 36;
+  wv[lane] = wl;
+  __syncwarp();
+  float run = base;
 #pragma unroll
-  for (int i = 0; i < SAMPLE_SEG; ++i) {
-    const float nxt = __fadd_rn(run, __shfl_sync(0xffffffffu, wl, i));
-    if (i == lane) after = nxt;
-    run = nxt;
-  }
-  const uint32_t hit = __ballot_sync(0xffffffffu, lane < SAMPLE_SEG - 1 && after > target);
+  for (int i = 0; i < SAMPLE_SEG / 4; ++i) run = chain4(run, reinterpret_cast<const float4*>(wv)[i], pref + 4 * i + 1);
+  __syncwarp();
+  const uint32_t hit = __ballot_sync(0xffffffffu, lane < SAMPLE_SEG - 1 && pref[lane + 1] > target);
+  __syncwarp();
   return hit ? __ffs(hit) - 1 : SAMPLE_SEG - 1;
 }
 
 // Persistent blocks: block b handles pairs b, b + gridDim.x, ...; logits row pitch ld; vocab must be 16384 (= 512 * 32).
 // Thread i < 512 owns segment i (codes 32 i .. 32 i + 31), register-resident.
-//  * While a pair is being evaluated (ALU-bound: ~25 instructions per code) the block's next pair travels
-//    global -> shared with cp.async, every thread fetching exactly the 2 x 64 bytes it will read back itself (no
-//    barrier; chunk positions are XOR-swizzled per thread so the 16-byte accesses are free of bank conflicts).
+//  * While a pair is being evaluated (ALU-bound: ~14 instructions per code) the block's next pair travels
+//    global -> shared as bulk copies (cp.async.bulk, one mbarrier per warp): every WARP fetches exactly the 2 x 2 KB
+//    its lanes read back themselves, lane 0 issuing the two copies once the warp has taken the current rows into
+//    registers -- no block-wide barrier, 2 instructions per pair instead of 8 16-byte cp.async per thread (whose
+//    sector-by-sector arrival cost 16 shared-memory write cycles per instruction).  The rows land linearly; lane l
+//    reads its four 16-byte chunks in the order q ^ ((l >> 1) & 3) so a quarter-warp covers all 32 banks.  The
+//    thread's codes are therefore held chunk-permuted in registers (slot q = chunk q ^ s): the tile exponent is a
+//    maximum and the butterfly tree sum adds chunk 0 + chunk 2 and chunk 1 + chunk 3 element-wise and then the two
+//    results -- both invariant under an XOR permutation of the chunks (IEEE addition commutes), so the segment sum
+//    has the same bits; the greedy arg-max and the merged-logits store use the true index.
 //  * Sampling: the serial part of a draw (global exponent, 16 sequential group sums, descent group -> segment ->
 //    code) belongs to two extra warps, one for the block's even pairs and one for the odd.  The 16 evaluating warps
-//    only deposit their segment sum and tile exponent in that tail warp's shared buffer (named barriers full[b] /
-//    empty[b]) and go on to the next pair; the tail warp rebuilds the 32 weights of the winning segment from the
+//    only deposit their segment sum and tile exponent in that tail warp's shared buffer (mbarriers full_bar[b] /
+//    empty_bar[b]) and go on to the next pair; the tail warp rebuilds the 32 weights of the winning segment from the
 //    logits (same operations, same bits) instead of asking its owner.
 //    With the CTA-wide barriers the draw used to need, the warps spent 4.7 cycles waiting per instruction issued.
 // WBF: MODE 0 with a bf16-exact cfg_weight -> the merge runs on the bf16x2 pipe (cfg_math.cuh)
 constexpr int SAMPLE_BLOCK = SAMPLE_THREADS + 64;  // sampling variant: + two tail warps (even / odd pairs of the block)
-constexpr int SAMPLE_HANDOVER = SAMPLE_THREADS + 32;  // threads on a full[b] / empty[b] barrier: evaluators + one tail warp
-__device__ __forceinline__ void named_bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int MODE, bool TDIV, bool WBF>
 __device__ __forceinline__ void merge_words(uint32_t wc, uint32_t wu, float cfg_weight, float temperature, float& t0,
@@ -601,49 +621,65 @@ __global__ void __launch_bounds__(GREEDY ? SAMPLE_THREADS : SAMPLE_BLOCK, 2)
 cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int vocab, float cfg_weight,
                         float temperature, const float* __restrict__ uniforms, int64_t* __restrict__ ids,
                         float* __restrict__ merged_out /* [P, V] optional */, int pairs) {
-  extern __shared__ uint4 next_rows[];  // [SAMPLE_THREADS][8]
-  __shared__ float seg_buf[2][SEG_PAD_WORDS];   // sampling: S relative to the tile exponent, rescaled in place by the tail
-  __shared__ float kt_buf[2][SAMPLE_THREADS];   // sampling: tile exponent, one copy per segment
-  __shared__ float grp_sums[2][SAMPLE_THREADS / SAMPLE_GRP];
+  extern __shared__ uint4 next_rows[];  // [2 rows][16 warps][2 KB]: the block's next pair, linear
+  __shared__ uint64_t row_bar[SAMPLE_THREADS / 32];  // one per evaluating warp: its 2 x 2 KB have landed
+  __shared__ uint64_t full_bar[2], empty_bar[2];
+  __shared__ __align__(16) float seg_buf[2][SEG_PAD_WORDS];  // sampling: S relative to the tile exponent, rescaled in place by the tail
+  __shared__ int kt_buf[2][SAMPLE_THREADS];  // sampling: tile exponent as exp_koff(kt) (an integer + a constant), one copy per segment
+  __shared__ __align__(16) float grp_sums[2][SAMPLE_THREADS / SAMPLE_GRP];
+  __shared__ __align__(16) float descent_scratch[2][DESCENT_SCRATCH];
   __shared__ float wmax[SAMPLE_THREADS / 32];   // greedy
   __shared__ int warg[SAMPLE_THREADS / 32];     // greedy
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  constexpr int FULL0 = 1, EMPTY0 = 3;  // named barriers: full[b] = 1 + b, empty[b] = 3 + b
+  // hand-over of buffer b (pairs k of the block with k & 1 == b) between the 16 evaluating warps and tail warp b:
+  // full_bar[b] collects one arrival per evaluating warp, empty_bar[b] the tail warp's.  mbarriers rather than named
+  // barriers: an evaluating warp never waits for its 15 siblings, only (two pairs later) for the tail warp, so the
+  // warps drift apart and their load / merge / scan phases overlap the others' FMA-bound weight phase.
+  if (tid < SAMPLE_THREADS / 32) mbar_init(&row_bar[tid], 1);
+  if (tid < 2) {
+    mbar_init(&full_bar[tid], SAMPLE_THREADS / 32);
+    mbar_init(&empty_bar[tid], 1);
+  }
+  fence_mbar_init();
+  __syncthreads();
 
   if (!GREEDY && warp >= SAMPLE_THREADS / 32) {
     // ===================== tail warps: one draw per pair; warp 16 takes the block's even pairs, warp 17 the odd =====
     const int b = warp - SAMPLE_THREADS / 32;
     float* grp_sum = grp_sums[b];
-    for (int p = blockIdx.x + b * gridDim.x; p < pairs; p += 2 * gridDim.x) {
+    uint32_t use = 0;  // how many times this buffer has been handed over
+    for (int p = blockIdx.x + b * gridDim.x; p < pairs; p += 2 * gridDim.x, ++use) {
       float* seg_sum = seg_buf[b];
-      const float* kts = kt_buf[b];
+      const int* kts = kt_buf[b];
       const float u01 = __ldg(uniforms + p);
-      named_bar_sync_n(FULL0 + b, SAMPLE_HANDOVER);
+      mbar_wait(&full_bar[b], use & 1, 0x5B00u + b);
       // global exponent K = max tile exponent; rescale the 512 segment sums (exact: powers of two)
-      float kt[SAMPLE_THREADS / 32];
-      float K = -3.0e38f;
+      int kq[SAMPLE_THREADS / 32];
+      int K = kts[lane];
+      kq[0] = K;
 #pragma unroll
-      for (int i = 0; i < SAMPLE_THREADS / 32; ++i) {
-        kt[i] = kts[i * 32 + lane];
-        K = fmaxf(K, kt[i]);
+      for (int i = 1; i < SAMPLE_THREADS / 32; ++i) {
+        kq[i] = kts[i * 32 + lane];
+        K = max(K, kq[i]);
       }
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) K = fmaxf(K, __shfl_xor_sync(0xffffffffu, K, off));
+      for (int off = 16; off > 0; off >>= 1) K = max(K, __shfl_xor_sync(0xffffffffu, K, off));
 #pragma unroll
       for (int i = 0; i < SAMPLE_THREADS / 32; ++i) {
-        const int sl = seg_slot(i * 32 + lane);
-        seg_sum[sl] = __fmul_rn(seg_sum[sl], pow2_factor(__fsub_rn(kt[i], K)));
+        const int sl = i * SEG_GRP_PITCH + lane;  // = seg_slot(i * 32 + lane)
+        seg_sum[sl] = __fmul_rn(seg_sum[sl], pow2_factor_i(kq[i] - K));
       }
       __syncwarp();
       int segi;
       float base, target;
-      warp_descent_segments(seg_sum, grp_sum, u01, lane, segi, base, target);
+      warp_descent_segments(seg_sum, grp_sum, descent_scratch[b], u01, lane, segi, base, target);
       // the winning segment's 32 weights again, lane j = code j (two codes per packed word, as in the evaluation)
-      const float kt_seg = kts[segi];
-      const float f = pow2_factor(__fsub_rn(kt_seg, K));
+      const int kseg = kts[segi];
+      const float kt_seg = __fsub_rn(__int_as_float(kseg), kRintMagic);  // exact: kseg is the bit pattern of kt + 1.5 * 2^23
+      const float f = pow2_factor_i(kseg - K);
       __syncwarp();
-      named_bar_arrive_n(EMPTY0 + b, SAMPLE_HANDOVER);  // the buffer is free for the pair after next
+      if (lane == 0) mbar_arrive(&empty_bar[b]);  // the buffer is free for the pair after next
       const uint32_t* rc = reinterpret_cast<const uint32_t*>(logits + static_cast<int64_t>(2 * p) * ld) + segi * (SAMPLE_SEG / 2);
       const uint32_t* ru = reinterpret_cast<const uint32_t*>(logits + static_cast<int64_t>(2 * p + 1) * ld) + segi * (SAMPLE_SEG / 2);
       float t0, t1;
@@ -651,37 +687,40 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
       float n;
       const float pr = exp_parts((lane & 1) ? t1 : t0, n);
       const float wl = __fmul_rn(__fmul_rn(pr, pow2_factor(__fsub_rn(n, kt_seg))), f);
-      const int j = warp_descent_codes(wl, base, target, lane);
+      const int j = warp_descent_codes(wl, base, target, lane, descent_scratch[b]);
       if (lane == 0) ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
     }
     return;
   }
 
   // ===================== evaluating warps =====================
-  uint4* mine = next_rows + tid * 8;
-  const int sw = tid & 7;
-  auto fetch = [&](int q) {
-    const uint4* lc = reinterpret_cast<const uint4*>(logits + static_cast<int64_t>(2 * q) * ld + tid * SAMPLE_SEG);
-    const uint4* lu = reinterpret_cast<const uint4*>(logits + static_cast<int64_t>(2 * q + 1) * ld + tid * SAMPLE_SEG);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      cp_async_16(mine + (i ^ sw), lc + i);
-      cp_async_16(mine + ((4 + i) ^ sw), lu + i);
-    }
-    cp_async_commit();
+  constexpr uint32_t kWarpRowBytes = 32 * SAMPLE_SEG * 2;      // 2 KB: one warp's share of a logits row
+  constexpr uint32_t kRowBytes = SAMPLE_THREADS * SAMPLE_SEG * 2;  // 32 KB
+  uint8_t* landing = reinterpret_cast<uint8_t*>(next_rows) + warp * kWarpRowBytes;  // this warp's cond share; uncond at + 32 KB
+  const int sw = (lane >> 1) & 3;  // chunk permutation of this lane: register slot q holds chunk q ^ sw
+  const uint8_t* mine = landing + lane * (SAMPLE_SEG * 2);
+  uint64_t* bar = &row_bar[warp];
+  const int64_t pair_stride = 2 * ld * static_cast<int64_t>(gridDim.x);  // elements between this block's pairs
+  const __nv_bfloat16* nxt = logits + static_cast<int64_t>(2 * blockIdx.x) * ld + warp * (32 * SAMPLE_SEG);  // next pair to fetch
+  auto fetch = [&]() {  // lane 0 only
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(bar, 2 * kWarpRowBytes);
+    bulk_load_evict_first(landing, nxt, kWarpRowBytes, bar);
+    bulk_load_evict_first(landing + kRowBytes, nxt + ld, kWarpRowBytes, bar);
   };
-  if (static_cast<int>(blockIdx.x) < pairs) fetch(blockIdx.x);
+  if (static_cast<int>(blockIdx.x) < pairs && lane == 0) fetch();
+  nxt += pair_stride;
   int k = 0;
   for (int p = blockIdx.x; p < pairs; p += gridDim.x, ++k) {
-    // ---- load + merge: t[j] for codes 32*tid + j ------------------------------------------------
+    // ---- load + merge: slot j of t = code 8 * ((j >> 3) ^ sw) + (j & 7) of segment tid -----------------
     float t[SAMPLE_SEG];
     {
       uint4 a[4], b[4];
-      cp_async_wait_all();
+      mbar_wait(bar, k & 1, 0x5A00u + warp);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        a[i] = mine[i ^ sw];
-        b[i] = mine[(4 + i) ^ sw];
+        a[i] = *reinterpret_cast<const uint4*>(mine + ((i ^ sw) << 4));
+        b[i] = *reinterpret_cast<const uint4*>(mine + kRowBytes + ((i ^ sw) << 4));
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -691,23 +730,39 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
           merge_words<MODE, TDIV, WBF>(wa[q], wb[q], cfg_weight, temperature, t[8 * i + 2 * q], t[8 * i + 2 * q + 1]);
       }
     }
-    // the rows of this block's next pair stream in while this one is evaluated (the values above are in registers)
-    if (p + static_cast<int>(gridDim.x) < pairs) fetch(p + gridDim.x);
+    // the rows of this block's next pair stream in while this one is evaluated (the warp's values are in registers)
+    __syncwarp();
+    if (p + static_cast<int>(gridDim.x) < pairs && lane == 0) fetch();
+    nxt += pair_stride;
     if (merged_out != nullptr) {
       float4* mo = reinterpret_cast<float4*>(merged_out + static_cast<int64_t>(p) * vocab + tid * SAMPLE_SEG);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mo[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+      for (int i = 0; i < 4; ++i) {
+        mo[2 * (i ^ sw)] = make_float4(t[8 * i], t[8 * i + 1], t[8 * i + 2], t[8 * i + 3]);
+        mo[2 * (i ^ sw) + 1] = make_float4(t[8 * i + 4], t[8 * i + 5], t[8 * i + 6], t[8 * i + 7]);
+      }
     }
 
     if constexpr (GREEDY) {
       // ---- arg-max (exact; lowest index wins ties) ----------------------------------------------
-      float lmax = t[0];
+      // per 8-code chunk in index order (strict > keeps the lowest index), then the four chunks by (value, index)
+      float lmax = 0.0f;
       int larg = 0;
 #pragma unroll
-      for (int j = 1; j < SAMPLE_SEG; ++j) {
-        if (t[j] > lmax) {
-          lmax = t[j];
-          larg = j;
+      for (int i = 0; i < 4; ++i) {
+        float cmax = t[8 * i];
+        int carg = 0;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+          if (t[8 * i + j] > cmax) {
+            cmax = t[8 * i + j];
+            carg = j;
+          }
+        }
+        carg += (i ^ sw) << 3;
+        if (i == 0 || cmax > lmax || (cmax == lmax && carg < larg)) {
+          lmax = cmax;
+          larg = carg;
         }
       }
       larg += tid * SAMPLE_SEG;
@@ -767,9 +822,17 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
       // ---- weights relative to K_tile and the segment's tree sum -------------------------------------
       const int koff = exp_koff(kt);
       uint64_t w[SAMPLE_SEG / 2];
-      if (inrange) {
+      // no code of the warp below the 2^-120 cut-off of its tile (n(min t) - kt >= -120; n is monotone in t)?
+      const bool nounderflow =
+          inrange && __all_sync(0xffffffffu, exp_koff(rintf(ylo)) - koff >= -120);
+      if (nounderflow) {
+        const uint32_t kbias = exp_kbias(koff);
 #pragma unroll
-        for (int j = 0; j < SAMPLE_SEG / 2; ++j) w[j] = exp_weight2p_inrange(f2_pack(t[2 * j], t[2 * j + 1]), koff);
+        for (int j = 0; j < SAMPLE_SEG / 2; ++j) w[j] = exp_weight2p_nounderflow(f2_pack(t[2 * j], t[2 * j + 1]), kbias);
+      } else if (inrange) {
+        const int kcut = koff - 121;
+#pragma unroll
+        for (int j = 0; j < SAMPLE_SEG / 2; ++j) w[j] = exp_weight2p_cut(f2_pack(t[2 * j], t[2 * j + 1]), kcut);
       } else {
 #pragma unroll
         for (int j = 0; j < SAMPLE_SEG / 2; ++j) w[j] = exp_weight2p(f2_pack(t[2 * j], t[2 * j + 1]), koff, koff);
@@ -777,10 +840,11 @@ cfg_merge_sample_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, in
       const float S = tree_sum32_packed(w);
       // ---- hand the segment over to the tail warp ----------------------------------------------------
       const int b = k & 1;
-      if (k >= 2) named_bar_sync_n(EMPTY0 + b, SAMPLE_HANDOVER);  // its draw of the pair before last is over
+      if (k >= 2) mbar_wait(&empty_bar[b], ((k >> 1) - 1) & 1, 0x5C00u + b);  // its draw of the pair before last is over
       seg_buf[b][seg_slot(tid)] = S;
-      kt_buf[b][tid] = kt;
-      named_bar_arrive_n(FULL0 + b, SAMPLE_HANDOVER);
+      kt_buf[b][tid] = koff;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[b]);
     }
   }
 }
@@ -877,8 +941,9 @@ template <bool EMBED>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ uniforms, int greedy,
                   int64_t* __restrict__ ids, int trace, EmbedUp eu) {
-  __shared__ float seg_sum[SEG_PAD_WORDS];
-  __shared__ float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
+  __shared__ __align__(16) float seg_sum[SEG_PAD_WORDS];
+  __shared__ __align__(16) float grp_sum[SAMPLE_THREADS / SAMPLE_GRP];
+  __shared__ __align__(16) float descent_scratch[DESCENT_SCRATCH];
   __shared__ float wmax[SAMPLE_THREADS / 32];
   __shared__ int bc_id;
   pdl_launch_dependents();  // successors may become resident and prefetch; they wait for our completion
@@ -935,10 +1000,10 @@ cfg_finish_kernel(CfgFusedBuffers b, int vocab, const float* __restrict__ unifor
     // group sums, descent group -> segment, then the winning segment's 32 weights (one coalesced load) -> code
     int segi;
     float base, target;
-    warp_descent_segments(seg_sum, grp_sum, u01, lane, segi, base, target);
+    warp_descent_segments(seg_sum, grp_sum, descent_scratch, u01, lane, segi, base, target);
     const float fs = pow2_factor(__fsub_rn(b.tile_k[p * ntile + segi / (SAMPLE_TILE / SAMPLE_SEG)], K));
     const float wl = __fmul_rn(__ldcg(b.wbuf + static_cast<int64_t>(p) * vocab + segi * SAMPLE_SEG + lane), fs);
-    const int j = warp_descent_codes(wl, base, target, lane);
+    const int j = warp_descent_codes(wl, base, target, lane, descent_scratch);
     if (lane == 0) {
       ids[p] = static_cast<int64_t>(segi) * SAMPLE_SEG + j;
       bc_id = segi * SAMPLE_SEG + j;

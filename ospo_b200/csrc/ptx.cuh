@@ -204,6 +204,16 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c
                : "memory");
 }
 
+// linear bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier; the line is
+// marked evict-first in L2 (data read exactly once)
+__device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(0x12F0000000000000ull)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             uint64_t hint) {
   asm volatile(

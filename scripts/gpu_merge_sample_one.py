@@ -11,7 +11,8 @@ from ospo_b200 import cfg_merge_sample  # noqa: E402
 dev = torch.device("cuda:0")
 steps, P, V = 576, 16, 16384
 g = torch.Generator(device=dev).manual_seed(5)
-lg = (torch.randn(steps, 2 * P, V, generator=g, device=dev) * 3).to(torch.bfloat16)
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 3.0  # 3: most tiles have codes under the 2^-120 cut-off; 1: none
+lg = (torch.randn(steps, 2 * P, V, generator=g, device=dev) * scale).to(torch.bfloat16)
 u = torch.rand(steps, P, generator=g, device=dev)
 for _ in range(3):
     ids = cfg_merge_sample(lg, 5.0, 1.0, uniforms=u)
@@ -22,4 +23,4 @@ for _ in range(10):
     cfg_merge_sample(lg, 5.0, 1.0, uniforms=u)
 e1.record()
 torch.cuda.synchronize()
-print("us per launch", e0.elapsed_time(e1) * 100, "checksum", int(ids.sum()))
+print("scale", scale, "us per launch", e0.elapsed_time(e1) * 100, "checksum", int(ids.sum()))

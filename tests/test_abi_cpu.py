@@ -295,3 +295,36 @@ def test_batched_preprocess_batch_matches_the_serial_reference_loop():
         for k in ("chosen_inputs_embeds", "rejected_inputs_embeds"):
             assert torch.equal(out[k], ref[k]), (which, k)
     assert ref["chosen_labels"].shape[1] == 9 + (S // 16) ** 2
+
+
+def test_packed_exp_rounding_step_is_not_contracted_in_the_sass():
+    """The samplers' n = rint(t log2 e) is  (rn(t * log2 e) + 1.5 * 2^23) - 1.5 * 2^23  on the packed fp32 pipe
+    (cfg_math.cuh); oracle/cfg_sample.c rounds the product before it rounds the sum.  ptxas contracts
+    mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 when it can, which rounds once and moves n at ties.  In every kernel of
+    the library each packed '+ 12582912' (FADD2, or FFMA2 with the multiplier 1 of f2_add_nofuse) must therefore
+    have its own packed multiply by log2 e in front of it."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", str(_abi.lib_path())], capture_output=True, text=True).stdout
+    per_fn, fn = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            per_fn[fn] = [0, 0]
+            continue
+        if fn is None:
+            continue
+        if re.search(r"\bFMUL2\b.*1\.44269502", line):
+            per_fn[fn][0] += 1
+        elif re.search(r"\b(FADD2|FFMA2)\b.*, 12582912 ;", line):
+            per_fn[fn][1] += 1
+    users = {k: v for k, v in per_fn.items() if v[1]}
+    assert users, "no kernel with the packed rounding step found: did the SASS mnemonics change?"
+    assert any("cfg_merge_sample_kernel" in k for k in users)
+    for k, (n_mul, n_magic) in users.items():
+        assert n_mul == n_magic, (k, n_mul, n_magic)

@@ -718,6 +718,12 @@ def test_cfg_merge_sample_bit_exact_vs_oracle(golden_dir):
     extra[0, :, 100:200] = extra[0, :, 100:101]            # runs of ties
     extra[1] = extra[1] * 8.0                              # wide range: most weights underflow to 0
     extra[2, 0::2] = extra[2, 1::2]                        # cond == uncond
+    # the 2^-120 cut-off of a tile, from both sides (the sampler's no-underflow form must hand over exactly there):
+    # cond == uncond so the merged logit is the value itself; tile maximum 0, single codes at n - K_tile = -119 ... -122
+    extra[3] = (torch.randn(8, 16384, generator=g) * 2.0 - 30.0).to(torch.bfloat16)
+    for k, v in enumerate((-82.5, -83.0, -83.5, -84.0, -84.5, -300.0)):
+        extra[3, :, 128 * (3 + 7 * k)] = 0.0
+        extra[3, :, 128 * (3 + 7 * k) + 33 + k] = v
     for lg, w, T in ((logits, 5.0, 1.0), (extra, 5.0, 1.0), (extra, 3.0, 0.7), (extra, 7.5, 1.3)):
         steps, twoP, V = lg.shape
         P = twoP // 2

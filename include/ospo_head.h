@@ -310,6 +310,11 @@ OSPO_API int ospo_head_set_decode_merged(int merged);
 OSPO_API int ospo_head_set_decode_l2_ahead(int kblocks);
 /* rasterisation group size (M-blocks walked together); pass 0 to query */
 OSPO_API int ospo_head_set_group_m(int group_m);
+/* k-splits of the two weight-gradient GEMMs: 0 (default) = chosen per shape so that the last wave of the persistent
+   grid is not left mostly empty (dW1 of the 7B head: 512 half-length work items instead of 256 tiles, both halves
+   added into the zeroed output -- two addends, order-independent bits), 1 = never split, 2 = always; -1 queries.
+   Returns the value in effect. */
+OSPO_API int ospo_head_set_wgrad_splitk(int splits);
 /* per training GEMM (kernel: 0 gemm1, 1 gemm2, 2 dact, 3 wgrad W2, 4 wgrad W1, 5 dgrad X): rasterisation group
    (0 = the global group_m) and the L2 eviction hints of its A / B operand loads (0 normal, 1 evict-first,
    2 evict-last); a negative argument leaves that setting unchanged */

@@ -190,6 +190,7 @@ EXPORTS = (
     "ospo_head_set_decode_l2_ahead",
     "ospo_head_set_group_m",
     "ospo_head_set_kernel_tune",
+    "ospo_head_set_wgrad_splitk",
     "ospo_head_profile_enable",
     "ospo_head_profile_read",
     "ospo_head_trace",
@@ -261,6 +262,8 @@ def load() -> C.CDLL:
     lib.ospo_head_set_group_m.restype = C.c_int
     lib.ospo_head_set_kernel_tune.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ospo_head_set_kernel_tune.restype = C.c_int
+    lib.ospo_head_set_wgrad_splitk.argtypes = [C.c_int]
+    lib.ospo_head_set_wgrad_splitk.restype = C.c_int
     lib.ospo_head_profile_enable.argtypes = [C.c_int]
     lib.ospo_head_profile_enable.restype = C.c_int
     lib.ospo_head_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]

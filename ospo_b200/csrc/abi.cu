@@ -50,6 +50,7 @@ struct Runtime {
   // hints of either polarity raise the traffic (a line marked evict-first leaves L2 before the sibling clusters of
   // the same wave have read it), so they stay off.
   int tune[6][3] = {{8, 0, 0}, {16, 0, 0}, {8, 0, 0}, {8, 0, 0}, {8, 0, 0}, {8, 0, 0}};
+  int wgrad_splitk = 0;  // k-splits of the weight-gradient GEMMs: 0 = per shape (gemm_bwd.cu: pick_wgrad_splits), 1 / 2 forced
   int decode_l2_ahead = 16;  // merged kernel: W2 k-blocks per CTA requested into L2 while the activation flag is closed
   int decode_next_prefetch = 1;  // merged kernel: the aligner Linear's weight is requested into L2 behind the last W2 tile
   bool trace_on = false;   // ospo_head_trace installed a timeline buffer
@@ -197,6 +198,7 @@ LaunchCtx make_ctx(cudaStream_t s) {
   c.num_sms = dev >= 0 ? g_dev[dev].num_sms : 0;
   c.cta_group = g_rt.cta_group;
   c.group_m = g_rt.group_m;
+  c.wgrad_splitk = g_rt.wgrad_splitk;
   c.stream = s;
   c.pdl = false;
   c.trace = g_rt.trace_on;
@@ -1044,6 +1046,12 @@ int ospo_head_set_group_m(int group_m) {
   runtime_init();
   if (group_m > 0) g_rt.group_m = group_m;
   return g_rt.group_m;
+}
+
+int ospo_head_set_wgrad_splitk(int splits) {
+  runtime_init();
+  if (splits >= 0 && splits <= 2) g_rt.wgrad_splitk = splits;
+  return g_rt.wgrad_splitk;
 }
 
 int ospo_head_set_kernel_tune(int kernel, int group_m, int a_evict, int b_evict) {

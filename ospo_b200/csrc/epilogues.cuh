@@ -178,6 +178,49 @@ struct EpiStore {
 };
 
 // ---------------------------------------------------------------------------
+// Split-K accumulation of a weight gradient: out += scale * acc with red.global.add (fire-and-forget, 16 bytes per
+// instruction) into an output the launcher has zeroed.  With exactly two splits the sum is order-independent.
+// ---------------------------------------------------------------------------
+struct EpiRedAdd {
+  struct Params {
+    float* out;
+    int64_t ld;
+    float scale;  // 0 means 1
+  };
+  struct State {
+    float* dst;
+  };
+  static constexpr int SMEM_BYTES = 0;
+  __device__ static void begin(const Params& p, State& st, int row, int, int, const GemmDims& d, uint8_t*) {
+    st.dst = row < d.M ? p.out + static_cast<int64_t>(row) * p.ld : nullptr;
+  }
+  template <bool FULL>
+  __device__ static void chunk(const Params& p, State& st, int row, int col0, float (&v)[32], const GemmDims& d,
+                               uint8_t*) {
+    if (row >= d.M) return;
+    const int valid = FULL ? 32 : d.N - col0;
+    if (valid <= 0) return;
+    if (p.scale != 0.0f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+    }
+    float* dst = st.dst + col0;
+    if (FULL && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                     "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) atomicAdd(dst + j, v[j]);
+    }
+  }
+  __device__ static void end(const Params&, State&, int, int, int, const GemmDims&, uint8_t*) {}
+};
+
+// ---------------------------------------------------------------------------
 // Weight-gradient store fused with the reduce-scatter of the data-parallel exchange: the rows of dW are
 // partitioned over the ranks, and every rank's epilogue writes each tile straight into the OWNER's inbox over
 // NVLink peer memory (plain posted stores: 128 contiguous bytes per thread and chunk) -- slot [source rank] of that

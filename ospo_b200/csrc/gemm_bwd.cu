@@ -13,6 +13,24 @@ using CfgD2 = GemmCfg<2, 256, false, true>;
 using CfgW1 = GemmCfg<1, 256, true, true>;
 using CfgW2 = GemmCfg<2, 256, true, true>;
 
+// Split-K for a weight-gradient GEMM whose tiles leave the last wave of the persistent grid mostly empty.  dW1 of the
+// 7B head is 4096 x 4096 = 256 tiles of 256 x 256 for 74 CTA pairs: 3.46 waves, the fourth 46 % full (measured: 1.09
+// PFLOP/s where dW2, 13.8 waves, runs at 1.38).  As 512 half-length work items it is 6.92 waves of half the length,
+// 7 x 0.5 = 3.5 instead of 4.  Both halves of a tile are ADDED into a zeroed output with red.global.add: two addends
+// onto +0 give the same bits in either order (0 + a is exact and IEEE addition commutes), so the gradient stays
+// bit-reproducible.  Taken only when it saves more than 4 % of the wave count and K is long enough to halve.
+// (Measured and rejected for the same purpose: 256 x 128 tiles, 3.3 - 3.5 ms against 2.27 ms --
+// profiles/r02_ab_wgrad_bn128_rejected_*.json.)
+static int pick_wgrad_splits(const LaunchCtx& c, int out_dim, int in_dim, int rows) {
+  if (c.wgrad_splitk == 1 || c.wgrad_splitk == 2) return c.wgrad_splitk;
+  if (rows < 2 * 64 * 256) return 1;
+  const int cg = c.cta_group == 2 ? 2 : 1;
+  const int64_t clusters = c.num_sms / cg > 0 ? c.num_sms / cg : 1;
+  const int64_t tiles = static_cast<int64_t>((out_dim + 128 * cg - 1) / (128 * cg)) * ((in_dim + 255) / 256);
+  const int64_t cost1 = 2 * ((tiles + clusters - 1) / clusters), cost2 = (2 * tiles + clusters - 1) / clusters;
+  return (cost2 * 104 < cost1 * 100) ? 2 : 1;
+}
+
 int launch_dact_gelu_bwd(const LaunchCtx& c, const __nv_bfloat16* g, const __nv_bfloat16* w2, const __nv_bfloat16* pre,
                          const float* row_w, __nv_bfloat16* dpre, __nv_bfloat16* act_w, int rows, int E, int V) {
   using Epi = EpiDactScale;
@@ -45,6 +63,17 @@ int launch_wgrad(const LaunchCtx& c, const __nv_bfloat16* dy, const __nv_bfloat1
   sb.seg_off = xl.seg_off;
   sb.segments = xl.segments;
   // D[out, in] = dY^T[out, rows] * X[rows, in]:  M = out_dim, N = in_dim, K = rows
+  const int splits = pick_wgrad_splits(c, out_dim, in_dim, rows);
+  if (splits == 2) {
+    using EpiAdd = EpiRedAdd;
+    if (cudaMemsetAsync(dw, 0, static_cast<size_t>(out_dim) * in_dim * sizeof(float), c.stream) != cudaSuccess) return -4;
+    EpiAdd::Params pa{dw, in_dim, scale};
+    if (c.cta_group == 2)
+      return launch_gemm<CfgW2, EpiAdd>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, pa, c.num_sms, c.stream,
+                                        2, false, SegOperand(), sb, 0, c.sync_ctr, c.a_evict, c.b_evict);
+    return launch_gemm<CfgW1, EpiAdd>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, pa, c.num_sms, c.stream,
+                                      2, false, SegOperand(), sb, 0, c.sync_ctr, c.a_evict, c.b_evict);
+  }
   if (c.cta_group == 2)
     return launch_gemm<CfgW2, Epi>(dy, out_dim, x, in_dim, out_dim, in_dim, rows, c.group_m, p, c.num_sms, c.stream, 1,
                                    false, SegOperand(), sb, 0, c.sync_ctr, c.a_evict, c.b_evict);

@@ -19,6 +19,7 @@ struct LaunchCtx {
   bool pdl;       // launch with programmatic stream serialization (decode chain)
   bool trace = false;  // timeline stamps on (ospo_head_trace); off = the stamps compile to a parameter test
   unsigned long long* trace_buf = nullptr;
+  int wgrad_splitk = 0;  // k-splits of the weight-gradient GEMMs: 0 = chosen per shape (gemm_bwd.cu), 1 / 2 = forced
   int a_evict = 0, b_evict = 0;  // L2 eviction hint of the A / B operand loads: 0 normal, 1 evict-first, 2 evict-last
   uint32_t* sync_ctr = nullptr;  // wave lock-step counter for the persistent training GEMMs (null = free-running)  // the installed timeline buffer (merged decode kernel stamps through it)
 };

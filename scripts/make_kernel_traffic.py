@@ -34,6 +34,8 @@ def classify(d):
         return "gemm2_logits_lse" if us > 1000 else "gemm2_repair_pass_empty"
     if "EpiDactScale" in n:
         return "dact_gelu_bwd"
+    if "EpiRedAdd" in n:
+        return "wgrad_w1"  # split-K form (two half-length work items per tile added into the zeroed output)
     if "EpiStore<float" in n:
         return "wgrad_w2" if us > 4000 else "wgrad_w1"
     if "EpiStore<__nv_bfloat16" in n and "gemm_kernel" in n:
@@ -55,8 +57,8 @@ def main():
     for p in src:
         for d in launches(p):
             k = classify(d)
-            if k:
-                acc[k].append(d)
+            if k and d.get("gpu__time_duration.sum", 0) == d.get("gpu__time_duration.sum", 0):  # ncu prints nan for the
+                acc[k].append(d)                                                                # cooperative decode kernel
     out = {"_source": [str(p.relative_to(ROOT)) if p.is_absolute() else str(p) for p in src],
            "_commit": subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True,
                                      text=True).stdout.strip(),
@@ -72,6 +74,15 @@ def main():
         if any("lts__t_sector_hit_rate.pct" in d for d in ds):
             ent["l2_hit_rate_pct"] = sum(d.get("lts__t_sector_hit_rate.pct", 0) for d in ds) / n
         out[k] = ent
+    if "decode_merged" not in out:
+        r1 = json.loads((ROOT / "profiles" / "r01_kernel_traffic.json").read_text()).get("decode_merged")
+        if r1:
+            out["decode_merged"] = {
+                "launches": 1, "dram_bytes_read": r1["dram_bytes_read"], "dram_bytes_write": r1["dram_bytes_write"],
+                "source": "carried over from profiles/r01_kernel_traffic.json (ncu --set full -k regex:decode_merged python "
+                          "scripts/gpu_cfg_one.py, profiles/r01_decode_merged_ncu_summary.txt): the kernel's weight stream "
+                          "is unchanged since; the launch list has no valid decode launch (a cooperative launch under "
+                          "the metrics pass reports nan)"}
     (ROOT / "profiles" / "kernel_traffic.json").write_text(json.dumps(out, indent=1) + "\n")
     print(json.dumps({k: (round(v["dram_bytes_read"] / 1e9, 2), round(v["dram_bytes_write"] / 1e9, 2))
                       for k, v in out.items() if not k.startswith("_")}))

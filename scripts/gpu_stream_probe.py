@@ -14,14 +14,14 @@ dev = torch.device("cuda:0")
 N = 32
 
 
-def bench(M, K, tag, variant=101):
-    A = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(2)]
+def bench(M, K, tag, variant=101, copies=2):
+    A = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(copies)]
     B = torch.randn(N, K, device=dev).to(torch.bfloat16)
     out = torch.empty(M, N, device=dev)
 
     def run():
         for i in range(32):
-            a = A[i & 1]
+            a = A[i % len(A)]
             lib.ospo_head_gemm_debug(variant, a.data_ptr(), a.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(),
                                      out.stride(0), M, N, K, torch.cuda.current_stream().cuda_stream)
 
@@ -49,3 +49,8 @@ for v in (300, 301, 302, 303, 101, 106):
     bench(16384, 4096, "W2", v)
 for v in (300, 301, 302, 303):
     bench(4096, 4096, "W1", v)
+# the same matrix every launch: 33.5 MB stay in L2 -- what one SM can take in from L2 (301: 32 CTAs x 128 rows ... 302 / 303: all SMs)
+for v in (301, 302, 303):
+    bench(4096, 4096, "W1 L2-resident", v, copies=1)
+for v in (301, 302, 303):
+    bench(16384, 2048, "W2(1B) L2-resident", v, copies=1)

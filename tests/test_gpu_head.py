@@ -565,6 +565,46 @@ def test_backward_twice_and_bias_gradients_are_bit_reproducible():
         assert torch.equal(a, p.grad)
 
 
+@pytest.mark.parametrize("H,E,V,T", [(256, 384, 4096, 128), (200, 328, 1000, 37)])
+def test_split_k_weight_gradients_are_bit_reproducible_and_match_unsplit(H, E, V, T):
+    """dW as two half-length split-K work items per tile added into the zeroed output (EpiRedAdd, gemm_bwd.cu; chosen
+    automatically for dW1 of the 7B head at full batch): two addends onto +0 give the same bits in either order, so
+    repeated backwards are bit-identical; against the unsplit GEMM only the summation order differs.  The second shape
+    has no dimension that is a multiple of a tile (scalar-atomic edge path, K = 296 rows = 3 + 2 k-blocks)."""
+    from ospo_b200 import _abi
+
+    dev = _cuda()
+    lib = _abi.load()
+    B, L = 4, 2
+    hp = dict(beta=10.0, gamma_beta_ratio=0.5, loss_type="sigmoid")
+    head_b = O.make_head(H, E, V, seed=73, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=74, dtype=torch.bfloat16)
+    hidden, labels = torch.cat([hc, hr]).to(dev), torch.cat([lc, lr]).to(dev)
+    fh = _fused_from(head_b, dev, dtype=torch.float32)
+
+    def grads():
+        fh.zero_grad(set_to_none=True)
+        x = hidden.clone().requires_grad_(True)
+        fh.simpo(x, labels, image_span=(L - 1, L - 1 + T) if T % 64 == 0 else None, **hp).loss.backward()
+        torch.cuda.synchronize()
+        return [x.grad.clone()] + [p.grad.clone() for p in fh.parameters()]
+
+    try:
+        assert lib.ospo_head_set_wgrad_splitk(1) == 1
+        ref = grads()
+        assert lib.ospo_head_set_wgrad_splitk(2) == 2
+        a, b = grads(), grads()
+    finally:
+        lib.ospo_head_set_wgrad_splitk(0)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    for u, r in zip(a, ref):
+        assert _rel_fro(u, r) < 1e-5
+    names = [n for n, _ in fh.named_parameters()]
+    changed = [n for n, u, r in zip(["x"] + names, a, ref) if not torch.equal(u, r)]
+    assert all("weight" in n for n in changed), changed     # dX and the bias gradients do not go through the split
+
+
 def test_logps_autograd_path_and_ragged_sequences():
     """get_batch_logps replacement with per-sequence different numbers of unmasked tokens + empty head grads."""
     dev = _cuda()

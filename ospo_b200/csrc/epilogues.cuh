@@ -555,8 +555,11 @@ struct EpiLogitsExp {
     st.m = fmaxf(st.m, cmax);
     st.s += acc0 + acc1;
     st.sum += ls0 + ls1;
+    // (in a partial N tile `valid` counts the columns up to the matrix edge, which can be more than this chunk's 32: a
+    //  label in a LATER chunk must not count as a hit here -- with the label in the other column half of the tile, two
+    //  warps would both store tgt[row], one of them the 0 it started with)
     const int rel = st.label - col0;
-    if (rel >= 0 && rel < valid) {
+    if (rel >= 0 && rel < (valid < 32 ? valid : 32)) {
       st.hit = true;
 #pragma unroll
       for (int j = 0; j < 32; ++j)

@@ -97,6 +97,90 @@ stream_probe_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* bas
   }
 }
 
+// The same stream with the decode GEMM's second operand beside it (variants 304 / 305): every stage also takes a
+// {64 cols x 32 rows} box of a [32, K] activation matrix -- 304: ONE matrix shared by all CTAs (what the decode
+// kernels do), 305: a private copy per CTA.  No MMA: what do 128 SMs asking for the same 4 KB at the same time cost?
+constexpr int kProbeBBytes = 32 * 64 * 2;
+template <bool PRIVATE_B>
+__global__ void __launch_bounds__(96, 1)
+stream_probe_b_kernel(const __grid_constant__ CUtensorMap tmap_b, const uint8_t* base, int num_kb, long long chunks,
+                      float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr int kStage = kProbeChunk + kProbeBBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kProbeStages * kStage);
+  uint64_t* empty_bar = full_bar + kProbeStages;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kProbeStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const long long G = gridDim.x, b = blockIdx.x;
+  const long long lo = chunks * b / G, hi = chunks * (b + 1) / G;
+  const long long n = hi - lo;
+  if (warp == 0) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long i = 0; i < n; ++i) {
+        mbar_wait(&empty_bar[s], ph ^ 1u, 21);
+        mbar_arrive_expect_tx(&full_bar[s], kStage);
+        bulk_load_1d(smem + s * kStage, base + (lo + i) * kProbeChunk, kProbeChunk, &full_bar[s]);
+        if (++s == kProbeStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 2) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long i = 0; i < n; ++i) {
+        mbar_wait(&empty_bar[s], ph ^ 1u, 23);
+        const int kb = static_cast<int>((lo + i) % num_kb);
+        tma_load_2d(smem + s * kStage + kProbeChunk, &tmap_b, &full_bar[s], kb * 64,
+                    PRIVATE_B ? static_cast<int>(b) * 32 : 0, kEvictLast);
+        if (++s == kProbeStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long i = 0; i < n; ++i) {
+        mbar_wait(&full_bar[s], ph, 22);
+        mbar_arrive(&empty_bar[s]);
+        if (++s == kProbeStages) { s = 0; ph ^= 1u; }
+      }
+      if (blockIdx.x == 0) out[0] = 1.0f;
+    }
+  }
+}
+
+// b: [32 * (PRIVATE_B ? ctas : 1), K] bf16
+template <bool PRIVATE_B>
+static int run_probe_b(const LaunchCtx& c, const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64_t ldb,
+                       float* out, int M, int K, int ctas) {
+  if ((M % 128) != 0 || (K % 64) != 0 || lda != K || ldb != K) return -100;
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_2d(&tm, b, PRIVATE_B ? 32 * ctas : 32, K, ldb, 32);
+  if (rc != 0) return rc;
+  auto kern = stream_probe_b_kernel<PRIVATE_B>;
+  const int smem = 1024 + kProbeStages * (kProbeChunk + kProbeBBytes) + 256;
+  static std::atomic<uint64_t> attr_set{0};  // per device ordinal
+  int attr_dev = 0;
+  if (func_attrs_needed(attr_set, &attr_dev)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -3;
+    func_attrs_mark(attr_set, attr_dev);
+  }
+  const long long chunks = static_cast<long long>(M) * K * 2 / kProbeChunk;
+  kern<<<ctas, 96, smem, c.stream>>>(tm, reinterpret_cast<const uint8_t*>(a), K / 64, chunks, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
 template <int MODE>
 static int run_probe(const LaunchCtx& c, const __nv_bfloat16* a, int64_t lda, float* out, int M, int K, int ctas) {
   if ((M % 128) != 0 || (K % 64) != 0 || lda != K) return -100;
@@ -138,6 +222,8 @@ int launch_gemm_debug(const LaunchCtx& c, int variant, const __nv_bfloat16* a, i
     case 301: return run_probe<1>(c, a, lda, out, M, K, M / 128);
     case 302: return run_probe<1>(c, a, lda, out, M, K, c.num_sms);
     case 303: return run_probe<2>(c, a, lda, out, M, K, c.num_sms);
+    case 304: return run_probe_b<false>(c, a, lda, b, ldb, out, M, K, M / 128);
+    case 305: return run_probe_b<true>(c, a, lda, b, ldb, out, M, K, M / 128);
     default: return -100;
   }
 }

@@ -16,7 +16,7 @@ N = 32
 
 def bench(M, K, tag, variant=101, copies=2):
     A = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(copies)]
-    B = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    B = torch.randn(N * (M // 128 if variant == 305 else 1), K, device=dev).to(torch.bfloat16)
     out = torch.empty(M, N, device=dev)
 
     def run():
@@ -45,8 +45,10 @@ def bench(M, K, tag, variant=101, copies=2):
     print(f"STREAM {tag} v{variant}: M={M} K={K} us={us:.2f} GB/s={M * K * 2 / us / 1e3:.0f}", flush=True)
 
 
-for v in (300, 301, 302, 303, 101, 106):
+for v in (300, 301, 302, 303, 304, 305, 101, 106):
     bench(16384, 4096, "W2", v)
+for v in (301, 304, 305):
+    bench(16384, 2048, "W2(1B)", v)
 for v in (300, 301, 302, 303):
     bench(4096, 4096, "W1", v)
 # the same matrix every launch: 33.5 MB stay in L2 -- what one SM can take in from L2 (301: 32 CTAs x 128 rows ... 302 / 303: all SMs)

@@ -137,6 +137,35 @@ def test_simpo_ragged_shapes_stay_in_bounds():
     assert torch.isfinite(fh.vision_head.weight.grad.float()).all()
 
 
+def test_target_gather_in_a_partial_vocab_tile():
+    """V that is not a multiple of the 256-column tile, every label in the LAST (partial) tile and most of them in its
+    second 128-column half: the target logit of a row is gathered by exactly one warp.  (Before the fix the hit test of
+    a partial tile compared against the columns left up to the matrix edge instead of the chunk's 32, so the warp of
+    the first half also stored tgt[row] -- its initial 0 -- and the two stores raced: per-token log-probs off by the
+    whole target logit, run-to-run different.)"""
+    dev = _cuda()
+    H, E, V, B, T, L = 200, 328, 1000, 4, 37, 2
+    head_b = O.make_head(H, E, V, seed=61, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=62, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(63)
+    lc[:, L:] = torch.randint(768, V, (B, T), generator=g)
+    lr[:, L:] = torch.randint(896, V, (B, T), generator=g)
+    hp = dict(beta=5.0, gamma_beta_ratio=0.5, loss_type="sigmoid")
+    ref = O.simpo_step(head_b, hc, hr, lc, lr, **hp)
+    ref_tok = ref["per_token_logps"].detach()[ref["loss_mask"]].float().numpy()
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16)
+    hidden, labels = torch.cat([hc, hr]).to(dev), torch.cat([lc, lr]).to(dev)
+    first = None
+    for _ in range(5):
+        out = fh.simpo(hidden, labels, **hp)
+        torch.cuda.synchronize()
+        tok = out.per_token_logps.cpu().numpy()
+        np.testing.assert_allclose(tok, ref_tok, rtol=1e-2, atol=3e-2)
+        if first is None:
+            first = tok
+        assert np.array_equal(tok, first)
+
+
 def test_abi_rejects_bad_arguments():
     """error behaviour of the C ABI on a live device: misalignment, short workspace, bad shapes, NULL pointers"""
     import ctypes as C

@@ -8,6 +8,8 @@ Tolerances: bf16 kernels vs fp32 reference -> rtol 1e-2 on loss / log-probs (BAS
 gradients -> relative Frobenius error <= 2e-2 vs fp32 reference and <= 1e-2 vs the bf16 oracle;
 sampled / greedy ids bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -164,6 +166,56 @@ def test_target_gather_in_a_partial_vocab_tile():
         if first is None:
             first = tok
         assert np.array_equal(tok, first)
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("OSPO_FUZZ_SEEDS", "8")))))   # more seeds: a sweep
+def test_simpo_random_ragged_shapes_are_reproducible_and_match_the_oracle(seed):
+    """shape fuzz: H, E, V any multiples of 8, any number of image tokens, with and without the SFT term / hinge loss /
+    image span -- two fresh forward + backward passes give the same bits everywhere (no racing stores, no uninitialised
+    reads in partial tiles) and the values match the bf16 oracle"""
+    dev = _cuda()
+    rng = np.random.default_rng(1000 + seed)
+    H, E = int(rng.integers(9, 80)) * 8, int(rng.integers(9, 80)) * 8
+    V = int(rng.integers(40, 400)) * 8
+    B, T, L = int(rng.integers(1, 5)), int(rng.choice([17, 37, 64, 100, 128, 150])), int(rng.integers(1, 4))
+    hp = dict(beta=float(rng.choice([2.0, 5.0, 10.0])), gamma_beta_ratio=0.5,
+              loss_type=str(rng.choice(["sigmoid", "hinge"])), sft_weight=float(rng.choice([0.0, 0.3])),
+              label_smoothing=float(rng.choice([0.0, 0.1])))
+    head_b = O.make_head(H, E, V, seed=200 + seed, w2_gain=3.0).to(torch.bfloat16)
+    hc, hr, lc, lr = O.synthetic_simpo_batch(B, T, L, H, V, seed=300 + seed, dtype=torch.bfloat16)
+    if seed % 2:   # crowd the labels into the last vocab tile
+        g = torch.Generator().manual_seed(seed)
+        lc[:, L:] = torch.randint(max(0, V - 200), V, (B, T), generator=g)
+        lr[:, L:] = torch.randint(max(0, V - 120), V, (B, T), generator=g)
+    ref = O.simpo_step(head_b, hc, hr, lc, lr, backward=True, **hp)
+    fh = _fused_from(head_b, dev, dtype=torch.float32)
+    hidden, labels = torch.cat([hc, hr]).to(dev), torch.cat([lc, lr]).to(dev)
+    span = (L - 1, L - 1 + T) if (T % 64 == 0 and seed % 3 != 0) else None
+    runs = []
+    for _ in range(2):
+        fh.zero_grad(set_to_none=True)
+        x = hidden.clone().requires_grad_(True)
+        out = fh.simpo(x, labels, image_span=span, **hp)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        runs.append([out.loss.detach().clone(), out.per_token_logps.clone(), out.chosen_logps.clone(),
+                     out.rejected_logps.clone(), x.grad.clone()] + [p.grad.clone() for _, p in fh.named_parameters()])
+    tag = f"H{H} E{E} V{V} B{B} T{T} L{L} span={span} {hp}"
+    for i, (a, b) in enumerate(zip(*runs)):
+        assert torch.equal(a, b), (tag, i)
+    loss, tok, clp, rlp, dx = runs[0][:5]
+    grads = dict(zip([n for n, _ in fh.named_parameters()], runs[0][5:]))
+    np.testing.assert_allclose(tok.cpu().numpy(), ref["per_token_logps"].detach()[ref["loss_mask"]].float().numpy(),
+                               rtol=1e-2, atol=3e-2, err_msg=tag)
+    np.testing.assert_allclose(clp.cpu().numpy(), ref["chosen_logps"].detach().float().numpy(), rtol=1e-2, err_msg=tag)
+    np.testing.assert_allclose(rlp.cpu().numpy(), ref["rejected_logps"].detach().float().numpy(), rtol=1e-2, err_msg=tag)
+    assert abs(float(loss) - float(ref["loss"])) < 1e-2 * abs(float(ref["loss"])) + hp["beta"] * 2 * 2e-2, tag
+    if float(ref["dW2"].float().norm()) > 0:   # hinge with every margin satisfied has zero gradients
+        assert _rel_fro(dx.float(), ref["dx"].float()) < 3e-2, tag
+        assert _rel_fro(grads["vision_head.weight"], ref["dW2"].float()) < 3e-2, tag
+        assert _rel_fro(grads["output_mlp_projector.weight"], ref["dW1"].float()) < 3e-2, tag
+        assert _rel_fro(grads["vision_head.bias"], ref["db2"].float()) < 3e-2, tag
+        assert _rel_fro(grads["output_mlp_projector.bias"], ref["db1"].float()) < 3e-2, tag
 
 
 def test_abi_rejects_bad_arguments():

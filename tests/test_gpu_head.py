@@ -718,6 +718,59 @@ def test_logps_autograd_path_and_ragged_sequences():
         assert _rel_fro(fh.output_mlp_projector.bias.grad.float(), head_b.output_mlp_projector.bias.grad.float()) < 2e-2
 
 
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("OSPO_FUZZ_SEEDS", "6")))))
+def test_logps_and_forward_random_shapes_and_masks(seed):
+    """get_batch_logps replacement and the plain forward on random shapes with random masks (text prefixes of different
+    lengths, holes, a fully masked sequence): values and gradients against the bf16 torch head, twice the same bits"""
+    dev = _cuda()
+    rng = np.random.default_rng(3000 + seed)
+    H, E, V = int(rng.integers(8, 70)) * 8, int(rng.integers(8, 70)) * 8, int(rng.integers(30, 300)) * 8
+    S, Lmax = int(rng.integers(2, 7)), int(rng.integers(8, 90))
+    avg = bool(seed % 2)
+    head_b = O.make_head(H, E, V, seed=600 + seed, w2_gain=2.0).to(torch.bfloat16)
+    g = torch.Generator().manual_seed(700 + seed)
+    hb = torch.randn(S, Lmax, H, generator=g).to(torch.bfloat16)
+    labels = torch.randint(0, V, (S, Lmax), generator=g)
+    for s_ in range(S):
+        labels[s_, :int(rng.integers(1, Lmax - 2))] = -100
+        if rng.random() < 0.5:
+            a = int(rng.integers(1, Lmax - 1))
+            labels[s_, a:a + int(rng.integers(1, 5))] = -100
+    if seed % 3 == 0 and not avg:
+        labels[S - 1, :] = -100            # nothing to predict in the last sequence: log-prob sum 0, no gradient
+    tag = f"H{H} E{E} V{V} S{S} L{Lmax} avg={avg}"
+    ref_in = hb.clone().requires_grad_(True)
+    head_b.zero_grad()
+    ref = O.get_batch_logps(head_b(ref_in), labels, average_log_prob=avg)
+    wts = torch.linspace(0.5, 1.5, S)
+    (ref * wts).sum().backward()
+    fh = _fused_from(head_b, dev, dtype=torch.float32)
+    runs = []
+    for _ in range(2):
+        fh.zero_grad(set_to_none=True)
+        x = hb.to(dev).requires_grad_(True)
+        got = fh.logps(x, labels.to(dev), average_log_prob=avg)
+        (got * wts.to(dev)).sum().backward()
+        torch.cuda.synchronize()
+        runs.append([got.detach().clone(), x.grad.clone()] + [p.grad.clone() for _, p in fh.named_parameters()])
+    for i, (a, b) in enumerate(zip(*runs)):
+        assert torch.equal(a, b), (tag, i)
+    got, dx = runs[0][:2]
+    grads = dict(zip([n for n, _ in fh.named_parameters()], runs[0][2:]))
+    np.testing.assert_allclose(got.cpu().numpy(), ref.detach().float().numpy(), rtol=1e-2, atol=1e-2 if avg else 0.3,
+                               err_msg=tag)
+    assert _rel_fro(dx.float(), ref_in.grad.float()) < 3e-2, tag
+    assert _rel_fro(grads["vision_head.weight"], head_b.vision_head.weight.grad.float()) < 3e-2, tag
+    assert _rel_fro(grads["output_mlp_projector.weight"], head_b.output_mlp_projector.weight.grad.float()) < 3e-2, tag
+    assert _rel_fro(grads["vision_head.bias"], head_b.vision_head.bias.grad.float()) < 3e-2, tag
+    assert _rel_fro(grads["output_mlp_projector.bias"], head_b.output_mlp_projector.bias.grad.float()) < 3e-2, tag
+    with torch.no_grad():
+        lg = fh.to(torch.bfloat16)(hb.to(dev))
+        torch.cuda.synchronize()
+        ref_lg = head_b(hb).float()
+    torch.testing.assert_close(lg.float().cpu(), ref_lg, rtol=2e-2, atol=2e-2 * float(ref_lg.abs().max()), msg=tag)
+
+
 def test_row_segmented_zero_copy_path_equals_gather_path():
     """T % 64 == 0 + bf16 contiguous hidden states: the kernels read [S, L+T, H] in place through a 3-D TMA view and
     write dX into it; results must equal the gathered-rows path bit for bit, masked rows must get zero gradient."""
@@ -1086,6 +1139,38 @@ def test_cfg_sample_fused_step_extremes(gain, w, T):
     oid, *_ = O.cfg_sample_det(lg.cpu(), w, T, u, merge_mode=0)
     ogid, *_ = O.cfg_sample_det(lg.cpu(), w, T, None, merge_mode=0, greedy=True)
     assert torch.equal(ids.cpu(), oid) and torch.equal(ids2.cpu(), oid) and torch.equal(gids.cpu(), ogid)
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("OSPO_FUZZ_SEEDS", "8")))))
+def test_cfg_sample_random_shapes_match_the_oracle(seed):
+    """decode-step fuzz: H, E any multiples of 8, 1 - 16 pairs, cfg_weight / temperature on and off the bf16 fast paths:
+    logits within bf16 tolerance of the bf16 torch head, ids (sampled, greedy, with and without the logits dump, twice)
+    bit-exact against the oracle on the step's own logits"""
+    dev = _cuda()
+    rng = np.random.default_rng(2000 + seed)
+    H, E, V = int(rng.integers(8, 160)) * 8, int(rng.integers(8, 160)) * 8, 16384
+    P = int(rng.integers(1, 17))
+    w = float(rng.choice([5.0, 3.0, 7.5, 3.3, 1.0]))
+    T = float(rng.choice([1.0, 1.0, 0.7, 1.3]))
+    head_b = O.make_head(H, E, V, seed=400 + seed, w2_gain=float(rng.choice([1.0, 4.0, 12.0]))).to(torch.bfloat16)
+    fh = _fused_from(head_b, dev, dtype=torch.bfloat16, requires_grad=False)
+    g = torch.Generator().manual_seed(500 + seed)
+    h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16)
+    u = torch.rand(P, generator=g)
+    tag = f"H{H} E{E} P{P} w{w} T{T}"
+    ids, lg = fh.cfg_sample(h.to(dev), w, T, uniforms=u.to(dev), return_logits=True)
+    ids2 = fh.cfg_sample(h.to(dev), w, T, uniforms=u.to(dev))
+    ids3 = fh.cfg_sample(h.to(dev), w, T, uniforms=u.to(dev))
+    gids = fh.cfg_sample(h.to(dev), w, T, greedy=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_lg = head_b(h).float()
+    torch.testing.assert_close(lg.float().cpu(), ref_lg, rtol=2e-2, atol=2e-2 * float(ref_lg.abs().max()), msg=tag)
+    oid, *_ = O.cfg_sample_det(lg.cpu(), w, T, u, merge_mode=0)
+    ogid, *_ = O.cfg_sample_det(lg.cpu(), w, T, None, merge_mode=0, greedy=True)
+    assert torch.equal(ids.cpu(), oid), tag
+    assert torch.equal(ids2.cpu(), oid) and torch.equal(ids3.cpu(), oid), tag
+    assert torch.equal(gids.cpu(), ogid), tag
 
 
 def test_cfg_sample_more_than_16_pairs_falls_back():

@@ -1487,6 +1487,48 @@ def test_gen_img_embeds_7b_shape_and_patch_model():
 
 
 
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("OSPO_FUZZ_SEEDS", "6")))))
+def test_gen_img_embeds_and_decode_chain_random_shapes(seed):
+    """N1 fuzz: gen_aligner widths D that are any multiple of 8, any number of ids / pairs: the drop-in call against
+    the torch modules, and sample -> embed -> aligner as one chain (streamed and memoised) against the two separate
+    calls -- same ids, same rows, twice the same bits"""
+    from ospo_b200 import FusedGenImgEmbeds
+
+    dev = _cuda()
+    rng = np.random.default_rng(4000 + seed)
+    D = int(rng.integers(8, 140)) * 8
+    CB, P = 16384, int(rng.integers(1, 17))
+    torch.manual_seed(800 + seed)
+    gen_embed = torch.nn.Embedding(CB, 8).to(torch.bfloat16).to(dev)
+    aligner = O.GenAligner(8, D).to(torch.bfloat16).to(dev)
+    fe = FusedGenImgEmbeds(gen_embed, aligner)
+    g = torch.Generator().manual_seed(900 + seed)
+    ids = torch.randint(0, CB, (int(rng.integers(1, 90)),), generator=g).to(dev)
+    tag = f"D{D} P{P} n{ids.numel()}"
+    with torch.no_grad():
+        got, got2 = fe(ids), fe(ids)
+        ref = O.prepare_gen_img_embeds(gen_embed, aligner, ids)
+    torch.cuda.synchronize()
+    assert torch.equal(got, got2), tag
+    torch.testing.assert_close(got.float(), ref.float(), rtol=2e-2, atol=2e-2, msg=tag)
+    # the chain behind the sampler (the head's hidden size must equal D for the dependent loop; any H works here)
+    H, E = int(rng.integers(8, 100)) * 8, int(rng.integers(8, 100)) * 8
+    head = O.make_head(H, E, CB, seed=950 + seed, w2_gain=3.0).to(torch.bfloat16)
+    fh = _fused_from(head, dev, dtype=torch.bfloat16, requires_grad=False)
+    h = torch.randn(2 * P, H, generator=g).to(torch.bfloat16).to(dev)
+    u = torch.rand(P, generator=g).to(dev)
+    ids_plain = fh.cfg_sample(h, 5.0, 1.0, uniforms=u)
+    ids_a, emb_a = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, next_embeds=fe)
+    ids_a2, emb_a2 = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, next_embeds=fe)
+    fe.build_table()
+    ids_b, emb_b = fh.cfg_sample(h, 5.0, 1.0, uniforms=u, next_embeds=fe)
+    torch.cuda.synchronize()
+    assert torch.equal(ids_a, ids_plain) and torch.equal(ids_b, ids_plain) and torch.equal(ids_a2, ids_plain), tag
+    assert torch.equal(emb_a, emb_a2) and torch.equal(emb_a, emb_b), tag
+    fe.use_table = False
+    assert torch.equal(emb_a, fe.from_sampled(ids_plain)), tag
+
+
 def test_gen_img_embeds_memo_table_is_bit_identical():
     """FusedGenImgEmbeds.build_table(): table[id] == gen_aligner(gen_embed(id)) bit for bit (same kernels), the table
     form of the call and of the fused decode chain returns the same rows / ids as the streamed form, and a parameter

@@ -586,11 +586,16 @@ def main():
     torch.cuda.reset_peak_memory_stats(dev)
     t_wall0 = time.time()
     ev0.record()
+    marks = []   # one event per step: the spread of the K steps is reported beside their total (step_ms)
     for _ in range(args.steps):
         loss, _ = step(hidden, labels)
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     ev1.record()
     sync_all()
     t_wall1 = time.time()
+    per_step = sorted(a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks))
+    step_ms = {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]}
     launches = int(_abi.load().ospo_head_launch_count() - launches0)
     mem_peak = torch.cuda.max_memory_allocated(dev)
     prof = _abi.profile_read()
@@ -813,7 +818,7 @@ def main():
                        "l2": "inputs larger than L2 (604 MB hidden states + 2.4 GB bf16 logits spill per step)",
                        "cta_group": _abi.load().ospo_head_set_cta_group(0), "loss": loss_val},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
-            "cpu_baseline": cpu, "frozen_head": frozen, "cfg": cfg, "clip_adamw": opt_res, "dp_check": dp,
+            "step_ms": step_ms, "cpu_baseline": cpu, "frozen_head": frozen, "cfg": cfg, "clip_adamw": opt_res, "dp_check": dp,
             "memory": {"peak_bytes": mem_peak, "resident_before_step_bytes": mem_resident,
                        "step_transient_bytes": mem_peak - mem_resident,
                        "note": "torch.cuda.max_memory_allocated over the timed steps; resident = weights, inputs, "

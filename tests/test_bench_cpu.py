@@ -54,7 +54,7 @@ def test_product_arm_refuses_to_run_without_a_gpu():
 
 
 def test_committed_bench_line_carries_the_contract():
-    line = (ROOT / "profiles" / "r02_bench_final_n1.json").read_text().strip().splitlines()[-1]
+    line = (ROOT / "profiles" / "r02_bench_final6_n1.json").read_text().strip().splitlines()[-1]
     d = json.loads(line)
     for k in CONTRACT_KEYS + ("clocks", "roofline"):
         assert k in d, k
@@ -80,10 +80,19 @@ def test_committed_bench_line_carries_the_contract():
     assert dep["us_per_step_dependent"] > d["cfg"]["us_per_step"]
     assert d["cfg"]["dependent_chain_embed_table"]["us_per_step_dependent"] < dep["us_per_step_dependent"]
     assert d["cpu_baseline"]["config1"]["value"] > 0
+    # the K timed steps one by one: their total is the metric, their spread shows whether a step was an outlier
+    sm = d["step_ms"]
+    assert sm["min"] <= sm["median"] <= sm["max"] and sm["max"] < 1.1 * sm["min"]
+    assert sm["min"] <= d["ms_per_step"] <= sm["max"]
+    # north_star's literal "CFG merge+sample at >= 70 % of HBM bandwidth": the fused decode step and the stand-alone
+    # sampler on supplied logits
+    assert dec["frac"] >= 0.70 and d["cfg"]["merge_sample_only"]["frac_of_hbm_peak"] >= 0.70
+    assert d["roofline"]["step_frac"] >= 0.60
 
 
 def test_committed_multi_gpu_lines_carry_a_passed_dp_check():
-    for name in ("r02_bench_n2.json", "r02_bench_n8_nccl.json", "r02_bench_n8_p2p2.json"):
+    for name in ("r02_bench_n2.json", "r02_bench_n2_final3.json", "r02_bench_n8_nccl.json", "r02_bench_n8_p2p2.json",
+                 "r02_bench_n8_final.json"):
         d = json.loads((ROOT / "profiles" / name).read_text().strip().splitlines()[-1])
         assert d["n_gpus"] > 1 and d["dp_check"]["status"] == "ok" and d["dp_check"]["ranks_bit_identical"] is True
         assert d["dp_check"]["world"] == d["n_gpus"]

@@ -920,6 +920,37 @@ def test_cfg_merge_sample_bit_exact_vs_oracle(golden_dir):
     assert torch.equal(gids.cpu(), torch.from_numpy(d["greedy"]))
 
 
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("OSPO_FUZZ_SEEDS", "6")))))
+def test_cfg_merge_sample_random_batches(seed):
+    """supplied-logits sampler fuzz: any number of steps and pairs (more pairs than blocks, fewer pairs than blocks,
+    odd counts), logits from nearly flat to far beyond the 2^-120 cut-off, both merge modes, temperature on / off:
+    merged logits, sampled ids and greedy ids bit-exact against the oracle, twice the same"""
+    from ospo_b200 import cfg_merge_sample
+
+    dev = _cuda()
+    rng = np.random.default_rng(5000 + seed)
+    steps, P, V = int(rng.integers(1, 6)), int(rng.integers(1, 21)), 16384
+    scale = float(rng.choice([0.2, 1.0, 3.0, 8.0, 30.0]))
+    w = float(rng.choice([5.0, 3.0, 7.5, 3.3]))
+    T = float(rng.choice([1.0, 1.0, 0.7, 1.3]))
+    mode_name, mode = [("bf16", 0), ("fp32", 1)][int(rng.integers(0, 2))]
+    g = torch.Generator().manual_seed(5100 + seed)
+    lg = (torch.randn(steps, 2 * P, V, generator=g) * scale + float(rng.choice([0.0, -40.0, 25.0]))).to(torch.bfloat16)
+    u = torch.rand(steps, P, generator=g)
+    tag = f"steps{steps} P{P} scale{scale} w{w} T{T} {mode_name}"
+    ids, merged = cfg_merge_sample(lg.to(dev), w, T, uniforms=u.to(dev), merge_mode=mode_name, return_merged=True)
+    ids2 = cfg_merge_sample(lg.to(dev), w, T, uniforms=u.to(dev), merge_mode=mode_name)
+    gids = cfg_merge_sample(lg.to(dev), w, T, greedy=True, merge_mode=mode_name)
+    torch.cuda.synchronize()
+    assert torch.equal(ids, ids2), tag
+    for s_ in range(steps):
+        oid, omerged, _, _ = O.cfg_sample_det(lg[s_], w, T, u[s_], merge_mode=mode)
+        ogid, *_ = O.cfg_sample_det(lg[s_], w, T, None, merge_mode=mode, greedy=True)
+        assert torch.equal(merged[s_].cpu(), omerged), (tag, s_)
+        assert torch.equal(ids[s_].cpu(), oid), (tag, s_)
+        assert torch.equal(gids[s_].cpu(), ogid), (tag, s_)
+
+
 def test_cfg_sample_fused_step_vs_oracle(golden_dir):
     """whole decode step (swap-AB GEMMs + merge + sample): logits vs the reference-generated golden within bf16
     tolerance; ids bit-exact against the oracle applied to the kernel's own dumped logits."""

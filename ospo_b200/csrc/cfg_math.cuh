@@ -107,28 +107,8 @@ __device__ __forceinline__ uint64_t exp_weight2p(uint64_t t, int koff0, int koff
   p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
   return f2_mul(p, f2_pack(f0, f1));
 }
-// The same weights when the caller has checked, for every code it passes, that the clamp is idle (|t log2 e| <= 1e4):
-// identical bits without the two clamps.
-__device__ __forceinline__ uint64_t exp_weight2p_inrange(uint64_t t, int koff) {
-  const uint64_t y = f2_mul(t, f2_pack(1.4426950408889634f, 1.4426950408889634f));
-  const uint64_t ym = f2_add_nofuse(y, f2_pack(kRintMagic, kRintMagic));
-  const uint64_t n = f2_add(ym, f2_pack(-kRintMagic, -kRintMagic));
-  float ym0, ym1;
-  f2_unpack(ym, ym0, ym1);
-  const float f0 = pow2_factor_i(__float_as_int(ym0) - koff);
-  const float f1 = pow2_factor_i(__float_as_int(ym1) - koff);
-  uint64_t r = f2_fma(n, f2_pack(-0.693145751953125f, -0.693145751953125f), t);
-  r = f2_fma(n, f2_pack(-1.42860682030941723212e-6f, -1.42860682030941723212e-6f), r);
-  uint64_t p = f2_pack(1.3888888888888889e-03f, 1.3888888888888889e-03f);
-  p = f2_fma(p, r, f2_pack(8.3333333333333332e-03f, 8.3333333333333332e-03f));
-  p = f2_fma(p, r, f2_pack(4.1666666666666664e-02f, 4.1666666666666664e-02f));
-  p = f2_fma(p, r, f2_pack(1.6666666666666666e-01f, 1.6666666666666666e-01f));
-  p = f2_fma(p, r, f2_pack(0.5f, 0.5f));
-  p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
-  p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
-  return f2_mul(p, f2_pack(f0, f1));
-}
-// The clamp-free form with the 2^-120 cut-off folded into the exponent construction: the polynomial is evaluated
+// For callers that have checked, for every code they pass, that the clamp is idle (|t log2 e| <= 1e4): the clamp-free
+// form, with the 2^-120 cut-off folded into the exponent construction: the polynomial is evaluated
 // with every coefficient times 64 (a power-of-two scaling commutes with each rounding of the Horner chain, so
 // P64(r) = 64 P(r) bit for bit) and the scale is 2^(n - kt - 6), whose bits are  max(n - kt + 121, 0) << 23:
 // for n - kt >= -120 that is the normal number 2^(n - kt - 6) and P64(r) 2^(n - kt - 6) = P(r) 2^(n - kt) exactly

@@ -162,15 +162,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 
 // ---------------------------------------------------------------------------
-// per-thread asynchronous copies global -> shared (16 bytes, kept in L1: neighbouring chunks share sectors)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// ---------------------------------------------------------------------------
 // device-wide flag words (grid barrier of the merged decode kernel)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {

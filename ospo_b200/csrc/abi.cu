@@ -471,6 +471,11 @@ int head_backward(const ospo_simpo_args* a, const Workspace& w, const float* sft
   // starts the all-reduce of the rest and runs 4.  dpre lives in the workspace: same buffer in every call.
   const int stage = a->bwd_stage == 0 ? 7 : a->bwd_stage;
   if (stage < 1 || stage > 7) return OSPO_ERR_UNSUPPORTED;
+  // A staged backward means a collective runs beside dW1 / dX.  There the split-K form of dW1 (gemm_bwd.cu) loses: its
+  // red.global.add traffic competes with the all-reduce of dW2 -- 2 GPUs, alternating runs on one box: dW1 2.25 - 2.41
+  // ms unsplit against 2.48 - 2.54 ms split, step 28.7 against 28.9 - 29.3 ms
+  // (profiles/r02_ab_n2_wgrad_splitk_*.json) -- so it is chosen only when the backward runs in one piece.
+  if (a->bwd_stage != 0 && c.wgrad_splitk == 0) c.wgrad_splitk = 1;
   const bool first = (stage & 1) != 0, second = (stage & 2) != 0, third = (stage & 4) != 0;
   if (!first && a->reserve_sms > 0) {
     // leave SMs to a collective kernel running beside the remaining GEMMs (even count: CTA pairs)

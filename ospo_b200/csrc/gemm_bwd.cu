@@ -18,7 +18,8 @@ using CfgW2 = GemmCfg<2, 256, true, true>;
 // PFLOP/s where dW2, 13.8 waves, runs at 1.38).  As 512 half-length work items it is 6.92 waves of half the length,
 // 7 x 0.5 = 3.5 instead of 4.  Both halves of a tile are ADDED into a zeroed output with red.global.add: two addends
 // onto +0 give the same bits in either order (0 + a is exact and IEEE addition commutes), so the gradient stays
-// bit-reproducible.  Taken only when it saves more than 4 % of the wave count and K is long enough to halve.
+// bit-reproducible (red.f32 flushes subnormal addends and sums to zero -- in either order).  Taken only when it saves
+// more than 4 % of the wave count and K is long enough to halve.
 // (Measured and rejected for the same purpose: 256 x 128 tiles, 3.3 - 3.5 ms against 2.27 ms --
 // profiles/r02_ab_wgrad_bn128_rejected_*.json.)
 static int pick_wgrad_splits(const LaunchCtx& c, int out_dim, int in_dim, int rows) {
